@@ -1,0 +1,148 @@
+"""Small circuits: the doc examples of the reference plus circomlib-style gadgets written from
+their public definitions (not in the reference tree; see SURVEY.md 'fixture gap')."""
+from __future__ import annotations
+
+from ..dsl import Function
+
+
+def Multiplier2(T):
+    """mkdocs/docs/getting-started/writing-circuits.md: c <== a*b."""
+    a = T.input("a")
+    b = T.input("b")
+    c = T.output("c")
+    T.bind(c, a * b)
+
+
+def MultiplierN(T, n):
+    """Chain of Multiplier2 components (component array, uniform): out = prod(in[i])."""
+    inp = T.input("in", (n,))
+    out = T.output("out")
+    comp = T.component("comp", (n - 1,))
+    i = T.var("i")
+    with T.for_(i, 0, i < n - 1):
+        T.new(comp[i], Multiplier2)
+    T.bind(comp[0].pin("a"), inp[0])
+    T.bind(comp[0].pin("b"), inp[1])
+    with T.for_(i, 0, i < n - 2):
+        T.bind(comp[i + 1].pin("a"), comp[i].pin("c"))
+        T.bind(comp[i + 1].pin("b"), inp[i + 2])
+    T.bind(out, comp[n - 2].pin("c"))
+
+
+def Num2Bits(T, n):
+    """circomlib bitify.circom Num2Bits."""
+    n_ = T.param("n", n)
+    inp = T.input("in")
+    out = T.output("out", (n,))
+    lc1 = T.var("lc1", init=0)
+    e2 = T.var("e2", init=1)
+    i = T.var("i")
+    with T.for_(i, 0, i < n_):
+        T.assign(out[i], (inp >> i) & 1)
+        T.constrain(out[i] * (out[i] - 1), 0)
+        T.set(lc1, lc1 + out[i] * e2)
+        T.set(e2, e2 + e2)
+    T.constrain(lc1, inp)
+
+
+def Bits2Num(T, n):
+    n_ = T.param("n", n)
+    inp = T.input("in", (n,))
+    out = T.output("out")
+    lc1 = T.var("lc1", init=0)
+    e2 = T.var("e2", init=1)
+    i = T.var("i")
+    with T.for_(i, 0, i < n_):
+        T.set(lc1, lc1 + inp[i] * e2)
+        T.set(e2, e2 + e2)
+    T.bind(out, lc1)
+
+
+def IsZero(T):
+    """circomlib comparators.circom IsZero: inv <-- in!=0 ? 1/in : 0."""
+    inp = T.input("in")
+    out = T.output("out")
+    inv = T.signal("inv")
+    tmp = T.var("tmp")
+    with T.if_(inp.ne(0)):
+        T.set(tmp, 1 / inp)
+    with T.else_():
+        T.set(tmp, 0)
+    T.assign(inv, tmp)
+    T.bind(out, -inp * inv + 1)
+    T.constrain(inp * out, 0)
+
+
+def IsEqual(T):
+    inp = T.input("in", (2,))
+    out = T.output("out")
+    isz = T.component("isz")
+    T.new(isz, IsZero)
+    T.bind(isz.pin("in"), inp[1] - inp[0])
+    T.bind(out, isz.pin("out"))
+
+
+def LessThan(T, n):
+    """circomlib comparators.circom LessThan(n)."""
+    inp = T.input("in", (2,))
+    out = T.output("out")
+    n2b = T.component("n2b")
+    T.new(n2b, Num2Bits, n + 1)
+    T.bind(n2b.pin("in"), inp[0] + (1 << n) - inp[1])
+    T.bind(out, 1 - n2b.pin("out")[n])
+
+
+def make_ops_function():
+    """A circom function touching every field operator (the op set of compute_bucket.rs:9-36);
+    used from a `<--` hint so that no constraint is involved."""
+    F = Function("allops")
+    a = F.arg("a")
+    b = F.arg("b")
+    sh = F.arg("sh")
+    F.returns = (24,)
+    r = F.var("r", (24,))
+    exprs = [a + b, a - b, a * b, a / (b + 1), a // (b + 1), a % (b + 1), a ** sh, a << sh, a >> sh,
+             a & b, a | b, a ^ b, ~a, -a, a < b, a <= b, a > b, a >= b, a.eq(b), a.ne(b),
+             a.land(b), a.lor(b), a.lnot(), (a >> sh) & 1]
+    for k, e in enumerate(exprs):
+        F.set(r[k], e)
+    F.ret(r)
+    return F
+
+
+ALLOPS = make_ops_function()
+
+
+def OpsZoo(T):
+    """Every operator through a function call with array return, array copy to signals, a
+    data-dependent branch, and a static loop over a var array."""
+    a = T.input("a")
+    b = T.input("b")
+    sh = T.input("sh")
+    out = T.output("out", (24,))
+    acc = T.output("acc")
+    res = T.var("res", (24,))
+    T.set(res, T.call(ALLOPS, a, b, sh))
+    T.assign(out, res)
+    s = T.var("s", init=0)
+    i = T.var("i")
+    with T.for_(i, 0, i < 24):
+        with T.if_(res[i] > 5):
+            T.set(s, s + res[i])
+        with T.else_():
+            T.set(s, s * 3 + 1)
+    T.assign(acc, s)
+
+
+def Sum3Cmp(T):
+    """Parent wiring three sub-components with array ports (multi-element stores) --
+    exercises Fr_copyn / the peeled copy loop of store_bucket.rs:899-1041."""
+    inp = T.input("in", (4,))
+    out = T.output("out", (4,))
+    b2n = T.component("b2n")
+    n2b = T.component("n2b")
+    T.new(b2n, Bits2Num, 4)
+    T.new(n2b, Num2Bits, 4)
+    T.bind(b2n.pin("in"), inp)
+    T.bind(n2b.pin("in"), b2n.pin("out"))
+    T.bind(out, n2b.pin("out"))
