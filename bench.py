@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: batched witness generation + R1CS check on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      (the reference's CPU calculator on the host cores)
+
+Workload (BASELINE.json configs[1]): Poseidon(2), 1,048,576 random inputs per GPU, witness generation
+followed by the R1CS check of every witness.  A "step" is one pass of both kernels over the batch.
+One JSON line is printed by rank 0 (contract in the task description).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "witnesses/sec (Poseidon(2) witness generation + R1CS check)"
+UNIT = "witnesses/s"
+MACS_PER_MUL = 136      # 8x8 + 8x8 + 8 32x32->64 multiply-accumulates per BN254 Montgomery product
+
+
+def build_workload(tmpdir):
+    from circom_cvm_b200 import formats
+    from tools.circuitgen.build import compile_circuit
+    from tools.circuitgen.circuits import poseidon
+    art = compile_circuit(poseidon.Poseidon, (2,), name="poseidon2")
+    cvm_path = os.path.join(tmpdir, "poseidon2.cvm")
+    r1cs_path = os.path.join(tmpdir, "poseidon2.r1cs")
+    with open(cvm_path, "w") as f:
+        f.write(art.cvm)
+    formats.write_r1cs(r1cs_path, art.constraints, art.n_wires, art.n_pub_out, art.n_pub_in, art.n_prv_in,
+                       art.witness, n_labels=art.n_signals)
+    return art, cvm_path, r1cs_path
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    self.samples.append((float(parts[0]), float(parts[1]), float(parts[2])))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+        except FileNotFoundError:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        hi = [s for s in sm if s >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": hi[len(hi) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
+                "power_w_max": max(s[2] for s in self.samples), "reasons": sorted(self.reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_baseline_port(art, seconds=12.0):
+    """Oracle port (pure Python CVM interpreter) on one core: a bounded sample of the same workload."""
+    import random
+
+    from oracle import cvm_interp as I
+    prog = I.load(art.cvm)
+    rng = random.Random(0xC1C00001)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        I.compute_witness(prog, [rng.randrange(I.M.Q) for _ in range(art.n_inputs)])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d Poseidon(2) witnesses, pure-Python CVM oracle (oracle/cvm_interp.py), witness generation only" % n}
+
+
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "poseidon2_bench")
+    return p if os.path.exists(p) else None
+
+
+def cpu_baseline_reference(n_threads, seconds=10.0):
+    """The reference's own C++ runtime + field arithmetic (oracle/_ref) running the Poseidon(2) program emitted
+    in the WriteC shapes; run(ctx) only is timed inside the binary; one process per thread."""
+    exe = reference_binary()
+    if exe is None:
+        return None
+    procs = [subprocess.Popen([exe, str(seconds), str(1234 + i)], stdout=subprocess.PIPE, text=True, cwd=os.path.dirname(exe))
+             for i in range(n_threads)]
+    total, count = 0.0, 0
+    for p in procs:
+        out, _ = p.communicate()
+        try:
+            d = json.loads(out.strip().splitlines()[-1])
+            total += d["witnesses_per_s"]
+            count += d["witnesses"]
+        except Exception:
+            return None
+    return {"value": total, "unit": UNIT, "cores": n_threads, "kind": "reference",
+            "sample": "%d Poseidon(2) witnesses over %d processes x %.0f s: reference common/calcwit.cpp + generic/fr.cpp "
+                      "(--no_asm arithmetic; bn128/fr.asm cannot be assembled here) running the circuit body emitted "
+                      "by tools/circuitgen in the WriteC shapes; run(ctx) only" % (count, n_threads, seconds)}
+
+
+def run_reference_arm(args, art):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    res = None
+    per = max(2.0, min(20.0, 6.0))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline_reference(cores, 1.0) if reference_binary() else None
+    for _ in range(args.steps):
+        res = cpu_baseline_reference(cores, per)
+        if res is None:
+            break
+        vals.append(res["value"])
+    if res is None:
+        res = cpu_baseline_port(art, seconds=10.0)
+        vals = [res["value"]]
+    value = sum(vals) / len(vals)
+    res["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * (time.perf_counter() - t0) / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr)",
+            "data": "synthetic", "config": {"workload": "Poseidon(2) witness generation on host cores, bounded sample per step"},
+            "cpu_baseline": res,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=1 << 20, help="witnesses per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 17)
+    ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+
+    tmpdir = tempfile.mkdtemp(prefix="cvmbench_")
+    art, cvm_path, r1cs_path = build_workload(tmpdir)
+    if args.impl == "reference":
+        run_reference_arm(args, art)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from circom_cvm_b200 import build as cbuild
+    from circom_cvm_b200 import engine as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        cbuild.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    E.set_device(local)
+    dev = torch.device("cuda", local)
+
+    wc = E.WitnessCalculator(cvm_path=cvm_path, n_slots=args.slots)
+    r1 = E.R1cs(r1cs_path)
+    info, rinfo = wc.info.asdict(), r1.info.asdict()
+    B = args.batch
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC1C00001 + rank)
+    inputs = torch.randint(0, 256, (B, wc.n_inputs, 32), dtype=torch.uint8, device=dev, generator=g)
+    inputs[:, :, 31] &= 0x1F          # < 2^253 < q: canonical field elements
+    store = torch.empty(wc.store_bytes(B), dtype=torch.uint8, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    bad = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        wc.run_dev(inputs, B, B, store, status, stream)
+        r1.check_dev(store, B, B, bad, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_start.record()
+    for k in range(args.steps):
+        ev[3 * k].record()
+        wc.run_dev(inputs, B, B, store, status, stream)
+        ev[3 * k + 1].record()
+        r1.check_dev(store, B, B, bad, stream)
+        ev[3 * k + 2].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    ms_tape = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps
+    ms_check = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)) / args.steps
+    n_fail = int((status != 0).sum()) + int((bad != -1).sum())
+    t = torch.tensor([ms_total, ms_tape, ms_check, float(n_fail)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the only exchange of the path: gather of per-witness flags (here: their count) at the end
+    ms_total, ms_tape, ms_check, n_fail = [float(x) for x in t.tolist()]
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- end-to-end through the public host-buffer API (pinned host memory, copies inside the timed region)
+    Be = min(args.e2e_batch, B)
+    h_in = torch.empty((Be, wc.n_inputs, 32), dtype=torch.uint8).pin_memory()
+    h_in.copy_(inputs[:Be].cpu())
+    h_wt = torch.empty((Be, wc.n_wires, 32), dtype=torch.uint8).pin_memory()
+    h_st = torch.empty(Be, dtype=torch.int32).pin_memory()
+    h_bad = torch.empty(Be, dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        wc.calculate_into(h_in, h_wt, h_st, r1, h_bad)
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        wc.calculate_into(h_in, h_wt, h_st, r1, h_bad)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_ok = int((h_st != 0).sum()) == 0 and int((h_bad != -1).sum()) == 0
+    e2e = {"value": world * Be / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Be * wc.n_inputs * 32,
+           "d2h_bytes_per_step": Be * (wc.n_wires * 32 + 8), "batch_per_gpu": Be, "ms_per_step": 1000 * e2e_s,
+           "all_witnesses_valid": bool(e2e_ok),
+           "api": "WitnessCalculator.calculate_into -> cvmgpu_witness_batch_checked (full .wtns rows returned)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tape kernel): integer multiply pipe
+    macs0, _ = E.imad_peak(0)
+    macs1, _ = E.imad_peak(1)
+    peak_macs = max(macs0, macs1)
+    alg_macs = B * info["ref_mul"] * MACS_PER_MUL
+    exe_macs = B * (info["tape_mul"] + 2 * info["n_inputs"]) * MACS_PER_MUL
+    achieved = alg_macs / (ms_tape * 1e-3)
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks["hbm_gbs"])
+    tape_bytes = B * (info["tape_st"] + info["tape_ld"]) * 32 + B * info["n_inputs"] * 32
+    check_bytes_alg = B * rinfo["n_wires"] * 32 + B * 4 + rinfo["nnz"] * 8 + 3 * (rinfo["n_constraints"] + 1) * 4
+    roofline = {
+        "kernel": "tape_kernel", "bound": "imad", "unit": "Tmac/s",
+        "achieved": achieved / 1e12, "peak": peak_macs / 1e12, "frac": achieved / peak_macs,
+        "achieved_executed": exe_macs / (ms_tape * 1e-3) / 1e12,
+        "peak_source": "in-run micro-benchmark cvmgpu_imad_peak: max(mad.lo+mad.hi pairs %.2f, mad.wide %.2f) Tmac/s"
+                       % (macs0 / 1e12, macs1 / 1e12),
+        "algorithmic_unit": "%d macs per field multiplication x N_mul=%d (reference program) per witness"
+                            % (MACS_PER_MUL, info["ref_mul"]),
+        "traffic": None,
+        "ms": ms_tape,
+    }
+    roofline_hbm = {
+        "tape_kernel": {"bound": "hbm", "unit": "GB/s", "achieved": tape_bytes / (ms_tape * 1e-3) / 1e9, "peak": hbm_peak,
+                        "frac": tape_bytes / (ms_tape * 1e-3) / 1e9 / hbm_peak, "ms": ms_tape, "peak_kind": peak_kind,
+                        "bytes": "B*(stores+loads)*32 + inputs"},
+        "r1cs_kernel": {"bound": "hbm", "unit": "GB/s", "achieved": check_bytes_alg / (ms_check * 1e-3) / 1e9,
+                        "peak": hbm_peak, "frac": check_bytes_alg / (ms_check * 1e-3) / 1e9 / hbm_peak, "ms": ms_check,
+                        "peak_kind": peak_kind, "constraints_per_s": world * B * rinfo["n_constraints"] / (ms_check * 1e-3),
+                        "pm1_fraction": rinfo["nnz_pm1"] / max(1, rinfo["nnz"]),
+                        "bytes": "B*nWires*32 + B*4 + nnz*8 + row pointers (compulsory)"},
+    }
+    if args.skip_cpu:
+        cpu = None
+    else:
+        cpu = cpu_baseline_reference(os.cpu_count() or 1) or cpu_baseline_port(art)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32x8 (BN254 Fr, Montgomery)", "data": "synthetic",
+        "config": {"workload": "Poseidon(2) batch of %d random inputs per GPU: witness generation + R1CS check" % B,
+                   "circuit": "tools/circuitgen Poseidon(2) (circomlib 0.5.x structure), %d signals, %d wires, %d constraints"
+                              % (info["n_signals"], info["n_wires"], rinfo["n_constraints"]),
+                   "batch_per_gpu": B, "l2": "working set %.1f GB per step >> 126 MB L2" % (wc.store_bytes(B) / 1e9),
+                   "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
+                   "n_slots": info["n_slots"], "tape_len": info["tape_len"], "failures": n_fail},
+        "kernels_ms": {"tape_kernel": ms_tape, "r1cs_kernel": ms_check},
+        "witnesses_per_s_gen_only": world * B / (ms_tape * 1e-3),
+        "constraints_per_s_check_only": world * B * rinfo["n_constraints"] / (ms_check * 1e-3),
+        "roofline": roofline, "roofline_hbm": roofline_hbm,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "clocks": sampler.summary(),
+        "program": info, "r1cs": rinfo,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,533 @@
+// C ABI of the engine (see include/cvmgpu.h for the reference interfaces each entry replaces).
+// There is NO CPU fallback: every compute entry point fails with CVMGPU_ERR_CUDA when no device works.
+#include "../../include/cvmgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cvm_parse.hpp"
+#include "host_fr.hpp"
+#include "kernels.cuh"
+#include "r1cs.hpp"
+#include "tape.hpp"
+#include "tracer.hpp"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(CVMGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= n) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(CVMGPU_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        n = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct cvmgpu_program {
+    tape::Tape tape;
+    tape::TraceStats tstats;
+    std::vector<fr::Fr> consts_mont;
+    uint64_t n_signals = 0;
+    uint32_t n_inputs = 0, n_outputs = 0;
+    // device copies (uploaded on first use on the current device)
+    int device = -1;
+    DevBuf d_tape, d_consts, d_store, d_inputs, d_status, d_wtns;
+};
+
+struct cvmgpu_r1cs {
+    r1cs::File file;
+    int device = -1;
+    DevBuf d_ptr, d_terms, d_coefs, d_store, d_wtns, d_bad;
+};
+
+extern "C" const char *cvmgpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cvmgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int cvmgpu_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return CVMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ program
+static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program **out) {
+    std::unique_ptr<cvmgpu_program> p(new cvmgpu_program());
+    if (n_slots == 0) n_slots = 24;
+    if (n_slots > 55) n_slots = 55;   // 55 * 4 KiB = 220 KiB of the 227 KiB a CTA may use
+    try {
+        tape::Tracer tr(parser.prog);
+        tr.trace();
+        p->tape = tape::build_tape(tr, n_slots);
+        p->tstats = tr.stats;
+        p->n_signals = (uint64_t)parser.prog.n_signals;
+        p->n_inputs = (uint32_t)tr.n_inputs;
+        p->n_outputs = (uint32_t)tr.n_outputs;
+        p->consts_mont.reserve(tr.consts.size());
+        for (const fr::Fr &c : tr.consts) p->consts_mont.push_back(fr::to_mont(c));
+    } catch (const tape::TraceError &e) {
+        return fail(CVMGPU_ERR_UNSUPPORTED, e.what());
+    } catch (const cvm::ParseError &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    *out = p.release();
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_load(const char *cvm_path, uint32_t n_slots, cvmgpu_program **out) {
+    if (!cvm_path || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvm::Parser parser;
+    try {
+        parser.parse_file(cvm_path);
+    } catch (const cvm::ParseError &e) {
+        std::string m = e.what();
+        return fail(m.rfind("cannot open", 0) == 0 ? CVMGPU_ERR_IO : CVMGPU_ERR_PARSE, m);
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    return build_program(parser, n_slots, out);
+}
+
+extern "C" int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32_t n_slots, cvmgpu_program **out) {
+    if (!cvm_text || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvm::Parser parser;
+    try {
+        parser.parse_text(std::string(cvm_text, len));
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    return build_program(parser, n_slots, out);
+}
+
+extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info) {
+    if (!p || !info) return fail(CVMGPU_ERR_ARG, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->n_signals = p->n_signals;
+    info->n_wires = p->tape.n_wires;
+    info->n_inputs = p->n_inputs;
+    info->n_outputs = p->n_outputs;
+    info->n_slots = p->tape.n_slots;
+    info->n_rows = p->tape.n_rows;
+    info->tape_len = p->tape.ins.size();
+    info->ref_mul = p->tstats.ref_mul;
+    info->ref_field_ops = p->tstats.ref_field_ops;
+    info->cvm_instructions = p->tstats.cvm_instructions;
+    info->tape_mul = p->tape.stats.n_mul;
+    info->tape_div = p->tape.stats.n_div;
+    info->tape_addsub = p->tape.stats.n_addsub;
+    info->tape_other = p->tape.stats.n_other;
+    info->tape_ld = p->tape.stats.n_ld;
+    info->tape_st = p->tape.stats.n_st;
+    info->tape_spill_st = p->tape.stats.n_spill_st;
+    info->n_consts = (uint32_t)p->consts_mont.size();
+    info->dyn_branches = (uint32_t)p->tstats.dyn_branches;
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_ins, const void **consts,
+                                   uint32_t *n_consts) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (ins) *ins = p->tape.ins.data();
+    if (n_ins) *n_ins = p->tape.ins.size();
+    if (consts) *consts = p->consts_mont.data();
+    if (n_consts) *n_consts = (uint32_t)p->consts_mont.size();
+    return CVMGPU_OK;
+}
+
+extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
+    if (!p) return;
+    p->d_tape.release();
+    p->d_consts.release();
+    p->d_store.release();
+    p->d_inputs.release();
+    p->d_status.release();
+    p->d_wtns.release();
+    delete p;
+}
+
+static int upload_program(cvmgpu_program *p) {
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (p->device == dev && p->d_tape.p) return CVMGPU_OK;
+    if (p->device != dev) {   // buffers belong to another device
+        p->d_tape = DevBuf(); p->d_consts = DevBuf(); p->d_store = DevBuf();
+        p->d_inputs = DevBuf(); p->d_status = DevBuf(); p->d_wtns = DevBuf();
+    }
+    size_t tb = std::max<size_t>(16, p->tape.ins.size() * sizeof(tape::TapeIns));
+    size_t cb = std::max<size_t>(32, p->consts_mont.size() * sizeof(fr::Fr));
+    if (int rc = p->d_tape.ensure(tb)) return rc;
+    if (int rc = p->d_consts.ensure(cb)) return rc;
+    if (!p->tape.ins.empty())
+        CUDA_TRY(cudaMemcpy(p->d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
+    if (!p->consts_mont.empty())
+        CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
+    size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * CVM_NT;
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p->device = dev;
+    return CVMGPU_OK;
+}
+
+extern "C" size_t cvmgpu_store_bytes(const cvmgpu_program *p, uint64_t bstride) {
+    if (!p) return 0;
+    return (size_t)p->tape.n_rows * 2 * sizeof(uint4) * bstride;
+}
+
+extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride,
+                                        void *d_store, void *d_status, void *stream) {
+    if (!p || !d_store || (!d_inputs && p->n_inputs)) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0) return CVMGPU_OK;
+    if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
+    if (int rc = upload_program(p)) return rc;
+    kern::TapeParams tp;
+    tp.tape = (const tape::TapeIns *)p->d_tape.p;
+    tp.n_ins = (uint32_t)p->tape.ins.size();
+    tp.consts = (const uint4 *)p->d_consts.p;
+    tp.store = (uint4 *)d_store;
+    tp.bstride = bstride;
+    tp.inputs = (const uint4 *)d_inputs;
+    tp.n_inputs = p->n_inputs;
+    tp.status = (uint32_t *)d_status;
+    tp.B = B;
+    size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * CVM_NT;
+    uint64_t grid = (B + CVM_NT - 1) / CVM_NT;
+    if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
+    kern::tape_kernel<<<(unsigned)grid, CVM_NT, smem, (cudaStream_t)stream>>>(tp);
+    CUDA_TRY(cudaGetLastError());
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_wtns,
+                                         void *stream) {
+    if (!p || !d_store || !d_wtns) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0) return CVMGPU_OK;
+    dim3 grid((unsigned)((B + 31) / 32), (p->tape.n_wires + 31) / 32);
+    kern::export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4 *)d_store, bstride, B, p->tape.n_wires,
+                                                              (uint4 *)d_wtns);
+    CUDA_TRY(cudaGetLastError());
+    return CVMGPU_OK;
+}
+
+static int upload_r1cs(cvmgpu_r1cs *r);
+
+// largest chunk of witnesses whose buffers fit in the free device memory
+static uint64_t pick_chunk(uint64_t B, size_t bytes_per_witness) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    uint64_t cap = (uint64_t)((double)free_b * 0.85 / (double)std::max<size_t>(1, bytes_per_witness));
+    cap = cap / 1024 * 1024;
+    if (cap < 128) cap = 128;
+    return std::min<uint64_t>(B, cap);
+}
+
+// Host-buffer pipeline: the batch is cut into chunks that alternate between two streams, each with its own
+// device buffers, so that (with pinned host memory) the H2D copy / kernels / D2H copy of consecutive chunks
+// overlap.  Optional R1CS check runs on the value store before it is exported.
+struct PipeBufs {
+    DevBuf store, inputs, status, wtns, bad;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
+                                            uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
+    if (!p || (!inputs && p->n_inputs)) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (r && !first_bad) return fail(CVMGPU_ERR_ARG, "first_bad is required with an r1cs handle");
+    if (r && r->file.n_wires != p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "r1cs and program disagree on the number of wires");
+    if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (B == 0) return CVMGPU_OK;
+    if (int rc = upload_program(p)) return rc;
+    if (r)
+        if (int rc = upload_r1cs(r)) return rc;
+    const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)p->tape.n_wires * 32;
+    size_t per_w = (size_t)p->tape.n_rows * 32 + in_row + (wtns_out ? out_row : 0) + 8;
+    uint64_t fit = pick_chunk(B, 2 * per_w);
+    if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
+    uint64_t chunk = std::min<uint64_t>(fit, 32768);
+    if (B <= chunk) chunk = B;
+    static thread_local PipeBufs pipe[2];
+    static thread_local int pipe_dev = -1;
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (pipe_dev != dev) {
+        for (auto &pb : pipe) { pb = PipeBufs(); }
+        pipe_dev = dev;
+    }
+    const int nbuf = (B > chunk) ? 2 : 1;
+    for (int k = 0; k < nbuf; k++) {
+        PipeBufs &pb = pipe[k];
+        if (!pb.stream) CUDA_TRY(cudaStreamCreateWithFlags(&pb.stream, cudaStreamNonBlocking));
+        if (int rc = pb.store.ensure(cvmgpu_store_bytes(p, chunk))) return rc;
+        if (int rc = pb.inputs.ensure(std::max<size_t>(32, in_row * chunk))) return rc;
+        if (int rc = pb.status.ensure(4 * chunk)) return rc;
+        if (int rc = pb.bad.ensure(4 * chunk)) return rc;
+        if (wtns_out)
+            if (int rc = pb.wtns.ensure(out_row * chunk)) return rc;
+    }
+    uint64_t idx = 0;
+    for (uint64_t b0 = 0; b0 < B; b0 += chunk, idx++) {
+        PipeBufs &pb = pipe[idx % nbuf];
+        cudaStream_t s = pb.stream;
+        uint64_t n = std::min<uint64_t>(chunk, B - b0);
+        // the stream's previous chunk must have left its buffers (stream order guarantees it)
+        if (in_row) CUDA_TRY(cudaMemcpyAsync(pb.inputs.p, inputs + b0 * in_row, n * in_row, cudaMemcpyHostToDevice, s));
+        if (int rc = cvmgpu_witness_batch_dev(p, pb.inputs.p, n, chunk, pb.store.p, pb.status.p, s)) return rc;
+        if (r) {
+            if (int rc = cvmgpu_r1cs_check_dev(r, pb.store.p, n, chunk, pb.bad.p, s)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(first_bad + b0, pb.bad.p, n * 4, cudaMemcpyDeviceToHost, s));
+        }
+        if (wtns_out) {
+            if (int rc = cvmgpu_witness_export_dev(p, pb.store.p, n, chunk, pb.wtns.p, s)) return rc;
+            CUDA_TRY(cudaMemcpyAsync(wtns_out + b0 * out_row, pb.wtns.p, n * out_row, cudaMemcpyDeviceToHost, s));
+        }
+        if (status) CUDA_TRY(cudaMemcpyAsync(status + b0, pb.status.p, n * 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < nbuf; k++) CUDA_TRY(cudaStreamSynchronize(pipe[k].stream));
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_witness_batch(cvmgpu_program *p, const uint8_t *inputs, uint64_t B, uint8_t *wtns_out, uint32_t *status) {
+    return cvmgpu_witness_batch_checked(p, nullptr, inputs, B, wtns_out, status, nullptr);
+}
+
+extern "C" int cvmgpu_wtns_write(const char *path, const uint8_t *witness, uint32_t n_wires) {
+    if (!path || !witness) return fail(CVMGPU_ERR_ARG, "null argument");
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(CVMGPU_ERR_IO, std::string("cannot create ") + path);
+    // common/main.cpp:286-332
+    static const uint8_t qle[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                                    0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+    uint32_t version = 2, nsec = 2, id1 = 1, n8 = 32, id2 = 2;
+    uint64_t len1 = 8 + n8, len2 = (uint64_t)n8 * n_wires;
+    bool ok = fwrite("wtns", 4, 1, f) == 1 && fwrite(&version, 4, 1, f) == 1 && fwrite(&nsec, 4, 1, f) == 1 &&
+              fwrite(&id1, 4, 1, f) == 1 && fwrite(&len1, 8, 1, f) == 1 && fwrite(&n8, 4, 1, f) == 1 &&
+              fwrite(qle, 32, 1, f) == 1 && fwrite(&n_wires, 4, 1, f) == 1 && fwrite(&id2, 4, 1, f) == 1 &&
+              fwrite(&len2, 8, 1, f) == 1 && (n_wires == 0 || fwrite(witness, (size_t)len2, 1, f) == 1);
+    fclose(f);
+    return ok ? CVMGPU_OK : fail(CVMGPU_ERR_IO, "short write");
+}
+
+// ------------------------------------------------------------------------------------------ r1cs
+extern "C" int cvmgpu_r1cs_load(const char *path, cvmgpu_r1cs **out) {
+    if (!path || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    std::unique_ptr<cvmgpu_r1cs> r(new cvmgpu_r1cs());
+    try {
+        r->file = r1cs::load(path);
+    } catch (const r1cs::Error &e) {
+        std::string m = e.what();
+        return fail(m.rfind("cannot open", 0) == 0 ? CVMGPU_ERR_IO : CVMGPU_ERR_PARSE, m);
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    *out = r.release();
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info) {
+    if (!r || !info) return fail(CVMGPU_ERR_ARG, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->n_wires = r->file.n_wires;
+    info->n_pub_out = r->file.n_pub_out;
+    info->n_pub_in = r->file.n_pub_in;
+    info->n_prv_in = r->file.n_prv_in;
+    info->n_constraints = r->file.n_constraints;
+    info->n_labels = r->file.n_labels;
+    info->nnz = r->file.terms.size();
+    info->nnz_pm1 = r->file.nnz_pm1;
+    info->n_coefs = (uint32_t)r->file.coefs.size();
+    return CVMGPU_OK;
+}
+
+extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
+    if (!r) return;
+    r->d_ptr.release(); r->d_terms.release(); r->d_coefs.release();
+    r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
+    delete r;
+}
+
+static int upload_r1cs(cvmgpu_r1cs *r) {
+    int dev = -1;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (r->device == dev && r->d_ptr.p) return CVMGPU_OK;
+    if (r->device != dev) {
+        r->d_ptr = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf();
+        r->d_store = DevBuf(); r->d_wtns = DevBuf(); r->d_bad = DevBuf();
+    }
+    const r1cs::File &f = r->file;
+    std::vector<fr::Fr> cm;
+    cm.reserve(f.coefs.size());
+    for (const fr::Fr &c : f.coefs) cm.push_back(fr::to_mont(c));
+    if (int rc = r->d_ptr.ensure(std::max<size_t>(16, f.ptr.size() * 4))) return rc;
+    if (int rc = r->d_terms.ensure(std::max<size_t>(16, f.terms.size() * 8))) return rc;
+    if (int rc = r->d_coefs.ensure(cm.size() * 32)) return rc;
+    CUDA_TRY(cudaMemcpy(r->d_ptr.p, f.ptr.data(), f.ptr.size() * 4, cudaMemcpyHostToDevice));
+    if (!f.terms.empty()) CUDA_TRY(cudaMemcpy(r->d_terms.p, f.terms.data(), f.terms.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->d_coefs.p, cm.data(), cm.size() * 32, cudaMemcpyHostToDevice));
+    r->device = dev;
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64_t B, uint64_t bstride, void *d_first_bad,
+                                     void *stream) {
+    if (!r || !d_store || !d_first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0) return CVMGPU_OK;
+    if (int rc = upload_r1cs(r)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(d_first_bad, 0xff, B * 4, s));
+    if (r->file.n_constraints == 0) return CVMGPU_OK;
+    uint64_t gx = (B + 127) / 128;
+    // enough CTAs to fill 148 SMs several times over even for small batches (config 5: B = 1K, 1.5M constraints)
+    uint64_t want = 148ull * 16;
+    uint64_t chunks = std::max<uint64_t>(1, (want + gx - 1) / gx);
+    uint32_t per = (uint32_t)std::max<uint64_t>(32, (r->file.n_constraints + chunks - 1) / chunks);
+    chunks = (r->file.n_constraints + per - 1) / per;
+    if (chunks > 65535) {
+        per = (r->file.n_constraints + 65534) / 65535;
+        chunks = (r->file.n_constraints + per - 1) / per;
+    }
+    kern::R1csParams rp;
+    rp.ptr = (const uint32_t *)r->d_ptr.p;
+    rp.terms = (const uint2 *)r->d_terms.p;
+    rp.coefs = (const uint4 *)r->d_coefs.p;
+    rp.n_cons = r->file.n_constraints;
+    rp.cons_per_chunk = per;
+    rp.store = (const uint4 *)d_store;
+    rp.bstride = bstride;
+    rp.B = B;
+    rp.first_bad = (uint32_t *)d_first_bad;
+    dim3 grid((unsigned)gx, (unsigned)chunks);
+    kern::r1cs_kernel<<<grid, 128, 0, s>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, uint64_t bstride, void *d_store,
+                                         void *stream) {
+    if (!d_wtns || !d_store) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0 || n_wires == 0) return CVMGPU_OK;
+    dim3 grid((unsigned)((B + 31) / 32), (n_wires + 31) / 32);
+    kern::import_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4 *)d_wtns, B, n_wires, (uint4 *)d_store, bstride);
+    CUDA_TRY(cudaGetLastError());
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_r1cs_check(cvmgpu_r1cs *r, const uint8_t *witnesses, uint64_t B, uint32_t *first_bad) {
+    if (!r || !witnesses || !first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (B == 0) return CVMGPU_OK;
+    if (int rc = upload_r1cs(r)) return rc;
+    const size_t row = (size_t)r->file.n_wires * 32;
+    uint64_t chunk = std::min<uint64_t>(pick_chunk(B, 2 * row + 4), 1u << 22);
+    if (chunk == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
+    if (int rc = r->d_store.ensure((size_t)r->file.n_wires * 32 * chunk)) return rc;
+    if (int rc = r->d_wtns.ensure(row * chunk)) return rc;
+    if (int rc = r->d_bad.ensure(4 * chunk)) return rc;
+    cudaStream_t s = 0;
+    for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
+        uint64_t n = std::min<uint64_t>(chunk, B - b0);
+        CUDA_TRY(cudaMemcpyAsync(r->d_wtns.p, witnesses + b0 * row, n * row, cudaMemcpyHostToDevice, s));
+        if (int rc = cvmgpu_witness_import_dev(r->file.n_wires, r->d_wtns.p, n, chunk, r->d_store.p, s)) return rc;
+        if (int rc = cvmgpu_r1cs_check_dev(r, r->d_store.p, n, chunk, r->d_bad.p, s)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(first_bad + b0, r->d_bad.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return CVMGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ field hooks
+extern "C" int cvmgpu_fr_host_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    if (!op || !a || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    hostfr::FfOp f = hostfr::op_from_name(op);
+    if (f == hostfr::F_NONE) return fail(CVMGPU_ERR_ARG, std::string("unknown field op ") + op);
+    fr::Fr x, y = fr::zero(), r = fr::zero();
+    memcpy(x.v, a, 32);
+    if (b) memcpy(y.v, b, 32);
+    bool ok = hostfr::apply(f, x, y, r);
+    memcpy(out, r.v, 32);
+    return ok ? 0 : 1;
+}
+
+extern "C" int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n) {
+    if (!op || !a || !b || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    hostfr::FfOp f = hostfr::op_from_name(op);
+    if (f == hostfr::F_NONE) return fail(CVMGPU_ERR_ARG, std::string("unknown field op ") + op);
+    if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (n == 0) return CVMGPU_OK;
+    void *da = nullptr, *db = nullptr, *dout = nullptr, *dund = nullptr;
+    CUDA_TRY(cudaMalloc(&da, n * 32));
+    CUDA_TRY(cudaMalloc(&db, n * 32));
+    CUDA_TRY(cudaMalloc(&dout, n * 32));
+    CUDA_TRY(cudaMalloc(&dund, n * 4));
+    CUDA_TRY(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(dund, 0, n * 4));
+    kern::fr_op_kernel<<<(unsigned)((n + 127) / 128), 128>>>((int)f, (const uint4 *)da, (const uint4 *)db, (uint4 *)dout, n,
+                                                            (uint32_t *)dund);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dund);
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms_out) {
+    if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available");
+    uint32_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 4));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const uint32_t iters = 4096;
+    unsigned blocks = (unsigned)prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        if (kind == 0) kern::imad_kernel<0><<<blocks, 256>>>(d, iters, 12345u + rep);
+        else kern::imad_kernel<1><<<blocks, 256>>>(d, iters, 12345u + rep);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CUDA_TRY(cudaGetLastError());
+    double macs = (double)blocks * 256.0 * iters * 8.0;
+    if (macs_per_second) *macs_per_second = macs / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return CVMGPU_OK;
+}

@@ -1,0 +1,443 @@
+// BN254 scalar field (Fr) arithmetic on 8x32-bit limbs, Montgomery form with R = 2^256.
+//
+// Replaces, for the GPU path, the reference's x86-64 field library
+//   code_producers/src/c_elements/bn128/fr.asm   (Fr_rawMMul :365, rawMSquare :533, add/sub/neg :1110-2300,
+//                                                  band/bor/bxor/bnot :2728-6415, shr/shl :7069-7420,
+//                                                  comparisons :7421-8380, constants :8779-8793)
+//   code_producers/src/c_elements/generic/fr.cpp  (the readable twin; value semantics in SURVEY.md App. B)
+// Same R as the reference, so constants are in the same Montgomery form as its .dat files
+// (c_code_generator.rs:560-612).
+//
+// Values on the device are ALWAYS long+Montgomery (no short/long tag dispatch); operations that look
+// at the integer (comparisons, shifts, bit ops, idiv/mod, pow exponent, toInt) leave Montgomery form
+// first, exactly like generic/fr.cpp does.
+//
+// The header is also compilable by a host C++ compiler (FR_HD expands to nothing) so that the
+// limb-level algorithms can be unit-tested on CPU against the reference-generated KATs.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FR_HD __host__ __device__ __forceinline__
+#define FR_D __device__ __forceinline__
+#else
+#define FR_HD inline
+#define FR_D inline
+#endif
+
+namespace fr {
+
+struct Fr {
+    uint32_t v[8];
+};
+
+// q, little-endian 32-bit limbs (program_structure/src/utils/constants.rs:3-4)
+#define FR_Q0 0xf0000001u
+#define FR_Q1 0x43e1f593u
+#define FR_Q2 0x79b97091u
+#define FR_Q3 0x2833e848u
+#define FR_Q4 0x8181585du
+#define FR_Q5 0xb85045b6u
+#define FR_Q6 0xe131a029u
+#define FR_Q7 0x30644e72u
+#define FR_NP0 0xefffffffu  // -q^-1 mod 2^32 (low word of bn128/fr.asm:8793 np)
+
+FR_HD uint32_t qlimb(int i) {
+    switch (i) {
+        case 0: return FR_Q0; case 1: return FR_Q1; case 2: return FR_Q2; case 3: return FR_Q3;
+        case 4: return FR_Q4; case 5: return FR_Q5; case 6: return FR_Q6; default: return FR_Q7;
+    }
+}
+
+// R mod q   (Montgomery form of 1)
+FR_HD Fr one_mont() {
+    Fr r = {{0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}};
+    return r;
+}
+// R^2 mod q  (bn128/fr.asm:8789 R2)
+FR_HD Fr r2_mont() {
+    Fr r = {{0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}};
+    return r;
+}
+FR_HD Fr zero() {
+    Fr r = {{0, 0, 0, 0, 0, 0, 0, 0}};
+    return r;
+}
+FR_HD Fr modulus() {
+    Fr r = {{FR_Q0, FR_Q1, FR_Q2, FR_Q3, FR_Q4, FR_Q5, FR_Q6, FR_Q7}};
+    return r;
+}
+// (q-1)/2  (bn128/fr.asm:8787 half)
+FR_HD Fr half_q() {
+    Fr r = {{0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u}};
+    return r;
+}
+
+FR_HD bool is_zero(const Fr &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.v[i];
+    return o == 0;
+}
+FR_HD bool equal(const Fr &a, const Fr &b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+}
+// a >= b on raw 256-bit integers
+FR_HD bool geq_raw(const Fr &a, const Fr &b) {
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a.v[i] - b.v[i] - borrow;
+        borrow = (d >> 32) & 1;
+    }
+    return borrow == 0;
+}
+FR_HD bool gt_raw(const Fr &a, const Fr &b) { return !geq_raw(b, a); }
+
+// r = a - b (raw), returns borrow
+FR_HD uint32_t sub_raw(Fr &r, const Fr &a, const Fr &b) {
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a.v[i] - b.v[i] - borrow;
+        r.v[i] = (uint32_t)d;
+        borrow = (d >> 32) & 1;
+    }
+    return (uint32_t)borrow;
+}
+// r = a + b (raw), returns carry
+FR_HD uint32_t add_raw(Fr &r, const Fr &a, const Fr &b) {
+    uint64_t carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t s = (uint64_t)a.v[i] + b.v[i] + carry;
+        r.v[i] = (uint32_t)s;
+        carry = s >> 32;
+    }
+    return (uint32_t)carry;
+}
+// branch-free: r = (t >= q) ? t - q : t     (one conditional subtraction)
+FR_HD Fr reduce_once(const Fr &t) {
+    Fr d;
+    uint32_t borrow = sub_raw(d, t, modulus());
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = borrow ? t.v[i] : d.v[i];
+    return r;
+}
+
+// ---- field add / sub / neg  (generic/fr.cpp:19-98 rawAdd/rawSub/rawNeg; valid in either representation)
+FR_HD Fr add(const Fr &a, const Fr &b) {
+    Fr t;
+    add_raw(t, a, b);  // a, b < q < 2^254: no carry out of 256 bits
+    return reduce_once(t);
+}
+FR_HD Fr sub(const Fr &a, const Fr &b) {
+    Fr d, e;
+    uint32_t borrow = sub_raw(d, a, b);
+    add_raw(e, d, modulus());
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = borrow ? e.v[i] : d.v[i];
+    return r;
+}
+FR_HD Fr neg(const Fr &a) {
+    Fr d;
+    sub_raw(d, modulus(), a);
+    bool z = is_zero(a);
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : d.v[i];
+    return r;
+}
+
+// ---- Montgomery multiplication, CIOS on 8x32 limbs  (generic/fr.cpp:110-164 Fr_rawMMul; bn128/fr.asm:365)
+// 8*8 (a*b) + 8*8 (m*q) + 8 (m) = 136 32x32->64 multiply-accumulates.
+// Portable formulation: 64-bit row accumulators; nvcc lowers each step to IMAD.WIDE.U32 + carry adds.
+FR_HD Fr mont_mul_portable(const Fr &a, const Fr &b) {
+    uint32_t t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t carry = 0;
+        uint32_t bi = b.v[i];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint64_t p = (uint64_t)a.v[j] * bi + t[j] + carry;
+            t[j] = (uint32_t)p;
+            carry = p >> 32;
+        }
+        uint64_t s = (uint64_t)t[8] + carry;
+        t[8] = (uint32_t)s;
+        t[9] = (uint32_t)(s >> 32);
+        uint32_t m = t[0] * FR_NP0;
+        uint64_t p = (uint64_t)m * FR_Q0 + t[0];
+        carry = p >> 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            p = (uint64_t)m * qlimb(j) + t[j] + carry;
+            t[j - 1] = (uint32_t)p;
+            carry = p >> 32;
+        }
+        s = (uint64_t)t[8] + carry;
+        t[7] = (uint32_t)s;
+        t[8] = t[9] + (uint32_t)(s >> 32);
+    }
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    // result < 2q and q < 2^254 so t[8] == 0 here; one conditional subtraction finishes
+    return reduce_once(r);
+}
+
+#if defined(__CUDA_ARCH__)
+// Device formulation with explicit carry chains (mad.lo.cc / madc.hi.cc): even and odd limb products are
+// accumulated in two separate 8-limb chains so that every chain is a straight run of IMAD with carry.
+//   T = E + O*2^32 ;  per b-limb:  E += a_even*bi, O += a_odd*bi ; m = E[0]*np ; E += q_even*m ; O += q_odd*m ;
+//   then T >>= 32 by folding E[1] into O and shifting E down by two limbs (roles of E and O swap).
+struct Chain {
+    // acc[j..j+1] += x[j]*y for j = 0,2,4,6 in one carry chain; returns the carry out of acc[7]
+    static __device__ __forceinline__ uint32_t mad_even(uint32_t *acc, const uint32_t *x, uint32_t y) {
+        uint32_t c;
+        asm volatile(
+            "mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, 0, 0;\n\t"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+              "+r"(acc[7]), "=r"(c)
+            : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
+        return c;
+    }
+};
+
+__device__ __forceinline__ Fr mont_mul_chain(const Fr &a, const Fr &b) {
+    // E holds limbs at even alignment (E[0] is weight 2^0), O at odd alignment (O[0] is weight 2^32).
+    uint32_t E[9], O[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { E[i] = 0; O[i] = 0; }
+    const uint32_t q[8] = {FR_Q0, FR_Q1, FR_Q2, FR_Q3, FR_Q4, FR_Q5, FR_Q6, FR_Q7};
+    uint32_t ao[8], qo[8];  // odd-limb views: x_odd[j] = x[j+1] so that mad_even(x_odd) multiplies limbs 1,3,5,7
+#pragma unroll
+    for (int j = 0; j < 7; j++) { ao[j] = a.v[j + 1]; qo[j] = q[j + 1]; }
+    ao[7] = 0; qo[7] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t bi = b.v[i];
+        E[8] += Chain::mad_even(E, a.v, bi);
+        O[8] += Chain::mad_even(O, ao, bi);
+        uint32_t m = E[0] * FR_NP0;
+        E[8] += Chain::mad_even(E, q, m);
+        O[8] += Chain::mad_even(O, qo, m);
+        // now E[0] == 0.  T' = T >> 32 = (O + E[1]) + 2^32 * (E[2..8])
+        // new E' = O + E[1] (aligned at weight 2^0), new O' = E >> 64 (aligned at weight 2^32)
+        uint32_t nE[9], nO[9];
+        asm volatile(
+            "add.cc.u32 %0, %9, %18;\n\t"
+            "addc.cc.u32 %1, %10, 0;\n\t"
+            "addc.cc.u32 %2, %11, 0;\n\t"
+            "addc.cc.u32 %3, %12, 0;\n\t"
+            "addc.cc.u32 %4, %13, 0;\n\t"
+            "addc.cc.u32 %5, %14, 0;\n\t"
+            "addc.cc.u32 %6, %15, 0;\n\t"
+            "addc.cc.u32 %7, %16, 0;\n\t"
+            "addc.u32 %8, %17, 0;\n\t"
+            : "=r"(nE[0]), "=r"(nE[1]), "=r"(nE[2]), "=r"(nE[3]), "=r"(nE[4]), "=r"(nE[5]), "=r"(nE[6]),
+              "=r"(nE[7]), "=r"(nE[8])
+            : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+              "r"(E[1]));
+#pragma unroll
+        for (int j = 0; j < 7; j++) nO[j] = E[j + 2];
+        nO[7] = 0; nO[8] = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+    }
+    // T = E + O*2^32, < 2q
+    Fr r;
+    asm volatile(
+        "add.cc.u32 %0, %8, 0;\n\t"
+        "addc.cc.u32 %1, %9, %16;\n\t"
+        "addc.cc.u32 %2, %10, %17;\n\t"
+        "addc.cc.u32 %3, %11, %18;\n\t"
+        "addc.cc.u32 %4, %12, %19;\n\t"
+        "addc.cc.u32 %5, %13, %20;\n\t"
+        "addc.cc.u32 %6, %14, %21;\n\t"
+        "addc.u32 %7, %15, %22;\n\t"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    return reduce_once(r);
+}
+#endif
+
+FR_HD Fr mont_mul(const Fr &a, const Fr &b) {
+#if defined(__CUDA_ARCH__) && defined(FR_USE_CHAIN)
+    return mont_mul_chain(a, b);
+#else
+    return mont_mul_portable(a, b);
+#endif
+}
+FR_HD Fr mont_sqr(const Fr &a) { return mont_mul(a, a); }  // the reference's rawMSquare also just multiplies (fr.cpp:166-169)
+
+// canonical <-> Montgomery (generic/fr.cpp:211-255)
+FR_HD Fr to_mont(const Fr &a) { return mont_mul(a, r2_mont()); }
+FR_HD Fr from_mont(const Fr &a) {
+    Fr one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+    return mont_mul(a, one);
+}
+
+// a^e for a fixed public exponent given as 8 limbs (square-and-multiply, MSB first); a in Montgomery form
+FR_HD Fr mont_pow(const Fr &a, const Fr &e) {
+    Fr r = one_mont();
+    bool started = false;
+    for (int i = 7; i >= 0; i--) {
+        for (int bit = 31; bit >= 0; bit--) {
+            if (started) r = mont_sqr(r);
+            if ((e.v[i] >> bit) & 1) {
+                r = started ? mont_mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+// inverse by Fermat: a^(q-2); inverse of 0 is 0 (mpz_invert leaves the reference's result undefined there)
+FR_HD Fr mont_inv(const Fr &a) {
+    Fr e = modulus();
+    e.v[0] -= 2;  // q-2 (no borrow: low limb is 0xf0000001)
+    return mont_pow(a, e);
+}
+
+// ---- integer-view operations on CANONICAL values ------------------------------
+// signed comparison around half = (q-1)/2: v > half means v - q   (generic/fr.cpp:1172-1363)
+FR_HD bool is_neg(const Fr &a) { return gt_raw(a, half_q()); }
+FR_HD bool lt_signed(const Fr &a, const Fr &b) {
+    bool na = is_neg(a), nb = is_neg(b);
+    if (na != nb) return na;           // negative < non-negative
+    return gt_raw(b, a);               // same sign: order of canonical values
+}
+
+// mask to 254 bits then one conditional subtraction (generic/fr.cpp:293-376)
+FR_HD Fr mask_reduce(Fr t) {
+    t.v[7] &= 0x3fffffffu;
+    return reduce_once(t);
+}
+FR_HD Fr band(const Fr &a, const Fr &b) { Fr t; for (int i = 0; i < 8; i++) t.v[i] = a.v[i] & b.v[i]; return mask_reduce(t); }
+FR_HD Fr bor(const Fr &a, const Fr &b) { Fr t; for (int i = 0; i < 8; i++) t.v[i] = a.v[i] | b.v[i]; return mask_reduce(t); }
+FR_HD Fr bxor(const Fr &a, const Fr &b) { Fr t; for (int i = 0; i < 8; i++) t.v[i] = a.v[i] ^ b.v[i]; return mask_reduce(t); }
+FR_HD Fr bnot(const Fr &a) { Fr t; for (int i = 0; i < 8; i++) t.v[i] = ~a.v[i]; return mask_reduce(t); }
+
+// raw shifts by 0 <= s < 256
+FR_HD Fr shl_raw(const Fr &a, uint32_t s) {
+    Fr r;
+    uint32_t w = s >> 5, b = s & 31;
+    for (int i = 7; i >= 0; i--) {
+        uint32_t lo = (i - (int)w >= 0) ? a.v[i - w] : 0u;
+        uint32_t lo2 = (i - (int)w - 1 >= 0) ? a.v[i - w - 1] : 0u;
+        r.v[i] = b ? ((lo << b) | (lo2 >> (32 - b))) : lo;
+    }
+    return r;
+}
+FR_HD Fr shr_raw(const Fr &a, uint32_t s) {
+    Fr r;
+    uint32_t w = s >> 5, b = s & 31;
+    for (int i = 0; i < 8; i++) {
+        uint32_t lo = (i + w < 8) ? a.v[i + w] : 0u;
+        uint32_t hi = (i + w + 1 < 8) ? a.v[i + w + 1] : 0u;
+        r.v[i] = b ? ((lo >> b) | (hi << (32 - b))) : lo;
+    }
+    return r;
+}
+// does the canonical value fit in [0, 254)?  returns the amount, else 0xffffffff
+FR_HD uint32_t small_amount(const Fr &b) {
+    uint32_t hi = 0;
+    for (int i = 1; i < 8; i++) hi |= b.v[i];
+    return (hi == 0 && b.v[0] < 254u) ? b.v[0] : 0xffffffffu;
+}
+// shl / shr with the reference's "negative shift" rule (generic/fr.cpp:1995-2307)
+FR_HD Fr shr(const Fr &a, const Fr &b);
+FR_HD Fr shl(const Fr &a, const Fr &b) {
+    uint32_t s = small_amount(b);
+    if (s != 0xffffffffu) return mask_reduce(shl_raw(a, s));
+    Fr nb;
+    sub_raw(nb, modulus(), b);          // q - b
+    uint32_t t = small_amount(nb);
+    if (t == 0xffffffffu) return zero();
+    return shr_raw(a, t);
+}
+FR_HD Fr shr(const Fr &a, const Fr &b) {
+    uint32_t s = small_amount(b);
+    if (s != 0xffffffffu) return shr_raw(a, s);
+    Fr nb;
+    sub_raw(nb, modulus(), b);
+    uint32_t t = small_amount(nb);
+    if (t == 0xffffffffu) return zero();
+    return mask_reduce(shl_raw(a, t));
+}
+
+// number of significant bits of a raw 256-bit integer
+FR_HD int bit_length(const Fr &a) {
+    for (int i = 7; i >= 0; i--) {
+        if (a.v[i]) {
+            int n = 0;
+            uint32_t x = a.v[i];
+            while (x) { n++; x >>= 1; }
+            return 32 * i + n;
+        }
+    }
+    return 0;
+}
+// floor division and remainder of canonical integers (generic/fr.cpp:2835-2875, mpz_fdiv_q / mpz_fdiv_r);
+// shift-subtract long division.  d must be non-zero.
+FR_HD void divmod(const Fr &n, const Fr &d, Fr &qt, Fr &rem) {
+    qt = zero();
+    rem = n;
+    int shift = bit_length(n) - bit_length(d);
+    if (shift < 0) return;
+    Fr ds = shl_raw(d, (uint32_t)shift);
+    for (int s = shift; s >= 0; s--) {
+        if (geq_raw(rem, ds)) {
+            Fr t;
+            sub_raw(t, rem, ds);
+            rem = t;
+            qt.v[s >> 5] |= 1u << (s & 31);
+        }
+        ds = shr_raw(ds, 1);
+    }
+}
+
+// a (Montgomery) ^ e (canonical, data-dependent)  (generic/fr.cpp:2877-2893 mpz_powm)
+FR_HD Fr mont_pow_var(const Fr &a, const Fr &e) {
+    Fr r = one_mont();
+    int n = bit_length(e);
+    for (int i = n - 1; i >= 0; i--) {
+        r = mont_sqr(r);
+        if ((e.v[i >> 5] >> (i & 31)) & 1) r = mont_mul(r, a);
+    }
+    return r;
+}
+
+// Fr_toInt domain check on a canonical value (generic/fr.cpp:1102-1170): fits int32 around 0 (mod q)
+FR_HD bool to_int(const Fr &a, int32_t &out) {
+    uint32_t hi = 0;
+    for (int i = 1; i < 8; i++) hi |= a.v[i];
+    if (hi == 0 && a.v[0] < 0x80000000u) { out = (int32_t)a.v[0]; return true; }
+    Fr d;
+    sub_raw(d, modulus(), a);           // q - a
+    hi = 0;
+    for (int i = 1; i < 8; i++) hi |= d.v[i];
+    if (hi == 0 && d.v[0] <= 0x80000000u && d.v[0] != 0) { out = (int32_t)(0u - d.v[0]); return true; }
+    return false;
+}
+
+}  // namespace fr

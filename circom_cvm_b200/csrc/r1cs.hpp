@@ -1,0 +1,131 @@
+// .r1cs loader -> compact CSR for the check kernel.
+// Format: constraint_writers/src/r1cs_writer.rs (header :245-269, constraints :282-308 / :49-91,
+// wire2label :328-341); sections are located by scanning the section table because the writer emits
+// constraints BEFORE the header (constraint_list/src/r1cs_porting.rs:19-53), as the reference's own
+// (unused) reader does (constraint_writers/src/r1cs_reader.rs:459-476).
+// Coefficients are interned like the compiler does (circom_algebra/src/constraint_storage/logic.rs:4-12):
+// table index 0 is +1, index 1 is -1 (q-1), so the kernel can special-case both as add/sub.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fr.cuh"
+#include "tracer.hpp"   // FrHash / FrEq
+
+namespace r1cs {
+
+struct Term {
+    uint32_t wire;
+    uint32_t coef;   // index into coefs
+};
+
+struct File {
+    uint32_t field_size = 0;
+    uint32_t n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_prv_in = 0, n_constraints = 0;
+    uint64_t n_labels = 0;
+    std::vector<uint32_t> ptr;       // 3*n_constraints + 1 offsets into terms: LC k of constraint c at ptr[3c+k]
+    std::vector<Term> terms;
+    std::vector<fr::Fr> coefs;       // canonical
+    std::vector<uint64_t> wire2label;
+    uint64_t nnz_pm1 = 0;
+};
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline File load(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot open " + path);
+    std::vector<uint8_t> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto need = [&](size_t pos, size_t n) {
+        if (pos + n > d.size()) throw Error("truncated r1cs file");
+    };
+    auto u32 = [&](size_t pos) { need(pos, 4); uint32_t v; memcpy(&v, &d[pos], 4); return v; };
+    auto u64 = [&](size_t pos) { need(pos, 8); uint64_t v; memcpy(&v, &d[pos], 8); return v; };
+    need(0, 12);
+    if (memcmp(&d[0], "r1cs", 4) != 0) throw Error("not an r1cs file");
+    if (u32(4) != 1) throw Error("unsupported r1cs version");
+    uint32_t nsec = u32(8);
+    size_t pos = 12;
+    size_t sec_pos[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t sec_len[6] = {0, 0, 0, 0, 0, 0};
+    bool have[6] = {false, false, false, false, false, false};
+    for (uint32_t s = 0; s < nsec; s++) {
+        uint32_t typ = u32(pos);
+        uint64_t len = u64(pos + 4);
+        pos += 12;
+        need(pos, len);
+        if (typ < 6) { sec_pos[typ] = pos; sec_len[typ] = len; have[typ] = true; }
+        pos += len;
+    }
+    if (!have[1] || !have[2]) throw Error("r1cs file lacks header or constraint section");
+    File out;
+    size_t hp = sec_pos[1];
+    out.field_size = u32(hp);
+    if (out.field_size != 32) throw Error("only 32-byte fields (bn128) are supported");
+    static const uint8_t qle[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                                    0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+    need(hp + 4, 32);
+    if (memcmp(&d[hp + 4], qle, 32) != 0) throw Error("r1cs prime is not bn128");
+    size_t q = hp + 4 + 32;
+    out.n_wires = u32(q);
+    out.n_pub_out = u32(q + 4);
+    out.n_pub_in = u32(q + 8);
+    out.n_prv_in = u32(q + 12);
+    out.n_labels = u64(q + 16);
+    out.n_constraints = u32(q + 24);
+    if (have[4] || have[5]) throw Error("custom-gate sections are not supported");
+
+    std::unordered_map<fr::Fr, uint32_t, tape::FrHash, tape::FrEq> index;
+    fr::Fr one = fr::zero();
+    one.v[0] = 1;
+    fr::Fr minus_one = fr::neg(one);
+    out.coefs.push_back(one);
+    out.coefs.push_back(minus_one);
+    index.emplace(one, 0);
+    index.emplace(minus_one, 1);
+
+    size_t p = sec_pos[2], end = sec_pos[2] + sec_len[2];
+    out.ptr.reserve((size_t)out.n_constraints * 3 + 1);
+    out.ptr.push_back(0);
+    for (uint32_t c = 0; c < out.n_constraints; c++) {
+        for (int k = 0; k < 3; k++) {
+            uint32_t n = u32(p);
+            p += 4;
+            for (uint32_t t = 0; t < n; t++) {
+                uint32_t wire = u32(p);
+                need(p + 4, 32);
+                fr::Fr v;
+                memcpy(v.v, &d[p + 4], 32);
+                p += 36;
+                if (wire >= out.n_wires) throw Error("r1cs term refers to a wire out of range");
+                if (!fr::gt_raw(fr::modulus(), v)) throw Error("r1cs coefficient is not reduced");
+                auto it = index.find(v);
+                uint32_t ci;
+                if (it == index.end()) {
+                    ci = (uint32_t)out.coefs.size();
+                    out.coefs.push_back(v);
+                    index.emplace(v, ci);
+                } else ci = it->second;
+                if (ci < 2) out.nnz_pm1++;
+                if (fr::is_zero(v)) continue;
+                out.terms.push_back(Term{wire, ci});
+            }
+            out.ptr.push_back((uint32_t)out.terms.size());
+        }
+    }
+    if (p > end) throw Error("constraint section overrun");
+    if (have[3]) {
+        size_t wp = sec_pos[3];
+        for (uint64_t i = 0; i < sec_len[3] / 8; i++) out.wire2label.push_back(u64(wp + 8 * i));
+    }
+    return out;
+}
+
+}  // namespace r1cs

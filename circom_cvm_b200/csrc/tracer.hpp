@@ -1,0 +1,697 @@
+// Trace-compiler: runs the CVM program ONCE on the host with abstract values and leaves a flat,
+// address-resolved SSA tape of field operations for the GPU.
+//
+// Why this is sound: the component tree, signal offsets, loop trip counts and array indices of a
+// circom program depend only on template parameters, which the compiler already resolved to
+// literals (template.rs:240-290, create_component_bucket.rs:221-350) -- so everything except
+// arithmetic on *signal values* is identical for every witness of a batch and is evaluated here.
+// What the reference's generated C++ does per witness (generated `T_run` bodies: template.rs:334-407;
+// sub-component triggering: store_bucket.rs:662-800; calls: call_bucket.rs:465-534) is replayed
+// with three kinds of values: known i64 (addresses/counters), known field constants, and dynamic
+// values (SSA ids).  Data-dependent `if`s are if-converted (both arms traced, writes merged with SEL);
+// data-dependent loops / returns / addresses are rejected with a clear error.
+//
+// Asserts: `c = ff.eqz v; if c; error 0; end` (assert_bucket.rs:88-107) becomes FAIL_IF(c).  The
+// `===` half of every `<==` recomputes the stored expression (translate.rs:676-734); value numbering
+// makes that `ff.eq x x`, which folds to 1, so those asserts vanish -- they can never fail.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <deque>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "cvm_parse.hpp"
+#include "host_fr.hpp"
+
+namespace tape {
+
+enum TOp : uint8_t {
+    T_NOP = 0, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR,
+    T_BNOT, T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF,
+    // inserted by the allocator
+    T_LD, T_ST, T_STC, T_COUNT
+};
+
+static const uint32_t CONST_FLAG = 0x80000000u;
+static const uint32_t NO_REF = 0xffffffffu;
+
+enum Status : uint32_t { ST_OK = 0, ST_ASSERT = 1, ST_TOINT = 2, ST_DIVZERO = 3, ST_INPUT = 4 };
+
+struct SOp {
+    uint8_t op;
+    uint32_t a, b, c;   // refs: CONST_FLAG | const index, or value id (= index of the producing SOp)
+    uint32_t aux;       // T_INPUT: input index; T_FAIL_IF: status code
+};
+
+struct TraceError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct TraceStats {
+    uint64_t cvm_instructions = 0;   // CVM instructions executed on the host
+    uint64_t ref_mul = 0;            // dynamic ff.mul (+1 per ff.div) the reference program executes: N_mul
+    uint64_t ref_div = 0;
+    uint64_t ref_field_ops = 0;      // all ff.* executions of the reference program
+    uint64_t folded = 0, cse_hits = 0;
+    uint64_t dyn_branches = 0;
+    uint64_t unset_signal_reads = 0;
+};
+
+struct FrHash {
+    size_t operator()(const fr::Fr &f) const {
+        uint64_t h = 1469598103934665603ull;
+        for (int i = 0; i < 8; i++) h = (h ^ f.v[i]) * 1099511628211ull;
+        return (size_t)h;
+    }
+};
+struct FrEq {
+    bool operator()(const fr::Fr &a, const fr::Fr &b) const { return fr::equal(a, b); }
+};
+
+class Tracer {
+  public:
+    enum { AV_UNDEF = 0, AV_I64, AV_FF, AV_DYN };
+    struct AV {
+        uint8_t kind = AV_UNDEF;
+        int64_t i = 0;
+        uint32_t ref = 0;   // AV_FF: const index ; AV_DYN: value id
+    };
+
+    std::vector<SOp> ops;
+    std::vector<fr::Fr> consts;   // canonical
+    std::vector<uint32_t> witness_ref;   // per witness wire: ref (const or value)
+    TraceStats stats;
+    int64_t n_inputs = 0, n_outputs = 0;
+
+    explicit Tracer(const cvm::Program &p) : prog(p) {
+        ffmap.resize(p.ffconst.size(), NO_REF);
+        c_zero = intern(fr::zero());
+        c_one = intern(hostfr::from_u64(1));
+    }
+
+    void trace() {
+        const cvm::Code &mainc = prog.codes[prog.start];
+        sig.assign((size_t)prog.n_signals, AV());
+        sig[0] = ff_av(c_one);                               // calcwit.cpp:34
+        n_inputs = mainc.n_inputs;
+        n_outputs = mainc.n_outputs;
+        int main_idx = new_comp(prog.start, 1);              // circuit.rs:539: main at signal 1
+        for (int64_t k = 0; k < n_inputs; k++) {             // main inputs follow main outputs (App. A.5)
+            SOp o{T_INPUT, NO_REF, NO_REF, NO_REF, (uint32_t)k};
+            ops.push_back(o);
+            AV v;
+            v.kind = AV_DYN;
+            v.ref = (uint32_t)ops.size() - 1;
+            sig[(size_t)(1 + n_outputs + k)] = v;
+        }
+        run_component(main_idx);
+        witness_ref.clear();
+        for (int64_t s : prog.witness) {
+            if (s < 0 || s >= prog.n_signals) throw TraceError("witness list refers to signal out of range");
+            witness_ref.push_back(field_ref(sig[(size_t)s]));
+        }
+    }
+
+  private:
+    struct Frame {
+        std::vector<AV> regs;
+        std::unordered_map<int64_t, AV> lvar;
+    };
+    struct Comp {
+        int code;
+        int64_t start;
+        int64_t counter;
+        std::vector<int> subs;
+    };
+    struct LogEntry {
+        uint8_t space;   // 0 reg, 1 lvar, 2 signal
+        Frame *frame;
+        int64_t key;
+        AV old;
+        bool existed;
+    };
+    struct RetTarget {
+        Frame *frame;
+        int64_t addr, size;
+        size_t pred_depth;
+    };
+
+    const cvm::Program &prog;
+    std::vector<AV> sig;
+    std::deque<Comp> comps;
+    std::vector<uint32_t> ffmap;
+    std::unordered_map<fr::Fr, uint32_t, FrHash, FrEq> const_index;
+    std::unordered_map<uint64_t, std::vector<uint32_t>> cse;
+    std::vector<std::vector<LogEntry>> logs;
+    std::vector<uint32_t> preds;   // refs of enclosing data-dependent conditions (already "is true" predicates)
+    uint32_t c_zero, c_one;
+    int depth = 0;
+    static const int64_t SPR_BASE = (int64_t)1 << 40;
+
+    // ---------------------------------------------------------------- constants / values
+    uint32_t intern(const fr::Fr &v) {
+        auto it = const_index.find(v);
+        if (it != const_index.end()) return it->second;
+        uint32_t id = (uint32_t)consts.size();
+        consts.push_back(v);
+        const_index.emplace(v, id);
+        return id;
+    }
+    static AV i64_av(int64_t x) {
+        AV v;
+        v.kind = AV_I64;
+        v.i = x;
+        return v;
+    }
+    static AV ff_av(uint32_t cidx) {
+        AV v;
+        v.kind = AV_FF;
+        v.ref = cidx;
+        return v;
+    }
+    static AV dyn_av(uint32_t id) {
+        AV v;
+        v.kind = AV_DYN;
+        v.ref = id;
+        return v;
+    }
+    AV ref_av(uint32_t ref) { return (ref & CONST_FLAG) ? ff_av(ref & ~CONST_FLAG) : dyn_av(ref); }
+
+    // field view of an abstract value -> ref
+    uint32_t field_ref(const AV &v) {
+        switch (v.kind) {
+            case AV_I64: return CONST_FLAG | intern(hostfr::from_i64(v.i));
+            case AV_FF: return CONST_FLAG | v.ref;
+            case AV_DYN: return v.ref;
+            default: stats.unset_signal_reads++; return CONST_FLAG | c_zero;
+        }
+    }
+    // integer view (addresses, counters); data-dependent addressing is not traceable
+    int64_t int_of(const AV &v, const char *what) {
+        if (v.kind == AV_I64) return v.i;
+        if (v.kind == AV_FF) {
+            int32_t out;
+            if (!fr::to_int(consts[v.ref], out))
+                throw TraceError(std::string("field constant does not fit an address (") + what + ")");
+            return out;
+        }
+        if (v.kind == AV_DYN)
+            throw TraceError(std::string("data-dependent ") + what + " is not supported by the trace compiler");
+        return 0;
+    }
+
+    // ---------------------------------------------------------------- SSA emission
+    static bool commutative(uint8_t op) {
+        return op == T_ADD || op == T_MUL || op == T_EQ || op == T_NEQ || op == T_BAND || op == T_BOR ||
+               op == T_BXOR || op == T_LAND || op == T_LOR;
+    }
+    static hostfr::FfOp host_op(uint8_t op) {
+        switch (op) {
+            case T_ADD: return hostfr::F_ADD; case T_SUB: return hostfr::F_SUB; case T_MUL: return hostfr::F_MUL;
+            case T_DIV: return hostfr::F_DIV; case T_IDIV: return hostfr::F_IDIV; case T_MOD: return hostfr::F_MOD;
+            case T_POW: return hostfr::F_POW; case T_SHL: return hostfr::F_SHL; case T_SHR: return hostfr::F_SHR;
+            case T_BAND: return hostfr::F_BAND; case T_BOR: return hostfr::F_BOR; case T_BXOR: return hostfr::F_BXOR;
+            case T_BNOT: return hostfr::F_BNOT; case T_LT: return hostfr::F_LT; case T_LE: return hostfr::F_LE;
+            case T_GT: return hostfr::F_GT; case T_GE: return hostfr::F_GE; case T_EQ: return hostfr::F_EQ;
+            case T_NEQ: return hostfr::F_NEQ; case T_LAND: return hostfr::F_LAND; case T_LOR: return hostfr::F_LOR;
+            case T_EQZ: return hostfr::F_EQZ; default: return hostfr::F_NONE;
+        }
+    }
+    bool is_const(uint32_t r) const { return r != NO_REF && (r & CONST_FLAG); }
+    const fr::Fr &cval(uint32_t r) const { return consts[r & ~CONST_FLAG]; }
+
+    uint32_t emit(uint8_t op, uint32_t a, uint32_t b = NO_REF, uint32_t c = NO_REF, uint32_t aux = 0) {
+        bool unary = (b == NO_REF);
+        if (op != T_SEL && op != T_FAIL_IF && is_const(a) && (unary || is_const(b))) {
+            fr::Fr out;
+            fr::Fr bb = unary ? fr::zero() : cval(b);
+            if (hostfr::apply(host_op(op), cval(a), bb, out)) {
+                stats.folded++;
+                return CONST_FLAG | intern(out);
+            }
+            if (op == T_DIV) return CONST_FLAG | c_zero;   // mpz_invert(0): undefined in the reference; we define 0
+            throw TraceError("integer division or modulo by a constant zero");
+        }
+        uint32_t zero = CONST_FLAG | c_zero, one = CONST_FLAG | c_one;
+        switch (op) {
+            case T_ADD:
+                if (a == zero) return b;
+                if (b == zero) return a;
+                break;
+            case T_SUB:
+                if (b == zero) return a;
+                if (a == b) return zero;
+                break;
+            case T_MUL:
+                if (a == zero || b == zero) return zero;
+                if (a == one) return b;
+                if (b == one) return a;
+                break;
+            case T_EQ:
+                if (a == b) return one;
+                break;
+            case T_NEQ:
+                if (a == b) return zero;
+                break;
+            case T_SEL:
+                if (b == c) return b;
+                if (is_const(a)) return fr::is_zero(cval(a)) ? c : b;
+                break;
+            case T_FAIL_IF:
+                if (is_const(a) && fr::is_zero(cval(a))) return NO_REF;
+                break;
+            default: break;
+        }
+        if (commutative(op) && a > b) std::swap(a, b);
+        uint64_t key = ((uint64_t)op << 56) ^ ((uint64_t)a * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)b * 0xC2B2AE3D27D4EB4Full) ^
+                       ((uint64_t)c * 0x165667B19E3779F9ull) ^ aux;
+        auto &bucket = cse[key];
+        for (uint32_t id : bucket) {
+            const SOp &o = ops[id];
+            if (o.op == op && o.a == a && o.b == b && o.c == c && o.aux == aux) {
+                stats.cse_hits++;
+                return id;
+            }
+        }
+        SOp o{op, a, b, c, aux};
+        ops.push_back(o);
+        uint32_t id = (uint32_t)ops.size() - 1;
+        bucket.push_back(id);
+        return id;
+    }
+
+    // ---------------------------------------------------------------- logged state writes
+    void log_write(uint8_t space, Frame *f, int64_t key, const AV &old, bool existed) {
+        if (!logs.empty()) logs.back().push_back(LogEntry{space, f, key, old, existed});
+    }
+    void set_reg(Frame &f, int r, const AV &v) {
+        log_write(0, &f, r, f.regs[(size_t)r], true);
+        f.regs[(size_t)r] = v;
+    }
+    void set_lvar(Frame &f, int64_t addr, const AV &v) {
+        auto it = f.lvar.find(addr);
+        if (it == f.lvar.end()) {
+            log_write(1, &f, addr, AV(), false);
+            f.lvar.emplace(addr, v);
+        } else {
+            log_write(1, &f, addr, it->second, true);
+            it->second = v;
+        }
+    }
+    void set_sig(int64_t idx, const AV &v) {
+        if (idx < 0 || idx >= (int64_t)sig.size()) throw TraceError("signal index out of range");
+        log_write(2, nullptr, idx, sig[(size_t)idx], true);
+        sig[(size_t)idx] = v;
+    }
+    AV read_loc(const LogEntry &e) {
+        if (e.space == 0) return e.frame->regs[(size_t)e.key];
+        if (e.space == 1) {
+            auto it = e.frame->lvar.find(e.key);
+            return it == e.frame->lvar.end() ? AV() : it->second;
+        }
+        return sig[(size_t)e.key];
+    }
+    void restore(const LogEntry &e) {
+        if (e.space == 0) e.frame->regs[(size_t)e.key] = e.old;
+        else if (e.space == 1) {
+            if (e.existed) e.frame->lvar[e.key] = e.old;
+            else e.frame->lvar.erase(e.key);
+        } else sig[(size_t)e.key] = e.old;
+    }
+    void write_loc(const LogEntry &e, const AV &v) {
+        if (e.space == 0) set_reg(*e.frame, (int)e.key, v);
+        else if (e.space == 1) set_lvar(*e.frame, e.key, v);
+        else set_sig(e.key, v);
+    }
+
+    // ---------------------------------------------------------------- operands
+    AV val(const Frame &f, const cvm::Operand &o) {
+        switch (o.kind) {
+            case cvm::K_REG: return f.regs[(size_t)o.val];
+            case cvm::K_I64: return i64_av(o.val);
+            case cvm::K_FF: {
+                uint32_t &m = ffmap[(size_t)o.val];
+                if (m == NO_REF) m = intern(prog.ffconst[(size_t)o.val]);
+                return ff_av(m);
+            }
+            case cvm::K_SPR: return i64_av(SPR_BASE);
+            default: throw TraceError("call-argument operand used as a value");
+        }
+    }
+    AV simple(const Frame &f, uint8_t kind, int64_t v) {
+        cvm::Operand o;
+        o.kind = kind;
+        o.val = v;
+        return val(f, o);
+    }
+    bool truth_known(const AV &v, bool &t) {
+        if (v.kind == AV_I64) { t = v.i != 0; return true; }
+        if (v.kind == AV_FF) { t = !fr::is_zero(consts[v.ref]); return true; }
+        if (v.kind == AV_UNDEF) { t = false; return true; }
+        return false;
+    }
+
+    // ---------------------------------------------------------------- components
+    int new_comp(int code, int64_t start) {
+        Comp c;
+        c.code = code;
+        c.start = start;
+        c.counter = prog.codes[(size_t)code].n_inputs;
+        c.subs.assign((size_t)prog.codes[(size_t)code].n_subcmps, -1);
+        comps.push_back(c);
+        return (int)comps.size() - 1;
+    }
+    void run_component(int ci) {
+        const cvm::Code &code = prog.codes[(size_t)comps[(size_t)ci].code];
+        Frame f;
+        f.regs.assign((size_t)code.nregs, AV());
+        if (++depth > 4000) throw TraceError("component/function nesting too deep");
+        run(code, f, ci, 0, (int)code.ins.size(), 0, nullptr);
+        depth--;
+    }
+    Comp &sub_of(int ci, const AV &slotv) {
+        int64_t slot = int_of(slotv, "sub-component index");
+        Comp &c = comps[(size_t)ci];
+        if (slot < 0 || slot >= (int64_t)c.subs.size() || c.subs[(size_t)slot] < 0)
+            throw TraceError("access to a sub-component that was never created (slot " + std::to_string(slot) +
+                             " of " + prog.codes[(size_t)c.code].header + ")");
+        return comps[(size_t)c.subs[(size_t)slot]];
+    }
+
+    uint32_t pred_conj() {
+        uint32_t p = preds[0];
+        for (size_t k = 1; k < preds.size(); k++) p = emit(T_LAND, p, preds[k]);
+        return p;
+    }
+
+    static uint8_t tape_op(uint16_t op) {
+        switch (op) {
+            case cvm::OP_FF_ADD: return T_ADD; case cvm::OP_FF_SUB: return T_SUB; case cvm::OP_FF_MUL: return T_MUL;
+            case cvm::OP_FF_DIV: return T_DIV; case cvm::OP_FF_IDIV: return T_IDIV; case cvm::OP_FF_REM: return T_MOD;
+            case cvm::OP_FF_POW: return T_POW; case cvm::OP_FF_SHL: return T_SHL; case cvm::OP_FF_SHR: return T_SHR;
+            case cvm::OP_FF_BAND: return T_BAND; case cvm::OP_FF_BOR: return T_BOR; case cvm::OP_FF_BXOR: return T_BXOR;
+            case cvm::OP_FF_BNOT: return T_BNOT; case cvm::OP_FF_LT: return T_LT; case cvm::OP_FF_LE: return T_LE;
+            case cvm::OP_FF_GT: return T_GT; case cvm::OP_FF_GE: return T_GE; case cvm::OP_FF_EQ: return T_EQ;
+            case cvm::OP_FF_NEQ: return T_NEQ; case cvm::OP_FF_AND: return T_LAND; case cvm::OP_FF_OR: return T_LOR;
+            case cvm::OP_FF_EQZ: return T_EQZ; default: return T_NOP;
+        }
+    }
+
+    // ---------------------------------------------------------------- the interpreter
+    // executes ins[pc, stop) of `code`; returns true when a `return` was executed
+    bool run(const cvm::Code &code, Frame &f, int ci, int pc, int stop, int range_begin, const RetTarget *ret) {
+        using namespace cvm;
+        while (pc < stop) {
+            const Ins &in = code.ins[(size_t)pc];
+            stats.cvm_instructions++;
+            switch (in.op) {
+                case OP_MOV: set_reg(f, in.dst, val(f, in.args[0])); pc++; break;
+                case OP_FF_ADD: case OP_FF_SUB: case OP_FF_MUL: case OP_FF_DIV: case OP_FF_IDIV: case OP_FF_REM:
+                case OP_FF_POW: case OP_FF_SHL: case OP_FF_SHR: case OP_FF_BAND: case OP_FF_BOR: case OP_FF_BXOR:
+                case OP_FF_LT: case OP_FF_LE: case OP_FF_GT: case OP_FF_GE: case OP_FF_EQ: case OP_FF_NEQ:
+                case OP_FF_AND: case OP_FF_OR: {
+                    stats.ref_field_ops++;
+                    if (in.op == OP_FF_MUL) stats.ref_mul++;
+                    if (in.op == OP_FF_DIV) { stats.ref_mul++; stats.ref_div++; }
+                    uint32_t a = field_ref(val(f, in.args.at(0))), b = field_ref(val(f, in.args.at(1)));
+                    set_reg(f, in.dst, ref_av(emit(tape_op(in.op), a, b)));
+                    pc++;
+                    break;
+                }
+                case OP_FF_BNOT: case OP_FF_EQZ: {
+                    stats.ref_field_ops++;
+                    uint32_t a = field_ref(val(f, in.args.at(0)));
+                    set_reg(f, in.dst, ref_av(emit(tape_op(in.op), a)));
+                    pc++;
+                    break;
+                }
+                case OP_FF_WRAP_I64: {
+                    AV v = val(f, in.args.at(0));
+                    set_reg(f, in.dst, i64_av(int_of(v, "array index (ff.wrap_i64)")));
+                    pc++;
+                    break;
+                }
+                case OP_I64_ADD: case OP_I64_SUB: case OP_I64_MUL: case OP_I64_LT: case OP_I64_LE: case OP_I64_GT:
+                case OP_I64_GE: case OP_I64_EQ: case OP_I64_NEQ: {
+                    int64_t a = int_of(val(f, in.args.at(0)), "i64 operand"), b = int_of(val(f, in.args.at(1)), "i64 operand");
+                    int64_t r = 0;
+                    switch (in.op) {
+                        case OP_I64_ADD: r = a + b; break; case OP_I64_SUB: r = a - b; break;
+                        case OP_I64_MUL: r = a * b; break; case OP_I64_LT: r = a < b; break;
+                        case OP_I64_LE: r = a <= b; break; case OP_I64_GT: r = a > b; break;
+                        case OP_I64_GE: r = a >= b; break; case OP_I64_EQ: r = a == b; break;
+                        default: r = a != b; break;
+                    }
+                    set_reg(f, in.dst, i64_av(r));
+                    pc++;
+                    break;
+                }
+                case OP_FF_LOAD: {
+                    int64_t addr = int_of(val(f, in.args.at(0)), "variable address");
+                    auto it = f.lvar.find(addr);
+                    set_reg(f, in.dst, it == f.lvar.end() ? ff_av(c_zero) : it->second);
+                    pc++;
+                    break;
+                }
+                case OP_FF_STORE: {
+                    int64_t addr = int_of(val(f, in.args.at(0)), "variable address");
+                    set_lvar(f, addr, ref_av(field_ref(val(f, in.args.at(1)))));
+                    pc++;
+                    break;
+                }
+                case OP_GET_SIGNAL: {
+                    int64_t idx = comps[(size_t)ci].start + int_of(val(f, in.args.at(0)), "signal index");
+                    if (idx < 0 || idx >= (int64_t)sig.size()) throw TraceError("signal index out of range");
+                    set_reg(f, in.dst, ref_av(field_ref(sig[(size_t)idx])));
+                    pc++;
+                    break;
+                }
+                case OP_SET_SIGNAL: {
+                    int64_t idx = comps[(size_t)ci].start + int_of(val(f, in.args.at(0)), "signal index");
+                    set_sig(idx, ref_av(field_ref(val(f, in.args.at(1)))));
+                    pc++;
+                    break;
+                }
+                case OP_GET_CMP_SIGNAL: {
+                    Comp &s = sub_of(ci, val(f, in.args.at(0)));
+                    int64_t idx = s.start + int_of(val(f, in.args.at(1)), "signal index");
+                    if (idx < 0 || idx >= (int64_t)sig.size()) throw TraceError("signal index out of range");
+                    set_reg(f, in.dst, ref_av(field_ref(sig[(size_t)idx])));
+                    pc++;
+                    break;
+                }
+                case OP_SET_CMP_INPUT: case OP_SET_CMP_INPUT_CNT: case OP_SET_CMP_INPUT_RUN:
+                case OP_SET_CMP_INPUT_CNT_CHECK: {
+                    if (!preds.empty())
+                        throw TraceError("sub-component input assigned under a data-dependent condition");
+                    AV slotv = val(f, in.args.at(0));
+                    Comp &s = sub_of(ci, slotv);
+                    int sidx = comps[(size_t)ci].subs[(size_t)int_of(slotv, "sub-component index")];
+                    set_sig(s.start + int_of(val(f, in.args.at(1)), "signal index"),
+                            ref_av(field_ref(val(f, in.args.at(2)))));
+                    // inputCounter / run rules: store_bucket.rs:662-800
+                    if (in.op == OP_SET_CMP_INPUT_CNT) s.counter -= 1;
+                    else if (in.op == OP_SET_CMP_INPUT_RUN) run_component(sidx);
+                    else if (in.op == OP_SET_CMP_INPUT_CNT_CHECK) {
+                        s.counter -= 1;
+                        if (s.counter == 0) run_component(sidx);
+                    }
+                    pc++;
+                    break;
+                }
+                case OP_CREATE_CMP: {
+                    if (!preds.empty()) throw TraceError("component created under a data-dependent condition");
+                    // create_component_bucket.rs:206-354: slot k -> signalStart = mine + off + k*jump
+                    const cvm::Code &tc = prog.codes[(size_t)in.target];
+                    for (int64_t k = 0; k < in.cc[5]; k++) {
+                        int sidx = new_comp(in.target, comps[(size_t)ci].start + in.cc[1] + k * in.cc[2]);
+                        int64_t slot = in.cc[0] + k;
+                        if (slot < 0 || slot >= (int64_t)comps[(size_t)ci].subs.size())
+                            throw TraceError("create_cmp slot out of range in " + code.header);
+                        comps[(size_t)ci].subs[(size_t)slot] = sidx;
+                        if (tc.n_inputs == 0) run_component(sidx);   // template.rs:326-331
+                    }
+                    pc++;
+                    break;
+                }
+                case OP_IF: {
+                    AV c = val(f, in.args.at(0));
+                    bool t;
+                    int then_end = in.m_else >= 0 ? in.m_else : in.m_end;
+                    if (truth_known(c, t)) {
+                        pc = t ? pc + 1 : (in.m_else >= 0 ? in.m_else + 1 : in.m_end + 1);
+                        break;
+                    }
+                    // assert shape: if c / error n / end  -> FAIL_IF without opening a region
+                    if (in.m_else < 0 && in.m_end == pc + 2 && code.ins[(size_t)pc + 1].op == OP_ERROR) {
+                        uint32_t p = c.ref;
+                        if (!preds.empty()) p = emit(T_LAND, pred_conj(), p);
+                        emit(T_FAIL_IF, p, NO_REF, NO_REF, ST_ASSERT);
+                        pc = in.m_end + 1;
+                        break;
+                    }
+                    stats.dyn_branches++;
+                    dynamic_if(code, f, ci, pc, then_end, in, c.ref, ret);
+                    pc = in.m_end + 1;
+                    break;
+                }
+                case OP_ELSE: pc = in.m_end + 1; break;    // fell off the end of a then-branch
+                case OP_END: pc++; break;                  // end of if, or falling out of a loop
+                case OP_LOOP: pc++; break;
+                case OP_CONTINUE:
+                    if (in.m_loop < range_begin) throw TraceError("continue under a data-dependent condition");
+                    pc = in.m_loop + 1;
+                    break;
+                case OP_BREAK: {
+                    if (in.m_loop < range_begin) throw TraceError("break under a data-dependent condition");
+                    pc = code.ins[(size_t)in.m_loop].m_end + 1;
+                    break;
+                }
+                case OP_ERROR: {
+                    uint32_t p = preds.empty() ? (CONST_FLAG | c_one) : pred_conj();
+                    // an unconditional error is a program that fails for every input; keep it as a flag
+                    SOp o{T_FAIL_IF, p, NO_REF, NO_REF, ST_ASSERT};
+                    ops.push_back(o);
+                    pc++;
+                    break;
+                }
+                case OP_CALL: call(code, f, ci, in); pc++; break;
+                case OP_RETURN: {
+                    if (!ret) throw TraceError("return outside a function");
+                    if (preds.size() != ret->pred_depth) throw TraceError("return under a data-dependent condition");
+                    if (in.scalar_return) {
+                        set_lvar(*ret->frame, ret->addr, ref_av(field_ref(val(f, in.args.at(0)))));
+                    } else {
+                        int64_t src = int_of(val(f, in.args.at(0)), "return address");
+                        int64_t n = std::min(int_of(val(f, in.args.at(1)), "return size"), ret->size);
+                        for (int64_t k = 0; k < n; k++) {
+                            auto it = f.lvar.find(src + k);
+                            set_lvar(*ret->frame, ret->addr + k, it == f.lvar.end() ? ff_av(c_zero) : it->second);
+                        }
+                    }
+                    return true;
+                }
+                case OP_MAPPED_UNSUPPORTED:
+                    throw TraceError("mapped accesses (mixed component arrays / buses) need the io-map, which the "
+                                     ".cvm file does not carry (reference circuit.rs:577-621)");
+                default: throw TraceError("unhandled CVM instruction");
+            }
+        }
+        return false;
+    }
+
+    void dynamic_if(const cvm::Code &code, Frame &f, int ci, int pc, int then_end, const cvm::Ins &in, uint32_t cond,
+                    const RetTarget *ret) {
+        // then-arm
+        logs.emplace_back();
+        preds.push_back(cond);
+        if (run(code, f, ci, pc + 1, then_end, pc + 1, ret)) throw TraceError("return under a data-dependent condition");
+        preds.pop_back();
+        std::vector<LogEntry> logT = std::move(logs.back());
+        logs.pop_back();
+        // collect final values of the then-arm, keep first-old per location, roll back
+        struct Merge { LogEntry first; AV vT; bool inT; AV vE; bool inE; };
+        std::vector<Merge> merges;
+        std::unordered_map<uint64_t, size_t> index;
+        auto keyof = [](const LogEntry &e) {
+            return ((uint64_t)e.space << 62) ^ ((uint64_t)(uintptr_t)e.frame * 0x9E3779B97F4A7C15ull) ^ (uint64_t)e.key * 0xC2B2AE3D27D4EB4Full;
+        };
+        auto same = [](const LogEntry &a, const LogEntry &b) { return a.space == b.space && a.frame == b.frame && a.key == b.key; };
+        auto slot_for = [&](const LogEntry &e) -> size_t {
+            uint64_t k = keyof(e);
+            auto it = index.find(k);
+            while (it != index.end() && !same(merges[it->second].first, e)) { k = k * 31 + 7; it = index.find(k); }
+            if (it != index.end()) return it->second;
+            merges.push_back(Merge{e, AV(), false, AV(), false});
+            index.emplace(k, merges.size() - 1);
+            return merges.size() - 1;
+        };
+        for (auto &e : logT) {
+            size_t s = slot_for(e);
+            if (!merges[s].inT) { merges[s].inT = true; merges[s].vT = read_loc(e); }
+        }
+        for (size_t k = logT.size(); k-- > 0;) restore(logT[k]);
+        // else-arm
+        logs.emplace_back();
+        if (in.m_else >= 0) {
+            preds.push_back(emit(T_EQZ, cond));
+            if (run(code, f, ci, in.m_else + 1, in.m_end, in.m_else + 1, ret))
+                throw TraceError("return under a data-dependent condition");
+            preds.pop_back();
+        }
+        std::vector<LogEntry> logE = std::move(logs.back());
+        logs.pop_back();
+        for (auto &e : logE) {
+            size_t s = slot_for(e);
+            if (!merges[s].inE) { merges[s].inE = true; merges[s].vE = read_loc(e); }
+        }
+        for (size_t k = logE.size(); k-- > 0;) restore(logE[k]);
+        // merge (writes are logged by the enclosing region, if any, against the pre-branch values)
+        for (auto &m : merges) {
+            AV before = read_loc(m.first);
+            AV vT = m.inT ? m.vT : before, vE = m.inE ? m.vE : before;
+            if (m.first.space == 0 && (vT.kind == AV_I64 || vE.kind == AV_I64 || vT.kind == AV_UNDEF || vE.kind == AV_UNDEF)) {
+                // registers are block-local temporaries; integer temporaries that differ cannot be merged, and
+                // are dead after the branch in emitted code.  Leave them undefined.
+                if (vT.kind == vE.kind && vT.i == vE.i && vT.ref == vE.ref) write_loc(m.first, vT);
+                else write_loc(m.first, AV());
+                continue;
+            }
+            uint32_t rT = field_ref(vT), rE = field_ref(vE);
+            write_loc(m.first, ref_av(emit(T_SEL, cond, rT, rE)));
+        }
+    }
+
+    void call(const cvm::Code &code, Frame &f, int ci, const cvm::Ins &in) {
+        using namespace cvm;
+        const cvm::Code &fn = prog.codes[(size_t)in.target];
+        if (!fn.is_function) throw TraceError("ff.call target is not a function");
+        RetTarget rt;
+        rt.frame = &f;
+        rt.addr = int_of(val(f, in.args.at(0)), "call destination");
+        rt.size = int_of(val(f, in.args.at(1)), "call destination size");
+        rt.pred_depth = preds.size();
+        Frame g;
+        g.regs.assign((size_t)fn.nregs, AV());
+        g.regs[(size_t)fn.reg_destination] = i64_av(rt.addr);
+        g.regs[(size_t)fn.reg_destination_size] = i64_av(rt.size);
+        int64_t pos = 0;   // arguments are packed consecutively into the callee's lvar (call_bucket.rs:478-515)
+        for (size_t k = 2; k < in.args.size(); k++) {
+            const Operand &o = in.args[k];
+            if (o.kind == K_ARG_MEM) {
+                int64_t base = int_of(simple(f, o.akind, o.aval), "argument address");
+                for (int64_t j = 0; j < o.n; j++) {
+                    auto it = f.lvar.find(base + j);
+                    g.lvar[pos + j] = it == f.lvar.end() ? ff_av(c_zero) : it->second;
+                }
+                pos += o.n;
+            } else if (o.kind == K_ARG_SIG || o.kind == K_ARG_SUBSIG) {
+                int64_t base;
+                if (o.kind == K_ARG_SIG) base = comps[(size_t)ci].start;
+                else base = sub_of(ci, simple(f, o.ckind, o.cval)).start;
+                base += int_of(simple(f, o.akind, o.aval), "argument address");
+                for (int64_t j = 0; j < o.n; j++) {
+                    if (base + j < 0 || base + j >= (int64_t)sig.size()) throw TraceError("signal index out of range");
+                    g.lvar[pos + j] = ref_av(field_ref(sig[(size_t)(base + j)]));
+                }
+                pos += o.n;
+            } else {
+                g.lvar[pos++] = ref_av(field_ref(val(f, o)));
+            }
+        }
+        if (++depth > 4000) throw TraceError("component/function nesting too deep");
+        run(fn, g, ci, 0, (int)fn.ins.size(), 0, &rt);
+        depth--;
+        // the callee frame dies here: drop undo-log entries that point into it
+        if (!logs.empty()) {
+            auto &L = logs.back();
+            L.erase(std::remove_if(L.begin(), L.end(), [&](const LogEntry &e) { return e.frame == &g; }), L.end());
+        }
+        (void)code;
+    }
+};
+
+}  // namespace tape

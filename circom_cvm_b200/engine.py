@@ -1,0 +1,292 @@
+"""Python host side over the C ABI (include/cvmgpu.h) -- the ctypes twin of the Rust `extern "C"`
+binding the north star asks for (no Rust toolchain in this image).
+
+The classes mirror the reference runtime's objects for this path:
+
+  WitnessCalculator   <->  Circom_CalcWit + generated <circuit>.cpp   (common/calcwit.hpp:17-66)
+      .calculate(inputs)        setInputSignal(...)/run(ctx)   for B inputs at once
+      .write_wtns(path, row)    writeBinWitness                (common/main.cpp:286-332)
+  R1cs                <->  the .r1cs written by constraint_writers/src/r1cs_writer.rs
+      .check(witnesses)         (A.w)*(B.w) - C.w == 0 per constraint
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, compute calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_size_t, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcvmgpu.so")
+
+ST_OK, ST_ASSERT, ST_TOINT, ST_DIVZERO = 0, 1, 2, 3
+NO_BAD = 0xFFFFFFFF
+
+EXPORTS = [
+    "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
+    "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_info_get", "cvmgpu_program_free",
+    "cvmgpu_program_tape",
+    "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_dev", "cvmgpu_witness_export_dev", "cvmgpu_store_bytes",
+    "cvmgpu_wtns_write",
+    "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
+    "cvmgpu_witness_import_dev",
+    "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak",
+]
+
+
+class CvmGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cvmgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ProgramInfo(ctypes.Structure):
+    _fields_ = [("n_signals", c_uint64), ("n_wires", c_uint32), ("n_inputs", c_uint32), ("n_outputs", c_uint32),
+                ("n_slots", c_uint32), ("n_rows", c_uint32), ("tape_len", c_uint64), ("ref_mul", c_uint64),
+                ("ref_field_ops", c_uint64), ("cvm_instructions", c_uint64), ("tape_mul", c_uint64),
+                ("tape_div", c_uint64), ("tape_addsub", c_uint64), ("tape_other", c_uint64), ("tape_ld", c_uint64),
+                ("tape_st", c_uint64), ("tape_spill_st", c_uint64), ("n_consts", c_uint32), ("dyn_branches", c_uint32)]
+
+    def asdict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class R1csInfo(ctypes.Structure):
+    _fields_ = [("n_wires", c_uint32), ("n_pub_out", c_uint32), ("n_pub_in", c_uint32), ("n_prv_in", c_uint32),
+                ("n_constraints", c_uint32), ("n_labels", c_uint64), ("nnz", c_uint64), ("nnz_pm1", c_uint64),
+                ("n_coefs", c_uint32)]
+
+    def asdict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+def lib():
+    """Load csrc/libcvmgpu.so (built by circom_cvm_b200.build).  Raises if it is missing: the product
+    path never substitutes a CPU implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise CvmGpuError(-4, "CUDA library %s is not built; run `python -m circom_cvm_b200.build`" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.cvmgpu_last_error.restype = c_char_p
+    L.cvmgpu_program_load.argtypes = [c_char_p, c_uint32, POINTER(c_void_p)]
+    L.cvmgpu_program_load_text.argtypes = [c_char_p, c_size_t, c_uint32, POINTER(c_void_p)]
+    L.cvmgpu_program_info_get.argtypes = [c_void_p, POINTER(ProgramInfo)]
+    L.cvmgpu_program_free.argtypes = [c_void_p]
+    L.cvmgpu_program_free.restype = None
+    L.cvmgpu_program_tape.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
+    L.cvmgpu_witness_batch.argtypes = [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]
+    L.cvmgpu_witness_batch_checked.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_witness_batch_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_witness_export_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
+    L.cvmgpu_store_bytes.argtypes = [c_void_p, c_uint64]
+    L.cvmgpu_store_bytes.restype = c_size_t
+    L.cvmgpu_wtns_write.argtypes = [c_char_p, c_void_p, c_uint32]
+    L.cvmgpu_r1cs_load.argtypes = [c_char_p, POINTER(c_void_p)]
+    L.cvmgpu_r1cs_info_get.argtypes = [c_void_p, POINTER(R1csInfo)]
+    L.cvmgpu_r1cs_free.argtypes = [c_void_p]
+    L.cvmgpu_r1cs_free.restype = None
+    L.cvmgpu_r1cs_check.argtypes = [c_void_p, c_void_p, c_uint64, c_void_p]
+    L.cvmgpu_r1cs_check_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
+    L.cvmgpu_witness_import_dev.argtypes = [c_uint32, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
+    L.cvmgpu_fr_host_op.argtypes = [c_char_p, c_char_p, c_char_p, c_char_p]
+    L.cvmgpu_fr_device_op.argtypes = [c_char_p, c_void_p, c_void_p, c_void_p, c_uint64]
+    L.cvmgpu_imad_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
+    L.cvmgpu_set_device.argtypes = [c_int]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise CvmGpuError(rc, lib().cvmgpu_last_error().decode(errors="replace"))
+
+
+def device_count():
+    return int(lib().cvmgpu_device_count())
+
+
+def set_device(i):
+    _check(lib().cvmgpu_set_device(int(i)))
+
+
+def _ptr(x):
+    """host numpy array / bytes / torch tensor -> address"""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+def ints_to_le(rows, width):
+    """rows of python ints -> uint8 array [len(rows), width, 32]"""
+    out = np.zeros((len(rows), width, 32), dtype=np.uint8)
+    for i, r in enumerate(rows):
+        assert len(r) == width, "expected %d values per row, got %d" % (width, len(r))
+        buf = b"".join(int(v).to_bytes(32, "little") for v in r)
+        out[i] = np.frombuffer(buf, dtype=np.uint8).reshape(width, 32)
+    return out
+
+
+def le_to_ints(arr):
+    """uint8 array [..., 32] -> nested lists of python ints (first two dims)"""
+    a = np.ascontiguousarray(arr)
+    flat = a.reshape(-1, 32)
+    vals = [int.from_bytes(flat[i].tobytes(), "little") for i in range(flat.shape[0])]
+    if a.ndim == 3:
+        n = a.shape[1]
+        return [vals[i * n:(i + 1) * n] for i in range(a.shape[0])]
+    return vals
+
+
+class WitnessCalculator:
+    """Batched counterpart of the reference's generated witness calculator."""
+
+    def __init__(self, cvm_path=None, cvm_text=None, n_slots=0):
+        L = lib()
+        h = c_void_p()
+        if cvm_path is not None:
+            _check(L.cvmgpu_program_load(os.fsencode(cvm_path), n_slots, byref(h)))
+        else:
+            data = cvm_text.encode() if isinstance(cvm_text, str) else cvm_text
+            _check(L.cvmgpu_program_load_text(data, len(data), n_slots, byref(h)))
+        self._h = h
+        info = ProgramInfo()
+        _check(L.cvmgpu_program_info_get(self._h, byref(info)))
+        self.info = info
+        self.n_inputs = int(info.n_inputs)
+        self.n_wires = int(info.n_wires)
+        self.n_rows = int(info.n_rows)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cvmgpu_program_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host-buffer API (what a user of the reference's calculator would call)
+    def calculate(self, inputs, want_witness=True):
+        """inputs: uint8 array [B, n_inputs, 32] (LE canonical) or list of rows of ints.
+        Returns (witness uint8 [B, n_wires, 32] or None, status uint32 [B])."""
+        if not isinstance(inputs, np.ndarray):
+            inputs = ints_to_le(inputs, self.n_inputs)
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        B = inputs.shape[0]
+        assert inputs.size == B * self.n_inputs * 32, "input shape mismatch"
+        wt = np.empty((B, self.n_wires, 32), dtype=np.uint8) if want_witness else None
+        st = np.empty((B,), dtype=np.uint32)
+        _check(lib().cvmgpu_witness_batch(self._h, _ptr(inputs) if inputs.size else None, B, _ptr(wt), _ptr(st)))
+        return wt, st
+
+    def calculate_into(self, inputs, wtns_out, status_out, r1cs=None, first_bad_out=None):
+        """Same, with caller-provided (e.g. pinned torch) host buffers; with `r1cs` every witness is also
+        checked on the device and first_bad_out[b] receives the first violated constraint (NO_BAD = none)."""
+        B = status_out.shape[0]
+        _check(lib().cvmgpu_witness_batch_checked(self._h, r1cs._h if r1cs is not None else None, _ptr(inputs), B,
+                                                  _ptr(wtns_out), _ptr(status_out), _ptr(first_bad_out)))
+
+    def calculate_checked(self, inputs, r1cs):
+        """-> (witness [B, n_wires, 32], status [B], first_bad [B])"""
+        if not isinstance(inputs, np.ndarray):
+            inputs = ints_to_le(inputs, self.n_inputs)
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint8)
+        B = inputs.shape[0]
+        wt = np.empty((B, self.n_wires, 32), dtype=np.uint8)
+        st = np.empty((B,), dtype=np.uint32)
+        bad = np.empty((B,), dtype=np.uint32)
+        self.calculate_into(inputs, wt, st, r1cs, bad)
+        return wt, st, bad
+
+    # ---- device-buffer API (torch tensors on the current CUDA device)
+    def store_bytes(self, bstride):
+        return int(lib().cvmgpu_store_bytes(self._h, bstride))
+
+    def run_dev(self, d_inputs, B, bstride, d_store, d_status, stream=0):
+        _check(lib().cvmgpu_witness_batch_dev(self._h, _ptr(d_inputs), B, bstride, _ptr(d_store), _ptr(d_status), stream))
+
+    def export_dev(self, d_store, B, bstride, d_wtns, stream=0):
+        _check(lib().cvmgpu_witness_export_dev(self._h, _ptr(d_store), B, bstride, _ptr(d_wtns), stream))
+
+    def write_wtns(self, path, witness_row):
+        row = np.ascontiguousarray(witness_row, dtype=np.uint8)
+        _check(lib().cvmgpu_wtns_write(os.fsencode(path), _ptr(row), self.n_wires))
+
+    def tape(self):
+        """-> (numpy structured array of tape instructions, constants as python ints in Montgomery form)"""
+        ins, n, cs, nc = c_void_p(), c_uint64(), c_void_p(), c_uint32()
+        _check(lib().cvmgpu_program_tape(self._h, byref(ins), byref(n), byref(cs), byref(nc)))
+        dt = np.dtype([("op", "u1"), ("flags", "u1"), ("dst", "<u2"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
+        tape = np.frombuffer((ctypes.c_char * (n.value * 16)).from_address(ins.value), dtype=dt).copy() if n.value else np.zeros(0, dt)
+        raw = bytes((ctypes.c_char * (nc.value * 32)).from_address(cs.value)) if nc.value else b""
+        consts = [int.from_bytes(raw[i * 32:(i + 1) * 32], "little") for i in range(nc.value)]
+        return tape, consts
+
+
+class R1cs:
+    def __init__(self, path):
+        h = c_void_p()
+        _check(lib().cvmgpu_r1cs_load(os.fsencode(path), byref(h)))
+        self._h = h
+        info = R1csInfo()
+        _check(lib().cvmgpu_r1cs_info_get(self._h, byref(info)))
+        self.info = info
+        self.n_wires = int(info.n_wires)
+        self.n_constraints = int(info.n_constraints)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cvmgpu_r1cs_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, witnesses):
+        """witnesses: uint8 [B, n_wires, 32] canonical -> uint32 [B] first violated constraint (NO_BAD = satisfied)"""
+        w = np.ascontiguousarray(witnesses, dtype=np.uint8)
+        B = w.shape[0]
+        assert w.size == B * self.n_wires * 32
+        bad = np.empty((B,), dtype=np.uint32)
+        _check(lib().cvmgpu_r1cs_check(self._h, _ptr(w), B, _ptr(bad)))
+        return bad
+
+    def check_dev(self, d_store, B, bstride, d_first_bad, stream=0):
+        _check(lib().cvmgpu_r1cs_check_dev(self._h, _ptr(d_store), B, bstride, _ptr(d_first_bad), stream))
+
+
+def fr_host_op(op, a, b=0):
+    out = ctypes.create_string_buffer(32)
+    rc = lib().cvmgpu_fr_host_op(op.encode(), int(a).to_bytes(32, "little"), int(b).to_bytes(32, "little"), out)
+    if rc < 0:
+        _check(rc)
+    return int.from_bytes(out.raw, "little"), rc
+
+
+def fr_device_op(op, a_list, b_list):
+    n = len(a_list)
+    a = ints_to_le([a_list], n)[0]
+    b = ints_to_le([b_list], n)[0]
+    out = np.empty((n, 32), dtype=np.uint8)
+    _check(lib().cvmgpu_fr_device_op(op.encode(), _ptr(a), _ptr(b), _ptr(out), n))
+    return le_to_ints(out)
+
+
+def imad_peak(kind):
+    v, ms = c_double(), c_double()
+    _check(lib().cvmgpu_imad_peak(kind, byref(v), byref(ms)))
+    return v.value, ms.value

@@ -1,0 +1,147 @@
+/* cvmgpu -- C ABI of the B200 batched witness-generation + R1CS-check engine.
+ *
+ * This is the drop-in boundary for the reference's one-witness-per-process calculator.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference tree,
+ * MarioCalvarro/circom_cvm):
+ *
+ *   reference                                                        this library
+ *   ---------------------------------------------------------------  ---------------------------------
+ *   loadCircuit(<circuit>.dat) + generated <circuit>.cpp             cvmgpu_program_load(<circuit>.cvm)
+ *     code_producers/src/c_elements/common/main.cpp:22-124             (the --cvm output of the same compile,
+ *     compiler/src/circuit_design/circuit.rs:424-567                    circuit.rs:577-621)
+ *   Circom_CalcWit::setInputSignal / tryRunCircuit -> run(ctx)       cvmgpu_witness_batch[_dev]
+ *     common/calcwit.cpp:71-97, generated T_run bodies                 (B independent inputs at once)
+ *   writeBinWitness(ctx, out.wtns)  common/main.cpp:286-332          cvmgpu_wtns_write / witness_batch output
+ *   R1CSWriter (the file our checker consumes)                       cvmgpu_r1cs_load
+ *     constraint_writers/src/r1cs_writer.rs:155-341
+ *   `===` asserts compiled into the program (translate.rs:676-734)   cvmgpu_r1cs_check[_dev]  (the reference has no
+ *     -- the reference's only satisfiability check                      stand-alone checker; semantics = file format:
+ *                                                                      A*B - C = 0, constraints-json.md:17)
+ *   extern "C" Fr_* (bn128/fr.hpp:28-70)                             device code (csrc/fr.cuh); cvmgpu_fr_host_op
+ *                                                                      exposes the same limb routines on the host
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure (never aborts --
+ * the reference exits through assert()); cvmgpu_last_error() returns a thread-local message.
+ * Field elements cross the boundary as 32-byte little-endian CANONICAL integers (the .wtns / .r1cs
+ * encoding).  The caller owns every buffer; handles are opaque and released with *_free.
+ * Host code can be Rust (`extern "C"`), C++, or Python ctypes; see INTEGRATION.md.
+ */
+#ifndef CVMGPU_H
+#define CVMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVMGPU_OK 0
+#define CVMGPU_ERR_IO (-1)          /* file missing / unreadable */
+#define CVMGPU_ERR_PARSE (-2)       /* malformed .cvm / .r1cs */
+#define CVMGPU_ERR_UNSUPPORTED (-3) /* program uses a feature the trace compiler rejects */
+#define CVMGPU_ERR_CUDA (-4)        /* no device / CUDA failure: there is NO CPU fallback */
+#define CVMGPU_ERR_ARG (-5)
+
+/* per-witness status words (the reference aborts the process in these cases) */
+#define CVMGPU_ST_OK 0
+#define CVMGPU_ST_ASSERT 1   /* failed assert / `===`   (assert_bucket.rs:71-86) */
+#define CVMGPU_ST_TOINT 2    /* Fr_toInt overflow        (bn128/fr.cpp:165-167) */
+#define CVMGPU_ST_DIVZERO 3  /* `\` or `%` by zero       (GMP division by zero in the reference) */
+
+typedef struct cvmgpu_program cvmgpu_program;
+typedef struct cvmgpu_r1cs cvmgpu_r1cs;
+
+typedef struct {
+    uint64_t n_signals;          /* %%signals */
+    uint32_t n_wires;            /* length of %%witness */
+    uint32_t n_inputs;           /* main input signals (field elements) */
+    uint32_t n_outputs;          /* main output signals */
+    uint32_t n_slots;            /* on-chip slots per witness chosen for the tape */
+    uint32_t n_rows;             /* rows of the device value store: wires + spill rows */
+    uint64_t tape_len;           /* tape instructions executed per witness */
+    uint64_t ref_mul;            /* N_mul: ff.mul (+1 per ff.div) the reference program executes per witness */
+    uint64_t ref_field_ops;      /* all ff.* operations the reference program executes per witness */
+    uint64_t cvm_instructions;   /* CVM instructions replayed on the host while tracing */
+    uint64_t tape_mul, tape_div, tape_addsub, tape_other, tape_ld, tape_st, tape_spill_st;
+    uint32_t n_consts;
+    uint32_t dyn_branches;
+} cvmgpu_program_info;
+
+typedef struct {
+    uint32_t n_wires, n_pub_out, n_pub_in, n_prv_in, n_constraints;
+    uint64_t n_labels;
+    uint64_t nnz;                /* non-zeros of A, B and C together */
+    uint64_t nnz_pm1;            /* of which coefficient +1 or -1 */
+    uint32_t n_coefs;            /* distinct coefficients (interned) */
+} cvmgpu_r1cs_info;
+
+const char *cvmgpu_last_error(void);
+int cvmgpu_device_count(void);
+int cvmgpu_set_device(int device);
+
+/* ---- program ---------------------------------------------------------------------------------- */
+/* Parse + trace-compile a .cvm file.  n_slots = 0 picks the default.  Works without a GPU. */
+int cvmgpu_program_load(const char *cvm_path, uint32_t n_slots, cvmgpu_program **out);
+int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32_t n_slots, cvmgpu_program **out);
+int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info);
+void cvmgpu_program_free(cvmgpu_program *p);
+/* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table
+ * (32-byte LE Montgomery values).  For inspection and for host-side tests of the trace compiler. */
+int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_ins, const void **consts, uint32_t *n_consts);
+
+/* ---- witness generation ----------------------------------------------------------------------- */
+/* HOST buffers.  inputs: B x n_inputs x 32 B (main inputs in signal order, canonical LE; values >= q are
+ * reduced like Fr_str2element does).  wtns_out: B x n_wires x 32 B canonical LE -- row b is exactly the
+ * data section of the .wtns the reference writes for input b.  status: B words.  Either output may be NULL. */
+int cvmgpu_witness_batch(cvmgpu_program *p, const uint8_t *inputs, uint64_t B, uint8_t *wtns_out, uint32_t *status);
+/* Same, plus the R1CS check of every witness on the device before it is exported: first_bad[b] as in
+ * cvmgpu_r1cs_check.  r may be NULL (then first_bad is ignored).  Chunks of the batch are pipelined over two
+ * streams; pass pinned host memory to let copies overlap the kernels. */
+int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
+                                 uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
+
+/* DEVICE buffers on the current device.
+ *   d_inputs  B x n_inputs x 32 B, as above
+ *   d_store   value store, n_rows x 2 x bstride x 16 B: row r, half h, witness w at ((r*2+h)*bstride + w)*16;
+ *             Montgomery form; rows [0, n_wires) are the witness wires
+ *   d_status  B words
+ * stream: a cudaStream_t (0 = default stream). */
+int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store,
+                             void *d_status, void *stream);
+/* value store -> .wtns row layout: d_wtns = B x n_wires x 32 B canonical LE */
+int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_wtns,
+                              void *stream);
+size_t cvmgpu_store_bytes(const cvmgpu_program *p, uint64_t bstride);
+
+/* write one witness (n_wires x 32 B canonical) as a .wtns file, byte-identical to main.cpp:286-332 */
+int cvmgpu_wtns_write(const char *path, const uint8_t *witness, uint32_t n_wires);
+
+/* ---- R1CS ------------------------------------------------------------------------------------- */
+int cvmgpu_r1cs_load(const char *r1cs_path, cvmgpu_r1cs **out);
+int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info);
+void cvmgpu_r1cs_free(cvmgpu_r1cs *r);
+/* HOST: witnesses B x n_wires x 32 B canonical; first_bad[b] = index of the first violated constraint or
+ * 0xffffffff when witness b satisfies every constraint. */
+int cvmgpu_r1cs_check(cvmgpu_r1cs *r, const uint8_t *witnesses, uint64_t B, uint32_t *first_bad);
+/* DEVICE: checks the value store written by cvmgpu_witness_batch_dev (Montgomery, same layout). */
+int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64_t B, uint64_t bstride, void *d_first_bad,
+                          void *stream);
+/* DEVICE: canonical AoS witnesses (B x n_wires x 32 B) -> value-store layout (Montgomery) */
+int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, uint64_t bstride, void *d_store,
+                              void *stream);
+
+/* ---- field arithmetic, host build of the device limb routines (test hook; no GPU needed) ------- */
+/* op: add sub mul div idiv mod pow shl shr band bor bxor bnot lt leq gt geq eq neq land lor lnot neg inv square
+ * a, b, out: 32-byte LE canonical.  Returns 1 when the reference's behaviour is undefined (division by zero). */
+int cvmgpu_fr_host_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out);
+/* same operations executed by a CUDA kernel over n element pairs (device self-test of csrc/fr.cuh) */
+int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n);
+/* dependency-free IMAD micro-benchmark: returns 32x32->64 multiply-accumulates per second; kind 0 = mad.lo+mad.hi
+ * pairs (u32), 1 = mad.wide (u64 accumulate) */
+int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVMGPU_H */

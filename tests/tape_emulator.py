@@ -1,0 +1,68 @@
+"""Test helper: execute a compiled tape (as the CUDA tape kernel would) with Python big ints.
+
+Used ONLY by the CPU test-suite to check the host-side trace compiler and slot allocator
+(csrc/tracer.hpp, csrc/tape.hpp) without a GPU.  It is not importable from the product package
+and is not a fallback: the product path has no CPU execution.
+"""
+from oracle import fr_model as M
+
+(T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
+ T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_LD, T_ST, T_STC) = range(29)
+
+BIN = {T_ADD: M.add, T_SUB: M.sub, T_MUL: M.mul, T_POW: M.pow_, T_SHL: M.shl, T_SHR: M.shr, T_BAND: M.band,
+       T_BOR: M.bor, T_BXOR: M.bxor, T_LT: M.lt, T_LE: M.leq, T_GT: M.gt, T_GE: M.geq, T_EQ: M.eq, T_NEQ: M.neq,
+       T_LAND: M.land, T_LOR: M.lor}
+
+
+def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
+    """-> (rows: list of canonical values per value-store row (None = never written), status)"""
+    consts = [M.from_mont(c) for c in consts_mont]
+    slots = [None] * n_slots
+    rows = [None] * n_rows
+    status = 0
+    for ins in tape:
+        op, flags, dst, a, b, c = (int(ins["op"]), int(ins["flags"]), int(ins["dst"]), int(ins["a"]), int(ins["b"]),
+                                   int(ins["c"]))
+
+        def operand(idx, bit):
+            if flags & bit:
+                return consts[idx]
+            v = slots[idx]
+            assert v is not None, "read of an empty slot"
+            return v
+
+        if op == T_INPUT:
+            slots[dst] = inputs[c] % M.Q
+        elif op == T_LD:
+            assert rows[c] is not None, "load of an unwritten row"
+            slots[dst] = rows[c]
+        elif op == T_ST:
+            assert slots[a] is not None
+            rows[c] = slots[a]
+        elif op == T_STC:
+            rows[c] = consts[a]
+        elif op == T_FAIL_IF:
+            if status == 0 and operand(a, 1) != 0:
+                status = c
+        elif op == T_SEL:
+            x, y, z = operand(a, 1), operand(b, 2), operand(c, 4)
+            slots[dst] = y if x != 0 else z
+        elif op in (T_BNOT, T_EQZ):
+            x = operand(a, 1)
+            slots[dst] = M.bnot(x) if op == T_BNOT else int(x == 0)
+        elif op == T_DIV:
+            x, y = operand(a, 1), operand(b, 2)
+            slots[dst] = 0 if y == 0 else M.div(x, y)
+        elif op in (T_IDIV, T_MOD):
+            x, y = operand(a, 1), operand(b, 2)
+            if y == 0:
+                if status == 0:
+                    status = 3
+                slots[dst] = 0
+            else:
+                slots[dst] = x // y if op == T_IDIV else x % y
+        elif op in BIN:
+            slots[dst] = BIN[op](operand(a, 1), operand(b, 2))
+        else:
+            raise ValueError("bad tape op %d" % op)
+    return rows, status

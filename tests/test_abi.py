@@ -1,0 +1,58 @@
+"""The C-ABI library loads and exports every symbol declared in include/cvmgpu.h; error behaviour
+without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cvmgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cvmgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(cvmlib):
+    from circom_cvm_b200 import engine as E
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(cvmlib, s), "missing export " + s
+    assert sorted(E.EXPORTS) == syms
+
+
+def test_load_errors_are_codes_not_aborts(cvmlib, tmp_path):
+    from circom_cvm_b200 import engine as E
+    with pytest.raises(E.CvmGpuError) as e:
+        E.WitnessCalculator(cvm_path=str(tmp_path / "missing.cvm"))
+    assert e.value.code == -1
+    bad = tmp_path / "bad.cvm"
+    bad.write_text("%%prime 7\n")
+    with pytest.raises(E.CvmGpuError) as e:
+        E.WitnessCalculator(cvm_path=str(bad))
+    assert e.value.code == -2
+    with pytest.raises(E.CvmGpuError) as e:
+        E.WitnessCalculator(cvm_text="%%prime 21888242871839275222246405745257275088548364400416034343698204186575808495617\n"
+                                     "%%signals 2\n%%start T_0\n%%witness 0 1\n%%template T_0 [ ] [ ff 0 ] [1] [0]\n"
+                                     "i64.3 = i64.add i64.3 i64.1\n")
+    assert e.value.code == -2 and "literal" in str(e.value)
+    with pytest.raises(E.CvmGpuError) as e:
+        E.R1cs(str(tmp_path / "missing.r1cs"))
+    assert e.value.code == -1
+
+
+def test_no_cpu_fallback(cvmlib):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    from circom_cvm_b200 import engine as E
+    from conftest import circuit
+    if E.device_count() > 0:
+        pytest.skip("a GPU is present")
+    wc = E.WitnessCalculator(cvm_text=circuit("multiplier2").cvm)
+    with pytest.raises(E.CvmGpuError) as e:
+        wc.calculate([[3, 11]])
+    assert e.value.code == -4
+    with pytest.raises(E.CvmGpuError):
+        E.fr_device_op("mul", [1], [2])

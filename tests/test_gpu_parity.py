@@ -1,0 +1,189 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI and is compared
+bit-exactly with the oracle (oracle/fr_model.py, oracle/cvm_interp.py) and the committed golden vectors."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import circuit, load_kats
+from oracle import cvm_interp as I
+from oracle import fr_model as M
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E(cvmlib):
+    from circom_cvm_b200 import engine
+    assert engine.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return engine
+
+
+def test_device_field_ops_match_reference_vectors(E):
+    """csrc/fr.cuh on the GPU against KATs produced by the reference's generic/fr.cpp."""
+    by_op = {}
+    for op, _af, _bf, a, b, out in load_kats():
+        if op in ("isTrue", "toInt", "rawMMul", "rawToMont", "rawFromMont", "copy"):
+            continue
+        by_op.setdefault(op, []).append((a, b or 0, int(out, 16)))
+    assert len(by_op) >= 24
+    for op, rows in by_op.items():
+        got = E.fr_device_op(op, [r[0] for r in rows], [r[1] for r in rows])
+        for (a, b, exp), g in zip(rows, got):
+            assert g == exp, (op, hex(a), hex(b), hex(g), hex(exp))
+
+
+def test_device_mul_random_bulk(E):
+    rng = random.Random(11)
+    a = [rng.randrange(M.Q) for _ in range(4096)]
+    b = [rng.randrange(M.Q) for _ in range(4096)]
+    for op in ("mul", "add", "sub", "div"):
+        got = E.fr_device_op(op, a, b)
+        f = M.BINOPS[op]
+        for x, y, g in zip(a, b, got):
+            assert g == f(x, y), op
+
+
+CASES = {
+    "multiplier2": [[3, 11], [M.Q - 1, 5], [0, 0]],
+    "multiplier4": [[2, 3, 4, 5]],
+    "num2bits8": [[0xA5], [0], [255], [256], [1 << 100]],
+    "iszero": [[0], [7], [M.Q - 1]],
+    "isequal": [[5, 5], [5, 6]],
+    "lessthan8": [[3, 200], [200, 3], [7, 7]],
+    "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
+    "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
+    "poseidon2": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],
+}
+
+
+def oracle_batch(art, rows):
+    prog = I.load(art.cvm)
+    wit, st = [], []
+    for r in rows:
+        try:
+            wit.append(I.compute_witness(prog, r))
+            st.append(0)
+        except I.WitnessError as e:
+            wit.append(None)
+            st.append(e.status)
+    return wit, st
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("slots", [0, 5])
+def test_witness_batch_matches_oracle(E, name, slots):
+    art = circuit(name)
+    rng = random.Random(3)
+    rows = list(CASES[name])
+    if name not in ("num2bits8", "sum3cmp", "lessthan8"):
+        rows += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(200)]
+    else:
+        rows = rows * 50                                   # ragged batch size, not a multiple of 128
+    wc = E.WitnessCalculator(cvm_text=art.cvm, n_slots=slots)
+    wt, st = wc.calculate(rows)
+    exp_w, exp_st = oracle_batch(art, rows)
+    assert list(st) == exp_st
+    got = E.le_to_ints(wt)
+    for g, e, s in zip(got, exp_w, exp_st):
+        if s == 0:
+            assert g == e
+
+
+def test_empty_batch(E):
+    wc = E.WitnessCalculator(cvm_text=circuit("multiplier2").cvm)
+    wt, st = wc.calculate(np.zeros((0, 2, 32), dtype=np.uint8))
+    assert wt.shape == (0, 4, 32) and st.shape == (0,)
+
+
+def test_inputs_not_reduced_are_reduced_like_str2element(E):
+    """Fr_str2element reduces mod q (bn128/fr.cpp:56-62)."""
+    wc = E.WitnessCalculator(cvm_text=circuit("multiplier2").cvm)
+    rows = [[M.Q + 3, 11], [(1 << 256) - 1, 2]]
+    wt, st = wc.calculate(rows)
+    got = E.le_to_ints(wt)
+    assert got[0] == [1, 33, 3, 11]
+    x = ((1 << 256) - 1) % M.Q
+    assert got[1] == [1, (2 * x) % M.Q, x, 2]
+
+
+def test_wtns_file_is_what_the_reference_writes(E, tmp_path):
+    """Byte-identical .wtns (common/main.cpp:286-332) for the reference's own walk-through input
+    (mkdocs/docs/getting-started/computing-the-witness.md:22-56: a=3, b=11)."""
+    from circom_cvm_b200 import formats
+    wc = E.WitnessCalculator(cvm_text=circuit("multiplier2").cvm)
+    wt, st = wc.calculate([[3, 11]])
+    p = tmp_path / "witness.wtns"
+    wc.write_wtns(str(p), wt[0])
+    assert p.read_bytes() == formats.wtns_bytes([1, 33, 3, 11])
+
+
+def test_poseidon_published_vector(E):
+    wc = E.WitnessCalculator(cvm_text=circuit("poseidon2").cvm)
+    wt, st = wc.calculate([[1, 2]])
+    assert st[0] == 0
+    assert E.le_to_ints(wt)[0][1] == 7853200120776062878684798364095072458815029376092732009249414926327459813530
+
+
+def _write_r1cs(art, path):
+    from circom_cvm_b200 import formats
+    formats.write_r1cs(str(path), art.constraints, art.n_wires, art.n_pub_out, art.n_pub_in, art.n_prv_in, art.witness,
+                       n_labels=art.n_signals)
+
+
+@pytest.mark.parametrize("name", ["multiplier2", "lessthan8", "sum3cmp", "poseidon2"])
+def test_r1cs_check_accepts_valid_and_pinpoints_invalid(E, name, tmp_path):
+    art = circuit(name)
+    _write_r1cs(art, tmp_path / "c.r1cs")
+    r = E.R1cs(str(tmp_path / "c.r1cs"))
+    rng = random.Random(5)
+    rows = [CASES[name][0]] * 3
+    if name in ("multiplier2", "poseidon2"):
+        rows += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(130)]
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    wt, st = wc.calculate(rows)
+    assert not st.any()
+    bad = r.check(wt)
+    assert (bad == E.NO_BAD).all()
+    # corrupt one wire of some witnesses; the CPU evaluation of the same .r1cs tells which constraint breaks first
+    wt2 = wt.copy()
+    victims = [0, len(rows) - 1]
+    for v in victims:
+        wire = 1 + (v % (art.n_wires - 1))
+        wt2[v, wire, 0] ^= 1
+    bad = r.check(wt2)
+    vals = E.le_to_ints(wt2)
+    for b in range(len(rows)):
+        w = vals[b]
+        first = E.NO_BAD
+        for ci, (a, bb, c) in enumerate(art.constraints):
+            ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
+            if (ev(a) * ev(bb) - ev(c)) % M.Q:
+                first = ci
+                break
+        assert bad[b] == first, (name, b)
+    assert all(bad[v] != E.NO_BAD for v in victims)
+
+
+def test_device_api_with_torch_buffers(E):
+    """The device-pointer entry points on torch-allocated buffers (value store layout, export, check)."""
+    import torch
+    art = circuit("poseidon2")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    B = 1000
+    rng = random.Random(9)
+    rows = [[rng.randrange(M.Q) for _ in range(2)] for _ in range(B)]
+    inp = torch.from_numpy(E.ints_to_le(rows, 2)).cuda()
+    store = torch.empty(wc.store_bytes(B), dtype=torch.uint8, device="cuda")
+    status = torch.empty(B, dtype=torch.int32, device="cuda")
+    wtns = torch.empty((B, wc.n_wires, 32), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    wc.run_dev(inp, B, B, store, status, s)
+    wc.export_dev(store, B, B, wtns, s)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    from tools.circuitgen.circuits import poseidon
+    got = E.le_to_ints(wtns.cpu().numpy())
+    for b in (0, 1, 511, 999):
+        assert got[b][1] == poseidon.poseidon_hash(rows[b])
+        assert got[b] == I.compute_witness(I.load(art.cvm), rows[b])

@@ -1,0 +1,100 @@
+"""Host logic of the product (CVM parser, trace compiler, slot allocator) checked on CPU: the compiled
+tape is executed by tests/tape_emulator.py and must reproduce the CVM oracle on every fixture circuit."""
+import random
+
+import pytest
+
+from conftest import circuit
+from oracle import cvm_interp as I
+from oracle import fr_model as M
+from tape_emulator import run_tape
+
+CASES = {
+    "multiplier2": [[3, 11], [M.Q - 1, 5], [0, 0]],
+    "multiplier4": [[2, 3, 4, 5], [M.Q - 1, M.Q - 2, 7, 0]],
+    "num2bits8": [[0xA5], [0], [255], [256]],            # 256 does not fit: assert must fail
+    "iszero": [[0], [7], [M.Q - 1]],
+    "isequal": [[5, 5], [5, 6]],
+    "lessthan8": [[3, 200], [200, 3], [7, 7]],
+    "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
+    "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
+    "poseidon2": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],
+}
+
+
+def oracle(prog, inp):
+    try:
+        return I.compute_witness(prog, inp), 0
+    except I.WitnessError as e:
+        return None, e.status
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("slots", [4, 7, 24])
+def test_tape_matches_oracle(cvmlib, name, slots):
+    from circom_cvm_b200 import engine as E
+    art = circuit(name)
+    prog = I.load(art.cvm)
+    wc = E.WitnessCalculator(cvm_text=art.cvm, n_slots=slots)
+    assert wc.n_wires == art.n_wires and wc.n_inputs == art.n_inputs
+    tape, consts = wc.tape()
+    rng = random.Random(7)
+    cases = list(CASES[name])
+    if name not in ("num2bits8", "sum3cmp", "lessthan8"):
+        cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
+    for inp in cases:
+        w, st = oracle(prog, inp)
+        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, inp)
+        assert status == st, (name, inp)
+        if st == 0:
+            assert rows[:wc.n_wires] == w, (name, inp)
+
+
+def test_reference_op_counts(cvmlib):
+    """N_mul reported by the tracer = dynamic ff.mul (+ff.div) count of the oracle interpreter."""
+    from circom_cvm_b200 import engine as E
+    for name in ("poseidon2", "opszoo", "lessthan8"):
+        art = circuit(name)
+        m = I.Machine(I.load(art.cvm))
+        m.witness(CASES[name][0])
+        wc = E.WitnessCalculator(cvm_text=art.cvm)
+        if wc.info.dyn_branches == 0:
+            assert wc.info.ref_mul == m.counters["mul"], name
+            assert wc.info.cvm_instructions == m.counters["ops"], name
+        else:   # both arms of a data-dependent branch are traced, so the tracer's count is an upper bound
+            assert wc.info.ref_mul >= m.counters["mul"], name
+
+
+def test_poseidon_known_answer():
+    from tools.circuitgen.circuits import poseidon
+    assert poseidon.poseidon_hash([1, 2]) == 7853200120776062878684798364095072458815029376092732009249414926327459813530
+    art = circuit("poseidon2")
+    w = I.compute_witness(I.load(art.cvm), [1, 2])
+    assert w[1] == poseidon.poseidon_hash([1, 2])
+
+
+def test_witness_satisfies_r1cs():
+    for name, cases in CASES.items():
+        art = circuit(name)
+        prog = I.load(art.cvm)
+        w, st = oracle(prog, cases[0])
+        assert st == 0
+        for (a, b, c) in art.constraints:
+            ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
+            assert (ev(a) * ev(b) - ev(c)) % M.Q == 0, name
+
+
+def test_unsupported_programs_are_rejected_with_a_reason(cvmlib):
+    from circom_cvm_b200 import engine as E
+    q = "21888242871839275222246405745257275088548364400416034343698204186575808495617"
+    head = "%%prime " + q + "\n%%signals 3\n%%start T_0\n%%witness 0 1 2\n%%template T_0 [ ff 0 ] [ ff 0 ] [2] [0]\n"
+    # data-dependent loop
+    text = head + "loop\nx_0 = get_signal i64.1\nif x_0\ncontinue\nend\nend\n"
+    with pytest.raises(E.CvmGpuError) as e:
+        E.WitnessCalculator(cvm_text=text)
+    assert e.value.code == -3 and "data-dependent" in str(e.value)
+    # data-dependent address
+    text = head + "x_0 = get_signal i64.1\nx_1 = ff.wrap_i64 x_0\nx_2 = get_signal x_1\nset_signal i64.0 x_2\n"
+    with pytest.raises(E.CvmGpuError) as e:
+        E.WitnessCalculator(cvm_text=text)
+    assert e.value.code == -3

@@ -9,6 +9,7 @@ Two documented departures from what the fork's emitter prints today (SURVEY.md F
   * copy loops increment their address operands textually in the reference, so literal
     addresses would be assigned to (`i64.5 = i64.add i64.5 i64.1`, store_bucket.rs:1026-1028);
     we first move literal addresses into fresh registers.
+  * array equality (`===` on arrays) is emitted as a counted loop over address registers, see array_eq().
   * multi-element `return` passes the *address* register as documented in
     mkdocs/docs/circom-language/formats/circom-virtual-machine.md:201-203 (the emitter at
     return_bucket.rs:131 loads the first element instead, which cannot work).
@@ -84,37 +85,60 @@ class CvmEmitter:
         return "%s = get_cmp_signal %s %s" % (res, vcmp, vloc)
 
     def compute(self, n):           # compute_bucket.rs:471-620
+        op = n.op
+        if isinstance(op, tuple):
+            return self.array_eq(n, op[1])
         ins = [";; compute bucket"]
         vres = []
         for a in n.args:
             i2, r = self.expr(a)
             ins += i2
             vres.append(r)
-        op = n.op
-        multi = isinstance(op, tuple)
-        opkey = op[0] if multi else op
-        if opkey == "neg":
+        if op == "neg":
             ins.append(";; OP(PREFIX_SUB)")
             res = self.fresh()
             ins.append("%s = ff.sub 0 %s" % (res, vres[0]))
-        elif multi:                 # array equality: compute_bucket.rs:538-586
-            ins.append(";; OP()")
-            _unused = self.fresh()
-            counter = self.fresh()
-            res = self.fresh()
-            ins.append("%s = i64.%d" % (counter, op[1]))
-            ins += ["loop", "if %s " % counter, "%s = ff.eq %s" % (res, " ".join(vres)), "if %s " % res,
-                    "%s = i64.sub %s i64.1" % (counter, counter),
-                    "%s = i64.add %s i64.1" % (vres[0], vres[0]),
-                    "%s = i64.add %s i64.1" % (vres[1], vres[1]),
-                    "continue", "end", "end", "break", "end"]
         else:
-            mnem, name = OPNAME[opkey]
+            mnem, name = OPNAME[op]
             ins.append(";; OP(%s)" % name)
             res = self.fresh()
             ins.append("%s = %s %s" % (res, mnem, " ".join(vres)))
         ins.append(";; end of compute bucket")
         return ins, res
+
+    def array_eq(self, n, size):
+        """Element-wise equality of two arrays (Eq(n>1)).  The fork's emitter for this case
+        (compute_bucket.rs:538-586) loads the FIRST ELEMENT VALUES and then increments those values as if
+        they were addresses, so its output cannot be executed.  We emit what the C++ twin computes
+        (compute_bucket.rs:430-455: a loop of Fr_eq over both arrays): a counted loop over address
+        registers that ANDs the per-element results, without the data-dependent early exit."""
+        ins = [";; compute bucket"]
+        locs = []
+        for a in n.args:
+            assert isinstance(a, Load)
+            i2, (vcmp, vloc) = self.location(a.atype, a.loc, a.cmp)
+            ins += i2
+            r = self.fresh()
+            ins.append("%s = %s" % (r, vloc))
+            locs.append((a.atype, vcmp, r))
+        ins.append(";; OP()")
+        counter, acc = self.fresh(), self.fresh()
+        ins.append("%s = i64.%d" % (counter, size))
+        ins.append("%s = ff.1" % acc)
+        ins += ["loop", "if %s " % counter]
+        vals = []
+        for (atype, vcmp, r) in locs:
+            v = self.fresh()
+            ins.append(self._get(atype, v, vcmp, r))
+            vals.append(v)
+        e = self.fresh()
+        ins.append("%s = ff.eq %s %s" % (e, vals[0], vals[1]))
+        ins.append("%s = ff.and %s %s" % (acc, acc, e))
+        ins.append("%s = i64.sub %s i64.1" % (counter, counter))
+        for (_a, _c, r) in locs:
+            ins.append("%s = i64.add %s i64.1" % (r, r))
+        ins += ["continue", "end", "break", "end", ";; end of compute bucket"]
+        return ins, acc
 
     # ---- statements
     @staticmethod
