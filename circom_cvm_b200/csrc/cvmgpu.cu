@@ -261,7 +261,9 @@ struct PipeBufs {
 
 extern "C" int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
                                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
-    if (!p || (!inputs && p->n_inputs)) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0) return CVMGPU_OK;
+    if (!inputs && p->n_inputs) return fail(CVMGPU_ERR_ARG, "null argument");
     if (r && !first_bad) return fail(CVMGPU_ERR_ARG, "first_bad is required with an r1cs handle");
     if (r && r->file.n_wires != p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "r1cs and program disagree on the number of wires");
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");

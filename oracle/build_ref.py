@@ -11,8 +11,8 @@ GPU box with gpurun snapshots):
                    code_producers/src/c_elements/c_code_generator.rs:1015-1067 renders
                    them (handlebars placeholders), + oracle/fr_ref_driver.cpp.
   calcwit.o main.o reference runtime code_producers/src/c_elements/common/{calcwit,main}.cpp,
-                   compiled unchanged (main.cpp with -Dmain=circom_reference_main so that
-                   our timing harness can own main()).
+                   compiled unchanged (the `main` symbol of main.o is renamed with objcopy
+                   so that our timing harness can own main()).
   fr.o             the rendered fr.cpp as an object for linking circuit binaries.
 
 Not buildable here (stated in DESIGN.md): bn128/fr.asm (no nasm) and the Rust compiler
@@ -197,8 +197,12 @@ def build():
              "-I", os.path.join(OUT, "inc")]
     sh(["g++", *flags, "-c", os.path.join(src, "fr.cpp"), "-o", os.path.join(OUT, "fr.o")])
     sh(["g++", *flags, "-c", os.path.join(common, "calcwit.cpp"), "-o", os.path.join(OUT, "calcwit.o")])
-    sh(["g++", *flags, "-include", "cstring", "-include", "cassert", "-Dmain=circom_reference_main",
-        "-c", os.path.join(common, "main.cpp"), "-o", os.path.join(OUT, "main.o")])
+    # main.cpp is compiled unchanged; its `main` symbol is then renamed so that oracle/ref_harness.cpp can own main()
+    # (a -Dmain=... macro would also rewrite identifiers inside the standard headers and breaks iostream).
+    sh(["g++", *flags, "-include", "cstring", "-include", "cassert",
+        "-c", os.path.join(common, "main.cpp"), "-o", os.path.join(OUT, "main_plain.o")])
+    sh(["objcopy", "--redefine-sym", "main=circom_reference_main", os.path.join(OUT, "main_plain.o"),
+        os.path.join(OUT, "main.o")])
     sh(["g++", *flags, "-shared", os.path.join(HERE, "fr_ref_driver.cpp"), os.path.join(OUT, "fr.o"),
         LIBGMP, "-o", os.path.join(OUT, "libfr_ref.so")])
     # headers needed later to compile emitted circuit bodies against the runtime

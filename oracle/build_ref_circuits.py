@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Build circuit binaries on top of the REFERENCE runtime: oracle/_ref/<name> (+ <name>.dat).
+
+TEST / BASELINE INFRASTRUCTURE ONLY.  The circuit bodies are emitted by tools/circuitgen in the shapes of the
+reference's WriteC emitters (the Rust compiler itself cannot run here); everything else that executes --
+loadCircuit, loadJson, Circom_CalcWit, Fr_*, writeBinWitness -- is the reference's own code (oracle/build_ref.py).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+OUT = os.path.join(HERE, "_ref")
+LIBGMP = "/usr/lib/x86_64-linux-gnu/libgmp.so.10"
+
+
+def circuits():
+    from tools.circuitgen.circuits import basic, poseidon
+    table = {
+        "multiplier2": (basic.Multiplier2, ()),
+        "multiplier4": (basic.MultiplierN, (4,)),
+        "num2bits8": (basic.Num2Bits, (8,)),
+        "iszero": (basic.IsZero, ()),
+        "lessthan8": (basic.LessThan, (8,)),
+        "sum3cmp": (basic.Sum3Cmp, ()),
+        "opszoo": (basic.OpsZoo, ()),
+        "poseidon2": (poseidon.Poseidon, (2,)),
+    }
+    try:
+        from tools.circuitgen.circuits import sha256
+        table["sha256_64"] = (sha256.Sha256, (64,))
+    except ImportError:
+        pass
+    return table
+
+
+def build(names=None):
+    from tools.circuitgen.build import compile_circuit, write_artifact
+    need = [os.path.join(OUT, f) for f in ("fr.o", "calcwit.o", "main.o")]
+    if not all(os.path.exists(p) for p in need):
+        print("oracle/_ref runtime objects missing; run oracle/build_ref.py first")
+        return False
+    src = os.path.join(OUT, "src")
+    cdir = os.path.join(OUT, "circuits")
+    flags = ["-std=c++11", "-O3", "-w", "-I", src, "-I", os.path.join(HERE, "gmp_shim"), "-I", os.path.join(OUT, "inc")]
+    harness = os.path.join(OUT, "ref_harness.o")
+    subprocess.check_call(["g++", *flags, "-c", os.path.join(HERE, "ref_harness.cpp"), "-o", harness])
+    for name, (fn, args) in circuits().items():
+        if names and name not in names:
+            continue
+        art = compile_circuit(fn, args, name=name)
+        paths = write_artifact(art, cdir, with_cpp=True)
+        exe = os.path.join(OUT, name)
+        cmd = ["g++", *flags, paths["cpp"], harness, *need, LIBGMP, "-o", exe]
+        print("+", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        with open(paths["dat"], "rb") as fsrc, open(exe + ".dat", "wb") as fdst:
+            fdst.write(fsrc.read())
+    # the bench binary name bench.py looks for
+    p2 = os.path.join(OUT, "poseidon2")
+    if os.path.exists(p2):
+        for ext in ("", ".dat"):
+            with open(p2 + ext, "rb") as fsrc, open(os.path.join(OUT, "poseidon2_bench") + ext, "wb") as fdst:
+                fdst.write(fsrc.read())
+        os.chmod(os.path.join(OUT, "poseidon2_bench"), 0o755)
+    return True
+
+
+if __name__ == "__main__":
+    sys.exit(0 if build(sys.argv[1:] or None) else 1)

@@ -1,0 +1,88 @@
+"""Program-level parity with the REFERENCE runtime.
+
+oracle/_ref/<circuit> is the reference's own main.cpp + calcwit.cpp + generic/fr.cpp (compiled where they lie by
+oracle/build_ref.py) linked with the circuit body that tools/circuitgen emits in the WriteC shapes.  Running
+`./<circuit> input.json out.wtns` is therefore what a user of the reference does.  The CVM oracle must produce the
+same witness, byte for byte -- this pins oracle/cvm_interp.py (and through it the GPU path) to the reference's
+execution of the same programs.  The binaries are prebuilt (they travel to the GPU box); tests skip if absent.
+"""
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+from circom_cvm_b200 import formats
+from conftest import ROOT, circuit
+from oracle import cvm_interp as I
+from oracle import fr_model as M
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def ref_binary(name):
+    p = os.path.join(REF, name)
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/%s not built (needs /root/reference; run oracle/build_ref.py + build_ref_circuits.py)" % name)
+    return p
+
+
+def input_json(art, values):
+    """main inputs in signal order -> the JSON object the reference's loadJson expects (main.cpp:241-284)"""
+    doc, k = {}, 0
+    for name, _start, size in art.main_inputs:
+        vals = [str(v) for v in values[k:k + size]]
+        k += size
+        dims = [s for s in art.prog.main.tmpl.signals if s.name == name][0].dims
+        doc[name] = vals[0] if dims == () else vals
+    return doc
+
+
+CASES = {
+    "multiplier2": [[3, 11], [M.Q - 7, 3]],
+    "multiplier4": [[2, 3, 4, 5]],
+    "num2bits8": [[0xA5], [255]],
+    "iszero": [[0], [7]],
+    "lessthan8": [[3, 200], [200, 3]],
+    "sum3cmp": [[1, 0, 1, 1]],
+    "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [1 << 200, (1 << 253) + 5, 254]],
+    "poseidon2": [[1, 2], [M.Q - 1, 12345678901234567890]],
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_runtime_byte_for_byte(name, tmp_path):
+    exe = ref_binary(name)
+    art = circuit(name)
+    prog = I.load(art.cvm)
+    rng = random.Random(21)
+    cases = list(CASES[name])
+    if name in ("multiplier2", "opszoo", "poseidon2", "multiplier4"):
+        cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
+    for k, values in enumerate(cases):
+        jin, wout = tmp_path / ("in%d.json" % k), tmp_path / ("out%d.wtns" % k)
+        jin.write_text(json.dumps(input_json(art, values)))
+        subprocess.run([exe, str(jin), str(wout)], check=True, timeout=60)
+        ours = formats.wtns_bytes(I.compute_witness(prog, values))
+        assert wout.read_bytes() == ours, (name, values)
+
+
+def test_reference_runtime_aborts_where_we_flag(tmp_path):
+    """A failing `===` aborts the reference process (assert); the oracle raises status ASSERT."""
+    exe = ref_binary("num2bits8")
+    art = circuit("num2bits8")
+    jin = tmp_path / "in.json"
+    jin.write_text(json.dumps(input_json(art, [256])))
+    r = subprocess.run([exe, str(jin), str(tmp_path / "o.wtns")], capture_output=True, timeout=60)
+    assert r.returncode != 0
+    with pytest.raises(I.WitnessError) as e:
+        I.compute_witness(I.load(art.cvm), [256])
+    assert e.value.status == I.ST_ASSERT
+
+
+def test_reference_bench_mode_runs():
+    exe = ref_binary("poseidon2")
+    out = subprocess.run([exe, "--bench", "0.3", "7"], capture_output=True, text=True, timeout=60, check=True).stdout
+    d = json.loads(out.strip().splitlines()[-1])
+    assert d["witnesses"] > 0 and d["witnesses_per_s"] > 0
