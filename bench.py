@@ -127,7 +127,7 @@ def cpu_baseline_reference(n_threads, seconds=10.0):
     exe = reference_binary()
     if exe is None:
         return None
-    procs = [subprocess.Popen([exe, str(seconds), str(1234 + i)], stdout=subprocess.PIPE, text=True, cwd=os.path.dirname(exe))
+    procs = [subprocess.Popen([exe, "--bench", str(seconds), str(1234 + i)], stdout=subprocess.PIPE, text=True, cwd=os.path.dirname(exe))
              for i in range(n_threads)]
     total, count = 0.0, 0
     for p in procs:

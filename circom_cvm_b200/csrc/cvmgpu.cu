@@ -85,12 +85,30 @@ extern "C" int cvmgpu_set_device(int device) {
 // ------------------------------------------------------------------------------------------ program
 static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program **out) {
     std::unique_ptr<cvmgpu_program> p(new cvmgpu_program());
-    if (n_slots == 0) n_slots = 24;
     if (n_slots > 55) n_slots = 55;   // 55 * 4 KiB = 220 KiB of the 227 KiB a CTA may use
     try {
         tape::Tracer tr(parser.prog);
         tr.trace();
-        p->tape = tape::build_tape(tr, n_slots);
+        if (n_slots == 0) {
+            // Fewer slots per witness = more resident CTAs per SM (4 KiB of shared memory per slot and CTA), but more
+            // reloads/spills through HBM.  Pick the candidate with the best (work / resident warps) estimate; the
+            // kernel stops gaining from occupancy at about 20 warps per SM.
+            static const uint32_t cand[] = {8, 12, 16, 24, 32};
+            double best = 0;
+            for (uint32_t c : cand) {
+                tape::Tape t = tape::build_tape(tr, c);
+                uint32_t ctas = std::min<uint32_t>(8, (227u * 1024u) / (c * 4096u + 1024u));
+                double warps = std::min<double>(4.0 * ctas, 20.0);
+                double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st);
+                double cost = work / warps;
+                if (best == 0 || cost < best) {
+                    best = cost;
+                    p->tape = std::move(t);
+                }
+            }
+        } else {
+            p->tape = tape::build_tape(tr, n_slots);
+        }
         p->tstats = tr.stats;
         p->n_signals = (uint64_t)parser.prog.n_signals;
         p->n_inputs = (uint32_t)tr.n_inputs;

@@ -195,94 +195,121 @@ FR_HD Fr mont_mul_portable(const Fr &a, const Fr &b) {
 }
 
 #if defined(__CUDA_ARCH__)
-// Device formulation with explicit carry chains (mad.lo.cc / madc.hi.cc): even and odd limb products are
-// accumulated in two separate 8-limb chains so that every chain is a straight run of IMAD with carry.
-//   T = E + O*2^32 ;  per b-limb:  E += a_even*bi, O += a_odd*bi ; m = E[0]*np ; E += q_even*m ; O += q_odd*m ;
-//   then T >>= 32 by folding E[1] into O and shifting E down by two limbs (roles of E and O swap).
-struct Chain {
-    // acc[j..j+1] += x[j]*y for j = 0,2,4,6 in one carry chain; returns the carry out of acc[7]
-    static __device__ __forceinline__ uint32_t mad_even(uint32_t *acc, const uint32_t *x, uint32_t y) {
-        uint32_t c;
-        asm volatile(
-            "mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
-            "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
-            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
-            "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
-            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
-            "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
-            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
-            "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-            "addc.u32 %8, 0, 0;\n\t"
-            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
-              "+r"(acc[7]), "=r"(c)
-            : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(y));
-        return c;
-    }
-};
+// Device formulation.  Per b-limb ("row"): the eight 32x32->64 products a[j]*b_i come from mul.wide.u32
+// (IMAD.WIDE.U32 with a zero addend: no register-pair set-up moves).  The products of the EVEN limbs occupy
+// disjoint 64-bit windows (columns 2k, 2k+1), so they form one 256-bit number that is added to T with a single
+// add.cc/addc.cc chain; the products of the ODD limbs form a second number shifted by 32 bits.  Hence
+// 8 IMAD.WIDE + 17 carry-chain adds per 8 multiply-accumulates, with the multiplies on the FMA pipe and the
+// adds on the ALU pipe.  The reduction row (m*q) has the same shape with q as immediates.
+__device__ __forceinline__ void mac_row(uint32_t (&t)[9], const uint32_t (&x)[8], uint32_t y) {
+    asm volatile(
+        "{\n\t"
+        ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
+        ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
+        "mul.wide.u32 e0, %9, %17;\n\t"
+        "mul.wide.u32 o0, %10, %17;\n\t"
+        "mul.wide.u32 e1, %11, %17;\n\t"
+        "mul.wide.u32 o1, %12, %17;\n\t"
+        "mul.wide.u32 e2, %13, %17;\n\t"
+        "mul.wide.u32 o2, %14, %17;\n\t"
+        "mul.wide.u32 e3, %15, %17;\n\t"
+        "mul.wide.u32 o3, %16, %17;\n\t"
+        "mov.b64 {el0, eh0}, e0;\n\t"
+        "mov.b64 {el1, eh1}, e1;\n\t"
+        "mov.b64 {el2, eh2}, e2;\n\t"
+        "mov.b64 {el3, eh3}, e3;\n\t"
+        "mov.b64 {ol0, oh0}, o0;\n\t"
+        "mov.b64 {ol1, oh1}, o1;\n\t"
+        "mov.b64 {ol2, oh2}, o2;\n\t"
+        "mov.b64 {ol3, oh3}, o3;\n\t"
+        "add.cc.u32 %0, %0, el0;\n\t"
+        "addc.cc.u32 %1, %1, eh0;\n\t"
+        "addc.cc.u32 %2, %2, el1;\n\t"
+        "addc.cc.u32 %3, %3, eh1;\n\t"
+        "addc.cc.u32 %4, %4, el2;\n\t"
+        "addc.cc.u32 %5, %5, eh2;\n\t"
+        "addc.cc.u32 %6, %6, el3;\n\t"
+        "addc.cc.u32 %7, %7, eh3;\n\t"
+        "addc.u32 %8, %8, 0;\n\t"
+        "add.cc.u32 %1, %1, ol0;\n\t"
+        "addc.cc.u32 %2, %2, oh0;\n\t"
+        "addc.cc.u32 %3, %3, ol1;\n\t"
+        "addc.cc.u32 %4, %4, oh1;\n\t"
+        "addc.cc.u32 %5, %5, ol2;\n\t"
+        "addc.cc.u32 %6, %6, oh2;\n\t"
+        "addc.cc.u32 %7, %7, ol3;\n\t"
+        "addc.u32 %8, %8, oh3;\n\t"
+        "}"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y));
+}
+// T += m * q with q as immediates
+__device__ __forceinline__ void mac_row_q(uint32_t (&t)[9], uint32_t m) {
+    asm volatile(
+        "{\n\t"
+        ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
+        ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
+        "mul.wide.u32 e0, %9, 0xf0000001;\n\t"
+        "mul.wide.u32 o0, %9, 0x43e1f593;\n\t"
+        "mul.wide.u32 e1, %9, 0x79b97091;\n\t"
+        "mul.wide.u32 o1, %9, 0x2833e848;\n\t"
+        "mul.wide.u32 e2, %9, 0x8181585d;\n\t"
+        "mul.wide.u32 o2, %9, 0xb85045b6;\n\t"
+        "mul.wide.u32 e3, %9, 0xe131a029;\n\t"
+        "mul.wide.u32 o3, %9, 0x30644e72;\n\t"
+        "mov.b64 {el0, eh0}, e0;\n\t"
+        "mov.b64 {el1, eh1}, e1;\n\t"
+        "mov.b64 {el2, eh2}, e2;\n\t"
+        "mov.b64 {el3, eh3}, e3;\n\t"
+        "mov.b64 {ol0, oh0}, o0;\n\t"
+        "mov.b64 {ol1, oh1}, o1;\n\t"
+        "mov.b64 {ol2, oh2}, o2;\n\t"
+        "mov.b64 {ol3, oh3}, o3;\n\t"
+        "add.cc.u32 %0, %0, el0;\n\t"
+        "addc.cc.u32 %1, %1, eh0;\n\t"
+        "addc.cc.u32 %2, %2, el1;\n\t"
+        "addc.cc.u32 %3, %3, eh1;\n\t"
+        "addc.cc.u32 %4, %4, el2;\n\t"
+        "addc.cc.u32 %5, %5, eh2;\n\t"
+        "addc.cc.u32 %6, %6, el3;\n\t"
+        "addc.cc.u32 %7, %7, eh3;\n\t"
+        "addc.u32 %8, %8, 0;\n\t"
+        "add.cc.u32 %1, %1, ol0;\n\t"
+        "addc.cc.u32 %2, %2, oh0;\n\t"
+        "addc.cc.u32 %3, %3, ol1;\n\t"
+        "addc.cc.u32 %4, %4, oh1;\n\t"
+        "addc.cc.u32 %5, %5, ol2;\n\t"
+        "addc.cc.u32 %6, %6, oh2;\n\t"
+        "addc.cc.u32 %7, %7, ol3;\n\t"
+        "addc.u32 %8, %8, oh3;\n\t"
+        "}"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(m));
+}
 
-__device__ __forceinline__ Fr mont_mul_chain(const Fr &a, const Fr &b) {
-    // E holds limbs at even alignment (E[0] is weight 2^0), O at odd alignment (O[0] is weight 2^32).
-    uint32_t E[9], O[9];
+__device__ __forceinline__ Fr mont_mul_wide(const Fr &a, const Fr &b) {
+    uint32_t t[9];
 #pragma unroll
-    for (int i = 0; i < 9; i++) { E[i] = 0; O[i] = 0; }
-    const uint32_t q[8] = {FR_Q0, FR_Q1, FR_Q2, FR_Q3, FR_Q4, FR_Q5, FR_Q6, FR_Q7};
-    uint32_t ao[8], qo[8];  // odd-limb views: x_odd[j] = x[j+1] so that mad_even(x_odd) multiplies limbs 1,3,5,7
-#pragma unroll
-    for (int j = 0; j < 7; j++) { ao[j] = a.v[j + 1]; qo[j] = q[j + 1]; }
-    ao[7] = 0; qo[7] = 0;
+    for (int i = 0; i < 9; i++) t[i] = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        uint32_t bi = b.v[i];
-        E[8] += Chain::mad_even(E, a.v, bi);
-        O[8] += Chain::mad_even(O, ao, bi);
-        uint32_t m = E[0] * FR_NP0;
-        E[8] += Chain::mad_even(E, q, m);
-        O[8] += Chain::mad_even(O, qo, m);
-        // now E[0] == 0.  T' = T >> 32 = (O + E[1]) + 2^32 * (E[2..8])
-        // new E' = O + E[1] (aligned at weight 2^0), new O' = E >> 64 (aligned at weight 2^32)
-        uint32_t nE[9], nO[9];
-        asm volatile(
-            "add.cc.u32 %0, %9, %18;\n\t"
-            "addc.cc.u32 %1, %10, 0;\n\t"
-            "addc.cc.u32 %2, %11, 0;\n\t"
-            "addc.cc.u32 %3, %12, 0;\n\t"
-            "addc.cc.u32 %4, %13, 0;\n\t"
-            "addc.cc.u32 %5, %14, 0;\n\t"
-            "addc.cc.u32 %6, %15, 0;\n\t"
-            "addc.cc.u32 %7, %16, 0;\n\t"
-            "addc.u32 %8, %17, 0;\n\t"
-            : "=r"(nE[0]), "=r"(nE[1]), "=r"(nE[2]), "=r"(nE[3]), "=r"(nE[4]), "=r"(nE[5]), "=r"(nE[6]),
-              "=r"(nE[7]), "=r"(nE[8])
-            : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
-              "r"(E[1]));
+        mac_row(t, a.v, b.v[i]);            // T += a * b_i          (T < 2^287)
+        uint32_t m = t[0] * FR_NP0;
+        mac_row_q(t, m);                    // T += m * q, T[0] == 0  (T < 2^288)
 #pragma unroll
-        for (int j = 0; j < 7; j++) nO[j] = E[j + 2];
-        nO[7] = 0; nO[8] = 0;
-#pragma unroll
-        for (int j = 0; j < 9; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+        for (int j = 0; j < 8; j++) t[j] = t[j + 1];   // T >>= 32 (register renaming after unrolling)
+        t[8] = 0;
     }
-    // T = E + O*2^32, < 2q
     Fr r;
-    asm volatile(
-        "add.cc.u32 %0, %8, 0;\n\t"
-        "addc.cc.u32 %1, %9, %16;\n\t"
-        "addc.cc.u32 %2, %10, %17;\n\t"
-        "addc.cc.u32 %3, %11, %18;\n\t"
-        "addc.cc.u32 %4, %12, %19;\n\t"
-        "addc.cc.u32 %5, %13, %20;\n\t"
-        "addc.cc.u32 %6, %14, %21;\n\t"
-        "addc.u32 %7, %15, %22;\n\t"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7])
-        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
-          "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
-    return reduce_once(r);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    return reduce_once(r);                  // T < 2q
 }
 #endif
 
 FR_HD Fr mont_mul(const Fr &a, const Fr &b) {
-#if defined(__CUDA_ARCH__) && defined(FR_USE_CHAIN)
-    return mont_mul_chain(a, b);
+#if defined(__CUDA_ARCH__) && !defined(FR_PORTABLE_MUL)
+    return mont_mul_wide(a, b);
 #else
     return mont_mul_portable(a, b);
 #endif

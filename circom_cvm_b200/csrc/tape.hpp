@@ -121,7 +121,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
             val_slot[v] = -1;
         }
         if (home_is_spill[v]) {
-            free_spill.push_back(val_home[v]);
+            free_spill.push_back(val_home[v] - out.n_wires);
             home_is_spill[v] = 0;
         }
         live_now--;

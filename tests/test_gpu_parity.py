@@ -187,3 +187,25 @@ def test_device_api_with_torch_buffers(E):
     for b in (0, 1, 511, 999):
         assert got[b][1] == poseidon.poseidon_hash(rows[b])
         assert got[b] == I.compute_witness(I.load(art.cvm), rows[b])
+
+
+def test_sha256_batch(E, tmp_path):
+    """Config 3 shape (bit-decomposition heavy): Sha256 over 64-bit messages, checked against hashlib for every
+    witness, against the CVM oracle for one, and through the R1CS check."""
+    from tools.circuitgen.circuits import sha256
+    art = circuit("sha256_64")
+    rng = random.Random(17)
+    rows = [[rng.randrange(2) for _ in range(64)] for _ in range(300)]
+    rows[7] = [M.Q - 1] + [0] * 63                        # not a bit: asserts must flag it
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    _write_r1cs(art, tmp_path / "s.r1cs")
+    r = E.R1cs(str(tmp_path / "s.r1cs"))
+    wt, st, bad = wc.calculate_checked(rows, r)
+    assert st[7] == E.ST_ASSERT and bad[7] != E.NO_BAD
+    ok = [i for i in range(len(rows)) if i != 7]
+    assert not st[ok].any() and (bad[ok] == E.NO_BAD).all()
+    vals = E.le_to_ints(wt[:, 1:257, :])
+    for i in ok:
+        assert vals[i] == sha256.sha256_bits(rows[i])
+    full = E.le_to_ints(wt[3:4])[0]
+    assert full == I.compute_witness(I.load(art.cvm), rows[3])

@@ -98,3 +98,28 @@ def test_unsupported_programs_are_rejected_with_a_reason(cvmlib):
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text=text)
     assert e.value.code == -3
+
+
+def test_sha256_circuit_matches_hashlib(cvmlib):
+    """Sha256(64 bits): one compression block, ~34K constraints.  The compiled tape must hash like hashlib
+    (FIPS 180-4) and its witness must satisfy every R1CS constraint."""
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.circuits import sha256
+    art = circuit("sha256_64")
+    assert len(art.constraints) > 30000
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    tape, consts = wc.tape()
+    rng = random.Random(5)
+    for _ in range(2):
+        bits = [rng.randrange(2) for _ in range(64)]
+        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, bits)
+        assert status == 0
+        w = rows[:wc.n_wires]
+        assert w[1:257] == sha256.sha256_bits(bits)
+        for (a, b, c) in art.constraints:
+            ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
+            assert (ev(a) * ev(b) - ev(c)) % M.Q == 0
+    # a non-bit input breaks the bit decompositions downstream (BinSum: lin === lout)
+    bad = [M.Q - 1] + [0] * 63
+    rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, bad)
+    assert status == 1

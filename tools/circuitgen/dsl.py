@@ -57,6 +57,11 @@ class Expr:
     def __rpow__(self, o): return self._rb("pow", o)
     def __lshift__(self, o): return self._b("shl", o)
     def __rshift__(self, o): return self._b("shr", o)
+    def __rlshift__(self, o): return self._rb("shl", o)
+    def __rrshift__(self, o): return self._rb("shr", o)
+    def __rmod__(self, o): return self._rb("mod", o)
+    def __ror__(self, o): return self._rb("bor", o)
+    def __rxor__(self, o): return self._rb("bxor", o)
     def __and__(self, o): return self._b("band", o)
     def __rand__(self, o): return self._rb("band", o)
     def __or__(self, o): return self._b("bor", o)
