@@ -519,6 +519,37 @@ extern "C" int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8
     return CVMGPU_OK;
 }
 
+extern "C" int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_second) {
+    if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available");
+    uint4 *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 32));
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const uint32_t iters = 2048;
+    unsigned blocks = (unsigned)prop.multiProcessorCount * (unsigned)std::max(1, ctas_per_sm);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        if (variant == 0) kern::mulbench_kernel<0><<<blocks, 128>>>(d, iters, 7u + rep);
+        else kern::mulbench_kernel<1><<<blocks, 128>>>(d, iters, 7u + rep);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (muls_per_second) *muls_per_second = (double)blocks * 128.0 * iters * 2.0 / (best * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return CVMGPU_OK;
+}
+
 extern "C" int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms_out) {
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available");
     uint32_t *d = nullptr;
@@ -535,8 +566,15 @@ extern "C" int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms_ou
     float best = 1e30f;
     for (int rep = 0; rep < 5; rep++) {
         CUDA_TRY(cudaEventRecord(e0));
-        if (kind == 0) kern::imad_kernel<0><<<blocks, 256>>>(d, iters, 12345u + rep);
-        else kern::imad_kernel<1><<<blocks, 256>>>(d, iters, 12345u + rep);
+        switch (kind) {
+            case 0: kern::imad_kernel<0><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 1: kern::imad_kernel<1><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 2: kern::imad_kernel<2><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 3: kern::imad_kernel<3><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 4: kern::imad_kernel<4><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 5: kern::imad_kernel<5><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            default: kern::imad_kernel<6><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+        }
         CUDA_TRY(cudaEventRecord(e1));
         CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0;

@@ -194,14 +194,14 @@ FR_HD Fr mont_mul_portable(const Fr &a, const Fr &b) {
     return reduce_once(r);
 }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // Device formulation.  Per b-limb ("row"): the eight 32x32->64 products a[j]*b_i come from mul.wide.u32
 // (IMAD.WIDE.U32 with a zero addend: no register-pair set-up moves).  The products of the EVEN limbs occupy
 // disjoint 64-bit windows (columns 2k, 2k+1), so they form one 256-bit number that is added to T with a single
 // add.cc/addc.cc chain; the products of the ODD limbs form a second number shifted by 32 bits.  Hence
 // 8 IMAD.WIDE + 17 carry-chain adds per 8 multiply-accumulates, with the multiplies on the FMA pipe and the
 // adds on the ALU pipe.  The reduction row (m*q) has the same shape with q as immediates.
-__device__ __forceinline__ void mac_row(uint32_t (&t)[9], const uint32_t (&x)[8], uint32_t y) {
+__device__ __forceinline__ void mac_row(uint32_t *t, const uint32_t *x, uint32_t y) {
     asm volatile(
         "{\n\t"
         ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
@@ -244,7 +244,7 @@ __device__ __forceinline__ void mac_row(uint32_t (&t)[9], const uint32_t (&x)[8]
         : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y));
 }
 // T += m * q with q as immediates
-__device__ __forceinline__ void mac_row_q(uint32_t (&t)[9], uint32_t m) {
+__device__ __forceinline__ void mac_row_q(uint32_t *t, uint32_t m) {
     asm volatile(
         "{\n\t"
         ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
@@ -304,6 +304,60 @@ __device__ __forceinline__ Fr mont_mul_wide(const Fr &a, const Fr &b) {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = t[i];
     return reduce_once(r);                  // T < 2q
+}
+
+// ---- lazy-reduction dot products ---------------------------------------------------------------------
+// sum_i c_i * v_i (all Montgomery) with ONE Montgomery reduction per <= 16 terms: each term costs the 64
+// multiply-accumulates of the plain 8x8 product instead of the 136 of a full Montgomery multiplication.
+struct Wide {
+    uint32_t t[17];
+};
+__device__ __forceinline__ void wide_zero(Wide &T) {
+#pragma unroll
+    for (int i = 0; i < 17; i++) T.t[i] = 0;
+}
+// T += c * v   (512-bit product; c, v < q so the product is < 2^508 and the 9-limb windows never overflow)
+__device__ __forceinline__ void wide_mac(Wide &T, const Fr &c, const Fr &v) {
+    uint32_t P[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) P[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) mac_row(P + i, c.v, v.v[i]);
+    uint64_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        uint64_t s = (uint64_t)T.t[k] + P[k] + carry;
+        T.t[k] = (uint32_t)s;
+        carry = s >> 32;
+    }
+    T.t[16] += (uint32_t)carry;
+}
+// Montgomery reduction of T < 16*q^2: (T + m*q) / 2^256 < 4.03*q, then conditional subtractions
+__device__ __forceinline__ Fr wide_reduce(Wide &T) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = T.t[i] * FR_NP0;
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint64_t p = (uint64_t)m * qlimb(j) + T.t[i + j] + carry;
+            T.t[i + j] = (uint32_t)p;
+            carry = p >> 32;
+        }
+#pragma unroll
+        for (int k = i + 8; k < 17; k++) {
+            uint64_t s2 = (uint64_t)T.t[k] + carry;
+            T.t[k] = (uint32_t)s2;
+            carry = s2 >> 32;
+        }
+    }
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = T.t[8 + i];
+    // T.t[16] == 0 (value < 4.03 q < 2^256)
+#pragma unroll
+    for (int k = 0; k < 4; k++) r = reduce_once(r);
+    return r;
 }
 #endif
 

@@ -275,7 +275,10 @@ struct R1csParams {
 };
 
 __device__ __forceinline__ Fr lc_eval(const R1csParams &p, uint32_t beg, uint32_t end, uint64_t w) {
-    Fr acc = fr::zero();
+    Fr acc = fr::zero();          // +-1 terms: plain field add/sub
+    fr::Wide T;                   // general coefficients: unreduced 512-bit accumulator (lazy reduction)
+    fr::wide_zero(T);
+    uint32_t pending = 0;
     for (uint32_t t = beg; t < end; t++) {
         uint2 term = __ldg(p.terms + t);
         const uint4 *src = p.store + ((uint64_t)term.x * 2) * p.bstride + w;
@@ -284,9 +287,15 @@ __device__ __forceinline__ Fr lc_eval(const R1csParams &p, uint32_t beg, uint32_
         else if (term.y == 1) acc = fr::sub(acc, v);
         else {
             Fr c = unpack(__ldg(p.coefs + 2 * (uint64_t)term.y), __ldg(p.coefs + 2 * (uint64_t)term.y + 1));
-            acc = fr::add(acc, fr::mont_mul(c, v));
+            fr::wide_mac(T, c, v);
+            if (++pending == 16) {
+                acc = fr::add(acc, fr::wide_reduce(T));
+                fr::wide_zero(T);
+                pending = 0;
+            }
         }
     }
+    if (pending) acc = fr::add(acc, fr::wide_reduce(T));
     return acc;
 }
 
@@ -362,19 +371,61 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t *out, uint32_t iters
     uint32_t a0 = x, a1 = x + 1, a2 = x + 2, a3 = x + 3, a4 = x + 4, a5 = x + 5, a6 = x + 6, a7 = x + 7;
     uint64_t d0 = x, d1 = x + 1, d2 = x + 2, d3 = x + 3, d4 = x + 4, d5 = x + 5, d6 = x + 6, d7 = x + 7;
     for (uint32_t i = 0; i < iters; i++) {
-        if (KIND == 0) {
+        if (KIND == 0) {        // mad.lo + mad.hi pair = one 32x32->64 multiply-accumulate
 #define STEP(r) asm volatile("mad.lo.u32 %0, %0, %1, %0;\n\tmad.hi.u32 %0, %0, %1, %0;" : "+r"(r) : "r"(y));
             STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
 #undef STEP
-        } else {
+        } else if (KIND == 1) { // mad.wide.u32
 #define STEPW(r) asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(r) : "r"(y));
             STEPW(d0) STEPW(d1) STEPW(d2) STEPW(d3) STEPW(d4) STEPW(d5) STEPW(d6) STEPW(d7)
 #undef STEPW
+        } else if (KIND == 2) { // mad.lo only (2 per step so that the op count matches kind 0)
+#define STEP(r) asm volatile("mad.lo.u32 %0, %0, %1, %0;\n\tmad.lo.u32 %0, %0, %1, %0;" : "+r"(r) : "r"(y));
+            STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
+#undef STEP
+        } else if (KIND == 3) { // mad.hi only
+#define STEP(r) asm volatile("mad.hi.u32 %0, %0, %1, %0;\n\tmad.hi.u32 %0, %0, %1, %0;" : "+r"(r) : "r"(y));
+            STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
+#undef STEP
+        } else if (KIND == 4) { // carry chain of 8 adds (IADD3.X)
+            asm volatile(
+                "add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %8;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.cc.u32 %3, %3, %8;\n\t"
+                "addc.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %8;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %8;\n\t"
+                "add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %8;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.cc.u32 %3, %3, %8;\n\t"
+                "addc.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %8;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %8;"
+                : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(y));
+        } else if (KIND == 5) { // independent plain adds (IADD3)
+#define STEP(r) asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %1;" : "+r"(r) : "r"(y));
+            STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
+#undef STEP
+        } else {                // mad.lo.cc / madc.hi.cc chain (8 instructions)
+            asm volatile(
+                "mad.lo.cc.u32 %0, %0, %8, %0;\n\tmadc.hi.cc.u32 %1, %1, %8, %1;\n\tmadc.lo.cc.u32 %2, %2, %8, %2;\n\t"
+                "madc.hi.cc.u32 %3, %3, %8, %3;\n\tmadc.lo.cc.u32 %4, %4, %8, %4;\n\tmadc.hi.cc.u32 %5, %5, %8, %5;\n\t"
+                "madc.lo.cc.u32 %6, %6, %8, %6;\n\tmadc.hi.u32 %7, %7, %8, %7;\n\t"
+                "mad.lo.cc.u32 %0, %0, %8, %0;\n\tmadc.hi.cc.u32 %1, %1, %8, %1;\n\tmadc.lo.cc.u32 %2, %2, %8, %2;\n\t"
+                "madc.hi.cc.u32 %3, %3, %8, %3;\n\tmadc.lo.cc.u32 %4, %4, %8, %4;\n\tmadc.hi.cc.u32 %5, %5, %8, %5;\n\t"
+                "madc.lo.cc.u32 %6, %6, %8, %6;\n\tmadc.hi.u32 %7, %7, %8, %7;"
+                : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(y));
         }
     }
     uint32_t acc = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ (uint32_t)(d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7) ^
                    (uint32_t)((d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7) >> 32);
     if (acc == 0x12345678u) out[0] = acc;   // keep the chains alive
+}
+
+// ---- field-multiplication throughput probe: two independent dependent-chains of Montgomery products per thread
+template <int VARIANT>
+__global__ void __launch_bounds__(128) mulbench_kernel(uint4 *out, uint32_t iters, uint32_t seed) {
+    Fr x = fr::one_mont(), y = fr::r2_mont(), z = fr::half_q();
+    x.v[0] += threadIdx.x + seed;
+    z.v[1] ^= blockIdx.x;
+    for (uint32_t i = 0; i < iters; i++) {
+        if (VARIANT == 0) { x = fr::mont_mul_portable(x, y); z = fr::mont_mul_portable(z, y); }
+        else { x = fr::mont_mul_wide(x, y); z = fr::mont_mul_wide(z, y); }
+    }
+    Fr r = fr::add(x, z);
+    if (r.v[0] == 0x12345678u && r.v[7] == 1u) pack(r, out[0], out[1]);
 }
 
 }  // namespace kern

@@ -33,7 +33,7 @@ EXPORTS = [
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
     "cvmgpu_witness_import_dev",
-    "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak",
+    "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak", "cvmgpu_mul_peak",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
     L.cvmgpu_fr_host_op.argtypes = [c_char_p, c_char_p, c_char_p, c_char_p]
     L.cvmgpu_fr_device_op.argtypes = [c_char_p, c_void_p, c_void_p, c_void_p, c_uint64]
     L.cvmgpu_imad_peak.argtypes = [c_int, POINTER(c_double), POINTER(c_double)]
+    L.cvmgpu_mul_peak.argtypes = [c_int, c_int, POINTER(c_double)]
     L.cvmgpu_set_device.argtypes = [c_int]
     _LIB = L
     return L
@@ -284,6 +285,12 @@ def fr_device_op(op, a_list, b_list):
     out = np.empty((n, 32), dtype=np.uint8)
     _check(lib().cvmgpu_fr_device_op(op.encode(), _ptr(a), _ptr(b), _ptr(out), n))
     return le_to_ints(out)
+
+
+def mul_peak(variant, ctas_per_sm):
+    v = c_double()
+    _check(lib().cvmgpu_mul_peak(variant, ctas_per_sm, byref(v)))
+    return v.value
 
 
 def imad_peak(kind):

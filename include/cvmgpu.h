@@ -137,9 +137,13 @@ int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, 
 int cvmgpu_fr_host_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out);
 /* same operations executed by a CUDA kernel over n element pairs (device self-test of csrc/fr.cuh) */
 int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n);
-/* dependency-free IMAD micro-benchmark: returns 32x32->64 multiply-accumulates per second; kind 0 = mad.lo+mad.hi
- * pairs (u32), 1 = mad.wide (u64 accumulate) */
+/* dependency-free integer-pipe micro-benchmark.  The returned rate counts 8 "units" per thread and iteration, where a
+ * unit is: kind 0 one mad.lo+mad.hi pair, 1 one mad.wide.u32 (both = one 32x32->64 multiply-accumulate), 2 two mad.lo,
+ * 3 two mad.hi, 4 two addc (carry chain), 5 two add, 6 two mad{c}.{lo,hi}.cc (carry chain on the multiply pipe). */
 int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms);
+/* register-resident Montgomery-multiplication throughput (no memory traffic): variant 0 = portable 64-bit CIOS,
+ * 1 = mul.wide formulation used by the kernels; ctas_per_sm x 128 threads per SM. */
+int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_second);
 
 #ifdef __cplusplus
 }
