@@ -23,18 +23,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "witnesses/sec (Poseidon(2) witness generation + R1CS check)"
 UNIT = "witnesses/s"
 MACS_PER_MUL = 136      # 8x8 + 8x8 + 8 32x32->64 multiply-accumulates per BN254 Montgomery product
 
+# BASELINE.json configs: [1] Poseidon(2) x 1M (the configuration the metric is quoted on: default), [2] Sha256(512) x 64K
+WORKLOADS = {
+    "poseidon2": {"label": "Poseidon(2)", "module": "poseidon", "fn": "Poseidon", "args": (2,), "batch": 1 << 20,
+                  "chunk": 1 << 20, "e2e_batch": 1 << 17, "bits": False, "ref": "poseidon2_bench"},
+    "sha256_512": {"label": "Sha256(512 bits)", "module": "sha256", "fn": "Sha256", "args": (512,), "batch": 1 << 16,
+                   "chunk": 1 << 15, "e2e_batch": 1 << 10, "bits": True, "ref": "sha256_512"},
+}
+WL = WORKLOADS["poseidon2"]
+METRIC = "witnesses/sec (Poseidon(2) witness generation + R1CS check)"
+
+
+def select_workload(name):
+    global WL, METRIC
+    WL = WORKLOADS[name]
+    METRIC = "witnesses/sec (%s witness generation + R1CS check)" % WL["label"]
+
 
 def build_workload(tmpdir):
+    import importlib
+
     from circom_cvm_b200 import formats
     from tools.circuitgen.build import compile_circuit
-    from tools.circuitgen.circuits import poseidon
-    art = compile_circuit(poseidon.Poseidon, (2,), name="poseidon2")
-    cvm_path = os.path.join(tmpdir, "poseidon2.cvm")
-    r1cs_path = os.path.join(tmpdir, "poseidon2.r1cs")
+    mod = importlib.import_module("tools.circuitgen.circuits." + WL["module"])
+    name = WL["ref"].replace("_bench", "")
+    art = compile_circuit(getattr(mod, WL["fn"]), WL["args"], name=name)
+    cvm_path = os.path.join(tmpdir, name + ".cvm")
+    r1cs_path = os.path.join(tmpdir, name + ".r1cs")
     with open(cvm_path, "w") as f:
         f.write(art.cvm)
     formats.write_r1cs(r1cs_path, art.constraints, art.n_wires, art.n_pub_out, art.n_pub_in, art.n_prv_in,
@@ -109,15 +127,16 @@ def cpu_baseline_port(art, seconds=12.0):
     rng = random.Random(0xC1C00001)
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
-        I.compute_witness(prog, [rng.randrange(I.M.Q) for _ in range(art.n_inputs)])
+        I.compute_witness(prog, [rng.randrange(2 if WL["bits"] else I.M.Q) for _ in range(art.n_inputs)])
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d Poseidon(2) witnesses, pure-Python CVM oracle (oracle/cvm_interp.py), witness generation only" % n}
+            "sample": "%d %s witnesses, pure-Python CVM oracle (oracle/cvm_interp.py), witness generation only"
+                      % (n, WL["label"])}
 
 
 def reference_binary():
-    p = os.path.join(ROOT, "oracle", "_ref", "poseidon2_bench")
+    p = os.path.join(ROOT, "oracle", "_ref", WL["ref"])
     return p if os.path.exists(p) else None
 
 
@@ -127,7 +146,8 @@ def cpu_baseline_reference(n_threads, seconds=10.0):
     exe = reference_binary()
     if exe is None:
         return None
-    procs = [subprocess.Popen([exe, "--bench", str(seconds), str(1234 + i)], stdout=subprocess.PIPE, text=True, cwd=os.path.dirname(exe))
+    procs = [subprocess.Popen([exe, "--bench", str(seconds), str(1234 + i), "1" if WL["bits"] else "0"],
+                              stdout=subprocess.PIPE, text=True, cwd=os.path.dirname(exe))
              for i in range(n_threads)]
     total, count = 0.0, 0
     for p in procs:
@@ -139,9 +159,9 @@ def cpu_baseline_reference(n_threads, seconds=10.0):
         except Exception:
             return None
     return {"value": total, "unit": UNIT, "cores": n_threads, "kind": "reference",
-            "sample": "%d Poseidon(2) witnesses over %d processes x %.0f s: reference common/calcwit.cpp + generic/fr.cpp "
+            "sample": "%d %s witnesses over %d processes x %.0f s: reference common/calcwit.cpp + generic/fr.cpp "
                       "(--no_asm arithmetic; bn128/fr.asm cannot be assembled here) running the circuit body emitted "
-                      "by tools/circuitgen in the WriteC shapes; run(ctx) only" % (count, n_threads, seconds)}
+                      "by tools/circuitgen in the WriteC shapes; run(ctx) only" % (count, WL["label"], n_threads, seconds)}
 
 
 def run_reference_arm(args, art):
@@ -168,7 +188,10 @@ def run_reference_arm(args, art):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * (time.perf_counter() - t0) / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr)",
-            "data": "synthetic", "config": {"workload": "Poseidon(2) witness generation on host cores, bounded sample per step"},
+            "data": "synthetic",
+            "config": {"workload": "%s batch of %d random inputs per GPU: witness generation + R1CS check" % (WL["label"], WL["batch"]),
+                       "reference_arm": "witness generation (run(ctx)) on the host cores, bounded sample per step; the reference "
+                                        "has no R1CS checker (SURVEY F4)"},
             "cpu_baseline": res,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -180,11 +203,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=1 << 20, help="witnesses per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=1 << 17)
+    ap.add_argument("--workload", default="poseidon2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="witnesses per GPU per step (default: the BASELINE config's)")
+    ap.add_argument("--chunk", type=int, default=0, help="witnesses per kernel launch (the value store is sized for it)")
+    ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out")
     args = ap.parse_args()
+    select_workload(args.workload)
+    args.batch = args.batch or WL["batch"]
+    args.chunk = min(args.batch, args.chunk or WL["chunk"])
+    args.e2e_batch = args.e2e_batch or WL["e2e_batch"]
 
     tmpdir = tempfile.mkdtemp(prefix="cvmbench_")
     art, cvm_path, r1cs_path = build_workload(tmpdir)
@@ -215,19 +245,33 @@ def main():
     wc = E.WitnessCalculator(cvm_path=cvm_path, n_slots=args.slots)
     r1 = E.R1cs(r1cs_path)
     info, rinfo = wc.info.asdict(), r1.info.asdict()
-    B = args.batch
+    B, CH = args.batch, args.chunk
+    n_chunks = (B + CH - 1) // CH
     g = torch.Generator(device=dev)
     g.manual_seed(0xC1C00001 + rank)
-    inputs = torch.randint(0, 256, (B, wc.n_inputs, 32), dtype=torch.uint8, device=dev, generator=g)
-    inputs[:, :, 31] &= 0x1F          # < 2^253 < q: canonical field elements
-    store = torch.empty(wc.store_bytes(B), dtype=torch.uint8, device=dev)
+    if WL["bits"]:
+        inputs = torch.zeros((B, wc.n_inputs, 32), dtype=torch.uint8, device=dev)
+        inputs[:, :, 0] = torch.randint(0, 2, (B, wc.n_inputs), dtype=torch.uint8, device=dev, generator=g)
+    else:
+        inputs = torch.randint(0, 256, (B, wc.n_inputs, 32), dtype=torch.uint8, device=dev, generator=g)
+        inputs[:, :, 31] &= 0x1F          # < 2^253 < q: canonical field elements
+    store = torch.empty(wc.store_bytes(CH), dtype=torch.uint8, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     bad = torch.empty(B, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
+    def gen(k):
+        n = min(CH, B - k * CH)
+        wc.run_dev(inputs[k * CH:], n, CH, store, status[k * CH:], stream)
+
+    def check(k):
+        n = min(CH, B - k * CH)
+        r1.check_dev(store, n, CH, bad[k * CH:], stream)
+
     def step():
-        wc.run_dev(inputs, B, B, store, status, stream)
-        r1.check_dev(store, B, B, bad, stream)
+        for k in range(n_chunks):
+            gen(k)
+            check(k)
 
     for _ in range(args.warmup):
         step()
@@ -237,15 +281,16 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
+    n_launch = args.steps * n_chunks
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * n_launch)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
-    for k in range(args.steps):
+    for k in range(n_launch):
         ev[3 * k].record()
-        wc.run_dev(inputs, B, B, store, status, stream)
+        gen(k % n_chunks)
         ev[3 * k + 1].record()
-        r1.check_dev(store, B, B, bad, stream)
+        check(k % n_chunks)
         ev[3 * k + 2].record()
     t_end.record()
     torch.cuda.synchronize()
@@ -254,8 +299,9 @@ def main():
     if rank == 0:
         sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
-    ms_tape = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)) / args.steps
-    ms_check = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)) / args.steps
+    # per step (= n_chunks launches of each kernel)
+    ms_tape = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(n_launch)) / args.steps
+    ms_check = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(n_launch)) / args.steps
     n_fail = int((status != 0).sum()) + int((bad != -1).sum())
     t = torch.tensor([ms_total, ms_tape, ms_check, float(n_fail)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -269,25 +315,27 @@ def main():
     Be = min(args.e2e_batch, B)
     h_in = torch.empty((Be, wc.n_inputs, 32), dtype=torch.uint8).pin_memory()
     h_in.copy_(inputs[:Be].cpu())
+    del store                          # the host-buffer API brings its own device buffers
+    torch.cuda.empty_cache()
     h_wt = torch.empty((Be, wc.n_wires, 32), dtype=torch.uint8).pin_memory()
     h_st = torch.empty(Be, dtype=torch.int32).pin_memory()
     h_bad = torch.empty(Be, dtype=torch.int32).pin_memory()
-    for _ in range(2):
+    for _ in range(0 if args.skip_e2e else 2):
         wc.calculate_into(h_in, h_wt, h_st, r1, h_bad)
     if world > 1:
         dist.barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = 0 if args.skip_e2e else max(2, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         wc.calculate_into(h_in, h_wt, h_st, r1, h_bad)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = (time.perf_counter() - t0) / max(1, e2e_steps)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e_ok = int((h_st != 0).sum()) == 0 and int((h_bad != -1).sum()) == 0
-    e2e = {"value": world * Be / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Be * wc.n_inputs * 32,
+    e2e = None if args.skip_e2e else {"value": world * Be / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Be * wc.n_inputs * 32,
            "d2h_bytes_per_step": Be * (wc.n_wires * 32 + 8), "batch_per_gpu": Be, "ms_per_step": 1000 * e2e_s,
            "all_witnesses_valid": bool(e2e_ok),
            "api": "WitnessCalculator.calculate_into -> cvmgpu_witness_batch_checked (full .wtns rows returned)"}
@@ -307,7 +355,7 @@ def main():
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
     tape_bytes = B * (info["tape_st"] + info["tape_ld"]) * 32 + B * info["n_inputs"] * 32
-    check_bytes_alg = B * rinfo["n_wires"] * 32 + B * 4 + rinfo["nnz"] * 8 + 3 * (rinfo["n_constraints"] + 1) * 4
+    check_bytes_alg = B * rinfo["n_wires"] * 32 + B * 4 + n_chunks * (rinfo["nnz"] * 8 + 3 * (rinfo["n_constraints"] + 1) * 4)
     roofline = {
         "kernel": "tape_kernel", "bound": "imad", "unit": "Tmac/s",
         "achieved": achieved / 1e12, "peak": peak_macs / 1e12, "frac": achieved / peak_macs,
@@ -337,17 +385,18 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 (BN254 Fr, Montgomery)", "data": "synthetic",
-        "config": {"workload": "Poseidon(2) batch of %d random inputs per GPU: witness generation + R1CS check" % B,
-                   "circuit": "tools/circuitgen Poseidon(2) (circomlib 0.5.x structure), %d signals, %d wires, %d constraints"
-                              % (info["n_signals"], info["n_wires"], rinfo["n_constraints"]),
-                   "batch_per_gpu": B, "l2": "working set %.1f GB per step >> 126 MB L2" % (wc.store_bytes(B) / 1e9),
+        "config": {"workload": "%s batch of %d random inputs per GPU: witness generation + R1CS check" % (WL["label"], B),
+                   "circuit": "tools/circuitgen %s (circomlib structure), %d signals, %d wires, %d constraints"
+                              % (WL["label"], info["n_signals"], info["n_wires"], rinfo["n_constraints"]),
+                   "batch_per_gpu": B, "witnesses_per_launch": CH,
+                   "l2": "working set %.1f GB per launch >> 126 MB L2" % (wc.store_bytes(CH) / 1e9),
                    "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                    "n_slots": info["n_slots"], "tape_len": info["tape_len"], "failures": n_fail},
         "kernels_ms": {"tape_kernel": ms_tape, "r1cs_kernel": ms_check},
         "witnesses_per_s_gen_only": world * B / (ms_tape * 1e-3),
         "constraints_per_s_check_only": world * B * rinfo["n_constraints"] / (ms_check * 1e-3),
         "roofline": roofline, "roofline_hbm": roofline_hbm,
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * n_launch,
         "clocks": sampler.summary(),
         "program": info, "r1cs": rinfo,
     }

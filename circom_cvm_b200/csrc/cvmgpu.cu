@@ -55,6 +55,7 @@ struct DevBuf {
 struct cvmgpu_program {
     tape::Tape tape;
     tape::TraceStats tstats;
+    tape::BatchInvStats binv;
     std::vector<fr::Fr> consts_mont;
     uint64_t n_signals = 0;
     uint32_t n_inputs = 0, n_outputs = 0;
@@ -66,7 +67,7 @@ struct cvmgpu_program {
 struct cvmgpu_r1cs {
     r1cs::File file;
     int device = -1;
-    DevBuf d_ptr, d_terms, d_coefs, d_store, d_wtns, d_bad;
+    DevBuf d_ptr, d_split, d_terms, d_coefs, d_store, d_wtns, d_bad;
 };
 
 extern "C" const char *cvmgpu_last_error(void) { return g_err.c_str(); }
@@ -89,6 +90,7 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
     try {
         tape::Tracer tr(parser.prog);
         tr.trace();
+        p->binv = tape::batch_inversions(tr);
         if (n_slots == 0) {
             // Fewer slots per witness = more resident CTAs per SM (4 KiB of shared memory per slot and CTA), but more
             // reloads/spills through HBM.  Pick the candidate with the best (work / resident warps) estimate; the
@@ -171,6 +173,9 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_spill_st = p->tape.stats.n_spill_st;
     info->n_consts = (uint32_t)p->consts_mont.size();
     info->dyn_branches = (uint32_t)p->tstats.dyn_branches;
+    info->ref_div = p->tstats.ref_div;
+    info->tape_inv = p->tape.stats.n_inv;
+    info->tape_sel = p->tape.stats.n_sel;
     return CVMGPU_OK;
 }
 
@@ -390,7 +395,7 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
 
 extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
     if (!r) return;
-    r->d_ptr.release(); r->d_terms.release(); r->d_coefs.release();
+    r->d_ptr.release(); r->d_split.release(); r->d_terms.release(); r->d_coefs.release();
     r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
     delete r;
 }
@@ -400,7 +405,7 @@ static int upload_r1cs(cvmgpu_r1cs *r) {
     CUDA_TRY(cudaGetDevice(&dev));
     if (r->device == dev && r->d_ptr.p) return CVMGPU_OK;
     if (r->device != dev) {
-        r->d_ptr = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf();
+        r->d_ptr = DevBuf(); r->d_split = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf();
         r->d_store = DevBuf(); r->d_wtns = DevBuf(); r->d_bad = DevBuf();
     }
     const r1cs::File &f = r->file;
@@ -408,9 +413,11 @@ static int upload_r1cs(cvmgpu_r1cs *r) {
     cm.reserve(f.coefs.size());
     for (const fr::Fr &c : f.coefs) cm.push_back(fr::to_mont(c));
     if (int rc = r->d_ptr.ensure(std::max<size_t>(16, f.ptr.size() * 4))) return rc;
+    if (int rc = r->d_split.ensure(std::max<size_t>(16, f.split.size() * 4))) return rc;
     if (int rc = r->d_terms.ensure(std::max<size_t>(16, f.terms.size() * 8))) return rc;
     if (int rc = r->d_coefs.ensure(cm.size() * 32)) return rc;
     CUDA_TRY(cudaMemcpy(r->d_ptr.p, f.ptr.data(), f.ptr.size() * 4, cudaMemcpyHostToDevice));
+    if (!f.split.empty()) CUDA_TRY(cudaMemcpy(r->d_split.p, f.split.data(), f.split.size() * 4, cudaMemcpyHostToDevice));
     if (!f.terms.empty()) CUDA_TRY(cudaMemcpy(r->d_terms.p, f.terms.data(), f.terms.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r->d_coefs.p, cm.data(), cm.size() * 32, cudaMemcpyHostToDevice));
     r->device = dev;
@@ -437,6 +444,7 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     }
     kern::R1csParams rp;
     rp.ptr = (const uint32_t *)r->d_ptr.p;
+    rp.split = (const uint32_t *)r->d_split.p;
     rp.terms = (const uint2 *)r->d_terms.p;
     rp.coefs = (const uint4 *)r->d_coefs.p;
     rp.n_cons = r->file.n_constraints;

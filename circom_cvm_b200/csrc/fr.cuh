@@ -309,54 +309,128 @@ __device__ __forceinline__ Fr mont_mul_wide(const Fr &a, const Fr &b) {
 // ---- lazy-reduction dot products ---------------------------------------------------------------------
 // sum_i c_i * v_i (all Montgomery) with ONE Montgomery reduction per <= 16 terms: each term costs the 64
 // multiply-accumulates of the plain 8x8 product instead of the 136 of a full Montgomery multiplication.
+// The 17-limb accumulator is updated row by row in place; the carry out of a row's 9-limb window goes to a
+// per-row overflow counter (weight 2^(32*(i+9))) that is folded in once, before the reduction.
+#define FR_ROW_ADDS_OVF                       \
+        "mov.b64 {el0, eh0}, e0;\n\t"         \
+        "mov.b64 {el1, eh1}, e1;\n\t"         \
+        "mov.b64 {el2, eh2}, e2;\n\t"         \
+        "mov.b64 {el3, eh3}, e3;\n\t"         \
+        "mov.b64 {ol0, oh0}, o0;\n\t"         \
+        "mov.b64 {ol1, oh1}, o1;\n\t"         \
+        "mov.b64 {ol2, oh2}, o2;\n\t"         \
+        "mov.b64 {ol3, oh3}, o3;\n\t"         \
+        "add.cc.u32 %0, %0, el0;\n\t"         \
+        "addc.cc.u32 %1, %1, eh0;\n\t"        \
+        "addc.cc.u32 %2, %2, el1;\n\t"        \
+        "addc.cc.u32 %3, %3, eh1;\n\t"        \
+        "addc.cc.u32 %4, %4, el2;\n\t"        \
+        "addc.cc.u32 %5, %5, eh2;\n\t"        \
+        "addc.cc.u32 %6, %6, el3;\n\t"        \
+        "addc.cc.u32 %7, %7, eh3;\n\t"        \
+        "addc.cc.u32 %8, %8, 0;\n\t"          \
+        "addc.u32 %9, %9, 0;\n\t"             \
+        "add.cc.u32 %1, %1, ol0;\n\t"         \
+        "addc.cc.u32 %2, %2, oh0;\n\t"        \
+        "addc.cc.u32 %3, %3, ol1;\n\t"        \
+        "addc.cc.u32 %4, %4, oh1;\n\t"        \
+        "addc.cc.u32 %5, %5, ol2;\n\t"        \
+        "addc.cc.u32 %6, %6, oh2;\n\t"        \
+        "addc.cc.u32 %7, %7, ol3;\n\t"        \
+        "addc.cc.u32 %8, %8, oh3;\n\t"        \
+        "addc.u32 %9, %9, 0;\n\t"
+// t[0..8] += x * y, carry out of t[8] counted in ovf
+__device__ __forceinline__ void mac_row_ovf(uint32_t *t, uint32_t &ovf, const uint32_t *x, uint32_t y) {
+    asm volatile(
+        "{\n\t"
+        ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
+        ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
+        "mul.wide.u32 e0, %10, %18;\n\t"
+        "mul.wide.u32 o0, %11, %18;\n\t"
+        "mul.wide.u32 e1, %12, %18;\n\t"
+        "mul.wide.u32 o1, %13, %18;\n\t"
+        "mul.wide.u32 e2, %14, %18;\n\t"
+        "mul.wide.u32 o2, %15, %18;\n\t"
+        "mul.wide.u32 e3, %16, %18;\n\t"
+        "mul.wide.u32 o3, %17, %18;\n\t"
+        FR_ROW_ADDS_OVF
+        "}"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(ovf)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y));
+}
+// t[0..8] += m * q, carry out of t[8] counted in ovf
+__device__ __forceinline__ void mac_row_q_ovf(uint32_t *t, uint32_t &ovf, uint32_t m) {
+    asm volatile(
+        "{\n\t"
+        ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
+        ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
+        "mul.wide.u32 e0, %10, 0xf0000001;\n\t"
+        "mul.wide.u32 o0, %10, 0x43e1f593;\n\t"
+        "mul.wide.u32 e1, %10, 0x79b97091;\n\t"
+        "mul.wide.u32 o1, %10, 0x2833e848;\n\t"
+        "mul.wide.u32 e2, %10, 0x8181585d;\n\t"
+        "mul.wide.u32 o2, %10, 0xb85045b6;\n\t"
+        "mul.wide.u32 e3, %10, 0xe131a029;\n\t"
+        "mul.wide.u32 o3, %10, 0x30644e72;\n\t"
+        FR_ROW_ADDS_OVF
+        "}"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(ovf)
+        : "r"(m));
+}
+
 struct Wide {
     uint32_t t[17];
+    uint32_t ovf[8];   // ovf[i] has the weight of t[i + 9]
 };
 __device__ __forceinline__ void wide_zero(Wide &T) {
 #pragma unroll
     for (int i = 0; i < 17; i++) T.t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) T.ovf[i] = 0;
 }
-// T += c * v   (512-bit product; c, v < q so the product is < 2^508 and the 9-limb windows never overflow)
+// T += c * v   (c, v < q; at most 16 terms between reductions so that T < 2^4 * q^2 < 2^512)
 __device__ __forceinline__ void wide_mac(Wide &T, const Fr &c, const Fr &v) {
-    uint32_t P[17];
 #pragma unroll
-    for (int i = 0; i < 17; i++) P[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) mac_row(P + i, c.v, v.v[i]);
-    uint64_t carry = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        uint64_t s = (uint64_t)T.t[k] + P[k] + carry;
-        T.t[k] = (uint32_t)s;
-        carry = s >> 32;
-    }
-    T.t[16] += (uint32_t)carry;
+    for (int i = 0; i < 8; i++) mac_row_ovf(T.t + i, T.ovf[i], c.v, v.v[i]);
 }
-// Montgomery reduction of T < 16*q^2: (T + m*q) / 2^256 < 4.03*q, then conditional subtractions
-__device__ __forceinline__ Fr wide_reduce(Wide &T) {
+// t[9..16] += ovf[0..7]
+__device__ __forceinline__ void wide_fold(Wide &T) {
+    asm volatile(
+        "add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(T.t[9]), "+r"(T.t[10]), "+r"(T.t[11]), "+r"(T.t[12]), "+r"(T.t[13]), "+r"(T.t[14]), "+r"(T.t[15]), "+r"(T.t[16])
+        : "r"(T.ovf[0]), "r"(T.ovf[1]), "r"(T.ovf[2]), "r"(T.ovf[3]), "r"(T.ovf[4]), "r"(T.ovf[5]), "r"(T.ovf[6]), "r"(T.ovf[7]));
+#pragma unroll
+    for (int i = 0; i < 8; i++) T.ovf[i] = 0;
+}
+// Montgomery reduction of T = sum of n products (n <= 16): (T + m*q) / 2^256 < q * (n * q / 2^256 + 1)
+// with q / 2^256 < 0.19, so ceil(0.19 n) conditional subtractions finish (1 for n <= 5).
+__device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
+    wide_fold(T);
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         uint32_t m = T.t[i] * FR_NP0;
-        uint64_t carry = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint64_t p = (uint64_t)m * qlimb(j) + T.t[i + j] + carry;
-            T.t[i + j] = (uint32_t)p;
-            carry = p >> 32;
-        }
-#pragma unroll
-        for (int k = i + 8; k < 17; k++) {
-            uint64_t s2 = (uint64_t)T.t[k] + carry;
-            T.t[k] = (uint32_t)s2;
-            carry = s2 >> 32;
-        }
+        mac_row_q_ovf(T.t + i, T.ovf[i], m);
     }
+    wide_fold(T);
     Fr r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = T.t[8 + i];
     // T.t[16] == 0 (value < 4.03 q < 2^256)
-#pragma unroll
-    for (int k = 0; k < 4; k++) r = reduce_once(r);
+    r = reduce_once(r);
+    if (n_terms > 5) {
+        r = reduce_once(r);
+        if (n_terms > 10) {
+            r = reduce_once(r);
+            r = reduce_once(r);
+        }
+    }
     return r;
 }
 #endif

@@ -47,46 +47,8 @@ struct TapeParams {
 
 __device__ __forceinline__ Fr mont_bool(bool b) { return b ? fr::one_mont() : fr::zero(); }
 
-// rarely used, heavy operations are kept out of line so that the hot loop stays small
-__device__ __noinline__ Fr op_div(const Fr &a, const Fr &b) { return fr::mont_mul(a, fr::mont_inv(b)); }
-__device__ __noinline__ Fr op_idivmod(const Fr &a, const Fr &b, bool want_rem, uint32_t &status) {
-    Fr ca = fr::from_mont(a), cb = fr::from_mont(b);
-    if (fr::is_zero(cb)) {
-        if (status == 0) status = tape::ST_DIVZERO;
-        return fr::zero();
-    }
-    Fr q, r;
-    fr::divmod(ca, cb, q, r);
-    return fr::to_mont(want_rem ? r : q);
-}
-__device__ __noinline__ Fr op_pow(const Fr &a, const Fr &b) { return fr::mont_pow_var(a, fr::from_mont(b)); }
-__device__ __noinline__ Fr op_shift(const Fr &a, const Fr &b, bool left) {
-    Fr ca = fr::from_mont(a), cb = fr::from_mont(b);
-    return fr::to_mont(left ? fr::shl(ca, cb) : fr::shr(ca, cb));
-}
-__device__ __noinline__ Fr op_bits(uint8_t op, const Fr &a, const Fr &b) {
-    Fr ca = fr::from_mont(a), cb = fr::from_mont(b), r;
-    switch (op) {
-        case tape::T_BAND: r = fr::band(ca, cb); break;
-        case tape::T_BOR: r = fr::bor(ca, cb); break;
-        case tape::T_BXOR: r = fr::bxor(ca, cb); break;
-        default: r = fr::bnot(ca); break;
-    }
-    return fr::to_mont(r);
-}
-__device__ __noinline__ Fr op_cmp(uint8_t op, const Fr &a, const Fr &b) {
-    Fr ca = fr::from_mont(a), cb = fr::from_mont(b);
-    bool r;
-    switch (op) {
-        case tape::T_LT: r = fr::lt_signed(ca, cb); break;
-        case tape::T_GT: r = fr::lt_signed(cb, ca); break;
-        case tape::T_LE: r = !fr::lt_signed(cb, ca); break;
-        default: r = !fr::lt_signed(ca, cb); break;
-    }
-    return mont_bool(r);
-}
 // canonical input (possibly >= q, like a decimal string fed to Fr_str2element) -> Montgomery
-__device__ __noinline__ Fr op_input(Fr v) {
+__device__ __forceinline__ Fr op_input(Fr v) {
     for (int k = 0; k < 6; k++) {
         Fr d;
         uint32_t borrow = fr::sub_raw(d, v, fr::modulus());
@@ -95,6 +57,86 @@ __device__ __noinline__ Fr op_input(Fr v) {
     return fr::to_mont(v);
 }
 
+// operand fetch: constant table (uniform address, L1-resident) or the thread's slot in shared memory
+__device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint4 *consts, uint32_t idx, bool is_const, uint32_t tid) {
+    uint4 lo, hi;
+    if (is_const) {
+        lo = __ldg(consts + 2 * (uint64_t)idx);
+        hi = __ldg(consts + 2 * (uint64_t)idx + 1);
+    } else {
+        lo = slots[(idx * 2) * CVM_NT + tid];
+        hi = slots[(idx * 2 + 1) * CVM_NT + tid];
+    }
+    return unpack(lo, hi);
+}
+
+// integer-view operations, division, logic: shared by the tape's slow path and the device self-test.
+// Operations that look at the integer leave Montgomery form first, as generic/fr.cpp does (one conversion site each
+// way, to keep the code small).
+__device__ __forceinline__ Fr slow_compute(uint32_t op, const Fr &a, const Fr &b, uint32_t &status) {
+    const bool logic = (op == tape::T_LAND || op == tape::T_LOR);
+    if (op == tape::T_INV) return fr::mont_inv(a);
+    if (op == tape::T_DIV) return fr::mont_mul(a, fr::mont_inv(b));
+    if (logic) {
+        bool x = !fr::is_zero(a), y = !fr::is_zero(b);
+        return mont_bool(op == tape::T_LAND ? (x && y) : (x || y));
+    }
+    const Fr cb = fr::from_mont(b);
+    if (op == tape::T_POW) return fr::mont_pow_var(a, cb);
+    const Fr ca = fr::from_mont(a);
+    Fr t = fr::zero();
+    switch (op) {
+        case tape::T_IDIV: case tape::T_MOD:
+            if (fr::is_zero(cb)) {
+                if (status == 0) status = tape::ST_DIVZERO;
+            } else {
+                Fr qt, rem;
+                fr::divmod(ca, cb, qt, rem);
+                t = (op == tape::T_MOD) ? rem : qt;
+            }
+            break;
+        case tape::T_SHL: t = fr::shl(ca, cb); break;
+        case tape::T_SHR: t = fr::shr(ca, cb); break;
+        case tape::T_BAND: t = fr::band(ca, cb); break;
+        case tape::T_BOR: t = fr::bor(ca, cb); break;
+        case tape::T_BXOR: t = fr::bxor(ca, cb); break;
+        case tape::T_BNOT: t = fr::bnot(ca); break;
+        case tape::T_LT: return mont_bool(fr::lt_signed(ca, cb));
+        case tape::T_GT: return mont_bool(fr::lt_signed(cb, ca));
+        case tape::T_LE: return mont_bool(!fr::lt_signed(cb, ca));
+        case tape::T_GE: return mont_bool(!fr::lt_signed(ca, cb));
+        default: return fr::zero();
+    }
+    return fr::to_mont(t);
+}
+
+// Everything that is not on the fast path of the tape loop (integer-view operations, division, inputs).  Out of
+// line, operands and result go through the slots, so that the hot loop keeps its working set in registers.
+__device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uint4 *consts, const uint4 *inputs,
+                                              uint32_t n_inputs, uint64_t w, uint32_t status) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t op = cur.x & 0xffu, flags = (cur.x >> 8) & 0xffu, dst = cur.x >> 16;
+    Fr r;
+    if (op == tape::T_INPUT) {
+        const uint4 *src = inputs + (w * n_inputs + cur.y) * 2;
+        r = op_input(unpack(src[0], src[1]));
+    } else {
+        Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+        Fr b = fr::zero();
+        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand(slots, consts, cur.z, flags & 2u, tid);
+        r = slow_compute(op, a, b, status);
+    }
+    uint4 lo, hi;
+    pack(r, lo, hi);
+    slots[(dst * 2) * CVM_NT + tid] = lo;
+    slots[(dst * 2 + 1) * CVM_NT + tid] = hi;
+    return status;
+}
+
+// One tape pass per witness.  Control flow is uniform (one instruction stream per circuit), so the branches on the
+// opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, SEL, EQ / NEQ / EQZ, BITC, the failure
+// checks and the value-store moves; the result of a producing instruction can be written to its witness wire by
+// the same instruction (flag bit 3).
 __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
     extern __shared__ uint4 slots[];
     const uint32_t tid = threadIdx.x;
@@ -102,91 +144,88 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
     const bool active = w < p.B;
     if (!active) w = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
     uint32_t status = 0;
+    uint4 *const wbase = p.store + w;
+    const uint64_t bstride = p.bstride;
+    const uint4 *const consts = p.consts;
 
     const uint4 *tp = reinterpret_cast<const uint4 *>(p.tape);
+    const uint32_t n_ins = p.n_ins;
     uint4 raw = __ldg(tp);
-    for (uint32_t pc = 0; pc < p.n_ins; pc++) {
-        uint4 cur = raw;
-        if (pc + 1 < p.n_ins) raw = __ldg(tp + pc + 1);   // prefetch the next instruction
+    for (uint32_t pc = 0; pc < n_ins; pc++) {
+        const uint4 cur = raw;
+        raw = __ldg(tp + min(pc + 1, n_ins - 1));   // prefetch the next instruction
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
-        Fr a, b;
-        if (op >= tape::T_ADD && op <= tape::T_FAIL_IF) {
-            if (flags & 1u) a = unpack(__ldg(p.consts + 2 * (uint64_t)cur.y), __ldg(p.consts + 2 * (uint64_t)cur.y + 1));
-            else a = unpack(slots[(cur.y * 2) * CVM_NT + tid], slots[(cur.y * 2 + 1) * CVM_NT + tid]);
-            if (op != tape::T_BNOT && op != tape::T_EQZ && op != tape::T_FAIL_IF) {
-                if (flags & 2u) b = unpack(__ldg(p.consts + 2 * (uint64_t)cur.z), __ldg(p.consts + 2 * (uint64_t)cur.z + 1));
-                else b = unpack(slots[(cur.z * 2) * CVM_NT + tid], slots[(cur.z * 2 + 1) * CVM_NT + tid]);
-            } else b = fr::zero();
-        }
         Fr r;
-        bool has_result = true;
-        switch (op) {
-            case tape::T_MUL: r = fr::mont_mul(a, b); break;
-            case tape::T_ADD: r = fr::add(a, b); break;
-            case tape::T_SUB: r = fr::sub(a, b); break;
-            case tape::T_LD: {
-                const uint4 *src = p.store + ((uint64_t)cur.w * 2) * p.bstride + w;
-                r = unpack(src[0], src[p.bstride]);
-                break;
+        if (op >= tape::T_ADD && op <= tape::T_MUL) {
+            const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+            const Fr b = tape_operand(slots, consts, cur.z, flags & 2u, tid);
+            if (op == tape::T_MUL) r = fr::mont_mul(a, b);
+            else if (op == tape::T_ADD) r = fr::add(a, b);
+            else r = fr::sub(a, b);
+        } else if (op == tape::T_SEL) {
+            const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+            const bool t = !fr::is_zero(a);
+            // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
+            const bool isc = t ? (flags & 2u) : (flags & 4u);
+            const uint32_t idx = t ? cur.z : cur.w;
+            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+            if (t || !(flags & tape::F_CZERO)) {
+                if (isc) { lo = __ldg(consts + 2 * (uint64_t)idx); hi = __ldg(consts + 2 * (uint64_t)idx + 1); }
+                else { lo = slots[(idx * 2) * CVM_NT + tid]; hi = slots[(idx * 2 + 1) * CVM_NT + tid]; }
             }
-            case tape::T_ST: {
-                if (active) {
-                    uint4 *d = p.store + ((uint64_t)cur.w * 2) * p.bstride + w;
-                    d[0] = slots[(cur.y * 2) * CVM_NT + tid];
-                    d[p.bstride] = slots[(cur.y * 2 + 1) * CVM_NT + tid];
-                }
-                has_result = false;
-                break;
+            r = unpack(lo, hi);
+        } else if (op == tape::T_BITC) {
+            // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
+            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
+            const uint32_t limb = cur.z >> 5;
+            const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * CVM_NT + tid) << 2) + (limb & 3u)];
+            r = mont_bool((word >> (cur.z & 31u)) & 1u);
+        } else if (op == tape::T_EQ || op == tape::T_NEQ || op == tape::T_EQZ || op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
+            const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+            bool e;
+            if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = fr::is_zero(a);
+            else e = fr::equal(a, tape_operand(slots, consts, cur.z, flags & 2u, tid));
+            if (op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
+                if (!e && status == 0) status = cur.w;
+                continue;
             }
-            case tape::T_STC: {
-                if (active) {
-                    uint4 *d = p.store + ((uint64_t)cur.w * 2) * p.bstride + w;
-                    d[0] = __ldg(p.consts + 2 * (uint64_t)cur.y);
-                    d[p.bstride] = __ldg(p.consts + 2 * (uint64_t)cur.y + 1);
-                }
-                has_result = false;
-                break;
-            }
-            case tape::T_INPUT: {
-                const uint4 *src = p.inputs + (w * p.n_inputs + cur.w) * 2;
-                r = op_input(unpack(src[0], src[1]));
-                break;
-            }
-            case tape::T_SEL: {
-                Fr c;
-                if (flags & 4u) c = unpack(__ldg(p.consts + 2 * (uint64_t)cur.w), __ldg(p.consts + 2 * (uint64_t)cur.w + 1));
-                else c = unpack(slots[(cur.w * 2) * CVM_NT + tid], slots[(cur.w * 2 + 1) * CVM_NT + tid]);
-                bool t = !fr::is_zero(a);
-#pragma unroll
-                for (int i = 0; i < 8; i++) r.v[i] = t ? b.v[i] : c.v[i];
-                break;
-            }
-            case tape::T_FAIL_IF:
-                if (status == 0 && !fr::is_zero(a)) status = cur.w;
-                has_result = false;
-                break;
-            case tape::T_EQ: r = mont_bool(fr::equal(a, b)); break;
-            case tape::T_NEQ: r = mont_bool(!fr::equal(a, b)); break;
-            case tape::T_EQZ: r = mont_bool(fr::is_zero(a)); break;
-            case tape::T_LAND: r = mont_bool(!fr::is_zero(a) && !fr::is_zero(b)); break;
-            case tape::T_LOR: r = mont_bool(!fr::is_zero(a) || !fr::is_zero(b)); break;
-            case tape::T_DIV: r = op_div(a, b); break;
-            case tape::T_IDIV: r = op_idivmod(a, b, false, status); break;
-            case tape::T_MOD: r = op_idivmod(a, b, true, status); break;
-            case tape::T_POW: r = op_pow(a, b); break;
-            case tape::T_SHL: r = op_shift(a, b, true); break;
-            case tape::T_SHR: r = op_shift(a, b, false); break;
-            case tape::T_BAND: case tape::T_BOR: case tape::T_BXOR: case tape::T_BNOT: r = op_bits((uint8_t)op, a, b); break;
-            case tape::T_LT: case tape::T_LE: case tape::T_GT: case tape::T_GE: r = op_cmp((uint8_t)op, a, b); break;
-            default: has_result = false; break;
-        }
-        if (has_result) {
+            r = mont_bool(op == tape::T_NEQ ? !e : e);
+        } else if (op == tape::T_LD) {
+            const uint4 *src = wbase + ((uint64_t)cur.w * 2) * bstride;
+            slots[(dst * 2) * CVM_NT + tid] = src[0];
+            slots[(dst * 2 + 1) * CVM_NT + tid] = src[bstride];
+            continue;
+        } else if (op == tape::T_ST || op == tape::T_STC) {
             uint4 lo, hi;
-            pack(r, lo, hi);
-            slots[(dst * 2) * CVM_NT + tid] = lo;
-            slots[(dst * 2 + 1) * CVM_NT + tid] = hi;
+            if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
+            else { lo = slots[(cur.y * 2) * CVM_NT + tid]; hi = slots[(cur.y * 2 + 1) * CVM_NT + tid]; }
+            if (active) {
+                uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
+                d[0] = lo;
+                d[bstride] = hi;
+            }
+            continue;
+        } else {
+            status = tape_slow_op(cur, slots, consts, p.inputs, p.n_inputs, w, status);
+            if (flags & tape::F_STORE) {
+                if (active) {
+                    uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
+                    d[0] = slots[(dst * 2) * CVM_NT + tid];
+                    d[bstride] = slots[(dst * 2 + 1) * CVM_NT + tid];
+                }
+            }
+            continue;
+        }
+        uint4 lo, hi;
+        pack(r, lo, hi);
+        slots[(dst * 2) * CVM_NT + tid] = lo;
+        slots[(dst * 2 + 1) * CVM_NT + tid] = hi;
+        if ((flags & tape::F_STORE) && active) {
+            uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
+            d[0] = lo;
+            d[bstride] = hi;
         }
     }
     if (active && p.status) p.status[w] = status;
@@ -264,6 +303,7 @@ __global__ void __launch_bounds__(256) import_kernel(const uint4 *in, uint64_t B
 // Coefficient index 0 is +1 and 1 is -1: those terms are one add/sub; others cost one Montgomery product.
 struct R1csParams {
     const uint32_t *ptr;        // 3*n_cons+1
+    const uint32_t *split;      // 3*n_cons: end of the +-1 terms of each linear combination
     const uint2 *terms;         // (wire, coef index)
     const uint4 *coefs;         // Montgomery, 2 x uint4 each
     uint32_t n_cons;
@@ -274,45 +314,53 @@ struct R1csParams {
     uint32_t *first_bad;        // B words, pre-set to 0xffffffff
 };
 
-__device__ __forceinline__ Fr lc_eval(const R1csParams &p, uint32_t beg, uint32_t end, uint64_t w) {
-    Fr acc = fr::zero();          // +-1 terms: plain field add/sub
-    fr::Wide T;                   // general coefficients: unreduced 512-bit accumulator (lazy reduction)
-    fr::wide_zero(T);
-    uint32_t pending = 0;
-    for (uint32_t t = beg; t < end; t++) {
-        uint2 term = __ldg(p.terms + t);
-        const uint4 *src = p.store + ((uint64_t)term.x * 2) * p.bstride + w;
-        Fr v = unpack(src[0], src[p.bstride]);
-        if (term.y == 0) acc = fr::add(acc, v);
-        else if (term.y == 1) acc = fr::sub(acc, v);
-        else {
-            Fr c = unpack(__ldg(p.coefs + 2 * (uint64_t)term.y), __ldg(p.coefs + 2 * (uint64_t)term.y + 1));
-            fr::wide_mac(T, c, v);
-            if (++pending == 16) {
-                acc = fr::add(acc, fr::wide_reduce(T));
-                fr::wide_zero(T);
-                pending = 0;
-            }
-        }
+// one linear combination: +-1 terms [beg, mid) by modular add/sub, general coefficients [mid, end) by a
+// lazy-reduction dot product (64 multiply-accumulates per term, one Montgomery reduction per <= 16 terms)
+__device__ __forceinline__ Fr lc_eval(const R1csParams &p, const uint4 *wbase, uint32_t beg, uint32_t mid, uint32_t end) {
+    Fr acc = fr::zero();
+    for (uint32_t t = beg; t < mid; t++) {
+        const uint2 term = __ldg(p.terms + t);
+        const uint4 *src = wbase + ((uint64_t)term.x * 2) * p.bstride;
+        const Fr v = unpack(src[0], src[p.bstride]);
+        acc = term.y ? fr::sub(acc, v) : fr::add(acc, v);
     }
-    if (pending) acc = fr::add(acc, fr::wide_reduce(T));
+    while (mid < end) {
+        const uint32_t n = min(end - mid, 16u);
+        fr::Wide T;
+        fr::wide_zero(T);
+        for (uint32_t t = mid; t < mid + n; t++) {
+            const uint2 term = __ldg(p.terms + t);
+            const uint4 *src = wbase + ((uint64_t)term.x * 2) * p.bstride;
+            const Fr v = unpack(src[0], src[p.bstride]);
+            const Fr c = unpack(__ldg(p.coefs + 2 * (uint64_t)term.y), __ldg(p.coefs + 2 * (uint64_t)term.y + 1));
+            fr::wide_mac(T, c, v);
+        }
+        acc = fr::add(acc, fr::wide_reduce(T, n));
+        mid += n;
+    }
     return acc;
 }
 
-__global__ void __launch_bounds__(128) r1cs_kernel(R1csParams p) {
+__global__ void __launch_bounds__(128, 5) r1cs_kernel(R1csParams p) {
     uint64_t w = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     const bool active = w < p.B;
     if (!active) w = p.B - 1;
+    const uint4 *wbase = p.store + w;
     uint32_t c0 = blockIdx.y * p.cons_per_chunk;
     uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
     uint32_t bad = 0xffffffffu;
     for (uint32_t c = c0; c < c1; c++) {
-        uint32_t p0 = __ldg(p.ptr + 3 * c), p1 = __ldg(p.ptr + 3 * c + 1), p2 = __ldg(p.ptr + 3 * c + 2),
-                 p3 = __ldg(p.ptr + 3 * c + 3);
-        Fr sc = lc_eval(p, p2, p3, w);
+        const uint32_t p0 = __ldg(p.ptr + 3 * c), p1 = __ldg(p.ptr + 3 * c + 1), p2 = __ldg(p.ptr + 3 * c + 2),
+                       p3 = __ldg(p.ptr + 3 * c + 3);
+        const uint32_t s0 = __ldg(p.split + 3 * c), s1 = __ldg(p.split + 3 * c + 1), s2 = __ldg(p.split + 3 * c + 2);
+        const Fr sc = lc_eval(p, wbase, p2, s2, p3);
         Fr prod;
         if (p0 == p1 || p1 == p2) prod = fr::zero();   // linear constraint: empty A or B (algebra.rs:1052-1054)
-        else prod = fr::mont_mul(lc_eval(p, p0, p1, w), lc_eval(p, p1, p2, w));
+        else {
+            const Fr sa = lc_eval(p, wbase, p0, s0, p1);
+            const Fr sb = lc_eval(p, wbase, p1, s1, p2);
+            prod = fr::mont_mul(sa, sb);
+        }
         if (bad == 0xffffffffu && !fr::equal(prod, sc)) bad = c;
     }
     if (active && bad != 0xffffffffu) atomicMin(p.first_bad + w, bad);
@@ -333,24 +381,24 @@ __global__ void fr_op_kernel(int op, const uint4 *a, const uint4 *b, uint4 *out,
         case hostfr::F_MUL: r = fr::mont_mul(x, y); break;
         case hostfr::F_SQUARE: r = fr::mont_sqr(x); break;
         case hostfr::F_INV: r = fr::mont_inv(x); break;
-        case hostfr::F_DIV: r = op_div(x, y); break;
-        case hostfr::F_IDIV: r = op_idivmod(x, y, false, st); break;
-        case hostfr::F_MOD: r = op_idivmod(x, y, true, st); break;
-        case hostfr::F_POW: r = op_pow(x, y); break;
-        case hostfr::F_SHL: r = op_shift(x, y, true); break;
-        case hostfr::F_SHR: r = op_shift(x, y, false); break;
-        case hostfr::F_BAND: r = op_bits(tape::T_BAND, x, y); break;
-        case hostfr::F_BOR: r = op_bits(tape::T_BOR, x, y); break;
-        case hostfr::F_BXOR: r = op_bits(tape::T_BXOR, x, y); break;
-        case hostfr::F_BNOT: r = op_bits(tape::T_BNOT, x, y); break;
-        case hostfr::F_LT: r = op_cmp(tape::T_LT, x, y); break;
-        case hostfr::F_LE: r = op_cmp(tape::T_LE, x, y); break;
-        case hostfr::F_GT: r = op_cmp(tape::T_GT, x, y); break;
-        case hostfr::F_GE: r = op_cmp(tape::T_GE, x, y); break;
+        case hostfr::F_DIV: r = fr::mont_mul(x, fr::mont_inv(y)); break;
+        case hostfr::F_IDIV: r = slow_compute(tape::T_IDIV, x, y, st); break;
+        case hostfr::F_MOD: r = slow_compute(tape::T_MOD, x, y, st); break;
+        case hostfr::F_POW: r = slow_compute(tape::T_POW, x, y, st); break;
+        case hostfr::F_SHL: r = slow_compute(tape::T_SHL, x, y, st); break;
+        case hostfr::F_SHR: r = slow_compute(tape::T_SHR, x, y, st); break;
+        case hostfr::F_BAND: r = slow_compute(tape::T_BAND, x, y, st); break;
+        case hostfr::F_BOR: r = slow_compute(tape::T_BOR, x, y, st); break;
+        case hostfr::F_BXOR: r = slow_compute(tape::T_BXOR, x, y, st); break;
+        case hostfr::F_BNOT: r = slow_compute(tape::T_BNOT, x, y, st); break;
+        case hostfr::F_LT: r = slow_compute(tape::T_LT, x, y, st); break;
+        case hostfr::F_LE: r = slow_compute(tape::T_LE, x, y, st); break;
+        case hostfr::F_GT: r = slow_compute(tape::T_GT, x, y, st); break;
+        case hostfr::F_GE: r = slow_compute(tape::T_GE, x, y, st); break;
         case hostfr::F_EQ: r = mont_bool(fr::equal(x, y)); break;
         case hostfr::F_NEQ: r = mont_bool(!fr::equal(x, y)); break;
-        case hostfr::F_LAND: r = mont_bool(!fr::is_zero(x) && !fr::is_zero(y)); break;
-        case hostfr::F_LOR: r = mont_bool(!fr::is_zero(x) || !fr::is_zero(y)); break;
+        case hostfr::F_LAND: r = slow_compute(tape::T_LAND, x, y, st); break;
+        case hostfr::F_LOR: r = slow_compute(tape::T_LOR, x, y, st); break;
         case hostfr::F_EQZ: r = mont_bool(fr::is_zero(x)); break;
         default: r = x; break;
     }

@@ -6,6 +6,7 @@
 // Coefficients are interned like the compiler does (circom_algebra/src/constraint_storage/logic.rs:4-12):
 // table index 0 is +1, index 1 is -1 (q-1), so the kernel can special-case both as add/sub.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -29,6 +30,7 @@ struct File {
     uint32_t n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_prv_in = 0, n_constraints = 0;
     uint64_t n_labels = 0;
     std::vector<uint32_t> ptr;       // 3*n_constraints + 1 offsets into terms: LC k of constraint c at ptr[3c+k]
+    std::vector<uint32_t> split;     // 3*n_constraints: within LC j the +-1 terms are [ptr[j], split[j]), the others follow
     std::vector<Term> terms;
     std::vector<fr::Fr> coefs;       // canonical
     std::vector<uint64_t> wire2label;
@@ -117,6 +119,11 @@ inline File load(const std::string &path) {
                 if (fr::is_zero(v)) continue;
                 out.terms.push_back(Term{wire, ci});
             }
+            // +-1 terms first (one modular add/sub each), general coefficients after them (lazy-reduction dot product)
+            size_t lo = out.ptr.back();
+            auto mid = std::stable_partition(out.terms.begin() + (ptrdiff_t)lo, out.terms.end(),
+                                             [](const Term &t) { return t.coef < 2; });
+            out.split.push_back((uint32_t)(mid - out.terms.begin()));
             out.ptr.push_back((uint32_t)out.terms.size());
         }
     }

@@ -31,6 +31,10 @@ namespace tape {
 enum TOp : uint8_t {
     T_NOP = 0, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR,
     T_BNOT, T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF,
+    // produced by the tracer's peepholes
+    T_FAIL_NE,   // status if a != b                (FAIL_IF(NEQ(a, b)): the `===` assert shape)
+    T_BITC,      // bit `aux` of the RAW limbs of a  (a = y * R^-1, whose Montgomery limbs are the canonical y)
+    T_INV,       // a^-1, with 0^-1 := 0  (ff.div a b is traced as a * INV(b) so that independent inversions can be batched)
     // inserted by the allocator
     T_LD, T_ST, T_STC, T_COUNT
 };
@@ -81,15 +85,21 @@ class Tracer {
     };
 
     std::vector<SOp> ops;
+    std::vector<uint8_t> isbool;  // per op: the value is provably 0 or 1 (comparison results, extracted bits, ANDs of those)
     std::vector<fr::Fr> consts;   // canonical
     std::vector<uint32_t> witness_ref;   // per witness wire: ref (const or value)
     TraceStats stats;
     int64_t n_inputs = 0, n_outputs = 0;
 
+    uint32_t zero_ref() const { return CONST_FLAG | c_zero; }
+    uint32_t one_ref() const { return CONST_FLAG | c_one; }
+
     explicit Tracer(const cvm::Program &p) : prog(p) {
         ffmap.resize(p.ffconst.size(), NO_REF);
         c_zero = intern(fr::zero());
         c_one = intern(hostfr::from_u64(1));
+        fr::Fr raw_one = hostfr::from_u64(1);
+        c_rinv = intern(fr::from_mont(raw_one));            // R^-1 mod q
     }
 
     void trace() {
@@ -101,7 +111,7 @@ class Tracer {
         int main_idx = new_comp(prog.start, 1);              // circuit.rs:539: main at signal 1
         for (int64_t k = 0; k < n_inputs; k++) {             // main inputs follow main outputs (App. A.5)
             SOp o{T_INPUT, NO_REF, NO_REF, NO_REF, (uint32_t)k};
-            ops.push_back(o);
+            push_op(o);
             AV v;
             v.kind = AV_DYN;
             v.ref = (uint32_t)ops.size() - 1;
@@ -147,7 +157,7 @@ class Tracer {
     std::unordered_map<uint64_t, std::vector<uint32_t>> cse;
     std::vector<std::vector<LogEntry>> logs;
     std::vector<uint32_t> preds;   // refs of enclosing data-dependent conditions (already "is true" predicates)
-    uint32_t c_zero, c_one;
+    uint32_t c_zero, c_one, c_rinv;
     int depth = 0;
     static const int64_t SPR_BASE = (int64_t)1 << 40;
 
@@ -217,22 +227,48 @@ class Tracer {
             case T_BNOT: return hostfr::F_BNOT; case T_LT: return hostfr::F_LT; case T_LE: return hostfr::F_LE;
             case T_GT: return hostfr::F_GT; case T_GE: return hostfr::F_GE; case T_EQ: return hostfr::F_EQ;
             case T_NEQ: return hostfr::F_NEQ; case T_LAND: return hostfr::F_LAND; case T_LOR: return hostfr::F_LOR;
-            case T_EQZ: return hostfr::F_EQZ; default: return hostfr::F_NONE;
+            case T_EQZ: return hostfr::F_EQZ; case T_INV: return hostfr::F_INV; default: return hostfr::F_NONE;
         }
     }
     bool is_const(uint32_t r) const { return r != NO_REF && (r & CONST_FLAG); }
     const fr::Fr &cval(uint32_t r) const { return consts[r & ~CONST_FLAG]; }
+    uint32_t push_op(const SOp &o) {
+        ops.push_back(o);
+        bool bl = false;
+        switch (o.op) {
+            case T_LT: case T_LE: case T_GT: case T_GE: case T_EQ: case T_NEQ: case T_LAND: case T_LOR: case T_EQZ:
+            case T_BITC: bl = true; break;
+            case T_SEL: bl = is_bool(o.b) && is_bool(o.c); break;
+            default: break;
+        }
+        isbool.push_back(bl ? 1 : 0);
+        return (uint32_t)ops.size() - 1;
+    }
+    // value provably in {0, 1}
+    bool is_bool(uint32_t r) const {
+        if (r == NO_REF) return false;
+        if (r & CONST_FLAG) return (r & ~CONST_FLAG) == c_zero || (r & ~CONST_FLAG) == c_one;
+        return isbool[r] != 0;
+    }
+    // the canonical value of a constant if it is a small non-negative integer, else -1
+    int64_t small_const(uint32_t r) const {
+        if (!is_const(r)) return -1;
+        const fr::Fr &c = cval(r);
+        for (int i = 1; i < 8; i++)
+            if (c.v[i]) return -1;
+        return (int64_t)c.v[0];
+    }
 
     uint32_t emit(uint8_t op, uint32_t a, uint32_t b = NO_REF, uint32_t c = NO_REF, uint32_t aux = 0) {
         bool unary = (b == NO_REF);
-        if (op != T_SEL && op != T_FAIL_IF && is_const(a) && (unary || is_const(b))) {
+        if (op != T_SEL && op != T_FAIL_IF && op != T_FAIL_NE && op != T_BITC && is_const(a) && (unary || is_const(b))) {
             fr::Fr out;
             fr::Fr bb = unary ? fr::zero() : cval(b);
             if (hostfr::apply(host_op(op), cval(a), bb, out)) {
                 stats.folded++;
                 return CONST_FLAG | intern(out);
             }
-            if (op == T_DIV) return CONST_FLAG | c_zero;   // mpz_invert(0): undefined in the reference; we define 0
+            if (op == T_DIV || op == T_INV) return CONST_FLAG | c_zero;   // mpz_invert(0): undefined in the reference; we define 0
             throw TraceError("integer division or modulo by a constant zero");
         }
         uint32_t zero = CONST_FLAG | c_zero, one = CONST_FLAG | c_one;
@@ -245,10 +281,44 @@ class Tracer {
                 if (b == zero) return a;
                 if (a == b) return zero;
                 break;
-            case T_MUL:
+            case T_DIV:
+                // a / b = a * b^-1 (generic/fr.cpp:2895-2912: Fr_inv then Fr_mul); the inversion is its own value so that
+                // equal divisors share it and tape::batch_inversions can apply Montgomery's trick to independent ones
+                if (a == zero) return zero;
+                return emit(T_MUL, a, emit(T_INV, b));
+            case T_MUL: {
                 if (a == zero || b == zero) return zero;
                 if (a == one) return b;
                 if (b == one) return a;
+                // value-range typing: a factor that is provably 0/1 turns the product into a select, and
+                // x*(x-1) of such an x is 0 (the `out*(out-1) === 0` of every bit decomposition)
+                for (int k = 0; k < 2; k++) {
+                    uint32_t x = k ? b : a, y = k ? a : b;
+                    if (!is_bool(x) || is_const(x)) continue;
+                    if (!is_const(y) && ops[y].op == T_SUB && ops[y].a == x && ops[y].b == one) return zero;
+                    return emit(T_SEL, x, y, zero);
+                }
+                break;
+            }
+            case T_BAND: {
+                // (y >> k) & 1 with constant k: read bit k of the canonical y.  y * R^-1 has the canonical y as its
+                // Montgomery limbs, is shared by all bits of y through value numbering, and costs one multiplication
+                // instead of the four representation changes of SHR + BAND.
+                for (int k = 0; k < 2; k++) {
+                    uint32_t x = k ? b : a, m = k ? a : b;
+                    if (m != one || is_const(x) || ops[x].op != T_SHR) continue;
+                    int64_t sh = small_const(ops[x].b);
+                    if (sh < 0 || sh >= 254 || is_const(ops[x].a)) continue;
+                    uint32_t canon = emit(T_MUL, ops[x].a, CONST_FLAG | c_rinv);
+                    return emit(T_BITC, canon, NO_REF, NO_REF, (uint32_t)sh);
+                }
+                break;
+            }
+            case T_EQZ:
+                if (!is_const(a)) {
+                    if (ops[a].op == T_EQ) return emit(T_NEQ, ops[a].a, ops[a].b);
+                    if (ops[a].op == T_NEQ) return emit(T_EQ, ops[a].a, ops[a].b);
+                }
                 break;
             case T_EQ:
                 if (a == b) return one;
@@ -262,6 +332,7 @@ class Tracer {
                 break;
             case T_FAIL_IF:
                 if (is_const(a) && fr::is_zero(cval(a))) return NO_REF;
+                if (!is_const(a) && ops[a].op == T_NEQ) return emit(T_FAIL_NE, ops[a].a, ops[a].b, NO_REF, aux);
                 break;
             default: break;
         }
@@ -277,9 +348,8 @@ class Tracer {
             }
         }
         SOp o{op, a, b, c, aux};
-        ops.push_back(o);
-        uint32_t id = (uint32_t)ops.size() - 1;
-        bucket.push_back(id);
+        uint32_t id = push_op(o);
+        cse[key].push_back(id);
         return id;
     }
 
@@ -554,7 +624,7 @@ class Tracer {
                     uint32_t p = preds.empty() ? (CONST_FLAG | c_one) : pred_conj();
                     // an unconditional error is a program that fails for every input; keep it as a flag
                     SOp o{T_FAIL_IF, p, NO_REF, NO_REF, ST_ASSERT};
-                    ops.push_back(o);
+                    push_op(o);
                     pc++;
                     break;
                 }

@@ -48,7 +48,8 @@ class ProgramInfo(ctypes.Structure):
                 ("n_slots", c_uint32), ("n_rows", c_uint32), ("tape_len", c_uint64), ("ref_mul", c_uint64),
                 ("ref_field_ops", c_uint64), ("cvm_instructions", c_uint64), ("tape_mul", c_uint64),
                 ("tape_div", c_uint64), ("tape_addsub", c_uint64), ("tape_other", c_uint64), ("tape_ld", c_uint64),
-                ("tape_st", c_uint64), ("tape_spill_st", c_uint64), ("n_consts", c_uint32), ("dyn_branches", c_uint32)]
+                ("tape_st", c_uint64), ("tape_spill_st", c_uint64), ("n_consts", c_uint32), ("dyn_branches", c_uint32),
+                ("ref_div", c_uint64), ("tape_inv", c_uint64), ("tape_sel", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

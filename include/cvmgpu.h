@@ -66,6 +66,9 @@ typedef struct {
     uint64_t tape_mul, tape_div, tape_addsub, tape_other, tape_ld, tape_st, tape_spill_st;
     uint32_t n_consts;
     uint32_t dyn_branches;
+    uint64_t ref_div;            /* ff.div the reference program executes per witness (Fr_div = mpz_invert + Fr_mul) */
+    uint64_t tape_inv;           /* field inversions left on the tape after batching independent ones (Montgomery's trick) */
+    uint64_t tape_sel;           /* selects on the tape (products with a 0/1 factor, if-converted branches, batch inversion) */
 } cvmgpu_program_info;
 
 typedef struct {

@@ -31,6 +31,7 @@ def circuits():
     try:
         from tools.circuitgen.circuits import sha256
         table["sha256_64"] = (sha256.Sha256, (64,))
+        table["sha256_512"] = (sha256.Sha256, (512,))      # BASELINE config 3 (CPU baseline of bench.py --workload sha256_512)
     except ImportError:
         pass
     return table

@@ -7,7 +7,11 @@ and is not a fallback: the product path has no CPU execution.
 from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
- T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_LD, T_ST, T_STC) = range(29)
+ T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_INV, T_LD,
+ T_ST, T_STC) = range(32)
+F_CZERO = 16         # T_SEL: third operand is the constant 0
+F_STORE = 8          # flag bit 3: the result is also stored to value-store row c
+R = 1 << 256
 
 BIN = {T_ADD: M.add, T_SUB: M.sub, T_MUL: M.mul, T_POW: M.pow_, T_SHL: M.shl, T_SHR: M.shr, T_BAND: M.band,
        T_BOR: M.bor, T_BXOR: M.bxor, T_LT: M.lt, T_LE: M.leq, T_GT: M.gt, T_GE: M.geq, T_EQ: M.eq, T_NEQ: M.neq,
@@ -32,7 +36,14 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             return v
 
         if op == T_INPUT:
-            slots[dst] = inputs[c] % M.Q
+            slots[dst] = inputs[a] % M.Q
+        elif op == T_BITC:
+            # bit b of the RAW (Montgomery) limbs of slot a
+            assert slots[a] is not None
+            slots[dst] = ((slots[a] * R % M.Q) >> b) & 1
+        elif op == T_FAIL_NE:
+            if status == 0 and operand(a, 1) != operand(b, 2):
+                status = c
         elif op == T_LD:
             assert rows[c] is not None, "load of an unwritten row"
             slots[dst] = rows[c]
@@ -45,11 +56,12 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             if status == 0 and operand(a, 1) != 0:
                 status = c
         elif op == T_SEL:
-            x, y, z = operand(a, 1), operand(b, 2), operand(c, 4)
+            x, y = operand(a, 1), operand(b, 2)
+            z = 0 if flags & F_CZERO else operand(c, 4)
             slots[dst] = y if x != 0 else z
-        elif op in (T_BNOT, T_EQZ):
+        elif op in (T_BNOT, T_EQZ, T_INV):
             x = operand(a, 1)
-            slots[dst] = M.bnot(x) if op == T_BNOT else int(x == 0)
+            slots[dst] = M.bnot(x) if op == T_BNOT else int(x == 0) if op == T_EQZ else pow(x, M.Q - 2, M.Q)
         elif op == T_DIV:
             x, y = operand(a, 1), operand(b, 2)
             slots[dst] = 0 if y == 0 else M.div(x, y)
@@ -65,4 +77,7 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             slots[dst] = BIN[op](operand(a, 1), operand(b, 2))
         else:
             raise ValueError("bad tape op %d" % op)
+        if flags & F_STORE:
+            assert op not in (T_LD, T_ST, T_STC, T_FAIL_IF, T_FAIL_NE) and (op != T_SEL or flags & F_CZERO)
+            rows[c] = slots[dst]
     return rows, status
