@@ -17,8 +17,9 @@ LIBGMP = "/usr/lib/x86_64-linux-gnu/libgmp.so.10"
 
 
 def circuits():
-    from tools.circuitgen.circuits import basic, poseidon
+    from tools.circuitgen.circuits import babyjub, basic, poseidon
     table = {
+        "babyadd4": (babyjub.BabyAddChain, (4,)),
         "multiplier2": (basic.Multiplier2, ()),
         "multiplier4": (basic.MultiplierN, (4,)),
         "num2bits8": (basic.Num2Bits, (8,)),

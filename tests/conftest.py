@@ -40,8 +40,9 @@ def circuit(name):
     if name in CIRCUITS:
         return CIRCUITS[name]
     from tools.circuitgen.build import compile_circuit
-    from tools.circuitgen.circuits import basic, poseidon
+    from tools.circuitgen.circuits import babyjub, basic, poseidon
     table = {
+        "babyadd4": (babyjub.BabyAddChain, (4,)),
         "multiplier2": (basic.Multiplier2, ()),
         "multiplier4": (basic.MultiplierN, (4,)),
         "num2bits8": (basic.Num2Bits, (8,)),
