@@ -31,7 +31,7 @@ WORKLOADS = {
     "poseidon2": {"label": "Poseidon(2)", "module": "poseidon", "fn": "Poseidon", "args": (2,), "batch": 1 << 20,
                   "chunk": 1 << 20, "e2e_batch": 1 << 17, "bits": False, "ref": "poseidon2_bench"},
     "sha256_512": {"label": "Sha256(512 bits)", "module": "sha256", "fn": "Sha256", "args": (512,), "batch": 1 << 16,
-                   "chunk": 1 << 15, "e2e_batch": 1 << 10, "bits": True, "ref": "sha256_512"},
+                   "chunk": 1 << 16, "e2e_batch": 1 << 10, "bits": True, "ref": "sha256_512"},
 }
 WL = WORKLOADS["poseidon2"]
 METRIC = "witnesses/sec (Poseidon(2) witness generation + R1CS check)"

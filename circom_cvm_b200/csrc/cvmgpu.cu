@@ -67,7 +67,7 @@ struct cvmgpu_program {
 struct cvmgpu_r1cs {
     r1cs::File file;
     int device = -1;
-    DevBuf d_ptr, d_split, d_terms, d_coefs, d_store, d_wtns, d_bad;
+    DevBuf d_ptr, d_split, d_terms, d_coefs, d_cmag, d_store, d_wtns, d_bad;
 };
 
 extern "C" const char *cvmgpu_last_error(void) { return g_err.c_str(); }
@@ -176,6 +176,8 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->ref_div = p->tstats.ref_div;
     info->tape_inv = p->tape.stats.n_inv;
     info->tape_sel = p->tape.stats.n_sel;
+    info->tape_dot = p->tape.stats.n_dot;
+    info->tape_dot_terms = p->tape.stats.n_dot_terms;
     return CVMGPU_OK;
 }
 
@@ -389,13 +391,14 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
     info->n_labels = r->file.n_labels;
     info->nnz = r->file.terms.size();
     info->nnz_pm1 = r->file.nnz_pm1;
+    info->nnz_small = r->file.nnz_small;
     info->n_coefs = (uint32_t)r->file.coefs.size();
     return CVMGPU_OK;
 }
 
 extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
     if (!r) return;
-    r->d_ptr.release(); r->d_split.release(); r->d_terms.release(); r->d_coefs.release();
+    r->d_ptr.release(); r->d_split.release(); r->d_terms.release(); r->d_coefs.release(); r->d_cmag.release();
     r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
     delete r;
 }
@@ -405,7 +408,7 @@ static int upload_r1cs(cvmgpu_r1cs *r) {
     CUDA_TRY(cudaGetDevice(&dev));
     if (r->device == dev && r->d_ptr.p) return CVMGPU_OK;
     if (r->device != dev) {
-        r->d_ptr = DevBuf(); r->d_split = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf();
+        r->d_ptr = DevBuf(); r->d_split = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf(); r->d_cmag = DevBuf();
         r->d_store = DevBuf(); r->d_wtns = DevBuf(); r->d_bad = DevBuf();
     }
     const r1cs::File &f = r->file;
@@ -416,6 +419,8 @@ static int upload_r1cs(cvmgpu_r1cs *r) {
     if (int rc = r->d_split.ensure(std::max<size_t>(16, f.split.size() * 4))) return rc;
     if (int rc = r->d_terms.ensure(std::max<size_t>(16, f.terms.size() * 8))) return rc;
     if (int rc = r->d_coefs.ensure(cm.size() * 32)) return rc;
+    if (int rc = r->d_cmag.ensure(f.cmag.size() * 4)) return rc;
+    CUDA_TRY(cudaMemcpy(r->d_cmag.p, f.cmag.data(), f.cmag.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r->d_ptr.p, f.ptr.data(), f.ptr.size() * 4, cudaMemcpyHostToDevice));
     if (!f.split.empty()) CUDA_TRY(cudaMemcpy(r->d_split.p, f.split.data(), f.split.size() * 4, cudaMemcpyHostToDevice));
     if (!f.terms.empty()) CUDA_TRY(cudaMemcpy(r->d_terms.p, f.terms.data(), f.terms.size() * 8, cudaMemcpyHostToDevice));
@@ -432,7 +437,7 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(d_first_bad, 0xff, B * 4, s));
     if (r->file.n_constraints == 0) return CVMGPU_OK;
-    uint64_t gx = (B + 127) / 128;
+    uint64_t gx = (B + R1CS_NT - 1) / R1CS_NT;
     // enough CTAs to fill 148 SMs several times over even for small batches (config 5: B = 1K, 1.5M constraints)
     uint64_t want = 148ull * 16;
     uint64_t chunks = std::max<uint64_t>(1, (want + gx - 1) / gx);
@@ -447,6 +452,7 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     rp.split = (const uint32_t *)r->d_split.p;
     rp.terms = (const uint2 *)r->d_terms.p;
     rp.coefs = (const uint4 *)r->d_coefs.p;
+    rp.cmag = (const uint32_t *)r->d_cmag.p;
     rp.n_cons = r->file.n_constraints;
     rp.cons_per_chunk = per;
     rp.store = (const uint4 *)d_store;
@@ -454,7 +460,7 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     rp.B = B;
     rp.first_bad = (uint32_t *)d_first_bad;
     dim3 grid((unsigned)gx, (unsigned)chunks);
-    kern::r1cs_kernel<<<grid, 128, 0, s>>>(rp);
+    kern::r1cs_kernel<<<grid, R1CS_NT, 0, s>>>(rp);
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }

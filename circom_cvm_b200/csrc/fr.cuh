@@ -119,29 +119,98 @@ FR_HD uint32_t add_raw(Fr &r, const Fr &a, const Fr &b) {
     }
     return (uint32_t)carry;
 }
+#if defined(__CUDA_ARCH__)
+// Device formulations: one carry chain per 256-bit add/subtract (IADD3.X), the borrow materialised as a mask.
+// r = a - b, returns 0xffffffff when the subtraction borrowed, else 0
+__device__ __forceinline__ uint32_t sub_mask(Fr &r, const Fr &a, const Fr &b) {
+    uint32_t m;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(m)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    return m;
+}
+// r = t - q, returns the borrow mask
+__device__ __forceinline__ uint32_t sub_q_mask(Fr &r, const Fr &t) {
+    uint32_t m;
+    asm("sub.cc.u32 %0, %9, 0xf0000001;\n\t"
+        "subc.cc.u32 %1, %10, 0x43e1f593;\n\t"
+        "subc.cc.u32 %2, %11, 0x79b97091;\n\t"
+        "subc.cc.u32 %3, %12, 0x2833e848;\n\t"
+        "subc.cc.u32 %4, %13, 0x8181585d;\n\t"
+        "subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
+        "subc.cc.u32 %6, %15, 0xe131a029;\n\t"
+        "subc.cc.u32 %7, %16, 0x30644e72;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(m)
+        : "r"(t.v[0]), "r"(t.v[1]), "r"(t.v[2]), "r"(t.v[3]), "r"(t.v[4]), "r"(t.v[5]), "r"(t.v[6]), "r"(t.v[7]));
+    return m;
+}
+#endif
+
 // branch-free: r = (t >= q) ? t - q : t     (one conditional subtraction)
 FR_HD Fr reduce_once(const Fr &t) {
-    Fr d;
-    uint32_t borrow = sub_raw(d, t, modulus());
-    Fr r;
+    Fr d, r;
+#if defined(__CUDA_ARCH__)
+    const bool keep = sub_q_mask(d, t) != 0;     // t < q
+#else
+    const bool keep = sub_raw(d, t, modulus()) != 0;
+#endif
 #pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = borrow ? t.v[i] : d.v[i];
+    for (int i = 0; i < 8; i++) r.v[i] = keep ? t.v[i] : d.v[i];
     return r;
 }
 
 // ---- field add / sub / neg  (generic/fr.cpp:19-98 rawAdd/rawSub/rawNeg; valid in either representation)
 FR_HD Fr add(const Fr &a, const Fr &b) {
     Fr t;
-    add_raw(t, a, b);  // a, b < q < 2^254: no carry out of 256 bits
-    return reduce_once(t);
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]), "=r"(t.v[6]), "=r"(t.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+#else
+    add_raw(t, a, b);
+#endif
+    return reduce_once(t);       // a, b < q < 2^254: no carry out of 256 bits
 }
 FR_HD Fr sub(const Fr &a, const Fr &b) {
-    Fr d, e;
+    Fr d, r;
+#if defined(__CUDA_ARCH__)
+    const uint32_t m = sub_mask(d, a, b);        // borrowed: add q back
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]), "r"(d.v[7]),
+          "r"(FR_Q0 & m), "r"(FR_Q1 & m), "r"(FR_Q2 & m), "r"(FR_Q3 & m), "r"(FR_Q4 & m), "r"(FR_Q5 & m), "r"(FR_Q6 & m), "r"(FR_Q7 & m));
+#else
+    Fr e;
     uint32_t borrow = sub_raw(d, a, b);
     add_raw(e, d, modulus());
-    Fr r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = borrow ? e.v[i] : d.v[i];
+#endif
     return r;
 }
 FR_HD Fr neg(const Fr &a) {
@@ -432,6 +501,36 @@ __device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
         }
     }
     return r;
+}
+// ---- small-scalar sums -----------------------------------------------------------------------------------
+// X = sum_k m_k * v_k with 32-bit scalars m_k is a plain integer (10 limbs, < 2^320); one CIOS pass with the
+// constant 2^320 mod q brings it back: sum_i X_i * C * 2^(32 i) / 2^320 = X (mod q), result < 2q.
+struct Small {
+    uint32_t t[10];
+};
+__device__ __forceinline__ void small_zero(Small &X) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) X.t[i] = 0;
+}
+__device__ __forceinline__ void small_mac(Small &X, uint32_t m, const Fr &v) { mac_row_ovf(X.t, X.t[9], v.v, m); }
+__device__ __forceinline__ Fr small_reduce(const Small &X) {
+    const uint32_t C[8] = {0x7c5fb586u, 0xb4c6edf9u, 0xbfeb93beu, 0x708c8d50u, 0x04f7e0efu, 0x9ffd1de4u, 0x9a392866u, 0x215b02acu};
+    uint32_t t[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        mac_row(t, C, X.t[i]);
+        uint32_t m = t[0] * FR_NP0;
+        mac_row_q(t, m);
+#pragma unroll
+        for (int j = 0; j < 8; j++) t[j] = t[j + 1];
+        t[8] = 0;
+    }
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    return reduce_once(r);
 }
 #endif
 

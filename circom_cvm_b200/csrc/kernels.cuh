@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
     uint4 raw = __ldg(tp);
     for (uint32_t pc = 0; pc < n_ins; pc++) {
         const uint4 cur = raw;
-        raw = __ldg(tp + min(pc + 1, n_ins - 1));   // prefetch the next instruction
+        raw = __ldg(tp + min(pc + 1, n_ins - 1));   // prefetch the next instruction (re-done after a DOT's records)
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
@@ -164,6 +164,22 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
             if (op == tape::T_MUL) r = fr::mont_mul(a, b);
             else if (op == tape::T_ADD) r = fr::add(a, b);
             else r = fr::sub(a, b);
+        } else if (op == tape::T_DOT) {
+            // sum_k c_k * x_k (+ addend): cur.y terms in the following ceil(n/2) records of (constant, slot) pairs
+            const uint32_t n = cur.y;
+            fr::Wide T;
+            fr::wide_zero(T);
+            for (uint32_t j = 0; j < n; j++) {
+                const uint4 rec = __ldg(tp + pc + 1 + (j >> 1));
+                const uint32_t cidx = (j & 1u) ? rec.z : rec.x, slot = (j & 1u) ? rec.w : rec.y;
+                const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cidx), __ldg(consts + 2 * (uint64_t)cidx + 1));
+                const Fr x = unpack(slots[(slot * 2) * CVM_NT + tid], slots[(slot * 2 + 1) * CVM_NT + tid]);
+                fr::wide_mac(T, c, x);
+            }
+            r = fr::wide_reduce(T, n);
+            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand(slots, consts, cur.z, flags & 2u, tid));
+            pc += (n + 1) >> 1;
+            raw = __ldg(tp + min(pc + 1, n_ins - 1));
         } else if (op == tape::T_SEL) {
             const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
             const bool t = !fr::is_zero(a);
@@ -303,7 +319,8 @@ __global__ void __launch_bounds__(256) import_kernel(const uint4 *in, uint64_t B
 // Coefficient index 0 is +1 and 1 is -1: those terms are one add/sub; others cost one Montgomery product.
 struct R1csParams {
     const uint32_t *ptr;        // 3*n_cons+1
-    const uint32_t *split;      // 3*n_cons: end of the +-1 terms of each linear combination
+    const uint32_t *split;      // 3 per linear combination: ends of the +-1 / small positive / small negative classes
+    const uint32_t *cmag;       // per coefficient: 32-bit magnitude of a small coefficient
     const uint2 *terms;         // (wire, coef index)
     const uint4 *coefs;         // Montgomery, 2 x uint4 each
     uint32_t n_cons;
@@ -314,55 +331,124 @@ struct R1csParams {
     uint32_t *first_bad;        // B words, pre-set to 0xffffffff
 };
 
-// one linear combination: +-1 terms [beg, mid) by modular add/sub, general coefficients [mid, end) by a
-// lazy-reduction dot product (64 multiply-accumulates per term, one Montgomery reduction per <= 16 terms)
-__device__ __forceinline__ Fr lc_eval(const R1csParams &p, const uint4 *wbase, uint32_t beg, uint32_t mid, uint32_t end) {
-    Fr acc = fr::zero();
-    for (uint32_t t = beg; t < mid; t++) {
-        const uint2 term = __ldg(p.terms + t);
-        const uint4 *src = wbase + ((uint64_t)term.x * 2) * p.bstride;
-        const Fr v = unpack(src[0], src[p.bstride]);
-        acc = term.y ? fr::sub(acc, v) : fr::add(acc, v);
+// One linear combination.  Its terms are ordered by coefficient class (r1cs.hpp):
+//   +-1              [beg, e0): modular add/sub
+//   small +, small - [e0, e1), [e1, e2): integer sums with 32-bit scalars (8 multiply-accumulates per term), one
+//                    reduction per class (fr.cuh small_reduce)
+//   general          [e2, end): lazy-reduction dot product (64 multiply-accumulates per term, one Montgomery
+//                    reduction per <= 16 terms)
+//
+// Operand stream.  The terms of a chunk of constraints are contiguous in the CSR (A, B, C of constraint c, then
+// c+1, ...) and their addresses do not depend on data, so every thread keeps R1CS_STAGES of its own witness's
+// values in flight with cp.async (LDGSTS, global -> its private column of a shared-memory ring, L2-only caching)
+// and consumes them in order: HBM latency is hidden even when few warps are resident (small batches).
+#define R1CS_NT 128
+#define R1CS_STAGES 8
+
+struct TermStream {
+    const uint2 *terms;
+    const uint4 *wbase;
+    uint64_t bstride;
+    uint4 *ring;            // [R1CS_STAGES][2][R1CS_NT]
+    uint32_t t_issue, t_end;
+
+    __device__ __forceinline__ void issue() {
+        if (t_issue < t_end) {
+            const uint2 term = __ldg(terms + t_issue);
+            const uint4 *src = wbase + ((uint64_t)term.x * 2) * bstride;
+            uint4 *dst = ring + (t_issue % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + R1CS_NT * 16), "l"(src + bstride) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        t_issue++;
     }
-    while (mid < end) {
-        const uint32_t n = min(end - mid, 16u);
+    __device__ __forceinline__ void start(uint32_t t_begin) {
+        t_issue = t_begin;
+#pragma unroll
+        for (int k = 0; k < R1CS_STAGES; k++) issue();
+    }
+    // value of term t (terms are consumed strictly in order); refills the stage it frees
+    __device__ __forceinline__ Fr take(uint32_t t) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(R1CS_STAGES - 1) : "memory");
+        const uint4 *s = ring + (t % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
+        const Fr v = unpack(s[0], s[R1CS_NT]);
+        issue();
+        return v;
+    }
+};
+
+__device__ __forceinline__ Fr lc_eval(const R1csParams &p, TermStream &ts, uint32_t beg, uint32_t e0, uint32_t e1,
+                                      uint32_t e2, uint32_t end) {
+    Fr acc = fr::zero();
+    uint32_t t = beg;
+    for (; t < e0; t++) {
+        const uint32_t neg = __ldg(p.terms + t).y;
+        const Fr v = ts.take(t);
+        acc = neg ? fr::sub(acc, v) : fr::add(acc, v);
+    }
+    if (e0 < e2) {
+        for (int neg = 0; neg < 2; neg++) {
+            const uint32_t stop = neg ? e2 : e1;
+            if (t >= stop) continue;
+            fr::Small X;
+            fr::small_zero(X);
+            for (; t < stop; t++) {
+                const uint32_t coef = __ldg(p.terms + t).y;
+                const Fr v = ts.take(t);
+                fr::small_mac(X, __ldg(p.cmag + coef), v);
+            }
+            const Fr sres = fr::small_reduce(X);
+            acc = neg ? fr::sub(acc, sres) : fr::add(acc, sres);
+        }
+    }
+    while (t < end) {
+        const uint32_t n = min(end - t, 16u);
         fr::Wide T;
         fr::wide_zero(T);
-        for (uint32_t t = mid; t < mid + n; t++) {
-            const uint2 term = __ldg(p.terms + t);
-            const uint4 *src = wbase + ((uint64_t)term.x * 2) * p.bstride;
-            const Fr v = unpack(src[0], src[p.bstride]);
-            const Fr c = unpack(__ldg(p.coefs + 2 * (uint64_t)term.y), __ldg(p.coefs + 2 * (uint64_t)term.y + 1));
+        for (uint32_t k = 0; k < n; k++, t++) {
+            const uint32_t coef = __ldg(p.terms + t).y;
+            const Fr c = unpack(__ldg(p.coefs + 2 * (uint64_t)coef), __ldg(p.coefs + 2 * (uint64_t)coef + 1));
+            const Fr v = ts.take(t);
             fr::wide_mac(T, c, v);
         }
         acc = fr::add(acc, fr::wide_reduce(T, n));
-        mid += n;
     }
     return acc;
 }
 
-__global__ void __launch_bounds__(128, 5) r1cs_kernel(R1csParams p) {
-    uint64_t w = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+__global__ void __launch_bounds__(R1CS_NT, 4) r1cs_kernel(R1csParams p) {
+    __shared__ uint4 ring[R1CS_STAGES * 2 * R1CS_NT];
+    uint64_t w = (uint64_t)blockIdx.x * R1CS_NT + threadIdx.x;
     const bool active = w < p.B;
     if (!active) w = p.B - 1;
-    const uint4 *wbase = p.store + w;
-    uint32_t c0 = blockIdx.y * p.cons_per_chunk;
-    uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
+    const uint32_t c0 = blockIdx.y * p.cons_per_chunk;
+    const uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
+    TermStream ts;
+    ts.terms = p.terms;
+    ts.wbase = p.store + w;
+    ts.bstride = p.bstride;
+    ts.ring = ring;
+    ts.t_end = __ldg(p.ptr + 3 * c1);
+    ts.start(__ldg(p.ptr + 3 * c0));
     uint32_t bad = 0xffffffffu;
     for (uint32_t c = c0; c < c1; c++) {
-        const uint32_t p0 = __ldg(p.ptr + 3 * c), p1 = __ldg(p.ptr + 3 * c + 1), p2 = __ldg(p.ptr + 3 * c + 2),
-                       p3 = __ldg(p.ptr + 3 * c + 3);
-        const uint32_t s0 = __ldg(p.split + 3 * c), s1 = __ldg(p.split + 3 * c + 1), s2 = __ldg(p.split + 3 * c + 2);
-        const Fr sc = lc_eval(p, wbase, p2, s2, p3);
-        Fr prod;
-        if (p0 == p1 || p1 == p2) prod = fr::zero();   // linear constraint: empty A or B (algebra.rs:1052-1054)
-        else {
-            const Fr sa = lc_eval(p, wbase, p0, s0, p1);
-            const Fr sb = lc_eval(p, wbase, p1, s1, p2);
-            prod = fr::mont_mul(sa, sb);
+        Fr sa = fr::zero(), sb = fr::zero(), sc = fr::zero();
+#pragma unroll 1
+        for (uint32_t k = 0; k < 3; k++) {   // A, B, C in CSR order (one inlined copy of lc_eval)
+            const uint32_t j = 3 * c + k;
+            const Fr v = lc_eval(p, ts, __ldg(p.ptr + j), __ldg(p.split + 3 * j), __ldg(p.split + 3 * j + 1),
+                                 __ldg(p.split + 3 * j + 2), __ldg(p.ptr + j + 1));
+            if (k == 0) sa = v;
+            else if (k == 1) sb = v;
+            else sc = v;
         }
+        // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054): sa or sb is 0 then
+        const Fr prod = (fr::is_zero(sa) || fr::is_zero(sb)) ? fr::zero() : fr::mont_mul(sa, sb);
         if (bad == 0xffffffffu && !fr::equal(prod, sc)) bad = c;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (active && bad != 0xffffffffu) atomicMin(p.first_bad + w, bad);
 }
 

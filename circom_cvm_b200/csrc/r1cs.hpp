@@ -30,11 +30,15 @@ struct File {
     uint32_t n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_prv_in = 0, n_constraints = 0;
     uint64_t n_labels = 0;
     std::vector<uint32_t> ptr;       // 3*n_constraints + 1 offsets into terms: LC k of constraint c at ptr[3c+k]
-    std::vector<uint32_t> split;     // 3*n_constraints: within LC j the +-1 terms are [ptr[j], split[j]), the others follow
+    // per LC j, terms are ordered [+-1 | small positive | small negative | general]; split[3j+k] = end of class k.
+    // "small": the coefficient c (positive) or q - c (negative) fits 32 bits; such terms cost 8 multiply-accumulates
+    // instead of 64 (kernels.cuh lc_eval).  A class is only used when it has >= 4 members, else they count as general.
+    std::vector<uint32_t> split;
+    std::vector<uint32_t> cmag;      // per coefficient: the 32-bit magnitude when small, else 0
     std::vector<Term> terms;
     std::vector<fr::Fr> coefs;       // canonical
     std::vector<uint64_t> wire2label;
-    uint64_t nnz_pm1 = 0;
+    uint64_t nnz_pm1 = 0, nnz_small = 0;
 };
 
 struct Error : std::runtime_error {
@@ -119,15 +123,43 @@ inline File load(const std::string &path) {
                 if (fr::is_zero(v)) continue;
                 out.terms.push_back(Term{wire, ci});
             }
-            // +-1 terms first (one modular add/sub each), general coefficients after them (lazy-reduction dot product)
-            size_t lo = out.ptr.back();
-            auto mid = std::stable_partition(out.terms.begin() + (ptrdiff_t)lo, out.terms.end(),
-                                             [](const Term &t) { return t.coef < 2; });
-            out.split.push_back((uint32_t)(mid - out.terms.begin()));
             out.ptr.push_back((uint32_t)out.terms.size());
         }
     }
     if (p > end) throw Error("constraint section overrun");
+    // ---- coefficient classes and per-LC term order
+    std::vector<uint8_t> kind(out.coefs.size(), 3);   // 0: +-1, 1: small positive, 2: small negative, 3: general
+    out.cmag.assign(out.coefs.size(), 0);
+    kind[0] = kind[1] = 0;
+    for (size_t i = 2; i < out.coefs.size(); i++) {
+        const fr::Fr &c = out.coefs[i];
+        fr::Fr n = fr::neg(c);
+        auto small = [](const fr::Fr &x) {
+            for (int k = 1; k < 8; k++)
+                if (x.v[k]) return false;
+            return true;
+        };
+        if (small(c)) { kind[i] = 1; out.cmag[i] = c.v[0]; }
+        else if (small(n)) { kind[i] = 2; out.cmag[i] = n.v[0]; }
+    }
+    out.split.resize(3 * (size_t)(out.ptr.size() - 1));
+    for (size_t j = 0; j + 1 < out.ptr.size(); j++) {
+        auto b = out.terms.begin() + (ptrdiff_t)out.ptr[j], e = out.terms.begin() + (ptrdiff_t)out.ptr[j + 1];
+        size_t cnt[4] = {0, 0, 0, 0};
+        for (auto it = b; it != e; ++it) cnt[kind[it->coef]]++;
+        const bool use1 = cnt[1] >= 4, use2 = cnt[2] >= 4;
+        auto cls = [&](const Term &t) -> int {
+            int k = kind[t.coef];
+            if ((k == 1 && !use1) || (k == 2 && !use2)) return 3;
+            return k;
+        };
+        std::stable_sort(b, e, [&](const Term &x, const Term &y) { return cls(x) < cls(y); });
+        size_t n0 = cnt[0], n1 = use1 ? cnt[1] : 0, n2 = use2 ? cnt[2] : 0;
+        out.split[3 * j] = out.ptr[j] + (uint32_t)n0;
+        out.split[3 * j + 1] = out.ptr[j] + (uint32_t)(n0 + n1);
+        out.split[3 * j + 2] = out.ptr[j] + (uint32_t)(n0 + n1 + n2);
+        out.nnz_small += n1 + n2;
+    }
     if (have[3]) {
         size_t wp = sec_pos[3];
         for (uint64_t i = 0; i < sec_len[3] / 8; i++) out.wire2label.push_back(u64(wp + 8 * i));

@@ -6,6 +6,8 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "tracer.hpp"
@@ -23,13 +25,14 @@ struct TapeIns {
                       // with flag bit3: value-store row
 };
 static const uint8_t F_STORE = 8;
-static const uint8_t F_CZERO = 16;   // T_SEL: the third operand is the constant 0 (field c is free for the fused store)
+static const uint8_t F_CZERO = 16;
+static const uint8_t F_ADDEND = 32;  // T_DOT: field b holds an addend (slot, or constant index with bit1)   // T_SEL: the third operand is the constant 0 (field c is free for the fused store)
 static_assert(sizeof(TapeIns) == 16, "tape instruction must be 16 bytes");
 
 struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
-    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0;
+    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0;
     uint32_t n_spill_rows = 0;
     uint32_t max_live = 0;
 };
@@ -132,35 +135,143 @@ inline BatchInvStats batch_inversions(Tracer &tr, uint32_t max_batch = 256) {
     return st;
 }
 
-inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
+// ---- dot-product fusion ------------------------------------------------------------------------------------
+// A tree of ff.add whose leaves are single-use products by constants (MDS mixing layers, linear combinations
+// computed in vars) becomes one DOT: sum_k c_k * x_k (+ addend) evaluated with ONE Montgomery reduction
+// (fr.cuh wide_mac / wide_reduce: 64 multiply-accumulates per term + 72 per reduction instead of 136 per term).
+struct XOp {
+    uint8_t op;
+    uint32_t a, b, c, aux;
+    uint32_t t0 = 0, tn = 0;   // T_DOT: terms [t0, t0+tn) of XProg::terms; c = addend ref or NO_REF
+};
+struct XProg {
+    std::vector<XOp> ops;
+    std::vector<std::pair<uint32_t, uint32_t>> terms;   // (constant ref, value id)
+    std::vector<uint32_t> witness_ref;
+};
+
+inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
     const std::vector<SOp> &ops = tr.ops;
     const size_t N = ops.size();
-    Tape out;
-    out.n_slots = n_slots;
-    out.n_wires = (uint32_t)tr.witness_ref.size();
-    out.stats.n_ssa = N;
-    if (n_slots < 4) throw TraceError("need at least 4 slots");
-
-    // ---- liveness (roots: failure checks and witness wires)
+    XProg xp;
     std::vector<uint8_t> live(N, 0);
     for (size_t i = 0; i < N; i++)
         if (ops[i].op == T_FAIL_IF || ops[i].op == T_FAIL_NE) live[i] = 1;
+    std::vector<uint32_t> uses(N, 0);
     for (uint32_t r : tr.witness_ref)
-        if (!(r & CONST_FLAG)) live[r] = 1;
+        if (!(r & CONST_FLAG)) { live[r] = 1; uses[r] += 2; }   // a wire must exist as a value of its own
     for (size_t i = N; i-- > 0;) {
         if (!live[i]) continue;
         const SOp &o = ops[i];
         uint32_t rs[3] = {o.a, o.b, o.c};
         for (uint32_t r : rs)
-            if (r != NO_REF && !(r & CONST_FLAG)) live[r] = 1;
+            if (r != NO_REF && !(r & CONST_FLAG)) { live[r] = 1; uses[r]++; }
     }
-    // ---- uses (CSR), in program order
+    std::vector<uint8_t> absorbed(N, 0);
+    struct Fused {
+        std::vector<std::pair<uint32_t, uint32_t>> terms;
+        std::vector<uint32_t> addends;
+    };
+    std::unordered_map<uint32_t, Fused> roots;
+    if (enable && max_terms >= 2) {
+        std::vector<uint32_t> stack, nodes;
+        for (size_t i = N; i-- > 0;) {
+            if (!live[i] || absorbed[i] || ops[i].op != T_ADD) continue;
+            Fused f;
+            nodes.clear();
+            stack.assign(1, (uint32_t)i);
+            while (!stack.empty()) {
+                uint32_t n = stack.back();
+                stack.pop_back();
+                const SOp &o = ops[n];
+                uint32_t ch[2] = {o.a, o.b};
+                for (uint32_t r : ch) {
+                    if (r & CONST_FLAG) { f.addends.push_back(r); continue; }
+                    const SOp &c = ops[r];
+                    bool single = uses[r] == 1;
+                    if (single && c.op == T_ADD) { nodes.push_back(r); stack.push_back(r); continue; }
+                    if (single && c.op == T_MUL && ((c.a & CONST_FLAG) != 0) != ((c.b & CONST_FLAG) != 0)) {
+                        nodes.push_back(r);
+                        f.terms.emplace_back((c.a & CONST_FLAG) ? c.a : c.b, (c.a & CONST_FLAG) ? c.b : c.a);
+                        continue;
+                    }
+                    f.addends.push_back(r);
+                }
+            }
+            if (f.terms.size() < 2) continue;
+            for (uint32_t n : nodes) absorbed[n] = 1;
+            roots.emplace((uint32_t)i, std::move(f));
+        }
+    }
+    std::vector<uint32_t> remap(N, NO_REF);
+    auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
+    xp.ops.reserve(N);
+    for (size_t i = 0; i < N; i++) {
+        if (!live[i] || absorbed[i]) continue;
+        const SOp &o = ops[i];
+        auto it = roots.find((uint32_t)i);
+        if (it == roots.end()) {
+            XOp x{o.op, mapref(o.a), mapref(o.b), mapref(o.c), o.aux};
+            xp.ops.push_back(x);
+            remap[i] = (uint32_t)xp.ops.size() - 1;
+            continue;
+        }
+        Fused &f = it->second;
+        uint32_t v = NO_REF;
+        size_t next_addend = 0;
+        // constant addends fold into one constant is not possible here (no field arithmetic on this side of the
+        // tracer): they are applied one by one like the others
+        for (size_t t0 = 0; t0 < f.terms.size(); t0 += max_terms) {
+            size_t n = std::min<size_t>(max_terms, f.terms.size() - t0);
+            XOp x{T_DOT, NO_REF, NO_REF, NO_REF, 0};
+            x.t0 = (uint32_t)xp.terms.size();
+            x.tn = (uint32_t)n;
+            for (size_t k = 0; k < n; k++) xp.terms.emplace_back(f.terms[t0 + k].first, mapref(f.terms[t0 + k].second));
+            if (v != NO_REF) x.c = v;
+            else if (next_addend < f.addends.size()) x.c = mapref(f.addends[next_addend++]);
+            xp.ops.push_back(x);
+            v = (uint32_t)xp.ops.size() - 1;
+        }
+        for (; next_addend < f.addends.size(); next_addend++) {
+            XOp x{T_ADD, v, mapref(f.addends[next_addend]), NO_REF, 0};
+            xp.ops.push_back(x);
+            v = (uint32_t)xp.ops.size() - 1;
+        }
+        remap[i] = v;
+    }
+    xp.witness_ref.reserve(tr.witness_ref.size());
+    for (uint32_t r : tr.witness_ref) xp.witness_ref.push_back(mapref(r));
+    return xp;
+}
+
+inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
+    if (n_slots < 4) throw TraceError("need at least 4 slots");
+    const uint32_t max_terms = std::min<uint32_t>(16, n_slots - 2);
+    const XProg xp = fuse_dots(tr, max_terms, fuse);
+    const std::vector<XOp> &ops = xp.ops;
+    const size_t N = ops.size();
+    Tape out;
+    out.n_slots = n_slots;
+    out.n_wires = (uint32_t)xp.witness_ref.size();
+    out.stats.n_ssa = tr.ops.size();
+    out.stats.n_live = N;
+
+    auto operands = [&](const XOp &o, std::vector<uint32_t> &rs) {
+        rs.clear();
+        if (o.op == T_DOT) {
+            for (uint32_t k = 0; k < o.tn; k++) rs.push_back(xp.terms[o.t0 + k].second);
+            rs.push_back(o.c);
+        } else {
+            rs.push_back(o.a);
+            rs.push_back(o.b);
+            rs.push_back(o.c);
+        }
+    };
+    std::vector<uint32_t> rs;
+    // ---- uses (CSR), in program order (fuse_dots already dropped dead code)
     std::vector<uint32_t> use_cnt(N + 1, 0);
     for (size_t i = 0; i < N; i++) {
-        if (!live[i]) continue;
-        out.stats.n_live++;
-        const SOp &o = ops[i];
-        uint32_t rs[3] = {o.a, o.b, o.c};
+        operands(ops[i], rs);
         for (uint32_t r : rs)
             if (r != NO_REF && !(r & CONST_FLAG)) use_cnt[r + 1]++;
     }
@@ -169,9 +280,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
     {
         std::vector<uint32_t> fill(use_cnt.begin(), use_cnt.end() - 1);
         for (size_t i = 0; i < N; i++) {
-            if (!live[i]) continue;
-            const SOp &o = ops[i];
-            uint32_t rs[3] = {o.a, o.b, o.c};
+            operands(ops[i], rs);
             for (uint32_t r : rs)
                 if (r != NO_REF && !(r & CONST_FLAG)) use_pos[fill[r]++] = (uint32_t)i;
         }
@@ -183,16 +292,16 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
         return p < use_cnt[v + 1] ? use_pos[p] : 0xffffffffu;
     };
     // ---- witness wires per value
-    std::vector<uint32_t> wire_head(N, NO_REF), wire_next(tr.witness_ref.size(), NO_REF);
-    for (size_t w = tr.witness_ref.size(); w-- > 0;) {
-        uint32_t r = tr.witness_ref[w];
+    std::vector<uint32_t> wire_head(N, NO_REF), wire_next(xp.witness_ref.size(), NO_REF);
+    for (size_t w = xp.witness_ref.size(); w-- > 0;) {
+        uint32_t r = xp.witness_ref[w];
         if (r & CONST_FLAG) continue;
         wire_next[w] = wire_head[r];
         wire_head[r] = (uint32_t)w;
     }
     // constants bound to wires are stored up front
-    for (size_t w = 0; w < tr.witness_ref.size(); w++) {
-        uint32_t r = tr.witness_ref[w];
+    for (size_t w = 0; w < xp.witness_ref.size(); w++) {
+        uint32_t r = xp.witness_ref[w];
         if (r & CONST_FLAG) {
             out.ins.push_back(TapeIns{T_STC, 1, 0, r & ~CONST_FLAG, 0, (uint32_t)w});
             out.stats.n_stc++;
@@ -220,7 +329,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
         }
         live_now--;
     };
-    auto alloc_slot = [&](uint32_t pos, const int32_t *pinned, int npinned) -> uint32_t {
+    auto alloc_slot = [&](uint32_t pos, const std::vector<int32_t> &pinned) -> uint32_t {
         if (!free_slots.empty()) {
             uint32_t s = free_slots.back();
             free_slots.pop_back();
@@ -229,8 +338,8 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
         uint32_t best = 0xffffffffu, best_use = 0;
         for (uint32_t s = 0; s < n_slots; s++) {
             bool pin = false;
-            for (int k = 0; k < npinned; k++)
-                if (pinned[k] == (int32_t)s) pin = true;
+            for (int32_t q : pinned)
+                if (q == (int32_t)s) pin = true;
             if (pin) continue;
             uint32_t v = (uint32_t)slot_val[s];
             uint32_t nu = next_use(v, pos);
@@ -253,90 +362,112 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots) {
         return best;
     };
 
+    std::vector<int32_t> pinned, still;
+    std::vector<uint32_t> enc;
     for (size_t i = 0; i < N; i++) {
-        if (!live[i]) continue;
-        const SOp &o = ops[i];
+        const XOp &o = ops[i];
         uint32_t pos = (uint32_t)i;
-        uint32_t rs[3] = {o.a, o.b, o.c};
-        int32_t pinned[8];
-        int npinned = 0;
-        uint32_t enc[3] = {0, 0, 0};
-        uint8_t flags = 0;
+        operands(o, rs);
+        pinned.clear();
+        enc.assign(rs.size(), 0);
+        std::vector<uint8_t> isc(rs.size(), 0);
         // resident operands are pinned first so that loading one operand cannot evict another
-        for (int k = 0; k < 3; k++) {
-            uint32_t r = rs[k];
+        for (uint32_t r : rs) {
             if (r == NO_REF || (r & CONST_FLAG)) continue;
-            if (val_slot[r] >= 0) pinned[npinned++] = val_slot[r];
+            if (val_slot[r] >= 0) pinned.push_back(val_slot[r]);
         }
-        for (int k = 0; k < 3; k++) {
+        for (size_t k = 0; k < rs.size(); k++) {
             uint32_t r = rs[k];
             if (r == NO_REF) continue;
-            if (r & CONST_FLAG) { flags |= (uint8_t)(1u << k); enc[k] = r & ~CONST_FLAG; continue; }
+            if (r & CONST_FLAG) { isc[k] = 1; enc[k] = r & ~CONST_FLAG; continue; }
             if (val_slot[r] < 0) {
                 if (val_home[r] == NO_REF) throw TraceError("slot allocator: value lost");
-                uint32_t s = alloc_slot(pos, pinned, npinned);
+                uint32_t s = alloc_slot(pos, pinned);
                 out.ins.push_back(TapeIns{T_LD, 0, (uint16_t)s, 0, 0, val_home[r]});
                 out.stats.n_ld++;
                 val_slot[r] = (int32_t)s;
                 slot_val[s] = (int32_t)r;
-                pinned[npinned++] = (int32_t)s;
+                pinned.push_back((int32_t)s);
             }
             enc[k] = (uint32_t)val_slot[r];
         }
         // operands that die here free their slots before the destination is chosen
-        for (int k = 0; k < 3; k++) {
+        for (size_t k = 0; k < rs.size(); k++) {
             uint32_t r = rs[k];
             if (r == NO_REF || (r & CONST_FLAG)) continue;
-            if (val_slot[r] >= 0 && next_use(r, pos) == 0xffffffffu) {
-                bool dup = false;
-                for (int j = 0; j < k; j++)
-                    if (rs[j] == r) dup = true;
-                if (!dup) release_value(r);
-            } else if (val_slot[r] < 0 && next_use(r, pos) == 0xffffffffu) {
-                // already released through a duplicate operand
-            }
+            if (val_slot[r] >= 0 && next_use(r, pos) == 0xffffffffu) release_value(r);
         }
+        uint8_t flags = 0;
+        if (o.op != T_DOT)
+            for (size_t k = 0; k < 3; k++)
+                if (isc[k]) flags |= (uint8_t)(1u << k);
         if (o.op == T_FAIL_IF || o.op == T_FAIL_NE) {
             out.ins.push_back(TapeIns{o.op, flags, 0, enc[0], enc[1], o.aux});
             out.stats.n_fail++;
             continue;
         }
         // destination (may reuse the slot of an operand that died; ops read all operands before writing)
-        int32_t still[4];
-        int nstill = 0;
-        for (int k = 0; k < 3; k++) {
-            uint32_t r = rs[k];
+        still.clear();
+        for (uint32_t r : rs) {
             if (r == NO_REF || (r & CONST_FLAG)) continue;
-            if (val_slot[r] >= 0) still[nstill++] = val_slot[r];
+            if (val_slot[r] >= 0) still.push_back(val_slot[r]);
         }
-        uint32_t d = alloc_slot(pos, still, nstill);
+        uint32_t d = alloc_slot(pos, still);
         val_slot[i] = (int32_t)d;
         slot_val[d] = (int32_t)i;
         live_now++;
         out.stats.max_live = std::max(out.stats.max_live, live_now);
-        if (o.op == T_INPUT) enc[0] = o.aux;
-        if (o.op == T_BITC) enc[1] = o.aux;
         uint32_t w0 = wire_head[i];
-        if (o.op == T_SEL && (o.c & CONST_FLAG) && fr::is_zero(tr.consts[o.c & ~CONST_FLAG])) {
-            flags = (uint8_t)((flags & ~4u) | F_CZERO);
-            enc[2] = 0;
-        }
-        if (w0 != NO_REF && (o.op != T_SEL || (flags & F_CZERO))) {   // the first wire of the value is written by the producing instruction
-            flags |= F_STORE;
-            enc[2] = w0;
-            out.stats.n_st++;
-            val_home[i] = w0;
-            w0 = wire_next[w0];
-        }
-        out.ins.push_back(TapeIns{o.op, flags, (uint16_t)d, enc[0], enc[1], enc[2]});
-        switch (o.op) {
-            case T_MUL: out.stats.n_mul++; break;
-            case T_DIV: out.stats.n_div++; break;
-            case T_INV: out.stats.n_inv++; break;
-            case T_SEL: out.stats.n_sel++; break;
-            case T_ADD: case T_SUB: out.stats.n_addsub++; break;
-            case T_INPUT: out.stats.n_input++; break;
-            default: out.stats.n_other++; break;
+        if (o.op == T_DOT) {
+            // header: a = number of terms, b = addend (slot or constant index), c = wire row with F_STORE;
+            // then ceil(n/2) records of (constant index, slot) x 2
+            const bool has_add = o.c != NO_REF;
+            if (has_add) flags |= F_ADDEND;
+            if (has_add && isc[o.tn]) flags |= 2;
+            uint32_t row = 0;
+            if (w0 != NO_REF) {
+                flags |= F_STORE;
+                row = w0;
+                out.stats.n_st++;
+                val_home[i] = w0;
+                w0 = wire_next[w0];
+            }
+            out.ins.push_back(TapeIns{T_DOT, flags, (uint16_t)d, o.tn, has_add ? enc[o.tn] : 0u, row});
+            for (uint32_t k = 0; k < o.tn; k += 2) {
+                uint32_t rec[4] = {xp.terms[o.t0 + k].first & ~CONST_FLAG, enc[k], 0, 0};
+                if (k + 1 < o.tn) { rec[2] = xp.terms[o.t0 + k + 1].first & ~CONST_FLAG; rec[3] = enc[k + 1]; }
+                TapeIns raw;
+                static_assert(sizeof(raw) == sizeof(rec), "record size");
+                memcpy(&raw, rec, sizeof(rec));
+                out.ins.push_back(raw);
+            }
+            out.stats.n_dot++;
+            out.stats.n_dot_terms += o.tn;
+        } else {
+            uint32_t e0 = enc[0], e1 = enc[1], e2 = enc[2];
+            if (o.op == T_INPUT) e0 = o.aux;
+            if (o.op == T_BITC) e1 = o.aux;
+            if (o.op == T_SEL && (o.c != NO_REF) && (o.c & CONST_FLAG) && fr::is_zero(tr.consts[o.c & ~CONST_FLAG])) {
+                flags = (uint8_t)((flags & ~4u) | F_CZERO);
+                e2 = 0;
+            }
+            if (w0 != NO_REF && (o.op != T_SEL || (flags & F_CZERO))) {   // the first wire of the value is written by the producing instruction
+                flags |= F_STORE;
+                e2 = w0;
+                out.stats.n_st++;
+                val_home[i] = w0;
+                w0 = wire_next[w0];
+            }
+            out.ins.push_back(TapeIns{o.op, flags, (uint16_t)d, e0, e1, e2});
+            switch (o.op) {
+                case T_MUL: out.stats.n_mul++; break;
+                case T_DIV: out.stats.n_div++; break;
+                case T_INV: out.stats.n_inv++; break;
+                case T_SEL: out.stats.n_sel++; break;
+                case T_ADD: case T_SUB: out.stats.n_addsub++; break;
+                case T_INPUT: out.stats.n_input++; break;
+                default: out.stats.n_other++; break;
+            }
         }
         for (uint32_t w = w0; w != NO_REF; w = wire_next[w]) {
             out.ins.push_back(TapeIns{T_ST, 0, 0, d, 0, w});

@@ -35,7 +35,8 @@ enum TOp : uint8_t {
     T_FAIL_NE,   // status if a != b                (FAIL_IF(NEQ(a, b)): the `===` assert shape)
     T_BITC,      // bit `aux` of the RAW limbs of a  (a = y * R^-1, whose Montgomery limbs are the canonical y)
     T_INV,       // a^-1, with 0^-1 := 0  (ff.div a b is traced as a * INV(b) so that independent inversions can be batched)
-    // inserted by the allocator
+    // inserted by the tape builder
+    T_DOT,       // sum_k c_k * x_k (+ addend): fused tree of additions of products by constants (tape.hpp fuse_dots)
     T_LD, T_ST, T_STC, T_COUNT
 };
 

@@ -69,6 +69,8 @@ typedef struct {
     uint64_t ref_div;            /* ff.div the reference program executes per witness (Fr_div = mpz_invert + Fr_mul) */
     uint64_t tape_inv;           /* field inversions left on the tape after batching independent ones (Montgomery's trick) */
     uint64_t tape_sel;           /* selects on the tape (products with a 0/1 factor, if-converted branches, batch inversion) */
+    uint64_t tape_dot;           /* fused dot products sum c_k*x_k (one Montgomery reduction each) */
+    uint64_t tape_dot_terms;     /* their terms (64 multiply-accumulates each instead of 136) */
 } cvmgpu_program_info;
 
 typedef struct {
@@ -77,6 +79,7 @@ typedef struct {
     uint64_t nnz;                /* non-zeros of A, B and C together */
     uint64_t nnz_pm1;            /* of which coefficient +1 or -1 */
     uint32_t n_coefs;            /* distinct coefficients (interned) */
+    uint64_t nnz_small;          /* non-zeros evaluated on the small-coefficient path (|c| < 2^32, 8 MACs per term) */
 } cvmgpu_r1cs_info;
 
 const char *cvmgpu_last_error(void);

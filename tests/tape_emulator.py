@@ -7,8 +7,9 @@ and is not a fallback: the product path has no CPU execution.
 from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
- T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_INV, T_LD,
- T_ST, T_STC) = range(32)
+ T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_INV, T_DOT,
+ T_LD, T_ST, T_STC) = range(33)
+F_ADDEND = 32        # T_DOT: field b is an addend
 F_CZERO = 16         # T_SEL: third operand is the constant 0
 F_STORE = 8          # flag bit 3: the result is also stored to value-store row c
 R = 1 << 256
@@ -24,7 +25,12 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
     slots = [None] * n_slots
     rows = [None] * n_rows
     status = 0
-    for ins in tape:
+    import numpy as np
+    words = np.ascontiguousarray(tape).view(np.uint32).reshape(-1, 4)
+    pc = 0
+    while pc < len(tape):
+        ins = tape[pc]
+        pc += 1
         op, flags, dst, a, b, c = (int(ins["op"]), int(ins["flags"]), int(ins["dst"]), int(ins["a"]), int(ins["b"]),
                                    int(ins["c"]))
 
@@ -35,7 +41,19 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             assert v is not None, "read of an empty slot"
             return v
 
-        if op == T_INPUT:
+        if op == T_DOT:
+            # a terms follow as (constant index, slot) pairs, two per 16-byte record
+            acc = 0
+            for j in range(a):
+                rec = words[pc + j // 2]
+                cidx, slot = (int(rec[2]), int(rec[3])) if j & 1 else (int(rec[0]), int(rec[1]))
+                assert slots[slot] is not None
+                acc += consts[cidx] * slots[slot]
+            if flags & F_ADDEND:
+                acc += operand(b, 2)
+            pc += (a + 1) // 2
+            slots[dst] = acc % M.Q
+        elif op == T_INPUT:
             slots[dst] = inputs[a] % M.Q
         elif op == T_BITC:
             # bit b of the RAW (Montgomery) limbs of slot a

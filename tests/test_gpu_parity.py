@@ -132,14 +132,14 @@ def _write_r1cs(art, path):
                        n_labels=art.n_signals)
 
 
-@pytest.mark.parametrize("name", ["multiplier2", "lessthan8", "sum3cmp", "poseidon2"])
+@pytest.mark.parametrize("name", ["multiplier2", "lessthan8", "sum3cmp", "poseidon2", "num2bits8", "babyadd4"])
 def test_r1cs_check_accepts_valid_and_pinpoints_invalid(E, name, tmp_path):
     art = circuit(name)
     _write_r1cs(art, tmp_path / "c.r1cs")
     r = E.R1cs(str(tmp_path / "c.r1cs"))
     rng = random.Random(5)
     rows = [CASES[name][0]] * 3
-    if name in ("multiplier2", "poseidon2"):
+    if name in ("multiplier2", "poseidon2", "babyadd4"):
         rows += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(130)]
     wc = E.WitnessCalculator(cvm_text=art.cvm)
     wt, st = wc.calculate(rows)
@@ -210,3 +210,19 @@ def test_sha256_batch(E, tmp_path):
         assert vals[i] == sha256.sha256_bits(rows[i])
     full = E.le_to_ints(wt[3:4])[0]
     assert full == I.compute_witness(I.load(art.cvm), rows[3])
+    # corrupted wires (small-coefficient and +-1 paths of the check): same first violated constraint as a CPU walk
+    wt2 = wt[:3].copy()
+    wt2[0, 300, 0] ^= 1
+    wt2[1, art.n_wires - 5, 0] ^= 1
+    bad2 = r.check(wt2)
+    vals2 = E.le_to_ints(wt2)
+    for b in range(3):
+        w = vals2[b]
+        first = E.NO_BAD
+        for ci, (a, bb, c) in enumerate(art.constraints):
+            ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
+            if (ev(a) * ev(bb) - ev(c)) % M.Q:
+                first = ci
+                break
+        assert bad2[b] == first, b
+    assert bad2[2] == E.NO_BAD and bad2[0] != E.NO_BAD and bad2[1] != E.NO_BAD
