@@ -32,6 +32,10 @@ WORKLOADS = {
                   "chunk": 1 << 20, "e2e_batch": 1 << 17, "bits": False, "ref": "poseidon2_bench"},
     "sha256_512": {"label": "Sha256(512 bits)", "module": "sha256", "fn": "Sha256", "args": (512,), "batch": 1 << 16,
                    "chunk": 1 << 16, "e2e_batch": 1 << 10, "bits": True, "ref": "sha256_512"},
+    # config 4: valid signatures from the integer signer (tools/circuitgen/circuits/eddsa.py); a pool of distinct
+    # signatures is tiled over the batch (signing in Python is slow; the instruction stream does not depend on the data)
+    "eddsa": {"label": "EdDSAPoseidonVerifier", "module": "eddsa", "fn": "EdDSAPoseidonVerifier", "args": (),
+              "batch": 1 << 16, "chunk": 1 << 16, "e2e_batch": 1 << 13, "bits": False, "ref": "eddsa", "pool": 1024},
 }
 WL = WORKLOADS["poseidon2"]
 METRIC = "witnesses/sec (Poseidon(2) witness generation + R1CS check)"
@@ -135,18 +139,41 @@ def cpu_baseline_port(art, seconds=12.0):
                       % (n, WL["label"])}
 
 
+_POOL = {}
+
+
+def input_pool(art):
+    """Workloads whose inputs must be valid (EdDSA): -> uint8 array [pool, n_inputs, 32] of LE canonical values."""
+    import random
+
+    import numpy as np
+    if "rows" not in _POOL:
+        from tools.circuitgen.circuits import eddsa
+        rng = random.Random(0xC1C00003)
+        rows = [eddsa.sign(rng.randrange(1, 1 << 250), rng.randrange(1, 1 << 250), rng.randrange(1 << 253))
+                for _ in range(WL["pool"])]
+        buf = b"".join(int(v).to_bytes(32, "little") for r in rows for v in r)
+        _POOL["rows"] = np.frombuffer(buf, dtype=np.uint8).reshape(len(rows), art.n_inputs, 32).copy()
+    return _POOL["rows"]
+
+
 def reference_binary():
     p = os.path.join(ROOT, "oracle", "_ref", WL["ref"])
     return p if os.path.exists(p) else None
 
 
-def cpu_baseline_reference(n_threads, seconds=10.0):
+def cpu_baseline_reference(n_threads, seconds=10.0, art=None):
     """The reference's own C++ runtime + field arithmetic (oracle/_ref) running the Poseidon(2) program emitted
     in the WriteC shapes; run(ctx) only is timed inside the binary; one process per thread."""
     exe = reference_binary()
     if exe is None:
         return None
-    procs = [subprocess.Popen([exe, "--bench", str(seconds), str(1234 + i), "1" if WL["bits"] else "0"],
+    mode = ["1" if WL["bits"] else "0"]
+    if WL.get("pool"):
+        pool_path = os.path.join(tempfile.gettempdir(), "cvmbench_pool_%d.bin" % os.getpid())
+        input_pool(art).tofile(pool_path)
+        mode = ["2", pool_path]
+    procs = [subprocess.Popen([exe, "--bench", str(seconds), str(1234 + i)] + mode,
                               stdout=subprocess.PIPE, text=True, cwd=os.path.dirname(exe))
              for i in range(n_threads)]
     total, count = 0.0, 0
@@ -174,9 +201,9 @@ def run_reference_arm(args, art):
     per = max(2.0, min(20.0, 6.0))
     vals = []
     for _ in range(args.warmup):
-        cpu_baseline_reference(cores, 1.0) if reference_binary() else None
+        cpu_baseline_reference(cores, 1.0, art) if reference_binary() else None
     for _ in range(args.steps):
-        res = cpu_baseline_reference(cores, per)
+        res = cpu_baseline_reference(cores, per, art)
         if res is None:
             break
         vals.append(res["value"])
@@ -249,7 +276,10 @@ def main():
     n_chunks = (B + CH - 1) // CH
     g = torch.Generator(device=dev)
     g.manual_seed(0xC1C00001 + rank)
-    if WL["bits"]:
+    if WL.get("pool"):
+        pool = torch.from_numpy(input_pool(art)).to(dev)
+        inputs = pool.repeat((B + pool.shape[0] - 1) // pool.shape[0], 1, 1)[:B].contiguous()
+    elif WL["bits"]:
         inputs = torch.zeros((B, wc.n_inputs, 32), dtype=torch.uint8, device=dev)
         inputs[:, :, 0] = torch.randint(0, 2, (B, wc.n_inputs), dtype=torch.uint8, device=dev, generator=g)
     else:
@@ -380,7 +410,7 @@ def main():
     if args.skip_cpu:
         cpu = None
     else:
-        cpu = cpu_baseline_reference(os.cpu_count() or 1) or cpu_baseline_port(art)
+        cpu = cpu_baseline_reference(os.cpu_count() or 1, art=art) or cpu_baseline_port(art)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

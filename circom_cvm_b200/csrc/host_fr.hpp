@@ -31,7 +31,7 @@ inline Fr boolean(bool b) { return from_u64(b ? 1 : 0); }
 
 inline Fr mul(const Fr &a, const Fr &b) { return fr::mont_mul(fr::mont_mul(a, b), fr::r2_mont()); }
 
-// returns false when the reference's behaviour is abort/undefined (division by zero)
+// returns false when the reference aborts (integer division / modulo by zero: GMP raises)
 inline bool apply(FfOp op, const Fr &a, const Fr &b, Fr &out) {
     switch (op) {
         case F_ADD: out = fr::add(a, b); return true;
@@ -39,13 +39,13 @@ inline bool apply(FfOp op, const Fr &a, const Fr &b, Fr &out) {
         case F_NEG: out = fr::neg(a); return true;
         case F_MUL: out = mul(a, b); return true;
         case F_SQUARE: out = mul(a, a); return true;
+        // 0 has no inverse: the reference's Fr_inv hands back the 0 its mpz_init wrote (bn128/fr.cpp:146-157), so
+        // Fr_inv(0) = 0 and Fr_div(a, 0) = 0; mont_inv (a^(q-2)) gives the same
         case F_INV: {
-            if (fr::is_zero(a)) return false;
             out = fr::from_mont(fr::mont_inv(fr::to_mont(a)));
             return true;
         }
         case F_DIV: {
-            if (fr::is_zero(b)) return false;
             Fr bi = fr::mont_inv(fr::to_mont(b));     // Montgomery form of b^-1
             out = fr::mont_mul(a, bi);                // a * b^-1 * R * R^-1
             return true;

@@ -30,6 +30,11 @@ def circuits():
         "poseidon2": (poseidon.Poseidon, (2,)),
     }
     try:
+        from tools.circuitgen.circuits import eddsa
+        table["eddsa"] = (eddsa.EdDSAPoseidonVerifier, ())   # BASELINE config 4
+    except ImportError:
+        pass
+    try:
         from tools.circuitgen.circuits import sha256
         table["sha256_64"] = (sha256.Sha256, (64,))
         table["sha256_512"] = (sha256.Sha256, (512,))      # BASELINE config 3 (CPU baseline of bench.py --workload sha256_512)

@@ -252,9 +252,7 @@ class Machine:
                 cnt["div"] += 1
                 cnt["mul"] += 1
                 y = self.val(regs, a[1]) % M.Q
-                if y == 0:
-                    raise WitnessError(ST_DIVZERO, "ff.div by zero")
-                regs[dst] = M.div(self.val(regs, a[0]) % M.Q, y)
+                regs[dst] = M.div(self.val(regs, a[0]) % M.Q, y)      # a / 0 = 0, as the reference's Fr_div (fr_model.inv)
             elif op == "ff.eqz":
                 regs[dst] = int(self.val(regs, a[0]) % M.Q == 0)
             elif op == "ff.bnot":

@@ -51,9 +51,12 @@ def square(a):   # generic/fr.cpp:2309-2349
     return (a * a) % Q
 
 
-def inv(a):      # generic/fr.cpp:2895-2906 (mpz_invert; 0 has no inverse -> reference leaves r undefined)
+def inv(a):      # bn128/fr.cpp:146-157 Fr_inv: mpz_init(mr); mpz_invert(mr, ma, q); Fr_fromMpz(r, mr)
+    # 0 has no inverse: mpz_invert returns 0 and leaves mr untouched, i.e. the 0 of mpz_init, so the reference's
+    # Fr_inv(0) is 0 and Fr_div(a, 0) is 0 (observed by running the reference's own code here:
+    # tests/test_oracle_fr.py::test_reference_division_by_zero_is_zero).
     if a == 0:
-        raise FrError("inverse of zero")
+        return 0
     return pow(a, -1, Q)
 
 

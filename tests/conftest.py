@@ -53,7 +53,10 @@ def circuit(name):
         "opszoo": (basic.OpsZoo, ()),
         "poseidon2": (poseidon.Poseidon, (2,)),
     }
-    if name == "sha256_64":
+    if name == "eddsa":
+        from tools.circuitgen.circuits import eddsa
+        art = compile_circuit(eddsa.EdDSAPoseidonVerifier, (), name=name)
+    elif name == "sha256_64":
         from tools.circuitgen.circuits import sha256
         art = compile_circuit(sha256.Sha256, (64,), name=name)
     else:

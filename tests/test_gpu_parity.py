@@ -190,6 +190,32 @@ def test_device_api_with_torch_buffers(E):
         assert got[b] == I.compute_witness(I.load(art.cvm), rows[b])
 
 
+def test_eddsa_batch(E, tmp_path):
+    """Config 4 shape: EdDSAPoseidonVerifier over signatures from the integer signer, 1 in 8 forged: per-witness
+    flags, witness parity with the oracle, and the R1CS check."""
+    from tools.circuitgen.circuits import eddsa
+    art = circuit("eddsa")
+    rng = random.Random(23)
+    rows, forged = [], []
+    for i in range(72):
+        sig = eddsa.sign(rng.randrange(1, 1 << 250), rng.randrange(1, 1 << 250), rng.randrange(M.Q))
+        if i % 8 == 5:
+            sig[6] = (sig[6] + 1) % M.Q
+            forged.append(i)
+        rows.append(sig)
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    _write_r1cs(art, tmp_path / "e.r1cs")
+    r = E.R1cs(str(tmp_path / "e.r1cs"))
+    wt, st, bad = wc.calculate_checked(rows, r)
+    ok = [i for i in range(len(rows)) if i not in forged]
+    assert (st[forged] == E.ST_ASSERT).all() and (bad[forged] != E.NO_BAD).all()
+    assert not st[ok].any() and (bad[ok] == E.NO_BAD).all()
+    prog = I.load(art.cvm)
+    got = E.le_to_ints(wt[[0, 1, 70]])
+    for g, i in zip(got, (0, 1, 70)):
+        assert g == I.compute_witness(prog, rows[i])
+
+
 def test_sha256_batch(E, tmp_path):
     """Config 3 shape (bit-decomposition heavy): Sha256 over 64-bit messages, checked against hashlib for every
     witness, against the CVM oracle for one, and through the R1CS check."""

@@ -62,4 +62,23 @@ def test_host_limb_routines_match_reference_vectors(cvmlib):
     assert n > 2500
     # undefined-in-reference cases are flagged, not crashed on
     assert E.fr_host_op("idiv", 5, 0)[1] == 1
-    assert E.fr_host_op("inv", 0, 0)[1] == 1
+    assert E.fr_host_op("inv", 0, 0) == (0, 0) and E.fr_host_op("div", 5, 0) == (0, 0)
+
+
+def test_reference_division_by_zero_is_zero():
+    """Fr_inv(0): mpz_invert finds no inverse and leaves the freshly initialised result at 0 (bn128/fr.cpp:146-163),
+    so the reference computes a / 0 = 0 -- checked on the reference's own code when it is built here."""
+    import ctypes
+    import os
+    lib_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libfr_ref.so")
+    assert M.inv(0) == 0 and M.div(7, 0) == 0
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libfr_ref.so not built")
+    lib = ctypes.CDLL(lib_path)
+    lib.frref_op.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p]
+    lib.frref_op.restype = ctypes.c_int
+    for a in (0, 5, M.Q - 1, 1 << 200):
+        for af in (0, 1, 2):
+            out = ctypes.create_string_buffer(32)
+            assert lib.frref_op(b"div", M.to_le32(a), af, M.to_le32(0), 0, out) == 0
+            assert M.from_le32(out.raw) == 0

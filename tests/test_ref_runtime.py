@@ -69,6 +69,31 @@ def test_oracle_matches_reference_runtime_byte_for_byte(name, tmp_path):
         assert wout.read_bytes() == ours, (name, values)
 
 
+def test_eddsa_verifier_matches_reference_runtime(tmp_path):
+    """BASELINE config 4: EdDSAPoseidonVerifier on signatures from the integer signer; byte-identical .wtns."""
+    from tools.circuitgen.circuits import eddsa
+    exe = ref_binary("eddsa")
+    art = circuit("eddsa")
+    prog = I.load(art.cvm)
+    for k, (sk, nonce, msg) in enumerate([(123456789, 987654321, 42), (M.Q - 5, 7, 0)]):
+        values = eddsa.sign(sk, nonce, msg)
+        assert eddsa.verify(values)
+        jin, wout = tmp_path / ("in%d.json" % k), tmp_path / ("out%d.wtns" % k)
+        jin.write_text(json.dumps(input_json(art, values)))
+        subprocess.run([exe, str(jin), str(wout)], check=True, timeout=120)
+        assert wout.read_bytes() == formats.wtns_bytes(I.compute_witness(prog, values))
+    # a forged message aborts the reference (assert) and raises ASSERT in the oracle
+    values = eddsa.sign(11, 22, 33)
+    values[6] = 34
+    jin = tmp_path / "bad.json"
+    jin.write_text(json.dumps(input_json(art, values)))
+    r = subprocess.run([exe, str(jin), str(tmp_path / "bad.wtns")], capture_output=True, timeout=120)
+    assert r.returncode != 0
+    with pytest.raises(I.WitnessError) as e:
+        I.compute_witness(prog, values)
+    assert e.value.status == I.ST_ASSERT
+
+
 def test_reference_runtime_aborts_where_we_flag(tmp_path):
     """A failing `===` aborts the reference process (assert); the oracle raises status ASSERT."""
     exe = ref_binary("num2bits8")

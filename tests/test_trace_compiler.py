@@ -101,6 +101,40 @@ def test_unsupported_programs_are_rejected_with_a_reason(cvmlib):
     assert e.value.code == -3
 
 
+def test_eddsa_verifier_tape(cvmlib):
+    """BASELINE config 4 (EdDSAPoseidonVerifier: Baby Jubjub scalar multiplications, 1320 `<--` divisions).  The tape
+    (batched inversions, selects for 0/1 factors, fused dot products) reproduces the oracle's witness; forged
+    signatures and out-of-range S raise the assert flag; the witness satisfies the R1CS."""
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.circuits import babyjub, eddsa
+    art = circuit("eddsa")
+    prog = I.load(art.cvm)
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    info = wc.info
+    assert info.ref_div > 1000 and info.tape_inv * 4 < info.ref_div      # Montgomery's trick across independent divisions
+    tape, consts = wc.tape()
+    good = eddsa.sign(123456789, 987654321, 42)
+    assert eddsa.verify(good)
+    w = I.compute_witness(prog, good)
+    rows, status = run_tape(tape, consts, info.n_slots, wc.n_rows, good)
+    assert status == 0 and rows[:wc.n_wires] == w
+    for (a, b, c) in art.constraints:
+        ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
+        assert (ev(a) * ev(b) - ev(c)) % M.Q == 0
+    forged = list(good)
+    forged[6] = 43
+    big_s = list(good)
+    big_s[3] = good[3] + babyjub.SUBORDER            # same point, but S >= l must be rejected by CompConstant
+    disabled = list(forged)
+    disabled[0] = 0                                   # enabled = 0 switches every check off
+    for inp, want in ((forged, 1), (big_s, 1), (disabled, 0)):
+        _w, st = oracle(prog, inp)
+        rows, status = run_tape(tape, consts, info.n_slots, wc.n_rows, inp)
+        assert status == st == want, inp
+        if want == 0:
+            assert rows[:wc.n_wires] == _w
+
+
 def test_sha256_circuit_matches_hashlib(cvmlib):
     """Sha256(64 bits): one compression block, ~34K constraints.  The compiled tape must hash like hashlib
     (FIPS 180-4) and its witness must satisfy every R1CS constraint."""

@@ -97,14 +97,32 @@ def add(p, q):
     return (x3, y3)
 
 
+def _padd(p, q):
+    """projective (X:Y:Z) unified addition (Bernstein-Lange add-2008-bbjlp): no inversion"""
+    x1, y1, z1 = p
+    x2, y2, z2 = q
+    a_ = z1 * z2 % P
+    b_ = a_ * a_ % P
+    c_ = x1 * x2 % P
+    d_ = y1 * y2 % P
+    e_ = D * c_ * d_ % P
+    f_ = (b_ - e_) % P
+    g_ = (b_ + e_) % P
+    x3 = a_ * f_ * ((x1 + y1) * (x2 + y2) - c_ - d_) % P
+    y3 = a_ * g_ * (d_ - A * c_) % P
+    return (x3, y3, f_ * g_ % P)
+
+
 def mul(k, p):
-    r = (0, 1)
+    r = (0, 1, 1)
+    q = (p[0], p[1], 1)
     while k:
         if k & 1:
-            r = add(r, p)
-        p = add(p, p)
+            r = _padd(r, q)
+        q = _padd(q, q)
         k >>= 1
-    return r
+    zi = inv(r[2])
+    return (r[0] * zi % P, r[1] * zi % P)
 
 
 GENERATOR = (995203441582195749578291179787384436505546430278305826713579947235728471134,
