@@ -178,6 +178,7 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_sel = p->tape.stats.n_sel;
     info->tape_dot = p->tape.stats.n_dot;
     info->tape_dot_terms = p->tape.stats.n_dot_terms;
+    info->tape_macs = p->tape.stats.macs;
     return CVMGPU_OK;
 }
 
@@ -219,7 +220,13 @@ static int upload_program(cvmgpu_program *p) {
     if (!p->consts_mont.empty())
         CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
     size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * CVM_NT;
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 2));
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
+    // the slots want the whole shared-memory carve-out of the SM (more resident CTAs); nothing here relies on L1
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     p->device = dev;
     return CVMGPU_OK;
 }
@@ -245,10 +252,21 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     tp.n_inputs = p->n_inputs;
     tp.status = (uint32_t *)d_status;
     tp.B = B;
-    size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * CVM_NT;
-    uint64_t grid = (B + CVM_NT - 1) / CVM_NT;
+    // CTA size: 128 witnesses for large batches; smaller CTAs when the batch would leave SMs with an uneven number of
+    // CTAs (a 64 K batch is 512 CTAs of 128 for 148 SMs: 3.46 per SM)
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const uint64_t want = (uint64_t)sms * 8;
+    const uint32_t nt = (B / 128 >= want) ? 128u : (B / 64 >= want) ? 64u : 32u;
+    size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * nt;
+    uint64_t grid = (B + nt - 1) / nt;
     if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
-    kern::tape_kernel<<<(unsigned)grid, CVM_NT, smem, (cudaStream_t)stream>>>(tp);
+    if (nt == 128) kern::tape_kernel<128><<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(tp);
+    else if (nt == 64) kern::tape_kernel<64><<<(unsigned)grid, 64, smem, (cudaStream_t)stream>>>(tp);
+    else kern::tape_kernel<32><<<(unsigned)grid, 32, smem, (cudaStream_t)stream>>>(tp);
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }
@@ -392,6 +410,8 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
     info->nnz = r->file.terms.size();
     info->nnz_pm1 = r->file.nnz_pm1;
     info->nnz_small = r->file.nnz_small;
+    info->macs = r->file.macs;
+    info->n_quadratic = r->file.n_quadratic;
     info->n_coefs = (uint32_t)r->file.coefs.size();
     return CVMGPU_OK;
 }
@@ -587,6 +607,7 @@ extern "C" int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms_ou
             case 3: kern::imad_kernel<3><<<blocks, 256>>>(d, iters, 12345u + rep); break;
             case 4: kern::imad_kernel<4><<<blocks, 256>>>(d, iters, 12345u + rep); break;
             case 5: kern::imad_kernel<5><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 7: kern::imad_kernel<7><<<blocks, 256>>>(d, iters, 12345u + rep); break;
             default: kern::imad_kernel<6><<<blocks, 256>>>(d, iters, 12345u + rep); break;
         }
         CUDA_TRY(cudaEventRecord(e1));

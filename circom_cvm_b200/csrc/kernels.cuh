@@ -20,7 +20,7 @@ namespace kern {
 
 using fr::Fr;
 
-#define CVM_NT 128   // threads (= witnesses) per CTA of the tape kernel
+#define CVM_NT 128   // threads (= witnesses) per CTA of the tape kernel for large batches (64 / 32 for small ones)
 
 __device__ __forceinline__ Fr unpack(const uint4 &lo, const uint4 &hi) {
     Fr r;
@@ -58,14 +58,15 @@ __device__ __forceinline__ Fr op_input(Fr v) {
 }
 
 // operand fetch: constant table (uniform address, L1-resident) or the thread's slot in shared memory
+template <int NT>
 __device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint4 *consts, uint32_t idx, bool is_const, uint32_t tid) {
     uint4 lo, hi;
     if (is_const) {
         lo = __ldg(consts + 2 * (uint64_t)idx);
         hi = __ldg(consts + 2 * (uint64_t)idx + 1);
     } else {
-        lo = slots[(idx * 2) * CVM_NT + tid];
-        hi = slots[(idx * 2 + 1) * CVM_NT + tid];
+        lo = slots[(idx * 2) * NT + tid];
+        hi = slots[(idx * 2 + 1) * NT + tid];
     }
     return unpack(lo, hi);
 }
@@ -112,6 +113,7 @@ __device__ __forceinline__ Fr slow_compute(uint32_t op, const Fr &a, const Fr &b
 
 // Everything that is not on the fast path of the tape loop (integer-view operations, division, inputs).  Out of
 // line, operands and result go through the slots, so that the hot loop keeps its working set in registers.
+template <int NT>
 __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uint4 *consts, const uint4 *inputs,
                                               uint32_t n_inputs, uint64_t w, uint32_t status) {
     const uint32_t tid = threadIdx.x;
@@ -121,15 +123,15 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
         const uint4 *src = inputs + (w * n_inputs + cur.y) * 2;
         r = op_input(unpack(src[0], src[1]));
     } else {
-        Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+        Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
         Fr b = fr::zero();
-        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand(slots, consts, cur.z, flags & 2u, tid);
+        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid);
         r = slow_compute(op, a, b, status);
     }
     uint4 lo, hi;
     pack(r, lo, hi);
-    slots[(dst * 2) * CVM_NT + tid] = lo;
-    slots[(dst * 2 + 1) * CVM_NT + tid] = hi;
+    slots[(dst * 2) * NT + tid] = lo;
+    slots[(dst * 2 + 1) * NT + tid] = hi;
     return status;
 }
 
@@ -137,10 +139,11 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
 // opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, SEL, EQ / NEQ / EQZ, BITC, the failure
 // checks and the value-store moves; the result of a producing instruction can be written to its witness wire by
 // the same instruction (flag bit 3).
-__global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
+template <int NT>
+__global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
     extern __shared__ uint4 slots[];
     const uint32_t tid = threadIdx.x;
-    uint64_t w = (uint64_t)blockIdx.x * CVM_NT + tid;
+    uint64_t w = (uint64_t)blockIdx.x * NT + tid;
     const bool active = w < p.B;
     if (!active) w = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
     uint32_t status = 0;
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
         const uint32_t dst = cur.x >> 16;
         Fr r;
         if (op >= tape::T_ADD && op <= tape::T_MUL) {
-            const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
-            const Fr b = tape_operand(slots, consts, cur.z, flags & 2u, tid);
+            const Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
+            const Fr b = tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid);
             if (op == tape::T_MUL) r = fr::mont_mul(a, b);
             else if (op == tape::T_ADD) r = fr::add(a, b);
             else r = fr::sub(a, b);
@@ -173,15 +176,15 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
                 const uint4 rec = __ldg(tp + pc + 1 + (j >> 1));
                 const uint32_t cidx = (j & 1u) ? rec.z : rec.x, slot = (j & 1u) ? rec.w : rec.y;
                 const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cidx), __ldg(consts + 2 * (uint64_t)cidx + 1));
-                const Fr x = unpack(slots[(slot * 2) * CVM_NT + tid], slots[(slot * 2 + 1) * CVM_NT + tid]);
+                const Fr x = unpack(slots[(slot * 2) * NT + tid], slots[(slot * 2 + 1) * NT + tid]);
                 fr::wide_mac(T, c, x);
             }
             r = fr::wide_reduce(T, n);
-            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand(slots, consts, cur.z, flags & 2u, tid));
+            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid));
             pc += (n + 1) >> 1;
             raw = __ldg(tp + min(pc + 1, n_ins - 1));
         } else if (op == tape::T_SEL) {
-            const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+            const Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
             const bool t = !fr::is_zero(a);
             // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
             const bool isc = t ? (flags & 2u) : (flags & 4u);
@@ -189,20 +192,20 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
             uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
             if (t || !(flags & tape::F_CZERO)) {
                 if (isc) { lo = __ldg(consts + 2 * (uint64_t)idx); hi = __ldg(consts + 2 * (uint64_t)idx + 1); }
-                else { lo = slots[(idx * 2) * CVM_NT + tid]; hi = slots[(idx * 2 + 1) * CVM_NT + tid]; }
+                else { lo = slots[(idx * 2) * NT + tid]; hi = slots[(idx * 2 + 1) * NT + tid]; }
             }
             r = unpack(lo, hi);
         } else if (op == tape::T_BITC) {
             // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
             const uint32_t limb = cur.z >> 5;
-            const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * CVM_NT + tid) << 2) + (limb & 3u)];
+            const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * NT + tid) << 2) + (limb & 3u)];
             r = mont_bool((word >> (cur.z & 31u)) & 1u);
         } else if (op == tape::T_EQ || op == tape::T_NEQ || op == tape::T_EQZ || op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
-            const Fr a = tape_operand(slots, consts, cur.y, flags & 1u, tid);
+            const Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
             bool e;
             if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = fr::is_zero(a);
-            else e = fr::equal(a, tape_operand(slots, consts, cur.z, flags & 2u, tid));
+            else e = fr::equal(a, tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid));
             if (op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
                 if (!e && status == 0) status = cur.w;
                 continue;
@@ -210,13 +213,13 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
             r = mont_bool(op == tape::T_NEQ ? !e : e);
         } else if (op == tape::T_LD) {
             const uint4 *src = wbase + ((uint64_t)cur.w * 2) * bstride;
-            slots[(dst * 2) * CVM_NT + tid] = src[0];
-            slots[(dst * 2 + 1) * CVM_NT + tid] = src[bstride];
+            slots[(dst * 2) * NT + tid] = src[0];
+            slots[(dst * 2 + 1) * NT + tid] = src[bstride];
             continue;
         } else if (op == tape::T_ST || op == tape::T_STC) {
             uint4 lo, hi;
             if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
-            else { lo = slots[(cur.y * 2) * CVM_NT + tid]; hi = slots[(cur.y * 2 + 1) * CVM_NT + tid]; }
+            else { lo = slots[(cur.y * 2) * NT + tid]; hi = slots[(cur.y * 2 + 1) * NT + tid]; }
             if (active) {
                 uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
                 d[0] = lo;
@@ -224,20 +227,20 @@ __global__ void __launch_bounds__(CVM_NT) tape_kernel(TapeParams p) {
             }
             continue;
         } else {
-            status = tape_slow_op(cur, slots, consts, p.inputs, p.n_inputs, w, status);
+            status = tape_slow_op<NT>(cur, slots, consts, p.inputs, p.n_inputs, w, status);
             if (flags & tape::F_STORE) {
                 if (active) {
                     uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
-                    d[0] = slots[(dst * 2) * CVM_NT + tid];
-                    d[bstride] = slots[(dst * 2 + 1) * CVM_NT + tid];
+                    d[0] = slots[(dst * 2) * NT + tid];
+                    d[bstride] = slots[(dst * 2 + 1) * NT + tid];
                 }
             }
             continue;
         }
         uint4 lo, hi;
         pack(r, lo, hi);
-        slots[(dst * 2) * CVM_NT + tid] = lo;
-        slots[(dst * 2 + 1) * CVM_NT + tid] = hi;
+        slots[(dst * 2) * NT + tid] = lo;
+        slots[(dst * 2 + 1) * NT + tid] = hi;
         if ((flags & tape::F_STORE) && active) {
             uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
             d[0] = lo;
@@ -510,9 +513,17 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t *out, uint32_t iters
             STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
 #undef STEP
         } else if (KIND == 1) { // mad.wide.u32
+            // the multiplicand is the low word of the chain's own accumulator (a register alias, no instruction): with
+            // loop-invariant multiplicands ptxas hoists the product and the loop degenerates into IADD3s
 #define STEPW(r) asm volatile("{ .reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(r) : "r"(y));
             STEPW(d0) STEPW(d1) STEPW(d2) STEPW(d3) STEPW(d4) STEPW(d5) STEPW(d6) STEPW(d7)
 #undef STEPW
+        } else if (KIND == 7) { // mul.wide.u32 with a zero addend (the form mont_mul_wide uses)
+            // both halves of the product feed the next multiplicand (a dead high half would let ptxas use a 32-bit IMAD);
+            // the add runs on the ALU pipe
+#define STEPM(r) asm volatile("{ .reg .u64 e; .reg .u32 el, eh; mul.wide.u32 e, %0, %1; mov.b64 {el, eh}, e; add.u32 %0, el, eh; }" : "+r"(r) : "r"(y));
+            STEPM(a0) STEPM(a1) STEPM(a2) STEPM(a3) STEPM(a4) STEPM(a5) STEPM(a6) STEPM(a7)
+#undef STEPM
         } else if (KIND == 2) { // mad.lo only (2 per step so that the op count matches kind 0)
 #define STEP(r) asm volatile("mad.lo.u32 %0, %0, %1, %0;\n\tmad.lo.u32 %0, %0, %1, %0;" : "+r"(r) : "r"(y));
             STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)

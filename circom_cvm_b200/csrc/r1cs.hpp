@@ -39,6 +39,9 @@ struct File {
     std::vector<fr::Fr> coefs;       // canonical
     std::vector<uint64_t> wire2label;
     uint64_t nnz_pm1 = 0, nnz_small = 0;
+    // what the check kernel executes per witness: 64 multiply-accumulates per general term + 72 per reduction of a dot
+    // product (<= 16 terms), 8 per small term + 170 per small-class reduction, 136 per quadratic constraint
+    uint64_t macs = 0, n_quadratic = 0, n_linear = 0;
 };
 
 struct Error : std::runtime_error {
@@ -159,6 +162,13 @@ inline File load(const std::string &path) {
         out.split[3 * j + 1] = out.ptr[j] + (uint32_t)(n0 + n1);
         out.split[3 * j + 2] = out.ptr[j] + (uint32_t)(n0 + n1 + n2);
         out.nnz_small += n1 + n2;
+        size_t n3 = (size_t)(e - b) - n0 - n1 - n2;
+        out.macs += 8 * (n1 + n2) + 170 * ((n1 ? 1 : 0) + (n2 ? 1 : 0)) + 64 * n3 + 72 * ((n3 + 15) / 16);
+    }
+    for (uint32_t c = 0; c < out.n_constraints; c++) {
+        bool quad = out.ptr[3 * c] != out.ptr[3 * c + 1] && out.ptr[3 * c + 1] != out.ptr[3 * c + 2];
+        if (quad) { out.n_quadratic++; out.macs += 136; }
+        else out.n_linear++;
     }
     if (have[3]) {
         size_t wp = sec_pos[3];

@@ -34,6 +34,10 @@ struct TapeStats {
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0;
     uint32_t n_spill_rows = 0;
+    // 32x32->64 multiply-accumulates the kernel executes per witness: 136 per Montgomery product (also the one that brings
+    // an input to Montgomery form and the one after an inversion), 64 per DOT term + 72 per DOT reduction, and the
+    // 20 x 90 of the safegcd inversion's matrix updates
+    uint64_t macs = 0;
     uint32_t max_live = 0;
 };
 
@@ -479,6 +483,8 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
     out.n_rows = out.n_wires + spill_rows;
     out.stats.n_spill_rows = spill_rows;
     out.stats.n_tape = out.ins.size();
+    out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +
+                     72 * out.stats.n_dot + 1800 * (out.stats.n_inv + out.stats.n_div);
     return out;
 }
 

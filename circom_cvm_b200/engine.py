@@ -50,7 +50,7 @@ class ProgramInfo(ctypes.Structure):
                 ("tape_div", c_uint64), ("tape_addsub", c_uint64), ("tape_other", c_uint64), ("tape_ld", c_uint64),
                 ("tape_st", c_uint64), ("tape_spill_st", c_uint64), ("n_consts", c_uint32), ("dyn_branches", c_uint32),
                 ("ref_div", c_uint64), ("tape_inv", c_uint64), ("tape_sel", c_uint64), ("tape_dot", c_uint64),
-                ("tape_dot_terms", c_uint64)]
+                ("tape_dot_terms", c_uint64), ("tape_macs", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -59,7 +59,7 @@ class ProgramInfo(ctypes.Structure):
 class R1csInfo(ctypes.Structure):
     _fields_ = [("n_wires", c_uint32), ("n_pub_out", c_uint32), ("n_pub_in", c_uint32), ("n_prv_in", c_uint32),
                 ("n_constraints", c_uint32), ("n_labels", c_uint64), ("nnz", c_uint64), ("nnz_pm1", c_uint64),
-                ("n_coefs", c_uint32), ("nnz_small", c_uint64)]
+                ("n_coefs", c_uint32), ("nnz_small", c_uint64), ("macs", c_uint64), ("n_quadratic", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

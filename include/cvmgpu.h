@@ -71,6 +71,7 @@ typedef struct {
     uint64_t tape_sel;           /* selects on the tape (products with a 0/1 factor, if-converted branches, batch inversion) */
     uint64_t tape_dot;           /* fused dot products sum c_k*x_k (one Montgomery reduction each) */
     uint64_t tape_dot_terms;     /* their terms (64 multiply-accumulates each instead of 136) */
+    uint64_t tape_macs;          /* 32x32->64 multiply-accumulates the tape kernel executes per witness */
 } cvmgpu_program_info;
 
 typedef struct {
@@ -80,6 +81,8 @@ typedef struct {
     uint64_t nnz_pm1;            /* of which coefficient +1 or -1 */
     uint32_t n_coefs;            /* distinct coefficients (interned) */
     uint64_t nnz_small;          /* non-zeros evaluated on the small-coefficient path (|c| < 2^32, 8 MACs per term) */
+    uint64_t macs;               /* 32x32->64 multiply-accumulates the check kernel executes per witness */
+    uint64_t n_quadratic;        /* constraints with non-empty A and B (one Montgomery product each) */
 } cvmgpu_r1cs_info;
 
 const char *cvmgpu_last_error(void);
