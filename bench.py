@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="witnesses per kernel launch (the value store is sized for it)")
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--tape-mode", type=int, default=0, help="witnesses per thread of the tape kernel: 0 auto, 1, 2")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out")
     args = ap.parse_args()
@@ -267,6 +268,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     E.set_device(local)
+    E.set_tape_mode(args.tape_mode)
     dev = torch.device("cuda", local)
 
     wc = E.WitnessCalculator(cvm_path=cvm_path, n_slots=args.slots)

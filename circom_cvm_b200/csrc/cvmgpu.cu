@@ -19,6 +19,7 @@
 #include "tracer.hpp"
 
 static thread_local std::string g_err;
+static int g_tape_mode = 0;
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -76,6 +77,11 @@ extern "C" int cvmgpu_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+extern "C" int cvmgpu_set_tape_mode(int mode) {
+    g_tape_mode = mode;
+    return CVMGPU_OK;
 }
 
 extern "C" int cvmgpu_set_device(int device) {
@@ -219,14 +225,17 @@ static int upload_program(cvmgpu_program *p) {
         CUDA_TRY(cudaMemcpy(p->d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
     if (!p->consts_mont.empty())
         CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
-    size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * CVM_NT;
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 2));
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
-    // the slots want the whole shared-memory carve-out of the SM (more resident CTAs); nothing here relies on L1
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    // dynamic shared memory = n_slots x 32 B per witness of the CTA; the slots want the whole carve-out of the SM
+    // (more resident CTAs), nothing here relies on L1
+    const size_t per_w = (size_t)p->tape.n_slots * 2 * sizeof(uint4);
+#define CVM_SET_ATTR(NT, W)                                                                                              \
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_w * NT * W))); \
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CVM_SET_ATTR(128, 1)
+    CVM_SET_ATTR(64, 1)
+    CVM_SET_ATTR(32, 1)
+    if (per_w * 128 * 2 <= 227 * 1024) { CVM_SET_ATTR(128, 2) }
+#undef CVM_SET_ATTR
     p->device = dev;
     return CVMGPU_OK;
 }
@@ -259,14 +268,28 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    // One witness per thread, with smaller CTAs when the batch would leave SMs unevenly loaded (a 64 K batch is 512 CTAs
+    // of 128 for 148 SMs: 3.46 per SM).  The two-witnesses-per-thread variant (two independent carry chains per thread,
+    // which lifts the bare multiplier from 45.7 to 62 G products/s) is kept behind cvmgpu_set_tape_mode(2): in the real
+    // kernel it halves the resident warps (shared-memory slots) and measured 21.0 ms against 18.3 ms on Poseidon(2).
     const uint64_t want = (uint64_t)sms * 8;
-    const uint32_t nt = (B / 128 >= want) ? 128u : (B / 64 >= want) ? 64u : 32u;
-    size_t smem = (size_t)p->tape.n_slots * 2 * sizeof(uint4) * nt;
-    uint64_t grid = (B + nt - 1) / nt;
-    if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
-    if (nt == 128) kern::tape_kernel<128><<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(tp);
-    else if (nt == 64) kern::tape_kernel<64><<<(unsigned)grid, 64, smem, (cudaStream_t)stream>>>(tp);
-    else kern::tape_kernel<32><<<(unsigned)grid, 32, smem, (cudaStream_t)stream>>>(tp);
+    const size_t per_w = (size_t)p->tape.n_slots * 2 * sizeof(uint4);
+    int mode = g_tape_mode;   // 0 auto, 1: W=1, 2: W=2 (cvmgpu_set_tape_mode, for experiments)
+    const bool w2_ok = per_w * 128 * 2 <= 227 * 1024;
+    const bool w2 = w2_ok && mode == 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w2) {
+        uint64_t grid = (B + 255) / 256;
+        if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
+        kern::tape_kernel<128, 2><<<(unsigned)grid, 128, per_w * 256, st>>>(tp);
+    } else {
+        const uint32_t nt = (B / 128 >= want) ? 128u : (B / 64 >= want) ? 64u : 32u;
+        uint64_t grid = (B + nt - 1) / nt;
+        if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
+        if (nt == 128) kern::tape_kernel<128, 1><<<(unsigned)grid, 128, per_w * 128, st>>>(tp);
+        else if (nt == 64) kern::tape_kernel<64, 1><<<(unsigned)grid, 64, per_w * 64, st>>>(tp);
+        else kern::tape_kernel<32, 1><<<(unsigned)grid, 32, per_w * 32, st>>>(tp);
+    }
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }
@@ -570,6 +593,7 @@ extern "C" int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_se
     for (int rep = 0; rep < 4; rep++) {
         CUDA_TRY(cudaEventRecord(e0));
         if (variant == 0) kern::mulbench_kernel<0><<<blocks, 128>>>(d, iters, 7u + rep);
+        else if (variant == 2) kern::mulbench_kernel<2><<<blocks, 128>>>(d, iters, 7u + rep);
         else kern::mulbench_kernel<1><<<blocks, 128>>>(d, iters, 7u + rep);
         CUDA_TRY(cudaEventRecord(e1));
         CUDA_TRY(cudaEventSynchronize(e1));

@@ -271,7 +271,7 @@ FR_HD Fr mont_mul_portable(const Fr &a, const Fr &b) {
 // 8 IMAD.WIDE + 17 carry-chain adds per 8 multiply-accumulates, with the multiplies on the FMA pipe and the
 // adds on the ALU pipe.  The reduction row (m*q) has the same shape with q as immediates.
 __device__ __forceinline__ void mac_row(uint32_t *t, const uint32_t *x, uint32_t y) {
-    asm volatile(
+    asm(
         "{\n\t"
         ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
         ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
@@ -314,7 +314,7 @@ __device__ __forceinline__ void mac_row(uint32_t *t, const uint32_t *x, uint32_t
 }
 // T += m * q with q as immediates
 __device__ __forceinline__ void mac_row_q(uint32_t *t, uint32_t m) {
-    asm volatile(
+    asm(
         "{\n\t"
         ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
         ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
@@ -410,7 +410,7 @@ __device__ __forceinline__ Fr mont_mul_wide(const Fr &a, const Fr &b) {
         "addc.u32 %9, %9, 0;\n\t"
 // t[0..8] += x * y, carry out of t[8] counted in ovf
 __device__ __forceinline__ void mac_row_ovf(uint32_t *t, uint32_t &ovf, const uint32_t *x, uint32_t y) {
-    asm volatile(
+    asm(
         "{\n\t"
         ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
         ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
@@ -429,7 +429,7 @@ __device__ __forceinline__ void mac_row_ovf(uint32_t *t, uint32_t &ovf, const ui
 }
 // t[0..8] += m * q, carry out of t[8] counted in ovf
 __device__ __forceinline__ void mac_row_q_ovf(uint32_t *t, uint32_t &ovf, uint32_t m) {
-    asm volatile(
+    asm(
         "{\n\t"
         ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
         ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
@@ -464,7 +464,7 @@ __device__ __forceinline__ void wide_mac(Wide &T, const Fr &c, const Fr &v) {
 }
 // t[9..16] += ovf[0..7]
 __device__ __forceinline__ void wide_fold(Wide &T) {
-    asm volatile(
+    asm(
         "add.cc.u32 %0, %0, %8;\n\t"
         "addc.cc.u32 %1, %1, %9;\n\t"
         "addc.cc.u32 %2, %2, %10;\n\t"

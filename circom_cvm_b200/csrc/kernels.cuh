@@ -115,8 +115,7 @@ __device__ __forceinline__ Fr slow_compute(uint32_t op, const Fr &a, const Fr &b
 // line, operands and result go through the slots, so that the hot loop keeps its working set in registers.
 template <int NT>
 __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uint4 *consts, const uint4 *inputs,
-                                              uint32_t n_inputs, uint64_t w, uint32_t status) {
-    const uint32_t tid = threadIdx.x;
+                                              uint32_t n_inputs, uint64_t w, uint32_t status, uint32_t tid) {
     const uint32_t op = cur.x & 0xffu, flags = (cur.x >> 8) & 0xffu, dst = cur.x >> 16;
     Fr r;
     if (op == tape::T_INPUT) {
@@ -136,18 +135,32 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
 }
 
 // One tape pass per witness.  Control flow is uniform (one instruction stream per circuit), so the branches on the
-// opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, SEL, EQ / NEQ / EQZ, BITC, the failure
+// opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, DOT, SEL, EQ / NEQ / EQZ, BITC, the failure
 // checks and the value-store moves; the result of a producing instruction can be written to its witness wire by
 // the same instruction (flag bit 3).
-template <int NT>
+//
+// W witnesses per thread (lanes tid + k*NT of a CTA that covers NT*W witnesses): the W copies of every operation
+// are independent, which gives the instruction scheduler two carry chains to interleave.  Measured on the bare
+// multiplier (cvmgpu_mul_peak): one dependent chain per thread tops out at 45.7 G products/s whatever the
+// occupancy, two independent chains reach 62 G products/s (profiles/r01_summary.md).
+template <int NT, int W>
 __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
+    constexpr int NS = NT * W;   // witnesses per CTA = stride of one slot half in shared memory
     extern __shared__ uint4 slots[];
-    const uint32_t tid = threadIdx.x;
-    uint64_t w = (uint64_t)blockIdx.x * NT + tid;
-    const bool active = w < p.B;
-    if (!active) w = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
-    uint32_t status = 0;
-    uint4 *const wbase = p.store + w;
+    uint32_t tk[W];
+    uint64_t w[W];
+    bool active[W];
+    uint32_t status[W];
+    uint4 *wbase[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        tk[k] = threadIdx.x + k * NT;
+        w[k] = (uint64_t)blockIdx.x * NS + tk[k];
+        active[k] = w[k] < p.B;
+        if (!active[k]) w[k] = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
+        status[k] = 0;
+        wbase[k] = p.store + w[k];
+    }
     const uint64_t bstride = p.bstride;
     const uint4 *const consts = p.consts;
 
@@ -160,94 +173,137 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
-        Fr r;
+        Fr r[W];
         if (op >= tape::T_ADD && op <= tape::T_MUL) {
-            const Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
-            const Fr b = tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid);
-            if (op == tape::T_MUL) r = fr::mont_mul(a, b);
-            else if (op == tape::T_ADD) r = fr::add(a, b);
-            else r = fr::sub(a, b);
+            Fr a[W], b[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                a[k] = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
+                b[k] = tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]);
+            }
+            if (op == tape::T_MUL) {
+#pragma unroll
+                for (int k = 0; k < W; k++) r[k] = fr::mont_mul(a[k], b[k]);
+            } else if (op == tape::T_ADD) {
+#pragma unroll
+                for (int k = 0; k < W; k++) r[k] = fr::add(a[k], b[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; k++) r[k] = fr::sub(a[k], b[k]);
+            }
         } else if (op == tape::T_DOT) {
-            // sum_k c_k * x_k (+ addend): cur.y terms in the following ceil(n/2) records of (constant, slot) pairs
+            // sum_j c_j * x_j (+ addend): cur.y terms in the following ceil(n/2) records of (constant, slot) pairs
             const uint32_t n = cur.y;
-            fr::Wide T;
-            fr::wide_zero(T);
+            fr::Wide T[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) fr::wide_zero(T[k]);
             for (uint32_t j = 0; j < n; j++) {
                 const uint4 rec = __ldg(tp + pc + 1 + (j >> 1));
                 const uint32_t cidx = (j & 1u) ? rec.z : rec.x, slot = (j & 1u) ? rec.w : rec.y;
                 const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cidx), __ldg(consts + 2 * (uint64_t)cidx + 1));
-                const Fr x = unpack(slots[(slot * 2) * NT + tid], slots[(slot * 2 + 1) * NT + tid]);
-                fr::wide_mac(T, c, x);
+                Fr x[W];
+#pragma unroll
+                for (int k = 0; k < W; k++) x[k] = unpack(slots[(slot * 2) * NS + tk[k]], slots[(slot * 2 + 1) * NS + tk[k]]);
+#pragma unroll
+                for (int k = 0; k < W; k++) fr::wide_mac(T[k], c, x[k]);
             }
-            r = fr::wide_reduce(T, n);
-            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid));
+#pragma unroll
+            for (int k = 0; k < W; k++) r[k] = fr::wide_reduce(T[k], n);
+            if (flags & tape::F_ADDEND) {
+#pragma unroll
+                for (int k = 0; k < W; k++) r[k] = fr::add(r[k], tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]));
+            }
             pc += (n + 1) >> 1;
             raw = __ldg(tp + min(pc + 1, n_ins - 1));
         } else if (op == tape::T_SEL) {
-            const Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
-            const bool t = !fr::is_zero(a);
-            // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
-            const bool isc = t ? (flags & 2u) : (flags & 4u);
-            const uint32_t idx = t ? cur.z : cur.w;
-            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-            if (t || !(flags & tape::F_CZERO)) {
-                if (isc) { lo = __ldg(consts + 2 * (uint64_t)idx); hi = __ldg(consts + 2 * (uint64_t)idx + 1); }
-                else { lo = slots[(idx * 2) * NT + tid]; hi = slots[(idx * 2 + 1) * NT + tid]; }
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const Fr a = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
+                const bool t = !fr::is_zero(a);
+                // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
+                const bool isc = t ? (flags & 2u) : (flags & 4u);
+                const uint32_t idx = t ? cur.z : cur.w;
+                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+                if (t || !(flags & tape::F_CZERO)) {
+                    if (isc) { lo = __ldg(consts + 2 * (uint64_t)idx); hi = __ldg(consts + 2 * (uint64_t)idx + 1); }
+                    else { lo = slots[(idx * 2) * NS + tk[k]]; hi = slots[(idx * 2 + 1) * NS + tk[k]]; }
+                }
+                r[k] = unpack(lo, hi);
             }
-            r = unpack(lo, hi);
         } else if (op == tape::T_BITC) {
             // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
             const uint32_t limb = cur.z >> 5;
-            const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * NT + tid) << 2) + (limb & 3u)];
-            r = mont_bool((word >> (cur.z & 31u)) & 1u);
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * NS + tk[k]) << 2) + (limb & 3u)];
+                r[k] = mont_bool((word >> (cur.z & 31u)) & 1u);
+            }
         } else if (op == tape::T_EQ || op == tape::T_NEQ || op == tape::T_EQZ || op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
-            const Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
-            bool e;
-            if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = fr::is_zero(a);
-            else e = fr::equal(a, tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid));
+            bool e[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const Fr a = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
+                if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e[k] = fr::is_zero(a);
+                else e[k] = fr::equal(a, tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]));
+            }
             if (op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
-                if (!e && status == 0) status = cur.w;
+#pragma unroll
+                for (int k = 0; k < W; k++)
+                    if (!e[k] && status[k] == 0) status[k] = cur.w;
                 continue;
             }
-            r = mont_bool(op == tape::T_NEQ ? !e : e);
+#pragma unroll
+            for (int k = 0; k < W; k++) r[k] = mont_bool(op == tape::T_NEQ ? !e[k] : e[k]);
         } else if (op == tape::T_LD) {
-            const uint4 *src = wbase + ((uint64_t)cur.w * 2) * bstride;
-            slots[(dst * 2) * NT + tid] = src[0];
-            slots[(dst * 2 + 1) * NT + tid] = src[bstride];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const uint4 *src = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                slots[(dst * 2) * NS + tk[k]] = src[0];
+                slots[(dst * 2 + 1) * NS + tk[k]] = src[bstride];
+            }
             continue;
         } else if (op == tape::T_ST || op == tape::T_STC) {
-            uint4 lo, hi;
-            if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
-            else { lo = slots[(cur.y * 2) * NT + tid]; hi = slots[(cur.y * 2 + 1) * NT + tid]; }
-            if (active) {
-                uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
-                d[0] = lo;
-                d[bstride] = hi;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                uint4 lo, hi;
+                if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
+                else { lo = slots[(cur.y * 2) * NS + tk[k]]; hi = slots[(cur.y * 2 + 1) * NS + tk[k]]; }
+                if (active[k]) {
+                    uint4 *d = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                    d[0] = lo;
+                    d[bstride] = hi;
+                }
             }
             continue;
         } else {
-            status = tape_slow_op<NT>(cur, slots, consts, p.inputs, p.n_inputs, w, status);
-            if (flags & tape::F_STORE) {
-                if (active) {
-                    uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
-                    d[0] = slots[(dst * 2) * NT + tid];
-                    d[bstride] = slots[(dst * 2 + 1) * NT + tid];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                status[k] = tape_slow_op<NS>(cur, slots, consts, p.inputs, p.n_inputs, w[k], status[k], tk[k]);
+                if ((flags & tape::F_STORE) && active[k]) {
+                    uint4 *d = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                    d[0] = slots[(dst * 2) * NS + tk[k]];
+                    d[bstride] = slots[(dst * 2 + 1) * NS + tk[k]];
                 }
             }
             continue;
         }
-        uint4 lo, hi;
-        pack(r, lo, hi);
-        slots[(dst * 2) * NT + tid] = lo;
-        slots[(dst * 2 + 1) * NT + tid] = hi;
-        if ((flags & tape::F_STORE) && active) {
-            uint4 *d = wbase + ((uint64_t)cur.w * 2) * bstride;
-            d[0] = lo;
-            d[bstride] = hi;
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            uint4 lo, hi;
+            pack(r[k], lo, hi);
+            slots[(dst * 2) * NS + tk[k]] = lo;
+            slots[(dst * 2 + 1) * NS + tk[k]] = hi;
+            if ((flags & tape::F_STORE) && active[k]) {
+                uint4 *d = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                d[0] = lo;
+                d[bstride] = hi;
+            }
         }
     }
-    if (active && p.status) p.status[w] = status;
+#pragma unroll
+    for (int k = 0; k < W; k++)
+        if (active[k] && p.status) p.status[w[k]] = status[k];
 }
 
 // ---- value store (Montgomery SoA) -> .wtns rows (canonical AoS: B x n_wires x 32 B) ----------------
@@ -567,6 +623,7 @@ __global__ void __launch_bounds__(128) mulbench_kernel(uint4 *out, uint32_t iter
     z.v[1] ^= blockIdx.x;
     for (uint32_t i = 0; i < iters; i++) {
         if (VARIANT == 0) { x = fr::mont_mul_portable(x, y); z = fr::mont_mul_portable(z, y); }
+        else if (VARIANT == 2) { x = fr::mont_mul_wide(x, y); x = fr::mont_mul_wide(x, z); }   // ONE dependent chain per thread
         else { x = fr::mont_mul_wide(x, y); z = fr::mont_mul_wide(z, y); }
     }
     Fr r = fr::add(x, z);

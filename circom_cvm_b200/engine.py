@@ -33,7 +33,7 @@ EXPORTS = [
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
     "cvmgpu_witness_import_dev",
-    "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak", "cvmgpu_mul_peak",
+    "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak", "cvmgpu_mul_peak", "cvmgpu_set_tape_mode",
 ]
 
 
@@ -270,6 +270,11 @@ class R1cs:
 
     def check_dev(self, d_store, B, bstride, d_first_bad, stream=0):
         _check(lib().cvmgpu_r1cs_check_dev(self._h, _ptr(d_store), B, bstride, _ptr(d_first_bad), stream))
+
+
+def set_tape_mode(mode):
+    """0 = automatic, 1 / 2 = witnesses per thread of the tape kernel (experiments)"""
+    lib().cvmgpu_set_tape_mode(int(mode))
 
 
 def fr_host_op(op, a, b=0):

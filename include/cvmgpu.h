@@ -88,6 +88,8 @@ typedef struct {
 const char *cvmgpu_last_error(void);
 int cvmgpu_device_count(void);
 int cvmgpu_set_device(int device);
+/* tuning knob for experiments: witnesses per thread of the tape kernel (0 = automatic, 1, 2) */
+int cvmgpu_set_tape_mode(int mode);
 
 /* ---- program ---------------------------------------------------------------------------------- */
 /* Parse + trace-compile a .cvm file.  n_slots = 0 picks the default.  Works without a GPU. */

@@ -91,6 +91,29 @@ def test_witness_batch_matches_oracle(E, name, slots):
             assert g == e
 
 
+@pytest.mark.parametrize("name", ["poseidon2", "opszoo", "babyadd4", "num2bits8", "lessthan8"])
+def test_two_witnesses_per_thread_mode(E, name):
+    """The large-batch variant of the tape kernel (two witnesses per thread) on ragged batches: same results."""
+    art = circuit(name)
+    rng = random.Random(31)
+    rows = list(CASES[name])
+    if name not in ("num2bits8", "lessthan8"):
+        rows += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(301)]
+    else:
+        rows = rows * 67
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    E.set_tape_mode(2)
+    try:
+        wt, st = wc.calculate(rows)
+    finally:
+        E.set_tape_mode(0)
+    exp_w, exp_st = oracle_batch(art, rows)
+    assert list(st) == exp_st
+    for g, e, s_ in zip(E.le_to_ints(wt), exp_w, exp_st):
+        if s_ == 0:
+            assert g == e
+
+
 def test_empty_batch(E):
     wc = E.WitnessCalculator(cvm_text=circuit("multiplier2").cvm)
     wt, st = wc.calculate(np.zeros((0, 2, 32), dtype=np.uint8))
