@@ -68,7 +68,7 @@ struct cvmgpu_program {
 struct cvmgpu_r1cs {
     r1cs::File file;
     int device = -1;
-    DevBuf d_ptr, d_split, d_terms, d_coefs, d_cmag, d_store, d_wtns, d_bad;
+    DevBuf d_hdr, d_terms, d_coefs, d_cmag, d_store, d_wtns, d_bad;
 };
 
 extern "C" const char *cvmgpu_last_error(void) { return g_err.c_str(); }
@@ -441,7 +441,7 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
 
 extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
     if (!r) return;
-    r->d_ptr.release(); r->d_split.release(); r->d_terms.release(); r->d_coefs.release(); r->d_cmag.release();
+    r->d_hdr.release(); r->d_terms.release(); r->d_coefs.release(); r->d_cmag.release();
     r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
     delete r;
 }
@@ -449,23 +449,30 @@ extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
 static int upload_r1cs(cvmgpu_r1cs *r) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (r->device == dev && r->d_ptr.p) return CVMGPU_OK;
+    if (r->device == dev && r->d_hdr.p) return CVMGPU_OK;
     if (r->device != dev) {
-        r->d_ptr = DevBuf(); r->d_split = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf(); r->d_cmag = DevBuf();
+        r->d_hdr = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf(); r->d_cmag = DevBuf();
         r->d_store = DevBuf(); r->d_wtns = DevBuf(); r->d_bad = DevBuf();
     }
     const r1cs::File &f = r->file;
     std::vector<fr::Fr> cm;
     cm.reserve(f.coefs.size());
     for (const fr::Fr &c : f.coefs) cm.push_back(fr::to_mont(c));
-    if (int rc = r->d_ptr.ensure(std::max<size_t>(16, f.ptr.size() * 4))) return rc;
-    if (int rc = r->d_split.ensure(std::max<size_t>(16, f.split.size() * 4))) return rc;
+    std::vector<uint32_t> hdr(4 * f.ptr.size(), 0);
+    for (size_t j = 0; j < f.ptr.size(); j++) {
+        hdr[4 * j] = f.ptr[j];
+        if (j + 1 < f.ptr.size()) {
+            hdr[4 * j + 1] = f.split[3 * j];
+            hdr[4 * j + 2] = f.split[3 * j + 1];
+            hdr[4 * j + 3] = f.split[3 * j + 2];
+        }
+    }
+    if (int rc = r->d_hdr.ensure(hdr.size() * 4)) return rc;
     if (int rc = r->d_terms.ensure(std::max<size_t>(16, f.terms.size() * 8))) return rc;
     if (int rc = r->d_coefs.ensure(cm.size() * 32)) return rc;
     if (int rc = r->d_cmag.ensure(f.cmag.size() * 4)) return rc;
     CUDA_TRY(cudaMemcpy(r->d_cmag.p, f.cmag.data(), f.cmag.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(r->d_ptr.p, f.ptr.data(), f.ptr.size() * 4, cudaMemcpyHostToDevice));
-    if (!f.split.empty()) CUDA_TRY(cudaMemcpy(r->d_split.p, f.split.data(), f.split.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->d_hdr.p, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
     if (!f.terms.empty()) CUDA_TRY(cudaMemcpy(r->d_terms.p, f.terms.data(), f.terms.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r->d_coefs.p, cm.data(), cm.size() * 32, cudaMemcpyHostToDevice));
     r->device = dev;
@@ -491,8 +498,7 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
         chunks = (r->file.n_constraints + per - 1) / per;
     }
     kern::R1csParams rp;
-    rp.ptr = (const uint32_t *)r->d_ptr.p;
-    rp.split = (const uint32_t *)r->d_split.p;
+    rp.hdr = (const uint4 *)r->d_hdr.p;
     rp.terms = (const uint2 *)r->d_terms.p;
     rp.coefs = (const uint4 *)r->d_coefs.p;
     rp.cmag = (const uint32_t *)r->d_cmag.p;

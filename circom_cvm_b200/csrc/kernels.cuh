@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(256) import_kernel(const uint4 *in, uint64_t B
 // (uniform, broadcast loads); witness values are read from the SoA store (coalesced 128-bit loads).
 // Coefficient index 0 is +1 and 1 is -1: those terms are one add/sub; others cost one Montgomery product.
 struct R1csParams {
-    const uint32_t *ptr;        // 3*n_cons+1
-    const uint32_t *split;      // 3 per linear combination: ends of the +-1 / small positive / small negative classes
+    const uint4 *hdr;           // 3*n_cons+1 linear-combination headers {begin, end of +-1, of small +, of small -}; the end of
+                                // an LC is the begin of the next one (the last header only carries the total)
     const uint32_t *cmag;       // per coefficient: 32-bit magnitude of a small coefficient
     const uint2 *terms;         // (wire, coef index)
     const uint4 *coefs;         // Montgomery, 2 x uint4 each
@@ -409,41 +409,47 @@ struct TermStream {
     const uint4 *wbase;
     uint64_t bstride;
     uint4 *ring;            // [R1CS_STAGES][2][R1CS_NT]
-    uint32_t t_issue, t_end;
-
-    __device__ __forceinline__ void issue() {
-        if (t_issue < t_end) {
-            const uint2 term = __ldg(terms + t_issue);
+    uint32_t t_end;
+    // the stream is position-determined: term t's value is requested R1CS_STAGES takes before it is consumed
+    __device__ __forceinline__ void issue(uint32_t t) const {
+        if (t < t_end) {
+            const uint2 term = __ldg(terms + t);
             const uint4 *src = wbase + ((uint64_t)term.x * 2) * bstride;
-            uint4 *dst = ring + (t_issue % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
+            uint4 *dst = ring + (t % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
             const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + R1CS_NT * 16), "l"(src + bstride) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        t_issue++;
     }
-    __device__ __forceinline__ void start(uint32_t t_begin) {
-        t_issue = t_begin;
+    __device__ __forceinline__ void start(uint32_t t_begin) const {
 #pragma unroll
-        for (int k = 0; k < R1CS_STAGES; k++) issue();
+        for (int k = 0; k < R1CS_STAGES; k++) issue(t_begin + k);
     }
     // value of term t (terms are consumed strictly in order); refills the stage it frees
-    __device__ __forceinline__ Fr take(uint32_t t) {
+    __device__ __forceinline__ Fr take(uint32_t t) const {
         asm volatile("cp.async.wait_group %0;" ::"n"(R1CS_STAGES - 1) : "memory");
         const uint4 *s = ring + (t % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
         const Fr v = unpack(s[0], s[R1CS_NT]);
-        issue();
+        issue(t + R1CS_STAGES);
         return v;
     }
 };
 
-__device__ __forceinline__ Fr lc_eval(const R1csParams &p, TermStream &ts, uint32_t beg, uint32_t e0, uint32_t e1,
-                                      uint32_t e2, uint32_t end) {
+// out of line: called up to three times per constraint (A, B, C in CSR order); hdr = {begin, e0, e1, e2}
+__device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const uint32_t *cmag, const uint4 *wbase,
+                                   uint64_t bstride, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
+    TermStream ts;
+    ts.terms = terms;
+    ts.wbase = wbase;
+    ts.bstride = bstride;
+    ts.ring = ring;
+    ts.t_end = t_end;
+    const uint32_t e0 = hdr.y, e1 = hdr.z, e2 = hdr.w;
     Fr acc = fr::zero();
-    uint32_t t = beg;
+    uint32_t t = hdr.x;
     for (; t < e0; t++) {
-        const uint32_t neg = __ldg(p.terms + t).y;
+        const uint32_t neg = __ldg(terms + t).y;
         const Fr v = ts.take(t);
         acc = neg ? fr::sub(acc, v) : fr::add(acc, v);
     }
@@ -454,9 +460,9 @@ __device__ __forceinline__ Fr lc_eval(const R1csParams &p, TermStream &ts, uint3
             fr::Small X;
             fr::small_zero(X);
             for (; t < stop; t++) {
-                const uint32_t coef = __ldg(p.terms + t).y;
+                const uint32_t coef = __ldg(terms + t).y;
                 const Fr v = ts.take(t);
-                fr::small_mac(X, __ldg(p.cmag + coef), v);
+                fr::small_mac(X, __ldg(cmag + coef), v);
             }
             const Fr sres = fr::small_reduce(X);
             acc = neg ? fr::sub(acc, sres) : fr::add(acc, sres);
@@ -467,12 +473,30 @@ __device__ __forceinline__ Fr lc_eval(const R1csParams &p, TermStream &ts, uint3
         fr::Wide T;
         fr::wide_zero(T);
         for (uint32_t k = 0; k < n; k++, t++) {
-            const uint32_t coef = __ldg(p.terms + t).y;
-            const Fr c = unpack(__ldg(p.coefs + 2 * (uint64_t)coef), __ldg(p.coefs + 2 * (uint64_t)coef + 1));
+            const uint32_t coef = __ldg(terms + t).y;
+            const Fr c = unpack(__ldg(coefs + 2 * (uint64_t)coef), __ldg(coefs + 2 * (uint64_t)coef + 1));
             const Fr v = ts.take(t);
             fr::wide_mac(T, c, v);
         }
         acc = fr::add(acc, fr::wide_reduce(T, n));
+    }
+    return acc;
+}
+
+// linear combinations made of +-1 terms only (the common case outside hash-heavy circuits) stay inline
+__device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
+    if (hdr.y != end) return lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hdr, end);
+    TermStream ts;
+    ts.terms = p.terms;
+    ts.wbase = wbase;
+    ts.bstride = p.bstride;
+    ts.ring = ring;
+    ts.t_end = t_end;
+    Fr acc = fr::zero();
+    for (uint32_t t = hdr.x; t < end; t++) {
+        const uint32_t neg = __ldg(p.terms + t).y;
+        const Fr v = ts.take(t);
+        acc = neg ? fr::sub(acc, v) : fr::add(acc, v);
     }
     return acc;
 }
@@ -484,28 +508,36 @@ __global__ void __launch_bounds__(R1CS_NT, 4) r1cs_kernel(R1csParams p) {
     if (!active) w = p.B - 1;
     const uint32_t c0 = blockIdx.y * p.cons_per_chunk;
     const uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
-    TermStream ts;
-    ts.terms = p.terms;
-    ts.wbase = p.store + w;
-    ts.bstride = p.bstride;
-    ts.ring = ring;
-    ts.t_end = __ldg(p.ptr + 3 * c1);
-    ts.start(__ldg(p.ptr + 3 * c0));
+    const uint4 *wbase = p.store + w;
+    const uint32_t t_end = __ldg(&p.hdr[3 * c1].x);
+    {
+        TermStream ts;
+        ts.terms = p.terms;
+        ts.wbase = wbase;
+        ts.bstride = p.bstride;
+        ts.ring = ring;
+        ts.t_end = t_end;
+        ts.start(__ldg(&p.hdr[3 * c0].x));
+    }
     uint32_t bad = 0xffffffffu;
+    uint4 hA = __ldg(p.hdr + 3 * c0);
     for (uint32_t c = c0; c < c1; c++) {
-        Fr sa = fr::zero(), sb = fr::zero(), sc = fr::zero();
-#pragma unroll 1
-        for (uint32_t k = 0; k < 3; k++) {   // A, B, C in CSR order (one inlined copy of lc_eval)
-            const uint32_t j = 3 * c + k;
-            const Fr v = lc_eval(p, ts, __ldg(p.ptr + j), __ldg(p.split + 3 * j), __ldg(p.split + 3 * j + 1),
-                                 __ldg(p.split + 3 * j + 2), __ldg(p.ptr + j + 1));
-            if (k == 0) sa = v;
-            else if (k == 1) sb = v;
-            else sc = v;
+        // headers of A, B, C and of the next constraint's A (its begin is the end of C)
+        const uint4 hB = __ldg(p.hdr + 3 * c + 1), hC = __ldg(p.hdr + 3 * c + 2), hN = __ldg(p.hdr + 3 * c + 3);
+        Fr prod = fr::zero();
+        if (hA.x != hB.x && hB.x != hC.x) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
+            const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            const Fr sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
+            prod = fr::mont_mul(sa, sb);
+        } else {
+            // the terms of a lone A or B still occupy the stream: consume them
+            if (hA.x != hB.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hA, hB.x);
+            if (hB.x != hC.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hB, hC.x);
         }
-        // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054): sa or sb is 0 then
-        const Fr prod = (fr::is_zero(sa) || fr::is_zero(sb)) ? fr::zero() : fr::mont_mul(sa, sb);
+        Fr sc = fr::zero();
+        if (hC.x != hN.x) sc = lc_any(p, wbase, ring, t_end, hC, hN.x);
         if (bad == 0xffffffffu && !fr::equal(prod, sc)) bad = c;
+        hA = hN;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (active && bad != 0xffffffffu) atomicMin(p.first_bad + w, bad);
