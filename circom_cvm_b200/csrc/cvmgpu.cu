@@ -185,6 +185,7 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_dot = p->tape.stats.n_dot;
     info->tape_dot_terms = p->tape.stats.n_dot_terms;
     info->tape_macs = p->tape.stats.macs;
+    info->tape_ld_streamed = p->tape.stats.n_ld_streamed;
     return CVMGPU_OK;
 }
 
@@ -209,6 +210,11 @@ extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
     delete p;
 }
 
+// dynamic shared memory per witness: the slots, plus the reload ring when the tape reloads anything
+static size_t tape_smem_per_witness(const cvmgpu_program *p) {
+    return ((size_t)p->tape.n_slots + (p->tape.stats.n_ld ? tape::LD_RING : 0)) * 2 * sizeof(uint4);
+}
+
 static int upload_program(cvmgpu_program *p) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -227,7 +233,7 @@ static int upload_program(cvmgpu_program *p) {
         CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
     // dynamic shared memory = n_slots x 32 B per witness of the CTA; the slots want the whole carve-out of the SM
     // (more resident CTAs), nothing here relies on L1
-    const size_t per_w = (size_t)p->tape.n_slots * 2 * sizeof(uint4);
+    const size_t per_w = tape_smem_per_witness(p);
 #define CVM_SET_ATTR(NT, W)                                                                                              \
     CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_w * NT * W))); \
     CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -273,7 +279,8 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     // which lifts the bare multiplier from 45.7 to 62 G products/s) is kept behind cvmgpu_set_tape_mode(2): in the real
     // kernel it halves the resident warps (shared-memory slots) and measured 21.0 ms against 18.3 ms on Poseidon(2).
     const uint64_t want = (uint64_t)sms * 8;
-    const size_t per_w = (size_t)p->tape.n_slots * 2 * sizeof(uint4);
+    const size_t per_w = tape_smem_per_witness(p);
+    tp.ring_off = 0;   // set per launch below (depends on the witnesses per CTA)
     int mode = g_tape_mode;   // 0 auto, 1: W=1, 2: W=2 (cvmgpu_set_tape_mode, for experiments)
     const bool w2_ok = per_w * 128 * 2 <= 227 * 1024;
     const bool w2 = w2_ok && mode == 2;
@@ -281,11 +288,13 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     if (w2) {
         uint64_t grid = (B + 255) / 256;
         if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
+        tp.ring_off = p->tape.n_slots * 2 * 256;
         kern::tape_kernel<128, 2><<<(unsigned)grid, 128, per_w * 256, st>>>(tp);
     } else {
         const uint32_t nt = (B / 128 >= want) ? 128u : (B / 64 >= want) ? 64u : 32u;
         uint64_t grid = (B + nt - 1) / nt;
         if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
+        tp.ring_off = p->tape.n_slots * 2 * nt;
         if (nt == 128) kern::tape_kernel<128, 1><<<(unsigned)grid, 128, per_w * 128, st>>>(tp);
         else if (nt == 64) kern::tape_kernel<64, 1><<<(unsigned)grid, 64, per_w * 64, st>>>(tp);
         else kern::tape_kernel<32, 1><<<(unsigned)grid, 32, per_w * 32, st>>>(tp);

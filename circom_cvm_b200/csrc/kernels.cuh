@@ -43,6 +43,7 @@ struct TapeParams {
     uint32_t n_inputs;
     uint32_t *status;
     uint64_t B;
+    uint32_t ring_off;       // uint4 offset of the reload ring inside the dynamic shared memory (after the slots)
 };
 
 __device__ __forceinline__ Fr mont_bool(bool b) { return b ? fr::one_mont() : fr::zero(); }
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
     for (uint32_t pc = 0; pc < n_ins; pc++) {
         const uint4 cur = raw;
         raw = __ldg(tp + min(pc + 1, n_ins - 1));   // prefetch the next instruction (re-done after a DOT's records)
+        if ((pc & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + min(pc + 32, n_ins - 1)));   // tape lines ahead
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
@@ -256,12 +258,31 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
 #pragma unroll
             for (int k = 0; k < W; k++) r[k] = mont_bool(op == tape::T_NEQ ? !e[k] : e[k]);
         } else if (op == tape::T_LD) {
+            // reload stream (tape.hpp schedule_reloads): ring entry cur.z holds this value if F_RING; cur.y is the row
+            // to request now for the reload LD_RING reloads ahead.  Every reload commits exactly one cp.async group.
+            uint4 *ring = slots + p.ring_off + cur.z * 2 * NS;
+            if (flags & tape::F_RING) asm volatile("cp.async.wait_group %0;" ::"n"(tape::LD_RING - 1) : "memory");
 #pragma unroll
             for (int k = 0; k < W; k++) {
-                const uint4 *src = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
-                slots[(dst * 2) * NS + tk[k]] = src[0];
-                slots[(dst * 2 + 1) * NS + tk[k]] = src[bstride];
+                uint4 lo, hi;
+                if (flags & tape::F_RING) {
+                    lo = ring[tk[k]];
+                    hi = ring[NS + tk[k]];
+                } else {
+                    const uint4 *src = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                    lo = src[0];
+                    hi = src[bstride];
+                }
+                slots[(dst * 2) * NS + tk[k]] = lo;
+                slots[(dst * 2 + 1) * NS + tk[k]] = hi;
+                if (cur.y != tape::NO_ROW) {
+                    const uint4 *nxt = wbase[k] + ((uint64_t)cur.y * 2) * bstride;
+                    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ring + tk[k]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(nxt) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + NS * 16), "l"(nxt + bstride) : "memory");
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
             continue;
         } else if (op == tape::T_ST || op == tape::T_STC) {
 #pragma unroll
@@ -301,6 +322,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < W; k++)
         if (active[k] && p.status) p.status[w[k]] = status[k];

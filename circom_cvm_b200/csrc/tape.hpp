@@ -20,19 +20,23 @@ struct TapeIns {
     uint8_t flags;    // bit0: a is a constant index, bit1: b is constant, bit2: c is constant,
                       // bit3: the result is also stored to value-store row c (fused witness-wire store)
     uint16_t dst;     // slot
-    uint32_t a, b;    // slot or constant index; T_INPUT: a = input index; T_BITC: b = bit number
+    uint32_t a, b;    // slot or constant index; T_INPUT: a = input index; T_BITC: b = bit number;
+                      // T_LD: a = row to request now for the reload LD_RING reloads ahead (NO_ROW: none), b = ring entry
     uint32_t c;       // T_SEL: third operand; T_LD/T_ST/T_STC: value-store row; T_FAIL_IF/T_FAIL_NE: status;
                       // with flag bit3: value-store row
 };
 static const uint8_t F_STORE = 8;
 static const uint8_t F_CZERO = 16;
-static const uint8_t F_ADDEND = 32;  // T_DOT: field b holds an addend (slot, or constant index with bit1)   // T_SEL: the third operand is the constant 0 (field c is free for the fused store)
+static const uint8_t F_ADDEND = 32;
+static const uint8_t F_RING = 64;    // T_LD: the value was requested LD_RING reloads ago and sits in ring entry b
+static const uint32_t LD_RING = 4;   // reloads in flight per witness (32 B of shared memory each)
+static const uint32_t NO_ROW = 0xffffffffu;  // T_DOT: field b holds an addend (slot, or constant index with bit1)   // T_SEL: the third operand is the constant 0 (field c is free for the fused store)
 static_assert(sizeof(TapeIns) == 16, "tape instruction must be 16 bytes");
 
 struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
-    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0;
+    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0;
     uint32_t n_spill_rows = 0;
     // 32x32->64 multiply-accumulates the kernel executes per witness: 136 per Montgomery product (also the one that brings
     // an input to Montgomery form and the one after an inversion), 64 per DOT term + 72 per DOT reduction, and the
@@ -246,6 +250,41 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
     xp.witness_ref.reserve(tr.witness_ref.size());
     for (uint32_t r : tr.witness_ref) xp.witness_ref.push_back(mapref(r));
     return xp;
+}
+
+// ---- reload stream ---------------------------------------------------------------------------------------
+// The rows a tape reloads (T_LD) and their order are fixed, so the kernel streams them: the n-th reload's row is
+// requested (cp.async into a per-witness ring in shared memory) when reload n - LD_RING executes, and reload n finds
+// it there -- HBM latency leaves the dependence chain, which is what small batches (few resident warps) are bound by.
+// A reload is only streamed when the store that produced its row precedes the request point (spill rows are
+// recycled); the others load directly, as before.
+inline void schedule_reloads(Tape &t) {
+    std::vector<uint32_t> ld_pos, ld_store;
+    std::vector<uint32_t> last_store(t.n_rows, NO_ROW);
+    for (size_t pc = 0; pc < t.ins.size(); pc++) {
+        TapeIns &in = t.ins[pc];
+        if (in.op == T_DOT) {
+            if (in.flags & F_STORE) last_store[in.c] = (uint32_t)pc;
+            pc += (in.a + 1) / 2;
+            continue;
+        }
+        if (in.op == T_LD) {
+            in.a = NO_ROW;
+            in.b = (uint32_t)(ld_pos.size() % LD_RING);
+            ld_pos.push_back((uint32_t)pc);
+            ld_store.push_back(last_store[in.c]);
+        } else if (in.op == T_ST || in.op == T_STC || (in.flags & F_STORE)) {
+            if (in.op != T_FAIL_IF && in.op != T_FAIL_NE) last_store[in.c] = (uint32_t)pc;
+        }
+    }
+    for (size_t n = LD_RING; n < ld_pos.size(); n++) {
+        const uint32_t issue_at = ld_pos[n - LD_RING];
+        if (ld_store[n] != NO_ROW && ld_store[n] < issue_at) {
+            t.ins[ld_pos[n]].flags |= F_RING;
+            t.ins[issue_at].a = t.ins[ld_pos[n]].c;
+            t.stats.n_ld_streamed++;
+        }
+    }
 }
 
 inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
@@ -483,6 +522,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
     out.n_rows = out.n_wires + spill_rows;
     out.stats.n_spill_rows = spill_rows;
     out.stats.n_tape = out.ins.size();
+    schedule_reloads(out);
     out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +
                      72 * out.stats.n_dot + 1800 * (out.stats.n_inv + out.stats.n_div);
     return out;

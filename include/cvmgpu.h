@@ -72,6 +72,7 @@ typedef struct {
     uint64_t tape_dot;           /* fused dot products sum c_k*x_k (one Montgomery reduction each) */
     uint64_t tape_dot_terms;     /* their terms (64 multiply-accumulates each instead of 136) */
     uint64_t tape_macs;          /* 32x32->64 multiply-accumulates the tape kernel executes per witness */
+    uint64_t tape_ld_streamed;   /* reloads served by the cp.async ring (requested 8 reloads ahead) */
 } cvmgpu_program_info;
 
 typedef struct {

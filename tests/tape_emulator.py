@@ -10,6 +10,8 @@ from oracle import fr_model as M
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_INV, T_DOT,
  T_LD, T_ST, T_STC) = range(33)
 F_ADDEND = 32        # T_DOT: field b is an addend
+F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
+NO_ROW = 0xFFFFFFFF
 F_CZERO = 16         # T_SEL: third operand is the constant 0
 F_STORE = 8          # flag bit 3: the result is also stored to value-store row c
 R = 1 << 256
@@ -24,6 +26,7 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
     consts = [M.from_mont(c) for c in consts_mont]
     slots = [None] * n_slots
     rows = [None] * n_rows
+    ring = [None] * 8     # reload stream (entries b < LD_RING): a snapshot of the row at request time, so that a stale request is caught
     status = 0
     import numpy as np
     words = np.ascontiguousarray(tape).view(np.uint32).reshape(-1, 4)
@@ -64,7 +67,16 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
                 status = c
         elif op == T_LD:
             assert rows[c] is not None, "load of an unwritten row"
-            slots[dst] = rows[c]
+            if flags & F_RING:
+                assert ring[b] is not None and ring[b][0] == c, "ring entry does not hold the expected row"
+                slots[dst] = ring[b][1]
+            else:
+                slots[dst] = rows[c]
+            assert slots[dst] == rows[c], "streamed reload is stale"
+            ring[b] = None
+            if a != NO_ROW:
+                assert rows[a] is not None, "request of an unwritten row"
+                ring[b] = (a, rows[a])
         elif op == T_ST:
             assert slots[a] is not None
             rows[c] = slots[a]
