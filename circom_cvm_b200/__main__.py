@@ -1,0 +1,51 @@
+"""Process-level drop-in for the reference's generated witness calculator (common/main.cpp:334-371):
+
+    python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>]
+
+reads `<circuit>.dat` next to the program (as the reference reads `<argv0>.dat`), takes the same input.json and
+writes the same bytes to output.wtns -- computed on the GPU.  input.json may also be an array of input objects:
+the batch goes through one kernel launch and `<output>` gets one file per witness (`out.wtns`, `out.1.wtns`, ...).
+Exit code 1 with the reference's message on a failing assert (the reference aborts).
+"""
+import os
+import sys
+
+
+def main(argv):
+    args = [a for a in argv[1:] if not a.startswith("--")]
+    if len(args) != 3:
+        print("Usage: python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <file>]", file=sys.stderr)
+        return 1
+    from . import engine as E
+    from .inputs import InputError, InputMap, rows_from_json_text
+    cvm, jin, wout = args
+    r1cs_path = argv[argv.index("--r1cs") + 1] if "--r1cs" in argv else None
+    wc = E.WitnessCalculator(cvm_path=cvm)
+    try:
+        imap = InputMap.from_files(os.path.splitext(cvm)[0] + ".dat", wc)
+        with open(jin) as f:
+            rows = rows_from_json_text(imap, f.read())
+    except InputError as e:
+        print(str(e), file=sys.stderr)
+        return 1
+    if r1cs_path:
+        wt, st, bad = wc.calculate_checked(rows, E.R1cs(r1cs_path))
+    else:
+        wt, st = wc.calculate(rows)
+        bad = None
+    rc = 0
+    for k in range(len(rows)):
+        if st[k] != 0:
+            print("witness %d: failed assert / toInt / division (status %d)" % (k, int(st[k])), file=sys.stderr)
+            rc = 1
+            continue
+        if bad is not None and bad[k] != E.NO_BAD:
+            print("witness %d: constraint %d is not satisfied" % (k, int(bad[k])), file=sys.stderr)
+            rc = 1
+        base, ext = os.path.splitext(wout)
+        wc.write_wtns(wout if k == 0 else "%s.%d%s" % (base, k, ext), wt[k])
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv))

@@ -58,6 +58,7 @@ struct cvmgpu_program {
     tape::TraceStats tstats;
     tape::BatchInvStats binv;
     std::vector<fr::Fr> consts_mont;
+    std::vector<uint64_t> witness;   // %%witness: signal index of every witness wire
     uint64_t n_signals = 0;
     uint32_t n_inputs = 0, n_outputs = 0;
     // device copies (uploaded on first use on the current device)
@@ -119,6 +120,7 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
         }
         p->tstats = tr.stats;
         p->n_signals = (uint64_t)parser.prog.n_signals;
+        p->witness.assign(parser.prog.witness.begin(), parser.prog.witness.end());
         p->n_inputs = (uint32_t)tr.n_inputs;
         p->n_outputs = (uint32_t)tr.n_outputs;
         p->consts_mont.reserve(tr.consts.size());
@@ -196,6 +198,13 @@ extern "C" int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, ui
     if (n_ins) *n_ins = p->tape.ins.size();
     if (consts) *consts = p->consts_mont.data();
     if (n_consts) *n_consts = (uint32_t)p->consts_mont.size();
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (signals) *signals = p->witness.data();
+    if (n) *n = (uint32_t)p->witness.size();
     return CVMGPU_OK;
 }
 

@@ -28,7 +28,7 @@ NO_BAD = 0xFFFFFFFF
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_info_get", "cvmgpu_program_free",
-    "cvmgpu_program_tape",
+    "cvmgpu_program_tape", "cvmgpu_program_witness",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_dev", "cvmgpu_witness_export_dev", "cvmgpu_store_bytes",
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
@@ -81,6 +81,7 @@ def lib():
     L.cvmgpu_program_free.argtypes = [c_void_p]
     L.cvmgpu_program_free.restype = None
     L.cvmgpu_program_tape.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
+    L.cvmgpu_program_witness.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_witness_batch.argtypes = [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_checked.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
@@ -225,6 +226,16 @@ class WitnessCalculator:
     def write_wtns(self, path, witness_row):
         row = np.ascontiguousarray(witness_row, dtype=np.uint8)
         _check(lib().cvmgpu_wtns_write(os.fsencode(path), _ptr(row), self.n_wires))
+
+    def witness_signals(self):
+        """the %%witness list: signal index of every witness wire"""
+        sig, n = c_void_p(), c_uint32()
+        _check(lib().cvmgpu_program_witness(self._h, byref(sig), byref(n)))
+        return list(np.ctypeslib.as_array(ctypes.cast(sig, POINTER(c_uint64)), shape=(n.value,))) if n.value else []
+
+    @property
+    def n_outputs(self):
+        return int(self.info.n_outputs)
 
     def tape(self):
         """-> (numpy structured array of tape instructions, constants as python ints in Montgomery form)"""

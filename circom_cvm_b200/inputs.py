@@ -1,0 +1,166 @@
+"""Named inputs: `<circuit>.dat` + input JSON -> the positional input rows the C ABI takes.
+
+Mirrors what the reference's generated calculator does before `run(ctx)`:
+  * loadCircuit reads the input hash map from `<circuit>.dat`            (common/main.cpp:22-124, App. A.3)
+  * loadJson qualifies nested names (`a.b[i].c`), parses numbers          (common/main.cpp:144-284)
+  * setInputSignal looks the FNV-1a hash up with linear probing, checks sizes and double assignment
+                                                                           (common/calcwit.cpp:17-24, 51-97)
+Errors the reference reports with assert / runtime_error are raised as InputError with the same message text.
+This is host-side glue above the C ABI (no arithmetic happens here; values >= q are reduced on the device like
+Fr_str2element does).
+"""
+from __future__ import annotations
+
+import json
+import struct
+
+from .formats import fnv1a
+
+
+class InputError(ValueError):
+    pass
+
+
+class InputMap:
+    """The input hash map of a `.dat` file.  The file does not carry its own section sizes (the generated C++ does,
+    circuit.rs:463-497); the map size is the power of two >= 256 for which the witness-to-signal list that follows
+    matches the program's `%%witness` list."""
+
+    def __init__(self, dat_bytes: bytes, witness: list[int], input_start: int, n_inputs: int):
+        self.input_start, self.n_inputs = input_start, n_inputs
+        want = b"".join(struct.pack("<Q", s) for s in witness)
+        size = 256
+        table = None
+        while 24 * size + len(want) <= len(dat_bytes):
+            if dat_bytes[24 * size:24 * size + len(want)] == want:
+                table = [struct.unpack_from("<QQQ", dat_bytes, 24 * k) for k in range(size)]
+                break
+            size *= 2
+        if table is None:
+            raise InputError("the .dat file does not belong to this program (witness list not found)")
+        self.table = table
+
+    @classmethod
+    def from_files(cls, dat_path, wc):
+        """wc: engine.WitnessCalculator (for the witness list and the main-input range)"""
+        with open(dat_path, "rb") as f:
+            data = f.read()
+        return cls(data, wc.witness_signals(), 1 + wc.n_outputs, wc.n_inputs)
+
+    def position(self, h):          # calcwit.cpp:51-69
+        n = len(self.table)
+        pos = h % n
+        for _ in range(n):
+            eh, sid, _sz = self.table[pos]
+            if eh == h:
+                return pos
+            if sid == 0:
+                raise InputError("Signal not found")
+            pos = (pos + 1) % n
+        raise InputError("Signals not found")
+
+
+def _parse_number(val):             # json2FrElements, main.cpp:144-190 (value mod q is taken on the device)
+    if isinstance(val, bool):
+        raise InputError("Invalid JSON type")
+    if isinstance(val, str):
+        s, base = val, 10
+        p = val[:2]
+        if p in ("0b", "0B"):
+            s, base = val[2:], 2
+        elif p in ("0o", "0O"):
+            s, base = val[2:], 8
+        elif p in ("0x", "0X"):
+            s, base = val[2:], 16
+        digits = "0123456789abcdef"[:base] if base == 16 else "0123456789"[:base]
+        body = s[1:] if s[:1] == "-" and base == 10 else s
+        if not body or any(ch not in digits + (digits.upper() if base == 16 else "") for ch in body):
+            raise InputError("Invalid number in JSON input: %s" % val)
+        return int(s, base)
+    if isinstance(val, int):
+        return int(format(float(val), ".0f")) if abs(val) >= 1 << 53 else val      # the reference goes through a double
+    if isinstance(val, float):
+        return int(format(val, ".0f"))
+    raise InputError("Invalid JSON type")
+
+
+def _flatten(val, out):
+    if isinstance(val, list):
+        for v in val:
+            _flatten(v, out)
+    else:
+        out.append(_parse_number(val))
+
+
+def _elem_type(prefix, v):          # check_type, main.cpp:192-207
+    if not isinstance(v, list):     # nlohmann value_t: unsigned / negative integers and floats are distinct types
+        if isinstance(v, dict):
+            return "object"
+        if isinstance(v, bool):
+            return "boolean"
+        if isinstance(v, int):
+            return "number_unsigned" if v >= 0 else "number_integer"
+        return {float: "number_float", str: "string", type(None): "null"}.get(type(v), type(v).__name__)
+    if not v:
+        return "null"
+    t = _elem_type(prefix, v[0])
+    for x in v[1:]:
+        if _elem_type(prefix, x) != t:
+            raise InputError("Types are not the same in the the key %s" % prefix)
+    return t
+
+
+def qualify(prefix, v, out):        # qualify_input / qualify_input_list, main.cpp:209-239
+    if isinstance(v, list):
+        if v and _elem_type(prefix, v) == "object":
+            def walk(pfx, x):
+                if isinstance(x, list):
+                    for i, y in enumerate(x):
+                        walk("%s[%d]" % (pfx, i), y)
+                else:
+                    qualify(pfx, x, out)
+            walk(prefix, v)
+        else:
+            out[prefix] = v
+    elif isinstance(v, dict):
+        for k, x in v.items():
+            qualify(k if not prefix else prefix + "." + k, x, out)
+    else:
+        out[prefix] = v
+
+
+def row_from_json(imap: InputMap, doc) -> list[int]:
+    """One input object -> the main inputs in signal order (loadJson + setInputSignal)."""
+    flat = {}
+    qualify("", doc, flat)
+    row = [None] * imap.n_inputs
+    for name, val in flat.items():
+        h = fnv1a(name)
+        try:
+            pos = imap.position(h)
+        except InputError as e:
+            raise InputError("Error loading signal %s: %s" % (name, e)) from None
+        _eh, sid, size = imap.table[pos]
+        vals = []
+        _flatten(val, vals)
+        if len(vals) < size:
+            raise InputError("Error loading signal %s: Not enough values" % name)
+        if len(vals) > size:
+            raise InputError("Error loading signal %s: Too many values" % name)
+        for i, x in enumerate(vals):
+            k = sid + i - imap.input_start
+            if not 0 <= k < imap.n_inputs:
+                raise InputError("Error setting signal: %s" % name)
+            if row[k] is not None:
+                raise InputError("Error setting signal: %s\nSignal assigned twice: %d" % (name, sid + i))
+            row[k] = x
+    if any(x is None for x in row):
+        raise InputError("Not all inputs have been set. Only %d out of %d" % (sum(x is not None for x in row), imap.n_inputs))
+    return row
+
+
+def rows_from_json_text(imap: InputMap, text: str) -> list[list[int]]:
+    """A JSON object (one witness, the reference's input.json) or an array of objects (a batch)."""
+    doc = json.loads(text)
+    docs = doc if isinstance(doc, list) else [doc]
+    return [row_from_json(imap, d) for d in docs]

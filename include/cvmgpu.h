@@ -101,6 +101,9 @@ void cvmgpu_program_free(cvmgpu_program *p);
 /* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table
  * (32-byte LE Montgomery values).  For inspection and for host-side tests of the trace compiler. */
 int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_ins, const void **consts, uint32_t *n_consts);
+/* The program's %%witness list: signal index of every witness wire (= the witness2SignalList of the .dat,
+ * c_code_generator.rs:541-550; used to locate the input hash map of a .dat, circom_cvm_b200/inputs.py). */
+int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n);
 
 /* ---- witness generation ----------------------------------------------------------------------- */
 /* HOST buffers.  inputs: B x n_inputs x 32 B (main inputs in signal order, canonical LE; values >= q are

@@ -239,6 +239,44 @@ def test_eddsa_batch(E, tmp_path):
         assert g == I.compute_witness(prog, rows[i])
 
 
+@pytest.mark.parametrize("name,doc", [
+    ("multiplier2", {"a": "3", "b": "11"}),
+    ("poseidon2", {"inputs": ["1", "0x2"]}),
+    ("babyadd4", {"q": ["5299619240641551281634865583518297030282874472190772894086521144482721001553",
+                        "16950150798460657717958625567821834550301663161624707787222815936182638968203"],
+                  "p": ["995203441582195749578291179787384436505546430278305826713579947235728471134",
+                        "5472060717959818805561601436314318772137091100104008585924551046643952123905"]}),
+])
+def test_process_abi_drop_in(E, name, doc, tmp_path):
+    """`python -m circom_cvm_b200 <circuit>.cvm input.json out.wtns` against the reference's own
+    `./<circuit> input.json out.wtns` (oracle/_ref, when built): same input file, byte-identical output file."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from tools.circuitgen.build import write_artifact
+    art = circuit(name)
+    paths = write_artifact(art, str(tmp_path), with_cpp=True)          # .cvm + .dat side by side
+    jin = tmp_path / "input.json"
+    jin.write_text(json.dumps(doc))
+    out = tmp_path / "ours.wtns"
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, "-m", "circom_cvm_b200", paths["cvm"], str(jin), str(out)], check=True, env=env,
+                   cwd=ROOT, timeout=300)
+    ref = os.path.join(ROOT, "oracle", "_ref", name)
+    if os.path.exists(ref):
+        rout = tmp_path / "ref.wtns"
+        subprocess.run([ref, str(jin), str(rout)], check=True, timeout=60)
+        assert out.read_bytes() == rout.read_bytes()
+    else:
+        from circom_cvm_b200 import formats
+        from circom_cvm_b200.inputs import InputMap, row_from_json
+        with open(paths["dat"], "rb") as f:
+            row = row_from_json(InputMap(f.read(), art.witness, art.input_start, art.n_inputs), doc)
+        assert out.read_bytes() == formats.wtns_bytes(I.compute_witness(I.load(art.cvm), row))
+
+
 def test_sha256_batch(E, tmp_path):
     """Config 3 shape (bit-decomposition heavy): Sha256 over 64-bit messages, checked against hashlib for every
     witness, against the CVM oracle for one, and through the R1CS check."""

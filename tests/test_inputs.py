@@ -1,0 +1,72 @@
+"""Named inputs (circom_cvm_b200/inputs.py): the .dat input hash map + input.json handling of the reference's
+generated calculator (common/main.cpp:144-284, calcwit.cpp:51-97), checked on CPU against the fixture artifacts."""
+import json
+
+import pytest
+
+from circom_cvm_b200 import formats
+from circom_cvm_b200.inputs import InputError, InputMap, qualify, row_from_json, rows_from_json_text
+from conftest import circuit
+
+
+def imap_of(art):
+    consts = sorted(art.compiled.constants, key=art.compiled.constants.get)
+    dat = formats.dat_bytes(art.main_inputs, art.witness, consts)
+    return InputMap(dat, art.witness, art.input_start, art.n_inputs)
+
+
+def test_scalar_and_array_inputs_in_any_key_order():
+    m = imap_of(circuit("multiplier2"))
+    assert row_from_json(m, {"b": "11", "a": 3}) == [3, 11]
+    m = imap_of(circuit("babyadd4"))
+    assert row_from_json(m, {"q": ["0x10", "0b11"], "p": ["7", "0o17"]}) == [7, 15, 16, 3]
+    m = imap_of(circuit("poseidon2"))
+    assert row_from_json(m, {"inputs": [1, 2]}) == [1, 2]
+    with pytest.raises(InputError, match="Types are not the same"):       # check_type, main.cpp:192-207
+        row_from_json(m, {"inputs": [1, "2"]})
+
+
+def test_number_forms_follow_json2FrElements():
+    m = imap_of(circuit("multiplier2"))
+    q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    assert row_from_json(m, {"a": str(q + 5), "b": "0X1f"}) == [q + 5, 31]        # reduced mod q on the device
+    assert row_from_json(m, {"a": 2 ** 60, "b": 1.0}) == [int(format(float(2 ** 60), ".0f")), 1]   # numbers pass through a double
+    for bad in ("12a", "0b102", "", "0x", "1e5"):
+        with pytest.raises(InputError, match="Invalid number"):
+            row_from_json(m, {"a": bad, "b": "1"})
+    with pytest.raises(InputError, match="Invalid JSON type"):
+        row_from_json(m, {"a": None, "b": "1"})
+
+
+def test_errors_match_the_reference_messages():
+    m = imap_of(circuit("babyadd4"))
+    with pytest.raises(InputError, match="Not enough values"):
+        row_from_json(m, {"p": ["1"], "q": ["1", "2"]})
+    with pytest.raises(InputError, match="Too many values"):
+        row_from_json(m, {"p": ["1", "2", "3"], "q": ["1", "2"]})
+    with pytest.raises(InputError, match="Signal not found"):
+        row_from_json(m, {"p": ["1", "2"], "q": ["1", "2"], "zz": "1"})
+    with pytest.raises(InputError, match="Not all inputs have been set"):
+        row_from_json(m, {"p": ["1", "2"]})
+
+
+def test_nested_names_are_qualified_like_the_reference():
+    out = {}
+    qualify("", {"a": {"b": [{"c": 1}, {"c": [2, 3]}]}, "d": [[1, 2], [3, 4]]}, out)
+    assert out == {"a.b[0].c": 1, "a.b[1].c": [2, 3], "d": [[1, 2], [3, 4]]}
+
+
+def test_batches_and_foreign_dat():
+    art = circuit("multiplier2")
+    m = imap_of(art)
+    assert rows_from_json_text(m, json.dumps([{"a": "1", "b": "2"}, {"a": "3", "b": "4"}])) == [[1, 2], [3, 4]]
+    with pytest.raises(InputError, match="does not belong"):
+        InputMap(b"\x07" * 9000, art.witness, art.input_start, art.n_inputs)
+
+
+def test_program_witness_list_through_the_abi(cvmlib):
+    from circom_cvm_b200 import engine as E
+    art = circuit("babyadd4")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    assert [int(x) for x in wc.witness_signals()] == list(art.witness)
+    assert wc.n_outputs == art.n_outputs
