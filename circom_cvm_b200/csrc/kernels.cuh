@@ -550,7 +550,8 @@ __global__ void __launch_bounds__(R1CS_NT, 4) r1cs_kernel(R1csParams p) {
         if (hA.x != hB.x && hB.x != hC.x) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
             const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
             const Fr sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
-            prod = fr::mont_mul(sa, sb);
+            // a zero factor needs no product (whole warps skip it where a wire is structurally 0, e.g. padding bits)
+            if (!fr::is_zero(sa) && !fr::is_zero(sb)) prod = fr::mont_mul(sa, sb);
         } else {
             // the terms of a lone A or B still occupy the stream: consume them
             if (hA.x != hB.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hA, hB.x);
