@@ -284,9 +284,9 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     // One witness per thread, with smaller CTAs when the batch would leave SMs unevenly loaded (a 64 K batch is 512 CTAs
-    // of 128 for 148 SMs: 3.46 per SM).  The two-witnesses-per-thread variant (two independent carry chains per thread,
-    // which lifts the bare multiplier from 45.7 to 62 G products/s) is kept behind cvmgpu_set_tape_mode(2): in the real
-    // kernel it halves the resident warps (shared-memory slots) and measured 21.0 ms against 18.3 ms on Poseidon(2).
+    // of 128 for 148 SMs: 3.46 per SM).  The two-witnesses-per-thread variant is kept behind cvmgpu_set_tape_mode(2): the
+    // kernel is integer-issue bound, so the extra independent chain buys nothing and the halved number of resident warps
+    // costs (21.0 ms against 18.3 ms on Poseidon(2), profiles/r01_summary.md).
     const uint64_t want = (uint64_t)sms * 8;
     const size_t per_w = tape_smem_per_witness(p);
     tp.ring_off = 0;   // set per launch below (depends on the witnesses per CTA)

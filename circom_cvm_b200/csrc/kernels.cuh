@@ -140,10 +140,9 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
 // checks and the value-store moves; the result of a producing instruction can be written to its witness wire by
 // the same instruction (flag bit 3).
 //
-// W witnesses per thread (lanes tid + k*NT of a CTA that covers NT*W witnesses): the W copies of every operation
-// are independent, which gives the instruction scheduler two carry chains to interleave.  Measured on the bare
-// multiplier (cvmgpu_mul_peak): one dependent chain per thread tops out at 45.7 G products/s whatever the
-// occupancy, two independent chains reach 62 G products/s (profiles/r01_summary.md).
+// W witnesses per thread (lanes tid + k*NT of a CTA that covers NT*W witnesses): W = 2 was an experiment (two
+// independent carry chains per thread); the kernel is bound by integer instruction issue (one IMAD.WIDE or IADD3 per two
+// cycles and scheduler, profiles/r01_summary.md), so it does not help and W = 1 is what runs.
 template <int NT, int W>
 __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
     constexpr int NS = NT * W;   // witnesses per CTA = stride of one slot half in shared memory
