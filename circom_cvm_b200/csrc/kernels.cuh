@@ -89,9 +89,9 @@ __device__ __forceinline__ Fr slow_compute(uint32_t op, const Fr &a, const Fr &b
     Fr t = fr::zero();
     switch (op) {
         case tape::T_IDIV: case tape::T_MOD:
-            if (fr::is_zero(cb)) {
-                if (status == 0) status = tape::ST_DIVZERO;
-            } else {
+            // a zero divisor leaves 0; the failure itself is raised by the explicit check the tracer emits in front of
+            // the operation (tracer.hpp), which knows whether the statement executes at all
+            if (!fr::is_zero(cb)) {
                 Fr qt, rem;
                 fr::divmod(ca, cb, qt, rem);
                 t = (op == tape::T_MOD) ? rem : qt;

@@ -488,6 +488,21 @@ class Tracer {
                     if (in.op == OP_FF_MUL) stats.ref_mul++;
                     if (in.op == OP_FF_DIV) { stats.ref_mul++; stats.ref_div++; }
                     uint32_t a = field_ref(val(f, in.args.at(0))), b = field_ref(val(f, in.args.at(1)));
+                    if (in.op == OP_FF_IDIV || in.op == OP_FF_REM) {
+                        // GMP aborts on a zero divisor (generic/fr.cpp:2835-2875) whether or not the quotient is used, but
+                        // only when the statement executes: an explicit check, guarded by the enclosing data-dependent
+                        // conditions (both arms of an if-converted branch are traced), raises the per-witness flag
+                        if (!is_const(b) || fr::is_zero(cval(b))) {
+                            uint32_t z = emit(T_EQZ, b);
+                            if (!preds.empty()) z = emit(T_LAND, pred_conj(), z);
+                            emit(T_FAIL_IF, z, NO_REF, NO_REF, ST_DIVZERO);
+                        }
+                        if (is_const(b) && fr::is_zero(cval(b))) {
+                            set_reg(f, in.dst, ff_av(c_zero));
+                            pc++;
+                            break;
+                        }
+                    }
                     set_reg(f, in.dst, ref_av(emit(tape_op(in.op), a, b)));
                     pc++;
                     break;

@@ -1,0 +1,87 @@
+"""Random straight-line circuits over the whole operator set (test helper, used by the CPU and the GPU suites).
+
+A template with 4 inputs and 12 outputs; a seeded sequence of `var = op(x, y)` statements whose operands are earlier
+values, inputs or constants (small, bit-like, near q), data-dependent `if/else` blocks, shifts and bit extractions by
+constants and by values, divisions (also by zero), comparisons feeding products (the value-range typing of the trace
+compiler), sums of products by constants (the dot-product fusion) and a few `===` that random inputs may violate."""
+import random
+
+from tools.circuitgen.dsl import P
+
+BIN = ["add", "sub", "mul", "div", "idiv", "mod", "pow", "shl", "shr", "band", "bor", "bxor", "lt", "leq", "gt", "geq",
+       "eq", "neq", "land", "lor"]
+
+
+def make_circuit(seed, n_stmts=40):
+    rng = random.Random(seed)
+
+    def tmpl(T):
+        inp = T.input("in", (4,))
+        out = T.output("out", (12,))
+        vals = [inp[k] for k in range(4)]
+        vars_ = []
+
+        def const():
+            c = rng.choice([0, 1, 2, 3, 5, 31, 32, 200, 253, 254, 255, (1 << 64) - 1, 1 << 200, P - 1, P - 2, P - 200,
+                            (P - 1) // 2, (P + 1) // 2, rng.randrange(P)])
+            return c
+
+        def operand():
+            return rng.choice(vals) if rng.random() < 0.8 else const()
+
+        def expr():
+            r = rng.random()
+            x, y = operand(), operand()
+            if isinstance(x, int) and isinstance(y, int):
+                x = rng.choice(vals)
+            if r < 0.08:
+                return (x >> rng.randrange(0, 254)) & 1            # bit extraction
+            if r < 0.14:
+                c1, c2, c3 = rng.randrange(P), rng.randrange(P), rng.randrange(P)
+                return c1 * rng.choice(vals) + c2 * rng.choice(vals) + c3 * rng.choice(vals) + const()   # dot product
+            if r < 0.20:
+                return (x < y) * rng.choice(vals)                  # 0/1 factor
+            if r < 0.24:
+                return -x if not isinstance(x, int) else ~y if not isinstance(y, int) else x
+            if r < 0.28:
+                return ~x if not isinstance(x, int) else x
+            if r < 0.32:
+                return x.lnot() if not isinstance(x, int) else x
+            op = rng.choice(BIN)
+            if isinstance(x, int):
+                x, y = y, x                                        # keep the expression object on the left
+            if op == "pow":
+                y = rng.choice([0, 1, 2, 3, 5, 7, 300])
+            if op in ("shl", "shr") and rng.random() < 0.7:
+                y = rng.choice([0, 1, 7, 31, 32, 33, 100, 253, 254, 300, P - 3])
+            return x._b(op, y)
+
+        for k in range(n_stmts):
+            v = T.var("v%d" % k)
+            if rng.random() < 0.15 and len(vals) > 4:
+                cond = rng.choice(vals)
+                with T.if_(cond if rng.random() < 0.5 else cond.ne(rng.choice([0, 1]))):
+                    T.set(v, expr())
+                with T.else_():
+                    T.set(v, expr())
+            else:
+                T.set(v, expr())
+            vals.append(v)
+            vars_.append(v)
+        for k in range(12):
+            T.assign(out[k], rng.choice(vars_))
+        # constraints must be quadratic in SIGNALS (as in circom): the outputs.  Odd seeds get one that random inputs
+        # usually violate (status parity), all get a trivially true one
+        T.constrain(out[0] * 1, out[0])
+        if seed % 2 == 1:
+            T.constrain(out[rng.randrange(12)] * out[rng.randrange(12)], out[rng.randrange(12)])
+    tmpl.__name__ = "Fuzz%d" % seed
+    return tmpl
+
+
+def inputs_for(seed, n):
+    rng = random.Random(seed * 7919 + 1)
+    rows = []
+    for _ in range(n):
+        rows.append([rng.choice([0, 1, 2, P - 1, rng.randrange(P), rng.randrange(1 << 40), rng.randrange(256)]) for _ in range(4)])
+    return rows

@@ -97,9 +97,7 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             slots[dst] = 0 if y == 0 else M.div(x, y)
         elif op in (T_IDIV, T_MOD):
             x, y = operand(a, 1), operand(b, 2)
-            if y == 0:
-                if status == 0:
-                    status = 3
+            if y == 0:          # the failure is raised by the FAIL_IF the tracer puts in front of the operation
                 slots[dst] = 0
             else:
                 slots[dst] = x // y if op == T_IDIV else x % y

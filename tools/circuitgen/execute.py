@@ -33,7 +33,7 @@ def const_binop(op, a, b):
     if op == "add": return (a + b) % P
     if op == "sub": return (a - b) % P
     if op == "mul": return (a * b) % P
-    if op == "div": return (a * pow(b, -1, P)) % P
+    if op == "div": return (a * pow(b, -1, P)) % P if b else 0     # Fr_div(a, 0) = 0 in the reference
     if op == "idiv": return a // b
     if op == "mod": return a % b
     if op == "pow": return pow(a, b, P)
@@ -290,7 +290,7 @@ class _Executor:
             if e.op == "add": return v_add(a, b)
             if e.op == "sub": return v_add(a, b, -1)
             if e.op == "mul": return v_mul(a, b)
-            if e.op == "div" and isinstance(b, int): return v_mul(a, pow(b, -1, P))
+            if e.op == "div" and isinstance(b, int): return v_mul(a, pow(b, -1, P) if b else 0)
             return UNK
         if isinstance(e, Un):
             a = self.ev(e.a)
