@@ -94,6 +94,44 @@ def test_eddsa_verifier_matches_reference_runtime(tmp_path):
     assert e.value.status == I.ST_ASSERT
 
 
+@pytest.mark.parametrize("seed", [200, 201, 202, 203])
+def test_random_circuits_against_reference_runtime(seed, tmp_path):
+    """The oracle itself is pinned on random programs: a fuzz circuit (tests/fuzz_circuits.py: every operator, shifts,
+    divisions incl. by zero, data-dependent branches) is emitted in the WriteC shapes, linked against the reference's
+    own runtime + field arithmetic here, and run as `./circuit input.json out.wtns`; where the reference does not
+    abort, the CVM oracle must produce the same bytes, and where it aborts the oracle must raise."""
+    import shutil
+    from fuzz_circuits import inputs_for, make_circuit
+    from tools.circuitgen.build import compile_circuit, write_artifact
+    need = [os.path.join(REF, f) for f in ("fr.o", "calcwit.o", "main.o", "ref_harness.o")]
+    if not all(os.path.exists(p) for p in need) or shutil.which("g++") is None:
+        pytest.skip("reference runtime objects not built (oracle/build_ref.py + build_ref_circuits.py)")
+    art = compile_circuit(make_circuit(seed, n_stmts=30), (), name="fuzzref%d" % seed)
+    paths = write_artifact(art, str(tmp_path), with_cpp=True)
+    exe = str(tmp_path / art.name)
+    flags = ["-std=c++11", "-O1", "-w", "-I", os.path.join(REF, "src"), "-I", os.path.join(ROOT, "oracle", "gmp_shim"),
+             "-I", os.path.join(REF, "inc")]
+    subprocess.run(["g++", *flags, paths["cpp"], *need[3:], *need[:3], "/usr/lib/x86_64-linux-gnu/libgmp.so.10", "-o", exe],
+                   check=True, timeout=300)
+    prog = I.load(art.cvm)
+    agreed = aborted = 0
+    for k, values in enumerate(inputs_for(seed, 10)):
+        jin, wout = tmp_path / ("in%d.json" % k), tmp_path / ("out%d.wtns" % k)
+        jin.write_text(json.dumps(input_json(art, values)))
+        r = subprocess.run([exe, str(jin), str(wout)], capture_output=True, timeout=60)
+        try:
+            ours = formats.wtns_bytes(I.compute_witness(prog, values))
+        except I.WitnessError:
+            ours = None
+        if r.returncode == 0:
+            assert ours is not None and wout.read_bytes() == ours, (seed, values)
+            agreed += 1
+        else:
+            assert ours is None, (seed, values, r.stderr[-200:])
+            aborted += 1
+    assert agreed + aborted == 10
+
+
 def test_reference_runtime_aborts_where_we_flag(tmp_path):
     """A failing `===` aborts the reference process (assert); the oracle raises status ASSERT."""
     exe = ref_binary("num2bits8")
