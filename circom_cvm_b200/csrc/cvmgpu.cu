@@ -359,7 +359,9 @@ extern "C" int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, c
     size_t per_w = (size_t)p->tape.n_rows * 32 + in_row + (wtns_out ? out_row : 0) + 8;
     uint64_t fit = pick_chunk(B, 2 * per_w);
     if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
-    uint64_t chunk = std::min<uint64_t>(fit, 32768);
+    // chunks of 32 K witnesses keep the D2H of one chunk under the kernels of the next; without a witness download
+    // there is nothing to overlap and larger launches fill the GPU better
+    uint64_t chunk = std::min<uint64_t>(fit, wtns_out ? 32768 : 262144);
     if (B <= chunk) chunk = B;
     static thread_local PipeBufs pipe[2];
     static thread_local int pipe_dev = -1;
