@@ -335,6 +335,21 @@ def main():
     ms_tape = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(n_launch)) / args.steps
     ms_check = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(n_launch)) / args.steps
     n_fail = int((status != 0).sum()) + int((bad != -1).sum())
+    # the path's only exchange (north_star): the final gather of the per-witness flags to rank 0, outside the timed region
+    gather_ms = 0.0
+    if world > 1:
+        from circom_cvm_b200.sharding import gather_flags
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather_flags(status, world * B)                  # first call sets the communicator up
+        g0.record()
+        all_status = gather_flags(status, world * B)
+        all_bad = gather_flags(bad, world * B)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        if rank == 0:
+            assert all_status.numel() == world * B and all_bad.numel() == world * B
+            n_fail = int((all_status != 0).sum()) + int((all_bad != -1).sum())
     t = torch.tensor([ms_total, ms_tape, ms_check, float(n_fail)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -496,7 +511,8 @@ def main():
                    "batch_per_gpu": B, "witnesses_per_launch": CH,
                    "l2": "working set %.1f GB per launch >> 126 MB L2" % (wc.store_bytes(CH) / 1e9),
                    "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
-                   "n_slots": info["n_slots"], "tape_len": info["tape_len"], "failures": n_fail},
+                   "n_slots": info["n_slots"], "tape_len": info["tape_len"], "failures": n_fail,
+                   "flags_gather_ms": gather_ms},
         "kernels_ms": {"tape_kernel": ms_tape, "r1cs_kernel": ms_check},
         "witnesses_per_s_gen_only": world * B / (ms_tape * 1e-3),
         "constraints_per_s_check_only": world * B * rinfo["n_constraints"] / (ms_check * 1e-3),
