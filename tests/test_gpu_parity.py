@@ -313,3 +313,97 @@ def test_sha256_batch(E, tmp_path):
                 break
         assert bad2[b] == first, b
     assert bad2[2] == E.NO_BAD and bad2[0] != E.NO_BAD and bad2[1] != E.NO_BAD
+
+
+# ---- BASELINE.json sizes: properties that do not need an oracle run per witness ----------------------------------
+def _run_full(E, art, inputs_dev, B, tmp_path):
+    import torch
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    _write_r1cs(art, tmp_path / "full.r1cs")
+    r = E.R1cs(str(tmp_path / "full.r1cs"))
+    store = torch.empty(wc.store_bytes(B), dtype=torch.uint8, device="cuda")
+    status = torch.empty(B, dtype=torch.int32, device="cuda")
+    bad = torch.empty(B, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    wc.run_dev(inputs_dev, B, B, store, status, s)
+    r.check_dev(store, B, B, bad, s)
+    torch.cuda.synchronize()
+    return wc, r, store, status, bad
+
+
+def test_poseidon_at_baseline_size(E, tmp_path):
+    """Config 2 (Poseidon(2), 1 048 576 random inputs): no flag raised, every witness satisfies all 634 constraints (the
+    check is an independent evaluation of the .r1cs), sampled outputs equal the plain-integer Poseidon, a second run
+    writes the same store (determinism), and a corrupted store is caught by the check."""
+    import torch
+    from tools.circuitgen.circuits import poseidon
+    art = circuit("poseidon2")
+    B = 1 << 20
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0xC1C00001)
+    inp = torch.randint(0, 256, (B, 2, 32), dtype=torch.uint8, device="cuda", generator=g)
+    inp[:, :, 31] &= 0x1F
+    wc, r, store, status, bad = _run_full(E, art, inp, B, tmp_path)
+    assert int((status != 0).sum()) == 0 and int((bad != -1).sum()) == 0
+    sample = [0, 1, 31, 32, 4095]
+    idx = torch.tensor(sample, device="cuda")
+    sub_in = E.le_to_ints(inp[idx].cpu().numpy())
+    # export works on a contiguous prefix of the batch: check the sampled witnesses of the first 4 096
+    wt = torch.empty((1 << 12, wc.n_wires, 32), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    wc.export_dev(store, 1 << 12, B, wt, s)
+    torch.cuda.synchronize()
+    head = E.le_to_ints(wt[[0, 1, 31, 32, 4095]].cpu().numpy())
+    for k, b in enumerate([0, 1, 31, 32, 4095]):
+        assert head[k][1] == poseidon.poseidon_hash(sub_in[k])
+    checksum = store.view(torch.int64).sum().item()
+    status2 = torch.empty_like(status)
+    wc.run_dev(inp, B, B, store, status2, s)
+    torch.cuda.synchronize()
+    assert store.view(torch.int64).sum().item() == checksum
+    # flip one byte of one wire of witnesses 5 and B-1: exactly those are reported
+    view = store.view(torch.uint8)
+    for b in (5, B - 1):
+        off = ((3 * 2) * B + b) * 16          # row 3, low half, witness b (layout in csrc/kernels.cuh)
+        view[off] ^= 1
+    r.check_dev(store, B, B, bad, s)
+    torch.cuda.synchronize()
+    hit = torch.nonzero(bad != -1).flatten().tolist()
+    assert hit == [5, B - 1]
+
+
+def test_sha256_at_baseline_size(E, tmp_path):
+    """Config 3 (Sha256(512 bits), 65 536 random messages): no flag, all 68 640 constraints hold for every witness, and
+    the digest wires of sampled witnesses equal hashlib's."""
+    import hashlib
+    import torch
+    from tools.circuitgen.build import compile_circuit
+    from tools.circuitgen.circuits import sha256
+    art = compile_circuit(sha256.Sha256, (512,), name="sha256_512")
+    B = 1 << 16
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _total = torch.cuda.mem_get_info()
+    if free < 156e9:
+        pytest.skip("needs ~150 GB of free device memory (the 64 K x 68 529-wire value store)")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0xC1C00002)
+    bits = torch.randint(0, 2, (B, 512), dtype=torch.uint8, device="cuda", generator=g)
+    inp = torch.zeros((B, 512, 32), dtype=torch.uint8, device="cuda")
+    inp[:, :, 0] = bits
+    try:
+        wc, r, store, status, bad = _run_full(E, art, inp, B, tmp_path)
+    except torch.cuda.OutOfMemoryError:
+        pytest.skip("not enough free device memory for the 64 K batch")
+    assert int((status != 0).sum()) == 0 and int((bad != -1).sum()) == 0
+    wt = torch.empty((64, wc.n_wires, 32), dtype=torch.uint8, device="cuda")
+    wc.export_dev(store, 64, B, wt, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    digests = wt[:, 1:257, 0].cpu().numpy()            # 256 output bits, each a 0/1 field element
+    assert int(wt[:, 1:257, 1:].sum()) == 0
+    msgs = bits[:64].cpu().numpy()
+    for k in range(64):
+        m = bytes(int("".join(str(int(x)) for x in msgs[k, 8 * j:8 * j + 8]), 2) for j in range(64))
+        want = "".join(format(byte, "08b") for byte in hashlib.sha256(m).digest())
+        assert "".join(str(int(x)) for x in digests[k]) == want, k
