@@ -188,6 +188,7 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_dot_terms = p->tape.stats.n_dot_terms;
     info->tape_macs = p->tape.stats.macs;
     info->tape_ld_streamed = p->tape.stats.n_ld_streamed;
+    info->unrolled_iterations = p->tstats.unrolled_iterations;
     return CVMGPU_OK;
 }
 

@@ -43,7 +43,7 @@ enum TOp : uint8_t {
 static const uint32_t CONST_FLAG = 0x80000000u;
 static const uint32_t NO_REF = 0xffffffffu;
 
-enum Status : uint32_t { ST_OK = 0, ST_ASSERT = 1, ST_TOINT = 2, ST_DIVZERO = 3, ST_INPUT = 4 };
+enum Status : uint32_t { ST_OK = 0, ST_ASSERT = 1, ST_TOINT = 2, ST_DIVZERO = 3, ST_INPUT = 4, ST_LOOP = 5 };
 
 struct SOp {
     uint8_t op;
@@ -62,6 +62,7 @@ struct TraceStats {
     uint64_t ref_field_ops = 0;      // all ff.* executions of the reference program
     uint64_t folded = 0, cse_hits = 0;
     uint64_t dyn_branches = 0;
+    uint64_t unrolled_iterations = 0;   // iterations of data-dependent while loops traced under predicates
     uint64_t unset_signal_reads = 0;
 };
 
@@ -160,6 +161,12 @@ class Tracer {
     std::vector<uint32_t> preds;   // refs of enclosing data-dependent conditions (already "is true" predicates)
     uint32_t c_zero, c_one, c_rinv;
     int depth = 0;
+    std::vector<int> loop_stack;      // pc of the open `loop` instructions of the code being traced
+    int unroll_depth = 0;
+    int last_exit_pc = 0;
+  public:
+    int max_unroll = 260;             // iterations traced for a data-dependent while loop (254-bit scans fit)
+  private:
     static const int64_t SPR_BASE = (int64_t)1 << 40;
 
     // ---------------------------------------------------------------- constants / values
@@ -626,9 +633,38 @@ class Tracer {
                 }
                 case OP_ELSE: pc = in.m_end + 1; break;    // fell off the end of a then-branch
                 case OP_END: pc++; break;                  // end of if, or falling out of a loop
-                case OP_LOOP: pc++; break;
+                case OP_LOOP: {
+                    // run the loop as its own region so that data-dependent `continue`s know which loop they belong to
+                    loop_stack.push_back(pc);
+                    const int lend = in.m_end;
+                    bool r = run_loop(code, f, ci, pc, lend, ret);
+                    loop_stack.pop_back();
+                    if (r) return true;
+                    if (last_exit_pc == lend) stats.cvm_instructions++;   // fell onto the loop's `end` (a `break` jumps past it)
+                    pc = lend + 1;
+                    break;
+                }
                 case OP_CONTINUE:
-                    if (in.m_loop < range_begin) throw TraceError("continue under a data-dependent condition");
+                    if (in.m_loop < range_begin) {
+                        // `while (c) body` with a data-dependent c is `loop; c; if c; body; continue; end; end`
+                        // (loop_bucket.rs:97-120): this `continue` sits in the if-converted then-arm.  The next
+                        // iteration is traced right here, nested in the arm (its own condition becomes one more
+                        // predicate), up to max_unroll iterations; a witness that would need more raises ST_LOOP.
+                        // Only the plain while shape is handled: the loop must be the innermost open one.
+                        if (preds.empty() || loop_stack.empty() || loop_stack.back() != in.m_loop)
+                            throw TraceError("continue under a data-dependent condition");
+                        const int loop_end = code.ins[(size_t)in.m_loop].m_end;
+                        if (++unroll_depth > max_unroll) {
+                            emit(T_FAIL_IF, pred_conj(), NO_REF, NO_REF, ST_LOOP);
+                        } else {
+                            stats.unrolled_iterations++;
+                            if (run(code, f, ci, in.m_loop + 1, loop_end, in.m_loop + 1, ret))
+                                throw TraceError("return under a data-dependent condition");
+                        }
+                        unroll_depth--;
+                        pc = stop;   // nothing after a `continue` executes in this arm
+                        break;
+                    }
                     pc = in.m_loop + 1;
                     break;
                 case OP_BREAK: {
@@ -666,7 +702,16 @@ class Tracer {
                 default: throw TraceError("unhandled CVM instruction");
             }
         }
+        last_exit_pc = pc;
         return false;
+    }
+
+    // body of `loop` at lpc .. its `end` at lend: iterate while `continue` jumps back (static trip counts), leave on
+    // `break` or by falling onto the loop's `end`
+    bool run_loop(const cvm::Code &code, Frame &f, int ci, int lpc, int lend, const RetTarget *ret) {
+        // the body is executed by the ordinary interpreter loop: `continue` (static) sets pc = lpc + 1, `break` jumps
+        // past lend; both stay inside [lpc + 1, lend + 1)
+        return run(code, f, ci, lpc + 1, lend, lpc, ret);
     }
 
     void dynamic_if(const cvm::Code &code, Frame &f, int ci, int pc, int then_end, const cvm::Ins &in, uint32_t cond,

@@ -48,6 +48,7 @@ extern "C" {
 #define CVMGPU_ST_ASSERT 1   /* failed assert / `===`   (assert_bucket.rs:71-86) */
 #define CVMGPU_ST_TOINT 2    /* Fr_toInt overflow        (bn128/fr.cpp:165-167) */
 #define CVMGPU_ST_DIVZERO 3  /* `\` or `%` by zero       (GMP division by zero in the reference) */
+#define CVMGPU_ST_LOOP 5     /* a data-dependent while loop needed more iterations than were traced (260) */
 
 typedef struct cvmgpu_program cvmgpu_program;
 typedef struct cvmgpu_r1cs cvmgpu_r1cs;
@@ -72,7 +73,8 @@ typedef struct {
     uint64_t tape_dot;           /* fused dot products sum c_k*x_k (one Montgomery reduction each) */
     uint64_t tape_dot_terms;     /* their terms (64 multiply-accumulates each instead of 136) */
     uint64_t tape_macs;          /* 32x32->64 multiply-accumulates the tape kernel executes per witness */
-    uint64_t tape_ld_streamed;   /* reloads served by the cp.async ring (requested 8 reloads ahead) */
+    uint64_t tape_ld_streamed;   /* reloads served by the cp.async ring (requested 4 reloads ahead) */
+    uint64_t unrolled_iterations; /* iterations of data-dependent while loops traced under predicates */
 } cvmgpu_program_info;
 
 typedef struct {

@@ -20,6 +20,8 @@ def circuits():
     from tools.circuitgen.circuits import babyjub, basic, poseidon
     table = {
         "babyadd4": (babyjub.BabyAddChain, (4,)),
+        "nbits": (basic.NBits, ()),
+        "countdown": (basic.CountDown, ()),
         "multiplier2": (basic.Multiplier2, ()),
         "multiplier4": (basic.MultiplierN, (4,)),
         "num2bits8": (basic.Num2Bits, (8,)),

@@ -45,6 +45,8 @@ def test_device_mul_random_bulk(E):
 
 
 CASES = {
+    "nbits": [[0], [1], [255], [256], [1 << 253], [M.Q - 1]],
+    "countdown": [[0], [1], [17], [200]],
     "babyadd4": [[995203441582195749578291179787384436505546430278305826713579947235728471134, 5472060717959818805561601436314318772137091100104008585924551046643952123905, 5299619240641551281634865583518297030282874472190772894086521144482721001553, 16950150798460657717958625567821834550301663161624707787222815936182638968203], [0, 1, 0, 1], [3, 5, 7, 11]],
     "multiplier2": [[3, 11], [M.Q - 1, 5], [0, 0]],
     "multiplier4": [[2, 3, 4, 5]],
@@ -77,7 +79,7 @@ def test_witness_batch_matches_oracle(E, name, slots):
     art = circuit(name)
     rng = random.Random(3)
     rows = list(CASES[name])
-    if name not in ("num2bits8", "sum3cmp", "lessthan8"):
+    if name not in ("num2bits8", "sum3cmp", "lessthan8", "countdown"):
         rows += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(200)]
     else:
         rows = rows * 50                                   # ragged batch size, not a multiple of 128

@@ -10,6 +10,8 @@ from oracle import fr_model as M
 from tape_emulator import run_tape
 
 CASES = {
+    "nbits": [[0], [1], [255], [256], [1 << 253], [M.Q - 1]],
+    "countdown": [[0], [1], [17], [200]],
     "babyadd4": [[995203441582195749578291179787384436505546430278305826713579947235728471134, 5472060717959818805561601436314318772137091100104008585924551046643952123905, 5299619240641551281634865583518297030282874472190772894086521144482721001553, 16950150798460657717958625567821834550301663161624707787222815936182638968203], [0, 1, 0, 1], [3, 5, 7, 11]],
     "multiplier2": [[3, 11], [M.Q - 1, 5], [0, 0]],
     "multiplier4": [[2, 3, 4, 5], [M.Q - 1, M.Q - 2, 7, 0]],
@@ -41,7 +43,7 @@ def test_tape_matches_oracle(cvmlib, name, slots):
     tape, consts = wc.tape()
     rng = random.Random(7)
     cases = list(CASES[name])
-    if name not in ("num2bits8", "sum3cmp", "lessthan8"):
+    if name not in ("num2bits8", "sum3cmp", "lessthan8", "countdown"):
         cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
     for inp in cases:
         w, st = oracle(prog, inp)
@@ -89,8 +91,8 @@ def test_unsupported_programs_are_rejected_with_a_reason(cvmlib):
     from circom_cvm_b200 import engine as E
     q = "21888242871839275222246405745257275088548364400416034343698204186575808495617"
     head = "%%prime " + q + "\n%%signals 3\n%%start T_0\n%%witness 0 1 2\n%%template T_0 [ ff 0 ] [ ff 0 ] [2] [0]\n"
-    # data-dependent loop
-    text = head + "loop\nx_0 = get_signal i64.1\nif x_0\ncontinue\nend\nend\n"
+    # data-dependent `break` (a plain data-dependent `while` is unrolled under predicates instead, see the test above)
+    text = head + "loop\nx_0 = get_signal i64.1\nif x_0\nbreak\nend\ncontinue\nend\n"
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text=text)
     assert e.value.code == -3 and "data-dependent" in str(e.value)
@@ -99,6 +101,25 @@ def test_unsupported_programs_are_rejected_with_a_reason(cvmlib):
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text=text)
     assert e.value.code == -3
+
+
+def test_data_dependent_while_is_unrolled_under_predicates(cvmlib):
+    """A `while` whose trip count depends on a signal is traced iteration by iteration inside the if-converted arm
+    (tracer.hpp OP_CONTINUE), up to 260 iterations; a witness that needs more gets CVMGPU_ST_LOOP instead of a wrong
+    value (the reference would simply keep looping)."""
+    from circom_cvm_b200 import engine as E
+    art = circuit("countdown")
+    prog = I.load(art.cvm)
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    assert wc.info.unrolled_iterations == 260
+    tape, consts = wc.tape()
+    for n in (0, 3, 259, 260):
+        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, [n])
+        assert status == 0 and rows[:wc.n_wires] == I.compute_witness(prog, [n]), n
+        assert rows[1] == sum(k * k for k in range(n + 1))
+    for n in (261, 5000, M.Q - 1):
+        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, [n])
+        assert status == 5, n
 
 
 def test_eddsa_verifier_tape(cvmlib):

@@ -146,3 +146,30 @@ def Sum3Cmp(T):
     T.bind(b2n.pin("in"), inp)
     T.bind(n2b.pin("in"), b2n.pin("out"))
     T.bind(out, n2b.pin("out"))
+
+
+def NBits(T):
+    """Bit length by a `while` whose trip count depends on the input (circomlib-style `nbits`, here on a signal in
+    `<--` code): exercises the bounded predicated unrolling of the trace compiler."""
+    inp = T.input("in")
+    out = T.output("out")
+    n = T.var("n", init=0)
+    r = T.var("r", init=0)
+    T.set(n, inp)
+    with T.loop(n.ne(0)):
+        T.set(r, r + 1)
+        T.set(n, n >> 1)
+    T.assign(out, r)
+
+
+def CountDown(T):
+    """while (n != 0) n = n - 1 with a running sum: needs `in` iterations (only small inputs stay within the bound)."""
+    inp = T.input("in")
+    out = T.output("out")
+    n = T.var("n", init=0)
+    acc = T.var("acc", init=0)
+    T.set(n, inp)
+    with T.loop(n.ne(0)):
+        T.set(acc, acc + n * n)
+        T.set(n, n - 1)
+    T.assign(out, acc)

@@ -348,7 +348,12 @@ class _Executor:
             while True:
                 c = self.ev(st.cond)
                 if not isinstance(c, int):
-                    raise CircuitError("loop condition depends on signals in %s" % self.inst.name)
+                    # trip count unknown at compile time: legal in circom as long as the body only touches vars, whose
+                    # values are then unknown to the constraint system (execute.rs treats the block as "unknown")
+                    self.shadow += 1
+                    self.block(st.body)
+                    self.shadow -= 1
+                    break
                 if c == 0:
                     break
                 self.block(st.body)
