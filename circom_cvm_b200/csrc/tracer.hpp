@@ -149,6 +149,9 @@ class Tracer {
         Frame *frame;
         int64_t addr, size;
         size_t pred_depth;
+        // disjunction of the predicates under which a `return` has been traced so far (NO_REF: none): what follows a
+        // data-dependent return runs under its negation
+        mutable uint32_t returned = NO_REF;
     };
 
     const cvm::Program &prog;
@@ -482,6 +485,15 @@ class Tracer {
     // executes ins[pc, stop) of `code`; returns true when a `return` was executed
     bool run(const cvm::Code &code, Frame &f, int ci, int pc, int stop, int range_begin, const RetTarget *ret) {
         using namespace cvm;
+        uint32_t applied = ret ? ret->returned : NO_REF;   // the "already returned" predicate this range runs under
+        // after a nested construct: did a data-dependent `return` happen inside it?  Then the rest of this range (later
+        // iterations of an enclosing static loop included) is one more predicated region, under "not returned".
+        auto rest_if_returned = [&](int at) -> bool {
+            if (!ret || ret->returned == NO_REF || ret->returned == applied) return false;
+            applied = ret->returned;
+            region(code, f, ci, emit(T_EQZ, ret->returned), at, stop, range_begin, -1, -1, -1, ret);
+            return true;
+        };
         while (pc < stop) {
             const Ins &in = code.ins[(size_t)pc];
             stats.cvm_instructions++;
@@ -627,8 +639,10 @@ class Tracer {
                         break;
                     }
                     stats.dyn_branches++;
-                    dynamic_if(code, f, ci, pc, then_end, in, c.ref, ret);
+                    region(code, f, ci, c.ref, pc + 1, then_end, pc + 1, in.m_else >= 0 ? in.m_else + 1 : -1, in.m_end,
+                           in.m_else + 1, ret);
                     pc = in.m_end + 1;
+                    if (rest_if_returned(pc)) pc = stop;
                     break;
                 }
                 case OP_ELSE: pc = in.m_end + 1; break;    // fell off the end of a then-branch
@@ -641,6 +655,7 @@ class Tracer {
                     loop_stack.pop_back();
                     if (r) return true;
                     if (last_exit_pc == lend) stats.cvm_instructions++;   // fell onto the loop's `end` (a `break` jumps past it)
+                    if (rest_if_returned(lend + 1)) { pc = stop; break; }
                     pc = lend + 1;
                     break;
                 }
@@ -658,8 +673,7 @@ class Tracer {
                             emit(T_FAIL_IF, pred_conj(), NO_REF, NO_REF, ST_LOOP);
                         } else {
                             stats.unrolled_iterations++;
-                            if (run(code, f, ci, in.m_loop + 1, loop_end, in.m_loop + 1, ret))
-                                throw TraceError("return under a data-dependent condition");
+                            run(code, f, ci, in.m_loop + 1, loop_end, in.m_loop + 1, ret);
                         }
                         unroll_depth--;
                         pc = stop;   // nothing after a `continue` executes in this arm
@@ -683,7 +697,7 @@ class Tracer {
                 case OP_CALL: call(code, f, ci, in); pc++; break;
                 case OP_RETURN: {
                     if (!ret) throw TraceError("return outside a function");
-                    if (preds.size() != ret->pred_depth) throw TraceError("return under a data-dependent condition");
+                    const bool predicated = preds.size() != ret->pred_depth;
                     if (in.scalar_return) {
                         set_lvar(*ret->frame, ret->addr, ref_av(field_ref(val(f, in.args.at(0)))));
                     } else {
@@ -694,7 +708,18 @@ class Tracer {
                             set_lvar(*ret->frame, ret->addr + k, it == f.lvar.end() ? ff_av(c_zero) : it->second);
                         }
                     }
-                    return true;
+                    if (!predicated) return true;
+                    // `return` in an if-converted arm: the writes above are merged with the previous contents of the
+                    // destination when the arm closes (they are logged like any other write); remember under which
+                    // condition the function is over, so that whatever follows runs under its negation
+                    {
+                        uint32_t p = preds[ret->pred_depth];
+                        for (size_t k = ret->pred_depth + 1; k < preds.size(); k++) p = emit(T_LAND, p, preds[k]);
+                        if (!is_bool(p)) p = emit(T_NEQ, p, CONST_FLAG | c_zero);
+                        ret->returned = ret->returned == NO_REF ? p : emit(T_LOR, ret->returned, p);
+                    }
+                    pc = stop;
+                    break;
                 }
                 case OP_MAPPED_UNSUPPORTED:
                     throw TraceError("mapped accesses (mixed component arrays / buses) need the io-map, which the "
@@ -714,12 +739,14 @@ class Tracer {
         return run(code, f, ci, lpc + 1, lend, lpc, ret);
     }
 
-    void dynamic_if(const cvm::Code &code, Frame &f, int ci, int pc, int then_end, const cvm::Ins &in, uint32_t cond,
-                    const RetTarget *ret) {
+    // If-conversion of one data-dependent region: the then-arm [t_begin, t_end) runs under `cond`, the optional else-arm
+    // [e_begin, e_end) under its negation, both against an undo log; the locations either of them wrote are merged with SEL.
+    void region(const cvm::Code &code, Frame &f, int ci, uint32_t cond, int t_begin, int t_end, int t_range, int e_begin,
+                int e_end, int e_range, const RetTarget *ret) {
         // then-arm
         logs.emplace_back();
         preds.push_back(cond);
-        if (run(code, f, ci, pc + 1, then_end, pc + 1, ret)) throw TraceError("return under a data-dependent condition");
+        run(code, f, ci, t_begin, t_end, t_range, ret);
         preds.pop_back();
         std::vector<LogEntry> logT = std::move(logs.back());
         logs.pop_back();
@@ -747,10 +774,9 @@ class Tracer {
         for (size_t k = logT.size(); k-- > 0;) restore(logT[k]);
         // else-arm
         logs.emplace_back();
-        if (in.m_else >= 0) {
+        if (e_begin >= 0) {
             preds.push_back(emit(T_EQZ, cond));
-            if (run(code, f, ci, in.m_else + 1, in.m_end, in.m_else + 1, ret))
-                throw TraceError("return under a data-dependent condition");
+            run(code, f, ci, e_begin, e_end, e_range, ret);
             preds.pop_back();
         }
         std::vector<LogEntry> logE = std::move(logs.back());

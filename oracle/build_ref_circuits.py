@@ -21,6 +21,7 @@ def circuits():
     table = {
         "babyadd4": (babyjub.BabyAddChain, (4,)),
         "nbits": (basic.NBits, ()),
+        "earlyret": (basic.EarlyReturns, ()),
         "countdown": (basic.CountDown, ()),
         "multiplier2": (basic.Multiplier2, ()),
         "multiplier4": (basic.MultiplierN, (4,)),

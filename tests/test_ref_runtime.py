@@ -40,6 +40,7 @@ def input_json(art, values):
 
 
 CASES = {
+    "earlyret": [[5, 3], [M.Q - 5, 3], [3, 5], [1000, 7], [0, 0], [255, 1], [7, 1000], [M.Q - 1, M.Q - 2]],
     "nbits": [[0], [1], [255], [256], [1 << 253], [M.Q - 1]],
     "countdown": [[0], [1], [17], [200]],
     "babyadd4": [[995203441582195749578291179787384436505546430278305826713579947235728471134, 5472060717959818805561601436314318772137091100104008585924551046643952123905, 5299619240641551281634865583518297030282874472190772894086521144482721001553, 16950150798460657717958625567821834550301663161624707787222815936182638968203], [0, 1, 0, 1], [3, 5, 7, 11]],
@@ -61,7 +62,7 @@ def test_oracle_matches_reference_runtime_byte_for_byte(name, tmp_path):
     prog = I.load(art.cvm)
     rng = random.Random(21)
     cases = list(CASES[name])
-    if name in ("multiplier2", "opszoo", "poseidon2", "multiplier4", "babyadd4"):
+    if name in ("multiplier2", "opszoo", "poseidon2", "multiplier4", "babyadd4", "earlyret"):
         cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
     for k, values in enumerate(cases):
         jin, wout = tmp_path / ("in%d.json" % k), tmp_path / ("out%d.wtns" % k)

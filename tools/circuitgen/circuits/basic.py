@@ -173,3 +173,57 @@ def CountDown(T):
         T.set(acc, acc + n * n)
         T.set(n, n - 1)
     T.assign(out, acc)
+
+
+def make_early_return_functions():
+    """circom functions that `return` from inside data-dependent branches and from inside a loop."""
+    fabs = Function("fabs")
+    a = fabs.arg("a")
+    fabs.returns = ()
+    with fabs.if_(a < 0):
+        fabs.ret(-a)
+    fabs.ret(a)
+
+    fclamp = Function("fclamp")
+    x = fclamp.arg("x")
+    lo = fclamp.arg("lo")
+    hi = fclamp.arg("hi")
+    fclamp.returns = ()
+    with fclamp.if_(x < lo):
+        fclamp.ret(lo)
+    with fclamp.else_():
+        with fclamp.if_(x > hi):
+            fclamp.ret(hi)
+    fclamp.ret(x * 1 + 0)
+
+    first = Function("first_ge")
+    v = first.arg("v")
+    b = first.arg("b")
+    first.returns = ()
+    i = first.var("i")
+    acc = first.var("acc", init=0)
+    with first.for_(i, 0, i < 8):
+        with first.if_((v >> i) <= b):
+            first.ret(i * 1000 + acc)
+        first.set(acc, acc + (v >> i))
+    first.ret(8000 + acc)
+    return fabs, fclamp, first
+
+
+FABS, FCLAMP, FIRST_GE = make_early_return_functions()
+
+
+def EarlyReturns(T):
+    """`<--` hints through functions with early returns under data-dependent conditions (if-converted by the tracer)."""
+    a = T.input("a")
+    b = T.input("b")
+    out = T.output("out", (4,))
+    t = T.var("t")
+    T.set(t, T.call(FABS, a))
+    T.assign(out[0], t)
+    T.set(t, T.call(FCLAMP, a, b, b + 100))
+    T.assign(out[1], t)
+    T.set(t, T.call(FIRST_GE, a, b))
+    T.assign(out[2], t)
+    T.set(t, T.call(FABS, a - b))
+    T.assign(out[3], t + 1)
