@@ -6,6 +6,7 @@ constants and by values, divisions (also by zero), comparisons feeding products 
 compiler), sums of products by constants (the dot-product fusion) and a few `===` that random inputs may violate."""
 import random
 
+from tools.circuitgen.circuits.basic import FABS, FCLAMP, FIRST_GE
 from tools.circuitgen.dsl import P
 
 BIN = ["add", "sub", "mul", "div", "idiv", "mod", "pow", "shl", "shr", "band", "bor", "bxor", "lt", "leq", "gt", "geq",
@@ -64,6 +65,11 @@ def make_circuit(seed, n_stmts=40):
                     T.set(v, expr())
                 with T.else_():
                     T.set(v, expr())
+            elif rng.random() < 0.12:
+                # circom functions with early returns under data-dependent conditions (also from inside a loop)
+                fn = rng.choice([FABS, FCLAMP, FIRST_GE])
+                nargs = {id(FABS): 1, id(FCLAMP): 3, id(FIRST_GE): 2}[id(fn)]
+                T.set(v, T.call(fn, *[rng.choice(vals) for _ in range(nargs)]))
             else:
                 T.set(v, expr())
             vals.append(v)
