@@ -182,6 +182,17 @@ def build():
         return False
     src = os.path.join(OUT, "src")
     inc = os.path.join(OUT, "inc", "nlohmann")
+    # up to date: every product newer than every input (reference sources where they lie, this recipe, the driver)
+    products = [os.path.join(OUT, f) for f in ("fr.o", "calcwit.o", "main.o", "libfr_ref.so")] + \
+               [os.path.join(src, f) for f in ("fr.cpp", "fr.hpp", "circom.hpp", "calcwit.hpp")]
+    inputs = [os.path.join(CEL, "generic", "fr.cpp"), os.path.join(CEL, "generic", "fr.hpp"),
+              os.path.join(CEL, "common", "calcwit.cpp"), os.path.join(CEL, "common", "main.cpp"),
+              os.path.join(CEL, "common", "calcwit.hpp"), os.path.join(CEL, "common", "circom.hpp"),
+              os.path.abspath(__file__), os.path.join(HERE, "fr_ref_driver.cpp"), os.path.join(HERE, "gmp_shim", "gmp.h")]
+    if all(os.path.exists(p) for p in products) and \
+            min(os.path.getmtime(p) for p in products) > max(os.path.getmtime(p) for p in inputs):
+        print("oracle/_ref runtime is up to date")
+        return True
     os.makedirs(src, exist_ok=True)
     os.makedirs(inc, exist_ok=True)
     ctx = bn254_context()

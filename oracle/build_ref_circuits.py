@@ -56,9 +56,20 @@ def build(names=None):
     cdir = os.path.join(OUT, "circuits")
     flags = ["-std=c++11", "-O3", "-w", "-I", src, "-I", os.path.join(HERE, "gmp_shim"), "-I", os.path.join(OUT, "inc")]
     harness = os.path.join(OUT, "ref_harness.o")
-    subprocess.check_call(["g++", *flags, "-c", os.path.join(HERE, "ref_harness.cpp"), "-o", harness])
+    hsrc = os.path.join(HERE, "ref_harness.cpp")
+    if not os.path.exists(harness) or os.path.getmtime(harness) < max(os.path.getmtime(hsrc), *(os.path.getmtime(p) for p in need)):
+        subprocess.check_call(["g++", *flags, "-c", hsrc, "-o", harness])
+    # a binary is up to date when it is newer than everything it is made from (the generator, the harness, the runtime)
+    gen_dir = os.path.join(ROOT, "tools", "circuitgen")
+    deps = [harness, *need, os.path.join(ROOT, "circom_cvm_b200", "formats.py")]
+    for d, _sub, files in os.walk(gen_dir):
+        deps += [os.path.join(d, f) for f in files if f.endswith(".py")]
+    newest = max(os.path.getmtime(p) for p in deps)
     for name, (fn, args) in circuits().items():
         if names and name not in names:
+            continue
+        exe = os.path.join(OUT, name)
+        if not names and os.path.exists(exe) and os.path.exists(exe + ".dat") and os.path.getmtime(exe) > newest:
             continue
         art = compile_circuit(fn, args, name=name)
         paths = write_artifact(art, cdir, with_cpp=True)
