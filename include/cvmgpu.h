@@ -150,16 +150,20 @@ int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, 
 
 /* ---- field arithmetic, host build of the device limb routines (test hook; no GPU needed) ------- */
 /* op: add sub mul div idiv mod pow shl shr band bor bxor bnot lt leq gt geq eq neq land lor lnot neg inv square
- * a, b, out: 32-byte LE canonical.  Returns 1 when the reference's behaviour is undefined (division by zero). */
+ * a, b, out: 32-byte LE canonical.  Returns 1 where the reference aborts (`\` or `%` by zero: GMP raises); a field
+ * division by zero yields 0, as the reference's Fr_div does (bn128/fr.cpp:146-163). */
 int cvmgpu_fr_host_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out);
 /* same operations executed by a CUDA kernel over n element pairs (device self-test of csrc/fr.cuh) */
 int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n);
 /* dependency-free integer-pipe micro-benchmark.  The returned rate counts 8 "units" per thread and iteration, where a
  * unit is: kind 0 one mad.lo+mad.hi pair, 1 one mad.wide.u32 (both = one 32x32->64 multiply-accumulate), 2 two mad.lo,
- * 3 two mad.hi, 4 two addc (carry chain), 5 two add, 6 two mad{c}.{lo,hi}.cc (carry chain on the multiply pipe). */
+ * 3 two mad.hi, 4 two addc (carry chain), 5 two add, 6 two mad{c}.{lo,hi}.cc (carry chain on the multiply pipe),
+ * 7 one mul.wide.u32 + one add (the zero-addend form the multiplier uses). */
 int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms);
 /* register-resident Montgomery-multiplication throughput (no memory traffic): variant 0 = portable 64-bit CIOS,
- * 1 = mul.wide formulation used by the kernels; ctas_per_sm x 128 threads per SM. */
+ * 1 = mul.wide formulation with a second, warp-uniform chain (which ptxas runs on the uniform datapath), 2 = mul.wide
+ * formulation, one dependent chain per thread (the figure that applies to per-witness arithmetic);
+ * ctas_per_sm x 128 threads per SM. */
 int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_second);
 
 #ifdef __cplusplus
