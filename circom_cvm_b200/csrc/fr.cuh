@@ -54,6 +54,11 @@ FR_HD Fr one_mont() {
     Fr r = {{0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}};
     return r;
 }
+// q - (R mod q)   (Montgomery form of -1)
+FR_HD Fr minus_one_mont() {
+    Fr r = {{0xa0000006u, 0x974bc177u, 0xda58a367u, 0xf13771b2u, 0x0908122eu, 0x51e1a247u, 0x4729c0fau, 0x2259d6b1u}};
+    return r;
+}
 // R^2 mod q  (bn128/fr.asm:8789 R2)
 FR_HD Fr r2_mont() {
     Fr r = {{0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}};

@@ -183,8 +183,30 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 b[k] = tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]);
             }
             if (op == tape::T_MUL) {
+                // bit-heavy programs (F_TRIVIAL, set by the tape builder): factors that are 0 or 1 at run time without
+                // being provably so (input bits of a hash) need no product; decided per warp to keep control flow uniform
+                bool cheap = false;
+                if (flags & tape::F_TRIVIAL) {
+                    const Fr one = fr::one_mont();
+                    bool triv = true;
 #pragma unroll
-                for (int k = 0; k < W; k++) r[k] = fr::mont_mul(a[k], b[k]);
+                    for (int k = 0; k < W; k++)
+                        triv = triv && (fr::is_zero(a[k]) || fr::is_zero(b[k]) || fr::equal(a[k], one) || fr::equal(b[k], one));
+                    cheap = __all_sync(0xffffffffu, triv);
+                    if (cheap) {
+#pragma unroll
+                        for (int k = 0; k < W; k++) {
+                            const bool z = fr::is_zero(a[k]) || fr::is_zero(b[k]);
+                            const bool a1 = fr::equal(a[k], one);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) r[k].v[i] = z ? 0u : (a1 ? b[k].v[i] : a[k].v[i]);
+                        }
+                    }
+                }
+                if (!cheap) {
+#pragma unroll
+                    for (int k = 0; k < W; k++) r[k] = fr::mont_mul(a[k], b[k]);
+                }
             } else if (op == tape::T_ADD) {
 #pragma unroll
                 for (int k = 0; k < W; k++) r[k] = fr::add(a[k], b[k]);
@@ -549,8 +571,18 @@ __global__ void __launch_bounds__(R1CS_NT, 4) r1cs_kernel(R1csParams p) {
         if (hA.x != hB.x && hB.x != hC.x) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
             const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
             const Fr sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
-            // a zero factor needs no product (whole warps skip it where a wire is structurally 0, e.g. padding bits)
-            if (!fr::is_zero(sa) && !fr::is_zero(sb)) prod = fr::mont_mul(sa, sb);
+            // trivial factors need no product: 0, 1 and -1 (bit-valued wires and the +-1 combinations of them that
+            // fill hash circuits: Sha256's 61 904 quadratic constraints per witness are almost all of this kind).
+            // The branch is per lane; a warp pays for the multiplication only if one of its witnesses needs it.
+            const Fr one = fr::one_mont();
+            const Fr mone = fr::minus_one_mont();
+            // (the low limb filters first: general field values fail it with one comparison per case)
+            if (fr::is_zero(sa) || fr::is_zero(sb)) prod = fr::zero();
+            else if (sa.v[0] == one.v[0] && fr::equal(sa, one)) prod = sb;
+            else if (sb.v[0] == one.v[0] && fr::equal(sb, one)) prod = sa;
+            else if (sa.v[0] == mone.v[0] && fr::equal(sa, mone)) prod = fr::neg(sb);
+            else if (sb.v[0] == mone.v[0] && fr::equal(sb, mone)) prod = fr::neg(sa);
+            else prod = fr::mont_mul(sa, sb);
         } else {
             // the terms of a lone A or B still occupy the stream: consume them
             if (hA.x != hB.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hA, hB.x);

@@ -27,6 +27,7 @@ struct TapeIns {
 };
 static const uint8_t F_STORE = 8;
 static const uint8_t F_CZERO = 16;
+static const uint8_t F_TRIVIAL = 16;  // T_MUL: check at run time whether the factors are 0 / 1 (bit-heavy programs)
 static const uint8_t F_ADDEND = 32;
 static const uint8_t F_RING = 64;    // T_LD: the value was requested LD_RING reloads ago and sits in ring entry b
 static const uint32_t LD_RING = 4;   // reloads in flight per witness (32 B of shared memory each)
@@ -522,6 +523,15 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
     out.n_rows = out.n_wires + spill_rows;
     out.stats.n_spill_rows = spill_rows;
     out.stats.n_tape = out.ins.size();
+    // bit-heavy program (more selects / bit extractions than products): its remaining products mostly have factors that
+    // are 0 or 1 at run time (unconstrained input bits); let the kernel look before it multiplies
+    if (out.stats.n_sel + out.stats.n_other > 2 * out.stats.n_mul) {
+        for (size_t pc = 0; pc < out.ins.size(); pc++) {
+            TapeIns &in = out.ins[pc];
+            if (in.op == T_DOT) { pc += (in.a + 1) / 2; continue; }
+            if (in.op == T_MUL) in.flags |= F_TRIVIAL;
+        }
+    }
     schedule_reloads(out);
     out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +
                      72 * out.stats.n_dot + 1800 * (out.stats.n_inv + out.stats.n_div);
