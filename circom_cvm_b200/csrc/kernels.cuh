@@ -434,7 +434,7 @@ struct R1csParams {
 };
 
 // One linear combination.  Its terms are ordered by coefficient class (r1cs.hpp):
-//   +-1              [beg, e0): modular add/sub
+//   +-2^k, k <= 3    [beg, e0): k modular doublings, then modular add/sub (+-1 is k = 0)
 //   small +, small - [e0, e1), [e1, e2): integer sums with 32-bit scalars (8 multiply-accumulates per term), one
 //                    reduction per class (fr.cuh small_reduce)
 //   general          [e2, end): lazy-reduction dot product (64 multiply-accumulates per term, one Montgomery
@@ -492,9 +492,10 @@ __device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const
     Fr acc = fr::zero();
     uint32_t t = hdr.x;
     for (; t < e0; t++) {
-        const uint32_t neg = __ldg(terms + t).y;
-        const Fr v = ts.take(t);
-        acc = neg ? fr::sub(acc, v) : fr::add(acc, v);
+        const uint32_t meta = __ldg(cmag + __ldg(terms + t).y);   // sign | k << 1: coefficient +-2^k, k <= 3
+        Fr v = ts.take(t);
+        for (uint32_t k = meta >> 1; k; k--) v = fr::add(v, v);
+        acc = (meta & 1u) ? fr::sub(acc, v) : fr::add(acc, v);
     }
     if (e0 < e2) {
         for (int neg = 0; neg < 2; neg++) {
@@ -526,7 +527,7 @@ __device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const
     return acc;
 }
 
-// linear combinations made of +-1 terms only (the common case outside hash-heavy circuits) stay inline
+// linear combinations made of +-2^k (k <= 3) terms only stay inline
 __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
     if (hdr.y != end) return lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hdr, end);
     TermStream ts;
@@ -537,9 +538,10 @@ __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, ui
     ts.t_end = t_end;
     Fr acc = fr::zero();
     for (uint32_t t = hdr.x; t < end; t++) {
-        const uint32_t neg = __ldg(p.terms + t).y;
-        const Fr v = ts.take(t);
-        acc = neg ? fr::sub(acc, v) : fr::add(acc, v);
+        const uint32_t meta = __ldg(p.cmag + __ldg(p.terms + t).y);   // sign | k << 1: coefficient +-2^k, k <= 3
+        Fr v = ts.take(t);
+        for (uint32_t k = meta >> 1; k; k--) v = fr::add(v, v);
+        acc = (meta & 1u) ? fr::sub(acc, v) : fr::add(acc, v);
     }
     return acc;
 }

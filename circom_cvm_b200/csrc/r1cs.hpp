@@ -131,9 +131,12 @@ inline File load(const std::string &path) {
     }
     if (p > end) throw Error("constraint section overrun");
     // ---- coefficient classes and per-LC term order
-    std::vector<uint8_t> kind(out.coefs.size(), 3);   // 0: +-1, 1: small positive, 2: small negative, 3: general
+    // 0: +-2^k with k <= 3 (k modular doublings and one add/sub; +-1 is k = 0), 1: small positive, 2: small negative,
+    // 3: general.  cmag: class 0 -> sign | k << 1, classes 1/2 -> the 32-bit magnitude.
+    std::vector<uint8_t> kind(out.coefs.size(), 3);
     out.cmag.assign(out.coefs.size(), 0);
     kind[0] = kind[1] = 0;
+    out.cmag[1] = 1;
     for (size_t i = 2; i < out.coefs.size(); i++) {
         const fr::Fr &c = out.coefs[i];
         fr::Fr n = fr::neg(c);
@@ -142,8 +145,13 @@ inline File load(const std::string &path) {
                 if (x.v[k]) return false;
             return true;
         };
-        if (small(c)) { kind[i] = 1; out.cmag[i] = c.v[0]; }
-        else if (small(n)) { kind[i] = 2; out.cmag[i] = n.v[0]; }
+        const bool sp = small(c), sn = small(n);
+        const uint32_t m = sp ? c.v[0] : n.v[0];
+        if ((sp || sn) && (m == 2 || m == 4 || m == 8)) {
+            kind[i] = 0;
+            out.cmag[i] = (sn ? 1u : 0u) | ((m == 2 ? 1u : m == 4 ? 2u : 3u) << 1);
+        } else if (sp) { kind[i] = 1; out.cmag[i] = c.v[0]; }
+        else if (sn) { kind[i] = 2; out.cmag[i] = n.v[0]; }
     }
     out.split.resize(3 * (size_t)(out.ptr.size() - 1));
     for (size_t j = 0; j + 1 < out.ptr.size(); j++) {
