@@ -189,6 +189,7 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_macs = p->tape.stats.macs;
     info->tape_ld_streamed = p->tape.stats.n_ld_streamed;
     info->unrolled_iterations = p->tstats.unrolled_iterations;
+    info->tape_lut = p->tape.stats.n_lut;
     return CVMGPU_OK;
 }
 

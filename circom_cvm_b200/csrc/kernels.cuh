@@ -253,6 +253,21 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 }
                 r[k] = unpack(lo, hi);
             }
+        } else if (op == tape::T_LUT) {
+            // boolean function of up to three 0/1 values: the low limb of a slot tells 0 from R mod q
+            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
+            const uint32_t nin = cur.z >> 8;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                uint32_t idx = 0;
+#pragma unroll
+                for (uint32_t i = 0; i < 3; i++)
+                    if (i < nin) {
+                        const uint32_t slot = (cur.y >> (8 * i)) & 0xffu;
+                        idx |= (s32[((slot * 2) * NS + tk[k]) << 2] != 0u ? 1u : 0u) << i;
+                    }
+                r[k] = mont_bool((cur.z >> idx) & 1u);
+            }
         } else if (op == tape::T_BITC) {
             // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);

@@ -21,6 +21,7 @@ struct TapeIns {
                       // bit3: the result is also stored to value-store row c (fused witness-wire store)
     uint16_t dst;     // slot
     uint32_t a, b;    // slot or constant index; T_INPUT: a = input index; T_BITC: b = bit number;
+                      // T_LUT: a = three input slots (one byte each), b = truth table | number of inputs << 8;
                       // T_LD: a = row to request now for the reload LD_RING reloads ahead (NO_ROW: none), b = ring entry
     uint32_t c;       // T_SEL: third operand; T_LD/T_ST/T_STC: value-store row; T_FAIL_IF/T_FAIL_NE: status;
                       // with flag bit3: value-store row
@@ -37,7 +38,7 @@ static_assert(sizeof(TapeIns) == 16, "tape instruction must be 16 bytes");
 struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
-    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0;
+    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
     uint32_t n_spill_rows = 0;
     // 32x32->64 multiply-accumulates the kernel executes per witness: 136 per Montgomery product (also the one that brings
     // an input to Montgomery form and the one after an inversion), 64 per DOT term + 72 per DOT reduction, and the
@@ -491,6 +492,12 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             uint32_t e0 = enc[0], e1 = enc[1], e2 = enc[2];
             if (o.op == T_INPUT) e0 = o.aux;
             if (o.op == T_BITC) e1 = o.aux;
+            if (o.op == T_LUT) {   // a = the three input slots, one byte each; b = table | k << 8; c is free for the fused store
+                e0 = enc[0] | (enc[1] << 8) | (enc[2] << 16);
+                e1 = o.aux;
+                e2 = 0;
+                out.stats.n_lut++;
+            }
             if (o.op == T_SEL && (o.c != NO_REF) && (o.c & CONST_FLAG) && fr::is_zero(tr.consts[o.c & ~CONST_FLAG])) {
                 flags = (uint8_t)((flags & ~4u) | F_CZERO);
                 e2 = 0;

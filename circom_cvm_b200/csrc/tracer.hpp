@@ -34,6 +34,8 @@ enum TOp : uint8_t {
     // produced by the tracer's peepholes
     T_FAIL_NE,   // status if a != b                (FAIL_IF(NEQ(a, b)): the `===` assert shape)
     T_BITC,      // bit `aux` of the RAW limbs of a  (a = y * R^-1, whose Montgomery limbs are the canonical y)
+    T_LUT,       // boolean function of up to three 0/1 values a, b, c: bit (a | b<<1 | c<<2) of the 8-bit table in aux
+                 // (aux >> 8 = number of inputs).  Produced by the boolean-cone collapsing below.
     T_INV,       // a^-1, with 0^-1 := 0  (ff.div a b is traced as a * INV(b) so that independent inversions can be batched)
     // inserted by the tape builder
     T_DOT,       // sum_k c_k * x_k (+ addend): fused tree of additions of products by constants (tape.hpp fuse_dots)
@@ -62,6 +64,7 @@ struct TraceStats {
     uint64_t ref_field_ops = 0;      // all ff.* executions of the reference program
     uint64_t folded = 0, cse_hits = 0;
     uint64_t dyn_branches = 0;
+    uint64_t luts = 0;                  // boolean cones emitted as one T_LUT
     uint64_t unrolled_iterations = 0;   // iterations of data-dependent while loops traced under predicates
     uint64_t unset_signal_reads = 0;
 };
@@ -88,6 +91,18 @@ class Tracer {
 
     std::vector<SOp> ops;
     std::vector<uint8_t> isbool;  // per op: the value is provably 0 or 1 (comparison results, extracted bits, ANDs of those)
+    // Boolean-cone collapsing.  For every value that is an arithmetic function of at most three provably-0/1 values, the
+    // function is tabulated while tracing (small signed integers; anything else invalidates the cone).  A value whose
+    // table only holds 0 and 1 IS a boolean function of its leaves -- XOR written as a+b-2ab, circomlib's Xor3 / Ch / Maj
+    // polynomials, ANDs, multiplexers -- and is emitted as one T_LUT instead of its cone of field operations; the cone's
+    // intermediate values die unless something else uses them.  Exact: the leaves can only be 0 or 1.
+    struct Cone {
+        uint8_t k = 0xff;            // number of leaves, 0xff = not tabulated
+        uint32_t leaf[3] = {0, 0, 0};
+        int8_t tt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    };
+    std::vector<Cone> cones;
+    std::vector<uint32_t> alias;  // per op: the T_LUT (or constant / leaf) that replaced it, for later CSE hits
     std::vector<fr::Fr> consts;   // canonical
     std::vector<uint32_t> witness_ref;   // per witness wire: ref (const or value)
     TraceStats stats;
@@ -248,12 +263,152 @@ class Tracer {
         bool bl = false;
         switch (o.op) {
             case T_LT: case T_LE: case T_GT: case T_GE: case T_EQ: case T_NEQ: case T_LAND: case T_LOR: case T_EQZ:
-            case T_BITC: bl = true; break;
+            case T_BITC: case T_LUT: bl = true; break;
             case T_SEL: bl = is_bool(o.b) && is_bool(o.c); break;
             default: break;
         }
         isbool.push_back(bl ? 1 : 0);
+        cones.emplace_back();
+        alias.push_back(NO_REF);
         return (uint32_t)ops.size() - 1;
+    }
+    // ---- boolean cones
+    static const int CONE_MAX = 100;   // |table entry| bound: cones of boolean logic only see tiny integers
+    bool cone_of(uint32_t r, Cone &out) const {
+        if (r == NO_REF) return false;
+        if (r & CONST_FLAG) {
+            const fr::Fr &c = cval(r);
+            fr::Fr n = fr::neg(c);
+            auto small = [](const fr::Fr &x, int &v) {
+                for (int i = 1; i < 8; i++)
+                    if (x.v[i]) return false;
+                if (x.v[0] > (uint32_t)CONE_MAX) return false;
+                v = (int)x.v[0];
+                return true;
+            };
+            int v;
+            out = Cone();
+            out.k = 0;
+            if (small(c, v)) { out.tt[0] = (int8_t)v; return true; }
+            if (small(n, v)) { out.tt[0] = (int8_t)-v; return true; }
+            return false;
+        }
+        if (cones[r].k != 0xff) { out = cones[r]; return true; }
+        if (isbool[r]) {            // a 0/1 value that is not itself tabulated: a leaf
+            out = Cone();
+            out.k = 1;
+            out.leaf[0] = r;
+            out.tt[0] = 0;
+            out.tt[1] = 1;
+            return true;
+        }
+        return false;
+    }
+    // table of `op` over the union of the operands' leaves; false when it does not apply
+    bool cone_eval(uint8_t op, const uint32_t *refs, int n, Cone &res) const {
+        Cone in[3];
+        for (int i = 0; i < n; i++)
+            if (!cone_of(refs[i], in[i])) return false;
+        res = Cone();
+        uint32_t u[9];
+        int nu = 0;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < in[i].k; j++) {
+                bool seen = false;
+                for (int q = 0; q < nu; q++) seen = seen || u[q] == in[i].leaf[j];
+                if (!seen) u[nu++] = in[i].leaf[j];
+            }
+        if (nu > 3) return false;
+        std::sort(u, u + nu);
+        res.k = (uint8_t)nu;
+        for (int q = 0; q < nu; q++) res.leaf[q] = u[q];
+        for (int r = 0; r < (1 << nu); r++) {
+            int v[3] = {0, 0, 0};
+            for (int i = 0; i < n; i++) {
+                int idx = 0;
+                for (int j = 0; j < in[i].k; j++)
+                    for (int q = 0; q < nu; q++)
+                        if (u[q] == in[i].leaf[j] && ((r >> q) & 1)) idx |= 1 << j;
+                v[i] = in[i].tt[idx];
+            }
+            int o;
+            switch (op) {
+                case T_ADD: o = v[0] + v[1]; break;
+                case T_SUB: o = v[0] - v[1]; break;
+                case T_MUL: o = v[0] * v[1]; break;
+                case T_SEL: o = v[0] != 0 ? v[1] : v[2]; break;
+                case T_EQ: o = v[0] == v[1]; break;
+                case T_NEQ: o = v[0] != v[1]; break;
+                case T_EQZ: o = v[0] == 0; break;
+                case T_LAND: o = v[0] != 0 && v[1] != 0; break;
+                case T_LOR: o = v[0] != 0 || v[1] != 0; break;
+                default: return false;
+            }
+            if (o > CONE_MAX || o < -CONE_MAX) return false;
+            res.tt[r] = (int8_t)o;
+        }
+        return true;
+    }
+    // CSE'd creation of an op without peepholes
+    uint32_t make_op(uint8_t op, uint32_t a, uint32_t b, uint32_t c, uint32_t aux) {
+        uint64_t key = ((uint64_t)op << 56) ^ ((uint64_t)a * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)b * 0xC2B2AE3D27D4EB4Full) ^
+                       ((uint64_t)c * 0x165667B19E3779F9ull) ^ aux;
+        for (uint32_t id : cse[key]) {
+            const SOp &o = ops[id];
+            if (o.op == op && o.a == a && o.b == b && o.c == c && o.aux == aux) {
+                stats.cse_hits++;
+                return alias[id] != NO_REF ? alias[id] : id;
+            }
+        }
+        SOp o{op, a, b, c, aux};
+        uint32_t id = push_op(o);
+        cse[key].push_back(id);
+        return id;
+    }
+    // after `id` was created: tabulate it; if it is a boolean function of its leaves, return what replaces it
+    uint32_t collapse(uint32_t id) {
+        const SOp o = ops[id];
+        if (o.op == T_LUT) return id;
+        uint32_t refs[3] = {o.a, o.b, o.c};
+        int n = (o.op == T_SEL) ? 3 : (o.b == NO_REF ? 1 : 2);
+        Cone c;
+        if (!cone_eval(o.op, refs, n, c)) return id;
+        // drop the leaves the function does not depend on
+        for (int q = c.k - 1; q >= 0; q--) {
+            bool dep = false;
+            for (int r = 0; r < (1 << c.k); r++) dep = dep || c.tt[r] != c.tt[r ^ (1 << q)];
+            if (dep) continue;
+            Cone d;
+            d.k = (uint8_t)(c.k - 1);
+            for (int j = 0, w = 0; j < c.k; j++)
+                if (j != q) d.leaf[w++] = c.leaf[j];
+            for (int r = 0; r < (1 << d.k); r++) {
+                int lo = r & ((1 << q) - 1), hi = r >> q;
+                d.tt[r] = c.tt[lo | (hi << (q + 1))];
+            }
+            c = d;
+        }
+        cones[id] = c;
+        bool boolean = true;
+        for (int r = 0; r < (1 << c.k); r++) boolean = boolean && (c.tt[r] == 0 || c.tt[r] == 1);
+        uint32_t rep = id;
+        if (c.k == 0) rep = CONST_FLAG | intern(hostfr::from_i64(c.tt[0]));
+        else if (!boolean) return id;
+        else if (c.k == 1 && c.tt[0] == 0 && c.tt[1] == 1) rep = c.leaf[0];
+        else if (isbool[id] && (o.op == T_EQ || o.op == T_NEQ || o.op == T_EQZ || o.op == T_LAND || o.op == T_LOR) && c.k >= 2 &&
+                 !(o.a & CONST_FLAG) && (o.b == NO_REF || !(o.b & CONST_FLAG)) && isbool[o.a] && (o.b == NO_REF || isbool[o.b]))
+            return id;   // already one cheap instruction on 0/1 operands
+        else {
+            uint32_t table = 0;
+            for (int r = 0; r < (1 << c.k); r++) table |= (uint32_t)c.tt[r] << r;
+            rep = make_op(T_LUT, c.leaf[0], c.k > 1 ? c.leaf[1] : NO_REF, c.k > 2 ? c.leaf[2] : NO_REF, table | ((uint32_t)c.k << 8));
+            if (cones[rep].k == 0xff) {
+                cones[rep] = c;
+                stats.luts++;
+            }
+        }
+        if (rep != id) alias[id] = rep;
+        return rep;
     }
     // value provably in {0, 1}
     bool is_bool(uint32_t r) const {
@@ -355,12 +510,15 @@ class Tracer {
             const SOp &o = ops[id];
             if (o.op == op && o.a == a && o.b == b && o.c == c && o.aux == aux) {
                 stats.cse_hits++;
-                return id;
+                return alias[id] != NO_REF ? alias[id] : id;
             }
         }
         SOp o{op, a, b, c, aux};
         uint32_t id = push_op(o);
         cse[key].push_back(id);
+        if (op == T_ADD || op == T_SUB || op == T_MUL || op == T_SEL || op == T_EQ || op == T_NEQ || op == T_EQZ || op == T_LAND ||
+            op == T_LOR)
+            return collapse(id);
         return id;
     }
 

@@ -75,6 +75,7 @@ typedef struct {
     uint64_t tape_macs;          /* 32x32->64 multiply-accumulates the tape kernel executes per witness */
     uint64_t tape_ld_streamed;   /* reloads served by the cp.async ring (requested 4 reloads ahead) */
     uint64_t unrolled_iterations; /* iterations of data-dependent while loops traced under predicates */
+    uint64_t tape_lut;           /* boolean cones (XOR / Ch / Maj / ... written as field polynomials) run as one table look-up */
 } cvmgpu_program_info;
 
 typedef struct {

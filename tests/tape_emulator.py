@@ -7,8 +7,8 @@ and is not a fallback: the product path has no CPU execution.
 from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
- T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_INV, T_DOT,
- T_LD, T_ST, T_STC) = range(33)
+ T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
+ T_DOT, T_LD, T_ST, T_STC) = range(34)
 F_ADDEND = 32        # T_DOT: field b is an addend
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
@@ -58,6 +58,14 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             slots[dst] = acc % M.Q
         elif op == T_INPUT:
             slots[dst] = inputs[a] % M.Q
+        elif op == T_LUT:
+            # boolean function of up to three 0/1 slots (one byte each in a); b = table | number of inputs << 8
+            idx = 0
+            for i in range(b >> 8):
+                v = slots[(a >> (8 * i)) & 0xFF]
+                assert v in (0, 1), "T_LUT input is not a 0/1 value"
+                idx |= v << i
+            slots[dst] = (b >> idx) & 1
         elif op == T_BITC:
             # bit b of the RAW (Montgomery) limbs of slot a
             assert slots[a] is not None
