@@ -253,6 +253,18 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 }
                 r[k] = unpack(lo, hi);
             }
+        } else if (op == tape::T_CADD) {
+            // a + (b != 0 ? constant c : 0)
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const Fr a = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
+                const Fr b = tape_operand<NS>(slots, consts, cur.z, false, tk[k]);
+                const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cur.w), __ldg(consts + 2 * (uint64_t)cur.w + 1));
+                const Fr sum = fr::add(a, c);
+                const bool t = !fr::is_zero(b);
+#pragma unroll
+                for (int i = 0; i < 8; i++) r[k].v[i] = t ? sum.v[i] : a.v[i];
+            }
         } else if (op == tape::T_LUT) {
             // boolean function of up to three 0/1 values: the low limb of a slot tells 0 from R mod q
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);

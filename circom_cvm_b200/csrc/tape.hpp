@@ -213,6 +213,26 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
             roots.emplace((uint32_t)i, std::move(f));
         }
     }
+    // acc + (bit ? constant : 0): an ADD (not part of a dot product) whose operand is a single-use select between a
+    // constant and 0 -- the `lin += in[k] * 2^k` of circomlib's Bits2Num / BinSum once 0/1 typing turned the product into
+    // a select.  cadd[i] = which operand (0: a, 1: b) is the select.
+    std::unordered_map<uint32_t, int> cadd;
+    if (enable) {
+        for (size_t i = 0; i < N; i++) {
+            if (!live[i] || absorbed[i] || ops[i].op != T_ADD || roots.count((uint32_t)i)) continue;
+            for (int k = 0; k < 2; k++) {
+                uint32_t r = k ? ops[i].b : ops[i].a;
+                if (r == NO_REF || (r & CONST_FLAG) || uses[r] != 1 || absorbed[r]) continue;
+                const SOp &sel = ops[r];
+                if (sel.op == T_SEL && !(sel.a & CONST_FLAG) && (sel.b & CONST_FLAG) && (sel.c & CONST_FLAG) &&
+                    fr::is_zero(tr.consts[sel.c & ~CONST_FLAG])) {
+                    absorbed[r] = 1;
+                    cadd.emplace((uint32_t)i, k);
+                    break;
+                }
+            }
+        }
+    }
     std::vector<uint32_t> remap(N, NO_REF);
     auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
     xp.ops.reserve(N);
@@ -221,6 +241,14 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
         const SOp &o = ops[i];
         auto it = roots.find((uint32_t)i);
         if (it == roots.end()) {
+            auto ca = cadd.find((uint32_t)i);
+            if (ca != cadd.end()) {   // acc + (bit ? constant : 0)
+                const SOp &sel = ops[ca->second ? o.b : o.a];
+                XOp x{T_CADD, mapref(ca->second ? o.a : o.b), mapref(sel.a), sel.b, 0};
+                xp.ops.push_back(x);
+                remap[i] = (uint32_t)xp.ops.size() - 1;
+                continue;
+            }
             XOp x{o.op, mapref(o.a), mapref(o.b), mapref(o.c), o.aux};
             xp.ops.push_back(x);
             remap[i] = (uint32_t)xp.ops.size() - 1;
@@ -502,7 +530,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
                 flags = (uint8_t)((flags & ~4u) | F_CZERO);
                 e2 = 0;
             }
-            if (w0 != NO_REF && (o.op != T_SEL || (flags & F_CZERO))) {   // the first wire of the value is written by the producing instruction
+            if (w0 != NO_REF && (o.op != T_SEL || (flags & F_CZERO)) && o.op != T_CADD) {   // the first wire of the value is written by the producing instruction
                 flags |= F_STORE;
                 e2 = w0;
                 out.stats.n_st++;
@@ -515,6 +543,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
                 case T_DIV: out.stats.n_div++; break;
                 case T_INV: out.stats.n_inv++; break;
                 case T_SEL: out.stats.n_sel++; break;
+                case T_CADD: out.stats.n_addsub++; break;
                 case T_ADD: case T_SUB: out.stats.n_addsub++; break;
                 case T_INPUT: out.stats.n_input++; break;
                 default: out.stats.n_other++; break;

@@ -38,6 +38,7 @@ enum TOp : uint8_t {
                  // (aux >> 8 = number of inputs).  Produced by the boolean-cone collapsing below.
     T_INV,       // a^-1, with 0^-1 := 0  (ff.div a b is traced as a * INV(b) so that independent inversions can be batched)
     // inserted by the tape builder
+    T_CADD,      // a + (b != 0 ? c : 0) with a constant c: the `acc += bit * 2^k` step of every bit-weighted sum (tape.hpp)
     T_DOT,       // sum_k c_k * x_k (+ addend): fused tree of additions of products by constants (tape.hpp fuse_dots)
     T_LD, T_ST, T_STC, T_COUNT
 };

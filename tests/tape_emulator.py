@@ -8,7 +8,7 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_DOT, T_LD, T_ST, T_STC) = range(34)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC) = range(35)
 F_ADDEND = 32        # T_DOT: field b is an addend
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
@@ -58,6 +58,11 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
             slots[dst] = acc % M.Q
         elif op == T_INPUT:
             slots[dst] = inputs[a] % M.Q
+        elif op == T_CADD:
+            # a + (b != 0 ? constant c : 0)
+            x = operand(a, 1)
+            assert slots[b] is not None
+            slots[dst] = (x + consts[c]) % M.Q if slots[b] != 0 else x
         elif op == T_LUT:
             # boolean function of up to three 0/1 slots (one byte each in a); b = table | number of inputs << 8
             idx = 0
@@ -114,6 +119,6 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
         else:
             raise ValueError("bad tape op %d" % op)
         if flags & F_STORE:
-            assert op not in (T_LD, T_ST, T_STC, T_FAIL_IF, T_FAIL_NE) and (op != T_SEL or flags & F_CZERO)
+            assert op not in (T_LD, T_ST, T_STC, T_FAIL_IF, T_FAIL_NE, T_CADD) and (op != T_SEL or flags & F_CZERO)
             rows[c] = slots[dst]
     return rows, status
