@@ -563,9 +563,17 @@ __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, ui
     ts.bstride = p.bstride;
     ts.ring = ring;
     ts.t_end = t_end;
-    Fr acc = fr::zero();
-    for (uint32_t t = hdr.x; t < end; t++) {
+    // first term: the value itself (most linear combinations of gate-level circuits are a single wire)
+    uint32_t t = hdr.x;
+    Fr acc;
+    {
         const uint32_t meta = __ldg(p.cmag + __ldg(p.terms + t).y);   // sign | k << 1: coefficient +-2^k, k <= 3
+        acc = ts.take(t);
+        for (uint32_t k = meta >> 1; k; k--) acc = fr::add(acc, acc);
+        if (meta & 1u) acc = fr::neg(acc);
+    }
+    for (t++; t < end; t++) {
+        const uint32_t meta = __ldg(p.cmag + __ldg(p.terms + t).y);
         Fr v = ts.take(t);
         for (uint32_t k = meta >> 1; k; k--) v = fr::add(v, v);
         acc = (meta & 1u) ? fr::sub(acc, v) : fr::add(acc, v);
