@@ -484,7 +484,7 @@ struct TermStream {
     __device__ __forceinline__ void issue(uint32_t t) const {
         if (t < t_end) {
             const uint2 term = __ldg(terms + t);
-            const uint4 *src = wbase + ((uint64_t)term.x * 2) * bstride;
+            const uint4 *src = wbase + ((uint64_t)(term.x & 0x0fffffffu) * 2) * bstride;   // top bits: +-2^k meta (r1cs.hpp)
             uint4 *dst = ring + (t % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
             const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
@@ -519,7 +519,7 @@ __device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const
     Fr acc = fr::zero();
     uint32_t t = hdr.x;
     for (; t < e0; t++) {
-        const uint32_t meta = __ldg(cmag + __ldg(terms + t).y);   // sign | k << 1: coefficient +-2^k, k <= 3
+        const uint32_t meta = __ldg(terms + t).x >> 28;   // sign | k << 1: coefficient +-2^k, k <= 3
         Fr v = ts.take(t);
         for (uint32_t k = meta >> 1; k; k--) v = fr::add(v, v);
         acc = (meta & 1u) ? fr::sub(acc, v) : fr::add(acc, v);
@@ -567,13 +567,13 @@ __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, ui
     uint32_t t = hdr.x;
     Fr acc;
     {
-        const uint32_t meta = __ldg(p.cmag + __ldg(p.terms + t).y);   // sign | k << 1: coefficient +-2^k, k <= 3
+        const uint32_t meta = __ldg(p.terms + t).x >> 28;   // sign | k << 1: coefficient +-2^k, k <= 3
         acc = ts.take(t);
         for (uint32_t k = meta >> 1; k; k--) acc = fr::add(acc, acc);
         if (meta & 1u) acc = fr::neg(acc);
     }
     for (t++; t < end; t++) {
-        const uint32_t meta = __ldg(p.cmag + __ldg(p.terms + t).y);
+        const uint32_t meta = __ldg(p.terms + t).x >> 28;
         Fr v = ts.take(t);
         for (uint32_t k = meta >> 1; k; k--) v = fr::add(v, v);
         acc = (meta & 1u) ? fr::sub(acc, v) : fr::add(acc, v);

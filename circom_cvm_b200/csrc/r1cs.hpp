@@ -166,6 +166,11 @@ inline File load(const std::string &path) {
         };
         std::stable_sort(b, e, [&](const Term &x, const Term &y) { return cls(x) < cls(y); });
         size_t n0 = cnt[0], n1 = use1 ? cnt[1] : 0, n2 = use2 ? cnt[2] : 0;
+        // the +-2^k terms carry their sign | k << 1 in the top four bits of the wire index (one load less per term)
+        for (auto it = b; it != b + (ptrdiff_t)n0; ++it) {
+            if (it->wire >> 28) throw Error("more than 2^28 wires");
+            it->wire |= out.cmag[it->coef] << 28;
+        }
         out.split[3 * j] = out.ptr[j] + (uint32_t)n0;
         out.split[3 * j + 1] = out.ptr[j] + (uint32_t)(n0 + n1);
         out.split[3 * j + 2] = out.ptr[j] + (uint32_t)(n0 + n1 + n2);
