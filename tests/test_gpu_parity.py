@@ -267,6 +267,12 @@ def test_process_abi_drop_in(E, name, doc, tmp_path):
     env = dict(os.environ, PYTHONPATH=ROOT)
     subprocess.run([sys.executable, "-m", "circom_cvm_b200", paths["cvm"], str(jin), str(out)], check=True, env=env,
                    cwd=ROOT, timeout=300)
+    # the native host program (csrc/calc_main.cpp) takes the same files
+    from circom_cvm_b200 import build as cbuild
+    cbuild.build()
+    nout = tmp_path / "native.wtns"
+    subprocess.run([cbuild.CALC, paths["cvm"], str(jin), str(nout)], check=True, timeout=300)
+    assert nout.read_bytes() == out.read_bytes()
     ref = os.path.join(ROOT, "oracle", "_ref", name)
     if os.path.exists(ref):
         rout = tmp_path / "ref.wtns"

@@ -70,3 +70,44 @@ def test_program_witness_list_through_the_abi(cvmlib):
     wc = E.WitnessCalculator(cvm_text=art.cvm)
     assert [int(x) for x in wc.witness_signals()] == list(art.witness)
     assert wc.n_outputs == art.n_outputs
+
+
+# ---- the native host program (csrc/calc_main.cpp): same input handling, in the reference's own language
+def _calc():
+    import os
+    from circom_cvm_b200 import build
+    build.build()
+    assert os.path.exists(build.CALC)
+    return build.CALC
+
+
+def test_native_calculator_input_errors_and_no_cpu_fallback(cvmlib, tmp_path):
+    import subprocess
+    from tools.circuitgen.build import write_artifact
+    exe = _calc()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
+    art = circuit("babyadd4")
+    paths = write_artifact(art, str(tmp_path), with_cpp=True)
+
+    def run(doc_text):
+        j = tmp_path / "in.json"
+        j.write_text(doc_text)
+        return subprocess.run([exe, paths["cvm"], str(j), str(tmp_path / "o.wtns")], capture_output=True, text=True, timeout=120)
+
+    for text, msg in (('{"p": ["1"], "q": ["1", "2"]}', "Not enough values"),
+                      ('{"p": ["1", "2", "3"], "q": ["1", "2"]}', "Too many values"),
+                      ('{"p": ["1", "2"], "q": ["1", "2"], "zz": "1"}', "Signal not found"),
+                      ('{"p": ["1", "2"]}', "Not all inputs have been set"),
+                      ('{"p": ["1", 2], "q": ["1", "2"]}', "Types are not the same"),
+                      ('{"p": ["0x1g", "2"], "q": ["1", "2"]}', "Invalid number"),
+                      ('{"p": ["1", "2"], "q": ["1", "2"]', "invalid JSON")):
+        r = run(text)
+        assert r.returncode == 1 and msg in r.stderr, (text, r.stderr)
+    # well-formed input: without a CUDA device the library refuses (no CPU fallback); with one the file is written
+    r = run('{"q": ["0x10", "0b11"], "p": ["7", "0o17"]}')
+    from circom_cvm_b200 import engine as E
+    if E.device_count() == 0:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
