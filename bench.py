@@ -32,6 +32,11 @@ WORKLOADS = {
                   "chunk": 1 << 20, "e2e_batch": 1 << 17, "bits": False, "ref": "poseidon2_bench"},
     "sha256_512": {"label": "Sha256(512 bits)", "module": "sha256", "fn": "Sha256", "args": (512,), "batch": 1 << 16,
                    "chunk": 1 << 16, "e2e_batch": 1 << 10, "bits": True, "ref": "sha256_512"},
+    # stand-in for the SCALE of config 5 (circom-ecdsa, ~1.5 M constraints, batch 1 K; the circuit itself is not built,
+    # DESIGN.md section 8): Sha256 over 44 blocks = 1.51 M constraints / 1.5 M wires, 1 024 inputs -- the large sparse check
+    # at a batch far too small to fill the GPU with one thread per witness.  Takes minutes to compile; never the default.
+    "sha256_44blocks": {"label": "Sha256(22 000 bits, 44 blocks)", "module": "sha256", "fn": "Sha256", "args": (22000,),
+                        "batch": 1 << 10, "chunk": 1 << 10, "e2e_batch": 1 << 5, "bits": True, "ref": "sha256_44blocks"},
     # config 4: valid signatures from the integer signer (tools/circuitgen/circuits/eddsa.py); a pool of distinct
     # signatures is tiled over the batch (signing in Python is slow; the instruction stream does not depend on the data)
     "eddsa": {"label": "EdDSAPoseidonVerifier", "module": "eddsa", "fn": "EdDSAPoseidonVerifier", "args": (),
