@@ -20,6 +20,7 @@
 
 static thread_local std::string g_err;
 static int g_tape_mode = 0;
+static int g_carveout = getenv("CVMGPU_CARVEOUT") ? atoi(getenv("CVMGPU_CARVEOUT")) : 100;
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -247,7 +248,7 @@ static int upload_program(cvmgpu_program *p) {
     const size_t per_w = tape_smem_per_witness(p);
 #define CVM_SET_ATTR(NT, W)                                                                                              \
     CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_w * NT * W))); \
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout));
     CVM_SET_ATTR(128, 1)
     CVM_SET_ATTR(64, 1)
     CVM_SET_ATTR(32, 1)
