@@ -458,6 +458,7 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
     info->nnz_small = r->file.nnz_small;
     info->macs = r->file.macs;
     info->n_quadratic = r->file.n_quadratic;
+    info->nnz_const = r->file.nnz_const;
     info->n_coefs = (uint32_t)r->file.coefs.size();
     return CVMGPU_OK;
 }

@@ -465,7 +465,7 @@ struct R1csParams {
 //   small +, small - [e0, e1), [e1, e2): integer sums with 32-bit scalars (8 multiply-accumulates per term), one
 //                    reduction per class (fr.cuh small_reduce)
 //   general          [e2, end): lazy-reduction dot product (64 multiply-accumulates per term, one Montgomery
-//                    reduction per <= 16 terms)
+//                    reduction per <= 16 terms); a general coefficient on wire 0 comes last and is added as is
 //
 // Operand stream.  The terms of a chunk of constraints are contiguous in the CSR (A, B, C of constraint c, then
 // c+1, ...) and their addresses do not depend on data, so every thread keeps R1CS_STAGES of its own witness's
@@ -539,8 +539,12 @@ __device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const
             acc = neg ? fr::sub(acc, sres) : fr::add(acc, sres);
         }
     }
-    while (t < end) {
-        const uint32_t n = min(end - t, 16u);
+    // a general coefficient on wire 0 (the constant 1) is the LC's last term, marked in bit 31: its value is the
+    // coefficient itself
+    const bool has_const = e2 < end && (__ldg(terms + end - 1).x >> 31);
+    const uint32_t gend = end - (has_const ? 1u : 0u);
+    while (t < gend) {
+        const uint32_t n = min(gend - t, 16u);
         fr::Wide T;
         fr::wide_zero(T);
         for (uint32_t k = 0; k < n; k++, t++) {
@@ -550,6 +554,11 @@ __device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const
             fr::wide_mac(T, c, v);
         }
         acc = fr::add(acc, fr::wide_reduce(T, n));
+    }
+    if (has_const) {
+        const uint32_t coef = __ldg(terms + t).y;
+        (void)ts.take(t);   // its slot of the operand stream
+        acc = fr::add(acc, unpack(__ldg(coefs + 2 * (uint64_t)coef), __ldg(coefs + 2 * (uint64_t)coef + 1)));
     }
     return acc;
 }

@@ -30,7 +30,10 @@ struct File {
     uint32_t n_wires = 0, n_pub_out = 0, n_pub_in = 0, n_prv_in = 0, n_constraints = 0;
     uint64_t n_labels = 0;
     std::vector<uint32_t> ptr;       // 3*n_constraints + 1 offsets into terms: LC k of constraint c at ptr[3c+k]
-    // per LC j, terms are ordered [+-1 | small positive | small negative | general]; split[3j+k] = end of class k.
+    // per LC j, terms are ordered [+-2^k | small positive | small negative | general | constant]; split[3j+k] = end of
+    // class k.  "constant": a general coefficient on wire 0 (the constant 1, r1cs_writer.rs wire numbering): the term's
+    // value is the coefficient itself, so the kernel adds it instead of multiplying (bit 31 of the wire word marks it;
+    // it is the last term of its LC).
     // "small": the coefficient c (positive) or q - c (negative) fits 32 bits; such terms cost 8 multiply-accumulates
     // instead of 64 (kernels.cuh lc_eval).  A class is only used when it has >= 4 members, else they count as general.
     std::vector<uint32_t> split;
@@ -38,7 +41,7 @@ struct File {
     std::vector<Term> terms;
     std::vector<fr::Fr> coefs;       // canonical
     std::vector<uint64_t> wire2label;
-    uint64_t nnz_pm1 = 0, nnz_small = 0;
+    uint64_t nnz_pm1 = 0, nnz_small = 0, nnz_const = 0;
     // what the check kernel executes per witness: 64 multiply-accumulates per general term + 72 per reduction of a dot
     // product (<= 16 terms), 8 per small term + 170 per small-class reduction, 136 per quadratic constraint
     uint64_t macs = 0, n_quadratic = 0, n_linear = 0;
@@ -90,6 +93,7 @@ inline File load(const std::string &path) {
     out.n_labels = u64(q + 16);
     out.n_constraints = u32(q + 24);
     if (have[4] || have[5]) throw Error("custom-gate sections are not supported");
+    if (out.n_wires >> 28) throw Error("more than 2^28 wires");   // the top four bits of a term's wire word carry its class
 
     std::unordered_map<fr::Fr, uint32_t, tape::FrHash, tape::FrEq> index;
     fr::Fr one = fr::zero();
@@ -161,14 +165,14 @@ inline File load(const std::string &path) {
         const bool use1 = cnt[1] >= 4, use2 = cnt[2] >= 4;
         auto cls = [&](const Term &t) -> int {
             int k = kind[t.coef];
-            if ((k == 1 && !use1) || (k == 2 && !use2)) return 3;
+            if ((k == 1 && !use1) || (k == 2 && !use2)) k = 3;
+            if (k == 3 && (t.wire & 0x0fffffffu) == 0) return 4;
             return k;
         };
         std::stable_sort(b, e, [&](const Term &x, const Term &y) { return cls(x) < cls(y); });
         size_t n0 = cnt[0], n1 = use1 ? cnt[1] : 0, n2 = use2 ? cnt[2] : 0;
         // the +-2^k terms carry their sign | k << 1 in the top four bits of the wire index (one load less per term)
         for (auto it = b; it != b + (ptrdiff_t)n0; ++it) {
-            if (it->wire >> 28) throw Error("more than 2^28 wires");
             it->wire |= out.cmag[it->coef] << 28;
         }
         out.split[3 * j] = out.ptr[j] + (uint32_t)n0;
@@ -176,6 +180,11 @@ inline File load(const std::string &path) {
         out.split[3 * j + 2] = out.ptr[j] + (uint32_t)(n0 + n1 + n2);
         out.nnz_small += n1 + n2;
         size_t n3 = (size_t)(e - b) - n0 - n1 - n2;
+        if (n3 && cls(*(e - 1)) == 4) {   // an LC is a map wire -> coefficient: at most one term on wire 0
+            (e - 1)->wire |= 0x80000000u;
+            n3--;
+            out.nnz_const++;
+        }
         out.macs += 8 * (n1 + n2) + 170 * ((n1 ? 1 : 0) + (n2 ? 1 : 0)) + 64 * n3 + 72 * ((n3 + 15) / 16);
     }
     for (uint32_t c = 0; c < out.n_constraints; c++) {
