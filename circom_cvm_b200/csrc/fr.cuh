@@ -380,97 +380,255 @@ __device__ __forceinline__ Fr mont_mul_wide(const Fr &a, const Fr &b) {
     return reduce_once(r);                  // T < 2q
 }
 
+// ---- carry-chained multiply-accumulate rows ----------------------------------------------------------------
+// ptxas fuses a  mad.lo.cc r[2k], x, y, r[2k] ; madc.hi.cc r[2k+1], x, y, r[2k+1]  pair into ONE
+// IMAD.WIDE.U32(.X) whose carry travels in a predicate: a 32x32->64 multiply-accumulate with carry-in and
+// carry-out is a single instruction when the 64-bit window is a register pair.  The products of limbs 0,2,4,6 of
+// an operand tile eight consecutive words, those of limbs 1,3,5,7 tile the eight words one position higher, so a
+// number is kept as TWO word arrays, T = E + 2^32 * O, and each row of a product is two 4-instruction chains.
+// (mont_mul_wide above - mul.wide + add chains on one array - needs 407 instructions per product; this form 190.)
+
+// acc[0..7] += (x0, x1, x2, x3) * y, x_k * y landing on acc[2k], acc[2k+1]; the carry out is counted in top
+__device__ __forceinline__ void mad4(uint32_t *acc, uint32_t &top, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+// the same when the sum is known to fit the eight words
+__device__ __forceinline__ void mad4_fit(uint32_t *acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+// low += pend (one word below acc's alignment); acc[0..7] += (x0..x3) * y + that carry; the sum fits
+__device__ __forceinline__ void mad4_pend(uint32_t *acc, uint32_t &low, uint32_t pend, uint32_t x0, uint32_t x1, uint32_t x2,
+                                          uint32_t x3, uint32_t y) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.u32 %7, %13, %14, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(low)
+        : "r"(pend), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+// acc[0..7] += (q0, q2, q4, q6) * m, carry out counted in top
+__device__ __forceinline__ void mad4_q_even(uint32_t *acc, uint32_t &top, uint32_t m) {
+    asm("mad.lo.cc.u32 %0, %9, 0xf0000001, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, 0xf0000001, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, 0x79b97091, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, 0x79b97091, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, 0x8181585d, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, 0x8181585d, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, 0xe131a029, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, 0xe131a029, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(m));
+}
+// acc[0..7] += (q1, q3, q5, q7) * m; the sum fits
+__device__ __forceinline__ void mad4_q_odd(uint32_t *acc, uint32_t m) {
+    asm("mad.lo.cc.u32 %0, %8, 0x43e1f593, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, 0x43e1f593, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, 0x2833e848, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, 0x2833e848, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, 0xb85045b6, %4;\n\t"
+        "madc.hi.cc.u32 %5, %8, 0xb85045b6, %5;\n\t"
+        "madc.lo.cc.u32 %6, %8, 0x30644e72, %6;\n\t"
+        "madc.hi.u32 %7, %8, 0x30644e72, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(m));
+}
+// low += pend; m = low * (-1/q); acc[0..7] += (q1, q3, q5, q7) * m + that carry (mul.lo leaves the carry flag alone)
+__device__ __forceinline__ uint32_t mad4_q_odd_pend(uint32_t *acc, uint32_t &low, uint32_t pend) {
+    uint32_t m;
+    asm("add.cc.u32 %8, %8, %10;\n\t"
+        "mul.lo.u32 %9, %8, 0xefffffff;\n\t"
+        "madc.lo.cc.u32 %0, %9, 0x43e1f593, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, 0x43e1f593, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, 0x2833e848, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, 0x2833e848, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, 0xb85045b6, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, 0xb85045b6, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, 0x30644e72, %6;\n\t"
+        "madc.hi.u32 %7, %9, 0x30644e72, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(low),
+          "=&r"(m)
+        : "r"(pend));
+    return m;
+}
+
+// Running value of a word-serial Montgomery pass: T = X + pend + 2^32 * Y, X aligned with word 0 (nine words),
+// Y with word 1 (eight words).  One pass step adds a row (for a product), makes word 0 vanish with m * q and
+// divides by 2^32.  T < 2^288 throughout (T < 2q before a step, the two rows add < 2^33 q), hence Y < 2^256
+// never carries out and X needs one overflow word.  The division is a renaming: the new X is Y, the new Y is
+// X[2..8], and X[1] - one word below the new Y - becomes "pend": it is added to the new X[0] at the start of the
+// next step, and that carry has exactly the weight of the new Y's first word, so it enters Y's next chain.
+struct MontAcc {
+    uint32_t x[9], y[8], pend;
+};
+__device__ __forceinline__ void mont_acc_zero(MontAcc &t) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) t.x[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.y[i] = 0;
+    t.pend = 0;
+}
+__device__ __forceinline__ void mont_acc_shift(MontAcc &t) {
+    const uint32_t p = t.x[1];
+    uint32_t ny[8];
+#pragma unroll
+    for (int i = 0; i < 7; i++) ny[i] = t.x[i + 2];
+    ny[7] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.x[i] = t.y[i];
+    t.x[8] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.y[i] = ny[i];
+    t.pend = p;
+}
+// T = (T + a * s + m * q) / 2^32
+__device__ __forceinline__ void mont_acc_step(MontAcc &t, const uint32_t *a, uint32_t s) {
+    mad4_pend(t.y, t.x[0], t.pend, a[1], a[3], a[5], a[7], s);
+    mad4(t.x, t.x[8], a[0], a[2], a[4], a[6], s);
+    const uint32_t m = t.x[0] * FR_NP0;
+    mad4_q_even(t.x, t.x[8], m);
+    mad4_q_odd(t.y, m);
+    mont_acc_shift(t);
+}
+// T = (T + m * q) / 2^32
+__device__ __forceinline__ void mont_acc_redc_step(MontAcc &t) {
+    const uint32_t m = mad4_q_odd_pend(t.y, t.x[0], t.pend);
+    mad4_q_even(t.x, t.x[8], m);
+    mont_acc_shift(t);
+}
+// the value as eight words (it is < 2^256 when the caller's bound says so)
+__device__ __forceinline__ Fr mont_acc_value(const MontAcc &t) {
+    Fr r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(t.x[0]), "r"(t.x[1]), "r"(t.x[2]), "r"(t.x[3]), "r"(t.x[4]), "r"(t.x[5]), "r"(t.x[6]), "r"(t.x[7]),
+          "r"(t.pend), "r"(t.y[0]), "r"(t.y[1]), "r"(t.y[2]), "r"(t.y[3]), "r"(t.y[4]), "r"(t.y[5]), "r"(t.y[6]));
+    return r;
+}
+
+// a * b / 2^256 mod q: 128 IMAD.WIDE + 8 IMAD + ~50 adds
+__device__ __forceinline__ Fr mont_mul_chain(const Fr &a, const Fr &b) {
+    MontAcc t;
+    mont_acc_zero(t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) mont_acc_step(t, a.v, b.v[i]);
+    return reduce_once(mont_acc_value(t));   // < 2q
+}
+
 // ---- lazy-reduction dot products ---------------------------------------------------------------------
 // sum_i c_i * v_i (all Montgomery) with ONE Montgomery reduction per <= 16 terms: each term costs the 64
 // multiply-accumulates of the plain 8x8 product instead of the 136 of a full Montgomery multiplication.
-// The 17-limb accumulator is updated row by row in place; the carry out of a row's 9-limb window goes to a
-// per-row overflow counter (weight 2^(32*(i+9))) that is folded in once, before the reduction.
-#define FR_ROW_ADDS_OVF                       \
-        "mov.b64 {el0, eh0}, e0;\n\t"         \
-        "mov.b64 {el1, eh1}, e1;\n\t"         \
-        "mov.b64 {el2, eh2}, e2;\n\t"         \
-        "mov.b64 {el3, eh3}, e3;\n\t"         \
-        "mov.b64 {ol0, oh0}, o0;\n\t"         \
-        "mov.b64 {ol1, oh1}, o1;\n\t"         \
-        "mov.b64 {ol2, oh2}, o2;\n\t"         \
-        "mov.b64 {ol3, oh3}, o3;\n\t"         \
-        "add.cc.u32 %0, %0, el0;\n\t"         \
-        "addc.cc.u32 %1, %1, eh0;\n\t"        \
-        "addc.cc.u32 %2, %2, el1;\n\t"        \
-        "addc.cc.u32 %3, %3, eh1;\n\t"        \
-        "addc.cc.u32 %4, %4, el2;\n\t"        \
-        "addc.cc.u32 %5, %5, eh2;\n\t"        \
-        "addc.cc.u32 %6, %6, el3;\n\t"        \
-        "addc.cc.u32 %7, %7, eh3;\n\t"        \
-        "addc.cc.u32 %8, %8, 0;\n\t"          \
-        "addc.u32 %9, %9, 0;\n\t"             \
-        "add.cc.u32 %1, %1, ol0;\n\t"         \
-        "addc.cc.u32 %2, %2, oh0;\n\t"        \
-        "addc.cc.u32 %3, %3, ol1;\n\t"        \
-        "addc.cc.u32 %4, %4, oh1;\n\t"        \
-        "addc.cc.u32 %5, %5, ol2;\n\t"        \
-        "addc.cc.u32 %6, %6, oh2;\n\t"        \
-        "addc.cc.u32 %7, %7, ol3;\n\t"        \
-        "addc.cc.u32 %8, %8, oh3;\n\t"        \
-        "addc.u32 %9, %9, 0;\n\t"
-// t[0..8] += x * y, carry out of t[8] counted in ovf
-__device__ __forceinline__ void mac_row_ovf(uint32_t *t, uint32_t &ovf, const uint32_t *x, uint32_t y) {
-    asm(
-        "{\n\t"
-        ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
-        ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
-        "mul.wide.u32 e0, %10, %18;\n\t"
-        "mul.wide.u32 o0, %11, %18;\n\t"
-        "mul.wide.u32 e1, %12, %18;\n\t"
-        "mul.wide.u32 o1, %13, %18;\n\t"
-        "mul.wide.u32 e2, %14, %18;\n\t"
-        "mul.wide.u32 o2, %15, %18;\n\t"
-        "mul.wide.u32 e3, %16, %18;\n\t"
-        "mul.wide.u32 o3, %17, %18;\n\t"
-        FR_ROW_ADDS_OVF
-        "}"
-        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(ovf)
-        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(y));
-}
-// t[0..8] += m * q, carry out of t[8] counted in ovf
-__device__ __forceinline__ void mac_row_q_ovf(uint32_t *t, uint32_t &ovf, uint32_t m) {
-    asm(
-        "{\n\t"
-        ".reg .u64 e0, e1, e2, e3, o0, o1, o2, o3;\n\t"
-        ".reg .u32 el0, eh0, el1, eh1, el2, eh2, el3, eh3, ol0, oh0, ol1, oh1, ol2, oh2, ol3, oh3;\n\t"
-        "mul.wide.u32 e0, %10, 0xf0000001;\n\t"
-        "mul.wide.u32 o0, %10, 0x43e1f593;\n\t"
-        "mul.wide.u32 e1, %10, 0x79b97091;\n\t"
-        "mul.wide.u32 o1, %10, 0x2833e848;\n\t"
-        "mul.wide.u32 e2, %10, 0x8181585d;\n\t"
-        "mul.wide.u32 o2, %10, 0xb85045b6;\n\t"
-        "mul.wide.u32 e3, %10, 0xe131a029;\n\t"
-        "mul.wide.u32 o3, %10, 0x30644e72;\n\t"
-        FR_ROW_ADDS_OVF
-        "}"
-        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(ovf)
-        : "r"(m));
-}
-
+// Accumulator T = E + 2^32 * O + counters: E holds the partial products c_j * v_i with i + j even (words 0..15), O those
+// with i + j odd (O[k] has the weight of word k + 1; words 1..14).  A row chain covers eight words of its array; its
+// carry out goes to a counter of that window (ce[k]: word 2k + 8, co[k]: word 2k + 9), folded in before the reduction.
 struct Wide {
-    uint32_t t[17];
-    uint32_t ovf[8];   // ovf[i] has the weight of t[i + 9]
+    uint32_t e[16], o[14];
+    uint32_t ce[5], co[4];
 };
 __device__ __forceinline__ void wide_zero(Wide &T) {
 #pragma unroll
-    for (int i = 0; i < 17; i++) T.t[i] = 0;
+    for (int i = 0; i < 16; i++) T.e[i] = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) T.ovf[i] = 0;
+    for (int i = 0; i < 14; i++) T.o[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) T.ce[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) T.co[i] = 0;
 }
 // T += c * v   (c, v < q; at most 16 terms between reductions so that T < 2^4 * q^2 < 2^512)
 __device__ __forceinline__ void wide_mac(Wide &T, const Fr &c, const Fr &v) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) mac_row_ovf(T.t + i, T.ovf[i], c.v, v.v[i]);
+    for (int i = 0; i < 8; i += 2) {
+        // row i (even): even limbs of c land on words i.., odd limbs on words i + 1..
+        mad4(T.e + i, T.ce[i / 2], c.v[0], c.v[2], c.v[4], c.v[6], v.v[i]);
+        mad4(T.o + i, T.co[i / 2], c.v[1], c.v[3], c.v[5], c.v[7], v.v[i]);
+        // row i + 1: even limbs on words i + 1.. (O), odd limbs on words i + 2.. (E)
+        mad4(T.o + i, T.co[i / 2], c.v[0], c.v[2], c.v[4], c.v[6], v.v[i + 1]);
+        mad4(T.e + i + 2, T.ce[i / 2 + 1], c.v[1], c.v[3], c.v[5], c.v[7], v.v[i + 1]);
+    }
 }
-// t[9..16] += ovf[0..7]
-__device__ __forceinline__ void wide_fold(Wide &T) {
-    asm(
-        "add.cc.u32 %0, %0, %8;\n\t"
+// Montgomery reduction of T = sum of n products (n <= 16): (T + m*q) / 2^256 < q * (n * q / 2^256 + 1)
+// with q / 2^256 < 0.19, so ceil(0.19 n) conditional subtractions finish (1 for n <= 5).
+__device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
+    // plain words: w[0..16] = E + (O << 32) + counters
+    uint32_t w[17];
+    w[0] = T.e[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, 0;"
+        : "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(w[8]), "=&r"(w[9]),
+          "=&r"(w[10]), "=&r"(w[11]), "=&r"(w[12]), "=&r"(w[13]), "=&r"(w[14]), "=&r"(w[15])
+        : "r"(T.e[1]), "r"(T.e[2]), "r"(T.e[3]), "r"(T.e[4]), "r"(T.e[5]), "r"(T.e[6]), "r"(T.e[7]), "r"(T.e[8]), "r"(T.e[9]),
+          "r"(T.e[10]), "r"(T.e[11]), "r"(T.e[12]), "r"(T.e[13]), "r"(T.e[14]), "r"(T.e[15]),
+          "r"(T.o[0]), "r"(T.o[1]), "r"(T.o[2]), "r"(T.o[3]), "r"(T.o[4]), "r"(T.o[5]), "r"(T.o[6]), "r"(T.o[7]), "r"(T.o[8]),
+          "r"(T.o[9]), "r"(T.o[10]), "r"(T.o[11]), "r"(T.o[12]), "r"(T.o[13]));
+    // (the carry out of word 15 is impossible here: E + (O << 32) alone is below the full sum < 2^512)
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, %17, 0;"
+        : "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "=r"(w[16])
+        : "r"(T.ce[0]), "r"(T.co[0]), "r"(T.ce[1]), "r"(T.co[1]), "r"(T.ce[2]), "r"(T.co[2]), "r"(T.ce[3]), "r"(T.co[3]), "r"(T.ce[4]));
+    // word-serial reduction of the low half; the high half is added to what is left
+    MontAcc t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.x[i] = w[i];
+    t.x[8] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.y[i] = 0;
+    t.pend = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) mont_acc_redc_step(t);
+    Fr r = mont_acc_value(t);   // (low + m*q) / 2^256 <= q
+    asm("add.cc.u32 %0, %0, %8;\n\t"
         "addc.cc.u32 %1, %1, %9;\n\t"
         "addc.cc.u32 %2, %2, %10;\n\t"
         "addc.cc.u32 %3, %3, %11;\n\t"
@@ -478,25 +636,9 @@ __device__ __forceinline__ void wide_fold(Wide &T) {
         "addc.cc.u32 %5, %5, %13;\n\t"
         "addc.cc.u32 %6, %6, %14;\n\t"
         "addc.u32 %7, %7, %15;"
-        : "+r"(T.t[9]), "+r"(T.t[10]), "+r"(T.t[11]), "+r"(T.t[12]), "+r"(T.t[13]), "+r"(T.t[14]), "+r"(T.t[15]), "+r"(T.t[16])
-        : "r"(T.ovf[0]), "r"(T.ovf[1]), "r"(T.ovf[2]), "r"(T.ovf[3]), "r"(T.ovf[4]), "r"(T.ovf[5]), "r"(T.ovf[6]), "r"(T.ovf[7]));
-#pragma unroll
-    for (int i = 0; i < 8; i++) T.ovf[i] = 0;
-}
-// Montgomery reduction of T = sum of n products (n <= 16): (T + m*q) / 2^256 < q * (n * q / 2^256 + 1)
-// with q / 2^256 < 0.19, so ceil(0.19 n) conditional subtractions finish (1 for n <= 5).
-__device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
-    wide_fold(T);
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t m = T.t[i] * FR_NP0;
-        mac_row_q_ovf(T.t + i, T.ovf[i], m);
-    }
-    wide_fold(T);
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = T.t[8 + i];
-    // T.t[16] == 0 (value < 4.03 q < 2^256)
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]));
+    // w[16] == 0 and no carry: the value is < 4.03 q < 2^256
     r = reduce_once(r);
     if (n_terms > 5) {
         r = reduce_once(r);
@@ -508,40 +650,49 @@ __device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
     return r;
 }
 // ---- small-scalar sums -----------------------------------------------------------------------------------
-// X = sum_k m_k * v_k with 32-bit scalars m_k is a plain integer (10 limbs, < 2^320); one CIOS pass with the
-// constant 2^320 mod q brings it back: sum_i X_i * C * 2^(32 i) / 2^320 = X (mod q), result < 2q.
+// X = sum_k m_k * v_k with 32-bit scalars m_k is a plain integer (10 limbs, < 2^320), kept as E + 2^32 * O + counters
+// like Wide; one word-serial Montgomery pass with the constant 2^320 mod q brings it back:
+// sum_i X_i * C * 2^(32 i) / 2^320 = X (mod q), result < 2q.
 struct Small {
-    uint32_t t[10];
+    uint32_t e[8], o[8], ce, co;
 };
 __device__ __forceinline__ void small_zero(Small &X) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) X.t[i] = 0;
+    for (int i = 0; i < 8; i++) X.e[i] = X.o[i] = 0;
+    X.ce = X.co = 0;
 }
-__device__ __forceinline__ void small_mac(Small &X, uint32_t m, const Fr &v) { mac_row_ovf(X.t, X.t[9], v.v, m); }
+__device__ __forceinline__ void small_mac(Small &X, uint32_t m, const Fr &v) {
+    mad4(X.e, X.ce, v.v[0], v.v[2], v.v[4], v.v[6], m);
+    mad4(X.o, X.co, v.v[1], v.v[3], v.v[5], v.v[7], m);
+}
 __device__ __forceinline__ Fr small_reduce(const Small &X) {
     const uint32_t C[8] = {0x7c5fb586u, 0xb4c6edf9u, 0xbfeb93beu, 0x708c8d50u, 0x04f7e0efu, 0x9ffd1de4u, 0x9a392866u, 0x215b02acu};
-    uint32_t t[9];
+    uint32_t w[10];
+    w[0] = X.e[0];
+    asm("add.cc.u32 %0, %9, %16;\n\t"
+        "addc.cc.u32 %1, %10, %17;\n\t"
+        "addc.cc.u32 %2, %11, %18;\n\t"
+        "addc.cc.u32 %3, %12, %19;\n\t"
+        "addc.cc.u32 %4, %13, %20;\n\t"
+        "addc.cc.u32 %5, %14, %21;\n\t"
+        "addc.cc.u32 %6, %15, %22;\n\t"
+        "addc.cc.u32 %7, %24, %23;\n\t"
+        "addc.u32 %8, %25, 0;"
+        : "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(w[8]), "=&r"(w[9])
+        : "r"(X.e[1]), "r"(X.e[2]), "r"(X.e[3]), "r"(X.e[4]), "r"(X.e[5]), "r"(X.e[6]), "r"(X.e[7]),
+          "r"(X.o[0]), "r"(X.o[1]), "r"(X.o[2]), "r"(X.o[3]), "r"(X.o[4]), "r"(X.o[5]), "r"(X.o[6]), "r"(X.o[7]),
+          "r"(X.ce), "r"(X.co));
+    MontAcc t;
+    mont_acc_zero(t);
 #pragma unroll
-    for (int i = 0; i < 9; i++) t[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-        mac_row(t, C, X.t[i]);
-        uint32_t m = t[0] * FR_NP0;
-        mac_row_q(t, m);
-#pragma unroll
-        for (int j = 0; j < 8; j++) t[j] = t[j + 1];
-        t[8] = 0;
-    }
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-    return reduce_once(r);
+    for (int i = 0; i < 10; i++) mont_acc_step(t, C, w[i]);
+    return reduce_once(mont_acc_value(t));
 }
 #endif
 
 FR_HD Fr mont_mul(const Fr &a, const Fr &b) {
 #if defined(__CUDA_ARCH__) && !defined(FR_PORTABLE_MUL)
-    return mont_mul_wide(a, b);
+    return mont_mul_chain(a, b);
 #else
     return mont_mul_portable(a, b);
 #endif

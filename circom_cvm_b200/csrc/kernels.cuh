@@ -756,6 +756,7 @@ __global__ void __launch_bounds__(128) mulbench_kernel(uint4 *out, uint32_t iter
     for (uint32_t i = 0; i < iters; i++) {
         if (VARIANT == 0) { x = fr::mont_mul_portable(x, y); z = fr::mont_mul_portable(z, y); }
         else if (VARIANT == 2) { x = fr::mont_mul_wide(x, y); x = fr::mont_mul_wide(x, z); }   // ONE dependent chain per thread
+        else if (VARIANT == 3) { x = fr::mont_mul_chain(x, y); x = fr::mont_mul_chain(x, z); }   // carry-chained rows, one chain
         else { x = fr::mont_mul_wide(x, y); z = fr::mont_mul_wide(z, y); }
     }
     Fr r = fr::add(x, z);
