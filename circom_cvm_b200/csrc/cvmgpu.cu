@@ -663,6 +663,7 @@ extern "C" int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms_ou
             case 4: kern::imad_kernel<4><<<blocks, 256>>>(d, iters, 12345u + rep); break;
             case 5: kern::imad_kernel<5><<<blocks, 256>>>(d, iters, 12345u + rep); break;
             case 7: kern::imad_kernel<7><<<blocks, 256>>>(d, iters, 12345u + rep); break;
+            case 8: kern::imad_kernel<8><<<blocks, 256>>>(d, iters, 12345u + rep); break;
             default: kern::imad_kernel<6><<<blocks, 256>>>(d, iters, 12345u + rep); break;
         }
         CUDA_TRY(cudaEventRecord(e1));
@@ -672,7 +673,7 @@ extern "C" int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms_ou
         if (rep > 0 && ms < best) best = ms;
     }
     CUDA_TRY(cudaGetLastError());
-    double macs = (double)blocks * 256.0 * iters * 8.0;
+    double macs = (double)blocks * 256.0 * iters * (kind == 8 ? 16.0 : 8.0);
     if (macs_per_second) *macs_per_second = macs / (best * 1e-3);
     if (ms_out) *ms_out = best;
     cudaEventDestroy(e0); cudaEventDestroy(e1);

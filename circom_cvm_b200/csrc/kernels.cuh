@@ -695,8 +695,26 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t *out, uint32_t iters
     uint32_t x = seed + threadIdx.x, y = seed * 3 + blockIdx.x;
     uint32_t a0 = x, a1 = x + 1, a2 = x + 2, a3 = x + 3, a4 = x + 4, a5 = x + 5, a6 = x + 6, a7 = x + 7;
     uint64_t d0 = x, d1 = x + 1, d2 = x + 2, d3 = x + 3, d4 = x + 4, d5 = x + 5, d6 = x + 6, d7 = x + 7;
+    uint32_t b0 = y, b1 = y + 1, b2 = y + 2, b3 = y + 3, b4 = y + 4, b5 = y + 5, b6 = y + 6, b7 = y + 7;
+    uint32_t c0 = x ^ y, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+    uint32_t e0 = x * y, e1 = e0 + 1, e2 = e0 + 2, e3 = e0 + 3, e4 = e0 + 4, e5 = e0 + 5, e6 = e0 + 6, e7 = e0 + 7;
     for (uint32_t i = 0; i < iters; i++) {
-        if (KIND == 0) {        // mad.lo + mad.hi pair = one 32x32->64 multiply-accumulate
+        if (KIND == 8) {        // the form the field arithmetic uses (fr.cuh mad4): mad.lo.cc / madc.hi.cc pairs with the SAME
+            // multiplicand on a register pair, which ptxas fuses into one IMAD.WIDE.U32.X each; four independent chains of
+            // four (16 units per iteration), multiplicands taken from another chain so that nothing is loop-invariant
+#define CHAIN(r0, r1, r2, r3, r4, r5, r6, r7, m0, m1, m2, m3)                                                              \
+            asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"                            \
+                         "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"                           \
+                         "madc.lo.cc.u32 %4, %10, %12, %4;\n\tmadc.hi.cc.u32 %5, %10, %12, %5;\n\t"                         \
+                         "madc.lo.cc.u32 %6, %11, %12, %6;\n\tmadc.hi.u32 %7, %11, %12, %7;"                                 \
+                         : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)                   \
+                         : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(y));
+            CHAIN(a0, a1, a2, a3, a4, a5, a6, a7, b0, b2, b4, b6)
+            CHAIN(b0, b1, b2, b3, b4, b5, b6, b7, c1, c3, c5, c7)
+            CHAIN(c0, c1, c2, c3, c4, c5, c6, c7, e0, e2, e4, e6)
+            CHAIN(e0, e1, e2, e3, e4, e5, e6, e7, a1, a3, a5, a7)
+#undef CHAIN
+        } else if (KIND == 0) {        // mad.lo + mad.hi pair = one 32x32->64 multiply-accumulate
 #define STEP(r) asm volatile("mad.lo.u32 %0, %0, %1, %0;\n\tmad.hi.u32 %0, %0, %1, %0;" : "+r"(r) : "r"(y));
             STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
 #undef STEP
@@ -742,7 +760,8 @@ __global__ void __launch_bounds__(256) imad_kernel(uint32_t *out, uint32_t iters
                 : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7) : "r"(y));
         }
     }
-    uint32_t acc = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ (uint32_t)(d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7) ^
+    uint32_t acc = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ b0 ^ b1 ^ b2 ^ b3 ^ b4 ^ b5 ^ b6 ^ b7 ^ c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^
+                   c7 ^ e0 ^ e1 ^ e2 ^ e3 ^ e4 ^ e5 ^ e6 ^ e7 ^ (uint32_t)(d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7) ^
                    (uint32_t)((d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7) >> 32);
     if (acc == 0x12345678u) out[0] = acc;   // keep the chains alive
 }

@@ -157,14 +157,16 @@ int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, 
 int cvmgpu_fr_host_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out);
 /* same operations executed by a CUDA kernel over n element pairs (device self-test of csrc/fr.cuh) */
 int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n);
-/* dependency-free integer-pipe micro-benchmark.  The returned rate counts 8 "units" per thread and iteration, where a
+/* dependency-free integer-pipe micro-benchmark.  The returned rate counts 8 (kind 8: 16) "units" per thread and iteration, where a
  * unit is: kind 0 one mad.lo+mad.hi pair, 1 one mad.wide.u32 (both = one 32x32->64 multiply-accumulate), 2 two mad.lo,
  * 3 two mad.hi, 4 two addc (carry chain), 5 two add, 6 two mad{c}.{lo,hi}.cc (carry chain on the multiply pipe),
- * 7 one mul.wide.u32 + one add (the zero-addend form the multiplier uses). */
+ * 7 one mul.wide.u32 + one add, 8 one fused mad.lo.cc/madc.hi.cc pair = IMAD.WIDE.U32.X with carry in and out (the form
+ * the field arithmetic uses). */
 int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms);
 /* register-resident Montgomery-multiplication throughput (no memory traffic): variant 0 = portable 64-bit CIOS,
  * 1 = mul.wide formulation with a second, warp-uniform chain (which ptxas runs on the uniform datapath), 2 = mul.wide
- * formulation, one dependent chain per thread (the figure that applies to per-witness arithmetic);
+ * formulation, one dependent chain per thread; 3 = carry-chained IMAD.WIDE rows, one dependent chain per thread (the
+ * multiplier the kernels use);
  * ctas_per_sm x 128 threads per SM. */
 int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_second);
 
