@@ -55,6 +55,7 @@ def circuit(name):
         "sum3cmp": (basic.Sum3Cmp, ()),
         "opszoo": (basic.OpsZoo, ()),
         "poseidon2": (poseidon.Poseidon, (2,)),
+        "widesums": (basic.WideSums, ()),
     }
     if name == "eddsa":
         from tools.circuitgen.circuits import eddsa

@@ -44,6 +44,23 @@ def test_device_mul_random_bulk(E):
             assert g == f(x, y), op
 
 
+def test_device_field_ops_extreme_pairs(E):
+    """All pairs of carry-stressing operands (all-ones limbs, q - small, powers of two) through the multiplier, the
+    adder chains and the inversion."""
+    top = (M.Q >> 224) - 1
+    pool = [M.Q - 1, M.Q - 2, (top << 224) | ((1 << 224) - 1), (1 << 253) - 1, (1 << 252) - 1, (1 << 224) - 1,
+            (1 << 32) - 1, (1 << 64) - 1, 0xffffffff00000000ffffffff00000000ffffffff00000000ffffffff, 1, 0, 2,
+            M.Q - (1 << 32), M.Q - (1 << 224), (M.Q - 1) // 2, (M.Q + 1) // 2, 1 << 253, (1 << 253) + (1 << 32) - 1]
+    pool += [pow(2, 256, M.Q), pow(2, 512, M.Q), M.Q - pow(2, 256, M.Q), pow(pow(2, 256, M.Q), -1, M.Q)]
+    a = [x for x in pool for _ in pool]
+    b = [y for _ in pool for y in pool]
+    for op in ("mul", "add", "sub", "div"):
+        got = E.fr_device_op(op, a, b)
+        f = M.BINOPS[op]
+        for x, y, g in zip(a, b, got):
+            assert g == f(x, y), (op, hex(x), hex(y))
+
+
 CASES = {
     "earlyret": [[5, 3], [M.Q - 5, 3], [3, 5], [1000, 7], [0, 0], [255, 1], [7, 1000], [M.Q - 1, M.Q - 2]],
     "nbits": [[0], [1], [255], [256], [1 << 253], [M.Q - 1]],
@@ -58,6 +75,8 @@ CASES = {
     "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
     "poseidon2": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],
+    "widesums": [[M.Q - 1] * 40, [(1 << 253) - 1] * 40, list(range(40)),
+                 [(M.Q - 1 - i) if i % 2 else ((1 << 224) - 1 + i) for i in range(40)]],
 }
 
 
@@ -158,14 +177,30 @@ def _write_r1cs(art, path):
                        n_labels=art.n_signals)
 
 
-@pytest.mark.parametrize("name", ["multiplier2", "lessthan8", "sum3cmp", "poseidon2", "num2bits8", "babyadd4"])
+def test_long_dot_products_with_many_slots(E):
+    """With 24 slots the tape fuses linear combinations of up to 16 terms into one lazy-reduction dot product (longer
+    ones are split): carry-stressing inputs against the oracle."""
+    art = circuit("widesums")
+    rng = random.Random(41)
+    rows = list(CASES["widesums"]) + [[rng.randrange(M.Q) for _ in range(40)] for _ in range(300)]
+    wc = E.WitnessCalculator(cvm_text=art.cvm, n_slots=24)
+    assert wc.info.tape_dot >= 6
+    wt, st = wc.calculate(rows)
+    assert not st.any()
+    got = E.le_to_ints(wt)
+    prog = I.load(art.cvm)
+    for b in list(range(8)) + [100, 303]:
+        assert got[b] == I.compute_witness(prog, rows[b]), b
+
+
+@pytest.mark.parametrize("name", ["multiplier2", "lessthan8", "sum3cmp", "poseidon2", "num2bits8", "babyadd4", "widesums"])
 def test_r1cs_check_accepts_valid_and_pinpoints_invalid(E, name, tmp_path):
     art = circuit(name)
     _write_r1cs(art, tmp_path / "c.r1cs")
     r = E.R1cs(str(tmp_path / "c.r1cs"))
     rng = random.Random(5)
     rows = [CASES[name][0]] * 3
-    if name in ("multiplier2", "poseidon2", "babyadd4"):
+    if name in ("multiplier2", "poseidon2", "babyadd4", "widesums"):
         rows += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(130)]
     wc = E.WitnessCalculator(cvm_text=art.cvm)
     wt, st = wc.calculate(rows)
@@ -416,3 +451,95 @@ def test_sha256_at_baseline_size(E, tmp_path):
         m = bytes(int("".join(str(int(x)) for x in msgs[k, 8 * j:8 * j + 8]), 2) for j in range(64))
         want = "".join(format(byte, "08b") for byte in hashlib.sha256(m).digest())
         assert "".join(str(int(x)) for x in digests[k]) == want, k
+
+
+def _extreme_values(rng):
+    """Field elements that stress carry propagation: all-ones limbs, q - small, powers of two."""
+    top = (M.Q >> 224) - 1
+    pool = [M.Q - 1, M.Q - 2, (top << 224) | ((1 << 224) - 1), (1 << 253) - 1, (1 << 252) - 1, (1 << 224) - 1,
+            (1 << 32) - 1, (1 << 64) - 1, 0xffffffff00000000ffffffff00000000ffffffff00000000ffffffff, 1, 0,
+            M.Q - (1 << 32), M.Q - (1 << 224), (M.Q - 1) // 2, (M.Q + 1) // 2]
+    return pool + [rng.randrange(M.Q) for _ in range(5)]
+
+
+@pytest.mark.gpu
+def test_r1cs_check_extreme_coefficients_and_values(E, tmp_path):
+    """Synthetic constraint system whose linear combinations hit every coefficient class with carry-stressing values:
+    16- and 17-term general dot products of (q-1)-like coefficients (the lazy accumulator's window-carry counters),
+    long runs of 32-bit coefficients of both signs (the small-scalar accumulator), +-2^k, and general constants on
+    wire 0.  The expected product wires come from Python integers."""
+    from circom_cvm_b200 import formats
+    rng = random.Random(77)
+    ext = _extreme_values(rng)
+    n_in = 48
+    cons = []
+
+    def lc_general(n, with_const):
+        lc = {1 + rng.randrange(n_in): ext[rng.randrange(len(ext) - 5)] or 5 for _ in range(n * 3)}
+        lc = dict(list(lc.items())[:n])
+        for k in list(lc):
+            if lc[k] in (0, 1, M.Q - 1) or lc[k] < (1 << 32) or M.Q - lc[k] < (1 << 32):
+                lc[k] = M.Q - 1 - (1 << 40) - k
+        if with_const:
+            lc[0] = M.Q - 12345678901234567890
+        return lc
+
+    def lc_small(n, sign):
+        out = {}
+        while len(out) < n:
+            c = rng.choice([(1 << 32) - 1, (1 << 32) - 2, 3, 5, 0x80000000, rng.randrange(9, 1 << 32)])
+            out[1 + rng.randrange(n_in)] = c if sign > 0 else M.Q - c
+        return out
+
+    def lc_pow2(n):
+        return {1 + rng.randrange(n_in): rng.choice([1, M.Q - 1, 2, M.Q - 2, 4, M.Q - 4, 8, M.Q - 8]) for _ in range(n)}
+
+    shapes = [
+        (lc_general(16, False), lc_general(17, True)),
+        (lc_general(33, True), lc_general(1, False)),
+        (lc_small(40, +1), lc_small(40, -1)),
+        ({**lc_small(6, +1), **lc_general(5, True)}, {**lc_pow2(7), **lc_small(9, -1)}),
+        ({**lc_pow2(5), **lc_general(16, False), **lc_small(4, 1)}, lc_pow2(1)),
+        ({0: M.Q - 7}, lc_general(3, True)),              # constant-only combination times a short dot product
+        (lc_general(2, True), {0: (1 << 200) + 9}),
+    ]
+    for a, b in shapes:
+        out_wire = 1 + n_in + len(cons)
+        cons.append((a, b, {out_wire: 1}))
+    # linear constraints: 0 = C with C = long mixed combination - its own value wire
+    for k in range(3):
+        out_wire = 1 + n_in + len(cons)
+        c = {**lc_general(16 + k, k == 1), **lc_small(7, -1), **lc_pow2(3)}
+        c[out_wire] = M.Q - 1
+        cons.append(({}, {}, c))
+    n_wires = 1 + n_in + len(cons)
+    path = tmp_path / "x.r1cs"
+    formats.write_r1cs(str(path), cons, n_wires, 0, 0, n_in, list(range(n_wires)))
+    r = E.R1cs(str(path))
+    info = r.info.asdict()
+    assert info["nnz_const"] >= 5 and info["nnz_small"] >= 80
+
+    ev = lambda lc, w: sum(v * w[k] for k, v in lc.items()) % M.Q
+    B = 96
+    rows = []
+    for b in range(B):
+        w = [1] + [ext[(b + 3 * i) % len(ext)] if (b + i) % 4 else rng.randrange(M.Q) for i in range(n_in)]
+        if b == 0:
+            w = [1] + [M.Q - 1] * n_in
+        w += [0] * len(cons)
+        for ci, (a, bb, c) in enumerate(cons):
+            ow = 1 + n_in + ci
+            if a:
+                w[ow] = ev(a, w) * ev(bb, w) % M.Q
+            else:
+                w[ow] = ev({k: v for k, v in c.items() if k != ow}, w)
+        rows.append(w)
+    wt = E.ints_to_le(rows, n_wires).reshape(B, n_wires, 32)
+    bad = r.check(wt)
+    assert (bad == E.NO_BAD).all(), bad
+    # every constraint must also be *violated* when its value wire is off by one (the check is not vacuous)
+    for ci in range(len(cons)):
+        wt2 = wt.copy()
+        wt2[:, 1 + n_in + ci, 0] ^= 1
+        bad = r.check(wt2)
+        assert (bad == ci).all(), (ci, bad[:8])

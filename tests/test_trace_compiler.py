@@ -23,6 +23,8 @@ CASES = {
     "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
     "poseidon2": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],
+    "widesums": [[M.Q - 1] * 40, [(1 << 253) - 1] * 40, list(range(40)),
+                 [(M.Q - 1 - i) if i % 2 else ((1 << 224) - 1 + i) for i in range(40)]],
 }
 
 

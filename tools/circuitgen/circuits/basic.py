@@ -227,3 +227,30 @@ def EarlyReturns(T):
     T.assign(out[2], t)
     T.set(t, T.call(FABS, a - b))
     T.assign(out[3], t + 1)
+
+
+WIDE_SUM_TERMS = (3, 6, 11, 16, 17, 33)
+
+
+def wide_sum_const(k, i):
+    """Deterministic full-size coefficients, several of them with long runs of one bits."""
+    q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    special = [q - 1, q - 2, (1 << 253) - 1, q - (1 << 224), (q - 1) // 2, (((q >> 224) - 1) << 224) | ((1 << 224) - 1)]
+    if (k + i) % 3 == 0:
+        return special[(k * 7 + i) % len(special)]
+    return pow(7 + k, 1000 + 37 * i, q)
+
+
+def WideSums(T):
+    """Linear combinations of 3..33 inputs with full-size constant coefficients (the shape of an MDS row, widened):
+    exercises fused dot products of every length, their multi-subtraction final reductions and splitting past 16 terms."""
+    inp = T.input("in", (40,))
+    out = T.output("out", (len(WIDE_SUM_TERMS),))
+    sq = T.output("sq")
+    for k, n in enumerate(WIDE_SUM_TERMS):
+        e = None
+        for i in range(n):
+            term = inp[(7 * k + i) % 40] * wide_sum_const(k, i)
+            e = term if e is None else e + term
+        T.bind(out[k], e)
+    T.bind(sq, out[3] * out[5])
