@@ -550,17 +550,47 @@ __device__ __forceinline__ Fr mont_mul_chain(const Fr &a, const Fr &b) {
 // sum_i c_i * v_i (all Montgomery) with ONE Montgomery reduction per <= 16 terms: each term costs the 64
 // multiply-accumulates of the plain 8x8 product instead of the 136 of a full Montgomery multiplication.
 // Accumulator T = E + 2^32 * O + counters: E holds the partial products c_j * v_i with i + j even (words 0..15), O those
-// with i + j odd (O[k] has the weight of word k + 1; words 1..14).  A row chain covers eight words of its array; its
-// carry out goes to a counter of that window (ce[k]: word 2k + 8, co[k]: word 2k + 9), folded in before the reduction.
+// with i + j odd (words 1..14).  A row chain covers eight words of its array; its carry out goes to a counter of that
+// window (ce[k]: word 2k + 8, co[k]: word 2k + 9), folded in before the reduction.
+// acc[0..3] (four 64-bit windows = eight words) += (x0, x1, x2, x3) * y, carry out counted in top.  The accumulator is
+// held as 64-bit registers so that it stays in aligned register pairs across loop iterations: with 32-bit variables
+// ptxas re-packs the pairs around every IMAD.WIDE of a loop-carried accumulator (one IMAD.MOV per word and term).
+__device__ __forceinline__ void mad4_pairs(uint64_t *acc, uint32_t &top, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+    asm("{\n\t"
+        ".reg .u32 l0, h0, l1, h1, l2, h2, l3, h3;\n\t"
+        "mov.b64 {l0, h0}, %0;\n\t"
+        "mov.b64 {l1, h1}, %1;\n\t"
+        "mov.b64 {l2, h2}, %2;\n\t"
+        "mov.b64 {l3, h3}, %3;\n\t"
+        "mad.lo.cc.u32 l0, %5, %9, l0;\n\t"
+        "madc.hi.cc.u32 h0, %5, %9, h0;\n\t"
+        "madc.lo.cc.u32 l1, %6, %9, l1;\n\t"
+        "madc.hi.cc.u32 h1, %6, %9, h1;\n\t"
+        "madc.lo.cc.u32 l2, %7, %9, l2;\n\t"
+        "madc.hi.cc.u32 h2, %7, %9, h2;\n\t"
+        "madc.lo.cc.u32 l3, %8, %9, l3;\n\t"
+        "madc.hi.cc.u32 h3, %8, %9, h3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mov.b64 %0, {l0, h0};\n\t"
+        "mov.b64 %1, {l1, h1};\n\t"
+        "mov.b64 %2, {l2, h2};\n\t"
+        "mov.b64 %3, {l3, h3};\n\t"
+        "}"
+        : "+l"(acc[0]), "+l"(acc[1]), "+l"(acc[2]), "+l"(acc[3]), "+r"(top)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+__device__ __forceinline__ uint32_t lo32(uint64_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi32(uint64_t v) { return (uint32_t)(v >> 32); }
+
 struct Wide {
-    uint32_t e[16], o[14];
+    uint64_t e[8], o[7];   // e[k] = words 2k, 2k+1;  o[k] = words 2k+1, 2k+2
     uint32_t ce[5], co[4];
 };
 __device__ __forceinline__ void wide_zero(Wide &T) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) T.e[i] = 0;
+    for (int i = 0; i < 8; i++) T.e[i] = 0;
 #pragma unroll
-    for (int i = 0; i < 14; i++) T.o[i] = 0;
+    for (int i = 0; i < 7; i++) T.o[i] = 0;
 #pragma unroll
     for (int i = 0; i < 5; i++) T.ce[i] = 0;
 #pragma unroll
@@ -569,13 +599,13 @@ __device__ __forceinline__ void wide_zero(Wide &T) {
 // T += c * v   (c, v < q; at most 16 terms between reductions so that T < 2^4 * q^2 < 2^512)
 __device__ __forceinline__ void wide_mac(Wide &T, const Fr &c, const Fr &v) {
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        // row i (even): even limbs of c land on words i.., odd limbs on words i + 1..
-        mad4(T.e + i, T.ce[i / 2], c.v[0], c.v[2], c.v[4], c.v[6], v.v[i]);
-        mad4(T.o + i, T.co[i / 2], c.v[1], c.v[3], c.v[5], c.v[7], v.v[i]);
-        // row i + 1: even limbs on words i + 1.. (O), odd limbs on words i + 2.. (E)
-        mad4(T.o + i, T.co[i / 2], c.v[0], c.v[2], c.v[4], c.v[6], v.v[i + 1]);
-        mad4(T.e + i + 2, T.ce[i / 2 + 1], c.v[1], c.v[3], c.v[5], c.v[7], v.v[i + 1]);
+    for (int i = 0; i < 4; i++) {
+        // row 2i: even limbs of c land on words 2i.., odd limbs on words 2i + 1..
+        mad4_pairs(T.e + i, T.ce[i], c.v[0], c.v[2], c.v[4], c.v[6], v.v[2 * i]);
+        mad4_pairs(T.o + i, T.co[i], c.v[1], c.v[3], c.v[5], c.v[7], v.v[2 * i]);
+        // row 2i + 1: even limbs on words 2i + 1.. (O), odd limbs on words 2i + 2.. (E)
+        mad4_pairs(T.o + i, T.co[i], c.v[0], c.v[2], c.v[4], c.v[6], v.v[2 * i + 1]);
+        mad4_pairs(T.e + i + 1, T.ce[i + 1], c.v[1], c.v[3], c.v[5], c.v[7], v.v[2 * i + 1]);
     }
 }
 // Montgomery reduction of T = sum of n products (n <= 16): (T + m*q) / 2^256 < q * (n * q / 2^256 + 1)
@@ -583,7 +613,7 @@ __device__ __forceinline__ void wide_mac(Wide &T, const Fr &c, const Fr &v) {
 __device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
     // plain words: w[0..16] = E + (O << 32) + counters
     uint32_t w[17];
-    w[0] = T.e[0];
+    w[0] = lo32(T.e[0]);
     asm("add.cc.u32 %0, %15, %30;\n\t"
         "addc.cc.u32 %1, %16, %31;\n\t"
         "addc.cc.u32 %2, %17, %32;\n\t"
@@ -601,10 +631,12 @@ __device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
         "addc.u32 %14, %29, 0;"
         : "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(w[8]), "=&r"(w[9]),
           "=&r"(w[10]), "=&r"(w[11]), "=&r"(w[12]), "=&r"(w[13]), "=&r"(w[14]), "=&r"(w[15])
-        : "r"(T.e[1]), "r"(T.e[2]), "r"(T.e[3]), "r"(T.e[4]), "r"(T.e[5]), "r"(T.e[6]), "r"(T.e[7]), "r"(T.e[8]), "r"(T.e[9]),
-          "r"(T.e[10]), "r"(T.e[11]), "r"(T.e[12]), "r"(T.e[13]), "r"(T.e[14]), "r"(T.e[15]),
-          "r"(T.o[0]), "r"(T.o[1]), "r"(T.o[2]), "r"(T.o[3]), "r"(T.o[4]), "r"(T.o[5]), "r"(T.o[6]), "r"(T.o[7]), "r"(T.o[8]),
-          "r"(T.o[9]), "r"(T.o[10]), "r"(T.o[11]), "r"(T.o[12]), "r"(T.o[13]));
+        : "r"(hi32(T.e[0])), "r"(lo32(T.e[1])), "r"(hi32(T.e[1])), "r"(lo32(T.e[2])), "r"(hi32(T.e[2])), "r"(lo32(T.e[3])),
+          "r"(hi32(T.e[3])), "r"(lo32(T.e[4])), "r"(hi32(T.e[4])), "r"(lo32(T.e[5])), "r"(hi32(T.e[5])), "r"(lo32(T.e[6])),
+          "r"(hi32(T.e[6])), "r"(lo32(T.e[7])), "r"(hi32(T.e[7])),
+          "r"(lo32(T.o[0])), "r"(hi32(T.o[0])), "r"(lo32(T.o[1])), "r"(hi32(T.o[1])), "r"(lo32(T.o[2])), "r"(hi32(T.o[2])),
+          "r"(lo32(T.o[3])), "r"(hi32(T.o[3])), "r"(lo32(T.o[4])), "r"(hi32(T.o[4])), "r"(lo32(T.o[5])), "r"(hi32(T.o[5])),
+          "r"(lo32(T.o[6])), "r"(hi32(T.o[6])));
     // (the carry out of word 15 is impossible here: E + (O << 32) alone is below the full sum < 2^512)
     asm("add.cc.u32 %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, %10;\n\t"
@@ -654,21 +686,22 @@ __device__ __forceinline__ Fr wide_reduce(Wide &T, uint32_t n_terms) {
 // like Wide; one word-serial Montgomery pass with the constant 2^320 mod q brings it back:
 // sum_i X_i * C * 2^(32 i) / 2^320 = X (mod q), result < 2q.
 struct Small {
-    uint32_t e[8], o[8], ce, co;
+    uint64_t e[4], o[4];
+    uint32_t ce, co;
 };
 __device__ __forceinline__ void small_zero(Small &X) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) X.e[i] = X.o[i] = 0;
+    for (int i = 0; i < 4; i++) X.e[i] = X.o[i] = 0;
     X.ce = X.co = 0;
 }
 __device__ __forceinline__ void small_mac(Small &X, uint32_t m, const Fr &v) {
-    mad4(X.e, X.ce, v.v[0], v.v[2], v.v[4], v.v[6], m);
-    mad4(X.o, X.co, v.v[1], v.v[3], v.v[5], v.v[7], m);
+    mad4_pairs(X.e, X.ce, v.v[0], v.v[2], v.v[4], v.v[6], m);
+    mad4_pairs(X.o, X.co, v.v[1], v.v[3], v.v[5], v.v[7], m);
 }
 __device__ __forceinline__ Fr small_reduce(const Small &X) {
     const uint32_t C[8] = {0x7c5fb586u, 0xb4c6edf9u, 0xbfeb93beu, 0x708c8d50u, 0x04f7e0efu, 0x9ffd1de4u, 0x9a392866u, 0x215b02acu};
     uint32_t w[10];
-    w[0] = X.e[0];
+    w[0] = lo32(X.e[0]);
     asm("add.cc.u32 %0, %9, %16;\n\t"
         "addc.cc.u32 %1, %10, %17;\n\t"
         "addc.cc.u32 %2, %11, %18;\n\t"
@@ -679,8 +712,10 @@ __device__ __forceinline__ Fr small_reduce(const Small &X) {
         "addc.cc.u32 %7, %24, %23;\n\t"
         "addc.u32 %8, %25, 0;"
         : "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(w[8]), "=&r"(w[9])
-        : "r"(X.e[1]), "r"(X.e[2]), "r"(X.e[3]), "r"(X.e[4]), "r"(X.e[5]), "r"(X.e[6]), "r"(X.e[7]),
-          "r"(X.o[0]), "r"(X.o[1]), "r"(X.o[2]), "r"(X.o[3]), "r"(X.o[4]), "r"(X.o[5]), "r"(X.o[6]), "r"(X.o[7]),
+        : "r"(hi32(X.e[0])), "r"(lo32(X.e[1])), "r"(hi32(X.e[1])), "r"(lo32(X.e[2])), "r"(hi32(X.e[2])), "r"(lo32(X.e[3])),
+          "r"(hi32(X.e[3])),
+          "r"(lo32(X.o[0])), "r"(hi32(X.o[0])), "r"(lo32(X.o[1])), "r"(hi32(X.o[1])), "r"(lo32(X.o[2])), "r"(hi32(X.o[2])),
+          "r"(lo32(X.o[3])), "r"(hi32(X.o[3])),
           "r"(X.ce), "r"(X.co));
     MontAcc t;
     mont_acc_zero(t);
