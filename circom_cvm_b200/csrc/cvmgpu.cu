@@ -268,6 +268,7 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     if (!p || !d_store || (!d_inputs && p->n_inputs)) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
     if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
+    if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
     if (int rc = upload_program(p)) return rc;
     kern::TapeParams tp;
     tp.tape = (const tape::TapeIns *)p->d_tape.p;
@@ -507,6 +508,8 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
                                      void *stream) {
     if (!r || !d_store || !d_first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
+    if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
+    if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
     if (int rc = upload_r1cs(r)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(d_first_bad, 0xff, B * 4, s));

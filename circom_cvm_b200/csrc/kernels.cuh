@@ -18,6 +18,13 @@
 
 namespace kern {
 
+// Address of row r of one witness's column: rows are 2 * bstride uint4 apart; the host guarantees bstride < 2^27 so that the
+// byte stride fits 32 bits and the address is ONE IMAD.WIDE.U32 (row * stride + base) instead of a 64-bit multiply.
+__device__ __forceinline__ uint4 *row_ptr(const uint4 *wbase, uint32_t row, uint64_t bstride) {
+    const uint32_t row_bytes = (uint32_t)bstride * 32u;
+    return (uint4 *)((char *)wbase + (uint64_t)row * row_bytes);
+}
+
 using fr::Fr;
 
 #define CVM_NT 128   // threads (= witnesses) per CTA of the tape kernel for large batches (64 / 32 for small ones)
@@ -317,14 +324,14 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                     lo = ring[tk[k]];
                     hi = ring[NS + tk[k]];
                 } else {
-                    const uint4 *src = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                    const uint4 *src = row_ptr(wbase[k], cur.w, bstride);
                     lo = src[0];
                     hi = src[bstride];
                 }
                 slots[(dst * 2) * NS + tk[k]] = lo;
                 slots[(dst * 2 + 1) * NS + tk[k]] = hi;
                 if (cur.y != tape::NO_ROW) {
-                    const uint4 *nxt = wbase[k] + ((uint64_t)cur.y * 2) * bstride;
+                    const uint4 *nxt = row_ptr(wbase[k], cur.y, bstride);
                     const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ring + tk[k]);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(nxt) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + NS * 16), "l"(nxt + bstride) : "memory");
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
                 else { lo = slots[(cur.y * 2) * NS + tk[k]]; hi = slots[(cur.y * 2 + 1) * NS + tk[k]]; }
                 if (active[k]) {
-                    uint4 *d = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                    uint4 *d = row_ptr(wbase[k], cur.w, bstride);
                     d[0] = lo;
                     d[bstride] = hi;
                 }
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             for (int k = 0; k < W; k++) {
                 status[k] = tape_slow_op<NS>(cur, slots, consts, p.inputs, p.n_inputs, w[k], status[k], tk[k]);
                 if ((flags & tape::F_STORE) && active[k]) {
-                    uint4 *d = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                    uint4 *d = row_ptr(wbase[k], cur.w, bstride);
                     d[0] = slots[(dst * 2) * NS + tk[k]];
                     d[bstride] = slots[(dst * 2 + 1) * NS + tk[k]];
                 }
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             slots[(dst * 2) * NS + tk[k]] = lo;
             slots[(dst * 2 + 1) * NS + tk[k]] = hi;
             if ((flags & tape::F_STORE) && active[k]) {
-                uint4 *d = wbase[k] + ((uint64_t)cur.w * 2) * bstride;
+                uint4 *d = row_ptr(wbase[k], cur.w, bstride);
                 d[0] = lo;
                 d[bstride] = hi;
             }

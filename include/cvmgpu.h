@@ -122,7 +122,7 @@ int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_
 
 /* DEVICE buffers on the current device.
  *   d_inputs  B x n_inputs x 32 B, as above
- *   d_store   value store, n_rows x 2 x bstride x 16 B: row r, half h, witness w at ((r*2+h)*bstride + w)*16;
+ *   d_store   value store, n_rows x 2 x bstride x 16 B: row r, half h, witness w at ((r*2+h)*bstride + w)*16; B <= bstride < 2^27;
  *             Montgomery form; rows [0, n_wires) are the witness wires
  *   d_status  B words
  * stream: a cudaStream_t (0 = default stream). */
