@@ -20,6 +20,7 @@
 
 static thread_local std::string g_err;
 static int g_tape_mode = 0;
+static int g_r1cs_minb = getenv("CVMGPU_R1CS_MINB") ? atoi(getenv("CVMGPU_R1CS_MINB")) : 0;   // 0 = by circuit
 static int g_carveout = getenv("CVMGPU_CARVEOUT") ? atoi(getenv("CVMGPU_CARVEOUT")) : 100;
 
 static int fail(int code, const std::string &msg) {
@@ -536,7 +537,11 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     rp.B = B;
     rp.first_bad = (uint32_t *)d_first_bad;
     dim3 grid((unsigned)gx, (unsigned)chunks);
-    kern::r1cs_kernel<<<grid, R1CS_NT, 0, s>>>(rp);
+    // resident CTAs per SM: 4 (128 registers) when the check is multiplier-bound, 5 (96 registers) when it is mostly +-1 /
+    // small coefficients and latency-bound (measured: Poseidon 17.9 vs 18.1 ms, Sha256(512) 112.9 vs 109.7 ms)
+    int minb = g_r1cs_minb ? g_r1cs_minb : (r->file.macs > 16 * (uint64_t)r->file.terms.size() ? 4 : 5);
+    if (minb == 5) kern::r1cs_kernel<5><<<grid, R1CS_NT, 0, s>>>(rp);
+    else kern::r1cs_kernel<4><<<grid, R1CS_NT, 0, s>>>(rp);
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }

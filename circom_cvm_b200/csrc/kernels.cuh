@@ -597,7 +597,8 @@ __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, ui
     return acc;
 }
 
-__global__ void __launch_bounds__(R1CS_NT, 4) r1cs_kernel(R1csParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     __shared__ uint4 ring[R1CS_STAGES * 2 * R1CS_NT];
     uint64_t w = (uint64_t)blockIdx.x * R1CS_NT + threadIdx.x;
     const bool active = w < p.B;
