@@ -633,6 +633,7 @@ extern "C" int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_se
         if (variant == 0) kern::mulbench_kernel<0><<<blocks, 128>>>(d, iters, 7u + rep);
         else if (variant == 2) kern::mulbench_kernel<2><<<blocks, 128>>>(d, iters, 7u + rep);
         else if (variant == 3) kern::mulbench_kernel<3><<<blocks, 128>>>(d, iters, 7u + rep);
+        else if (variant == 4) kern::mulbench_kernel<4><<<blocks, 128>>>(d, iters, 7u + rep);
         else kern::mulbench_kernel<1><<<blocks, 128>>>(d, iters, 7u + rep);
         CUDA_TRY(cudaEventRecord(e1));
         CUDA_TRY(cudaEventSynchronize(e1));

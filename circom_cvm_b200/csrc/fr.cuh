@@ -546,6 +546,190 @@ __device__ __forceinline__ Fr mont_mul_chain(const Fr &a, const Fr &b) {
     return reduce_once(mont_acc_value(t));   // < 2q
 }
 
+// ---- squaring: 36 + 64 multiply-accumulates instead of 128 --------------------------------------------------------
+// a^2 = sum_i a_i 2^(32 i) * (a_i 2^(32 i) + 2 * sum_{j > i} a_j 2^(32 j)): row i of the word-serial pass multiplies a_i
+// by the words (a_i, 2 a_{i+1} mod 2^32, limbs i+2.. of the number 2a) at positions i..7 of the running value, so the rows
+// get shorter instead of repeating the symmetric products.  The running value is bounded by 3.01 q before a row (< 2^288
+// after it), so MontAcc's word counts hold; the final value (a^2 + M q) / 2^256 is < 2q like a product's.
+// >>> GENERATED by tools/gen_sqr_rows.py (one asm statement per carry chain; do not edit by hand)
+__device__ __forceinline__ void sqr_row_0(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.u32 %7, %13, %14, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"((a[1] << 1)), "r"(d[3]), "r"(d[5]), "r"(d[7]), "r"(a[0]));
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"(a[0]), "r"(d[2]), "r"(d[4]), "r"(d[6]), "r"(a[0]));
+}
+__device__ __forceinline__ void sqr_row_1(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.u32 %7, %13, %14, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"(a[1]), "r"(d[3]), "r"(d[5]), "r"(d[7]), "r"(a[1]));
+    asm("mad.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"((a[2] << 1)), "r"(d[4]), "r"(d[6]), "r"(a[1]));
+}
+__device__ __forceinline__ void sqr_row_2(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.u32 %7, %12, %13, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"((a[3] << 1)), "r"(d[5]), "r"(d[7]), "r"(a[2]));
+    asm("mad.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"(a[2]), "r"(d[4]), "r"(d[6]), "r"(a[2]));
+}
+__device__ __forceinline__ void sqr_row_3(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.u32 %7, %12, %13, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"(a[3]), "r"(d[5]), "r"(d[7]), "r"(a[3]));
+    asm("mad.lo.cc.u32 %4, %9, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %10, %11, %6;\n\t"
+        "madc.hi.cc.u32 %7, %10, %11, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"((a[4] << 1)), "r"(d[6]), "r"(a[3]));
+}
+__device__ __forceinline__ void sqr_row_4(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"((a[5] << 1)), "r"(d[7]), "r"(a[4]));
+    asm("mad.lo.cc.u32 %4, %9, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %10, %11, %6;\n\t"
+        "madc.hi.cc.u32 %7, %10, %11, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"(a[4]), "r"(d[6]), "r"(a[4]));
+}
+__device__ __forceinline__ void sqr_row_5(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"(a[5]), "r"(d[7]), "r"(a[5]));
+    asm("mad.lo.cc.u32 %6, %9, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"((a[6] << 1)), "r"(a[5]));
+}
+__device__ __forceinline__ void sqr_row_6(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "madc.lo.cc.u32 %6, %10, %11, %6;\n\t"
+        "madc.hi.u32 %7, %10, %11, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"((a[7] << 1)), "r"(a[6]));
+    asm("mad.lo.cc.u32 %6, %9, %10, %6;\n\t"
+        "madc.hi.cc.u32 %7, %9, %10, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(t.x[0]), "+r"(t.x[1]), "+r"(t.x[2]), "+r"(t.x[3]), "+r"(t.x[4]), "+r"(t.x[5]), "+r"(t.x[6]), "+r"(t.x[7]), "+r"(t.x[8])
+        : "r"(a[6]), "r"(a[6]));
+}
+__device__ __forceinline__ void sqr_row_7(MontAcc &t, const uint32_t *a, const uint32_t *d) {
+    asm("add.cc.u32 %8, %8, %9;\n\t"
+        "addc.cc.u32 %0, %0, 0;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "madc.lo.cc.u32 %6, %10, %11, %6;\n\t"
+        "madc.hi.u32 %7, %10, %11, %7;"
+        : "+r"(t.y[0]), "+r"(t.y[1]), "+r"(t.y[2]), "+r"(t.y[3]), "+r"(t.y[4]), "+r"(t.y[5]), "+r"(t.y[6]), "+r"(t.y[7]), "+r"(t.x[0])
+        : "r"(t.pend), "r"(a[7]), "r"(a[7]));
+}
+// <<< GENERATED
+__device__ __forceinline__ Fr mont_sqr_chain(const Fr &a) {
+    uint32_t d[8];   // limbs of 2a (a < 2^254: no ninth limb)
+    d[0] = a.v[0] << 1;
+#pragma unroll
+    for (int j = 1; j < 8; j++) d[j] = __funnelshift_l(a.v[j - 1], a.v[j], 1);
+    MontAcc t;
+    mont_acc_zero(t);
+#define FR_SQR_STEP(i)                                  \
+    sqr_row_##i(t, a.v, d);                             \
+    {                                                   \
+        const uint32_t m = t.x[0] * FR_NP0;             \
+        mad4_q_even(t.x, t.x[8], m);                    \
+        mad4_q_odd(t.y, m);                             \
+        mont_acc_shift(t);                              \
+    }
+    FR_SQR_STEP(0) FR_SQR_STEP(1) FR_SQR_STEP(2) FR_SQR_STEP(3) FR_SQR_STEP(4) FR_SQR_STEP(5) FR_SQR_STEP(6) FR_SQR_STEP(7)
+#undef FR_SQR_STEP
+    return reduce_once(mont_acc_value(t));
+}
+
 // ---- lazy-reduction dot products ---------------------------------------------------------------------
 // sum_i c_i * v_i (all Montgomery) with ONE Montgomery reduction per <= 16 terms: each term costs the 64
 // multiply-accumulates of the plain 8x8 product instead of the 136 of a full Montgomery multiplication.
@@ -732,7 +916,14 @@ FR_HD Fr mont_mul(const Fr &a, const Fr &b) {
     return mont_mul_portable(a, b);
 #endif
 }
-FR_HD Fr mont_sqr(const Fr &a) { return mont_mul(a, a); }  // the reference's rawMSquare also just multiplies (fr.cpp:166-169)
+// (the reference's rawMSquare just multiplies, fr.cpp:166-169; the result is the same number)
+FR_HD Fr mont_sqr(const Fr &a) {
+#if defined(__CUDA_ARCH__) && !defined(FR_PORTABLE_MUL)
+    return mont_sqr_chain(a);
+#else
+    return mont_mul(a, a);
+#endif
+}
 
 // canonical <-> Montgomery (generic/fr.cpp:211-255)
 FR_HD Fr to_mont(const Fr &a) { return mont_mul(a, r2_mont()); }

@@ -211,8 +211,14 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                     }
                 }
                 if (!cheap) {
+                    // same operand twice (x^2, x^4 of an S-box): the squaring needs 100 instead of 128 IMAD.WIDE
+                    if (cur.y == cur.z && (flags & 3u) == 0) {
 #pragma unroll
-                    for (int k = 0; k < W; k++) r[k] = fr::mont_mul(a[k], b[k]);
+                        for (int k = 0; k < W; k++) r[k] = fr::mont_sqr(a[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < W; k++) r[k] = fr::mont_mul(a[k], b[k]);
+                    }
                 }
             } else if (op == tape::T_ADD) {
 #pragma unroll
@@ -636,6 +642,7 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
             else if (sb.v[0] == one.v[0] && fr::equal(sb, one)) prod = sa;
             else if (sa.v[0] == mone.v[0] && fr::equal(sa, mone)) prod = fr::neg(sb);
             else if (sb.v[0] == mone.v[0] && fr::equal(sb, mone)) prod = fr::neg(sa);
+            else if (sa.v[0] == sb.v[0] && fr::equal(sa, sb)) prod = fr::mont_sqr(sa);   // S-box squarings: A and B are the same combination
             else prod = fr::mont_mul(sa, sb);
         } else {
             // the terms of a lone A or B still occupy the stream: consume them
@@ -784,6 +791,7 @@ __global__ void __launch_bounds__(128) mulbench_kernel(uint4 *out, uint32_t iter
         if (VARIANT == 0) { x = fr::mont_mul_portable(x, y); z = fr::mont_mul_portable(z, y); }
         else if (VARIANT == 2) { x = fr::mont_mul_wide(x, y); x = fr::mont_mul_wide(x, z); }   // ONE dependent chain per thread
         else if (VARIANT == 3) { x = fr::mont_mul_chain(x, y); x = fr::mont_mul_chain(x, z); }   // carry-chained rows, one chain
+        else if (VARIANT == 4) { x = fr::mont_sqr_chain(x); x = fr::mont_sqr_chain(x); }          // squarings
         else { x = fr::mont_mul_wide(x, y); z = fr::mont_mul_wide(z, y); }
     }
     Fr r = fr::add(x, z);

@@ -166,7 +166,7 @@ int cvmgpu_imad_peak(int kind, double *macs_per_second, double *ms);
 /* register-resident Montgomery-multiplication throughput (no memory traffic): variant 0 = portable 64-bit CIOS,
  * 1 = mul.wide formulation with a second, warp-uniform chain (which ptxas runs on the uniform datapath), 2 = mul.wide
  * formulation, one dependent chain per thread; 3 = carry-chained IMAD.WIDE rows, one dependent chain per thread (the
- * multiplier the kernels use);
+ * multiplier the kernels use), 4 = the squaring (100 instead of 128 IMAD.WIDE);
  * ctas_per_sm x 128 threads per SM. */
 int cvmgpu_mul_peak(int variant, int ctas_per_sm, double *muls_per_second);
 

@@ -59,6 +59,10 @@ def test_cpp_r1cs_loader_agrees(cvmlib, tmp_path):
     pm1 = sum(1 for c in art.constraints for lc in c for v in lc.values() if v in (1, Q - 1))
     assert info["nnz_pm1"] == pm1
     assert info["n_labels"] == art.n_signals
+    # coefficient classes of the check kernel: full-size coefficients on wire 0 (the constant 1) are added, not multiplied
+    small = lambda v: v < (1 << 32) or Q - v < (1 << 32)
+    assert info["nnz_const"] == sum(1 for c in art.constraints for lc in c for w, v in lc.items() if w == 0 and not small(v))
+    assert info["n_quadratic"] == sum(1 for a, b, _ in art.constraints if a and b)
 
 
 def test_doc_example_constraint_convention():

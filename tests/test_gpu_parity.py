@@ -52,6 +52,10 @@ def test_device_field_ops_extreme_pairs(E):
             (1 << 32) - 1, (1 << 64) - 1, 0xffffffff00000000ffffffff00000000ffffffff00000000ffffffff, 1, 0, 2,
             M.Q - (1 << 32), M.Q - (1 << 224), (M.Q - 1) // 2, (M.Q + 1) // 2, 1 << 253, (1 << 253) + (1 << 32) - 1]
     pool += [pow(2, 256, M.Q), pow(2, 512, M.Q), M.Q - pow(2, 256, M.Q), pow(pow(2, 256, M.Q), -1, M.Q)]
+    rng = random.Random(19)
+    sq = pool + [rng.randrange(M.Q) for _ in range(2000)] + [(1 << k) % M.Q for k in range(0, 300, 7)]
+    for x, g in zip(sq, E.fr_device_op("square", sq, sq)):
+        assert g == x * x % M.Q, hex(x)
     a = [x for x in pool for _ in pool]
     b = [y for _ in pool for y in pool]
     for op in ("mul", "add", "sub", "div"):
