@@ -455,12 +455,14 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
     info->n_prv_in = r->file.n_prv_in;
     info->n_constraints = r->file.n_constraints;
     info->n_labels = r->file.n_labels;
-    info->nnz = r->file.terms.size();
+    info->nnz = r->file.nnz;
     info->nnz_pm1 = r->file.nnz_pm1;
     info->nnz_small = r->file.nnz_small;
     info->macs = r->file.macs;
     info->n_quadratic = r->file.n_quadratic;
     info->nnz_const = r->file.nnz_const;
+    info->n_squares = r->file.n_squares;
+    static_assert(r1cs::SAME_AS_A == R1CS_SAME_AS_A, "marker mismatch");
     info->n_coefs = (uint32_t)r->file.coefs.size();
     return CVMGPU_OK;
 }

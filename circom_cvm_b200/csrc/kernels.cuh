@@ -485,6 +485,7 @@ struct R1csParams {
 // values in flight with cp.async (LDGSTS, global -> its private column of a shared-memory ring, L2-only caching)
 // and consumes them in order: HBM latency is hidden even when few warps are resident (small batches).
 #define R1CS_NT 128
+#define R1CS_SAME_AS_A 0xffffffffu   // r1cs.hpp SAME_AS_A: first class boundary of a B combination that repeats A
 #define R1CS_STAGES 8
 
 struct TermStream {
@@ -628,7 +629,13 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         // headers of A, B, C and of the next constraint's A (its begin is the end of C)
         const uint4 hB = __ldg(p.hdr + 3 * c + 1), hC = __ldg(p.hdr + 3 * c + 2), hN = __ldg(p.hdr + 3 * c + 3);
         Fr prod = fr::zero();
-        if (hA.x != hB.x && hB.x != hC.x) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
+        if (hB.y == R1CS_SAME_AS_A) {        // B repeats A (r1cs.hpp): one evaluation, one squaring
+            const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            const Fr one = fr::one_mont();
+            if (fr::is_zero(sa)) prod = fr::zero();
+            else if (sa.v[0] == one.v[0] && fr::equal(sa, one)) prod = one;
+            else prod = fr::mont_sqr(sa);
+        } else if (hA.x != hB.x && hB.x != hC.x) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
             const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
             const Fr sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
             // trivial factors need no product: 0, 1 and -1 (bit-valued wires and the +-1 combinations of them that

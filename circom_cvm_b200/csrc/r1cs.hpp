@@ -20,6 +20,8 @@
 
 namespace r1cs {
 
+static const uint32_t SAME_AS_A = 0xffffffffu;   // first class boundary of a B combination that repeats A
+
 struct Term {
     uint32_t wire;
     uint32_t coef;   // index into coefs
@@ -41,7 +43,8 @@ struct File {
     std::vector<Term> terms;
     std::vector<fr::Fr> coefs;       // canonical
     std::vector<uint64_t> wire2label;
-    uint64_t nnz_pm1 = 0, nnz_small = 0, nnz_const = 0;
+    uint64_t nnz = 0;                // non-zeros of the file (terms may hold fewer: the B side of squares is dropped)
+    uint64_t nnz_pm1 = 0, nnz_small = 0, nnz_const = 0, n_squares = 0;
     // what the check kernel executes per witness: 64 multiply-accumulates per general term + 72 per reduction of a dot
     // product (<= 16 terms), 8 per small term + 170 per small-class reduction, 136 per quadratic constraint
     uint64_t macs = 0, n_quadratic = 0, n_linear = 0;
@@ -187,10 +190,50 @@ inline File load(const std::string &path) {
         }
         out.macs += 8 * (n1 + n2) + 170 * ((n1 ? 1 : 0) + (n2 ? 1 : 0)) + 64 * n3 + 72 * ((n3 + 15) / 16);
     }
+    out.nnz = out.terms.size();
     for (uint32_t c = 0; c < out.n_constraints; c++) {
         bool quad = out.ptr[3 * c] != out.ptr[3 * c + 1] && out.ptr[3 * c + 1] != out.ptr[3 * c + 2];
         if (quad) { out.n_quadratic++; out.macs += 136; }
         else out.n_linear++;
+    }
+    // ---- squares: when B is the same combination as A (x*x of an S-box) its terms are dropped from the CSR and its
+    // header carries SAME_AS_A in the first class boundary; the kernel evaluates A once and squares it.
+    {
+        std::vector<Term> terms;
+        std::vector<uint32_t> ptr, split;
+        terms.reserve(out.terms.size());
+        ptr.reserve(out.ptr.size());
+        split.reserve(out.split.size());
+        ptr.push_back(0);
+        for (size_t j = 0; j + 1 < out.ptr.size(); j++) {
+            const uint32_t b = out.ptr[j], e = out.ptr[j + 1];
+            bool same = false;
+            if (j % 3 == 1 && e > b) {
+                const uint32_t ab = out.ptr[j - 1];
+                same = (b - ab) == (e - b);
+                for (uint32_t k = 0; same && k < e - b; k++)
+                    same = out.terms[ab + k].wire == out.terms[b + k].wire && out.terms[ab + k].coef == out.terms[b + k].coef;
+            }
+            const uint32_t nb = (uint32_t)terms.size();
+            if (same) {
+                out.n_squares++;
+                // (what B would have cost is no longer executed)
+                const size_t n0 = out.split[3 * j] - b, n1 = out.split[3 * j + 1] - out.split[3 * j], n2 = out.split[3 * j + 2] - out.split[3 * j + 1];
+                size_t n3 = (e - b) - n0 - n1 - n2;
+                if (n3 && (out.terms[e - 1].wire >> 31)) n3--;
+                out.macs -= 8 * (n1 + n2) + 170 * ((n1 ? 1 : 0) + (n2 ? 1 : 0)) + 64 * n3 + 72 * ((n3 + 15) / 16);
+                split.push_back(SAME_AS_A);
+                split.push_back(nb);
+                split.push_back(nb);
+            } else {
+                terms.insert(terms.end(), out.terms.begin() + b, out.terms.begin() + e);
+                for (int k = 0; k < 3; k++) split.push_back(out.split[3 * j + k] - b + nb);
+            }
+            ptr.push_back((uint32_t)terms.size());
+        }
+        out.terms.swap(terms);
+        out.ptr.swap(ptr);
+        out.split.swap(split);
     }
     if (have[3]) {
         size_t wp = sec_pos[3];

@@ -60,7 +60,7 @@ class R1csInfo(ctypes.Structure):
     _fields_ = [("n_wires", c_uint32), ("n_pub_out", c_uint32), ("n_pub_in", c_uint32), ("n_prv_in", c_uint32),
                 ("n_constraints", c_uint32), ("n_labels", c_uint64), ("nnz", c_uint64), ("nnz_pm1", c_uint64),
                 ("n_coefs", c_uint32), ("nnz_small", c_uint64), ("macs", c_uint64), ("n_quadratic", c_uint64),
-                ("nnz_const", c_uint64)]
+                ("nnz_const", c_uint64), ("n_squares", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -88,6 +88,7 @@ typedef struct {
     uint64_t macs;               /* 32x32->64 multiply-accumulates the check kernel executes per witness */
     uint64_t n_quadratic;        /* constraints with non-empty A and B (one Montgomery product each) */
     uint64_t nnz_const;          /* general coefficients on wire 0 (the constant 1): added, not multiplied */
+    uint64_t n_squares;          /* quadratic constraints whose B repeats A: evaluated once and squared */
 } cvmgpu_r1cs_info;
 
 const char *cvmgpu_last_error(void);

@@ -63,6 +63,7 @@ def test_cpp_r1cs_loader_agrees(cvmlib, tmp_path):
     small = lambda v: v < (1 << 32) or Q - v < (1 << 32)
     assert info["nnz_const"] == sum(1 for c in art.constraints for lc in c for w, v in lc.items() if w == 0 and not small(v))
     assert info["n_quadratic"] == sum(1 for a, b, _ in art.constraints if a and b)
+    assert info["n_squares"] == sum(1 for a, b, _ in art.constraints if a and a == b) == 162
 
 
 def test_doc_example_constraint_convention():

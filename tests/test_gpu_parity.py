@@ -507,6 +507,8 @@ def test_r1cs_check_extreme_coefficients_and_values(E, tmp_path):
         ({0: M.Q - 7}, lc_general(3, True)),              # constant-only combination times a short dot product
         (lc_general(2, True), {0: (1 << 200) + 9}),
     ]
+    for g in (lc_general(5, True), {**lc_pow2(2), **lc_small(5, -1)}, {3: 1}, {0: M.Q - 3, 7: 1}):
+        shapes.append((g, dict(g)))                       # B repeats A: evaluated once and squared
     for a, b in shapes:
         out_wire = 1 + n_in + len(cons)
         cons.append((a, b, {out_wire: 1}))
@@ -521,7 +523,7 @@ def test_r1cs_check_extreme_coefficients_and_values(E, tmp_path):
     formats.write_r1cs(str(path), cons, n_wires, 0, 0, n_in, list(range(n_wires)))
     r = E.R1cs(str(path))
     info = r.info.asdict()
-    assert info["nnz_const"] >= 5 and info["nnz_small"] >= 80
+    assert info["nnz_const"] >= 5 and info["nnz_small"] >= 80 and info["n_squares"] == 4
 
     ev = lambda lc, w: sum(v * w[k] for k, v in lc.items()) % M.Q
     B = 96
