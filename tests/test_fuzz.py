@@ -50,3 +50,12 @@ def test_random_circuit_gpu_matches_oracle(cvmlib, seed):
             assert st[b] == 0 and got[b] == w, (seed, inp)
         else:
             assert st[b] != 0, (seed, inp)
+
+
+@pytest.mark.gpu
+def test_random_constraint_systems_gpu_check(cvmlib):
+    """Random R1CS over every coefficient class, empty / repeated combinations and carry-stressing values: the first
+    violated constraint per witness against Python integers (tools/fuzz_r1cs_gpu.py is the long-running version)."""
+    from tools.fuzz_r1cs_gpu import main
+    n, bad = main(40)
+    assert n == 40 * 64 and bad == 0
