@@ -190,7 +190,7 @@ def cpu_baseline_reference(n_threads, seconds=10.0, art=None):
             count += d["witnesses"]
         except Exception:
             return None
-    return {"value": total, "unit": UNIT, "cores": n_threads, "kind": "reference",
+    return {"value": total, "unit": UNIT, "cores": n_threads, "kind": "reference", "value_per_core": total / max(1, n_threads),
             "sample": "%d %s witnesses over %d processes x %.0f s: reference common/calcwit.cpp + generic/fr.cpp "
                       "(--no_asm arithmetic; bn128/fr.asm cannot be assembled here) running the circuit body emitted "
                       "by tools/circuitgen in the WriteC shapes; run(ctx) only" % (count, WL["label"], n_threads, seconds)}
@@ -500,8 +500,9 @@ def main():
     roofline.update({"kernel": dom, "ms": kd["ms"], "peak_source": peak_src if view == "imad" else "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_kind,
                      "traffic": kd["hbm"]["traffic"],
                      "other_view": {k: kd["hbm" if view == "imad" else "imad"][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
-                     "note": "integer-pipe bound (north_star: field arithmetic); ncu: ALU and FMA-heavy pipes both ~60-67% busy, "
-                             "DRAM < 20% (profiles/r01_summary.md)"})
+                     "note": "integer-multiply bound (north_star: field arithmetic): every multiply-accumulate is one IMAD.WIDE.U32.X, "
+                             "one warp-instruction per 4 cycles per scheduler; ncu on Poseidon(2): FMA-heavy pipe 82% busy in the tape "
+                             "kernel, 67% in the check, DRAM 27-33% (profiles/r01_summary.md)"})
     roofline_hbm = {k: v["hbm"] for k, v in kernels.items()}
     if args.skip_cpu:
         cpu = None
