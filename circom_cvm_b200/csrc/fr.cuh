@@ -269,7 +269,8 @@ FR_HD Fr mont_mul_portable(const Fr &a, const Fr &b) {
 }
 
 #if defined(__CUDACC__)
-// Device formulation.  Per b-limb ("row"): the eight 32x32->64 products a[j]*b_i come from mul.wide.u32
+// First device formulation of the round, kept as the comparison variant of cvmgpu_mul_peak (the kernels use
+// mont_mul_chain below).  Per b-limb ("row"): the eight 32x32->64 products a[j]*b_i come from mul.wide.u32
 // (IMAD.WIDE.U32 with a zero addend: no register-pair set-up moves).  The products of the EVEN limbs occupy
 // disjoint 64-bit windows (columns 2k, 2k+1), so they form one 256-bit number that is added to T with a single
 // add.cc/addc.cc chain; the products of the ODD limbs form a second number shifted by 32 bits.  Hence
@@ -386,7 +387,7 @@ __device__ __forceinline__ Fr mont_mul_wide(const Fr &a, const Fr &b) {
 // carry-out is a single instruction when the 64-bit window is a register pair.  The products of limbs 0,2,4,6 of
 // an operand tile eight consecutive words, those of limbs 1,3,5,7 tile the eight words one position higher, so a
 // number is kept as TWO word arrays, T = E + 2^32 * O, and each row of a product is two 4-instruction chains.
-// (mont_mul_wide above - mul.wide + add chains on one array - needs 407 instructions per product; this form 190.)
+// (mont_mul_wide above - mul.wide + add chains on one array - needs 407 instructions per product; this form 210.)
 
 // acc[0..7] += (x0, x1, x2, x3) * y, x_k * y landing on acc[2k], acc[2k+1]; the carry out is counted in top
 __device__ __forceinline__ void mad4(uint32_t *acc, uint32_t &top, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {

@@ -148,8 +148,8 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
 // the same instruction (flag bit 3).
 //
 // W witnesses per thread (lanes tid + k*NT of a CTA that covers NT*W witnesses): W = 2 was an experiment (two
-// independent carry chains per thread); the kernel is bound by integer instruction issue (one IMAD.WIDE or IADD3 per two
-// cycles and scheduler, profiles/r01_summary.md), so it does not help and W = 1 is what runs.
+// independent carry chains per thread); the kernel is bound by the IMAD.WIDE pipe, which more resident warps saturate
+// just as well (profiles/r01_summary.md), so it does not help and W = 1 is what runs.
 template <int NT, int W>
 __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
     constexpr int NS = NT * W;   // witnesses per CTA = stride of one slot half in shared memory
