@@ -966,28 +966,43 @@ FR_HD Fr mont_inv_fermat(const Fr &a) {
 struct S30 {
     int32_t v[9];   // signed 30-bit limbs
 };
+// 30 division steps on the low words of (f, g); t = the transition matrix (u v; q r), scaled by 2^30.  The matrix is
+// tracked in three runs of 10 steps with its rows PACKED two entries to a word (P = u + v * 2^16, Q = q + r * 2^16,
+// |entries| <= 2^10 within a run): conditional negation, masked addition and doubling are linear, so they act on both
+// entries at once - 20 instead of 29 operations per step - and the three 2x2 matrices are multiplied together at the end
+// of each run (the inversions are 59 % of the EdDSA verifier tape's instructions, profiles/r01_summary.md).
 FR_HD int32_t by_divsteps_30(int32_t zeta, uint32_t f0, uint32_t g0, int32_t *t) {
-    uint32_t u = 1, v = 0, q = 0, r = 1;
-    uint32_t c1, c2, f = f0, g = g0, x, y, z;
-    for (int i = 0; i < 30; ++i) {
-        c1 = (uint32_t)(zeta >> 31);      // zeta < 0
-        c2 = 0u - (g & 1u);               // g odd
-        x = (f ^ c1) - c1;                // conditionally negated f, u, v
-        y = (u ^ c1) - c1;
-        z = (v ^ c1) - c1;
-        g += x & c2;
-        q += y & c2;
-        r += z & c2;
-        c1 &= c2;
-        zeta = (int32_t)((uint32_t)zeta ^ c1) - 1;
-        f += g & c1;
-        u += q & c1;
-        v += r & c1;
-        g >>= 1;
-        u <<= 1;
-        v <<= 1;
+    uint32_t f = f0, g = g0;
+    int32_t m0 = 1, m1 = 0, m2 = 0, m3 = 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int part = 0; part < 3; ++part) {
+        uint32_t P = 1u, Q = 1u << 16;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int i = 0; i < 10; ++i) {
+            uint32_t c1 = (uint32_t)(zeta >> 31);      // zeta < 0
+            const uint32_t c2 = 0u - (g & 1u);         // g odd
+            const uint32_t x = (f ^ c1) - c1;          // conditionally negated f and (u, v)
+            const uint32_t y = (P ^ c1) - c1;
+            g += x & c2;
+            Q += y & c2;
+            c1 &= c2;
+            zeta = (int32_t)((uint32_t)zeta ^ c1) - 1;
+            f += g & c1;
+            P += Q & c1;
+            g >>= 1;
+            P <<= 1;
+        }
+        const int32_t u = (int32_t)(P << 16) >> 16, v = (int32_t)(P - (uint32_t)u) >> 16;
+        const int32_t q = (int32_t)(Q << 16) >> 16, r = (int32_t)(Q - (uint32_t)q) >> 16;
+        // (u v; q r) * (m0 m1; m2 m3): entries stay within 2^30
+        const int32_t n0 = u * m0 + v * m2, n1 = u * m1 + v * m3, n2 = q * m0 + r * m2, n3 = q * m1 + r * m3;
+        m0 = n0; m1 = n1; m2 = n2; m3 = n3;
     }
-    t[0] = (int32_t)u; t[1] = (int32_t)v; t[2] = (int32_t)q; t[3] = (int32_t)r;
+    t[0] = m0; t[1] = m1; t[2] = m2; t[3] = m3;
     return zeta;
 }
 FR_HD int32_t by_q30(int i) {
