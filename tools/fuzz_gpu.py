@@ -6,7 +6,7 @@ from oracle import cvm_interp as I
 from circom_cvm_b200 import engine as E
 from tools.circuitgen.build import compile_circuit
 bad=0; n=0
-for seed in range(3000, 3600):
+for seed in range(5000, 5600):
     try:
         art = compile_circuit(make_circuit(seed, n_stmts=70), (), name="fz%d"%seed)
     except ZeroDivisionError:
