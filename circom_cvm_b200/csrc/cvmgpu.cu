@@ -61,6 +61,7 @@ struct cvmgpu_program {
     tape::BatchInvStats binv;
     std::vector<fr::Fr> consts_mont;
     std::vector<uint64_t> witness;   // %%witness: signal index of every witness wire
+    std::vector<uint8_t> wire_bool;  // per witness wire: the value is proven 0/1 by the trace compiler's typing
     uint64_t n_signals = 0;
     uint32_t n_inputs = 0, n_outputs = 0;
     // device copies (uploaded on first use on the current device)
@@ -121,6 +122,8 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
             p->tape = tape::build_tape(tr, n_slots);
         }
         p->tstats = tr.stats;
+        p->wire_bool.reserve(tr.witness_ref.size());
+        for (uint32_t r : tr.witness_ref) p->wire_bool.push_back(tr.ref_is_bool(r) ? 1 : 0);
         p->n_signals = (uint64_t)parser.prog.n_signals;
         p->witness.assign(parser.prog.witness.begin(), parser.prog.witness.end());
         p->n_inputs = (uint32_t)tr.n_inputs;
@@ -133,6 +136,13 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
         return fail(CVMGPU_ERR_PARSE, e.what());
     }
     *out = p.release();
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_wire_types(const cvmgpu_program *p, const uint8_t **is_bool, uint32_t *n) {
+    if (!p || !is_bool || !n) return fail(CVMGPU_ERR_ARG, "null argument");
+    *is_bool = p->wire_bool.data();
+    *n = (uint32_t)p->wire_bool.size();
     return CVMGPU_OK;
 }
 

@@ -185,6 +185,8 @@ class Tracer {
     int last_exit_pc = 0;
   public:
     int max_unroll = 260;             // iterations traced for a data-dependent while loop (254-bit scans fit)
+    // the value behind a ref (constant or traced value) is provably 0 or 1 for every input
+    bool ref_is_bool(uint32_t r) const { return is_bool(r); }
   private:
     static const int64_t SPR_BASE = (int64_t)1 << 40;
 

@@ -28,7 +28,7 @@ NO_BAD = 0xFFFFFFFF
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_info_get", "cvmgpu_program_free",
-    "cvmgpu_program_tape", "cvmgpu_program_witness",
+    "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_dev", "cvmgpu_witness_export_dev", "cvmgpu_store_bytes",
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
@@ -83,6 +83,7 @@ def lib():
     L.cvmgpu_program_free.restype = None
     L.cvmgpu_program_tape.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_witness.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
+    L.cvmgpu_program_wire_types.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_witness_batch.argtypes = [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_checked.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
@@ -233,6 +234,12 @@ class WitnessCalculator:
         sig, n = c_void_p(), c_uint32()
         _check(lib().cvmgpu_program_witness(self._h, byref(sig), byref(n)))
         return list(np.ctypeslib.as_array(ctypes.cast(sig, POINTER(c_uint64)), shape=(n.value,))) if n.value else []
+
+    def wire_is_bool(self):
+        """uint8 per witness wire: proven 0/1 by the trace compiler's typing"""
+        ptr, n = c_void_p(), c_uint32()
+        _check(lib().cvmgpu_program_wire_types(self._h, byref(ptr), byref(n)))
+        return np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(ctypes.c_uint8)), shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint8)
 
     @property
     def n_outputs(self):

@@ -109,6 +109,10 @@ int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_i
 /* The program's %%witness list: signal index of every witness wire (= the witness2SignalList of the .dat,
  * c_code_generator.rs:541-550; used to locate the input hash map of a .dat, circom_cvm_b200/inputs.py). */
 int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n);
+/* Per witness wire: 1 when the trace compiler's value-range typing proves the wire 0/1 for every input (comparison
+ * results, extracted bits, boolean combinations of those, constants 0 and 1).  Informational: the basis of a compact
+ * row type for bit-valued wires. */
+int cvmgpu_program_wire_types(const cvmgpu_program *p, const uint8_t **is_bool, uint32_t *n);
 
 /* ---- witness generation ----------------------------------------------------------------------- */
 /* HOST buffers.  inputs: B x n_inputs x 32 B (main inputs in signal order, canonical LE; values >= q are

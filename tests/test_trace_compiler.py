@@ -182,3 +182,30 @@ def test_sha256_circuit_matches_hashlib(cvmlib):
     bad = [M.Q - 1] + [0] * 63
     rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, bad)
     assert status == 1
+
+
+@pytest.mark.parametrize("name", ["num2bits8", "lessthan8", "opszoo", "sum3cmp", "earlyret", "poseidon2"])
+def test_wire_typing_is_sound(cvmlib, name):
+    """Wires the trace compiler types as 0/1 (cvmgpu_program_wire_types) really are 0 or 1 in the oracle's witness, for
+    ordinary and extreme inputs."""
+    from circom_cvm_b200 import engine as E
+    art = circuit(name)
+    prog = I.load(art.cvm)
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    typed = wc.wire_is_bool()
+    assert len(typed) == art.n_wires and typed[0] == 1          # wire 0 is the constant 1
+    rng = random.Random(13)
+    cases = list(CASES[name]) + [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(20)]
+    for inp in cases:
+        w, st = oracle(prog, inp)
+        if st:
+            continue
+        for k, v in enumerate(w):
+            assert not typed[k] or v in (0, 1), (name, inp, k, v)
+
+
+def test_sha256_wires_are_almost_all_bits(cvmlib):
+    from circom_cvm_b200 import engine as E
+    art = circuit("sha256_64")
+    typed = E.WitnessCalculator(cvm_text=art.cvm).wire_is_bool()
+    assert typed.sum() > 0.99 * len(typed)
