@@ -549,9 +549,10 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     rp.B = B;
     rp.first_bad = (uint32_t *)d_first_bad;
     dim3 grid((unsigned)gx, (unsigned)chunks);
-    // resident CTAs per SM: 4 (128 registers) when the check is multiplier-bound, 5 (96 registers) when it is mostly +-1 /
-    // small coefficients and latency-bound (measured: Poseidon 17.9 vs 18.1 ms, Sha256(512) 112.9 vs 109.7 ms)
-    int minb = g_r1cs_minb ? g_r1cs_minb : (r->file.macs > 16 * (uint64_t)r->file.terms.size() ? 4 : 5);
+    // resident CTAs per SM: 4 (128 registers) when the check is multiplier-bound (Poseidon: 28 % of the terms have
+    // full-size coefficients, EdDSA 12 %), 5 (96 registers) when it is mostly +-1 / small coefficients and latency-bound
+    // (Sha256: 0.3 %); measured: Poseidon 17.9 vs 18.1 ms, Sha256(512) 112.9 vs 109.7 ms
+    int minb = g_r1cs_minb ? g_r1cs_minb : (20 * r->file.nnz_general > r->file.nnz ? 4 : 5);
     if (minb == 5) kern::r1cs_kernel<5><<<grid, R1CS_NT, 0, s>>>(rp);
     else kern::r1cs_kernel<4><<<grid, R1CS_NT, 0, s>>>(rp);
     CUDA_TRY(cudaGetLastError());

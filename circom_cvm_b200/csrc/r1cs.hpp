@@ -44,7 +44,7 @@ struct File {
     std::vector<fr::Fr> coefs;       // canonical
     std::vector<uint64_t> wire2label;
     uint64_t nnz = 0;                // non-zeros of the file (terms may hold fewer: the B side of squares is dropped)
-    uint64_t nnz_pm1 = 0, nnz_small = 0, nnz_const = 0, n_squares = 0;
+    uint64_t nnz_pm1 = 0, nnz_small = 0, nnz_const = 0, n_squares = 0, nnz_general = 0;
     // what the check kernel executes per witness: 64 multiply-accumulates per general term + 72 per reduction of a dot
     // product (<= 16 terms), 8 per small term + 170 per small-class reduction, 136 per quadratic constraint
     uint64_t macs = 0, n_quadratic = 0, n_linear = 0;
@@ -189,6 +189,7 @@ inline File load(const std::string &path) {
             out.nnz_const++;
         }
         out.macs += 8 * (n1 + n2) + 170 * ((n1 ? 1 : 0) + (n2 ? 1 : 0)) + 64 * n3 + 72 * ((n3 + 15) / 16);
+        out.nnz_general += n3;
     }
     out.nnz = out.terms.size();
     for (uint32_t c = 0; c < out.n_constraints; c++) {
