@@ -202,6 +202,10 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_ld_streamed = p->tape.stats.n_ld_streamed;
     info->unrolled_iterations = p->tstats.unrolled_iterations;
     info->tape_lut = p->tape.stats.n_lut;
+    info->tape_ld_bool = p->tape.stats.n_ld_bool;
+    info->tape_spill_st_bool = p->tape.stats.n_spill_st_bool;
+    info->n_bool_wires = 0;
+    for (uint8_t b : p->wire_bool) info->n_bool_wires += b;
     return CVMGPU_OK;
 }
 

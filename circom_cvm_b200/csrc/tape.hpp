@@ -39,6 +39,7 @@ struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
+    uint64_t n_ld_bool = 0, n_spill_st_bool = 0;   // of n_ld / n_spill_st: the value is typed 0/1 (what compact bit rows would shrink)
     uint32_t n_spill_rows = 0;
     // 32x32->64 multiply-accumulates the kernel executes per witness: 136 per Montgomery product (also the one that brings
     // an input to Montgomery form and the one after an inversion), 64 per DOT term + 72 per DOT reduction, and the
@@ -158,6 +159,7 @@ struct XProg {
     std::vector<XOp> ops;
     std::vector<std::pair<uint32_t, uint32_t>> terms;   // (constant ref, value id)
     std::vector<uint32_t> witness_ref;
+    std::vector<uint8_t> isbool;   // per op: the tracer proved the value 0/1 (fused results: not typed)
 };
 
 inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
@@ -279,6 +281,10 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
     }
     xp.witness_ref.reserve(tr.witness_ref.size());
     for (uint32_t r : tr.witness_ref) xp.witness_ref.push_back(mapref(r));
+    xp.isbool.assign(xp.ops.size(), 0);
+    for (size_t i = 0; i < N; i++)
+        if (remap[i] != NO_REF && roots.find((uint32_t)i) == roots.end() && cadd.find((uint32_t)i) == cadd.end())
+            xp.isbool[remap[i]] = tr.ref_is_bool((uint32_t)i) ? 1 : 0;
     return xp;
 }
 
@@ -429,6 +435,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             out.ins.push_back(TapeIns{T_ST, 0, 0, best, 0, val_home[v]});
             out.stats.n_st++;
             out.stats.n_spill_st++;
+            out.stats.n_spill_st_bool += xp.isbool[v];
         }
         val_slot[v] = -1;
         slot_val[best] = -1;
@@ -458,6 +465,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
                 uint32_t s = alloc_slot(pos, pinned);
                 out.ins.push_back(TapeIns{T_LD, 0, (uint16_t)s, 0, 0, val_home[r]});
                 out.stats.n_ld++;
+                out.stats.n_ld_bool += xp.isbool[r];
                 val_slot[r] = (int32_t)s;
                 slot_val[s] = (int32_t)r;
                 pinned.push_back((int32_t)s);

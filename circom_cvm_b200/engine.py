@@ -50,7 +50,8 @@ class ProgramInfo(ctypes.Structure):
                 ("tape_div", c_uint64), ("tape_addsub", c_uint64), ("tape_other", c_uint64), ("tape_ld", c_uint64),
                 ("tape_st", c_uint64), ("tape_spill_st", c_uint64), ("n_consts", c_uint32), ("dyn_branches", c_uint32),
                 ("ref_div", c_uint64), ("tape_inv", c_uint64), ("tape_sel", c_uint64), ("tape_dot", c_uint64),
-                ("tape_dot_terms", c_uint64), ("tape_macs", c_uint64), ("tape_ld_streamed", c_uint64), ("unrolled_iterations", c_uint64), ("tape_lut", c_uint64)]
+                ("tape_dot_terms", c_uint64), ("tape_macs", c_uint64), ("tape_ld_streamed", c_uint64), ("unrolled_iterations", c_uint64), ("tape_lut", c_uint64),
+                ("tape_ld_bool", c_uint64), ("tape_spill_st_bool", c_uint64), ("n_bool_wires", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -76,6 +76,9 @@ typedef struct {
     uint64_t tape_ld_streamed;   /* reloads served by the cp.async ring (requested 4 reloads ahead) */
     uint64_t unrolled_iterations; /* iterations of data-dependent while loops traced under predicates */
     uint64_t tape_lut;           /* boolean cones (XOR / Ch / Maj / ... written as field polynomials) run as one table look-up */
+    uint64_t tape_ld_bool;       /* of tape_ld: reloads of values typed 0/1 (32 B each today; see cvmgpu_program_wire_types) */
+    uint64_t tape_spill_st_bool; /* of tape_spill_st: spills of values typed 0/1 */
+    uint64_t n_bool_wires;       /* witness wires typed 0/1 */
 } cvmgpu_program_info;
 
 typedef struct {
