@@ -1,8 +1,9 @@
 """Process-level drop-in for the reference's generated witness calculator (common/main.cpp:334-371):
 
-    python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>]
+    python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>] [--sym <circuit.sym>]
 
-reads `<circuit>.dat` next to the program (as the reference reads `<argv0>.dat`), takes the same input.json and
+reads `<circuit>.dat` next to the program (as the reference reads `<argv0>.dat`) - or, with --sym or when there is no
+.dat, the `circom --sym` symbol file - to resolve the input names, takes the same input.json and
 writes the same bytes to output.wtns -- computed on the GPU.  input.json may also be an array of input objects:
 the batch goes through one kernel launch and `<output>` gets one file per witness (`out.wtns`, `out.1.wtns`, ...).
 Exit code 1 with the reference's message on a failing assert (the reference aborts).
@@ -12,17 +13,30 @@ import sys
 
 
 def main(argv):
-    args = [a for a in argv[1:] if not a.startswith("--")]
+    args, opts, k = [], {}, 1
+    while k < len(argv):
+        if argv[k] in ("--r1cs", "--sym") and k + 1 < len(argv):
+            opts[argv[k]] = argv[k + 1]
+            k += 2
+        elif argv[k].startswith("--"):
+            args = []
+            break
+        else:
+            args.append(argv[k])
+            k += 1
     if len(args) != 3:
-        print("Usage: python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <file>]", file=sys.stderr)
+        print("Usage: python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <file>] [--sym <file>]",
+              file=sys.stderr)
         return 1
     from . import engine as E
-    from .inputs import InputError, InputMap, rows_from_json_text
+    from .inputs import InputError, InputMap, SymInputMap, rows_from_json_text
     cvm, jin, wout = args
-    r1cs_path = argv[argv.index("--r1cs") + 1] if "--r1cs" in argv else None
+    r1cs_path = opts.get("--r1cs")
     wc = E.WitnessCalculator(cvm_path=cvm)
     try:
-        imap = InputMap.from_files(os.path.splitext(cvm)[0] + ".dat", wc)
+        stem = os.path.splitext(cvm)[0]
+        sym_path = opts.get("--sym") or (stem + ".sym" if not os.path.exists(stem + ".dat") and os.path.exists(stem + ".sym") else None)
+        imap = SymInputMap.from_files(sym_path, wc) if sym_path else InputMap.from_files(stem + ".dat", wc)
         with open(jin) as f:
             rows = rows_from_json_text(imap, f.read())
     except InputError as e:

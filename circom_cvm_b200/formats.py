@@ -175,3 +175,23 @@ def pack_inputs(rows, n_inputs):
         for v in r:
             out += int(v).to_bytes(32, "little")
     return bytes(out)
+
+
+# ---- .sym (constraint_writers/src/sym_writer.rs:4-14; mkdocs/docs/circom-language/formats/sym.md) -------------------
+def write_sym(path, entries):
+    """entries: iterable of (signal label, witness position or -1, component number, qualified name)"""
+    with open(path, "w") as f:
+        for s, w, c, name in entries:
+            f.write("%d,%d,%d,%s\n" % (s, w, c, name))
+
+
+def read_sym(path):
+    out = []
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if not line:
+                continue
+            s, w, c, name = line.split(",", 3)
+            out.append((int(s), int(w), int(c), name))
+    return out

@@ -12,6 +12,7 @@ Fr_str2element does).
 from __future__ import annotations
 
 import json
+import re
 import struct
 
 from .formats import fnv1a
@@ -58,6 +59,37 @@ class InputMap:
                 raise InputError("Signal not found")
             pos = (pos + 1) % n
         raise InputError("Signals not found")
+
+
+class SymInputMap(InputMap):
+    """The same lookup built from a `.sym` file (`circom --sym`: one `#s,#w,#c,name` line per signal,
+    constraint_writers/src/sym_writer.rs:4-14) instead of the `.dat` hash map: the main component's input signals are
+    grouped by name without their trailing indices (`main.in[3]` -> key `in`, as loadJson addresses them,
+    main.cpp:241-284), first signal and element count per key."""
+
+    def __init__(self, sym_entries, input_start: int, n_inputs: int):
+        self.input_start, self.n_inputs = input_start, n_inputs
+        groups = {}
+        for label, _w, _c, name in sym_entries:
+            if not (input_start <= label < input_start + n_inputs) or not name.startswith("main."):
+                continue
+            key = re.sub(r"(\[\d+\])+$", "", name[5:])
+            first, count = groups.get(key, (label, 0))
+            groups[key] = (min(first, label), count + 1)
+        if sum(c for _f, c in groups.values()) != n_inputs:
+            raise InputError("the .sym file does not belong to this program (main inputs not found)")
+        self.table = [(fnv1a(k), first, count) for k, (first, count) in groups.items()]
+        self._pos = {h: i for i, (h, _f, _c) in enumerate(self.table)}
+
+    @classmethod
+    def from_files(cls, sym_path, wc):
+        from . import formats
+        return cls(formats.read_sym(sym_path), 1 + wc.n_outputs, wc.n_inputs)
+
+    def position(self, h):
+        if h not in self._pos:
+            raise InputError("Signal not found")
+        return self._pos[h]
 
 
 def _parse_number(val):             # json2FrElements, main.cpp:144-190 (value mod q is taken on the device)

@@ -306,6 +306,11 @@ def test_process_abi_drop_in(E, name, doc, tmp_path):
     env = dict(os.environ, PYTHONPATH=ROOT)
     subprocess.run([sys.executable, "-m", "circom_cvm_b200", paths["cvm"], str(jin), str(out)], check=True, env=env,
                    cwd=ROOT, timeout=300)
+    # names resolved from the `circom --sym` file instead of the .dat, with the R1CS check on: same bytes
+    out2 = tmp_path / "ours_sym.wtns"
+    subprocess.run([sys.executable, "-m", "circom_cvm_b200", paths["cvm"], str(jin), str(out2), "--sym", paths["sym"],
+                    "--r1cs", paths["r1cs"]], check=True, env=env, cwd=ROOT, timeout=300)
+    assert out2.read_bytes() == out.read_bytes()
     # the native host program (csrc/calc_main.cpp) takes the same files
     from circom_cvm_b200 import build as cbuild
     cbuild.build()

@@ -5,7 +5,7 @@ import json
 import pytest
 
 from circom_cvm_b200 import formats
-from circom_cvm_b200.inputs import InputError, InputMap, qualify, row_from_json, rows_from_json_text
+from circom_cvm_b200.inputs import InputError, InputMap, SymInputMap, qualify, row_from_json, rows_from_json_text
 from conftest import circuit
 
 
@@ -62,6 +62,37 @@ def test_batches_and_foreign_dat():
     assert rows_from_json_text(m, json.dumps([{"a": "1", "b": "2"}, {"a": "3", "b": "4"}])) == [[1, 2], [3, 4]]
     with pytest.raises(InputError, match="does not belong"):
         InputMap(b"\x07" * 9000, art.witness, art.input_start, art.n_inputs)
+
+
+def test_sym_file_resolves_the_same_inputs(tmp_path):
+    """`circom --sym` lines (sym_writer.rs:4-14, formats/sym.md) as the name source instead of the .dat hash map: same
+    rows, same error messages; the fixture generator's .sym lists every signal once with its witness position."""
+    from tools.circuitgen.build import sym_entries
+    for name, doc in (("multiplier2", {"b": "11", "a": 3}), ("babyadd4", {"q": ["0x10", "0b11"], "p": ["7", "0o17"]}),
+                      ("poseidon2", {"inputs": [1, 2]}), ("multiplier4", {"in": [2, 3, 4, 5]})):
+        art = circuit(name)
+        ent = sym_entries(art)
+        p = tmp_path / (name + ".sym")
+        formats.write_sym(str(p), ent)
+        assert formats.read_sym(str(p)) == ent
+        # every signal once, in label order; witness positions 1..n_wires-1 each exactly once (sym.md)
+        assert [e[0] for e in ent] == list(range(1, art.n_signals))
+        assert sorted(e[1] for e in ent if e[1] >= 0) == list(range(1, art.n_wires))
+        assert all(art.witness[e[1]] == e[0] for e in ent if e[1] >= 0)
+        ms = SymInputMap(ent, art.input_start, art.n_inputs)
+        assert row_from_json(ms, doc) == row_from_json(imap_of(art), doc)
+    art = circuit("multiplier2")
+    ms = SymInputMap(sym_entries(art), art.input_start, art.n_inputs)
+    with pytest.raises(InputError, match="Signal not found"):
+        row_from_json(ms, {"a": 1, "c": 2})
+    with pytest.raises(InputError, match="Not all inputs have been set"):
+        row_from_json(ms, {"a": 1})
+    with pytest.raises(InputError, match="does not belong"):
+        SymInputMap(sym_entries(art), art.input_start, art.n_inputs + 3)     # fewer main signals than the program has inputs
+    # the doc example's shape (sym.md:43-50): main.c.* lines are not inputs of main
+    doc_sym = [(1, 1, 1, "main.out"), (2, 2, 1, "main.in[0]"), (3, 3, 1, "main.in[1]"), (4, -1, 0, "main.c.out"),
+               (5, -1, 0, "main.c.in[0]"), (6, 4, 0, "main.c.in[1]")]
+    assert row_from_json(SymInputMap(doc_sym, 2, 2), {"in": ["5", "6"]}) == [5, 6]
 
 
 def test_program_witness_list_through_the_abi(cvmlib):

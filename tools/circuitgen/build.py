@@ -47,6 +47,33 @@ def compile_circuit(main_fn, args=(), public=(), functions=(), name=None, o1=Tru
     return art
 
 
+def _indices(dims, flat):
+    out = []
+    for d in reversed(dims):
+        out.append(flat % d)
+        flat //= d
+    return "".join("[%d]" % i for i in reversed(out))
+
+
+def sym_entries(art):
+    """(#s, #w, #c, name) for every signal, as `circom --sym` lists them (constraint_writers/src/sym_writer.rs:4-14,
+    mkdocs/docs/circom-language/formats/sym.md): signal label, witness position or -1, component number, qualified name."""
+    sig2wit = {s: w for w, s in enumerate(art.witness)}
+    out = []
+
+    def walk(inst, base_sig, cmp_id, prefix):
+        for s in inst.tmpl.signals:
+            for flat in range(s.size):
+                label = base_sig + s.offset + flat
+                out.append((label, sig2wit.get(label, -1), cmp_id, "%s.%s%s" % (prefix, s.name, _indices(s.dims, flat))))
+        for cmpsym, flat, sub, sig_off, cmp_off in inst.subs:
+            walk(sub, base_sig + sig_off, cmp_id + 1 + cmp_off, "%s.%s%s" % (prefix, cmpsym.name, _indices(cmpsym.dims, flat)))
+
+    walk(art.prog.main, 1, 0, "main")
+    out.sort()
+    return out
+
+
 def write_artifact(art, outdir, with_cpp=False):
     os.makedirs(outdir, exist_ok=True)
     base = os.path.join(outdir, art.name)
@@ -54,7 +81,8 @@ def write_artifact(art, outdir, with_cpp=False):
         f.write(art.cvm)
     formats.write_r1cs(base + ".r1cs", art.constraints, art.n_wires, art.n_pub_out, art.n_pub_in, art.n_prv_in,
                        art.witness, n_labels=art.n_signals)
-    paths = {"cvm": base + ".cvm", "r1cs": base + ".r1cs"}
+    formats.write_sym(base + ".sym", sym_entries(art))
+    paths = {"cvm": base + ".cvm", "r1cs": base + ".r1cs", "sym": base + ".sym"}
     if with_cpp:
         from .emit_cpp import emit_cpp
         with open(base + ".cpp", "w") as f:
