@@ -1,7 +1,7 @@
 // cvmgpu_calc -- native host program above the C ABI, with the process interface of the reference's generated
 // witness calculator (code_producers/src/c_elements/common/main.cpp:334-371):
 //
-//     cvmgpu_calc <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>]
+//     cvmgpu_calc <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>] [--sym <circuit.sym>]
 //
 // reads <circuit>.dat next to the program for the input hash map (as the reference reads <argv0>.dat,
 // main.cpp:22-124), takes the same input.json (main.cpp:144-284: nested names qualified as a.b[i].c, numbers as
@@ -252,6 +252,49 @@ InputMap load_map(const std::string &dat_path, const uint64_t *witness, uint32_t
     throw Fail("the .dat file does not belong to this program (witness list not found)");
 }
 
+// The same table built from a `circom --sym` file (one "#s,#w,#c,name" line per signal,
+// constraint_writers/src/sym_writer.rs:4-14): the main component's input signals grouped by name without their trailing
+// indices ("main.in[3]" -> key "in", as loadJson addresses them), first signal and element count per key.
+InputMap load_sym_map(const std::string &sym_path, uint64_t input_start, uint64_t n_inputs) {
+    std::ifstream f(sym_path);
+    if (!f) throw Fail("cannot open " + sym_path);
+    std::map<std::string, std::pair<uint64_t, uint64_t>> groups;   // key -> (first signal, count)
+    std::string line;
+    uint64_t total = 0;
+    while (std::getline(f, line)) {
+        if (line.empty()) continue;
+        size_t c1 = line.find(','), c2 = line.find(',', c1 + 1), c3 = line.find(',', c2 + 1);
+        if (c1 == std::string::npos || c2 == std::string::npos || c3 == std::string::npos) throw Fail("malformed .sym line: " + line);
+        const uint64_t label = strtoull(line.substr(0, c1).c_str(), nullptr, 10);
+        std::string name = line.substr(c3 + 1);
+        if (label < input_start || label >= input_start + n_inputs || name.compare(0, 5, "main.") != 0) continue;
+        name = name.substr(5);
+        while (!name.empty() && name.back() == ']') {   // strip trailing [i] groups
+            size_t open = name.rfind('[');
+            if (open == std::string::npos) break;
+            name.erase(open);
+        }
+        auto it = groups.find(name);
+        if (it == groups.end()) groups.emplace(name, std::make_pair(label, (uint64_t)1));
+        else { it->second.first = std::min(it->second.first, label); it->second.second++; }
+        total++;
+    }
+    if (total != n_inputs) throw Fail("the .sym file does not belong to this program (main inputs not found)");
+    InputMap m;
+    m.input_start = input_start;
+    m.n_inputs = n_inputs;
+    size_t size = 256;
+    while (size < 2 * groups.size()) size *= 2;
+    m.table.assign(size, HashEntry{0, 0, 0});
+    for (const auto &kv : groups) {
+        const uint64_t h = fnv1a(kv.first);
+        size_t pos = (size_t)(h % size);
+        while (m.table[pos].signalid != 0) pos = (pos + 1) % size;
+        m.table[pos] = HashEntry{h, kv.second.first, kv.second.second};
+    }
+    return m;
+}
+
 void row_from_json(const InputMap &m, const JVal &doc, uint8_t *row) {   // loadJson + setInputSignal
     std::map<std::string, const JVal *> flat;
     qualify("", doc, flat);
@@ -300,14 +343,15 @@ std::string strip_ext(const std::string &p) {
 
 int main(int argc, char *argv[]) {
     std::vector<std::string> pos;
-    std::string r1cs_path;
+    std::string r1cs_path, sym_path;
     for (int k = 1; k < argc; k++) {
         std::string a = argv[k];
         if (a == "--r1cs" && k + 1 < argc) r1cs_path = argv[++k];
+        else if (a == "--sym" && k + 1 < argc) sym_path = argv[++k];
         else pos.push_back(a);
     }
     if (pos.size() != 3) {
-        fprintf(stderr, "Usage: %s <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>]\n", argv[0]);
+        fprintf(stderr, "Usage: %s <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>] [--sym <circuit.sym>]\n", argv[0]);
         return 1;
     }
     cvmgpu_program *prog = nullptr;
@@ -320,7 +364,8 @@ int main(int argc, char *argv[]) {
         const uint64_t *witness = nullptr;
         uint32_t n_wit = 0;
         cvmgpu_program_witness(prog, &witness, &n_wit);
-        InputMap m = load_map(strip_ext(pos[0]) + ".dat", witness, n_wit, 1 + info.n_outputs, info.n_inputs);
+        InputMap m = sym_path.empty() ? load_map(strip_ext(pos[0]) + ".dat", witness, n_wit, 1 + info.n_outputs, info.n_inputs)
+                                      : load_sym_map(sym_path, 1 + info.n_outputs, info.n_inputs);
         std::string text = slurp(pos[1]);
         JParser jp(text);
         JVal doc = jp.value();

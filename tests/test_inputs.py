@@ -142,3 +142,33 @@ def test_native_calculator_input_errors_and_no_cpu_fallback(cvmlib, tmp_path):
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
     else:
         assert r.returncode == 0, r.stderr
+
+
+def test_native_calculator_reads_sym(cvmlib, tmp_path):
+    """cvmgpu_calc --sym: the same input errors through the .sym-built table; a foreign .sym is refused."""
+    import subprocess
+    from tools.circuitgen.build import write_artifact
+    exe = _calc()
+    art = circuit("babyadd4")
+    paths = write_artifact(art, str(tmp_path), with_cpp=False)          # no .dat: only the .sym names the inputs
+
+    def run(doc_text, sym):
+        j = tmp_path / "in.json"
+        j.write_text(doc_text)
+        return subprocess.run([exe, paths["cvm"], str(j), str(tmp_path / "o.wtns"), "--sym", sym], capture_output=True, text=True,
+                              timeout=120)
+
+    for text, msg in (('{"p": ["1"], "q": ["1", "2"]}', "Not enough values"),
+                      ('{"p": ["1", "2"], "q": ["1", "2"], "zz": "1"}', "Signal not found"),
+                      ('{"p": ["1", "2"]}', "Not all inputs have been set")):
+        r = run(text, paths["sym"])
+        assert r.returncode == 1 and msg in r.stderr, (text, r.stderr)
+    other = write_artifact(circuit("multiplier2"), str(tmp_path / "m2"))
+    r = run('{"q": ["1", "2"], "p": ["7", "8"]}', other["sym"])
+    assert r.returncode == 1 and "does not belong" in r.stderr
+    r = run('{"q": ["0x10", "0b11"], "p": ["7", "0o17"]}', paths["sym"])
+    from circom_cvm_b200 import engine as E
+    if E.device_count() == 0:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
