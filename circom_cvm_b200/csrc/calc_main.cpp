@@ -360,7 +360,8 @@ int main(int argc, char *argv[]) {
     try {
         if (cvmgpu_program_load(pos[0].c_str(), 0, &prog) != CVMGPU_OK) throw Fail(cvmgpu_last_error());
         cvmgpu_program_info info;
-        cvmgpu_program_info_get(prog, &info);
+        info.struct_size = sizeof(info);
+        if (cvmgpu_program_info_get(prog, &info) != CVMGPU_OK) throw Fail(cvmgpu_last_error());
         const uint64_t *witness = nullptr;
         uint32_t n_wit = 0;
         cvmgpu_program_witness(prog, &witness, &n_wit);

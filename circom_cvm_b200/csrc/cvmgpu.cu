@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <memory>
 #include <string>
 #include <vector>
@@ -64,16 +65,32 @@ struct cvmgpu_program {
     std::vector<uint8_t> wire_bool;  // per witness wire: the value is proven 0/1 by the trace compiler's typing
     uint64_t n_signals = 0;
     uint32_t n_inputs = 0, n_outputs = 0;
+    uint64_t layout_id = 0;          // identifies this program's value-store layout (r1cs bindings are cached against it)
     // device copies (uploaded on first use on the current device)
     int device = -1;
-    DevBuf d_tape, d_consts, d_store, d_inputs, d_status, d_wtns;
+    DevBuf d_tape, d_consts, d_wire_loc;
+};
+
+// the CSR of an .r1cs bound to one value-store layout (r1cs.hpp bind), on the device
+struct BoundDev {
+    uint64_t layout_id = ~0ull;      // 0: the plain layout (row = wire)
+    bool typed = false;
+    uint32_t n_brows = 0;
+    uint64_t macs = 0, bit_adds = 0, n_int_constraints = 0, n_bterms = 0, n_fterms = 0;
+    DevBuf d_hdr, d_terms, d_bhdr, d_bterms;
+    void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); layout_id = ~0ull; }
 };
 
 struct cvmgpu_r1cs {
     r1cs::File file;
     int device = -1;
-    DevBuf d_hdr, d_terms, d_coefs, d_cmag, d_store, d_wtns, d_bad;
+    DevBuf d_coefs, d_cmag, d_cint, d_store, d_wtns, d_bad;
+    BoundDev plain, typed;           // typed: the binding to the last program layout used (re-bound when it changes)
 };
+
+static uint64_t g_next_layout_id = 1;
+
+static void release_pipe_buffers();
 
 extern "C" const char *cvmgpu_last_error(void) { return g_err.c_str(); }
 
@@ -102,28 +119,35 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
         tr.trace();
         p->binv = tape::batch_inversions(tr);
         if (n_slots == 0) {
-            // Fewer slots per witness = more resident CTAs per SM (4 KiB of shared memory per slot and CTA), but more
-            // reloads/spills through HBM.  Pick the candidate with the best (work / resident warps) estimate; the
-            // kernel stops gaining from occupancy at about 20 warps per SM.
+            // Fewer slots per witness = more resident CTAs per SM (4 KiB of shared memory per field slot and CTA, 16 B per
+            // bit slot), but more reloads/spills through HBM.  Pick the candidate with the best (work / resident warps)
+            // estimate; the kernel stops gaining from occupancy at about 20 warps per SM.  Candidates beyond what the
+            // program can keep live at once cannot differ (max_live_field of the first build), so a program with few
+            // field values -- a hash circuit is almost all bits -- is compiled once.
             static const uint32_t cand[] = {8, 12, 16, 24, 32};
             double best = 0;
+            uint32_t live_field = 0xffffffffu;
             for (uint32_t c : cand) {
                 tape::Tape t = tape::build_tape(tr, c);
-                uint32_t ctas = std::min<uint32_t>(8, (227u * 1024u) / (c * 4096u + 1024u));
-                double warps = std::min<double>(4.0 * ctas, 20.0);
+                live_field = t.stats.max_live_field;
+                const size_t smem = (size_t)(c + (t.stats.n_ld ? tape::LD_RING : 0)) * 4096u + (size_t)t.n_bslots * 16u + 1024u;
+                uint32_t ctas = std::min<uint32_t>(8, (uint32_t)((227u * 1024u) / smem));
+                double warps = std::min<double>(4.0 * std::max<uint32_t>(1, ctas), 20.0);
                 double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st);
                 double cost = work / warps;
                 if (best == 0 || cost < best) {
                     best = cost;
                     p->tape = std::move(t);
                 }
+                if (c >= live_field + 2) break;   // every field value already has a slot
             }
         } else {
             p->tape = tape::build_tape(tr, n_slots);
         }
+        p->layout_id = g_next_layout_id++;
         p->tstats = tr.stats;
         p->wire_bool.reserve(tr.witness_ref.size());
-        for (uint32_t r : tr.witness_ref) p->wire_bool.push_back(tr.ref_is_bool(r) ? 1 : 0);
+        for (uint32_t loc : p->tape.wire_loc) p->wire_bool.push_back((loc & tape::ROW_BIT) ? 1 : 0);
         p->n_signals = (uint64_t)parser.prog.n_signals;
         p->witness.assign(parser.prog.witness.begin(), parser.prog.witness.end());
         p->n_inputs = (uint32_t)tr.n_inputs;
@@ -171,8 +195,22 @@ extern "C" int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32
     return build_program(parser, n_slots, out);
 }
 
-extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info) {
-    if (!p || !info) return fail(CVMGPU_ERR_ARG, "null argument");
+// info structs carry their size in the first field: the caller sets it to sizeof(its struct), the library fills
+// min(that, its own size) bytes -- a binding compiled against an older header keeps working when counters are added
+template <class T>
+static int fill_info(T *dst, const T &src) {
+    uint32_t want = dst->struct_size;
+    if (want < sizeof(uint32_t)) return fail(CVMGPU_ERR_ARG, "info.struct_size is not set (set it to sizeof(the struct) before the call)");
+    if (want > sizeof(T)) want = (uint32_t)sizeof(T);
+    memcpy(dst, &src, want);
+    dst->struct_size = want;
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *out) {
+    if (!p || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvmgpu_program_info v;
+    cvmgpu_program_info *info = &v;
     memset(info, 0, sizeof(*info));
     info->n_signals = p->n_signals;
     info->n_wires = p->tape.n_wires;
@@ -204,9 +242,13 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->tape_lut = p->tape.stats.n_lut;
     info->tape_ld_bool = p->tape.stats.n_ld_bool;
     info->tape_spill_st_bool = p->tape.stats.n_spill_st_bool;
-    info->n_bool_wires = 0;
-    for (uint8_t b : p->wire_bool) info->n_bool_wires += b;
-    return CVMGPU_OK;
+    info->n_bool_wires = p->tape.n_bwires;
+    info->n_bslots = p->tape.n_bslots;
+    info->n_frows = p->tape.n_frows;
+    info->n_brows = p->tape.n_brows;
+    info->max_live_field = p->tape.stats.max_live_field;
+    info->max_live_bool = p->tape.stats.max_live_bool;
+    return fill_info(out, v);
 }
 
 extern "C" int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_ins, const void **consts,
@@ -219,6 +261,13 @@ extern "C" int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, ui
     return CVMGPU_OK;
 }
 
+extern "C" int cvmgpu_program_wire_rows(const cvmgpu_program *p, const uint32_t **wire_loc, uint32_t *n) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (wire_loc) *wire_loc = p->tape.wire_loc.data();
+    if (n) *n = (uint32_t)p->tape.wire_loc.size();
+    return CVMGPU_OK;
+}
+
 extern "C" int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n) {
     if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
     if (signals) *signals = p->witness.data();
@@ -226,56 +275,79 @@ extern "C" int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **
     return CVMGPU_OK;
 }
 
+// device buffers belong to the device they were allocated on: release them there
+static void release_on(int device, std::initializer_list<DevBuf *> bufs) {
+    int cur = -1;
+    bool sw = device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+    for (DevBuf *b : bufs) b->release();
+    if (sw) cudaSetDevice(cur);
+}
+
 extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
     if (!p) return;
-    p->d_tape.release();
-    p->d_consts.release();
-    p->d_store.release();
-    p->d_inputs.release();
-    p->d_status.release();
-    p->d_wtns.release();
+    release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc});
+    release_pipe_buffers();
     delete p;
 }
 
-// dynamic shared memory per witness: the slots, plus the reload ring when the tape reloads anything
-static size_t tape_smem_per_witness(const cvmgpu_program *p) {
+// dynamic shared memory of a tape CTA of nt witnesses: the field slots, the reload ring when the tape reloads
+// anything, and the bit-slot file of each warp
+static size_t tape_field_smem_per_witness(const cvmgpu_program *p) {
     return ((size_t)p->tape.n_slots + (p->tape.stats.n_ld ? tape::LD_RING : 0)) * 2 * sizeof(uint4);
+}
+static size_t tape_smem(const cvmgpu_program *p, uint32_t nt) {
+    return tape_field_smem_per_witness(p) * nt + (((size_t)p->tape.n_bslots * (nt / 32) * 4 + 15) & ~(size_t)15);
 }
 
 static int upload_program(cvmgpu_program *p) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
     if (p->device == dev && p->d_tape.p) return CVMGPU_OK;
-    if (p->device != dev) {   // buffers belong to another device
-        p->d_tape = DevBuf(); p->d_consts = DevBuf(); p->d_store = DevBuf();
-        p->d_inputs = DevBuf(); p->d_status = DevBuf(); p->d_wtns = DevBuf();
-    }
+    if (p->device != dev) release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc});
     size_t tb = std::max<size_t>(16, p->tape.ins.size() * sizeof(tape::TapeIns));
     size_t cb = std::max<size_t>(32, p->consts_mont.size() * sizeof(fr::Fr));
     if (int rc = p->d_tape.ensure(tb)) return rc;
     if (int rc = p->d_consts.ensure(cb)) return rc;
+    if (int rc = p->d_wire_loc.ensure(std::max<size_t>(4, p->tape.wire_loc.size() * 4))) return rc;
     if (!p->tape.ins.empty())
         CUDA_TRY(cudaMemcpy(p->d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
     if (!p->consts_mont.empty())
         CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
-    // dynamic shared memory = n_slots x 32 B per witness of the CTA; the slots want the whole carve-out of the SM
-    // (more resident CTAs), nothing here relies on L1
-    const size_t per_w = tape_smem_per_witness(p);
-#define CVM_SET_ATTR(NT, W)                                                                                              \
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_w * NT * W))); \
-    CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, W>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout));
-    CVM_SET_ATTR(128, 1)
-    CVM_SET_ATTR(64, 1)
-    CVM_SET_ATTR(32, 1)
-    if (per_w * 128 * 2 <= 227 * 1024) { CVM_SET_ATTR(128, 2) }
-#undef CVM_SET_ATTR
+    if (!p->tape.wire_loc.empty())
+        CUDA_TRY(cudaMemcpy(p->d_wire_loc.p, p->tape.wire_loc.data(), p->tape.wire_loc.size() * 4, cudaMemcpyHostToDevice));
+    // the tables are read by kernels on non-blocking streams, which do not order themselves after the copies above
+    // (pageable-memory copies may return once the data is staged)
+    CUDA_TRY(cudaDeviceSynchronize());
     p->device = dev;
     return CVMGPU_OK;
 }
 
+// Typed value store of `bstride` witnesses: n_frows field rows (2 x 16 B x bstride each), then n_brows bit rows as one
+// 32-bit word per warp of witnesses and row, warp-major: word (w >> 5) * n_brows + row.
+static size_t store_field_bytes(const cvmgpu_program *p, uint64_t bstride) { return (size_t)p->tape.n_frows * 2 * sizeof(uint4) * bstride; }
+static size_t store_bit_bytes(const cvmgpu_program *p, uint64_t bstride) {
+    return (((size_t)((bstride + 31) / 32) * p->tape.n_brows * 4) + 15) & ~(size_t)15;
+}
 extern "C" size_t cvmgpu_store_bytes(const cvmgpu_program *p, uint64_t bstride) {
     if (!p) return 0;
-    return (size_t)p->tape.n_rows * 2 * sizeof(uint4) * bstride;
+    return std::max<size_t>(16, store_field_bytes(p, bstride) + store_bit_bytes(p, bstride));
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and device, and several programs may be live: only ever raise it
+template <int NT>
+static int launch_tape(const kern::TapeParams &tp, unsigned grid, size_t smem, cudaStream_t st) {
+    static size_t allowed[64] = {0};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && smem > allowed[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the slots want the whole carve-out of the SM (more resident CTAs), nothing here relies on L1
+        CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout));
+        allowed[dev] = smem;
+    }
+    kern::tape_kernel<NT><<<grid, NT, smem, st>>>(tp);
+    CUDA_TRY(cudaGetLastError());
+    return CVMGPU_OK;
 }
 
 extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride,
@@ -290,7 +362,10 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     tp.n_ins = (uint32_t)p->tape.ins.size();
     tp.consts = (const uint4 *)p->d_consts.p;
     tp.store = (uint4 *)d_store;
+    tp.bits = (uint32_t *)((char *)d_store + store_field_bytes(p, bstride));
     tp.bstride = bstride;
+    tp.n_brows = p->tape.n_brows;
+    tp.n_bslots = p->tape.n_bslots;
     tp.inputs = (const uint4 *)d_inputs;
     tp.n_inputs = p->n_inputs;
     tp.status = (uint32_t *)d_status;
@@ -302,44 +377,46 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
         int dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // One witness per thread, with smaller CTAs when the batch would leave SMs unevenly loaded (a 64 K batch is 512 CTAs
-    // of 128 for 148 SMs: 3.46 per SM).  The two-witnesses-per-thread variant is kept behind cvmgpu_set_tape_mode(2): the
-    // kernel is integer-issue bound, so the extra independent chain buys nothing and the halved number of resident warps
-    // costs (21.0 ms against 18.3 ms on Poseidon(2), profiles/r01_summary.md).
     const uint64_t want = (uint64_t)sms * 8;
-    const size_t per_w = tape_smem_per_witness(p);
-    tp.ring_off = 0;   // set per launch below (depends on the witnesses per CTA)
-    int mode = g_tape_mode;   // 0 auto, 1: W=1, 2: W=2 (cvmgpu_set_tape_mode, for experiments)
-    const bool w2_ok = per_w * 128 * 2 <= 227 * 1024;
-    const bool w2 = w2_ok && mode == 2;
+    const size_t per_w = tape_field_smem_per_witness(p);
     cudaStream_t st = (cudaStream_t)stream;
-    if (w2) {
-        uint64_t grid = (B + 255) / 256;
-        if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
-        tp.ring_off = p->tape.n_slots * 2 * 256;
-        kern::tape_kernel<128, 2><<<(unsigned)grid, 128, per_w * 256, st>>>(tp);
-    } else {
-        const uint32_t nt = (B / 128 >= want) ? 128u : (B / 64 >= want) ? 64u : 32u;
-        uint64_t grid = (B + nt - 1) / nt;
-        if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
-        tp.ring_off = p->tape.n_slots * 2 * nt;
-        if (nt == 128) kern::tape_kernel<128, 1><<<(unsigned)grid, 128, per_w * 128, st>>>(tp);
-        else if (nt == 64) kern::tape_kernel<64, 1><<<(unsigned)grid, 64, per_w * 64, st>>>(tp);
-        else kern::tape_kernel<32, 1><<<(unsigned)grid, 32, per_w * 32, st>>>(tp);
-    }
+    const uint32_t nt = (B / 128 >= want) ? 128u : (B / 64 >= want) ? 64u : 32u;
+    uint64_t grid = (B + nt - 1) / nt;
+    if (grid > 0x7fffffffull) return fail(CVMGPU_ERR_ARG, "batch too large for one launch");
+    tp.ring_off = p->tape.n_slots * 2 * nt;
+    tp.bslot_off = (uint32_t)(per_w * nt / sizeof(uint4));
+    const size_t smem = tape_smem(p, nt);
+    if (nt == 128) return launch_tape<128>(tp, (unsigned)grid, smem, st);
+    if (nt == 64) return launch_tape<64>(tp, (unsigned)grid, smem, st);
+    return launch_tape<32>(tp, (unsigned)grid, smem, st);
+}
+
+static kern::StoreView store_view(const cvmgpu_program *p, const void *d_store, uint64_t bstride) {
+    kern::StoreView sv;
+    sv.store = (const uint4 *)d_store;
+    sv.bits = (const uint32_t *)((const char *)d_store + store_field_bytes(p, bstride));
+    sv.bstride = bstride;
+    sv.n_brows = p->tape.n_brows;
+    sv.wire_loc = (const uint32_t *)p->d_wire_loc.p;
+    return sv;
+}
+
+extern "C" int cvmgpu_witness_export_range_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride,
+                                               uint32_t wire0, uint32_t n_sel, void *d_out, void *stream) {
+    if (!p || !d_store || !d_out) return fail(CVMGPU_ERR_ARG, "null argument");
+    if ((uint64_t)wire0 + n_sel > p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "wire range exceeds the witness");
+    if (B == 0 || n_sel == 0) return CVMGPU_OK;
+    if (int rc = upload_program(p)) return rc;
+    dim3 grid((unsigned)((B + 31) / 32), (n_sel + 31) / 32);
+    kern::export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(store_view(p, d_store, bstride), B, wire0, n_sel, (uint4 *)d_out);
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }
 
 extern "C" int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_wtns,
                                          void *stream) {
-    if (!p || !d_store || !d_wtns) return fail(CVMGPU_ERR_ARG, "null argument");
-    if (B == 0) return CVMGPU_OK;
-    dim3 grid((unsigned)((B + 31) / 32), (p->tape.n_wires + 31) / 32);
-    kern::export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4 *)d_store, bstride, B, p->tape.n_wires,
-                                                              (uint4 *)d_wtns);
-    CUDA_TRY(cudaGetLastError());
-    return CVMGPU_OK;
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    return cvmgpu_witness_export_range_dev(p, d_store, B, bstride, 0, p->tape.n_wires, d_wtns, stream);
 }
 
 static int upload_r1cs(cvmgpu_r1cs *r);
@@ -360,67 +437,106 @@ static uint64_t pick_chunk(uint64_t B, size_t bytes_per_witness) {
 struct PipeBufs {
     DevBuf store, inputs, status, wtns, bad;
     cudaStream_t stream = nullptr;
+    void release() {
+        store.release(); inputs.release(); status.release(); wtns.release(); bad.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
 };
+// per host thread and device; released by cvmgpu_program_free / cvmgpu_release_buffers on the calling thread
+struct PipeSet {
+    PipeBufs pipe[2];
+    int device = -1;
+};
+static thread_local PipeSet g_pipe;
 
-extern "C" int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
-                                            uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
+static void release_pipe_buffers() {
+    if (g_pipe.device < 0) return;
+    int cur = -1;
+    bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != g_pipe.device && cudaSetDevice(g_pipe.device) == cudaSuccess;
+    for (auto &pb : g_pipe.pipe) pb.release();
+    if (sw) cudaSetDevice(cur);
+    g_pipe.device = -1;
+}
+
+extern "C" void cvmgpu_release_buffers(void) { release_pipe_buffers(); }
+
+extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
+                                           uint32_t wire0, uint32_t n_sel, uint8_t *wtns_out, uint32_t *status,
+                                           uint32_t *first_bad) {
     if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
     if (!inputs && p->n_inputs) return fail(CVMGPU_ERR_ARG, "null argument");
     if (r && !first_bad) return fail(CVMGPU_ERR_ARG, "first_bad is required with an r1cs handle");
     if (r && r->file.n_wires != p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "r1cs and program disagree on the number of wires");
+    if (wtns_out && (uint64_t)wire0 + n_sel > p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "wire range exceeds the witness");
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
-    if (B == 0) return CVMGPU_OK;
+    if (!wtns_out) n_sel = 0;
     if (int rc = upload_program(p)) return rc;
     if (r)
         if (int rc = upload_r1cs(r)) return rc;
-    const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)p->tape.n_wires * 32;
-    size_t per_w = (size_t)p->tape.n_rows * 32 + in_row + (wtns_out ? out_row : 0) + 8;
+    const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)n_sel * 32;
+    size_t per_w = (cvmgpu_store_bytes(p, 1024) + 1023) / 1024 + in_row + out_row + 8;
     uint64_t fit = pick_chunk(B, 2 * per_w);
     if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
-    // chunks of 32 K witnesses keep the D2H of one chunk under the kernels of the next; without a witness download
-    // there is nothing to overlap and larger launches fill the GPU better
-    uint64_t chunk = std::min<uint64_t>(fit, wtns_out ? 32768 : 262144);
+    // chunks keep the D2H of one chunk under the kernels of the next: about 1 GiB of exported rows per chunk; without a
+    // witness download there is nothing to overlap and larger launches fill the GPU better
+    uint64_t chunk = 262144;
+    if (out_row) chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, ((1ull << 30) / out_row) / 1024 * 1024));
+    chunk = std::min<uint64_t>(fit, chunk);
     if (B <= chunk) chunk = B;
-    static thread_local PipeBufs pipe[2];
-    static thread_local int pipe_dev = -1;
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (pipe_dev != dev) {
-        for (auto &pb : pipe) { pb = PipeBufs(); }
-        pipe_dev = dev;
+    if (g_pipe.device != dev) {
+        release_pipe_buffers();
+        g_pipe.device = dev;
     }
+    PipeBufs *pipe = g_pipe.pipe;
     const int nbuf = (B > chunk) ? 2 : 1;
+    const uint64_t cstride = (chunk + 31) / 32 * 32;
     for (int k = 0; k < nbuf; k++) {
         PipeBufs &pb = pipe[k];
         if (!pb.stream) CUDA_TRY(cudaStreamCreateWithFlags(&pb.stream, cudaStreamNonBlocking));
-        if (int rc = pb.store.ensure(cvmgpu_store_bytes(p, chunk))) return rc;
+        if (int rc = pb.store.ensure(cvmgpu_store_bytes(p, cstride))) return rc;
         if (int rc = pb.inputs.ensure(std::max<size_t>(32, in_row * chunk))) return rc;
         if (int rc = pb.status.ensure(4 * chunk)) return rc;
         if (int rc = pb.bad.ensure(4 * chunk)) return rc;
-        if (wtns_out)
+        if (out_row)
             if (int rc = pb.wtns.ensure(out_row * chunk)) return rc;
     }
+    int rc = CVMGPU_OK;
     uint64_t idx = 0;
-    for (uint64_t b0 = 0; b0 < B; b0 += chunk, idx++) {
+    for (uint64_t b0 = 0; b0 < B && rc == CVMGPU_OK; b0 += chunk, idx++) {
         PipeBufs &pb = pipe[idx % nbuf];
         cudaStream_t s = pb.stream;
         uint64_t n = std::min<uint64_t>(chunk, B - b0);
+        cudaError_t e = cudaSuccess;
         // the stream's previous chunk must have left its buffers (stream order guarantees it)
-        if (in_row) CUDA_TRY(cudaMemcpyAsync(pb.inputs.p, inputs + b0 * in_row, n * in_row, cudaMemcpyHostToDevice, s));
-        if (int rc = cvmgpu_witness_batch_dev(p, pb.inputs.p, n, chunk, pb.store.p, pb.status.p, s)) return rc;
-        if (r) {
-            if (int rc = cvmgpu_r1cs_check_dev(r, pb.store.p, n, chunk, pb.bad.p, s)) return rc;
-            CUDA_TRY(cudaMemcpyAsync(first_bad + b0, pb.bad.p, n * 4, cudaMemcpyDeviceToHost, s));
+        if (in_row) e = cudaMemcpyAsync(pb.inputs.p, inputs + b0 * in_row, n * in_row, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) rc = cvmgpu_witness_batch_dev(p, pb.inputs.p, n, cstride, pb.store.p, pb.status.p, s);
+        if (e == cudaSuccess && rc == CVMGPU_OK && r) {
+            rc = cvmgpu_r1cs_check_store_dev(r, p, pb.store.p, n, cstride, pb.bad.p, s);
+            if (rc == CVMGPU_OK) e = cudaMemcpyAsync(first_bad + b0, pb.bad.p, n * 4, cudaMemcpyDeviceToHost, s);
         }
-        if (wtns_out) {
-            if (int rc = cvmgpu_witness_export_dev(p, pb.store.p, n, chunk, pb.wtns.p, s)) return rc;
-            CUDA_TRY(cudaMemcpyAsync(wtns_out + b0 * out_row, pb.wtns.p, n * out_row, cudaMemcpyDeviceToHost, s));
+        if (e == cudaSuccess && rc == CVMGPU_OK && out_row) {
+            rc = cvmgpu_witness_export_range_dev(p, pb.store.p, n, cstride, wire0, n_sel, pb.wtns.p, s);
+            if (rc == CVMGPU_OK) e = cudaMemcpyAsync(wtns_out + b0 * out_row, pb.wtns.p, n * out_row, cudaMemcpyDeviceToHost, s);
         }
-        if (status) CUDA_TRY(cudaMemcpyAsync(status + b0, pb.status.p, n * 4, cudaMemcpyDeviceToHost, s));
+        if (e == cudaSuccess && rc == CVMGPU_OK && status) e = cudaMemcpyAsync(status + b0, pb.status.p, n * 4, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = fail(CVMGPU_ERR_CUDA, std::string("host-buffer pipeline: ") + cudaGetErrorString(e));
     }
-    for (int k = 0; k < nbuf; k++) CUDA_TRY(cudaStreamSynchronize(pipe[k].stream));
-    return CVMGPU_OK;
+    // also on the error path: copies into the caller's buffers must not be in flight when this returns
+    for (int k = 0; k < nbuf; k++) {
+        cudaError_t e = cudaStreamSynchronize(pipe[k].stream);
+        if (e != cudaSuccess && rc == CVMGPU_OK) rc = fail(CVMGPU_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+extern "C" int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
+                                            uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    return cvmgpu_witness_batch_select(p, r, inputs, B, 0, p->tape.n_wires, wtns_out, status, first_bad);
 }
 
 extern "C" int cvmgpu_witness_batch(cvmgpu_program *p, const uint8_t *inputs, uint64_t B, uint8_t *wtns_out, uint32_t *status) {
@@ -460,8 +576,10 @@ extern "C" int cvmgpu_r1cs_load(const char *path, cvmgpu_r1cs **out) {
     return CVMGPU_OK;
 }
 
-extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info) {
-    if (!r || !info) return fail(CVMGPU_ERR_ARG, "null argument");
+extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *out) {
+    if (!r || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvmgpu_r1cs_info v;
+    cvmgpu_r1cs_info *info = &v;
     memset(info, 0, sizeof(*info));
     info->n_wires = r->file.n_wires;
     info->n_pub_out = r->file.n_pub_out;
@@ -477,58 +595,79 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info
     info->nnz_const = r->file.nnz_const;
     info->n_squares = r->file.n_squares;
     static_assert(r1cs::SAME_AS_A == R1CS_SAME_AS_A, "marker mismatch");
+    static_assert(r1cs::LOC_BIT == tape::ROW_BIT, "row type bit mismatch");
     info->n_coefs = (uint32_t)r->file.coefs.size();
-    return CVMGPU_OK;
+    // the binding to the last program layout this handle checked (cvmgpu_r1cs_check_store_dev / witness_batch_checked)
+    info->bound_int_constraints = r->typed.n_int_constraints;
+    info->bound_bit_terms = r->typed.n_bterms;
+    info->bound_field_terms = r->typed.layout_id == ~0ull ? 0 : r->typed.n_fterms;
+    info->bound_macs = r->typed.layout_id == ~0ull ? 0 : r->typed.macs;
+    info->bound_bit_adds = r->typed.bit_adds;
+    return fill_info(out, v);
 }
 
 extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
     if (!r) return;
-    r->d_hdr.release(); r->d_terms.release(); r->d_coefs.release(); r->d_cmag.release();
+    int cur = -1;
+    bool sw = r->device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != r->device && cudaSetDevice(r->device) == cudaSuccess;
+    r->d_coefs.release(); r->d_cmag.release(); r->d_cint.release();
     r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
+    r->plain.release();
+    r->typed.release();
+    if (sw) cudaSetDevice(cur);
     delete r;
+}
+
+static int upload_bound(const r1cs::Bound &b, BoundDev &d) {
+    if (int rc = d.d_hdr.ensure(b.hdr.size() * 4)) return rc;
+    if (int rc = d.d_terms.ensure(std::max<size_t>(16, b.fterms.size() * 8))) return rc;
+    if (int rc = d.d_bhdr.ensure(b.bhdr.size() * 4)) return rc;
+    if (int rc = d.d_bterms.ensure(std::max<size_t>(16, b.bterms.size() * 8))) return rc;
+    CUDA_TRY(cudaMemcpy(d.d_hdr.p, b.hdr.data(), b.hdr.size() * 4, cudaMemcpyHostToDevice));
+    if (!b.fterms.empty()) CUDA_TRY(cudaMemcpy(d.d_terms.p, b.fterms.data(), b.fterms.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_bhdr.p, b.bhdr.data(), b.bhdr.size() * 4, cudaMemcpyHostToDevice));
+    if (!b.bterms.empty()) CUDA_TRY(cudaMemcpy(d.d_bterms.p, b.bterms.data(), b.bterms.size() * 8, cudaMemcpyHostToDevice));
+    d.macs = b.macs;
+    d.bit_adds = b.bit_adds;
+    d.n_int_constraints = b.n_int_constraints;
+    d.n_bterms = b.bterms.size();
+    d.n_fterms = b.fterms.size();
+    CUDA_TRY(cudaDeviceSynchronize());
+    return CVMGPU_OK;
 }
 
 static int upload_r1cs(cvmgpu_r1cs *r) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (r->device == dev && r->d_hdr.p) return CVMGPU_OK;
-    if (r->device != dev) {
-        r->d_hdr = DevBuf(); r->d_terms = DevBuf(); r->d_coefs = DevBuf(); r->d_cmag = DevBuf();
-        r->d_store = DevBuf(); r->d_wtns = DevBuf(); r->d_bad = DevBuf();
+    if (r->device == dev && r->d_coefs.p) return CVMGPU_OK;
+    if (r->device != dev && r->device >= 0) {
+        int cur = dev;
+        if (cudaSetDevice(r->device) == cudaSuccess) {
+            r->d_coefs.release(); r->d_cmag.release(); r->d_cint.release();
+            r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
+            r->plain.release();
+            r->typed.release();
+            cudaSetDevice(cur);
+        }
     }
     const r1cs::File &f = r->file;
     std::vector<fr::Fr> cm;
     cm.reserve(f.coefs.size());
     for (const fr::Fr &c : f.coefs) cm.push_back(fr::to_mont(c));
-    std::vector<uint32_t> hdr(4 * f.ptr.size(), 0);
-    for (size_t j = 0; j < f.ptr.size(); j++) {
-        hdr[4 * j] = f.ptr[j];
-        if (j + 1 < f.ptr.size()) {
-            hdr[4 * j + 1] = f.split[3 * j];
-            hdr[4 * j + 2] = f.split[3 * j + 1];
-            hdr[4 * j + 3] = f.split[3 * j + 2];
-        }
-    }
-    if (int rc = r->d_hdr.ensure(hdr.size() * 4)) return rc;
-    if (int rc = r->d_terms.ensure(std::max<size_t>(16, f.terms.size() * 8))) return rc;
     if (int rc = r->d_coefs.ensure(cm.size() * 32)) return rc;
     if (int rc = r->d_cmag.ensure(f.cmag.size() * 4)) return rc;
+    if (int rc = r->d_cint.ensure(f.cint.size() * 8)) return rc;
     CUDA_TRY(cudaMemcpy(r->d_cmag.p, f.cmag.data(), f.cmag.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(r->d_hdr.p, hdr.data(), hdr.size() * 4, cudaMemcpyHostToDevice));
-    if (!f.terms.empty()) CUDA_TRY(cudaMemcpy(r->d_terms.p, f.terms.data(), f.terms.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(r->d_cint.p, f.cint.data(), f.cint.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(r->d_coefs.p, cm.data(), cm.size() * 32, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaDeviceSynchronize());
     r->device = dev;
     return CVMGPU_OK;
 }
 
-extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64_t B, uint64_t bstride, void *d_first_bad,
-                                     void *stream) {
-    if (!r || !d_store || !d_first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
-    if (B == 0) return CVMGPU_OK;
-    if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
-    if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
-    if (int rc = upload_r1cs(r)) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
+// bd: the CSR bound to the layout of d_store; bits / n_brows: its bit rows (nullptr / 0 for the plain layout)
+static int launch_check(cvmgpu_r1cs *r, const BoundDev &bd, const void *d_store, const uint32_t *bits, uint64_t B,
+                        uint64_t bstride, void *d_first_bad, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(d_first_bad, 0xff, B * 4, s));
     if (r->file.n_constraints == 0) return CVMGPU_OK;
     uint64_t gx = (B + R1CS_NT - 1) / R1CS_NT;
@@ -542,8 +681,8 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
         chunks = (r->file.n_constraints + per - 1) / per;
     }
     kern::R1csParams rp;
-    rp.hdr = (const uint4 *)r->d_hdr.p;
-    rp.terms = (const uint2 *)r->d_terms.p;
+    rp.hdr = (const uint4 *)bd.d_hdr.p;
+    rp.terms = (const uint2 *)bd.d_terms.p;
     rp.coefs = (const uint4 *)r->d_coefs.p;
     rp.cmag = (const uint32_t *)r->d_cmag.p;
     rp.n_cons = r->file.n_constraints;
@@ -552,15 +691,57 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     rp.bstride = bstride;
     rp.B = B;
     rp.first_bad = (uint32_t *)d_first_bad;
+    rp.bits = bits;
+    rp.n_brows = bd.n_brows;
+    rp.bhdr = (const uint32_t *)bd.d_bhdr.p;
+    rp.bterms = (const uint2 *)bd.d_bterms.p;
+    rp.cint = (const long long *)r->d_cint.p;
     dim3 grid((unsigned)gx, (unsigned)chunks);
     // resident CTAs per SM: 4 (128 registers) when the check is multiplier-bound (Poseidon: 28 % of the terms have
     // full-size coefficients, EdDSA 12 %), 5 (96 registers) when it is mostly +-1 / small coefficients and latency-bound
-    // (Sha256: 0.3 %); measured: Poseidon 17.9 vs 18.1 ms, Sha256(512) 112.9 vs 109.7 ms
     int minb = g_r1cs_minb ? g_r1cs_minb : (20 * r->file.nnz_general > r->file.nnz ? 4 : 5);
-    if (minb == 5) kern::r1cs_kernel<5><<<grid, R1CS_NT, 0, s>>>(rp);
-    else kern::r1cs_kernel<4><<<grid, R1CS_NT, 0, s>>>(rp);
+    if (bd.typed) {
+        if (minb == 5) kern::r1cs_kernel<5, true><<<grid, R1CS_NT, 0, s>>>(rp);
+        else kern::r1cs_kernel<4, true><<<grid, R1CS_NT, 0, s>>>(rp);
+    } else {
+        if (minb == 5) kern::r1cs_kernel<5, false><<<grid, R1CS_NT, 0, s>>>(rp);
+        else kern::r1cs_kernel<4, false><<<grid, R1CS_NT, 0, s>>>(rp);
+    }
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64_t B, uint64_t bstride, void *d_first_bad,
+                                     void *stream) {
+    if (!r || !d_store || !d_first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0) return CVMGPU_OK;
+    if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
+    if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
+    if (int rc = upload_r1cs(r)) return rc;
+    if (r->plain.layout_id != 0) {
+        if (int rc = upload_bound(r1cs::bind(r->file, nullptr), r->plain)) return rc;
+        r->plain.layout_id = 0;
+        r->plain.typed = false;
+    }
+    return launch_check(r, r->plain, d_store, nullptr, B, bstride, d_first_bad, (cudaStream_t)stream);
+}
+
+extern "C" int cvmgpu_r1cs_check_store_dev(cvmgpu_r1cs *r, cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride,
+                                           void *d_first_bad, void *stream) {
+    if (!r || !p || !d_store || !d_first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (r->file.n_wires != p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "r1cs and program disagree on the number of wires");
+    if (B == 0) return CVMGPU_OK;
+    if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
+    if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
+    if (int rc = upload_r1cs(r)) return rc;
+    if (r->typed.layout_id != p->layout_id) {
+        if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data()), r->typed)) return rc;
+        r->typed.layout_id = p->layout_id;
+        r->typed.typed = p->tape.n_brows != 0;
+        r->typed.n_brows = p->tape.n_brows;
+    }
+    const uint32_t *bits = (const uint32_t *)((const char *)d_store + store_field_bytes(p, bstride));
+    return launch_check(r, r->typed, d_store, bits, B, bstride, d_first_bad, (cudaStream_t)stream);
 }
 
 extern "C" int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, uint64_t bstride, void *d_store,
@@ -615,19 +796,22 @@ extern "C" int cvmgpu_fr_device_op(const char *op, const uint8_t *a, const uint8
     if (f == hostfr::F_NONE) return fail(CVMGPU_ERR_ARG, std::string("unknown field op ") + op);
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
     if (n == 0) return CVMGPU_OK;
-    void *da = nullptr, *db = nullptr, *dout = nullptr, *dund = nullptr;
-    CUDA_TRY(cudaMalloc(&da, n * 32));
-    CUDA_TRY(cudaMalloc(&db, n * 32));
-    CUDA_TRY(cudaMalloc(&dout, n * 32));
-    CUDA_TRY(cudaMalloc(&dund, n * 4));
-    CUDA_TRY(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(dund, 0, n * 4));
-    kern::fr_op_kernel<<<(unsigned)((n + 127) / 128), 128>>>((int)f, (const uint4 *)da, (const uint4 *)db, (uint4 *)dout, n,
-                                                            (uint32_t *)dund);
+    DevBuf da, db, dout, dund;
+    struct Guard {
+        DevBuf &a, &b, &c, &d;
+        ~Guard() { a.release(); b.release(); c.release(); d.release(); }
+    } guard{da, db, dout, dund};
+    if (int rc = da.ensure(n * 32)) return rc;
+    if (int rc = db.ensure(n * 32)) return rc;
+    if (int rc = dout.ensure(n * 32)) return rc;
+    if (int rc = dund.ensure(n * 4)) return rc;
+    CUDA_TRY(cudaMemcpy(da.p, a, n * 32, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db.p, b, n * 32, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(dund.p, 0, n * 4));
+    kern::fr_op_kernel<<<(unsigned)((n + 127) / 128), 128>>>((int)f, (const uint4 *)da.p, (const uint4 *)db.p, (uint4 *)dout.p, n,
+                                                            (uint32_t *)dund.p);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
-    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dund);
+    CUDA_TRY(cudaMemcpy(out, dout.p, n * 32, cudaMemcpyDeviceToHost));
     return CVMGPU_OK;
 }
 

@@ -928,9 +928,24 @@ FR_HD Fr mont_sqr(const Fr &a) {
 
 // canonical <-> Montgomery (generic/fr.cpp:211-255)
 FR_HD Fr to_mont(const Fr &a) { return mont_mul(a, r2_mont()); }
+// leaving Montgomery form is a pure reduction: a / 2^256 mod q = eight word-serial REDC steps (72 multiply-accumulates
+// instead of the 136 of a product by 1); (a + m*q) / 2^256 <= q, so one conditional subtraction finishes
 FR_HD Fr from_mont(const Fr &a) {
+#if defined(__CUDA_ARCH__) && !defined(FR_PORTABLE_MUL)
+    MontAcc t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.x[i] = a.v[i];
+    t.x[8] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.y[i] = 0;
+    t.pend = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) mont_acc_redc_step(t);
+    return reduce_once(mont_acc_value(t));
+#else
     Fr one = {{1, 0, 0, 0, 0, 0, 0, 0}};
     return mont_mul(a, one);
+#endif
 }
 
 // a^e for a fixed public exponent given as 8 limbs (square-and-multiply, MSB first); a in Montgomery form

@@ -44,13 +44,17 @@ struct TapeParams {
     const tape::TapeIns *tape;
     uint32_t n_ins;
     const uint4 *consts;     // Montgomery, 2 x uint4 per constant
-    uint4 *store;            // value store
+    uint4 *store;            // field rows of the value store
+    uint32_t *bits;          // bit rows: word (w >> 5) * n_brows + row holds the row's bit of the 32 witnesses of warp w >> 5
     uint64_t bstride;
+    uint32_t n_brows;
+    uint32_t n_bslots;       // bit slots per warp
     const uint4 *inputs;     // B x n_inputs x 2 uint4, canonical
     uint32_t n_inputs;
     uint32_t *status;
     uint64_t B;
-    uint32_t ring_off;       // uint4 offset of the reload ring inside the dynamic shared memory (after the slots)
+    uint32_t ring_off;       // uint4 offset of the reload ring inside the dynamic shared memory (after the field slots)
+    uint32_t bslot_off;      // uint4 offset of the bit-slot file (after the ring)
 };
 
 __device__ __forceinline__ Fr mont_bool(bool b) { return b ? fr::one_mont() : fr::zero(); }
@@ -65,9 +69,12 @@ __device__ __forceinline__ Fr op_input(Fr v) {
     return fr::to_mont(v);
 }
 
-// operand fetch: constant table (uniform address, L1-resident) or the thread's slot in shared memory
+// operand fetch: constant table (uniform address, L1-resident), the thread's field slot in shared memory, or -- for a
+// value typed 0/1 -- the thread's bit of the warp's word in the bit-slot file (bw = this warp's file)
 template <int NT>
-__device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint4 *consts, uint32_t idx, bool is_const, uint32_t tid) {
+__device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint32_t *bw, const uint4 *consts, uint32_t idx, bool is_const,
+                                           uint32_t tid) {
+    if (!is_const && (idx & tape::BSLOT)) return mont_bool((bw[idx & 0xffffu] >> (tid & 31u)) & 1u);
     uint4 lo, hi;
     if (is_const) {
         lo = __ldg(consts + 2 * (uint64_t)idx);
@@ -77,6 +84,13 @@ __device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint4 *cons
         hi = slots[(idx * 2 + 1) * NT + tid];
     }
     return unpack(lo, hi);
+}
+// truth value of an operand (select conditions): the bit itself when the value is typed 0/1
+template <int NT>
+__device__ __forceinline__ bool tape_truth(const uint4 *slots, const uint32_t *bw, const uint4 *consts, uint32_t idx, bool is_const,
+                                           uint32_t tid) {
+    if (!is_const && (idx & tape::BSLOT)) return (bw[idx & 0xffffu] >> (tid & 31u)) & 1u;
+    return !fr::is_zero(tape_operand<NT>(slots, bw, consts, idx, is_const, tid));
 }
 
 // integer-view operations, division, logic: shared by the tape's slow path and the device self-test.
@@ -120,56 +134,56 @@ __device__ __forceinline__ Fr slow_compute(uint32_t op, const Fr &a, const Fr &b
 }
 
 // Everything that is not on the fast path of the tape loop (integer-view operations, division, inputs).  Out of
-// line, operands and result go through the slots, so that the hot loop keeps its working set in registers.
+// line, operands and result go through the slots, so that the hot loop keeps its working set in registers.  A result
+// typed 0/1 is returned as `truth` (the caller packs the warp's bits); a field result is written to its slot here.
 template <int NT>
-__device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uint4 *consts, const uint4 *inputs,
-                                              uint32_t n_inputs, uint64_t w, uint32_t status, uint32_t tid) {
+__device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uint32_t *bw, const uint4 *consts, const uint4 *inputs,
+                                              uint32_t n_inputs, uint64_t w, uint32_t status, uint32_t tid, uint32_t &truth) {
     const uint32_t op = cur.x & 0xffu, flags = (cur.x >> 8) & 0xffu, dst = cur.x >> 16;
     Fr r;
     if (op == tape::T_INPUT) {
         const uint4 *src = inputs + (w * n_inputs + cur.y) * 2;
         r = op_input(unpack(src[0], src[1]));
     } else {
-        Fr a = tape_operand<NT>(slots, consts, cur.y, flags & 1u, tid);
+        Fr a = tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
         Fr b = fr::zero();
-        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand<NT>(slots, consts, cur.z, flags & 2u, tid);
+        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid);
         r = slow_compute(op, a, b, status);
     }
-    uint4 lo, hi;
-    pack(r, lo, hi);
-    slots[(dst * 2) * NT + tid] = lo;
-    slots[(dst * 2 + 1) * NT + tid] = hi;
+    truth = r.v[0] != 0u;   // a 0/1 value in Montgomery form is 0 or R mod q, whose low word is not 0
+    if (!(dst & tape::BSLOT_DST)) {
+        uint4 lo, hi;
+        pack(r, lo, hi);
+        slots[(dst * 2) * NT + tid] = lo;
+        slots[(dst * 2 + 1) * NT + tid] = hi;
+    }
     return status;
 }
 
 // One tape pass per witness.  Control flow is uniform (one instruction stream per circuit), so the branches on the
-// opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, DOT, SEL, EQ / NEQ / EQZ, BITC, the failure
+// opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, DOT, SEL, EQ / NEQ / EQZ, BITC, LUT, the failure
 // checks and the value-store moves; the result of a producing instruction can be written to its witness wire by
 // the same instruction (flag bit 3).
 //
-// W witnesses per thread (lanes tid + k*NT of a CTA that covers NT*W witnesses): W = 2 was an experiment (two
-// independent carry chains per thread); the kernel is bound by the IMAD.WIDE pipe, which more resident warps saturate
-// just as well (profiles/r01_summary.md), so it does not help and W = 1 is what runs.
-template <int NT, int W>
+// Typed values (tape.hpp build_tape): a result the trace compiler proved 0/1 goes to the BIT file -- the 32 lanes of a
+// warp pack their bits into one word (__ballot_sync), every lane stores that same word to the warp's slot (so each lane
+// later reads its own store: no fence needed), and a bit row of the value store is that word per warp: 4 bytes where a
+// field row costs 1 KiB.
+template <int NT>
 __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
-    constexpr int NS = NT * W;   // witnesses per CTA = stride of one slot half in shared memory
     extern __shared__ uint4 slots[];
-    uint32_t tk[W];
-    uint64_t w[W];
-    bool active[W];
-    uint32_t status[W];
-    uint4 *wbase[W];
-#pragma unroll
-    for (int k = 0; k < W; k++) {
-        tk[k] = threadIdx.x + k * NT;
-        w[k] = (uint64_t)blockIdx.x * NS + tk[k];
-        active[k] = w[k] < p.B;
-        if (!active[k]) w[k] = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
-        status[k] = 0;
-        wbase[k] = p.store + w[k];
-    }
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    uint64_t w = (uint64_t)blockIdx.x * NT + tid;
+    const bool active = w < p.B;
+    // a warp whose first witness exists owns its word of every bit row (its padding lanes carry copies of the last witness)
+    const bool warp_active = (w - lane) < p.B;
+    if (!active) w = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
+    uint32_t status = 0;
+    uint4 *const wbase = p.store + w;
     const uint64_t bstride = p.bstride;
     const uint4 *const consts = p.consts;
+    uint32_t *const bw = reinterpret_cast<uint32_t *>(slots + p.bslot_off) + (tid >> 5) * p.n_bslots;
+    uint32_t *const brow = p.bits + (warp_active ? (((uint64_t)blockIdx.x * NT + tid) >> 5) : 0ull) * p.n_brows;
 
     const uint4 *tp = reinterpret_cast<const uint4 *>(p.tape);
     const uint32_t n_ins = p.n_ins;
@@ -181,219 +195,186 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
-        Fr r[W];
+        Fr r;
+        uint32_t rb = 0;        // result of an instruction that produces a truth value
+        bool is_rb = false;
         if (op >= tape::T_ADD && op <= tape::T_MUL) {
-            Fr a[W], b[W];
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                a[k] = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
-                b[k] = tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]);
-            }
+            const Fr a = tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
+            const Fr b = tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid);
             if (op == tape::T_MUL) {
                 // bit-heavy programs (F_TRIVIAL, set by the tape builder): factors that are 0 or 1 at run time without
                 // being provably so (input bits of a hash) need no product; decided per warp to keep control flow uniform
                 bool cheap = false;
                 if (flags & tape::F_TRIVIAL) {
                     const Fr one = fr::one_mont();
-                    bool triv = true;
-#pragma unroll
-                    for (int k = 0; k < W; k++)
-                        triv = triv && (fr::is_zero(a[k]) || fr::is_zero(b[k]) || fr::equal(a[k], one) || fr::equal(b[k], one));
+                    const bool triv = fr::is_zero(a) || fr::is_zero(b) || fr::equal(a, one) || fr::equal(b, one);
                     cheap = __all_sync(0xffffffffu, triv);
                     if (cheap) {
+                        const bool z = fr::is_zero(a) || fr::is_zero(b);
+                        const bool a1 = fr::equal(a, one);
 #pragma unroll
-                        for (int k = 0; k < W; k++) {
-                            const bool z = fr::is_zero(a[k]) || fr::is_zero(b[k]);
-                            const bool a1 = fr::equal(a[k], one);
-#pragma unroll
-                            for (int i = 0; i < 8; i++) r[k].v[i] = z ? 0u : (a1 ? b[k].v[i] : a[k].v[i]);
-                        }
+                        for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : (a1 ? b.v[i] : a.v[i]);
                     }
                 }
                 if (!cheap) {
                     // same operand twice (x^2, x^4 of an S-box): the squaring needs 100 instead of 128 IMAD.WIDE
-                    if (cur.y == cur.z && (flags & 3u) == 0) {
-#pragma unroll
-                        for (int k = 0; k < W; k++) r[k] = fr::mont_sqr(a[k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < W; k++) r[k] = fr::mont_mul(a[k], b[k]);
-                    }
+                    if (cur.y == cur.z && (flags & 3u) == 0) r = fr::mont_sqr(a);
+                    else r = fr::mont_mul(a, b);
                 }
             } else if (op == tape::T_ADD) {
-#pragma unroll
-                for (int k = 0; k < W; k++) r[k] = fr::add(a[k], b[k]);
+                r = fr::add(a, b);
             } else {
-#pragma unroll
-                for (int k = 0; k < W; k++) r[k] = fr::sub(a[k], b[k]);
+                r = fr::sub(a, b);
             }
         } else if (op == tape::T_DOT) {
             // sum_j c_j * x_j (+ addend): cur.y terms in the following ceil(n/2) records of (constant, slot) pairs
             const uint32_t n = cur.y;
-            fr::Wide T[W];
-#pragma unroll
-            for (int k = 0; k < W; k++) fr::wide_zero(T[k]);
+            fr::Wide T;
+            fr::wide_zero(T);
             for (uint32_t j = 0; j < n; j++) {
                 const uint4 rec = __ldg(tp + pc + 1 + (j >> 1));
                 const uint32_t cidx = (j & 1u) ? rec.z : rec.x, slot = (j & 1u) ? rec.w : rec.y;
                 const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cidx), __ldg(consts + 2 * (uint64_t)cidx + 1));
-                Fr x[W];
-#pragma unroll
-                for (int k = 0; k < W; k++) x[k] = unpack(slots[(slot * 2) * NS + tk[k]], slots[(slot * 2 + 1) * NS + tk[k]]);
-#pragma unroll
-                for (int k = 0; k < W; k++) fr::wide_mac(T[k], c, x[k]);
+                const Fr x = tape_operand<NT>(slots, bw, consts, slot, false, tid);
+                fr::wide_mac(T, c, x);
             }
-#pragma unroll
-            for (int k = 0; k < W; k++) r[k] = fr::wide_reduce(T[k], n);
-            if (flags & tape::F_ADDEND) {
-#pragma unroll
-                for (int k = 0; k < W; k++) r[k] = fr::add(r[k], tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]));
-            }
+            r = fr::wide_reduce(T, n);
+            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid));
             pc += (n + 1) >> 1;
             raw = __ldg(tp + min(pc + 1, n_ins - 1));
         } else if (op == tape::T_SEL) {
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                const Fr a = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
-                const bool t = !fr::is_zero(a);
-                // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
-                const bool isc = t ? (flags & 2u) : (flags & 4u);
-                const uint32_t idx = t ? cur.z : cur.w;
-                uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-                if (t || !(flags & tape::F_CZERO)) {
-                    if (isc) { lo = __ldg(consts + 2 * (uint64_t)idx); hi = __ldg(consts + 2 * (uint64_t)idx + 1); }
-                    else { lo = slots[(idx * 2) * NS + tk[k]]; hi = slots[(idx * 2 + 1) * NS + tk[k]]; }
-                }
-                r[k] = unpack(lo, hi);
-            }
+            const bool t = tape_truth<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
+            // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
+            const bool isc = t ? (flags & 2u) : (flags & 4u);
+            const uint32_t idx = t ? cur.z : cur.w;
+            r = fr::zero();
+            if (t || !(flags & tape::F_CZERO)) r = tape_operand<NT>(slots, bw, consts, idx, isc, tid);
         } else if (op == tape::T_CADD) {
             // a + (b != 0 ? constant c : 0)
+            const Fr a = tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
+            const bool t = tape_truth<NT>(slots, bw, consts, cur.z, false, tid);
+            const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cur.w), __ldg(consts + 2 * (uint64_t)cur.w + 1));
+            const Fr sum = fr::add(a, c);
 #pragma unroll
-            for (int k = 0; k < W; k++) {
-                const Fr a = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
-                const Fr b = tape_operand<NS>(slots, consts, cur.z, false, tk[k]);
-                const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cur.w), __ldg(consts + 2 * (uint64_t)cur.w + 1));
-                const Fr sum = fr::add(a, c);
-                const bool t = !fr::is_zero(b);
-#pragma unroll
-                for (int i = 0; i < 8; i++) r[k].v[i] = t ? sum.v[i] : a.v[i];
-            }
+            for (int i = 0; i < 8; i++) r.v[i] = t ? sum.v[i] : a.v[i];
         } else if (op == tape::T_LUT) {
-            // boolean function of up to three 0/1 values: the low limb of a slot tells 0 from R mod q
-            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
-            const uint32_t nin = cur.z >> 8;
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                uint32_t idx = 0;
-#pragma unroll
-                for (uint32_t i = 0; i < 3; i++)
-                    if (i < nin) {
-                        const uint32_t slot = (cur.y >> (8 * i)) & 0xffu;
-                        idx |= (s32[((slot * 2) * NS + tk[k]) << 2] != 0u ? 1u : 0u) << i;
-                    }
-                r[k] = mont_bool((cur.z >> idx) & 1u);
-            }
+            // boolean function of up to three typed 0/1 values: this lane's bits of the three words index the table
+            const uint32_t nin = (cur.z >> 8) & 0xffu;
+            uint32_t idx = (bw[cur.y & 0xffffu] >> lane) & 1u;
+            if (nin > 1) idx |= ((bw[cur.y >> 16] >> lane) & 1u) << 1;
+            if (nin > 2) idx |= ((bw[cur.z >> 16] >> lane) & 1u) << 2;
+            rb = (cur.z >> idx) & 1u;
+            is_rb = true;
         } else if (op == tape::T_BITC) {
             // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
             const uint32_t limb = cur.z >> 5;
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * NS + tk[k]) << 2) + (limb & 3u)];
-                r[k] = mont_bool((word >> (cur.z & 31u)) & 1u);
-            }
+            const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * NT + tid) << 2) + (limb & 3u)];
+            rb = (word >> (cur.z & 31u)) & 1u;
+            is_rb = true;
         } else if (op == tape::T_EQ || op == tape::T_NEQ || op == tape::T_EQZ || op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
-            bool e[W];
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                const Fr a = tape_operand<NS>(slots, consts, cur.y, flags & 1u, tk[k]);
-                if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e[k] = fr::is_zero(a);
-                else e[k] = fr::equal(a, tape_operand<NS>(slots, consts, cur.z, flags & 2u, tk[k]));
-            }
+            bool e;
+            if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = !tape_truth<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
+            else e = fr::equal(tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid),
+                               tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid));
             if (op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
-#pragma unroll
-                for (int k = 0; k < W; k++)
-                    if (!e[k] && status[k] == 0) status[k] = cur.w;
+                if (!e && status == 0) status = cur.w;
                 continue;
             }
-#pragma unroll
-            for (int k = 0; k < W; k++) r[k] = mont_bool(op == tape::T_NEQ ? !e[k] : e[k]);
+            rb = (op == tape::T_NEQ) ? !e : e;
+            is_rb = true;
         } else if (op == tape::T_LD) {
+            if (dst & tape::BSLOT_DST) {     // a bit row: the warp's word (written earlier by these same lanes)
+                bw[dst & 0x7fffu] = brow[cur.w & ~tape::ROW_BIT];
+                continue;
+            }
             // reload stream (tape.hpp schedule_reloads): ring entry cur.z holds this value if F_RING; cur.y is the row
-            // to request now for the reload LD_RING reloads ahead.  Every reload commits exactly one cp.async group.
-            uint4 *ring = slots + p.ring_off + cur.z * 2 * NS;
+            // to request now for the reload LD_RING reloads ahead.  Every field reload commits exactly one cp.async group.
+            uint4 *ring = slots + p.ring_off + cur.z * 2 * NT;
             if (flags & tape::F_RING) asm volatile("cp.async.wait_group %0;" ::"n"(tape::LD_RING - 1) : "memory");
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                uint4 lo, hi;
-                if (flags & tape::F_RING) {
-                    lo = ring[tk[k]];
-                    hi = ring[NS + tk[k]];
-                } else {
-                    const uint4 *src = row_ptr(wbase[k], cur.w, bstride);
-                    lo = src[0];
-                    hi = src[bstride];
-                }
-                slots[(dst * 2) * NS + tk[k]] = lo;
-                slots[(dst * 2 + 1) * NS + tk[k]] = hi;
-                if (cur.y != tape::NO_ROW) {
-                    const uint4 *nxt = row_ptr(wbase[k], cur.y, bstride);
-                    const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ring + tk[k]);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(nxt) : "memory");
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + NS * 16), "l"(nxt + bstride) : "memory");
-                }
+            uint4 lo, hi;
+            if (flags & tape::F_RING) {
+                lo = ring[tid];
+                hi = ring[NT + tid];
+            } else {
+                const uint4 *src = row_ptr(wbase, cur.w, bstride);
+                lo = src[0];
+                hi = src[bstride];
+            }
+            slots[(dst * 2) * NT + tid] = lo;
+            slots[(dst * 2 + 1) * NT + tid] = hi;
+            if (cur.y != tape::NO_ROW) {
+                const uint4 *nxt = row_ptr(wbase, cur.y, bstride);
+                const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ring + tid);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(nxt) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + NT * 16), "l"(nxt + bstride) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             continue;
         } else if (op == tape::T_ST || op == tape::T_STC) {
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                uint4 lo, hi;
-                if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
-                else { lo = slots[(cur.y * 2) * NS + tk[k]]; hi = slots[(cur.y * 2 + 1) * NS + tk[k]]; }
-                if (active[k]) {
-                    uint4 *d = row_ptr(wbase[k], cur.w, bstride);
-                    d[0] = lo;
-                    d[bstride] = hi;
-                }
+            if (cur.w & tape::ROW_BIT) {
+                uint32_t word;
+                if (op == tape::T_STC) word = __ldg(consts + 2 * (uint64_t)cur.y).x ? 0xffffffffu : 0u;
+                else word = bw[cur.y & 0xffffu];
+                if (warp_active) brow[cur.w & ~tape::ROW_BIT] = word;
+                continue;
+            }
+            uint4 lo, hi;
+            if (op == tape::T_STC) { lo = __ldg(consts + 2 * (uint64_t)cur.y); hi = __ldg(consts + 2 * (uint64_t)cur.y + 1); }
+            else { lo = slots[(cur.y * 2) * NT + tid]; hi = slots[(cur.y * 2 + 1) * NT + tid]; }
+            if (active) {
+                uint4 *d = row_ptr(wbase, cur.w, bstride);
+                d[0] = lo;
+                d[bstride] = hi;
             }
             continue;
         } else {
-#pragma unroll
-            for (int k = 0; k < W; k++) {
-                status[k] = tape_slow_op<NS>(cur, slots, consts, p.inputs, p.n_inputs, w[k], status[k], tk[k]);
-                if ((flags & tape::F_STORE) && active[k]) {
-                    uint4 *d = row_ptr(wbase[k], cur.w, bstride);
-                    d[0] = slots[(dst * 2) * NS + tk[k]];
-                    d[bstride] = slots[(dst * 2 + 1) * NS + tk[k]];
+            status = tape_slow_op<NT>(cur, slots, bw, consts, p.inputs, p.n_inputs, w, status, tid, rb);
+            if (!(dst & tape::BSLOT_DST)) {
+                if ((flags & tape::F_STORE) && active) {
+                    uint4 *d = row_ptr(wbase, cur.w, bstride);
+                    d[0] = slots[(dst * 2) * NT + tid];
+                    d[bstride] = slots[(dst * 2 + 1) * NT + tid];
                 }
+                continue;
             }
-            continue;
+            is_rb = true;
         }
-#pragma unroll
-        for (int k = 0; k < W; k++) {
+        if (dst & tape::BSLOT_DST) {
+            const uint32_t word = __ballot_sync(0xffffffffu, is_rb ? rb != 0u : r.v[0] != 0u);
+            bw[dst & 0x7fffu] = word;
+            if ((flags & tape::F_STORE) && warp_active) brow[cur.w & ~tape::ROW_BIT] = word;
+        } else {
+            if (is_rb) r = mont_bool(rb);
             uint4 lo, hi;
-            pack(r[k], lo, hi);
-            slots[(dst * 2) * NS + tk[k]] = lo;
-            slots[(dst * 2 + 1) * NS + tk[k]] = hi;
-            if ((flags & tape::F_STORE) && active[k]) {
-                uint4 *d = row_ptr(wbase[k], cur.w, bstride);
+            pack(r, lo, hi);
+            slots[(dst * 2) * NT + tid] = lo;
+            slots[(dst * 2 + 1) * NT + tid] = hi;
+            if ((flags & tape::F_STORE) && active) {
+                uint4 *d = row_ptr(wbase, cur.w, bstride);
                 d[0] = lo;
                 d[bstride] = hi;
             }
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < W; k++)
-        if (active[k] && p.status) p.status[w[k]] = status[k];
+    if (active && p.status) p.status[w] = status;
 }
 
-// ---- value store (Montgomery SoA) -> .wtns rows (canonical AoS: B x n_wires x 32 B) ----------------
+// ---- typed value store -> .wtns rows (canonical AoS: B x n_sel x 32 B) ----------------------------------
 // Fuses Fr_toLongNormal + the 32-byte write of writeBinWitness (common/main.cpp:324-330) with the
 // SoA->AoS transpose: tile of 32 witnesses x 32 wires through shared memory so that both sides coalesce.
-__global__ void __launch_bounds__(256) export_kernel(const uint4 *store, uint64_t bstride, uint64_t B, uint32_t n_wires,
-                                                     uint4 *out) {
+// A wire is a field row (Montgomery, left with an 8-step REDC) or a bit row (one word per 32 witnesses, expanded to
+// the canonical 0 / 1 here); wire_loc == nullptr means the plain layout (row = wire, all field rows).
+// Wires [wire0, wire0 + n_sel) are exported (the whole witness, or e.g. only the public outputs and inputs).
+struct StoreView {
+    const uint4 *store;
+    const uint32_t *bits;
+    uint64_t bstride;
+    uint32_t n_brows;
+    const uint32_t *wire_loc;
+};
+__global__ void __launch_bounds__(256) export_kernel(StoreView sv, uint64_t B, uint32_t wire0, uint32_t n_sel, uint4 *out) {
     __shared__ uint32_t tile[32][32][9];   // [wire][witness][limb], padded
     const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const uint64_t w0 = (uint64_t)blockIdx.x * 32;
@@ -401,9 +382,15 @@ __global__ void __launch_bounds__(256) export_kernel(const uint4 *store, uint64_
     for (uint32_t k = wrp; k < 32; k += 8) {
         uint32_t row = r0 + k;
         uint64_t w = w0 + lane;
-        if (row < n_wires && w < B) {
-            const uint4 *src = store + ((uint64_t)row * 2) * bstride + w;
-            Fr v = fr::from_mont(unpack(src[0], src[bstride]));
+        if (row < n_sel && w < B) {
+            const uint32_t loc = sv.wire_loc ? __ldg(sv.wire_loc + wire0 + row) : wire0 + row;
+            Fr v = fr::zero();
+            if (loc & tape::ROW_BIT) {
+                v.v[0] = (__ldg(sv.bits + (w0 >> 5) * sv.n_brows + (loc & ~tape::ROW_BIT)) >> lane) & 1u;
+            } else {
+                const uint4 *src = sv.store + ((uint64_t)loc * 2) * sv.bstride + w;
+                v = fr::from_mont(unpack(src[0], src[sv.bstride]));
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) tile[k][lane][i] = v.v[i];
         }
@@ -412,8 +399,8 @@ __global__ void __launch_bounds__(256) export_kernel(const uint4 *store, uint64_
     for (uint32_t k = wrp; k < 32; k += 8) {   // k = witness in tile, lane = wire in tile
         uint64_t w = w0 + k;
         uint32_t row = r0 + lane;
-        if (row < n_wires && w < B) {
-            uint4 *d = out + (w * n_wires + row) * 2;
+        if (row < n_sel && w < B) {
+            uint4 *d = out + (w * n_sel + row) * 2;
             d[0] = make_uint4(tile[lane][k][0], tile[lane][k][1], tile[lane][k][2], tile[lane][k][3]);
             d[1] = make_uint4(tile[lane][k][4], tile[lane][k][5], tile[lane][k][6], tile[lane][k][7]);
         }
@@ -471,6 +458,14 @@ struct R1csParams {
     uint64_t bstride;
     uint64_t B;
     uint32_t *first_bad;        // B words, pre-set to 0xffffffff
+    // typed stores (a program's layout, tape.hpp): terms on bit rows live in their own CSR.  bhdr[j] = begin of LC j's
+    // bit terms (3*n_cons+1 entries); bit 31 of bhdr[3c] marks a constraint made only of bit terms with coefficients that
+    // fit 64-bit integers (cint): it is evaluated in plain integers.  bterms = (bit row, coefficient index).
+    const uint32_t *bits;
+    uint32_t n_brows;
+    const uint32_t *bhdr;
+    const uint2 *bterms;
+    const long long *cint;
 };
 
 // One linear combination.  Its terms are ordered by coefficient class (r1cs.hpp):
@@ -604,15 +599,43 @@ __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, ui
     return acc;
 }
 
-template <int MINB>
+// bit-row terms of one linear combination in the field: acc += bit ? coefficient : 0 (no multiplication)
+__device__ __forceinline__ Fr lc_bits(const R1csParams &p, const uint32_t *brow, uint32_t lane, uint32_t b, uint32_t e, Fr acc) {
+    for (uint32_t t = b; t < e; t++) {
+        const uint2 term = __ldg(p.bterms + t);
+        const bool bit = (__ldg(brow + term.x) >> lane) & 1u;
+        const uint4 lo = __ldg(p.coefs + 2 * (uint64_t)term.y), hi = __ldg(p.coefs + 2 * (uint64_t)term.y + 1);
+        Fr c;
+        c.v[0] = bit ? lo.x : 0u; c.v[1] = bit ? lo.y : 0u; c.v[2] = bit ? lo.z : 0u; c.v[3] = bit ? lo.w : 0u;
+        c.v[4] = bit ? hi.x : 0u; c.v[5] = bit ? hi.y : 0u; c.v[6] = bit ? hi.z : 0u; c.v[7] = bit ? hi.w : 0u;
+        acc = fr::add(acc, c);
+    }
+    return acc;
+}
+// the same in plain integers (the host guarantees that no partial sum leaves 63 bits)
+__device__ __forceinline__ long long lc_int(const R1csParams &p, const uint32_t *brow, uint32_t lane, uint32_t b, uint32_t e) {
+    long long acc = 0;
+#pragma unroll 4
+    for (uint32_t t = b; t < e; t++) {
+        const uint2 term = __ldg(p.bterms + t);
+        const uint32_t word = __ldg(brow + term.x);
+        const long long c = __ldg(p.cint + term.y);
+        acc += ((word >> lane) & 1u) ? c : 0ll;
+    }
+    return acc;
+}
+
+template <int MINB, bool TYPED>
 __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     __shared__ uint4 ring[R1CS_STAGES * 2 * R1CS_NT];
     uint64_t w = (uint64_t)blockIdx.x * R1CS_NT + threadIdx.x;
     const bool active = w < p.B;
     if (!active) w = p.B - 1;
+    const uint32_t lane = (uint32_t)w & 31u;
     const uint32_t c0 = blockIdx.y * p.cons_per_chunk;
     const uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
     const uint4 *wbase = p.store + w;
+    const uint32_t *brow = TYPED ? p.bits + (w >> 5) * p.n_brows : nullptr;
     const uint32_t t_end = __ldg(&p.hdr[3 * c1].x);
     {
         TermStream ts;
@@ -628,19 +651,43 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     for (uint32_t c = c0; c < c1; c++) {
         // headers of A, B, C and of the next constraint's A (its begin is the end of C)
         const uint4 hB = __ldg(p.hdr + 3 * c + 1), hC = __ldg(p.hdr + 3 * c + 2), hN = __ldg(p.hdr + 3 * c + 3);
+        uint32_t bA = 0, bB = 0, bC = 0, bN = 0;
+        if (TYPED) {
+            bA = __ldg(p.bhdr + 3 * c);
+            bB = __ldg(p.bhdr + 3 * c + 1) & 0x7fffffffu;
+            bC = __ldg(p.bhdr + 3 * c + 2) & 0x7fffffffu;
+            bN = __ldg(p.bhdr + 3 * c + 3) & 0x7fffffffu;
+            if (bA >> 31) {
+                // every term is a 0/1 wire with a small integer coefficient: |A*B - C| is far below q, so the constraint
+                // holds mod q iff it holds in the integers
+                bA &= 0x7fffffffu;
+                const long long ia = lc_int(p, brow, lane, bA, bB), ib = lc_int(p, brow, lane, bB, bC), ic = lc_int(p, brow, lane, bC, bN);
+                const long long lo = ia * ib, hi = __mul64hi(ia, ib);
+                if (bad == 0xffffffffu && (lo != ic || hi != (ic >> 63))) bad = c;
+                hA = hN;
+                continue;
+            }
+        }
+        const bool hasA = hA.x != hB.x || bA != bB, hasC = hC.x != hN.x || bC != bN;
+        const bool hasB = hB.x != hC.x || bB != bC || hB.y == R1CS_SAME_AS_A;
         Fr prod = fr::zero();
         if (hB.y == R1CS_SAME_AS_A) {        // B repeats A (r1cs.hpp): one evaluation, one squaring
-            const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            Fr sa = fr::zero();
+            if (hA.x != hB.x) sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            if (TYPED) sa = lc_bits(p, brow, lane, bA, bB, sa);
             const Fr one = fr::one_mont();
             if (fr::is_zero(sa)) prod = fr::zero();
             else if (sa.v[0] == one.v[0] && fr::equal(sa, one)) prod = one;
             else prod = fr::mont_sqr(sa);
-        } else if (hA.x != hB.x && hB.x != hC.x) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
-            const Fr sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
-            const Fr sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
+        } else if (hasA && hasB) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
+            Fr sa = fr::zero(), sb = fr::zero();
+            if (hA.x != hB.x) sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            if (TYPED) sa = lc_bits(p, brow, lane, bA, bB, sa);
+            if (hB.x != hC.x) sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
+            if (TYPED) sb = lc_bits(p, brow, lane, bB, bC, sb);
             // trivial factors need no product: 0, 1 and -1 (bit-valued wires and the +-1 combinations of them that
-            // fill hash circuits: Sha256's 61 904 quadratic constraints per witness are almost all of this kind).
-            // The branch is per lane; a warp pays for the multiplication only if one of its witnesses needs it.
+            // fill hash circuits).  The branch is per lane; a warp pays for the multiplication only if one of its
+            // witnesses needs it.
             const Fr one = fr::one_mont();
             const Fr mone = fr::minus_one_mont();
             // (the low limb filters first: general field values fail it with one comparison per case)
@@ -652,12 +699,13 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
             else if (sa.v[0] == sb.v[0] && fr::equal(sa, sb)) prod = fr::mont_sqr(sa);   // S-box squarings: A and B are the same combination
             else prod = fr::mont_mul(sa, sb);
         } else {
-            // the terms of a lone A or B still occupy the stream: consume them
+            // the field terms of a lone A or B still occupy the stream: consume them
             if (hA.x != hB.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hA, hB.x);
             if (hB.x != hC.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hB, hC.x);
         }
         Fr sc = fr::zero();
         if (hC.x != hN.x) sc = lc_any(p, wbase, ring, t_end, hC, hN.x);
+        if (TYPED && hasC) sc = lc_bits(p, brow, lane, bC, bN, sc);
         if (bad == 0xffffffffu && !fr::equal(prod, sc)) bad = c;
         hA = hN;
     }

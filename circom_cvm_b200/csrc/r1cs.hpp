@@ -48,7 +48,102 @@ struct File {
     // what the check kernel executes per witness: 64 multiply-accumulates per general term + 72 per reduction of a dot
     // product (<= 16 terms), 8 per small term + 170 per small-class reduction, 136 per quadratic constraint
     uint64_t macs = 0, n_quadratic = 0, n_linear = 0;
+    // per coefficient: its value as a signed 64-bit integer when |c| < 2^62 (c or c - q), and whether it has one
+    std::vector<int64_t> cint;
+    std::vector<uint8_t> cint_ok;
 };
+
+// The CSR bound to a typed value store (tape.hpp: a wire is a field row or a bit row).  Field-row terms keep the
+// layout above (hdr = {begin, end of +-2^k, of small +, of small -} per LC, rows instead of wires); bit-row terms go to a
+// second CSR (bhdr / bterms).  A constraint whose terms are ALL bit rows with 64-bit integer coefficients (partial sums
+// below 2^62) is marked in bit 31 of bhdr[3c] and evaluated in plain integers: (A*B - C) = 0 mod q iff = 0 in Z then.
+struct Bound {
+    std::vector<uint32_t> hdr;      // 4 * (3 * n_constraints + 1)
+    std::vector<Term> fterms;
+    std::vector<uint32_t> bhdr;     // 3 * n_constraints + 1
+    std::vector<Term> bterms;       // (bit row, coefficient index)
+    uint64_t n_int_constraints = 0, n_field_constraints = 0;
+    // 32x32->64 multiply-accumulates the check executes per witness on this layout (upper bound: products with a 0 / +-1
+    // factor are skipped at run time), and its executed field additions of bit-row terms
+    uint64_t macs = 0, bit_adds = 0;
+};
+
+static const uint32_t LOC_BIT = 0x80000000u;   // tape::ROW_BIT
+
+// wire_loc == nullptr: the plain layout (row = wire, no bit rows)
+inline Bound bind(const File &f, const uint32_t *wire_loc) {
+    Bound b;
+    const size_t n_lc = f.ptr.size() - 1;
+    b.hdr.assign(4 * (n_lc + 1), 0);
+    b.bhdr.assign(n_lc + 1, 0);
+    b.fterms.reserve(f.terms.size());
+    auto loc_of = [&](uint32_t wire) -> uint32_t { return wire_loc ? wire_loc[wire] : wire; };
+    for (uint32_t c = 0; c < f.n_constraints; c++) {
+        // source range of each LC (a B that repeats A has no terms of its own in File)
+        uint32_t sb[3], se[3];
+        bool same_b = false;
+        for (int k = 0; k < 3; k++) {
+            const size_t j = 3 * (size_t)c + k;
+            sb[k] = f.ptr[j];
+            se[k] = f.ptr[j + 1];
+            if (k == 1 && f.split[3 * j] == SAME_AS_A) same_b = true;
+        }
+        bool intok = wire_loc != nullptr;
+        for (int k = 0; k < 3 && intok; k++) {
+            const int src = (k == 1 && same_b) ? 0 : k;
+            uint64_t sumabs = 0;
+            for (uint32_t t = sb[src]; t < se[src] && intok; t++) {
+                const Term &tm = f.terms[t];
+                if (!(loc_of(tm.wire & 0x0fffffffu) & LOC_BIT) || !f.cint_ok[tm.coef]) { intok = false; break; }
+                const int64_t v = f.cint[tm.coef];
+                sumabs += (uint64_t)(v < 0 ? -v : v);
+                if (sumabs >> 62) intok = false;
+            }
+        }
+        if (intok) b.n_int_constraints++; else b.n_field_constraints++;
+        bool has[3] = {false, false, false};
+        for (int k = 0; k < 3; k++) {
+            const size_t j = 3 * (size_t)c + k;
+            const uint32_t fb = (uint32_t)b.fterms.size();
+            b.hdr[4 * j] = fb;
+            b.bhdr[j] = (uint32_t)b.bterms.size() | ((k == 0 && intok) ? 0x80000000u : 0u);
+            if (k == 1 && same_b && !intok) {
+                b.hdr[4 * j + 1] = SAME_AS_A;
+                b.hdr[4 * j + 2] = fb;
+                b.hdr[4 * j + 3] = fb;
+                has[1] = true;
+                continue;
+            }
+            const int src = (k == 1 && same_b) ? 0 : k;
+            const size_t js = 3 * (size_t)c + src;
+            const uint32_t e0 = f.split[3 * js], e1 = f.split[3 * js + 1], e2 = f.split[3 * js + 2];
+            uint32_t n[4] = {0, 0, 0, 0}, n_const = 0;
+            for (uint32_t t = sb[src]; t < se[src]; t++) {
+                const Term &tm = f.terms[t];
+                const uint32_t loc = loc_of(tm.wire & 0x0fffffffu);
+                if (loc & LOC_BIT) {
+                    b.bterms.push_back(Term{loc & ~LOC_BIT, tm.coef});
+                    if (!intok) b.bit_adds++;
+                    continue;
+                }
+                b.fterms.push_back(Term{loc | (tm.wire & 0xf0000000u), tm.coef});
+                const int cls = t < e0 ? 0 : t < e1 ? 1 : t < e2 ? 2 : 3;
+                n[cls]++;
+                if (cls == 3 && (tm.wire >> 31)) n_const++;
+            }
+            b.hdr[4 * j + 1] = fb + n[0];
+            b.hdr[4 * j + 2] = fb + n[0] + n[1];
+            b.hdr[4 * j + 3] = fb + n[0] + n[1] + n[2];
+            const uint64_t n3 = n[3] - n_const;
+            b.macs += 8 * (uint64_t)(n[1] + n[2]) + 170 * (uint64_t)((n[1] ? 1 : 0) + (n[2] ? 1 : 0)) + 64 * n3 + 72 * ((n3 + 15) / 16);
+            has[k] = se[src] > sb[src];
+        }
+        if (!intok && has[0] && has[1]) b.macs += 136;
+    }
+    b.hdr[4 * n_lc] = (uint32_t)b.fterms.size();
+    b.bhdr[n_lc] = (uint32_t)b.bterms.size();
+    return b;
+}
 
 struct Error : std::runtime_error {
     using std::runtime_error::runtime_error;
@@ -159,6 +254,19 @@ inline File load(const std::string &path) {
             out.cmag[i] = (sn ? 1u : 0u) | ((m == 2 ? 1u : m == 4 ? 2u : 3u) << 1);
         } else if (sp) { kind[i] = 1; out.cmag[i] = c.v[0]; }
         else if (sn) { kind[i] = 2; out.cmag[i] = n.v[0]; }
+    }
+    out.cint.assign(out.coefs.size(), 0);
+    out.cint_ok.assign(out.coefs.size(), 0);
+    for (size_t i = 0; i < out.coefs.size(); i++) {
+        const fr::Fr &c = out.coefs[i];
+        const fr::Fr n = fr::neg(c);
+        auto fits = [](const fr::Fr &x) {
+            for (int k = 2; k < 8; k++)
+                if (x.v[k]) return false;
+            return (x.v[1] >> 30) == 0;
+        };
+        if (fits(c)) { out.cint[i] = (int64_t)(((uint64_t)c.v[1] << 32) | c.v[0]); out.cint_ok[i] = 1; }
+        else if (fits(n)) { out.cint[i] = -(int64_t)(((uint64_t)n.v[1] << 32) | n.v[0]); out.cint_ok[i] = 1; }
     }
     out.split.resize(3 * (size_t)(out.ptr.size() - 1));
     for (size_t j = 0; j + 1 < out.ptr.size(); j++) {

@@ -6,6 +6,8 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -19,12 +21,12 @@ struct TapeIns {
     uint8_t op;
     uint8_t flags;    // bit0: a is a constant index, bit1: b is constant, bit2: c is constant,
                       // bit3: the result is also stored to value-store row c (fused witness-wire store)
-    uint16_t dst;     // slot
-    uint32_t a, b;    // slot or constant index; T_INPUT: a = input index; T_BITC: b = bit number;
-                      // T_LUT: a = three input slots (one byte each), b = truth table | number of inputs << 8;
+    uint16_t dst;     // slot; BSLOT_DST: a slot of the bit file (the value is typed 0/1)
+    uint32_t a, b;    // slot (BSLOT: of the bit file) or constant index; T_INPUT: a = input index; T_BITC: b = bit number;
+                      // T_LUT: a = bit slots 0 | 1 << 16, b = truth table | number of inputs << 8 | bit slot 2 << 16;
                       // T_LD: a = row to request now for the reload LD_RING reloads ahead (NO_ROW: none), b = ring entry
-    uint32_t c;       // T_SEL: third operand; T_LD/T_ST/T_STC: value-store row; T_FAIL_IF/T_FAIL_NE: status;
-                      // with flag bit3: value-store row
+    uint32_t c;       // T_SEL: third operand; T_LD/T_ST/T_STC: value-store row (ROW_BIT: a bit row); T_FAIL_IF/T_FAIL_NE:
+                      // status; with flag bit3: value-store row
 };
 static const uint8_t F_STORE = 8;
 static const uint8_t F_CZERO = 16;
@@ -32,6 +34,9 @@ static const uint8_t F_TRIVIAL = 16;  // T_MUL: check at run time whether the fa
 static const uint8_t F_ADDEND = 32;
 static const uint8_t F_RING = 64;    // T_LD: the value was requested LD_RING reloads ago and sits in ring entry b
 static const uint32_t LD_RING = 4;   // reloads in flight per witness (32 B of shared memory each)
+static const uint32_t BSLOT = 0x40000000u;     // operand field: the value lives in the bit-slot file (one word per warp; bit = lane)
+static const uint16_t BSLOT_DST = 0x8000;      // dst field: idem
+static const uint32_t ROW_BIT = 0x80000000u;   // row field: a bit row (one word per warp) instead of a field row
 static const uint32_t NO_ROW = 0xffffffffu;  // T_DOT: field b holds an addend (slot, or constant index with bit1)   // T_SEL: the third operand is the constant 0 (field c is free for the fused store)
 static_assert(sizeof(TapeIns) == 16, "tape instruction must be 16 bytes");
 
@@ -41,6 +46,7 @@ struct TapeStats {
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
     uint64_t n_ld_bool = 0, n_spill_st_bool = 0;   // of n_ld / n_spill_st: the value is typed 0/1 (what compact bit rows would shrink)
     uint32_t n_spill_rows = 0;
+    uint32_t max_live_field = 0, max_live_bool = 0;   // simultaneously live values of each kind (unlimited slots)
     // 32x32->64 multiply-accumulates the kernel executes per witness: 136 per Montgomery product (also the one that brings
     // an input to Montgomery form and the one after an inversion), 64 per DOT term + 72 per DOT reduction, and the
     // 20 x 90 of the safegcd inversion's matrix updates
@@ -52,7 +58,12 @@ struct Tape {
     std::vector<TapeIns> ins;
     uint32_t n_slots = 0;
     uint32_t n_wires = 0;
-    uint32_t n_rows = 0;      // wires + spill rows
+    uint32_t n_rows = 0;      // n_frows + n_brows
+    // typed value store: field rows (32 B per witness) hold the field-typed wires [0, n_fwires) and field spills; bit rows
+    // (one 32-bit word per warp of witnesses) hold the wires proven 0/1 [0, n_bwires) and bit spills
+    uint32_t n_bslots = 0;    // bit slots per warp
+    uint32_t n_frows = 0, n_brows = 0, n_fwires = 0, n_bwires = 0;
+    std::vector<uint32_t> wire_loc;   // per witness wire: field row, or ROW_BIT | bit row
     TapeStats stats;
 };
 
@@ -220,20 +231,28 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
     // a select.  cadd[i] = which operand (0: a, 1: b) is the select.
     std::unordered_map<uint32_t, int> cadd;
     if (enable) {
+        // The select may have other users (the same bit * 2^k enters several sums of a hash round): every ADD that takes it
+        // re-does the select from the bit -- which costs a CADD nothing -- and the select itself disappears once no other
+        // kind of user is left.  Otherwise such selects stay live as 32-byte field values across whole rounds.
+        auto is_bit_times_const = [&](uint32_t r) {
+            if (r == NO_REF || (r & CONST_FLAG) || absorbed[r]) return false;
+            const SOp &sel = ops[r];
+            return sel.op == T_SEL && !(sel.a & CONST_FLAG) && (sel.b & CONST_FLAG) && (sel.c & CONST_FLAG) &&
+                   fr::is_zero(tr.consts[sel.c & ~CONST_FLAG]);
+        };
+        std::vector<uint32_t> rem(uses);
         for (size_t i = 0; i < N; i++) {
             if (!live[i] || absorbed[i] || ops[i].op != T_ADD || roots.count((uint32_t)i)) continue;
             for (int k = 0; k < 2; k++) {
                 uint32_t r = k ? ops[i].b : ops[i].a;
-                if (r == NO_REF || (r & CONST_FLAG) || uses[r] != 1 || absorbed[r]) continue;
-                const SOp &sel = ops[r];
-                if (sel.op == T_SEL && !(sel.a & CONST_FLAG) && (sel.b & CONST_FLAG) && (sel.c & CONST_FLAG) &&
-                    fr::is_zero(tr.consts[sel.c & ~CONST_FLAG])) {
-                    absorbed[r] = 1;
-                    cadd.emplace((uint32_t)i, k);
-                    break;
-                }
+                if (!is_bit_times_const(r)) continue;
+                rem[r]--;
+                cadd.emplace((uint32_t)i, k);
+                break;
             }
         }
+        for (size_t r = 0; r < N; r++)
+            if (live[r] && rem[r] == 0 && is_bit_times_const((uint32_t)r)) absorbed[r] = 1;
     }
     std::vector<uint32_t> remap(N, NO_REF);
     auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
@@ -289,28 +308,31 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
 }
 
 // ---- reload stream ---------------------------------------------------------------------------------------
-// The rows a tape reloads (T_LD) and their order are fixed, so the kernel streams them: the n-th reload's row is
-// requested (cp.async into a per-witness ring in shared memory) when reload n - LD_RING executes, and reload n finds
-// it there -- HBM latency leaves the dependence chain, which is what small batches (few resident warps) are bound by.
-// A reload is only streamed when the store that produced its row precedes the request point (spill rows are
-// recycled); the others load directly, as before.
+// The FIELD rows a tape reloads (T_LD into a field slot) and their order are fixed, so the kernel streams them: the
+// n-th reload's row is requested (cp.async into a per-witness ring in shared memory) when reload n - LD_RING executes,
+// and reload n finds it there -- HBM latency leaves the dependence chain, which is what small batches (few resident
+// warps) are bound by.  A reload is only streamed when the store that produced its row precedes the request point
+// (spill rows are recycled); the others load directly.  Bit-row reloads (one word per warp) are not streamed.
+inline bool is_field_ld(const TapeIns &in) { return in.op == T_LD && !(in.dst & BSLOT_DST); }
+
 inline void schedule_reloads(Tape &t) {
     std::vector<uint32_t> ld_pos, ld_store;
-    std::vector<uint32_t> last_store(t.n_rows, NO_ROW);
+    std::vector<uint32_t> last_store(t.n_frows, NO_ROW);
     for (size_t pc = 0; pc < t.ins.size(); pc++) {
         TapeIns &in = t.ins[pc];
         if (in.op == T_DOT) {
-            if (in.flags & F_STORE) last_store[in.c] = (uint32_t)pc;
+            if ((in.flags & F_STORE) && !(in.c & ROW_BIT)) last_store[in.c] = (uint32_t)pc;
             pc += (in.a + 1) / 2;
             continue;
         }
         if (in.op == T_LD) {
+            if (!is_field_ld(in)) continue;
             in.a = NO_ROW;
             in.b = (uint32_t)(ld_pos.size() % LD_RING);
             ld_pos.push_back((uint32_t)pc);
             ld_store.push_back(last_store[in.c]);
         } else if (in.op == T_ST || in.op == T_STC || (in.flags & F_STORE)) {
-            if (in.op != T_FAIL_IF && in.op != T_FAIL_NE) last_store[in.c] = (uint32_t)pc;
+            if (in.op != T_FAIL_IF && in.op != T_FAIL_NE && !(in.c & ROW_BIT)) last_store[in.c] = (uint32_t)pc;
         }
     }
     for (size_t n = LD_RING; n < ld_pos.size(); n++) {
@@ -323,7 +345,58 @@ inline void schedule_reloads(Tape &t) {
     }
 }
 
-inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
+// Largest number of simultaneously live values of each kind (0: field, 1: 0/1-typed) in program order: what an
+// allocator with unlimited slots would need.  Sizes the bit-slot file and bounds the useful number of field slots.
+inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
+    const size_t N = xp.ops.size();
+    std::vector<uint32_t> last(N);
+    for (size_t i = 0; i < N; i++) {
+        const XOp &o = xp.ops[i];
+        last[i] = (uint32_t)i;
+        auto use = [&](uint32_t r) {
+            if (r != NO_REF && !(r & CONST_FLAG)) last[r] = (uint32_t)i;
+        };
+        if (o.op == T_DOT)
+            for (uint32_t k = 0; k < o.tn; k++) use(xp.terms[o.t0 + k].second);
+        use(o.a);
+        use(o.b);
+        use(o.c);
+    }
+    auto produces = [&](size_t i) { return xp.ops[i].op != T_FAIL_IF && xp.ops[i].op != T_FAIL_NE; };
+    std::vector<uint32_t> deaths[2];
+    deaths[0].assign(N, 0);
+    deaths[1].assign(N, 0);
+    for (size_t v = 0; v < N; v++)
+        if (produces(v)) deaths[xp.isbool[v] ? 1 : 0][last[v]]++;
+    uint32_t live[2] = {0, 0};
+    out[0] = out[1] = 0;
+    size_t peak_at = 0;
+    for (size_t i = 0; i < N; i++) {
+        if (produces(i)) {
+            const int k = xp.isbool[i] ? 1 : 0;
+            live[k]++;
+            if (k == 0 && live[0] > out[0]) peak_at = i;
+            out[k] = std::max(out[k], live[k]);
+        }
+        live[0] -= deaths[0][i];
+        live[1] -= deaths[1][i];
+    }
+    if (getenv("CVMGPU_DEBUG_LIVE")) {
+        uint32_t hist[T_COUNT] = {0};
+        for (size_t v = 0; v <= peak_at; v++)
+            if (produces(v) && !xp.isbool[v] && last[v] > peak_at) hist[xp.ops[v].op]++;
+        fprintf(stderr, "field values live at op %zu of %zu:", peak_at, N);
+        for (int o = 0; o < T_COUNT; o++)
+            if (hist[o]) fprintf(stderr, " op%d:%u", o, hist[o]);
+        fprintf(stderr, "\n");
+    }
+}
+
+// Typed allocation.  Values the tracer proved 0/1 live in the BIT file: one 32-bit word per warp and slot (bit = lane =
+// witness), spilled to / reloaded from bit rows of the value store (one word per warp).  Everything else lives in the
+// FIELD file (32-byte slots per witness) and in field rows.  A witness wire is a bit row or a field row according to
+// the type of the value bound to it (Tape::wire_loc); consumers of a 0/1 value in field arithmetic convert on fetch.
+inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uint32_t max_bslots = 2048) {
     if (n_slots < 4) throw TraceError("need at least 4 slots");
     const uint32_t max_terms = std::min<uint32_t>(16, n_slots - 2);
     const XProg xp = fuse_dots(tr, max_terms, fuse);
@@ -334,6 +407,34 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
     out.n_wires = (uint32_t)xp.witness_ref.size();
     out.stats.n_ssa = tr.ops.size();
     out.stats.n_live = N;
+
+    auto is_bool_ref = [&](uint32_t r) -> bool {
+        if (r == NO_REF) return false;
+        if (r & CONST_FLAG) {
+            const fr::Fr &c = tr.consts[r & ~CONST_FLAG];
+            for (int i = 1; i < 8; i++)
+                if (c.v[i]) return false;
+            return c.v[0] <= 1;
+        }
+        return xp.isbool[r] != 0;
+    };
+    // ---- witness wire -> typed row
+    out.wire_loc.resize(out.n_wires);
+    {
+        uint32_t nf = 0, nb = 0;
+        for (uint32_t w = 0; w < out.n_wires; w++) out.wire_loc[w] = is_bool_ref(xp.witness_ref[w]) ? (ROW_BIT | nb++) : nf++;
+        out.n_fwires = nf;
+        out.n_bwires = nb;
+    }
+    uint32_t ml[2];
+    max_live_by_kind(xp, ml);
+    out.stats.max_live_field = ml[0];
+    out.stats.max_live_bool = ml[1];
+    // the bit file: enough for every live 0/1 value when that fits (no bit spills at all), else the cap
+    uint32_t n_bslots = ml[1] == 0 ? 0 : std::min<uint32_t>(max_bslots, ((ml[1] + 3 + 31) / 32) * 32);
+    if (ml[1] && n_bslots < 8) n_bslots = 8;
+    out.n_bslots = n_bslots;
+    const uint32_t file_slots[2] = {n_slots, n_bslots};
 
     auto operands = [&](const XOp &o, std::vector<uint32_t> &rs) {
         rs.clear();
@@ -382,67 +483,77 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
     for (size_t w = 0; w < xp.witness_ref.size(); w++) {
         uint32_t r = xp.witness_ref[w];
         if (r & CONST_FLAG) {
-            out.ins.push_back(TapeIns{T_STC, 1, 0, r & ~CONST_FLAG, 0, (uint32_t)w});
+            out.ins.push_back(TapeIns{T_STC, 1, 0, r & ~CONST_FLAG, 0, out.wire_loc[w]});
             out.stats.n_stc++;
         }
     }
-    // ---- linear scan
-    std::vector<int32_t> slot_val(n_slots, -1);
+    // ---- linear scan over two slot files (0: field, 1: bit)
+    std::vector<int32_t> slot_val[2];
+    std::vector<uint32_t> free_slots[2], free_spill[2];
+    uint32_t spill_rows[2] = {0, 0};
+    const uint32_t wire_rows[2] = {out.n_fwires, out.n_bwires};
+    for (int k = 0; k < 2; k++) {
+        slot_val[k].assign(file_slots[k], -1);
+        for (uint32_t s = file_slots[k]; s-- > 0;) free_slots[k].push_back(s);
+    }
     std::vector<int32_t> val_slot(N, -1);
-    std::vector<uint32_t> val_home(N, NO_REF);
+    std::vector<uint32_t> val_home(N, NO_REF);      // typed row (ROW_BIT for bit rows)
     std::vector<uint8_t> home_is_spill(N, 0);
-    std::vector<uint32_t> free_slots, free_spill;
-    for (uint32_t s = n_slots; s-- > 0;) free_slots.push_back(s);
-    uint32_t spill_rows = 0;
     uint32_t live_now = 0;
+    auto kind_of = [&](uint32_t v) -> int { return xp.isbool[v] ? 1 : 0; };
+    auto slot_code = [&](uint32_t v) -> uint32_t { return (uint32_t)val_slot[v] | (xp.isbool[v] ? BSLOT : 0u); };
 
     auto release_value = [&](uint32_t v) {
+        const int k = kind_of(v);
         if (val_slot[v] >= 0) {
-            slot_val[(size_t)val_slot[v]] = -1;
-            free_slots.push_back((uint32_t)val_slot[v]);
+            slot_val[k][(size_t)val_slot[v]] = -1;
+            free_slots[k].push_back((uint32_t)val_slot[v]);
             val_slot[v] = -1;
         }
         if (home_is_spill[v]) {
-            free_spill.push_back(val_home[v] - out.n_wires);
+            free_spill[k].push_back((val_home[v] & ~ROW_BIT) - wire_rows[k]);
             home_is_spill[v] = 0;
         }
         live_now--;
     };
-    auto alloc_slot = [&](uint32_t pos, const std::vector<int32_t> &pinned) -> uint32_t {
-        if (!free_slots.empty()) {
-            uint32_t s = free_slots.back();
-            free_slots.pop_back();
+    // pinned: slot codes (with BSLOT for the bit file) that must not be evicted
+    auto alloc_slot = [&](int k, uint32_t pos, const std::vector<uint32_t> &pinned) -> uint32_t {
+        if (!free_slots[k].empty()) {
+            uint32_t s = free_slots[k].back();
+            free_slots[k].pop_back();
             return s;
         }
+        const uint32_t tag = k ? BSLOT : 0u;
         uint32_t best = 0xffffffffu, best_use = 0;
-        for (uint32_t s = 0; s < n_slots; s++) {
+        for (uint32_t s = 0; s < file_slots[k]; s++) {
             bool pin = false;
-            for (int32_t q : pinned)
-                if (q == (int32_t)s) pin = true;
+            for (uint32_t q : pinned)
+                if (q == (s | tag)) pin = true;
             if (pin) continue;
-            uint32_t v = (uint32_t)slot_val[s];
+            uint32_t v = (uint32_t)slot_val[k][s];
             uint32_t nu = next_use(v, pos);
             if (best == 0xffffffffu || nu > best_use) { best = s; best_use = nu; }
+            if (nu == 0xffffffffu) break;
         }
         if (best == 0xffffffffu) throw TraceError("slot allocator: all slots pinned");
-        uint32_t v = (uint32_t)slot_val[best];
+        uint32_t v = (uint32_t)slot_val[k][best];
         if (val_home[v] == NO_REF) {   // not yet in HBM: spill
             uint32_t row;
-            if (!free_spill.empty()) { row = free_spill.back(); free_spill.pop_back(); }
-            else row = spill_rows++;
-            val_home[v] = out.n_wires + row;
+            if (!free_spill[k].empty()) { row = free_spill[k].back(); free_spill[k].pop_back(); }
+            else row = spill_rows[k]++;
+            val_home[v] = (wire_rows[k] + row) | (k ? ROW_BIT : 0u);
             home_is_spill[v] = 1;
-            out.ins.push_back(TapeIns{T_ST, 0, 0, best, 0, val_home[v]});
+            out.ins.push_back(TapeIns{T_ST, 0, 0, best | tag, 0, val_home[v]});
             out.stats.n_st++;
             out.stats.n_spill_st++;
-            out.stats.n_spill_st_bool += xp.isbool[v];
+            out.stats.n_spill_st_bool += (uint64_t)k;
         }
         val_slot[v] = -1;
-        slot_val[best] = -1;
+        slot_val[k][best] = -1;
         return best;
     };
 
-    std::vector<int32_t> pinned, still;
+    std::vector<uint32_t> pinned, still;
     std::vector<uint32_t> enc;
     for (size_t i = 0; i < N; i++) {
         const XOp &o = ops[i];
@@ -454,7 +565,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
         // resident operands are pinned first so that loading one operand cannot evict another
         for (uint32_t r : rs) {
             if (r == NO_REF || (r & CONST_FLAG)) continue;
-            if (val_slot[r] >= 0) pinned.push_back(val_slot[r]);
+            if (val_slot[r] >= 0) pinned.push_back(slot_code(r));
         }
         for (size_t k = 0; k < rs.size(); k++) {
             uint32_t r = rs[k];
@@ -462,16 +573,20 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             if (r & CONST_FLAG) { isc[k] = 1; enc[k] = r & ~CONST_FLAG; continue; }
             if (val_slot[r] < 0) {
                 if (val_home[r] == NO_REF) throw TraceError("slot allocator: value lost");
-                uint32_t s = alloc_slot(pos, pinned);
-                out.ins.push_back(TapeIns{T_LD, 0, (uint16_t)s, 0, 0, val_home[r]});
+                const int kd = kind_of(r);
+                uint32_t s = alloc_slot(kd, pos, pinned);
+                out.ins.push_back(TapeIns{T_LD, 0, (uint16_t)(s | (kd ? BSLOT_DST : 0)), 0, 0, val_home[r]});
                 out.stats.n_ld++;
-                out.stats.n_ld_bool += xp.isbool[r];
+                out.stats.n_ld_bool += (uint64_t)kd;
                 val_slot[r] = (int32_t)s;
-                slot_val[s] = (int32_t)r;
-                pinned.push_back((int32_t)s);
+                slot_val[kd][s] = (int32_t)r;
+                pinned.push_back(slot_code(r));
             }
-            enc[k] = (uint32_t)val_slot[r];
+            enc[k] = slot_code(r);
         }
+        if (o.op == T_LUT)
+            for (size_t k = 0; k < 3; k++)
+                if (rs[k] != NO_REF && ((rs[k] & CONST_FLAG) || !xp.isbool[rs[k]])) throw TraceError("T_LUT input is not a typed 0/1 value");
         // operands that die here free their slots before the destination is chosen
         for (size_t k = 0; k < rs.size(); k++) {
             uint32_t r = rs[k];
@@ -491,11 +606,13 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
         still.clear();
         for (uint32_t r : rs) {
             if (r == NO_REF || (r & CONST_FLAG)) continue;
-            if (val_slot[r] >= 0) still.push_back(val_slot[r]);
+            if (val_slot[r] >= 0) still.push_back(slot_code(r));
         }
-        uint32_t d = alloc_slot(pos, still);
+        const int dk = kind_of((uint32_t)i);
+        uint32_t d = alloc_slot(dk, pos, still);
         val_slot[i] = (int32_t)d;
-        slot_val[d] = (int32_t)i;
+        slot_val[dk][d] = (int32_t)i;
+        const uint16_t dcode = (uint16_t)(d | (dk ? BSLOT_DST : 0));
         live_now++;
         out.stats.max_live = std::max(out.stats.max_live, live_now);
         uint32_t w0 = wire_head[i];
@@ -508,12 +625,12 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             uint32_t row = 0;
             if (w0 != NO_REF) {
                 flags |= F_STORE;
-                row = w0;
+                row = out.wire_loc[w0];
                 out.stats.n_st++;
-                val_home[i] = w0;
+                val_home[i] = row;
                 w0 = wire_next[w0];
             }
-            out.ins.push_back(TapeIns{T_DOT, flags, (uint16_t)d, o.tn, has_add ? enc[o.tn] : 0u, row});
+            out.ins.push_back(TapeIns{T_DOT, flags, dcode, o.tn, has_add ? enc[o.tn] : 0u, row});
             for (uint32_t k = 0; k < o.tn; k += 2) {
                 uint32_t rec[4] = {xp.terms[o.t0 + k].first & ~CONST_FLAG, enc[k], 0, 0};
                 if (k + 1 < o.tn) { rec[2] = xp.terms[o.t0 + k + 1].first & ~CONST_FLAG; rec[3] = enc[k + 1]; }
@@ -528,9 +645,9 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             uint32_t e0 = enc[0], e1 = enc[1], e2 = enc[2];
             if (o.op == T_INPUT) e0 = o.aux;
             if (o.op == T_BITC) e1 = o.aux;
-            if (o.op == T_LUT) {   // a = the three input slots, one byte each; b = table | k << 8; c is free for the fused store
-                e0 = enc[0] | (enc[1] << 8) | (enc[2] << 16);
-                e1 = o.aux;
+            if (o.op == T_LUT) {   // a = bit slots 0 and 1 (16 bits each); b = table | k << 8 | bit slot 2 << 16; c is free for the fused store
+                e0 = (enc[0] & 0xffffu) | ((enc[1] & 0xffffu) << 16);
+                e1 = (o.aux & 0xffffu) | ((enc[2] & 0xffffu) << 16);
                 e2 = 0;
                 out.stats.n_lut++;
             }
@@ -540,12 +657,12 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             }
             if (w0 != NO_REF && (o.op != T_SEL || (flags & F_CZERO)) && o.op != T_CADD) {   // the first wire of the value is written by the producing instruction
                 flags |= F_STORE;
-                e2 = w0;
+                e2 = out.wire_loc[w0];
                 out.stats.n_st++;
-                val_home[i] = w0;
+                val_home[i] = e2;
                 w0 = wire_next[w0];
             }
-            out.ins.push_back(TapeIns{o.op, flags, (uint16_t)d, e0, e1, e2});
+            out.ins.push_back(TapeIns{o.op, flags, dcode, e0, e1, e2});
             switch (o.op) {
                 case T_MUL: out.stats.n_mul++; break;
                 case T_DIV: out.stats.n_div++; break;
@@ -558,14 +675,16 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true) {
             }
         }
         for (uint32_t w = w0; w != NO_REF; w = wire_next[w]) {
-            out.ins.push_back(TapeIns{T_ST, 0, 0, d, 0, w});
+            out.ins.push_back(TapeIns{T_ST, 0, 0, (uint32_t)d | (dk ? BSLOT : 0u), 0, out.wire_loc[w]});
             out.stats.n_st++;
-            if (val_home[i] == NO_REF) val_home[i] = w;
+            if (val_home[i] == NO_REF) val_home[i] = out.wire_loc[w];
         }
         if (next_use((uint32_t)i, pos) == 0xffffffffu) release_value((uint32_t)i);
     }
-    out.n_rows = out.n_wires + spill_rows;
-    out.stats.n_spill_rows = spill_rows;
+    out.n_frows = out.n_fwires + spill_rows[0];
+    out.n_brows = out.n_bwires + spill_rows[1];
+    out.n_rows = out.n_frows + out.n_brows;
+    out.stats.n_spill_rows = spill_rows[0] + spill_rows[1];
     out.stats.n_tape = out.ins.size();
     // bit-heavy program (more selects / bit extractions than products): its remaining products mostly have factors that
     // are 0 or 1 at run time (unconstrained input bits); let the kernel look before it multiplies

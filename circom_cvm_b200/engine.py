@@ -22,17 +22,19 @@ import numpy as np
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcvmgpu.so")
 
-ST_OK, ST_ASSERT, ST_TOINT, ST_DIVZERO = 0, 1, 2, 3
+ST_OK, ST_ASSERT, ST_TOINT, ST_DIVZERO, ST_INPUT, ST_LOOP = 0, 1, 2, 3, 4, 5   # include/cvmgpu.h CVMGPU_ST_*
 NO_BAD = 0xFFFFFFFF
+ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (csrc/tape.hpp ROW_BIT)
 
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_info_get", "cvmgpu_program_free",
-    "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types",
-    "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_dev", "cvmgpu_witness_export_dev", "cvmgpu_store_bytes",
+    "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows",
+    "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_dev",
+    "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
-    "cvmgpu_witness_import_dev",
+    "cvmgpu_r1cs_check_store_dev", "cvmgpu_witness_import_dev",
     "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak", "cvmgpu_mul_peak", "cvmgpu_set_tape_mode",
 ]
 
@@ -44,24 +46,28 @@ class CvmGpuError(RuntimeError):
 
 
 class ProgramInfo(ctypes.Structure):
-    _fields_ = [("n_signals", c_uint64), ("n_wires", c_uint32), ("n_inputs", c_uint32), ("n_outputs", c_uint32),
+    _fields_ = [("struct_size", c_uint32), ("reserved0", c_uint32), ("n_signals", c_uint64), ("n_wires", c_uint32), ("n_inputs", c_uint32), ("n_outputs", c_uint32),
                 ("n_slots", c_uint32), ("n_rows", c_uint32), ("tape_len", c_uint64), ("ref_mul", c_uint64),
                 ("ref_field_ops", c_uint64), ("cvm_instructions", c_uint64), ("tape_mul", c_uint64),
                 ("tape_div", c_uint64), ("tape_addsub", c_uint64), ("tape_other", c_uint64), ("tape_ld", c_uint64),
                 ("tape_st", c_uint64), ("tape_spill_st", c_uint64), ("n_consts", c_uint32), ("dyn_branches", c_uint32),
                 ("ref_div", c_uint64), ("tape_inv", c_uint64), ("tape_sel", c_uint64), ("tape_dot", c_uint64),
                 ("tape_dot_terms", c_uint64), ("tape_macs", c_uint64), ("tape_ld_streamed", c_uint64), ("unrolled_iterations", c_uint64), ("tape_lut", c_uint64),
-                ("tape_ld_bool", c_uint64), ("tape_spill_st_bool", c_uint64), ("n_bool_wires", c_uint64)]
+                ("tape_ld_bool", c_uint64), ("tape_spill_st_bool", c_uint64), ("n_bool_wires", c_uint64),
+                ("n_bslots", c_uint32), ("n_frows", c_uint32), ("n_brows", c_uint32), ("max_live_field", c_uint32),
+                ("max_live_bool", c_uint32), ("reserved1", c_uint32)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
 class R1csInfo(ctypes.Structure):
-    _fields_ = [("n_wires", c_uint32), ("n_pub_out", c_uint32), ("n_pub_in", c_uint32), ("n_prv_in", c_uint32),
+    _fields_ = [("struct_size", c_uint32), ("n_wires", c_uint32), ("n_pub_out", c_uint32), ("n_pub_in", c_uint32), ("n_prv_in", c_uint32),
                 ("n_constraints", c_uint32), ("n_labels", c_uint64), ("nnz", c_uint64), ("nnz_pm1", c_uint64),
                 ("n_coefs", c_uint32), ("nnz_small", c_uint64), ("macs", c_uint64), ("n_quadratic", c_uint64),
-                ("nnz_const", c_uint64), ("n_squares", c_uint64)]
+                ("nnz_const", c_uint64), ("n_squares", c_uint64), ("bound_int_constraints", c_uint64),
+                ("bound_bit_terms", c_uint64), ("bound_field_terms", c_uint64), ("bound_macs", c_uint64),
+                ("bound_bit_adds", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -85,6 +91,12 @@ def lib():
     L.cvmgpu_program_tape.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_witness.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_wire_types.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
+    L.cvmgpu_program_wire_rows.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
+    L.cvmgpu_witness_batch_select.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_witness_export_range_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p]
+    L.cvmgpu_r1cs_check_store_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
+    L.cvmgpu_release_buffers.argtypes = []
+    L.cvmgpu_release_buffers.restype = None
     L.cvmgpu_witness_batch.argtypes = [c_void_p, c_void_p, c_uint64, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_checked.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
@@ -166,6 +178,7 @@ class WitnessCalculator:
             _check(L.cvmgpu_program_load_text(data, len(data), n_slots, byref(h)))
         self._h = h
         info = ProgramInfo()
+        info.struct_size = ctypes.sizeof(ProgramInfo)
         _check(L.cvmgpu_program_info_get(self._h, byref(info)))
         self.info = info
         self.n_inputs = int(info.n_inputs)
@@ -226,6 +239,27 @@ class WitnessCalculator:
     def export_dev(self, d_store, B, bstride, d_wtns, stream=0):
         _check(lib().cvmgpu_witness_export_dev(self._h, _ptr(d_store), B, bstride, _ptr(d_wtns), stream))
 
+    def export_range_dev(self, d_store, B, bstride, wire0, n_sel, d_out, stream=0):
+        _check(lib().cvmgpu_witness_export_range_dev(self._h, _ptr(d_store), B, bstride, wire0, n_sel, _ptr(d_out), stream))
+
+    def calculate_select_into(self, inputs, wire0, n_sel, wtns_out, status_out, r1cs=None, first_bad_out=None):
+        """calculate_into with an output selector: only wires [wire0, wire0 + n_sel) come back (wtns_out [B, n_sel, 32])"""
+        B = status_out.shape[0]
+        _check(lib().cvmgpu_witness_batch_select(self._h, r1cs._h if r1cs is not None else None, _ptr(inputs), B, wire0, n_sel,
+                                                 _ptr(wtns_out), _ptr(status_out), _ptr(first_bad_out)))
+
+    def wire_rows(self):
+        """uint32 per witness wire: its row in the typed value store (ROW_BIT | bit row, or field row)"""
+        ptr, n = c_void_p(), c_uint32()
+        _check(lib().cvmgpu_program_wire_rows(self._h, byref(ptr), byref(n)))
+        return np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(c_uint32)), shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+
+    def layout(self):
+        """what tests/tape_emulator.py needs to execute the tape: slot files, row counts, wire -> row map"""
+        i = self.info
+        return {"n_slots": int(i.n_slots), "n_bslots": int(i.n_bslots), "n_frows": int(i.n_frows), "n_brows": int(i.n_brows),
+                "wire_loc": [int(x) for x in self.wire_rows()]}
+
     def write_wtns(self, path, witness_row):
         row = np.ascontiguousarray(witness_row, dtype=np.uint8)
         _check(lib().cvmgpu_wtns_write(os.fsencode(path), _ptr(row), self.n_wires))
@@ -262,9 +296,7 @@ class R1cs:
         h = c_void_p()
         _check(lib().cvmgpu_r1cs_load(os.fsencode(path), byref(h)))
         self._h = h
-        info = R1csInfo()
-        _check(lib().cvmgpu_r1cs_info_get(self._h, byref(info)))
-        self.info = info
+        info = self.refresh_info()
         self.n_wires = int(info.n_wires)
         self.n_constraints = int(info.n_constraints)
 
@@ -279,6 +311,14 @@ class R1cs:
         except Exception:
             pass
 
+    def refresh_info(self):
+        """(the bound_* counters describe the binding to the last program layout checked)"""
+        info = R1csInfo()
+        info.struct_size = ctypes.sizeof(R1csInfo)
+        _check(lib().cvmgpu_r1cs_info_get(self._h, byref(info)))
+        self.info = info
+        return info
+
     def check(self, witnesses):
         """witnesses: uint8 [B, n_wires, 32] canonical -> uint32 [B] first violated constraint (NO_BAD = satisfied)"""
         w = np.ascontiguousarray(witnesses, dtype=np.uint8)
@@ -289,7 +329,12 @@ class R1cs:
         return bad
 
     def check_dev(self, d_store, B, bstride, d_first_bad, stream=0):
+        """PLAIN store (row = wire, as written by cvmgpu_witness_import_dev)"""
         _check(lib().cvmgpu_r1cs_check_dev(self._h, _ptr(d_store), B, bstride, _ptr(d_first_bad), stream))
+
+    def check_store_dev(self, wc, d_store, B, bstride, d_first_bad, stream=0):
+        """typed store written by wc.run_dev (WitnessCalculator wc)"""
+        _check(lib().cvmgpu_r1cs_check_store_dev(self._h, wc._h, _ptr(d_store), B, bstride, _ptr(d_first_bad), stream))
 
 
 def set_tape_mode(mode):

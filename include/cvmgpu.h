@@ -53,13 +53,17 @@ extern "C" {
 typedef struct cvmgpu_program cvmgpu_program;
 typedef struct cvmgpu_r1cs cvmgpu_r1cs;
 
+/* Info structs are versioned by size: set info.struct_size = sizeof(info) before the call; the library fills
+ * min(struct_size, its own sizeof) bytes and writes back how many it filled.  New counters are only ever appended. */
 typedef struct {
+    uint32_t struct_size;        /* in: sizeof(cvmgpu_program_info) of the caller; out: bytes filled */
+    uint32_t reserved0;
     uint64_t n_signals;          /* %%signals */
     uint32_t n_wires;            /* length of %%witness */
     uint32_t n_inputs;           /* main input signals (field elements) */
     uint32_t n_outputs;          /* main output signals */
     uint32_t n_slots;            /* on-chip slots per witness chosen for the tape */
-    uint32_t n_rows;             /* rows of the device value store: wires + spill rows */
+    uint32_t n_rows;             /* rows of the device value store: n_frows + n_brows */
     uint64_t tape_len;           /* tape instructions executed per witness */
     uint64_t ref_mul;            /* N_mul: ff.mul (+1 per ff.div) the reference program executes per witness */
     uint64_t ref_field_ops;      /* all ff.* operations the reference program executes per witness */
@@ -76,12 +80,19 @@ typedef struct {
     uint64_t tape_ld_streamed;   /* reloads served by the cp.async ring (requested 4 reloads ahead) */
     uint64_t unrolled_iterations; /* iterations of data-dependent while loops traced under predicates */
     uint64_t tape_lut;           /* boolean cones (XOR / Ch / Maj / ... written as field polynomials) run as one table look-up */
-    uint64_t tape_ld_bool;       /* of tape_ld: reloads of values typed 0/1 (32 B each today; see cvmgpu_program_wire_types) */
+    uint64_t tape_ld_bool;       /* of tape_ld: reloads of values typed 0/1 (one word per warp from a bit row) */
     uint64_t tape_spill_st_bool; /* of tape_spill_st: spills of values typed 0/1 */
-    uint64_t n_bool_wires;       /* witness wires typed 0/1 */
+    uint64_t n_bool_wires;       /* witness wires typed 0/1: stored as bit rows */
+    uint32_t n_bslots;           /* bit slots per warp (on-chip file of the values typed 0/1) */
+    uint32_t n_frows;            /* field rows of the value store (field-typed wires + field spill rows), 32 B per witness */
+    uint32_t n_brows;            /* bit rows (wires typed 0/1 + bit spill rows), one 32-bit word per 32 witnesses */
+    uint32_t max_live_field;     /* most field-typed values live at once */
+    uint32_t max_live_bool;      /* most 0/1-typed values live at once */
+    uint32_t reserved1;
 } cvmgpu_program_info;
 
 typedef struct {
+    uint32_t struct_size;        /* in: sizeof(cvmgpu_r1cs_info) of the caller; out: bytes filled */
     uint32_t n_wires, n_pub_out, n_pub_in, n_prv_in, n_constraints;
     uint64_t n_labels;
     uint64_t nnz;                /* non-zeros of A, B and C together */
@@ -92,13 +103,21 @@ typedef struct {
     uint64_t n_quadratic;        /* constraints with non-empty A and B (one Montgomery product each) */
     uint64_t nnz_const;          /* general coefficients on wire 0 (the constant 1): added, not multiplied */
     uint64_t n_squares;          /* quadratic constraints whose B repeats A: evaluated once and squared */
+    /* the binding to the typed store of the last program this handle checked (0 before the first such check) */
+    uint64_t bound_int_constraints; /* constraints over 0/1 wires with small coefficients: evaluated in 64-bit integers */
+    uint64_t bound_bit_terms;       /* non-zeros on bit rows */
+    uint64_t bound_field_terms;     /* non-zeros on field rows (the operand stream) */
+    uint64_t bound_macs;            /* multiply-accumulates per witness on that layout (upper bound: 0 / +-1 factors skip the product) */
+    uint64_t bound_bit_adds;        /* field additions of bit-row terms outside integer constraints */
 } cvmgpu_r1cs_info;
 
 const char *cvmgpu_last_error(void);
 int cvmgpu_device_count(void);
 int cvmgpu_set_device(int device);
-/* tuning knob for experiments: witnesses per thread of the tape kernel (0 = automatic, 1, 2) */
+/* reserved (was: witnesses per thread of the tape kernel); accepted and ignored */
 int cvmgpu_set_tape_mode(int mode);
+/* frees the calling thread's pipeline buffers of the host-buffer entry points (also done by cvmgpu_program_free) */
+void cvmgpu_release_buffers(void);
 
 /* ---- program ---------------------------------------------------------------------------------- */
 /* Parse + trace-compile a .cvm file.  n_slots = 0 picks the default.  Works without a GPU. */
@@ -113,9 +132,10 @@ int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_i
  * c_code_generator.rs:541-550; used to locate the input hash map of a .dat, circom_cvm_b200/inputs.py). */
 int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n);
 /* Per witness wire: 1 when the trace compiler's value-range typing proves the wire 0/1 for every input (comparison
- * results, extracted bits, boolean combinations of those, constants 0 and 1).  Informational: the basis of a compact
- * row type for bit-valued wires. */
+ * results, extracted bits, boolean combinations of those, constants 0 and 1).  Such wires are stored as bit rows. */
 int cvmgpu_program_wire_types(const cvmgpu_program *p, const uint8_t **is_bool, uint32_t *n);
+/* Per witness wire: its row in the typed value store -- a field row index, or 0x80000000 | bit row index. */
+int cvmgpu_program_wire_rows(const cvmgpu_program *p, const uint32_t **wire_loc, uint32_t *n);
 
 /* ---- witness generation ----------------------------------------------------------------------- */
 /* HOST buffers.  inputs: B x n_inputs x 32 B (main inputs in signal order, canonical LE; values >= q are
@@ -128,10 +148,18 @@ int cvmgpu_witness_batch(cvmgpu_program *p, const uint8_t *inputs, uint64_t B, u
 int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
                                  uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
 
+/* Same with an output selector: only wires [wire0, wire0 + n_sel) of every witness are exported and downloaded
+ * (wtns_out: B x n_sel x 32 B).  Wires 0 .. n_outputs + n_pub_inputs are the public part of a witness (constant 1,
+ * main outputs, public inputs): what a caller that keeps the witness on the device for a GPU prover needs back. */
+int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t wire0,
+                                uint32_t n_sel, uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
+
 /* DEVICE buffers on the current device.
  *   d_inputs  B x n_inputs x 32 B, as above
- *   d_store   value store, n_rows x 2 x bstride x 16 B: row r, half h, witness w at ((r*2+h)*bstride + w)*16; B <= bstride < 2^27;
- *             Montgomery form; rows [0, n_wires) are the witness wires
+ *   d_store   typed value store of cvmgpu_store_bytes(p, bstride) bytes, B <= bstride < 2^27:
+ *               field rows: row r, half h, witness w at ((r*2+h)*bstride + w)*16, Montgomery form;
+ *               then bit rows (values proven 0/1): 32-bit word ((w >> 5) * n_brows + row), bit w & 31;
+ *             cvmgpu_program_wire_rows maps witness wires to rows
  *   d_status  B words
  * stream: a cudaStream_t (0 = default stream). */
 int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store,
@@ -139,6 +167,9 @@ int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B
 /* value store -> .wtns row layout: d_wtns = B x n_wires x 32 B canonical LE */
 int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_wtns,
                               void *stream);
+/* only wires [wire0, wire0 + n_sel): d_out = B x n_sel x 32 B */
+int cvmgpu_witness_export_range_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, uint32_t wire0,
+                                    uint32_t n_sel, void *d_out, void *stream);
 size_t cvmgpu_store_bytes(const cvmgpu_program *p, uint64_t bstride);
 
 /* write one witness (n_wires x 32 B canonical) as a .wtns file, byte-identical to main.cpp:286-332 */
@@ -151,10 +182,14 @@ void cvmgpu_r1cs_free(cvmgpu_r1cs *r);
 /* HOST: witnesses B x n_wires x 32 B canonical; first_bad[b] = index of the first violated constraint or
  * 0xffffffff when witness b satisfies every constraint. */
 int cvmgpu_r1cs_check(cvmgpu_r1cs *r, const uint8_t *witnesses, uint64_t B, uint32_t *first_bad);
-/* DEVICE: checks the value store written by cvmgpu_witness_batch_dev (Montgomery, same layout). */
+/* DEVICE: checks the typed value store written by cvmgpu_witness_batch_dev for program p (the CSR is bound to p's
+ * wire -> row map on first use; constraints over 0/1 wires with small coefficients are evaluated in 64-bit integers). */
+int cvmgpu_r1cs_check_store_dev(cvmgpu_r1cs *r, cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride,
+                                void *d_first_bad, void *stream);
+/* DEVICE: checks a PLAIN store (row = wire, all field rows, Montgomery) as written by cvmgpu_witness_import_dev. */
 int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64_t B, uint64_t bstride, void *d_first_bad,
                           void *stream);
-/* DEVICE: canonical AoS witnesses (B x n_wires x 32 B) -> value-store layout (Montgomery) */
+/* DEVICE: canonical AoS witnesses (B x n_wires x 32 B) -> plain value-store layout (n_wires x 2 x bstride x 16 B, Montgomery) */
 int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, uint64_t bstride, void *d_store,
                               void *stream);
 

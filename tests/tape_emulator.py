@@ -21,15 +21,52 @@ BIN = {T_ADD: M.add, T_SUB: M.sub, T_MUL: M.mul, T_POW: M.pow_, T_SHL: M.shl, T_
        T_LAND: M.land, T_LOR: M.lor}
 
 
-def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
-    """-> (rows: list of canonical values per value-store row (None = never written), status)"""
+BSLOT = 0x40000000      # operand field: a slot of the bit file (value typed 0/1)
+BSLOT_DST = 0x8000      # dst field: idem
+ROW_BIT = 0x80000000    # row field: a bit row
+
+
+def run_tape(tape, consts_mont, layout, inputs):
+    """layout: WitnessCalculator.layout() (slot files, typed rows, wire -> row map)
+    -> (witness: canonical value of every wire (None = its row was never written), status)"""
     consts = [M.from_mont(c) for c in consts_mont]
-    slots = [None] * n_slots
-    rows = [None] * n_rows
+    slots = [None] * layout["n_slots"]
+    bslots = [None] * layout["n_bslots"]
+    frows = [None] * layout["n_frows"]
+    brows = [None] * layout["n_brows"]
     ring = [None] * 8     # reload stream (entries b < LD_RING): a snapshot of the row at request time, so that a stale request is caught
     status = 0
     import numpy as np
     words = np.ascontiguousarray(tape).view(np.uint32).reshape(-1, 4)
+
+    def get_slot(code):
+        if code & BSLOT:
+            v = bslots[code & 0xFFFF]
+            assert v in (0, 1), "bit slot holds %r" % (v,)
+        else:
+            v = slots[code]
+        assert v is not None, "read of an empty slot"
+        return v
+
+    def set_slot(dst, v):
+        if dst & BSLOT_DST:
+            assert v in (0, 1), "a value typed 0/1 is %r" % (v,)
+            bslots[dst & 0x7FFF] = v
+        else:
+            slots[dst] = v
+
+    def set_row(row, v):
+        if row & ROW_BIT:
+            assert v in (0, 1), "bit row written with %r" % (v,)
+            brows[row & ~ROW_BIT] = v
+        else:
+            frows[row] = v
+
+    def get_row(row):
+        v = brows[row & ~ROW_BIT] if row & ROW_BIT else frows[row]
+        assert v is not None, "load of an unwritten row"
+        return v
+
     pc = 0
     while pc < len(tape):
         ins = tape[pc]
@@ -40,85 +77,97 @@ def run_tape(tape, consts_mont, n_slots, n_rows, inputs):
         def operand(idx, bit):
             if flags & bit:
                 return consts[idx]
-            v = slots[idx]
-            assert v is not None, "read of an empty slot"
-            return v
+            return get_slot(idx)
 
+        res = None
         if op == T_DOT:
             # a terms follow as (constant index, slot) pairs, two per 16-byte record
             acc = 0
             for j in range(a):
                 rec = words[pc + j // 2]
                 cidx, slot = (int(rec[2]), int(rec[3])) if j & 1 else (int(rec[0]), int(rec[1]))
-                assert slots[slot] is not None
-                acc += consts[cidx] * slots[slot]
+                acc += consts[cidx] * get_slot(slot)
             if flags & F_ADDEND:
                 acc += operand(b, 2)
             pc += (a + 1) // 2
-            slots[dst] = acc % M.Q
+            res = acc % M.Q
         elif op == T_INPUT:
-            slots[dst] = inputs[a] % M.Q
+            res = inputs[a] % M.Q
         elif op == T_CADD:
             # a + (b != 0 ? constant c : 0)
             x = operand(a, 1)
-            assert slots[b] is not None
-            slots[dst] = (x + consts[c]) % M.Q if slots[b] != 0 else x
+            res = (x + consts[c]) % M.Q if get_slot(b) != 0 else x
         elif op == T_LUT:
-            # boolean function of up to three 0/1 slots (one byte each in a); b = table | number of inputs << 8
+            # boolean function of up to three bit slots: a = slots 0 | 1 << 16; b = table | number of inputs << 8 | slot 2 << 16
+            sl = [a & 0xFFFF, a >> 16, b >> 16]
             idx = 0
-            for i in range(b >> 8):
-                v = slots[(a >> (8 * i)) & 0xFF]
+            for i in range((b >> 8) & 0xFF):
+                v = bslots[sl[i]]
                 assert v in (0, 1), "T_LUT input is not a 0/1 value"
                 idx |= v << i
-            slots[dst] = (b >> idx) & 1
+            res = (b >> idx) & 1
+            assert dst & BSLOT_DST
         elif op == T_BITC:
-            # bit b of the RAW (Montgomery) limbs of slot a
-            assert slots[a] is not None
-            slots[dst] = ((slots[a] * R % M.Q) >> b) & 1
+            # bit b of the RAW (Montgomery) limbs of field slot a
+            assert not (a & BSLOT) and slots[a] is not None
+            res = ((slots[a] * R % M.Q) >> b) & 1
         elif op == T_FAIL_NE:
             if status == 0 and operand(a, 1) != operand(b, 2):
                 status = c
+            continue
         elif op == T_LD:
-            assert rows[c] is not None, "load of an unwritten row"
+            v = get_row(c)
+            if dst & BSLOT_DST:
+                assert c & ROW_BIT and not flags & F_RING
+                bslots[dst & 0x7FFF] = v
+                continue
+            assert not c & ROW_BIT
             if flags & F_RING:
                 assert ring[b] is not None and ring[b][0] == c, "ring entry does not hold the expected row"
                 slots[dst] = ring[b][1]
             else:
-                slots[dst] = rows[c]
-            assert slots[dst] == rows[c], "streamed reload is stale"
+                slots[dst] = v
+            assert slots[dst] == v, "streamed reload is stale"
             ring[b] = None
             if a != NO_ROW:
-                assert rows[a] is not None, "request of an unwritten row"
-                ring[b] = (a, rows[a])
+                assert not a & ROW_BIT and frows[a] is not None, "request of an unwritten row"
+                ring[b] = (a, frows[a])
+            continue
         elif op == T_ST:
-            assert slots[a] is not None
-            rows[c] = slots[a]
+            assert bool(a & BSLOT) == bool(c & ROW_BIT), "store between a slot and a row of different types"
+            set_row(c, get_slot(a))
+            continue
         elif op == T_STC:
-            rows[c] = consts[a]
+            set_row(c, consts[a])
+            continue
         elif op == T_FAIL_IF:
             if status == 0 and operand(a, 1) != 0:
                 status = c
+            continue
         elif op == T_SEL:
             x, y = operand(a, 1), operand(b, 2)
             z = 0 if flags & F_CZERO else operand(c, 4)
-            slots[dst] = y if x != 0 else z
+            res = y if x != 0 else z
         elif op in (T_BNOT, T_EQZ, T_INV):
             x = operand(a, 1)
-            slots[dst] = M.bnot(x) if op == T_BNOT else int(x == 0) if op == T_EQZ else pow(x, M.Q - 2, M.Q)
+            res = M.bnot(x) if op == T_BNOT else int(x == 0) if op == T_EQZ else pow(x, M.Q - 2, M.Q)
         elif op == T_DIV:
             x, y = operand(a, 1), operand(b, 2)
-            slots[dst] = 0 if y == 0 else M.div(x, y)
+            res = 0 if y == 0 else M.div(x, y)
         elif op in (T_IDIV, T_MOD):
             x, y = operand(a, 1), operand(b, 2)
             if y == 0:          # the failure is raised by the FAIL_IF the tracer puts in front of the operation
-                slots[dst] = 0
+                res = 0
             else:
-                slots[dst] = x // y if op == T_IDIV else x % y
+                res = x // y if op == T_IDIV else x % y
         elif op in BIN:
-            slots[dst] = BIN[op](operand(a, 1), operand(b, 2))
+            res = BIN[op](operand(a, 1), operand(b, 2))
         else:
             raise ValueError("bad tape op %d" % op)
+        set_slot(dst, res)
         if flags & F_STORE:
-            assert op not in (T_LD, T_ST, T_STC, T_FAIL_IF, T_FAIL_NE, T_CADD) and (op != T_SEL or flags & F_CZERO)
-            rows[c] = slots[dst]
-    return rows, status
+            assert op not in (T_CADD,) and (op != T_SEL or flags & F_CZERO)
+            assert bool(dst & BSLOT_DST) == bool(c & ROW_BIT), "fused store between a slot and a row of different types"
+            set_row(c, res)
+    witness = [(brows[loc & ~ROW_BIT] if loc & ROW_BIT else frows[loc]) for loc in layout["wire_loc"]]
+    return witness, status

@@ -20,10 +20,10 @@ def test_random_circuit_tape_matches_oracle(cvmlib, seed):
                 w, st = I.compute_witness(prog, inp), 0
             except I.WitnessError as e:
                 w, st = None, e.status
-            rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, inp)
+            rows, status = run_tape(tape, consts, wc.layout(), inp)
             if st == 0:
                 assert status == 0, (seed, inp)
-                assert rows[:wc.n_wires] == w, (seed, inp)
+                assert rows == w, (seed, inp)
             else:
                 # the oracle stops at the first failure; the tape runs on and reports the first one it meets in ITS order
                 assert status != 0, (seed, inp)

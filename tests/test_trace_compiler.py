@@ -50,10 +50,10 @@ def test_tape_matches_oracle(cvmlib, name, slots):
         cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
     for inp in cases:
         w, st = oracle(prog, inp)
-        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, inp)
+        rows, status = run_tape(tape, consts, wc.layout(), inp)
         assert status == st, (name, inp)
         if st == 0:
-            assert rows[:wc.n_wires] == w, (name, inp)
+            assert rows == w, (name, inp)
 
 
 def test_reference_op_counts(cvmlib):
@@ -117,11 +117,11 @@ def test_data_dependent_while_is_unrolled_under_predicates(cvmlib):
     assert wc.info.unrolled_iterations == 260
     tape, consts = wc.tape()
     for n in (0, 3, 259, 260):
-        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, [n])
-        assert status == 0 and rows[:wc.n_wires] == I.compute_witness(prog, [n]), n
+        rows, status = run_tape(tape, consts, wc.layout(), [n])
+        assert status == 0 and rows == I.compute_witness(prog, [n]), n
         assert rows[1] == sum(k * k for k in range(n + 1))
     for n in (261, 5000, M.Q - 1):
-        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, [n])
+        rows, status = run_tape(tape, consts, wc.layout(), [n])
         assert status == 5, n
 
 
@@ -140,8 +140,8 @@ def test_eddsa_verifier_tape(cvmlib):
     good = eddsa.sign(123456789, 987654321, 42)
     assert eddsa.verify(good)
     w = I.compute_witness(prog, good)
-    rows, status = run_tape(tape, consts, info.n_slots, wc.n_rows, good)
-    assert status == 0 and rows[:wc.n_wires] == w
+    rows, status = run_tape(tape, consts, wc.layout(), good)
+    assert status == 0 and rows == w
     for (a, b, c) in art.constraints:
         ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
         assert (ev(a) * ev(b) - ev(c)) % M.Q == 0
@@ -153,10 +153,10 @@ def test_eddsa_verifier_tape(cvmlib):
     disabled[0] = 0                                   # enabled = 0 switches every check off
     for inp, want in ((forged, 1), (big_s, 1), (disabled, 0)):
         _w, st = oracle(prog, inp)
-        rows, status = run_tape(tape, consts, info.n_slots, wc.n_rows, inp)
+        rows, status = run_tape(tape, consts, wc.layout(), inp)
         assert status == st == want, inp
         if want == 0:
-            assert rows[:wc.n_wires] == _w
+            assert rows == _w
 
 
 def test_sha256_circuit_matches_hashlib(cvmlib):
@@ -171,16 +171,16 @@ def test_sha256_circuit_matches_hashlib(cvmlib):
     rng = random.Random(5)
     for _ in range(2):
         bits = [rng.randrange(2) for _ in range(64)]
-        rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, bits)
+        rows, status = run_tape(tape, consts, wc.layout(), bits)
         assert status == 0
-        w = rows[:wc.n_wires]
+        w = rows
         assert w[1:257] == sha256.sha256_bits(bits)
         for (a, b, c) in art.constraints:
             ev = lambda lc: sum(v * w[k] for k, v in lc.items()) % M.Q
             assert (ev(a) * ev(b) - ev(c)) % M.Q == 0
     # a non-bit input breaks the bit decompositions downstream (BinSum: lin === lout)
     bad = [M.Q - 1] + [0] * 63
-    rows, status = run_tape(tape, consts, wc.info.n_slots, wc.n_rows, bad)
+    rows, status = run_tape(tape, consts, wc.layout(), bad)
     assert status == 1
 
 
