@@ -7,7 +7,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <initializer_list>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -68,7 +70,7 @@ struct cvmgpu_program {
     uint64_t layout_id = 0;          // identifies this program's value-store layout (r1cs bindings are cached against it)
     // device copies (uploaded on first use on the current device)
     int device = -1;
-    DevBuf d_tape, d_consts, d_wire_loc;
+    DevBuf d_tape, d_consts, d_wire_loc, d_iconsts;
 };
 
 // the CSR of an .r1cs bound to one value-store layout (r1cs.hpp bind), on the device
@@ -119,35 +121,55 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
         tr.trace();
         p->binv = tape::batch_inversions(tr);
         if (n_slots == 0) {
-            // Fewer slots per witness = more resident CTAs per SM (4 KiB of shared memory per field slot and CTA, 16 B per
-            // bit slot), but more reloads/spills through HBM.  Pick the candidate with the best (work / resident warps)
-            // estimate; the kernel stops gaining from occupancy at about 20 warps per SM.  Candidates beyond what the
-            // program can keep live at once cannot differ (max_live_field of the first build), so a program with few
-            // field values -- a hash circuit is almost all bits -- is compiled once.
+            // Fewer slots per witness = more resident warps per SM (1 KiB of shared memory per field slot and warp, 4 B per
+            // bit slot), but more reloads/spills through the value store.  Pick the candidate with the best
+            // (work / resident warps) estimate; the kernel stops gaining from occupancy at about 24 warps per SM.
+            // Field-slot candidates beyond what the program keeps live at once cannot differ (max_live_field), and the
+            // bit file is first sized to hold every live 0/1 value, then tried smaller for the chosen field file.
             static const uint32_t cand[] = {8, 12, 16, 24, 32};
+            std::map<uint32_t, tape::XProg> prepared;   // by longest dot product: fusion and typing run once each
+            auto build = [&](uint32_t c, uint32_t max_bslots) {
+                const uint32_t mt = std::min<uint32_t>(16, c - 2);
+                auto it = prepared.find(mt);
+                if (it == prepared.end()) it = prepared.emplace(mt, tape::prepare_program(tr, mt)).first;
+                return tape::allocate_tape(tr, it->second, c, max_bslots);
+            };
+            auto cost_of = [&](const tape::Tape &t) {
+                const size_t per_warp = (size_t)(t.n_slots + (t.use_ring ? tape::LD_RING : 0)) * 1024u + (size_t)t.n_bslots * 4u;
+                const double warps = std::min<double>(std::floor(226.0 * 1024.0 / (double)(per_warp * 4)) * 4.0, 24.0);
+                const double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st - t.stats.n_ld_bool - t.stats.n_spill_st_bool);
+                return work / std::max(4.0, warps);
+            };
             double best = 0;
-            uint32_t live_field = 0xffffffffu;
             for (uint32_t c : cand) {
-                tape::Tape t = tape::build_tape(tr, c);
-                live_field = t.stats.max_live_field;
-                const size_t smem = (size_t)(c + (t.stats.n_ld ? tape::LD_RING : 0)) * 4096u + (size_t)t.n_bslots * 16u + 1024u;
-                uint32_t ctas = std::min<uint32_t>(8, (uint32_t)((227u * 1024u) / smem));
-                double warps = std::min<double>(4.0 * std::max<uint32_t>(1, ctas), 20.0);
-                double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st);
-                double cost = work / warps;
+                tape::Tape t = build(c, 2048);
+                const uint32_t live_field = t.stats.max_live_field;
+                const double cost = cost_of(t);
                 if (best == 0 || cost < best) {
                     best = cost;
                     p->tape = std::move(t);
                 }
                 if (c >= live_field + 2) break;   // every field value already has a slot
             }
+            for (uint32_t nb : {1024u, 512u, 256u}) {
+                if (nb >= p->tape.n_bslots) continue;
+                tape::Tape t = build(p->tape.n_slots, nb);
+                const double cost = cost_of(t);
+                if (cost < best) {
+                    best = cost;
+                    p->tape = std::move(t);
+                }
+            }
         } else {
-            p->tape = tape::build_tape(tr, n_slots);
+            // explicit slot count (experiments): CVMGPU_BSLOTS caps the bit file
+            const uint32_t nb = getenv("CVMGPU_BSLOTS") ? (uint32_t)atoi(getenv("CVMGPU_BSLOTS")) : 2048u;
+            p->tape = tape::build_tape(tr, n_slots, true, std::max<uint32_t>(8, nb));
         }
         p->layout_id = g_next_layout_id++;
         p->tstats = tr.stats;
         p->wire_bool.reserve(tr.witness_ref.size());
         for (uint32_t loc : p->tape.wire_loc) p->wire_bool.push_back((loc & tape::ROW_BIT) ? 1 : 0);
+        if (!p->wire_bool.empty()) p->wire_bool[0] = 1;   // the constant 1 (kept as a field row, plus a bit row of ones)
         p->n_signals = (uint64_t)parser.prog.n_signals;
         p->witness.assign(parser.prog.witness.begin(), parser.prog.witness.end());
         p->n_inputs = (uint32_t)tr.n_inputs;
@@ -248,6 +270,7 @@ extern "C" int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_i
     info->n_brows = p->tape.n_brows;
     info->max_live_field = p->tape.stats.max_live_field;
     info->max_live_bool = p->tape.stats.max_live_bool;
+    info->tape_int = p->tape.stats.n_int;
     return fill_info(out, v);
 }
 
@@ -258,6 +281,13 @@ extern "C" int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, ui
     if (n_ins) *n_ins = p->tape.ins.size();
     if (consts) *consts = p->consts_mont.data();
     if (n_consts) *n_consts = (uint32_t)p->consts_mont.size();
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_iconsts(const cvmgpu_program *p, const uint64_t **iconsts, uint32_t *n) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (iconsts) *iconsts = p->tape.iconsts.data();
+    if (n) *n = (uint32_t)p->tape.iconsts.size();
     return CVMGPU_OK;
 }
 
@@ -285,7 +315,7 @@ static void release_on(int device, std::initializer_list<DevBuf *> bufs) {
 
 extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
     if (!p) return;
-    release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc});
+    release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc, &p->d_iconsts});
     release_pipe_buffers();
     delete p;
 }
@@ -293,7 +323,7 @@ extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
 // dynamic shared memory of a tape CTA of nt witnesses: the field slots, the reload ring when the tape reloads
 // anything, and the bit-slot file of each warp
 static size_t tape_field_smem_per_witness(const cvmgpu_program *p) {
-    return ((size_t)p->tape.n_slots + (p->tape.stats.n_ld ? tape::LD_RING : 0)) * 2 * sizeof(uint4);
+    return ((size_t)p->tape.n_slots + (p->tape.use_ring ? tape::LD_RING : 0)) * 2 * sizeof(uint4);
 }
 static size_t tape_smem(const cvmgpu_program *p, uint32_t nt) {
     return tape_field_smem_per_witness(p) * nt + (((size_t)p->tape.n_bslots * (nt / 32) * 4 + 15) & ~(size_t)15);
@@ -303,7 +333,7 @@ static int upload_program(cvmgpu_program *p) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
     if (p->device == dev && p->d_tape.p) return CVMGPU_OK;
-    if (p->device != dev) release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc});
+    if (p->device != dev) release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc, &p->d_iconsts});
     size_t tb = std::max<size_t>(16, p->tape.ins.size() * sizeof(tape::TapeIns));
     size_t cb = std::max<size_t>(32, p->consts_mont.size() * sizeof(fr::Fr));
     if (int rc = p->d_tape.ensure(tb)) return rc;
@@ -313,6 +343,9 @@ static int upload_program(cvmgpu_program *p) {
         CUDA_TRY(cudaMemcpy(p->d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
     if (!p->consts_mont.empty())
         CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
+    if (int rc = p->d_iconsts.ensure(std::max<size_t>(8, p->tape.iconsts.size() * 8))) return rc;
+    if (!p->tape.iconsts.empty())
+        CUDA_TRY(cudaMemcpy(p->d_iconsts.p, p->tape.iconsts.data(), p->tape.iconsts.size() * 8, cudaMemcpyHostToDevice));
     if (!p->tape.wire_loc.empty())
         CUDA_TRY(cudaMemcpy(p->d_wire_loc.p, p->tape.wire_loc.data(), p->tape.wire_loc.size() * 4, cudaMemcpyHostToDevice));
     // the tables are read by kernels on non-blocking streams, which do not order themselves after the copies above
@@ -334,18 +367,18 @@ extern "C" size_t cvmgpu_store_bytes(const cvmgpu_program *p, uint64_t bstride) 
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel and device, and several programs may be live: only ever raise it
-template <int NT>
+template <int NT, bool BITS>
 static int launch_tape(const kern::TapeParams &tp, unsigned grid, size_t smem, cudaStream_t st) {
     static size_t allowed[64] = {0};
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && smem > allowed[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // the slots want the whole carve-out of the SM (more resident CTAs), nothing here relies on L1
-        CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout));
+        CUDA_TRY(cudaFuncSetAttribute(kern::tape_kernel<NT, BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout));
         allowed[dev] = smem;
     }
-    kern::tape_kernel<NT><<<grid, NT, smem, st>>>(tp);
+    kern::tape_kernel<NT, BITS><<<grid, NT, smem, st>>>(tp);
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }
@@ -366,6 +399,7 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     tp.bstride = bstride;
     tp.n_brows = p->tape.n_brows;
     tp.n_bslots = p->tape.n_bslots;
+    tp.iconsts = (const unsigned long long *)p->d_iconsts.p;
     tp.inputs = (const uint4 *)d_inputs;
     tp.n_inputs = p->n_inputs;
     tp.status = (uint32_t *)d_status;
@@ -386,9 +420,15 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     tp.ring_off = p->tape.n_slots * 2 * nt;
     tp.bslot_off = (uint32_t)(per_w * nt / sizeof(uint4));
     const size_t smem = tape_smem(p, nt);
-    if (nt == 128) return launch_tape<128>(tp, (unsigned)grid, smem, st);
-    if (nt == 64) return launch_tape<64>(tp, (unsigned)grid, smem, st);
-    return launch_tape<32>(tp, (unsigned)grid, smem, st);
+    // programs without values typed 0/1 run the instantiation that has no bit-slot file
+    if (p->tape.n_bslots) {
+        if (nt == 128) return launch_tape<128, true>(tp, (unsigned)grid, smem, st);
+        if (nt == 64) return launch_tape<64, true>(tp, (unsigned)grid, smem, st);
+        return launch_tape<32, true>(tp, (unsigned)grid, smem, st);
+    }
+    if (nt == 128) return launch_tape<128, false>(tp, (unsigned)grid, smem, st);
+    if (nt == 64) return launch_tape<64, false>(tp, (unsigned)grid, smem, st);
+    return launch_tape<32, false>(tp, (unsigned)grid, smem, st);
 }
 
 static kern::StoreView store_view(const cvmgpu_program *p, const void *d_store, uint64_t bstride) {
@@ -735,9 +775,9 @@ extern "C" int cvmgpu_r1cs_check_store_dev(cvmgpu_r1cs *r, cvmgpu_program *p, co
     if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
     if (int rc = upload_r1cs(r)) return rc;
     if (r->typed.layout_id != p->layout_id) {
-        if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data()), r->typed)) return rc;
+        if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow), r->typed)) return rc;
         r->typed.layout_id = p->layout_id;
-        r->typed.typed = p->tape.n_brows != 0;
+        r->typed.typed = r->typed.n_bterms != 0;   // no term on a bit row: the plain kernel runs on the field rows
         r->typed.n_brows = p->tape.n_brows;
     }
     const uint32_t *bits = (const uint32_t *)((const char *)d_store + store_field_bytes(p, bstride));

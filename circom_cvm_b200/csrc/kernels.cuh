@@ -53,6 +53,7 @@ struct TapeParams {
     uint32_t n_inputs;
     uint32_t *status;
     uint64_t B;
+    const unsigned long long *iconsts;   // constants of the integer operations
     uint32_t ring_off;       // uint4 offset of the reload ring inside the dynamic shared memory (after the field slots)
     uint32_t bslot_off;      // uint4 offset of the bit-slot file (after the ring)
 };
@@ -71,10 +72,10 @@ __device__ __forceinline__ Fr op_input(Fr v) {
 
 // operand fetch: constant table (uniform address, L1-resident), the thread's field slot in shared memory, or -- for a
 // value typed 0/1 -- the thread's bit of the warp's word in the bit-slot file (bw = this warp's file)
-template <int NT>
+template <int NT, bool BITS>
 __device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint32_t *bw, const uint4 *consts, uint32_t idx, bool is_const,
                                            uint32_t tid) {
-    if (!is_const && (idx & tape::BSLOT)) return mont_bool((bw[idx & 0xffffu] >> (tid & 31u)) & 1u);
+    if (BITS && !is_const && (idx & tape::BSLOT)) return mont_bool((bw[idx & 0xffffu] >> (tid & 31u)) & 1u);
     uint4 lo, hi;
     if (is_const) {
         lo = __ldg(consts + 2 * (uint64_t)idx);
@@ -86,11 +87,22 @@ __device__ __forceinline__ Fr tape_operand(const uint4 *slots, const uint32_t *b
     return unpack(lo, hi);
 }
 // truth value of an operand (select conditions): the bit itself when the value is typed 0/1
-template <int NT>
+template <int NT, bool BITS>
 __device__ __forceinline__ bool tape_truth(const uint4 *slots, const uint32_t *bw, const uint4 *consts, uint32_t idx, bool is_const,
                                            uint32_t tid) {
-    if (!is_const && (idx & tape::BSLOT)) return (bw[idx & 0xffffu] >> (tid & 31u)) & 1u;
-    return !fr::is_zero(tape_operand<NT>(slots, bw, consts, idx, is_const, tid));
+    if (BITS && !is_const && (idx & tape::BSLOT)) return (bw[idx & 0xffffu] >> (tid & 31u)) & 1u;
+    return !fr::is_zero(tape_operand<NT, BITS>(slots, bw, consts, idx, is_const, tid));
+}
+
+// operand of an integer operation (tape.hpp type_ints): a raw 64-bit integer in the low words of a field slot, a 0/1
+// value of the bit file, or an integer constant
+template <int NT, bool BITS>
+__device__ __forceinline__ unsigned long long tape_int(const uint4 *slots, const uint32_t *bw, const unsigned long long *iconsts,
+                                                       uint32_t idx, bool is_const, uint32_t tid) {
+    if (is_const) return __ldg(iconsts + idx);
+    if (BITS && (idx & tape::BSLOT)) return (bw[idx & 0xffffu] >> (tid & 31u)) & 1u;
+    const uint2 v = *reinterpret_cast<const uint2 *>(slots + (idx * 2) * NT + tid);
+    return (unsigned long long)v.x | ((unsigned long long)v.y << 32);
 }
 
 // integer-view operations, division, logic: shared by the tape's slow path and the device self-test.
@@ -136,7 +148,7 @@ __device__ __forceinline__ Fr slow_compute(uint32_t op, const Fr &a, const Fr &b
 // Everything that is not on the fast path of the tape loop (integer-view operations, division, inputs).  Out of
 // line, operands and result go through the slots, so that the hot loop keeps its working set in registers.  A result
 // typed 0/1 is returned as `truth` (the caller packs the warp's bits); a field result is written to its slot here.
-template <int NT>
+template <int NT, bool BITS>
 __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uint32_t *bw, const uint4 *consts, const uint4 *inputs,
                                               uint32_t n_inputs, uint64_t w, uint32_t status, uint32_t tid, uint32_t &truth) {
     const uint32_t op = cur.x & 0xffu, flags = (cur.x >> 8) & 0xffu, dst = cur.x >> 16;
@@ -145,13 +157,13 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
         const uint4 *src = inputs + (w * n_inputs + cur.y) * 2;
         r = op_input(unpack(src[0], src[1]));
     } else {
-        Fr a = tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
+        Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
         Fr b = fr::zero();
-        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid);
+        if (op != tape::T_BNOT && op != tape::T_INV) b = tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid);
         r = slow_compute(op, a, b, status);
     }
     truth = r.v[0] != 0u;   // a 0/1 value in Montgomery form is 0 or R mod q, whose low word is not 0
-    if (!(dst & tape::BSLOT_DST)) {
+    if (!BITS || !(dst & tape::BSLOT_DST)) {
         uint4 lo, hi;
         pack(r, lo, hi);
         slots[(dst * 2) * NT + tid] = lo;
@@ -169,7 +181,7 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
 // warp pack their bits into one word (__ballot_sync), every lane stores that same word to the warp's slot (so each lane
 // later reads its own store: no fence needed), and a bit row of the value store is that word per warp: 4 bytes where a
 // field row costs 1 KiB.
-template <int NT>
+template <int NT, bool BITS>
 __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
     extern __shared__ uint4 slots[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
@@ -199,8 +211,8 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
         uint32_t rb = 0;        // result of an instruction that produces a truth value
         bool is_rb = false;
         if (op >= tape::T_ADD && op <= tape::T_MUL) {
-            const Fr a = tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
-            const Fr b = tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid);
+            const Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
+            const Fr b = tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid);
             if (op == tape::T_MUL) {
                 // bit-heavy programs (F_TRIVIAL, set by the tape builder): factors that are 0 or 1 at run time without
                 // being provably so (input bits of a hash) need no product; decided per warp to keep control flow uniform
@@ -235,29 +247,55 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 const uint4 rec = __ldg(tp + pc + 1 + (j >> 1));
                 const uint32_t cidx = (j & 1u) ? rec.z : rec.x, slot = (j & 1u) ? rec.w : rec.y;
                 const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cidx), __ldg(consts + 2 * (uint64_t)cidx + 1));
-                const Fr x = tape_operand<NT>(slots, bw, consts, slot, false, tid);
+                const Fr x = tape_operand<NT, BITS>(slots, bw, consts, slot, false, tid);
                 fr::wide_mac(T, c, x);
             }
             r = fr::wide_reduce(T, n);
-            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid));
+            if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid));
             pc += (n + 1) >> 1;
             raw = __ldg(tp + min(pc + 1, n_ins - 1));
         } else if (op == tape::T_SEL) {
-            const bool t = tape_truth<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
+            const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
             // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
             const bool isc = t ? (flags & 2u) : (flags & 4u);
             const uint32_t idx = t ? cur.z : cur.w;
             r = fr::zero();
-            if (t || !(flags & tape::F_CZERO)) r = tape_operand<NT>(slots, bw, consts, idx, isc, tid);
+            if (t || !(flags & tape::F_CZERO)) r = tape_operand<NT, BITS>(slots, bw, consts, idx, isc, tid);
         } else if (op == tape::T_CADD) {
             // a + (b != 0 ? constant c : 0)
-            const Fr a = tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
-            const bool t = tape_truth<NT>(slots, bw, consts, cur.z, false, tid);
+            const Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
+            const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.z, false, tid);
             const Fr c = unpack(__ldg(consts + 2 * (uint64_t)cur.w), __ldg(consts + 2 * (uint64_t)cur.w + 1));
             const Fr sum = fr::add(a, c);
 #pragma unroll
             for (int i = 0; i < 8; i++) r.v[i] = t ? sum.v[i] : a.v[i];
-        } else if (op == tape::T_LUT) {
+        } else if (op >= tape::T_ICADD && op <= tape::T_IFAIL_NE) {
+            // small-integer arithmetic: raw 64-bit values (sums of 0/1 values times small constants)
+            if (op == tape::T_IBIT) {
+                const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, false, tid);
+                rb = cur.z < 64u ? (uint32_t)(a >> cur.z) & 1u : 0u;
+                is_rb = true;
+            } else if (op == tape::T_IFAIL_NE) {
+                const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid);
+                const unsigned long long b = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+                if (a != b && status == 0) status = cur.w;
+                continue;
+            } else {
+                unsigned long long v;
+                if (op == tape::T_ICADD) {
+                    v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid);
+                    if (tape_truth<NT, BITS>(slots, bw, consts, cur.z, false, tid)) v += __ldg(p.iconsts + cur.w);
+                } else if (op == tape::T_IADD) {
+                    v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid) +
+                        tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+                } else {
+                    const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
+                    v = tape_int<NT, BITS>(slots, bw, p.iconsts, t ? cur.z : cur.w, t ? (flags & 2u) : (flags & 4u), tid);
+                }
+                slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
+                continue;
+            }
+        } else if (BITS && op == tape::T_LUT) {
             // boolean function of up to three typed 0/1 values: this lane's bits of the three words index the table
             const uint32_t nin = (cur.z >> 8) & 0xffu;
             uint32_t idx = (bw[cur.y & 0xffffu] >> lane) & 1u;
@@ -274,9 +312,9 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             is_rb = true;
         } else if (op == tape::T_EQ || op == tape::T_NEQ || op == tape::T_EQZ || op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
             bool e;
-            if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = !tape_truth<NT>(slots, bw, consts, cur.y, flags & 1u, tid);
-            else e = fr::equal(tape_operand<NT>(slots, bw, consts, cur.y, flags & 1u, tid),
-                               tape_operand<NT>(slots, bw, consts, cur.z, flags & 2u, tid));
+            if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = !tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
+            else e = fr::equal(tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid),
+                               tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid));
             if (op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
                 if (!e && status == 0) status = cur.w;
                 continue;
@@ -284,7 +322,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             rb = (op == tape::T_NEQ) ? !e : e;
             is_rb = true;
         } else if (op == tape::T_LD) {
-            if (dst & tape::BSLOT_DST) {     // a bit row: the warp's word (written earlier by these same lanes)
+            if (BITS && (dst & tape::BSLOT_DST)) {     // a bit row: the warp's word (written earlier by these same lanes)
                 bw[dst & 0x7fffu] = brow[cur.w & ~tape::ROW_BIT];
                 continue;
             }
@@ -315,7 +353,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             if (cur.w & tape::ROW_BIT) {
                 uint32_t word;
                 if (op == tape::T_STC) word = __ldg(consts + 2 * (uint64_t)cur.y).x ? 0xffffffffu : 0u;
-                else word = bw[cur.y & 0xffffu];
+                else word = BITS ? bw[cur.y & 0xffffu] : 0u;
                 if (warp_active) brow[cur.w & ~tape::ROW_BIT] = word;
                 continue;
             }
@@ -329,8 +367,8 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             }
             continue;
         } else {
-            status = tape_slow_op<NT>(cur, slots, bw, consts, p.inputs, p.n_inputs, w, status, tid, rb);
-            if (!(dst & tape::BSLOT_DST)) {
+            status = tape_slow_op<NT, BITS>(cur, slots, bw, consts, p.inputs, p.n_inputs, w, status, tid, rb);
+            if (!BITS || !(dst & tape::BSLOT_DST)) {
                 if ((flags & tape::F_STORE) && active) {
                     uint4 *d = row_ptr(wbase, cur.w, bstride);
                     d[0] = slots[(dst * 2) * NT + tid];
@@ -340,7 +378,7 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             }
             is_rb = true;
         }
-        if (dst & tape::BSLOT_DST) {
+        if (BITS && (dst & tape::BSLOT_DST)) {
             const uint32_t word = __ballot_sync(0xffffffffu, is_rb ? rb != 0u : r.v[0] != 0u);
             bw[dst & 0x7fffu] = word;
             if ((flags & tape::F_STORE) && warp_active) brow[cur.w & ~tape::ROW_BIT] = word;
@@ -599,12 +637,54 @@ __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, ui
     return acc;
 }
 
+// Stream of the bit-row terms of a chunk of constraints.  They are consumed strictly in CSR order by every lane of a
+// warp, and a term's operand is one 32-bit word for the whole warp -- so the warp fetches them cooperatively: lane l
+// loads term (base + l), its word of the bit row and its integer coefficient (32 independent gathers in flight at
+// once), the batch after the one being consumed waits in registers, and the batch being consumed sits in a 512-byte
+// stage of shared memory that every lane reads with broadcast loads.  The DRAM / L2 latency of the gathers is paid
+// once per 32 terms, under the arithmetic of the previous batch, instead of once per term on the dependence chain.
+struct BitStream {
+    const uint2 *bterms;
+    const uint32_t *brow;
+    const long long *cint;
+    uint4 *stage;        // this warp's 32 entries: (word, coefficient index, integer coefficient lo, hi)
+    uint32_t base, t_end, lane;   // lane: the thread's own lane (which entry of a batch it fetches)
+    uint32_t bitlane;             // the lane whose bit of a word this thread reads (a padding thread copies the last witness)
+    uint4 nxt;
+    __device__ __forceinline__ void load(uint32_t b) {
+        const uint32_t t = b + lane;
+        nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (t < t_end) {
+            const uint2 term = __ldg(bterms + t);
+            const long long c = __ldg(cint + term.y);
+            nxt = make_uint4(__ldg(brow + term.x), term.y, (uint32_t)c, (uint32_t)((unsigned long long)c >> 32));
+        }
+    }
+    __device__ __forceinline__ void start(uint32_t t0) {
+        base = t0;
+        load(t0);
+        stage[lane] = nxt;
+        __syncwarp();
+        load(t0 + 32);
+    }
+    __device__ __forceinline__ uint4 at(uint32_t t) {
+        while (t >= base + 32) {     // uniform: every lane of the warp walks the same terms
+            __syncwarp();
+            stage[lane] = nxt;
+            __syncwarp();
+            base += 32;
+            load(base + 32);
+        }
+        return stage[t - base];
+    }
+};
+
 // bit-row terms of one linear combination in the field: acc += bit ? coefficient : 0 (no multiplication)
-__device__ __forceinline__ Fr lc_bits(const R1csParams &p, const uint32_t *brow, uint32_t lane, uint32_t b, uint32_t e, Fr acc) {
+__device__ __forceinline__ Fr lc_bits(const R1csParams &p, BitStream &bs, uint32_t b, uint32_t e, Fr acc) {
     for (uint32_t t = b; t < e; t++) {
-        const uint2 term = __ldg(p.bterms + t);
-        const bool bit = (__ldg(brow + term.x) >> lane) & 1u;
-        const uint4 lo = __ldg(p.coefs + 2 * (uint64_t)term.y), hi = __ldg(p.coefs + 2 * (uint64_t)term.y + 1);
+        const uint4 s = bs.at(t);
+        const bool bit = (s.x >> bs.bitlane) & 1u;
+        const uint4 lo = __ldg(p.coefs + 2 * (uint64_t)s.y), hi = __ldg(p.coefs + 2 * (uint64_t)s.y + 1);
         Fr c;
         c.v[0] = bit ? lo.x : 0u; c.v[1] = bit ? lo.y : 0u; c.v[2] = bit ? lo.z : 0u; c.v[3] = bit ? lo.w : 0u;
         c.v[4] = bit ? hi.x : 0u; c.v[5] = bit ? hi.y : 0u; c.v[6] = bit ? hi.z : 0u; c.v[7] = bit ? hi.w : 0u;
@@ -613,14 +693,12 @@ __device__ __forceinline__ Fr lc_bits(const R1csParams &p, const uint32_t *brow,
     return acc;
 }
 // the same in plain integers (the host guarantees that no partial sum leaves 63 bits)
-__device__ __forceinline__ long long lc_int(const R1csParams &p, const uint32_t *brow, uint32_t lane, uint32_t b, uint32_t e) {
+__device__ __forceinline__ long long lc_int(BitStream &bs, uint32_t b, uint32_t e) {
     long long acc = 0;
-#pragma unroll 4
     for (uint32_t t = b; t < e; t++) {
-        const uint2 term = __ldg(p.bterms + t);
-        const uint32_t word = __ldg(brow + term.x);
-        const long long c = __ldg(p.cint + term.y);
-        acc += ((word >> lane) & 1u) ? c : 0ll;
+        const uint4 s = bs.at(t);
+        const long long c = (long long)((unsigned long long)s.z | ((unsigned long long)s.w << 32));
+        acc += ((s.x >> bs.bitlane) & 1u) ? c : 0ll;
     }
     return acc;
 }
@@ -628,10 +706,12 @@ __device__ __forceinline__ long long lc_int(const R1csParams &p, const uint32_t 
 template <int MINB, bool TYPED>
 __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     __shared__ uint4 ring[R1CS_STAGES * 2 * R1CS_NT];
+    __shared__ uint4 bstage[TYPED ? R1CS_NT : 1];
     uint64_t w = (uint64_t)blockIdx.x * R1CS_NT + threadIdx.x;
     const bool active = w < p.B;
+    // (a padding lane evaluates a copy of the last witness: its bit is the last witness's lane of that warp's word)
+    const uint32_t lane = (uint32_t)(active ? w : p.B - 1) & 31u;
     if (!active) w = p.B - 1;
-    const uint32_t lane = (uint32_t)w & 31u;
     const uint32_t c0 = blockIdx.y * p.cons_per_chunk;
     const uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
     const uint4 *wbase = p.store + w;
@@ -645,6 +725,17 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         ts.ring = ring;
         ts.t_end = t_end;
         ts.start(__ldg(&p.hdr[3 * c0].x));
+    }
+    BitStream bs;
+    if (TYPED) {
+        bs.bterms = p.bterms;
+        bs.brow = brow;
+        bs.cint = p.cint;
+        bs.stage = bstage + (threadIdx.x & ~31u);
+        bs.lane = threadIdx.x & 31u;
+        bs.bitlane = lane;
+        bs.t_end = __ldg(p.bhdr + 3 * c1) & 0x7fffffffu;
+        bs.start(__ldg(p.bhdr + 3 * c0) & 0x7fffffffu);
     }
     uint32_t bad = 0xffffffffu;
     uint4 hA = __ldg(p.hdr + 3 * c0);
@@ -661,7 +752,7 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
                 // every term is a 0/1 wire with a small integer coefficient: |A*B - C| is far below q, so the constraint
                 // holds mod q iff it holds in the integers
                 bA &= 0x7fffffffu;
-                const long long ia = lc_int(p, brow, lane, bA, bB), ib = lc_int(p, brow, lane, bB, bC), ic = lc_int(p, brow, lane, bC, bN);
+                const long long ia = lc_int(bs, bA, bB), ib = lc_int(bs, bB, bC), ic = lc_int(bs, bC, bN);
                 const long long lo = ia * ib, hi = __mul64hi(ia, ib);
                 if (bad == 0xffffffffu && (lo != ic || hi != (ic >> 63))) bad = c;
                 hA = hN;
@@ -674,7 +765,7 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         if (hB.y == R1CS_SAME_AS_A) {        // B repeats A (r1cs.hpp): one evaluation, one squaring
             Fr sa = fr::zero();
             if (hA.x != hB.x) sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
-            if (TYPED) sa = lc_bits(p, brow, lane, bA, bB, sa);
+            if (TYPED) sa = lc_bits(p, bs, bA, bB, sa);
             const Fr one = fr::one_mont();
             if (fr::is_zero(sa)) prod = fr::zero();
             else if (sa.v[0] == one.v[0] && fr::equal(sa, one)) prod = one;
@@ -682,9 +773,9 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         } else if (hasA && hasB) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
             Fr sa = fr::zero(), sb = fr::zero();
             if (hA.x != hB.x) sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
-            if (TYPED) sa = lc_bits(p, brow, lane, bA, bB, sa);
+            if (TYPED) sa = lc_bits(p, bs, bA, bB, sa);
             if (hB.x != hC.x) sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
-            if (TYPED) sb = lc_bits(p, brow, lane, bB, bC, sb);
+            if (TYPED) sb = lc_bits(p, bs, bB, bC, sb);
             // trivial factors need no product: 0, 1 and -1 (bit-valued wires and the +-1 combinations of them that
             // fill hash circuits).  The branch is per lane; a warp pays for the multiplication only if one of its
             // witnesses needs it.
@@ -705,7 +796,7 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         }
         Fr sc = fr::zero();
         if (hC.x != hN.x) sc = lc_any(p, wbase, ring, t_end, hC, hN.x);
-        if (TYPED && hasC) sc = lc_bits(p, brow, lane, bC, bN, sc);
+        if (TYPED && hasC) sc = lc_bits(p, bs, bC, bN, sc);
         if (bad == 0xffffffffu && !fr::equal(prod, sc)) bad = c;
         hA = hN;
     }

@@ -70,8 +70,9 @@ struct Bound {
 
 static const uint32_t LOC_BIT = 0x80000000u;   // tape::ROW_BIT
 
-// wire_loc == nullptr: the plain layout (row = wire, no bit rows)
-inline Bound bind(const File &f, const uint32_t *wire_loc) {
+// wire_loc == nullptr: the plain layout (row = wire, no bit rows).  one_brow: the bit row that holds the constant 1 (wire 0
+// itself is a field row): terms on wire 0 use it in constraints evaluated in integers.
+inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0) {
     Bound b;
     const size_t n_lc = f.ptr.size() - 1;
     b.hdr.assign(4 * (n_lc + 1), 0);
@@ -94,7 +95,8 @@ inline Bound bind(const File &f, const uint32_t *wire_loc) {
             uint64_t sumabs = 0;
             for (uint32_t t = sb[src]; t < se[src] && intok; t++) {
                 const Term &tm = f.terms[t];
-                if (!(loc_of(tm.wire & 0x0fffffffu) & LOC_BIT) || !f.cint_ok[tm.coef]) { intok = false; break; }
+                const uint32_t wire = tm.wire & 0x0fffffffu;
+                if ((wire != 0 && !(loc_of(wire) & LOC_BIT)) || !f.cint_ok[tm.coef]) { intok = false; break; }
                 const int64_t v = f.cint[tm.coef];
                 sumabs += (uint64_t)(v < 0 ? -v : v);
                 if (sumabs >> 62) intok = false;
@@ -120,7 +122,8 @@ inline Bound bind(const File &f, const uint32_t *wire_loc) {
             uint32_t n[4] = {0, 0, 0, 0}, n_const = 0;
             for (uint32_t t = sb[src]; t < se[src]; t++) {
                 const Term &tm = f.terms[t];
-                const uint32_t loc = loc_of(tm.wire & 0x0fffffffu);
+                uint32_t loc = loc_of(tm.wire & 0x0fffffffu);
+                if (intok && (tm.wire & 0x0fffffffu) == 0) loc = LOC_BIT | one_brow;
                 if (loc & LOC_BIT) {
                     b.bterms.push_back(Term{loc & ~LOC_BIT, tm.coef});
                     if (!intok) b.bit_adds++;

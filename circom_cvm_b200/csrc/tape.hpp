@@ -44,6 +44,7 @@ struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
+    uint64_t n_int = 0;            // small-integer operations (type_ints): sums of 0/1 values kept as raw 64-bit integers
     uint64_t n_ld_bool = 0, n_spill_st_bool = 0;   // of n_ld / n_spill_st: the value is typed 0/1 (what compact bit rows would shrink)
     uint32_t n_spill_rows = 0;
     uint32_t max_live_field = 0, max_live_bool = 0;   // simultaneously live values of each kind (unlimited slots)
@@ -63,7 +64,10 @@ struct Tape {
     // (one 32-bit word per warp of witnesses) hold the wires proven 0/1 [0, n_bwires) and bit spills
     uint32_t n_bslots = 0;    // bit slots per warp
     uint32_t n_frows = 0, n_brows = 0, n_fwires = 0, n_bwires = 0;
+    std::vector<uint64_t> iconsts;    // constants of the integer operations
     std::vector<uint32_t> wire_loc;   // per witness wire: field row, or ROW_BIT | bit row
+    bool use_ring = false;            // field reloads are streamed through the cp.async ring (schedule_reloads)
+    uint32_t one_brow = 0;            // bit row that holds the constant 1 for every witness (wire 0 itself is a field row)
     TapeStats stats;
 };
 
@@ -171,6 +175,7 @@ struct XProg {
     std::vector<std::pair<uint32_t, uint32_t>> terms;   // (constant ref, value id)
     std::vector<uint32_t> witness_ref;
     std::vector<uint8_t> isbool;   // per op: the tracer proved the value 0/1 (fused results: not typed)
+    std::vector<uint8_t> isint;    // per op: a raw 64-bit integer (type_ints), only consumed by integer operations
 };
 
 inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
@@ -307,6 +312,176 @@ inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
     return xp;
 }
 
+// ---- small-integer typing ---------------------------------------------------------------------------------
+// circomlib's BinSum / Bits2Num compute  lin = sum_k bit_k * 2^k  in the field and then take it apart again with
+// (lin >> k) & 1.  Every value on that path is a small non-negative integer; as field elements each step costs a
+// 256-bit modular addition and each decomposition a Montgomery product (to read the canonical limbs).  This pass finds
+// the values that (1) are provably below 2^62 -- sums of 0/1 values times small constants -- and (2) are ONLY consumed
+// by other such sums, by bit extractions and by equality asserts between two of them, and retypes them as raw 64-bit
+// integers: T_CADD -> T_ICADD, T_ADD -> T_IADD, T_SEL -> T_ISEL, BITC(x * R^-1, k) -> IBIT(x, k) (the product dies),
+// FAIL_NE -> IFAIL_NE.  A value with any other consumer (field arithmetic, a witness wire) stays a field element, so
+// no conversion is ever needed; the result of every wire is bit-identical.
+inline void type_ints(XProg &xp, const Tracer &tr) {
+    std::vector<XOp> &ops = xp.ops;
+    const size_t N = ops.size();
+    xp.isint.assign(N, 0);
+    const uint64_t LIM = 1ull << 62;
+    auto small_const = [&](uint32_t r, uint64_t &v) -> bool {
+        if (r == NO_REF || !(r & CONST_FLAG)) return false;
+        const fr::Fr &c = tr.consts[r & ~CONST_FLAG];
+        for (int i = 2; i < 8; i++)
+            if (c.v[i]) return false;
+        v = ((uint64_t)c.v[1] << 32) | c.v[0];
+        return v < LIM;
+    };
+    std::vector<uint8_t> cand(N, 0);
+    std::vector<uint64_t> bound(N, 0);
+    // integer view of a ref under the current candidates: constants below 2^62, 0/1 values, candidate integers
+    auto intable = [&](uint32_t r, uint64_t &b) -> bool {
+        if (r == NO_REF) return false;
+        if (r & CONST_FLAG) return small_const(r, b);
+        if (xp.isbool[r]) { b = 1; return true; }
+        if (cand[r]) { b = bound[r]; return true; }
+        return false;
+    };
+    auto eval = [&](size_t i) -> bool {   // can op i be an integer op, given its operands?  sets bound[i]
+        const XOp &o = ops[i];
+        uint64_t x, y;
+        if (xp.isbool[i]) return false;
+        switch (o.op) {
+            case T_CADD: {
+                uint64_t k;
+                if (!intable(o.a, x) || !small_const(o.c, k) || x + k >= LIM) return false;
+                bound[i] = x + k;
+                return true;
+            }
+            case T_ADD:
+                if (!intable(o.a, x) || !intable(o.b, y) || x + y >= LIM) return false;
+                bound[i] = x + y;
+                return true;
+            case T_SEL:
+                if (!intable(o.b, x) || !intable(o.c, y)) return false;
+                bound[i] = std::max(x, y);
+                return true;
+            default: return false;
+        }
+    };
+    for (size_t i = 0; i < N; i++) cand[i] = eval(i) ? 1 : 0;
+    // uses
+    std::vector<uint32_t> use_cnt(N + 1, 0);
+    auto each_operand = [&](const XOp &o, auto &&fn) {
+        if (o.op == T_DOT)
+            for (uint32_t k = 0; k < o.tn; k++) fn(xp.terms[o.t0 + k].second, 3);
+        fn(o.a, 0);
+        fn(o.b, 1);
+        fn(o.c, 2);
+    };
+    for (size_t i = 0; i < N; i++)
+        each_operand(ops[i], [&](uint32_t r, int) { if (r != NO_REF && !(r & CONST_FLAG)) use_cnt[r + 1]++; });
+    for (size_t i = 0; i < N; i++) use_cnt[i + 1] += use_cnt[i];
+    std::vector<uint32_t> use_op(use_cnt[N]);
+    {
+        std::vector<uint32_t> fill(use_cnt.begin(), use_cnt.end() - 1);
+        for (size_t i = 0; i < N; i++)
+            each_operand(ops[i], [&](uint32_t r, int) { if (r != NO_REF && !(r & CONST_FLAG)) use_op[fill[r]++] = (uint32_t)i; });
+    }
+    std::vector<uint8_t> on_wire(N, 0);
+    for (uint32_t r : xp.witness_ref)
+        if (!(r & CONST_FLAG)) on_wire[r] = 1;
+    const uint32_t rinv = tr.rinv_ref();
+    // x * R^-1 whose only consumers are bit extractions: with an integer x those read the integer directly
+    auto is_canon_for_bits = [&](uint32_t u, uint32_t v) -> bool {
+        const XOp &o = ops[u];
+        if (o.op != T_MUL || on_wire[u]) return false;
+        if (!((o.a == v && o.b == rinv) || (o.b == v && o.a == rinv))) return false;
+        for (uint32_t k = use_cnt[u]; k < use_cnt[u + 1]; k++)
+            if (ops[use_op[k]].op != T_BITC || ops[use_op[k]].a != u) return false;
+        return use_cnt[u + 1] > use_cnt[u];
+    };
+    auto uses_ok = [&](uint32_t v) -> bool {
+        if (on_wire[v]) return false;
+        for (uint32_t k = use_cnt[v]; k < use_cnt[v + 1]; k++) {
+            const uint32_t u = use_op[k];
+            const XOp &o = ops[u];
+            if (cand[u]) {
+                // as an integer operand (not as the condition of a select / conditional add)
+                if (o.op == T_CADD && o.a == v && o.b != v) continue;
+                if (o.op == T_ADD) continue;
+                if (o.op == T_SEL && o.a != v) continue;
+                return false;
+            }
+            if (o.op == T_FAIL_NE) {
+                uint64_t x, y;
+                if (intable(o.a, x) && intable(o.b, y)) continue;
+                return false;
+            }
+            if (is_canon_for_bits(u, v)) continue;
+            return false;
+        }
+        return true;
+    };
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (size_t i = 0; i < N; i++)
+            if (cand[i] && !(eval(i) && uses_ok((uint32_t)i))) { cand[i] = 0; changed = true; }
+        for (size_t i = N; i-- > 0;)
+            if (cand[i] && !(eval(i) && uses_ok((uint32_t)i))) { cand[i] = 0; changed = true; }
+    }
+    // rewrite
+    for (size_t i = 0; i < N; i++) {
+        XOp &o = ops[i];
+        if (cand[i]) {
+            o.op = o.op == T_CADD ? T_ICADD : o.op == T_ADD ? T_IADD : T_ISEL;
+            xp.isint[i] = 1;
+        } else if (o.op == T_BITC && !(o.a & CONST_FLAG)) {
+            const XOp &m = ops[o.a];
+            if (m.op == T_MUL && (m.a == rinv || m.b == rinv)) {
+                const uint32_t x = m.a == rinv ? m.b : m.a;
+                if (x != NO_REF && !(x & CONST_FLAG) && cand[x]) {
+                    o.op = T_IBIT;
+                    o.a = x;
+                }
+            }
+        } else if (o.op == T_FAIL_NE) {
+            const bool ia = !(o.a & CONST_FLAG) && cand[o.a], ib = !(o.b & CONST_FLAG) && cand[o.b];
+            uint64_t x, y;
+            if ((ia || ib) && intable(o.a, x) && intable(o.b, y)) o.op = T_IFAIL_NE;
+        }
+    }
+    // drop what died (the x * R^-1 products of retyped values)
+    std::vector<uint8_t> live(N, 0);
+    for (uint32_t r : xp.witness_ref)
+        if (!(r & CONST_FLAG)) live[r] = 1;
+    for (size_t i = N; i-- > 0;) {
+        const XOp &o = ops[i];
+        if (o.op == T_FAIL_IF || o.op == T_FAIL_NE || o.op == T_IFAIL_NE) live[i] = 1;
+        if (!live[i]) continue;
+        each_operand(o, [&](uint32_t r, int) { if (r != NO_REF && !(r & CONST_FLAG)) live[r] = 1; });
+    }
+    std::vector<uint32_t> remap(N, NO_REF);
+    auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
+    std::vector<XOp> out;
+    std::vector<uint8_t> ob, oi;
+    out.reserve(N);
+    for (size_t i = 0; i < N; i++) {
+        if (!live[i]) continue;
+        XOp o = ops[i];
+        if (o.op == T_DOT)
+            for (uint32_t k = 0; k < o.tn; k++) xp.terms[o.t0 + k].second = mapref(xp.terms[o.t0 + k].second);
+        o.a = mapref(o.a);
+        o.b = mapref(o.b);
+        o.c = mapref(o.c);
+        remap[i] = (uint32_t)out.size();
+        out.push_back(o);
+        ob.push_back(xp.isbool[i]);
+        oi.push_back(xp.isint[i]);
+    }
+    for (uint32_t &r : xp.witness_ref) r = mapref(r);
+    ops.swap(out);
+    xp.isbool.swap(ob);
+    xp.isint.swap(oi);
+}
+
 // ---- reload stream ---------------------------------------------------------------------------------------
 // The FIELD rows a tape reloads (T_LD into a field slot) and their order are fixed, so the kernel streams them: the
 // n-th reload's row is requested (cp.async into a per-witness ring in shared memory) when reload n - LD_RING executes,
@@ -362,7 +537,7 @@ inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
         use(o.b);
         use(o.c);
     }
-    auto produces = [&](size_t i) { return xp.ops[i].op != T_FAIL_IF && xp.ops[i].op != T_FAIL_NE; };
+    auto produces = [&](size_t i) { return xp.ops[i].op != T_FAIL_IF && xp.ops[i].op != T_FAIL_NE && xp.ops[i].op != T_IFAIL_NE; };
     std::vector<uint32_t> deaths[2];
     deaths[0].assign(N, 0);
     deaths[1].assign(N, 0);
@@ -396,10 +571,16 @@ inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
 // witness), spilled to / reloaded from bit rows of the value store (one word per warp).  Everything else lives in the
 // FIELD file (32-byte slots per witness) and in field rows.  A witness wire is a bit row or a field row according to
 // the type of the value bound to it (Tape::wire_loc); consumers of a 0/1 value in field arithmetic convert on fetch.
-inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uint32_t max_bslots = 2048) {
+// fusions and typing that do not depend on the slot files (max_terms: longest fused dot product)
+inline XProg prepare_program(const Tracer &tr, uint32_t max_terms, bool fuse = true) {
+    XProg xp = fuse_dots(tr, max_terms, fuse);
+    if (fuse) type_ints(xp, tr);
+    else xp.isint.assign(xp.ops.size(), 0);
+    return xp;
+}
+
+inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, uint32_t max_bslots = 2048) {
     if (n_slots < 4) throw TraceError("need at least 4 slots");
-    const uint32_t max_terms = std::min<uint32_t>(16, n_slots - 2);
-    const XProg xp = fuse_dots(tr, max_terms, fuse);
     const std::vector<XOp> &ops = xp.ops;
     const size_t N = ops.size();
     Tape out;
@@ -421,9 +602,12 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
     // ---- witness wire -> typed row
     out.wire_loc.resize(out.n_wires);
     {
+        // wire 0 is the constant 1 (calcwit.cpp:34): it keeps a field row (linear combinations evaluated in the field add
+        // their constant term through it) AND gets a bit row (Tape::one_brow) for constraints evaluated in integers
         uint32_t nf = 0, nb = 0;
-        for (uint32_t w = 0; w < out.n_wires; w++) out.wire_loc[w] = is_bool_ref(xp.witness_ref[w]) ? (ROW_BIT | nb++) : nf++;
+        for (uint32_t w = 0; w < out.n_wires; w++) out.wire_loc[w] = (w != 0 && is_bool_ref(xp.witness_ref[w])) ? (ROW_BIT | nb++) : nf++;
         out.n_fwires = nf;
+        out.one_brow = nb++;
         out.n_bwires = nb;
     }
     uint32_t ml[2];
@@ -480,6 +664,10 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
         wire_head[r] = (uint32_t)w;
     }
     // constants bound to wires are stored up front
+    if (out.n_wires) {
+        out.ins.push_back(TapeIns{T_STC, 1, 0, tr.one_ref() & ~CONST_FLAG, 0, ROW_BIT | out.one_brow});
+        out.stats.n_stc++;
+    }
     for (size_t w = 0; w < xp.witness_ref.size(); w++) {
         uint32_t r = xp.witness_ref[w];
         if (r & CONST_FLAG) {
@@ -555,6 +743,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
 
     std::vector<uint32_t> pinned, still;
     std::vector<uint32_t> enc;
+    std::unordered_map<uint64_t, uint32_t> iconst_index;
     for (size_t i = 0; i < N; i++) {
         const XOp &o = ops[i];
         uint32_t pos = (uint32_t)i;
@@ -597,7 +786,22 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
         if (o.op != T_DOT)
             for (size_t k = 0; k < 3; k++)
                 if (isc[k]) flags |= (uint8_t)(1u << k);
-        if (o.op == T_FAIL_IF || o.op == T_FAIL_NE) {
+        if (o.op == T_ICADD || o.op == T_IADD || o.op == T_ISEL || o.op == T_IFAIL_NE) {
+            // integer operations take their constants from the table of raw 64-bit integers
+            for (size_t k = (o.op == T_ISEL ? 1 : 0); k < 3; k++) {
+                if (!isc[k]) continue;
+                const fr::Fr &cv = tr.consts[enc[k]];
+                const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
+                auto it = iconst_index.find(v);
+                if (it == iconst_index.end()) {
+                    it = iconst_index.emplace(v, (uint32_t)out.iconsts.size()).first;
+                    out.iconsts.push_back(v);
+                }
+                enc[k] = it->second;
+            }
+            if (o.op != T_IFAIL_NE) out.stats.n_int++;
+        }
+        if (o.op == T_FAIL_IF || o.op == T_FAIL_NE || o.op == T_IFAIL_NE) {
             out.ins.push_back(TapeIns{o.op, flags, 0, enc[0], enc[1], o.aux});
             out.stats.n_fail++;
             continue;
@@ -644,7 +848,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
         } else {
             uint32_t e0 = enc[0], e1 = enc[1], e2 = enc[2];
             if (o.op == T_INPUT) e0 = o.aux;
-            if (o.op == T_BITC) e1 = o.aux;
+            if (o.op == T_BITC || o.op == T_IBIT) e1 = o.aux;
             if (o.op == T_LUT) {   // a = bit slots 0 and 1 (16 bits each); b = table | k << 8 | bit slot 2 << 16; c is free for the fused store
                 e0 = (enc[0] & 0xffffu) | ((enc[1] & 0xffffu) << 16);
                 e1 = (o.aux & 0xffffu) | ((enc[2] & 0xffffu) << 16);
@@ -670,6 +874,7 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
                 case T_SEL: out.stats.n_sel++; break;
                 case T_CADD: out.stats.n_addsub++; break;
                 case T_ADD: case T_SUB: out.stats.n_addsub++; break;
+                case T_ICADD: case T_IADD: case T_ISEL: break;   // counted in n_int
                 case T_INPUT: out.stats.n_input++; break;
                 default: out.stats.n_other++; break;
             }
@@ -695,10 +900,17 @@ inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uin
             if (in.op == T_MUL) in.flags |= F_TRIVIAL;
         }
     }
-    schedule_reloads(out);
+    // the reload ring costs 128 B of shared memory per witness: only worth it when the tape reloads field rows often
+    out.use_ring = (uint64_t)(out.stats.n_ld - out.stats.n_ld_bool) * 50 >= out.ins.size();
+    if (out.use_ring) schedule_reloads(out);
     out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +
                      72 * out.stats.n_dot + 1800 * (out.stats.n_inv + out.stats.n_div);
     return out;
+}
+
+inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uint32_t max_bslots = 2048) {
+    if (n_slots < 4) throw TraceError("need at least 4 slots");
+    return allocate_tape(tr, prepare_program(tr, std::min<uint32_t>(16, n_slots - 2), fuse), n_slots, max_bslots);
 }
 
 }  // namespace tape

@@ -40,7 +40,15 @@ enum TOp : uint8_t {
     // inserted by the tape builder
     T_CADD,      // a + (b != 0 ? c : 0) with a constant c: the `acc += bit * 2^k` step of every bit-weighted sum (tape.hpp)
     T_DOT,       // sum_k c_k * x_k (+ addend): fused tree of additions of products by constants (tape.hpp fuse_dots)
-    T_LD, T_ST, T_STC, T_COUNT
+    T_LD, T_ST, T_STC,
+    // small-integer arithmetic (tape.hpp type_ints): values proven below 2^62 that only feed each other and bit
+    // extractions -- the bit-weighted sums of BinSum / Bits2Num -- are kept as raw 64-bit integers in their slot
+    T_ICADD,     // a + (b != 0 ? K : 0), K = integer constant c
+    T_IADD,      // a + b
+    T_ISEL,      // a != 0 ? b : c
+    T_IBIT,      // bit `aux` of the integer a (a value typed 0/1)
+    T_IFAIL_NE,  // status if the integers a and b differ
+    T_COUNT
 };
 
 static const uint32_t CONST_FLAG = 0x80000000u;
@@ -109,6 +117,7 @@ class Tracer {
     TraceStats stats;
     int64_t n_inputs = 0, n_outputs = 0;
 
+    uint32_t rinv_ref() const { return CONST_FLAG | c_rinv; }
     uint32_t zero_ref() const { return CONST_FLAG | c_zero; }
     uint32_t one_ref() const { return CONST_FLAG | c_one; }
 

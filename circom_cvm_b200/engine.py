@@ -29,7 +29,7 @@ ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (cs
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_info_get", "cvmgpu_program_free",
-    "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows",
+    "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
     "cvmgpu_wtns_write",
@@ -55,7 +55,7 @@ class ProgramInfo(ctypes.Structure):
                 ("tape_dot_terms", c_uint64), ("tape_macs", c_uint64), ("tape_ld_streamed", c_uint64), ("unrolled_iterations", c_uint64), ("tape_lut", c_uint64),
                 ("tape_ld_bool", c_uint64), ("tape_spill_st_bool", c_uint64), ("n_bool_wires", c_uint64),
                 ("n_bslots", c_uint32), ("n_frows", c_uint32), ("n_brows", c_uint32), ("max_live_field", c_uint32),
-                ("max_live_bool", c_uint32), ("reserved1", c_uint32)]
+                ("max_live_bool", c_uint32), ("reserved1", c_uint32), ("tape_int", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -92,6 +92,7 @@ def lib():
     L.cvmgpu_program_witness.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_wire_types.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_wire_rows.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
+    L.cvmgpu_program_iconsts.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_witness_batch_select.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_export_range_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p]
     L.cvmgpu_r1cs_check_store_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
@@ -257,8 +258,11 @@ class WitnessCalculator:
     def layout(self):
         """what tests/tape_emulator.py needs to execute the tape: slot files, row counts, wire -> row map"""
         i = self.info
+        ptr, n = c_void_p(), c_uint32()
+        _check(lib().cvmgpu_program_iconsts(self._h, byref(ptr), byref(n)))
+        iconsts = [int(x) for x in np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(c_uint64)), shape=(n.value,))] if n.value else []
         return {"n_slots": int(i.n_slots), "n_bslots": int(i.n_bslots), "n_frows": int(i.n_frows), "n_brows": int(i.n_brows),
-                "wire_loc": [int(x) for x in self.wire_rows()]}
+                "wire_loc": [int(x) for x in self.wire_rows()], "iconsts": iconsts}
 
     def write_wtns(self, path, witness_row):
         row = np.ascontiguousarray(witness_row, dtype=np.uint8)

@@ -89,6 +89,7 @@ typedef struct {
     uint32_t max_live_field;     /* most field-typed values live at once */
     uint32_t max_live_bool;      /* most 0/1-typed values live at once */
     uint32_t reserved1;
+    uint64_t tape_int;           /* small-integer operations: bit-weighted sums kept as raw 64-bit integers instead of field values */
 } cvmgpu_program_info;
 
 typedef struct {
@@ -128,6 +129,8 @@ void cvmgpu_program_free(cvmgpu_program *p);
 /* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table
  * (32-byte LE Montgomery values).  For inspection and for host-side tests of the trace compiler. */
 int cvmgpu_program_tape(const cvmgpu_program *p, const void **ins, uint64_t *n_ins, const void **consts, uint32_t *n_consts);
+/* constants of the tape's small-integer operations (raw 64-bit integers) */
+int cvmgpu_program_iconsts(const cvmgpu_program *p, const uint64_t **iconsts, uint32_t *n);
 /* The program's %%witness list: signal index of every witness wire (= the witness2SignalList of the .dat,
  * c_code_generator.rs:541-550; used to locate the input hash map of a .dat, circom_cvm_b200/inputs.py). */
 int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n);

@@ -8,7 +8,7 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC) = range(35)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE) = range(40)
 F_ADDEND = 32        # T_DOT: field b is an addend
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
@@ -67,6 +67,18 @@ def run_tape(tape, consts_mont, layout, inputs):
         assert v is not None, "load of an unwritten row"
         return v
 
+    iconsts = layout.get("iconsts", [])
+
+    class Int(int):
+        """a raw 64-bit integer in a field slot: must never be read as a field element"""
+
+    def get_int(idx, is_const):
+        if is_const:
+            return iconsts[idx]
+        v = get_slot(idx)
+        assert idx & BSLOT or isinstance(v, Int), "integer operation reads a field value"
+        return int(v)
+
     pc = 0
     while pc < len(tape):
         ins = tape[pc]
@@ -77,7 +89,9 @@ def run_tape(tape, consts_mont, layout, inputs):
         def operand(idx, bit):
             if flags & bit:
                 return consts[idx]
-            return get_slot(idx)
+            v = get_slot(idx)
+            assert not isinstance(v, Int), "field operation reads a raw integer"
+            return v
 
         res = None
         if op == T_DOT:
@@ -109,12 +123,30 @@ def run_tape(tape, consts_mont, layout, inputs):
             assert dst & BSLOT_DST
         elif op == T_BITC:
             # bit b of the RAW (Montgomery) limbs of field slot a
-            assert not (a & BSLOT) and slots[a] is not None
+            assert not (a & BSLOT) and slots[a] is not None and not isinstance(slots[a], Int)
             res = ((slots[a] * R % M.Q) >> b) & 1
         elif op == T_FAIL_NE:
             if status == 0 and operand(a, 1) != operand(b, 2):
                 status = c
             continue
+        elif op == T_IFAIL_NE:
+            if status == 0 and get_int(a, flags & 1) != get_int(b, flags & 2):
+                status = c
+            continue
+        elif op == T_ICADD:
+            res = get_int(a, flags & 1)
+            if int(get_slot(b)) != 0:
+                res += iconsts[c]
+            assert res < 1 << 62
+            res = Int(res)
+        elif op == T_IADD:
+            res = Int(get_int(a, flags & 1) + get_int(b, flags & 2))
+            assert res < 1 << 62
+        elif op == T_ISEL:
+            cond = consts[a] if flags & 1 else int(get_slot(a))
+            res = Int(get_int(b, flags & 2) if cond != 0 else get_int(c, flags & 4))
+        elif op == T_IBIT:
+            res = (get_int(a, 0) >> b) & 1
         elif op == T_LD:
             v = get_row(c)
             if dst & BSLOT_DST:

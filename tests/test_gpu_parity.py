@@ -255,6 +255,38 @@ def test_device_api_with_torch_buffers(E):
         assert got[b] == I.compute_witness(I.load(art.cvm), rows[b])
 
 
+def test_output_selector_and_typed_check_agree(E, tmp_path):
+    """cvmgpu_witness_batch_select returns only the requested wire range (here: the public part and an inner slice),
+    identical to the same columns of the full export; the typed check (bit rows, integer constraints) reports the same
+    first violated constraint as the plain check of the exported rows for inputs that break constraints."""
+    art = circuit("sha256_64")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    _write_r1cs(art, tmp_path / "s.r1cs")
+    r = E.R1cs(str(tmp_path / "s.r1cs"))
+    rng = random.Random(21)
+    rows = [[rng.randrange(2) for _ in range(64)] for _ in range(70)]
+    rows[3] = [M.Q - 1] + [0] * 63      # not a bit, and too large for the 35-bit sums: their decomposition constraint fails
+    rows[40][0] = M.Q - 5
+    rows[41][63] = 5                    # not a bit either, but every constraint still holds (the inputs are unconstrained)
+    wt, st, bad = wc.calculate_checked(rows, r)
+    assert (bad[[3, 40]] != E.NO_BAD).all() and (np.delete(bad, [3, 40]) == E.NO_BAD).all()
+    assert (r.check(wt) == bad).all()
+    vals = E.le_to_ints(wt[[3, 40]])
+    for k, b in enumerate((3, 40)):
+        w = vals[k]
+        ev = lambda lc: sum(v * w[j] for j, v in lc.items()) % M.Q
+        first = next(ci for ci, (a, bb, c) in enumerate(art.constraints) if (ev(a) * ev(bb) - ev(c)) % M.Q)
+        assert bad[b] == first, b
+    B = len(rows)
+    inp = E.ints_to_le(rows, 64)
+    for wire0, n_sel in ((0, 1 + 256 + 64), (1000, 777)):
+        out = np.empty((B, n_sel, 32), dtype=np.uint8)
+        st2 = np.empty(B, dtype=np.uint32)
+        bad2 = np.empty(B, dtype=np.uint32)
+        wc.calculate_select_into(inp, wire0, n_sel, out, st2, r, bad2)
+        assert (out == wt[:, wire0:wire0 + n_sel]).all() and (st2 == st).all() and (bad2 == bad).all()
+
+
 def test_eddsa_batch(E, tmp_path):
     """Config 4 shape: EdDSAPoseidonVerifier over signatures from the integer signer, 1 in 8 forged: per-witness
     flags, witness parity with the oracle, and the R1CS check."""
@@ -379,7 +411,7 @@ def _run_full(E, art, inputs_dev, B, tmp_path):
     bad = torch.empty(B, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     wc.run_dev(inputs_dev, B, B, store, status, s)
-    r.check_dev(store, B, B, bad, s)
+    r.check_store_dev(wc, store, B, B, bad, s)
     torch.cuda.synchronize()
     return wc, r, store, status, bad
 
@@ -416,10 +448,12 @@ def test_poseidon_at_baseline_size(E, tmp_path):
     assert store.view(torch.int64).sum().item() == checksum
     # flip one byte of one wire of witnesses 5 and B-1: exactly those are reported
     view = store.view(torch.uint8)
+    row3 = int(wc.wire_rows()[3])
+    assert not row3 & E.ROW_BIT                # wire 3 of Poseidon(2) is a field row
     for b in (5, B - 1):
-        off = ((3 * 2) * B + b) * 16          # row 3, low half, witness b (layout in csrc/kernels.cuh)
+        off = ((row3 * 2) * B + b) * 16       # field row of wire 3, low half, witness b (layout in include/cvmgpu.h)
         view[off] ^= 1
-    r.check_dev(store, B, B, bad, s)
+    r.check_store_dev(wc, store, B, B, bad, s)
     torch.cuda.synchronize()
     hit = torch.nonzero(bad != -1).flatten().tolist()
     assert hit == [5, B - 1]
@@ -438,8 +472,8 @@ def test_sha256_at_baseline_size(E, tmp_path):
     gc.collect()
     torch.cuda.empty_cache()
     free, _total = torch.cuda.mem_get_info()
-    if free < 156e9:
-        pytest.skip("needs ~150 GB of free device memory (the 64 K x 68 529-wire value store)")
+    if free < 12e9:
+        pytest.skip("needs ~10 GB of free device memory (typed value store 5.6 GB + inputs)")
     g = torch.Generator(device="cuda")
     g.manual_seed(0xC1C00002)
     bits = torch.randint(0, 2, (B, 512), dtype=torch.uint8, device="cuda", generator=g)
@@ -460,6 +494,25 @@ def test_sha256_at_baseline_size(E, tmp_path):
         m = bytes(int("".join(str(int(x)) for x in msgs[k, 8 * j:8 * j + 8]), 2) for j in range(64))
         want = "".join(format(byte, "08b") for byte in hashlib.sha256(m).digest())
         assert "".join(str(int(x)) for x in digests[k]) == want, k
+    # typed store: 97.8 % of the wires are bit rows (one word per 32 witnesses); the exported rows are still full 32-byte
+    # canonical values, and the host-side check of those rows (plain layout, field arithmetic only) agrees with the typed one
+    info = wc.info
+    assert info.n_bool_wires > 0.97 * wc.n_wires and info.n_brows >= info.n_bool_wires
+    assert wc.store_bytes(B) < 8e9
+    assert (r.check(wt.cpu().numpy()) == E.NO_BAD).all()
+    ri = r.refresh_info()
+    assert ri.bound_int_constraints > 0.8 * r.n_constraints
+    # flip the bit of one bit-row wire for witnesses 7 and B-1: exactly those are reported
+    rows = wc.wire_rows()
+    wire = int(np.nonzero(rows & E.ROW_BIT)[0][5000])
+    brow = int(rows[wire]) & ~E.ROW_BIT
+    bits_base = info.n_frows * 32 * B
+    words = store[bits_base:].view(torch.int32)
+    for b in (7, B - 1):
+        words[(b >> 5) * info.n_brows + brow] ^= (1 << (b & 31)) if (b & 31) < 31 else -(1 << 31)
+    r.check_store_dev(wc, store, B, B, bad, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.nonzero(bad != -1).flatten().tolist() == [7, B - 1]
 
 
 def _extreme_values(rng):
