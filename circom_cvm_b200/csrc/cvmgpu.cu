@@ -135,30 +135,30 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
                 return tape::allocate_tape(tr, it->second, c, max_bslots);
             };
             auto cost_of = [&](const tape::Tape &t) {
-                const size_t per_warp = (size_t)(t.n_slots + (t.use_ring ? tape::LD_RING : 0)) * 1024u + (size_t)t.n_bslots * 4u;
-                const double warps = std::min<double>(std::floor(226.0 * 1024.0 / (double)(per_warp * 4)) * 4.0, 24.0);
+                // resident warps per SM at one warp per CTA (what small batches launch): 1 KiB of the SM's 228 KiB is reserved
+                // per CTA.  A 64 K batch -- 2 048 warps over 148 SMs, BASELINE configs 3 and 4 -- must fit in ONE wave: at 13
+                // resident warps per SM it takes two (measured: Sha256(512) 115 ms against 64 ms), hence the quantisation term.
+                const size_t per_warp = (size_t)(t.n_slots + (t.use_ring ? tape::LD_RING : 0)) * 1024u + (size_t)t.n_bslots * 4u + 1024u;
+                const double resident = std::min<double>(std::floor(228.0 * 1024.0 / (double)per_warp), 64.0);
+                const double waves = 2048.0 / (148.0 * std::max(1.0, resident));
+                const double quant = std::ceil(waves) / std::max(waves, 1.0);
                 const double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st - t.stats.n_ld_bool - t.stats.n_spill_st_bool);
-                return work / std::max(4.0, warps);
+                return work * quant / std::max(4.0, std::min(resident, 24.0));
             };
             double best = 0;
             for (uint32_t c : cand) {
-                tape::Tape t = build(c, 2048);
-                const uint32_t live_field = t.stats.max_live_field;
-                const double cost = cost_of(t);
-                if (best == 0 || cost < best) {
-                    best = cost;
-                    p->tape = std::move(t);
+                uint32_t live_field = 0, full_bslots = 0;
+                for (uint32_t nb : {2048u, 1024u, 512u, 256u}) {
+                    if (nb != 2048u && nb >= full_bslots) continue;   // the file already holds every live 0/1 value
+                    tape::Tape t = build(c, nb);
+                    if (nb == 2048u) { full_bslots = t.n_bslots; live_field = t.stats.max_live_field; }
+                    const double cost = cost_of(t);
+                    if (best == 0 || cost < best) {
+                        best = cost;
+                        p->tape = std::move(t);
+                    }
                 }
                 if (c >= live_field + 2) break;   // every field value already has a slot
-            }
-            for (uint32_t nb : {1024u, 512u, 256u}) {
-                if (nb >= p->tape.n_bslots) continue;
-                tape::Tape t = build(p->tape.n_slots, nb);
-                const double cost = cost_of(t);
-                if (cost < best) {
-                    best = cost;
-                    p->tape = std::move(t);
-                }
             }
         } else {
             // explicit slot count (experiments): CVMGPU_BSLOTS caps the bit file
@@ -334,11 +334,12 @@ static int upload_program(cvmgpu_program *p) {
     CUDA_TRY(cudaGetDevice(&dev));
     if (p->device == dev && p->d_tape.p) return CVMGPU_OK;
     if (p->device != dev) release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc, &p->d_iconsts});
-    size_t tb = std::max<size_t>(16, p->tape.ins.size() * sizeof(tape::TapeIns));
+    size_t tb = (p->tape.ins.size() + TAPE_PAD) * sizeof(tape::TapeIns);
     size_t cb = std::max<size_t>(32, p->consts_mont.size() * sizeof(fr::Fr));
     if (int rc = p->d_tape.ensure(tb)) return rc;
     if (int rc = p->d_consts.ensure(cb)) return rc;
     if (int rc = p->d_wire_loc.ensure(std::max<size_t>(4, p->tape.wire_loc.size() * 4))) return rc;
+    CUDA_TRY(cudaMemset(p->d_tape.p, 0, tb));   // the padding: T_NOP
     if (!p->tape.ins.empty())
         CUDA_TRY(cudaMemcpy(p->d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
     if (!p->consts_mont.empty())
@@ -733,7 +734,7 @@ static int launch_check(cvmgpu_r1cs *r, const BoundDev &bd, const void *d_store,
     rp.first_bad = (uint32_t *)d_first_bad;
     rp.bits = bits;
     rp.n_brows = bd.n_brows;
-    rp.bhdr = (const uint32_t *)bd.d_bhdr.p;
+    rp.bhdr = (const uint4 *)bd.d_bhdr.p;
     rp.bterms = (const uint2 *)bd.d_bterms.p;
     rp.cint = (const long long *)r->d_cint.p;
     dim3 grid((unsigned)gx, (unsigned)chunks);

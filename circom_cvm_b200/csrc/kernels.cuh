@@ -27,6 +27,7 @@ __device__ __forceinline__ uint4 *row_ptr(const uint4 *wbase, uint32_t row, uint
 
 using fr::Fr;
 
+#define TAPE_PAD 48   // no-op instructions after the last one on the device copy of a tape (fetch / prefetch without bound checks)
 #define CVM_NT 128   // threads (= witnesses) per CTA of the tape kernel for large batches (64 / 32 for small ones)
 
 __device__ __forceinline__ Fr unpack(const uint4 &lo, const uint4 &hi) {
@@ -197,20 +198,23 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
     uint32_t *const bw = reinterpret_cast<uint32_t *>(slots + p.bslot_off) + (tid >> 5) * p.n_bslots;
     uint32_t *const brow = p.bits + (warp_active ? (((uint64_t)blockIdx.x * NT + tid) >> 5) : 0ull) * p.n_brows;
 
+    // The tape is padded with TAPE_PAD no-ops on the device (cvmgpu.cu upload_program): the fetch of the next instruction
+    // and the prefetch of the lines ahead never need a bound check.
     const uint4 *tp = reinterpret_cast<const uint4 *>(p.tape);
     const uint32_t n_ins = p.n_ins;
     uint4 raw = __ldg(tp);
     for (uint32_t pc = 0; pc < n_ins; pc++) {
         const uint4 cur = raw;
-        raw = __ldg(tp + min(pc + 1, n_ins - 1));   // prefetch the next instruction (re-done after a DOT's records)
-        if ((pc & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + min(pc + 32, n_ins - 1)));   // tape lines ahead
+        raw = __ldg(tp + pc + 1);   // the next instruction (re-done after the records of a DOT / ISUM)
+        if ((pc & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + pc + 32));   // tape lines ahead
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
         Fr r;
         uint32_t rb = 0;        // result of an instruction that produces a truth value
         bool is_rb = false;
-        if (op >= tape::T_ADD && op <= tape::T_MUL) {
+        switch (op) {
+        case tape::T_ADD: case tape::T_SUB: case tape::T_MUL: {
             const Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
             const Fr b = tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid);
             if (op == tape::T_MUL) {
@@ -238,7 +242,9 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             } else {
                 r = fr::sub(a, b);
             }
-        } else if (op == tape::T_DOT) {
+            break;
+        }
+        case tape::T_DOT: {
             // sum_j c_j * x_j (+ addend): cur.y terms in the following ceil(n/2) records of (constant, slot) pairs
             const uint32_t n = cur.y;
             fr::Wide T;
@@ -253,15 +259,19 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             r = fr::wide_reduce(T, n);
             if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid));
             pc += (n + 1) >> 1;
-            raw = __ldg(tp + min(pc + 1, n_ins - 1));
-        } else if (op == tape::T_SEL) {
+            raw = __ldg(tp + pc + 1);
+            break;
+        }
+        case tape::T_SEL: {
             const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
             // only the selected operand is fetched; with F_CZERO the "else" value is the constant 0
             const bool isc = t ? (flags & 2u) : (flags & 4u);
             const uint32_t idx = t ? cur.z : cur.w;
             r = fr::zero();
             if (t || !(flags & tape::F_CZERO)) r = tape_operand<NT, BITS>(slots, bw, consts, idx, isc, tid);
-        } else if (op == tape::T_CADD) {
+            break;
+        }
+        case tape::T_CADD: {
             // a + (b != 0 ? constant c : 0)
             const Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
             const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.z, false, tid);
@@ -269,33 +279,54 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             const Fr sum = fr::add(a, c);
 #pragma unroll
             for (int i = 0; i < 8; i++) r.v[i] = t ? sum.v[i] : a.v[i];
-        } else if (op >= tape::T_ICADD && op <= tape::T_IFAIL_NE) {
-            // small-integer arithmetic: raw 64-bit values (sums of 0/1 values times small constants)
-            if (op == tape::T_IBIT) {
-                const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, false, tid);
-                rb = cur.z < 64u ? (uint32_t)(a >> cur.z) & 1u : 0u;
-                is_rb = true;
-            } else if (op == tape::T_IFAIL_NE) {
-                const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid);
-                const unsigned long long b = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
-                if (a != b && status == 0) status = cur.w;
-                continue;
-            } else {
-                unsigned long long v;
-                if (op == tape::T_ICADD) {
-                    v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid);
-                    if (tape_truth<NT, BITS>(slots, bw, consts, cur.z, false, tid)) v += __ldg(p.iconsts + cur.w);
-                } else if (op == tape::T_IADD) {
-                    v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid) +
-                        tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
-                } else {
-                    const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
-                    v = tape_int<NT, BITS>(slots, bw, p.iconsts, t ? cur.z : cur.w, t ? (flags & 2u) : (flags & 4u), tid);
-                }
-                slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
-                continue;
+            break;
+        }
+        case tape::T_ISUM: {
+            // small-integer arithmetic: addend + sum_j (bit_j << shift_j), four (bit slot, shift) terms per record
+            const uint32_t n = cur.y;
+            unsigned long long v = 0;
+            if (flags & tape::F_ADDEND) v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            for (uint32_t j = 0; j < n; j += 4) {
+                const uint4 rec = __ldg(tp + pc + 1 + (j >> 2));
+                v += (unsigned long long)((bw[rec.x & 0xffffu] >> lane) & 1u) << (rec.x >> 16);
+                if (j + 1 < n) v += (unsigned long long)((bw[rec.y & 0xffffu] >> lane) & 1u) << (rec.y >> 16);
+                if (j + 2 < n) v += (unsigned long long)((bw[rec.z & 0xffffu] >> lane) & 1u) << (rec.z >> 16);
+                if (j + 3 < n) v += (unsigned long long)((bw[rec.w & 0xffffu] >> lane) & 1u) << (rec.w >> 16);
             }
-        } else if (BITS && op == tape::T_LUT) {
+            slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
+            pc += (n + 3) >> 2;
+            raw = __ldg(tp + pc + 1);
+            continue;
+        }
+        case tape::T_ICADD: case tape::T_IADD: case tape::T_ISEL: {
+            // raw 64-bit values (sums of 0/1 values times small constants)
+            unsigned long long v;
+            if (op == tape::T_ICADD) {
+                v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid);
+                if (tape_truth<NT, BITS>(slots, bw, consts, cur.z, false, tid)) v += __ldg(p.iconsts + cur.w);
+            } else if (op == tape::T_IADD) {
+                v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid) +
+                    tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            } else {
+                const bool t = tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
+                v = tape_int<NT, BITS>(slots, bw, p.iconsts, t ? cur.z : cur.w, t ? (flags & 2u) : (flags & 4u), tid);
+            }
+            slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
+            continue;
+        }
+        case tape::T_IBIT: {
+            const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, false, tid);
+            rb = cur.z < 64u ? (uint32_t)(a >> cur.z) & 1u : 0u;
+            is_rb = true;
+            break;
+        }
+        case tape::T_IFAIL_NE: {
+            const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.y, flags & 1u, tid);
+            const unsigned long long b = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            if (a != b && status == 0) status = cur.w;
+            continue;
+        }
+        case tape::T_LUT: {
             // boolean function of up to three typed 0/1 values: this lane's bits of the three words index the table
             const uint32_t nin = (cur.z >> 8) & 0xffu;
             uint32_t idx = (bw[cur.y & 0xffffu] >> lane) & 1u;
@@ -303,14 +334,18 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             if (nin > 2) idx |= ((bw[cur.z >> 16] >> lane) & 1u) << 2;
             rb = (cur.z >> idx) & 1u;
             is_rb = true;
-        } else if (op == tape::T_BITC) {
+            break;
+        }
+        case tape::T_BITC: {
             // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);
             const uint32_t limb = cur.z >> 5;
             const uint32_t word = s32[(((cur.y * 2 + (limb >> 2)) * NT + tid) << 2) + (limb & 3u)];
             rb = (word >> (cur.z & 31u)) & 1u;
             is_rb = true;
-        } else if (op == tape::T_EQ || op == tape::T_NEQ || op == tape::T_EQZ || op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
+            break;
+        }
+        case tape::T_EQ: case tape::T_NEQ: case tape::T_EQZ: case tape::T_FAIL_IF: case tape::T_FAIL_NE: {
             bool e;
             if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = !tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
             else e = fr::equal(tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid),
@@ -321,13 +356,15 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             }
             rb = (op == tape::T_NEQ) ? !e : e;
             is_rb = true;
-        } else if (op == tape::T_LD) {
+            break;
+        }
+        case tape::T_LD: {
             if (BITS && (dst & tape::BSLOT_DST)) {     // a bit row: the warp's word (written earlier by these same lanes)
                 bw[dst & 0x7fffu] = brow[cur.w & ~tape::ROW_BIT];
                 continue;
             }
             // reload stream (tape.hpp schedule_reloads): ring entry cur.z holds this value if F_RING; cur.y is the row
-            // to request now for the reload LD_RING reloads ahead.  Every field reload commits exactly one cp.async group.
+            // to request now for the reload LD_RING reloads ahead.  Every streamed reload commits one cp.async group.
             uint4 *ring = slots + p.ring_off + cur.z * 2 * NT;
             if (flags & tape::F_RING) asm volatile("cp.async.wait_group %0;" ::"n"(tape::LD_RING - 1) : "memory");
             uint4 lo, hi;
@@ -349,7 +386,8 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             continue;
-        } else if (op == tape::T_ST || op == tape::T_STC) {
+        }
+        case tape::T_ST: case tape::T_STC: {
             if (cur.w & tape::ROW_BIT) {
                 uint32_t word;
                 if (op == tape::T_STC) word = __ldg(consts + 2 * (uint64_t)cur.y).x ? 0xffffffffu : 0u;
@@ -366,7 +404,8 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 d[bstride] = hi;
             }
             continue;
-        } else {
+        }
+        default: {
             status = tape_slow_op<NT, BITS>(cur, slots, bw, consts, p.inputs, p.n_inputs, w, status, tid, rb);
             if (!BITS || !(dst & tape::BSLOT_DST)) {
                 if ((flags & tape::F_STORE) && active) {
@@ -377,6 +416,8 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
                 continue;
             }
             is_rb = true;
+            break;
+        }
         }
         if (BITS && (dst & tape::BSLOT_DST)) {
             const uint32_t word = __ballot_sync(0xffffffffu, is_rb ? rb != 0u : r.v[0] != 0u);
@@ -496,12 +537,13 @@ struct R1csParams {
     uint64_t bstride;
     uint64_t B;
     uint32_t *first_bad;        // B words, pre-set to 0xffffffff
-    // typed stores (a program's layout, tape.hpp): terms on bit rows live in their own CSR.  bhdr[j] = begin of LC j's
-    // bit terms (3*n_cons+1 entries); bit 31 of bhdr[3c] marks a constraint made only of bit terms with coefficients that
-    // fit 64-bit integers (cint): it is evaluated in plain integers.  bterms = (bit row, coefficient index).
+    // typed stores (a program's layout, tape.hpp): terms on bit rows live in their own CSR.  bhdr[c] = begin of the bit
+    // terms of A | mode << 30, of B, of C, of the next constraint's A (n_cons + 1 entries); mode 1 / 2 marks a constraint
+    // made only of bit terms with integer coefficients (cint): it is evaluated in 64- / 32-bit integers (r1cs.hpp Bound).
+    // bterms = (bit row, coefficient index).
     const uint32_t *bits;
     uint32_t n_brows;
-    const uint32_t *bhdr;
+    const uint4 *bhdr;
     const uint2 *bterms;
     const long long *cint;
 };
@@ -647,9 +689,10 @@ struct BitStream {
     const uint2 *bterms;
     const uint32_t *brow;
     const long long *cint;
-    uint4 *stage;        // this warp's 32 entries: (word, coefficient index, integer coefficient lo, hi)
-    uint32_t base, t_end, lane;   // lane: the thread's own lane (which entry of a batch it fetches)
-    uint32_t bitlane;             // the lane whose bit of a word this thread reads (a padding thread copies the last witness)
+    uint32_t stage;      // shared-space address of this warp's 32 entries: (word, coefficient lo, hi, coefficient index)
+    uint32_t base, t_end;
+    uint32_t lane;       // the thread's own lane (which entry of a batch it fetches)
+    uint32_t bitlane;    // the lane whose bit of a word this thread reads (a padding thread copies the last witness)
     uint4 nxt;
     __device__ __forceinline__ void load(uint32_t b) {
         const uint32_t t = b + lane;
@@ -657,25 +700,35 @@ struct BitStream {
         if (t < t_end) {
             const uint2 term = __ldg(bterms + t);
             const long long c = __ldg(cint + term.y);
-            nxt = make_uint4(__ldg(brow + term.x), term.y, (uint32_t)c, (uint32_t)((unsigned long long)c >> 32));
+            nxt = make_uint4(__ldg(brow + term.x), (uint32_t)c, (uint32_t)((unsigned long long)c >> 32), term.y);
         }
+    }
+    __device__ __forceinline__ void put() {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 16u), "r"(nxt.x), "r"(nxt.y), "r"(nxt.z), "r"(nxt.w)
+                     : "memory");
     }
     __device__ __forceinline__ void start(uint32_t t0) {
         base = t0;
         load(t0);
-        stage[lane] = nxt;
+        put();
         __syncwarp();
         load(t0 + 32);
     }
-    __device__ __forceinline__ uint4 at(uint32_t t) {
-        while (t >= base + 32) {     // uniform: every lane of the warp walks the same terms
+    // make the batch that holds term t current (uniform: every lane of the warp walks the same terms)
+    __device__ __forceinline__ void seek(uint32_t t) {
+        while (t >= base + 32) {
             __syncwarp();
-            stage[lane] = nxt;
+            put();
             __syncwarp();
             base += 32;
             load(base + 32);
         }
-        return stage[t - base];
+    }
+    __device__ __forceinline__ uint4 at(uint32_t t) {
+        seek(t);
+        uint4 s;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s.x), "=r"(s.y), "=r"(s.z), "=r"(s.w) : "r"(stage + (t - base) * 16u));
+        return s;
     }
 };
 
@@ -684,7 +737,7 @@ __device__ __forceinline__ Fr lc_bits(const R1csParams &p, BitStream &bs, uint32
     for (uint32_t t = b; t < e; t++) {
         const uint4 s = bs.at(t);
         const bool bit = (s.x >> bs.bitlane) & 1u;
-        const uint4 lo = __ldg(p.coefs + 2 * (uint64_t)s.y), hi = __ldg(p.coefs + 2 * (uint64_t)s.y + 1);
+        const uint4 lo = __ldg(p.coefs + 2 * (uint64_t)s.w), hi = __ldg(p.coefs + 2 * (uint64_t)s.w + 1);
         Fr c;
         c.v[0] = bit ? lo.x : 0u; c.v[1] = bit ? lo.y : 0u; c.v[2] = bit ? lo.z : 0u; c.v[3] = bit ? lo.w : 0u;
         c.v[4] = bit ? hi.x : 0u; c.v[5] = bit ? hi.y : 0u; c.v[6] = bit ? hi.z : 0u; c.v[7] = bit ? hi.w : 0u;
@@ -692,15 +745,31 @@ __device__ __forceinline__ Fr lc_bits(const R1csParams &p, BitStream &bs, uint32
     }
     return acc;
 }
-// the same in plain integers (the host guarantees that no partial sum leaves 63 bits)
+// the same in plain integers: 64-bit (the host guarantees that no partial sum leaves 62 bits), or 32-bit when every
+// partial sum stays below 2^31 -- one multiply-add per term
+template <bool I32>
 __device__ __forceinline__ long long lc_int(BitStream &bs, uint32_t b, uint32_t e) {
     long long acc = 0;
-    for (uint32_t t = b; t < e; t++) {
-        const uint4 s = bs.at(t);
-        const long long c = (long long)((unsigned long long)s.z | ((unsigned long long)s.w << 32));
-        acc += ((s.x >> bs.bitlane) & 1u) ? c : 0ll;
+    int acc32 = 0;
+    uint32_t t = b;
+    while (t < e) {
+        bs.seek(t);
+        const uint32_t stop = min(e, bs.base + 32u);
+        uint32_t sa = bs.stage + (t - bs.base) * 16u;
+        for (; t < stop; t++, sa += 16u) {
+            if (I32) {
+                uint32_t w, c;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(c) : "r"(sa));
+                acc32 += (int)((w >> bs.bitlane) & 1u) * (int)c;
+            } else {
+                uint32_t w, c0, c1, ci;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w), "=r"(c0), "=r"(c1), "=r"(ci) : "r"(sa));
+                const long long c = (long long)((unsigned long long)c0 | ((unsigned long long)c1 << 32));
+                acc += ((w >> bs.bitlane) & 1u) ? c : 0ll;
+            }
+        }
     }
-    return acc;
+    return I32 ? (long long)acc32 : acc;
 }
 
 template <int MINB, bool TYPED>
@@ -731,34 +800,38 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         bs.bterms = p.bterms;
         bs.brow = brow;
         bs.cint = p.cint;
-        bs.stage = bstage + (threadIdx.x & ~31u);
+        bs.stage = (uint32_t)__cvta_generic_to_shared(bstage + (threadIdx.x & ~31u));
         bs.lane = threadIdx.x & 31u;
         bs.bitlane = lane;
-        bs.t_end = __ldg(p.bhdr + 3 * c1) & 0x7fffffffu;
-        bs.start(__ldg(p.bhdr + 3 * c0) & 0x7fffffffu);
+        bs.t_end = __ldg(&p.bhdr[c1].x) & 0x3fffffffu;
+        bs.start(__ldg(&p.bhdr[c0].x) & 0x3fffffffu);
     }
     uint32_t bad = 0xffffffffu;
     uint4 hA = __ldg(p.hdr + 3 * c0);
     for (uint32_t c = c0; c < c1; c++) {
-        // headers of A, B, C and of the next constraint's A (its begin is the end of C)
-        const uint4 hB = __ldg(p.hdr + 3 * c + 1), hC = __ldg(p.hdr + 3 * c + 2), hN = __ldg(p.hdr + 3 * c + 3);
         uint32_t bA = 0, bB = 0, bC = 0, bN = 0;
         if (TYPED) {
-            bA = __ldg(p.bhdr + 3 * c);
-            bB = __ldg(p.bhdr + 3 * c + 1) & 0x7fffffffu;
-            bC = __ldg(p.bhdr + 3 * c + 2) & 0x7fffffffu;
-            bN = __ldg(p.bhdr + 3 * c + 3) & 0x7fffffffu;
-            if (bA >> 31) {
+            const uint4 bh = __ldg(p.bhdr + c);
+            bA = bh.x & 0x3fffffffu; bB = bh.y; bC = bh.z; bN = bh.w;
+            const uint32_t mode = bh.x >> 30;
+            if (mode) {
                 // every term is a 0/1 wire with a small integer coefficient: |A*B - C| is far below q, so the constraint
-                // holds mod q iff it holds in the integers
-                bA &= 0x7fffffffu;
-                const long long ia = lc_int(bs, bA, bB), ib = lc_int(bs, bB, bC), ic = lc_int(bs, bC, bN);
-                const long long lo = ia * ib, hi = __mul64hi(ia, ib);
-                if (bad == 0xffffffffu && (lo != ic || hi != (ic >> 63))) bad = c;
-                hA = hN;
+                // holds mod q iff it holds in the integers.  (No field-row terms: the operand stream is not touched.)
+                bool ok;
+                if (mode == 2) {
+                    const long long ia = lc_int<true>(bs, bA, bB), ib = lc_int<true>(bs, bB, bC), ic = lc_int<true>(bs, bC, bN);
+                    ok = ia * ib == ic;
+                } else {
+                    const long long ia = lc_int<false>(bs, bA, bB), ib = lc_int<false>(bs, bB, bC), ic = lc_int<false>(bs, bC, bN);
+                    ok = ia * ib == ic && __mul64hi(ia, ib) == (ic >> 63);
+                }
+                if (bad == 0xffffffffu && !ok) bad = c;
                 continue;
             }
+            hA = __ldg(p.hdr + 3 * c);   // (the chain hA = hN below is broken by integer constraints)
         }
+        // headers of A, B, C and of the next constraint's A (its begin is the end of C)
+        const uint4 hB = __ldg(p.hdr + 3 * c + 1), hC = __ldg(p.hdr + 3 * c + 2), hN = __ldg(p.hdr + 3 * c + 3);
         const bool hasA = hA.x != hB.x || bA != bB, hasC = hC.x != hN.x || bC != bN;
         const bool hasB = hB.x != hC.x || bB != bC || hB.y == R1CS_SAME_AS_A;
         Fr prod = fr::zero();

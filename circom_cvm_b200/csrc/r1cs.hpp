@@ -56,11 +56,14 @@ struct File {
 // The CSR bound to a typed value store (tape.hpp: a wire is a field row or a bit row).  Field-row terms keep the
 // layout above (hdr = {begin, end of +-2^k, of small +, of small -} per LC, rows instead of wires); bit-row terms go to a
 // second CSR (bhdr / bterms).  A constraint whose terms are ALL bit rows with 64-bit integer coefficients (partial sums
-// below 2^62) is marked in bit 31 of bhdr[3c] and evaluated in plain integers: (A*B - C) = 0 mod q iff = 0 in Z then.
+// below 2^62) is evaluated in plain integers: (A*B - C) = 0 mod q iff = 0 in Z then (mode field of bhdr).
 struct Bound {
     std::vector<uint32_t> hdr;      // 4 * (3 * n_constraints + 1)
     std::vector<Term> fterms;
-    std::vector<uint32_t> bhdr;     // 3 * n_constraints + 1
+    // 4 words per constraint (+ one closing entry): begin of the bit terms of A | mode << 30, of B, of C, of the next
+    // constraint's A.  mode 0: evaluated in the field; 1: in 64-bit integers; 2: in 32-bit integers (every partial sum
+    // below 2^31, the product in 64 bits)
+    std::vector<uint32_t> bhdr;
     std::vector<Term> bterms;       // (bit row, coefficient index)
     uint64_t n_int_constraints = 0, n_field_constraints = 0;
     // 32x32->64 multiply-accumulates the check executes per witness on this layout (upper bound: products with a 0 / +-1
@@ -76,7 +79,7 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
     Bound b;
     const size_t n_lc = f.ptr.size() - 1;
     b.hdr.assign(4 * (n_lc + 1), 0);
-    b.bhdr.assign(n_lc + 1, 0);
+    b.bhdr.assign(4 * ((size_t)f.n_constraints + 1), 0);
     b.fterms.reserve(f.terms.size());
     auto loc_of = [&](uint32_t wire) -> uint32_t { return wire_loc ? wire_loc[wire] : wire; };
     for (uint32_t c = 0; c < f.n_constraints; c++) {
@@ -90,6 +93,7 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
             if (k == 1 && f.split[3 * j] == SAME_AS_A) same_b = true;
         }
         bool intok = wire_loc != nullptr;
+        uint64_t max_sumabs = 0;
         for (int k = 0; k < 3 && intok; k++) {
             const int src = (k == 1 && same_b) ? 0 : k;
             uint64_t sumabs = 0;
@@ -101,14 +105,18 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
                 sumabs += (uint64_t)(v < 0 ? -v : v);
                 if (sumabs >> 62) intok = false;
             }
+            max_sumabs = std::max(max_sumabs, sumabs);
         }
+        const uint32_t mode = !intok ? 0u : (max_sumabs >> 31) ? 1u : 2u;
         if (intok) b.n_int_constraints++; else b.n_field_constraints++;
         bool has[3] = {false, false, false};
         for (int k = 0; k < 3; k++) {
             const size_t j = 3 * (size_t)c + k;
             const uint32_t fb = (uint32_t)b.fterms.size();
             b.hdr[4 * j] = fb;
-            b.bhdr[j] = (uint32_t)b.bterms.size() | ((k == 0 && intok) ? 0x80000000u : 0u);
+            if (b.bterms.size() >> 30) throw std::runtime_error("more than 2^30 terms on bit rows");
+            b.bhdr[4 * (size_t)c + k] = (uint32_t)b.bterms.size() | (k == 0 ? mode << 30 : 0u);
+            if (c > 0 && k == 0) b.bhdr[4 * (size_t)c - 1] = (uint32_t)b.bterms.size();
             if (k == 1 && same_b && !intok) {
                 b.hdr[4 * j + 1] = SAME_AS_A;
                 b.hdr[4 * j + 2] = fb;
@@ -144,7 +152,8 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
         if (!intok && has[0] && has[1]) b.macs += 136;
     }
     b.hdr[4 * n_lc] = (uint32_t)b.fterms.size();
-    b.bhdr[n_lc] = (uint32_t)b.bterms.size();
+    if (f.n_constraints) b.bhdr[4 * (size_t)f.n_constraints - 1] = (uint32_t)b.bterms.size();
+    b.bhdr[4 * (size_t)f.n_constraints] = (uint32_t)b.bterms.size();
     return b;
 }
 

@@ -44,6 +44,7 @@ struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
+    uint64_t n_isum_terms = 0;     // conditional adds of bits fused into T_ISUM instructions
     uint64_t n_int = 0;            // small-integer operations (type_ints): sums of 0/1 values kept as raw 64-bit integers
     uint64_t n_ld_bool = 0, n_spill_st_bool = 0;   // of n_ld / n_spill_st: the value is typed 0/1 (what compact bit rows would shrink)
     uint32_t n_spill_rows = 0;
@@ -482,6 +483,95 @@ inline void type_ints(XProg &xp, const Tracer &tr) {
     xp.isint.swap(oi);
 }
 
+// ---- integer sums ------------------------------------------------------------------------------------------
+// lin = sum_k bit_k * 2^k arrives as a chain of T_ICADD, each result used only by the next link.  One T_ISUM evaluates
+// up to ISUM_MAX links: the accumulator stays in a register instead of going through its slot once per bit, and the
+// instruction fetch / dispatch of the interpreter is paid once.  Links whose constant is not a power of two, or whose
+// condition is not a value typed 0/1, stay T_ICADD.
+static const uint32_t ISUM_MAX = 32;
+
+inline void fuse_isums(XProg &xp, const Tracer &tr) {
+    std::vector<XOp> &ops = xp.ops;
+    const size_t N = ops.size();
+    std::vector<uint32_t> uses(N, 0);
+    for (uint32_t r : xp.witness_ref)
+        if (!(r & CONST_FLAG)) uses[r] += 2;
+    for (size_t i = 0; i < N; i++) {
+        const XOp &o = ops[i];
+        auto use = [&](uint32_t r) { if (r != NO_REF && !(r & CONST_FLAG)) uses[r]++; };
+        if (o.op == T_DOT)
+            for (uint32_t k = 0; k < o.tn; k++) use(xp.terms[o.t0 + k].second);
+        use(o.a); use(o.b); use(o.c);
+    }
+    auto shift_of = [&](uint32_t cref, uint32_t &sh) -> bool {   // constant = 2^sh, sh < 62
+        const fr::Fr &c = tr.consts[cref & ~CONST_FLAG];
+        for (int i = 2; i < 8; i++)
+            if (c.v[i]) return false;
+        const uint64_t v = ((uint64_t)c.v[1] << 32) | c.v[0];
+        if (v == 0 || (v & (v - 1)) || v >= (1ull << 62)) return false;
+        sh = 0;
+        while (!((v >> sh) & 1)) sh++;
+        return true;
+    };
+    auto fusable = [&](size_t i) -> bool {
+        const XOp &o = ops[i];
+        uint32_t sh;
+        return o.op == T_ICADD && !(o.b & CONST_FLAG) && xp.isbool[o.b] && (o.c & CONST_FLAG) && shift_of(o.c, sh);
+    };
+    std::vector<uint8_t> absorbed(N, 0);
+    // walk chains from their last link backwards
+    for (size_t i = N; i-- > 0;) {
+        if (absorbed[i] || !fusable(i)) continue;
+        std::vector<uint32_t> chain;   // links, last first
+        uint32_t cur = (uint32_t)i;
+        while (chain.size() < ISUM_MAX) {
+            chain.push_back(cur);
+            const uint32_t prev = ops[cur].a;
+            if (prev == NO_REF || (prev & CONST_FLAG) || absorbed[prev] || uses[prev] != 1 || !fusable(prev)) break;
+            cur = prev;
+        }
+        if (chain.size() < 2) continue;
+        XOp x{T_ISUM, NO_REF, NO_REF, ops[chain.back()].a, 0};
+        x.t0 = (uint32_t)xp.terms.size();
+        x.tn = (uint32_t)chain.size();
+        for (size_t k = chain.size(); k-- > 0;) {
+            xp.terms.emplace_back(ops[chain[k]].c, ops[chain[k]].b);
+            if (k) absorbed[chain[k]] = 1;
+        }
+        ops[i] = x;
+    }
+    // compact
+    std::vector<uint32_t> remap(N, NO_REF);
+    auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
+    std::vector<XOp> out;
+    std::vector<uint8_t> ob, oi;
+    out.reserve(N);
+    for (size_t i = 0; i < N; i++) {
+        if (absorbed[i]) continue;
+        XOp o = ops[i];
+        if (o.op == T_DOT || o.op == T_ISUM)
+            for (uint32_t k = 0; k < o.tn; k++) xp.terms[o.t0 + k].second = mapref(xp.terms[o.t0 + k].second);
+        o.a = mapref(o.a);
+        o.b = mapref(o.b);
+        o.c = mapref(o.c);
+        remap[i] = (uint32_t)out.size();
+        out.push_back(o);
+        ob.push_back(xp.isbool[i]);
+        oi.push_back(xp.isint[i]);
+    }
+    for (uint32_t &r : xp.witness_ref) r = mapref(r);
+    ops.swap(out);
+    xp.isbool.swap(ob);
+    xp.isint.swap(oi);
+}
+
+// records that follow an instruction on the tape (term lists)
+inline uint32_t extra_records(const TapeIns &in) {
+    if (in.op == T_DOT) return (in.a + 1) / 2;
+    if (in.op == T_ISUM) return (in.a + 3) / 4;
+    return 0;
+}
+
 // ---- reload stream ---------------------------------------------------------------------------------------
 // The FIELD rows a tape reloads (T_LD into a field slot) and their order are fixed, so the kernel streams them: the
 // n-th reload's row is requested (cp.async into a per-witness ring in shared memory) when reload n - LD_RING executes,
@@ -495,9 +585,9 @@ inline void schedule_reloads(Tape &t) {
     std::vector<uint32_t> last_store(t.n_frows, NO_ROW);
     for (size_t pc = 0; pc < t.ins.size(); pc++) {
         TapeIns &in = t.ins[pc];
-        if (in.op == T_DOT) {
+        if (in.op == T_DOT || in.op == T_ISUM) {
             if ((in.flags & F_STORE) && !(in.c & ROW_BIT)) last_store[in.c] = (uint32_t)pc;
-            pc += (in.a + 1) / 2;
+            pc += extra_records(in);
             continue;
         }
         if (in.op == T_LD) {
@@ -531,7 +621,7 @@ inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
         auto use = [&](uint32_t r) {
             if (r != NO_REF && !(r & CONST_FLAG)) last[r] = (uint32_t)i;
         };
-        if (o.op == T_DOT)
+        if (o.op == T_DOT || o.op == T_ISUM)
             for (uint32_t k = 0; k < o.tn; k++) use(xp.terms[o.t0 + k].second);
         use(o.a);
         use(o.b);
@@ -574,8 +664,10 @@ inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
 // fusions and typing that do not depend on the slot files (max_terms: longest fused dot product)
 inline XProg prepare_program(const Tracer &tr, uint32_t max_terms, bool fuse = true) {
     XProg xp = fuse_dots(tr, max_terms, fuse);
-    if (fuse) type_ints(xp, tr);
-    else xp.isint.assign(xp.ops.size(), 0);
+    if (fuse) {
+        type_ints(xp, tr);
+        fuse_isums(xp, tr);
+    } else xp.isint.assign(xp.ops.size(), 0);
     return xp;
 }
 
@@ -616,13 +708,13 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     out.stats.max_live_bool = ml[1];
     // the bit file: enough for every live 0/1 value when that fits (no bit spills at all), else the cap
     uint32_t n_bslots = ml[1] == 0 ? 0 : std::min<uint32_t>(max_bslots, ((ml[1] + 3 + 31) / 32) * 32);
-    if (ml[1] && n_bslots < 8) n_bslots = 8;
+    if (ml[1] && n_bslots < 64) n_bslots = 64;   // a T_ISUM pins up to ISUM_MAX bit slots at once
     out.n_bslots = n_bslots;
     const uint32_t file_slots[2] = {n_slots, n_bslots};
 
     auto operands = [&](const XOp &o, std::vector<uint32_t> &rs) {
         rs.clear();
-        if (o.op == T_DOT) {
+        if (o.op == T_DOT || o.op == T_ISUM) {
             for (uint32_t k = 0; k < o.tn; k++) rs.push_back(xp.terms[o.t0 + k].second);
             rs.push_back(o.c);
         } else {
@@ -783,7 +875,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
             if (val_slot[r] >= 0 && next_use(r, pos) == 0xffffffffu) release_value(r);
         }
         uint8_t flags = 0;
-        if (o.op != T_DOT)
+        if (o.op != T_DOT && o.op != T_ISUM)
             for (size_t k = 0; k < 3; k++)
                 if (isc[k]) flags |= (uint8_t)(1u << k);
         if (o.op == T_ICADD || o.op == T_IADD || o.op == T_ISEL || o.op == T_IFAIL_NE) {
@@ -820,7 +912,43 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
         live_now++;
         out.stats.max_live = std::max(out.stats.max_live, live_now);
         uint32_t w0 = wire_head[i];
-        if (o.op == T_DOT) {
+        if (o.op == T_ISUM) {
+            // header: a = number of terms, b = addend (integer slot, 0/1 slot, or integer constant with bit1); then ceil(n/4)
+            // records of four terms: bit slot | shift << 16
+            const bool has_add = o.c != NO_REF;
+            uint32_t addend = 0;
+            if (has_add) {
+                flags |= F_ADDEND;
+                addend = enc[o.tn];
+                if (isc[o.tn]) {
+                    flags |= 2;
+                    const fr::Fr &cv = tr.consts[enc[o.tn]];
+                    const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
+                    auto it = iconst_index.find(v);
+                    if (it == iconst_index.end()) {
+                        it = iconst_index.emplace(v, (uint32_t)out.iconsts.size()).first;
+                        out.iconsts.push_back(v);
+                    }
+                    addend = it->second;
+                }
+            }
+            out.ins.push_back(TapeIns{T_ISUM, flags, dcode, o.tn, addend, 0});
+            for (uint32_t k = 0; k < o.tn; k += 4) {
+                uint32_t rec[4] = {0, 0, 0, 0};
+                for (uint32_t j = 0; j < 4 && k + j < o.tn; j++) {
+                    const fr::Fr &cv = tr.consts[xp.terms[o.t0 + k + j].first & ~CONST_FLAG];
+                    const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
+                    uint32_t sh = 0;
+                    while (!((v >> sh) & 1)) sh++;
+                    rec[j] = (enc[k + j] & 0xffffu) | (sh << 16);
+                }
+                TapeIns raw;
+                memcpy(&raw, rec, sizeof(rec));
+                out.ins.push_back(raw);
+            }
+            out.stats.n_int++;
+            out.stats.n_isum_terms += o.tn;
+        } else if (o.op == T_DOT) {
             // header: a = number of terms, b = addend (slot or constant index), c = wire row with F_STORE;
             // then ceil(n/2) records of (constant index, slot) x 2
             const bool has_add = o.c != NO_REF;
@@ -896,13 +1024,19 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     if (out.stats.n_sel + out.stats.n_other > 2 * out.stats.n_mul) {
         for (size_t pc = 0; pc < out.ins.size(); pc++) {
             TapeIns &in = out.ins[pc];
-            if (in.op == T_DOT) { pc += (in.a + 1) / 2; continue; }
+            if (in.op == T_DOT || in.op == T_ISUM) { pc += extra_records(in); continue; }
             if (in.op == T_MUL) in.flags |= F_TRIVIAL;
         }
     }
     // the reload ring costs 128 B of shared memory per witness: only worth it when the tape reloads field rows often
     out.use_ring = (uint64_t)(out.stats.n_ld - out.stats.n_ld_bool) * 50 >= out.ins.size();
     if (out.use_ring) schedule_reloads(out);
+    else
+        for (size_t pc = 0; pc < out.ins.size(); pc++) {
+            TapeIns &in = out.ins[pc];
+            if (in.op == T_DOT || in.op == T_ISUM) { pc += extra_records(in); continue; }
+            if (in.op == T_LD) in.a = NO_ROW;   // nothing to request: there is no ring
+        }
     out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +
                      72 * out.stats.n_dot + 1800 * (out.stats.n_inv + out.stats.n_div);
     return out;

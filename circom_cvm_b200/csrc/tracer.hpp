@@ -48,6 +48,7 @@ enum TOp : uint8_t {
     T_ISEL,      // a != 0 ? b : c
     T_IBIT,      // bit `aux` of the integer a (a value typed 0/1)
     T_IFAIL_NE,  // status if the integers a and b differ
+    T_ISUM,      // addend + sum_j (bit_j << shift_j): a chain of T_ICADD with power-of-two constants (tape.hpp fuse_isums)
     T_COUNT
 };
 

@@ -8,7 +8,7 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE) = range(40)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM) = range(41)
 F_ADDEND = 32        # T_DOT: field b is an addend
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
@@ -105,6 +105,17 @@ def run_tape(tape, consts_mont, layout, inputs):
                 acc += operand(b, 2)
             pc += (a + 1) // 2
             res = acc % M.Q
+        elif op == T_ISUM:
+            # addend + sum_j (bit_j << shift_j): a terms follow, four (bit slot | shift << 16) per 16-byte record
+            acc = get_int(b, flags & 2) if flags & F_ADDEND else 0
+            for j in range(a):
+                t = int(words[pc + j // 4][j % 4])
+                v = bslots[t & 0xFFFF]
+                assert v in (0, 1), "T_ISUM term is not a 0/1 value"
+                acc += v << (t >> 16)
+            pc += (a + 3) // 4
+            assert acc < 1 << 62 and not dst & BSLOT_DST
+            res = Int(acc)
         elif op == T_INPUT:
             res = inputs[a] % M.Q
         elif op == T_CADD:
