@@ -298,6 +298,60 @@ __global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
             raw = __ldg(tp + pc + 1);
             continue;
         }
+        case tape::T_LUTG: case tape::T_IBITG: {
+            // Warp-cooperative groups (tape.hpp group_bit_ops): cur.y independent operations on values typed 0/1, lane m doing
+            // member m for all 32 witnesses of the warp at once on their packed words.  Record m = (operand slots, result
+            // slot, truth table, bit row or NO_ROW).  Every lane reads its operands before any lane writes a result.
+            const uint32_t n = cur.y;
+            uint32_t word = 0, dslot = 0, row = tape::NO_ROW;
+            if (op == tape::T_LUTG) {
+                if (lane < n) {
+                    const uint4 rec = __ldg(tp + pc + 1 + lane);
+                    const uint32_t nin = (rec.z >> 8) & 0xffu;
+                    const uint32_t x0 = bw[rec.x & 0xffffu];
+                    const uint32_t x1 = nin > 1 ? bw[rec.x >> 16] : 0u;
+                    const uint32_t x2 = nin > 2 ? bw[rec.y & 0xffffu] : 0u;
+                    // multiplexer tree over the truth table, bitwise for the 32 witnesses: m_k = all ones if entry k is set
+                    const uint32_t t = rec.z;
+                    const uint32_t m0 = 0u - (t & 1u), m1 = 0u - ((t >> 1) & 1u), m2 = 0u - ((t >> 2) & 1u), m3 = 0u - ((t >> 3) & 1u),
+                                   m4 = 0u - ((t >> 4) & 1u), m5 = 0u - ((t >> 5) & 1u), m6 = 0u - ((t >> 6) & 1u), m7 = 0u - ((t >> 7) & 1u);
+                    const uint32_t a0 = (x0 & m1) | (~x0 & m0), a1 = (x0 & m3) | (~x0 & m2), a2 = (x0 & m5) | (~x0 & m4),
+                                   a3 = (x0 & m7) | (~x0 & m6);
+                    const uint32_t b0 = (x1 & a1) | (~x1 & a0), b1 = (x1 & a3) | (~x1 & a2);
+                    word = (x2 & b1) | (~x2 & b0);
+                    dslot = rec.y >> 16;
+                    row = rec.w;
+                }
+            } else {
+                // bits cur.w .. cur.w + n - 1 of the integer in slot cur.z: one vote per bit, lane m keeps word m
+                const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, false, tid);
+                for (uint32_t j = 0; j < n; j++) {
+                    const uint32_t k = cur.w + j;
+                    const uint32_t b = __ballot_sync(0xffffffffu, k < 64u ? (uint32_t)(a >> k) & 1u : 0u);
+                    if (lane == j) word = b;
+                }
+                if (lane < n) {
+                    const uint4 rec = __ldg(tp + pc + 1 + lane);
+                    dslot = rec.x & 0xffffu;
+                    row = rec.w;
+                }
+            }
+            __syncwarp();
+            if (lane < n) {
+                bw[dslot] = word;
+                if (row != tape::NO_ROW && warp_active) brow[row & ~tape::ROW_BIT] = word;
+            }
+            __syncwarp();
+            pc += n;
+            raw = __ldg(tp + pc + 1);
+            continue;
+        }
+        case tape::T_FILL: {
+            // constant bit rows [cur.w, cur.w + cur.z) = the word cur.y
+            if (warp_active)
+                for (uint32_t k = lane; k < cur.z; k += 32u) brow[(cur.w & ~tape::ROW_BIT) + k] = cur.y;
+            continue;
+        }
         case tape::T_ICADD: case tape::T_IADD: case tape::T_ISEL: {
             // raw 64-bit values (sums of 0/1 values times small constants)
             unsigned long long v;

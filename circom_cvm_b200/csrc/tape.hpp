@@ -44,6 +44,7 @@ struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
+    uint64_t n_groups = 0;         // warp-cooperative group instructions (T_LUTG / T_IBITG)
     uint64_t n_isum_terms = 0;     // conditional adds of bits fused into T_ISUM instructions
     uint64_t n_int = 0;            // small-integer operations (type_ints): sums of 0/1 values kept as raw 64-bit integers
     uint64_t n_ld_bool = 0, n_spill_st_bool = 0;   // of n_ld / n_spill_st: the value is typed 0/1 (what compact bit rows would shrink)
@@ -68,6 +69,7 @@ struct Tape {
     std::vector<uint64_t> iconsts;    // constants of the integer operations
     std::vector<uint32_t> wire_loc;   // per witness wire: field row, or ROW_BIT | bit row
     bool use_ring = false;            // field reloads are streamed through the cp.async ring (schedule_reloads)
+    uint32_t const_rows[2][2] = {{0, 0}, {0, 0}};   // bit rows of the wires bound to the constant v: [v] = {first, count}
     uint32_t one_brow = 0;            // bit row that holds the constant 1 for every witness (wire 0 itself is a field row)
     TapeStats stats;
 };
@@ -177,6 +179,8 @@ struct XProg {
     std::vector<uint32_t> witness_ref;
     std::vector<uint8_t> isbool;   // per op: the tracer proved the value 0/1 (fused results: not typed)
     std::vector<uint8_t> isint;    // per op: a raw 64-bit integer (type_ints), only consumed by integer operations
+    // group_bit_ops: ops [i, i + group_len[i]) form one warp-cooperative group instruction (0 / absent: none starts at i)
+    std::vector<uint8_t> group_len;
 };
 
 inline XProg fuse_dots(const Tracer &tr, uint32_t max_terms, bool enable) {
@@ -565,10 +569,93 @@ inline void fuse_isums(XProg &xp, const Tracer &tr) {
     xp.isint.swap(oi);
 }
 
-// records that follow an instruction on the tape (term lists)
+// ---- warp-cooperative groups ---------------------------------------------------------------------------------
+// A value typed 0/1 is one packed word per warp, so a boolean function of such values can be evaluated for the warp's 32
+// witnesses by ONE lane with a handful of bitwise instructions -- and 32 independent functions by the 32 lanes at
+// once.  This pass defers every T_LUT until something needs one of the deferred results (or 32 are waiting) and emits
+// them as one group; likewise runs of T_IBIT that extract consecutive bits of the same integer.  Deferring is safe:
+// values are in SSA form, the deferred operations have no side effects, and the group is placed before the first
+// consumer of any of its results.  Sha256(512): 32 808 look-ups -> ~1 100 group instructions.
+inline void group_bit_ops(XProg &xp) {
+    std::vector<XOp> &ops = xp.ops;
+    const size_t N = ops.size();
+    std::vector<uint32_t> order;
+    std::vector<uint8_t> glen;
+    order.reserve(N);
+    glen.reserve(N);
+    std::vector<uint32_t> open_lut, open_bit;
+    std::vector<uint8_t> deferred(N, 0);   // 1: in open_lut, 2: in open_bit
+    auto flush = [&](std::vector<uint32_t> &open) {
+        if (open.empty()) return;
+        const size_t at = order.size();
+        for (uint32_t i : open) {
+            order.push_back(i);
+            glen.push_back(0);
+            deferred[i] = 0;
+        }
+        if (open.size() >= 2) glen[at] = (uint8_t)open.size();
+        open.clear();
+    };
+    for (size_t i = 0; i < N; i++) {
+        const XOp &o = ops[i];
+        bool use_lut = false, use_bit = false;
+        auto chk = [&](uint32_t r) {
+            if (r == NO_REF || (r & CONST_FLAG)) return;
+            if (deferred[r] == 1) use_lut = true;
+            if (deferred[r] == 2) use_bit = true;
+        };
+        if (o.op == T_DOT || o.op == T_ISUM)
+            for (uint32_t k = 0; k < o.tn; k++) chk(xp.terms[o.t0 + k].second);
+        chk(o.a); chk(o.b); chk(o.c);
+        if (use_lut) flush(open_lut);
+        if (use_bit) flush(open_bit);
+        if (o.op == T_LUT) {
+            open_lut.push_back((uint32_t)i);
+            deferred[i] = 1;
+            if (open_lut.size() == 32) flush(open_lut);
+        } else if (o.op == T_IBIT) {
+            if (!open_bit.empty()) {
+                const XOp &l = ops[open_bit.back()];
+                if (l.a != o.a || l.aux + 1 != o.aux) flush(open_bit);
+            }
+            open_bit.push_back((uint32_t)i);
+            deferred[i] = 2;
+            if (open_bit.size() == 32) flush(open_bit);
+        } else {
+            order.push_back((uint32_t)i);
+            glen.push_back(0);
+        }
+    }
+    flush(open_lut);
+    flush(open_bit);
+    std::vector<uint32_t> remap(N, NO_REF);
+    for (size_t k = 0; k < N; k++) remap[order[k]] = (uint32_t)k;
+    auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
+    std::vector<XOp> out(N);
+    std::vector<uint8_t> ob(N), oi(N);
+    for (size_t k = 0; k < N; k++) {
+        XOp o = ops[order[k]];
+        if (o.op == T_DOT || o.op == T_ISUM)
+            for (uint32_t t = 0; t < o.tn; t++) xp.terms[o.t0 + t].second = mapref(xp.terms[o.t0 + t].second);
+        o.a = mapref(o.a);
+        o.b = mapref(o.b);
+        o.c = mapref(o.c);
+        out[k] = o;
+        ob[k] = xp.isbool[order[k]];
+        oi[k] = xp.isint[order[k]];
+    }
+    for (uint32_t &r : xp.witness_ref) r = mapref(r);
+    ops.swap(out);
+    xp.isbool.swap(ob);
+    xp.isint.swap(oi);
+    xp.group_len.swap(glen);
+}
+
+// records that follow an instruction on the tape (term / member lists)
 inline uint32_t extra_records(const TapeIns &in) {
     if (in.op == T_DOT) return (in.a + 1) / 2;
     if (in.op == T_ISUM) return (in.a + 3) / 4;
+    if (in.op == T_LUTG || in.op == T_IBITG) return in.a;
     return 0;
 }
 
@@ -585,7 +672,7 @@ inline void schedule_reloads(Tape &t) {
     std::vector<uint32_t> last_store(t.n_frows, NO_ROW);
     for (size_t pc = 0; pc < t.ins.size(); pc++) {
         TapeIns &in = t.ins[pc];
-        if (in.op == T_DOT || in.op == T_ISUM) {
+        if (extra_records(in)) {
             if ((in.flags & F_STORE) && !(in.c & ROW_BIT)) last_store[in.c] = (uint32_t)pc;
             pc += extra_records(in);
             continue;
@@ -667,7 +754,9 @@ inline XProg prepare_program(const Tracer &tr, uint32_t max_terms, bool fuse = t
     if (fuse) {
         type_ints(xp, tr);
         fuse_isums(xp, tr);
+        group_bit_ops(xp);
     } else xp.isint.assign(xp.ops.size(), 0);
+    if (xp.group_len.size() != xp.ops.size()) xp.group_len.assign(xp.ops.size(), 0);
     return xp;
 }
 
@@ -696,10 +785,26 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     {
         // wire 0 is the constant 1 (calcwit.cpp:34): it keeps a field row (linear combinations evaluated in the field add
         // their constant term through it) AND gets a bit row (Tape::one_brow) for constraints evaluated in integers
+        // Bit rows: first the wires bound to computed 0/1 values (in wire order), then the wires bound to the constant 0,
+        // then those bound to the constant 1 and one_brow -- two contiguous ranges that a T_FILL each writes.
         uint32_t nf = 0, nb = 0;
-        for (uint32_t w = 0; w < out.n_wires; w++) out.wire_loc[w] = (w != 0 && is_bool_ref(xp.witness_ref[w])) ? (ROW_BIT | nb++) : nf++;
+        auto const_bit = [&](uint32_t w) -> int {   // -1: not a constant 0/1 wire
+            const uint32_t r = xp.witness_ref[w];
+            if (w == 0 || !(r & CONST_FLAG) || !is_bool_ref(r)) return -1;
+            return (int)tr.consts[r & ~CONST_FLAG].v[0];
+        };
+        for (uint32_t w = 0; w < out.n_wires; w++) {
+            if (const_bit(w) >= 0) continue;
+            out.wire_loc[w] = (w != 0 && is_bool_ref(xp.witness_ref[w])) ? (ROW_BIT | nb++) : nf++;
+        }
         out.n_fwires = nf;
-        out.one_brow = nb++;
+        for (int v = 0; v < 2; v++) {
+            out.const_rows[v][0] = nb;
+            for (uint32_t w = 0; w < out.n_wires; w++)
+                if (const_bit(w) == v) out.wire_loc[w] = ROW_BIT | nb++;
+            if (v == 1) out.one_brow = nb++;
+            out.const_rows[v][1] = nb - out.const_rows[v][0];
+        }
         out.n_bwires = nb;
     }
     uint32_t ml[2];
@@ -755,14 +860,15 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
         wire_next[w] = wire_head[r];
         wire_head[r] = (uint32_t)w;
     }
-    // constants bound to wires are stored up front
-    if (out.n_wires) {
-        out.ins.push_back(TapeIns{T_STC, 1, 0, tr.one_ref() & ~CONST_FLAG, 0, ROW_BIT | out.one_brow});
-        out.stats.n_stc++;
-    }
+    // constants bound to wires are stored up front: the 0 / 1 wires as two filled ranges of bit rows
+    for (int v = 0; v < 2; v++)
+        if (out.const_rows[v][1]) {
+            out.ins.push_back(TapeIns{T_FILL, 0, 0, v ? 0xffffffffu : 0u, out.const_rows[v][1], ROW_BIT | out.const_rows[v][0]});
+            out.stats.n_stc++;
+        }
     for (size_t w = 0; w < xp.witness_ref.size(); w++) {
         uint32_t r = xp.witness_ref[w];
-        if (r & CONST_FLAG) {
+        if ((r & CONST_FLAG) && !(out.wire_loc[w] & ROW_BIT)) {
             out.ins.push_back(TapeIns{T_STC, 1, 0, r & ~CONST_FLAG, 0, out.wire_loc[w]});
             out.stats.n_stc++;
         }
@@ -837,6 +943,94 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     std::vector<uint32_t> enc;
     std::unordered_map<uint64_t, uint32_t> iconst_index;
     for (size_t i = 0; i < N; i++) {
+        if (xp.group_len[i] >= 2) {
+            // ---- warp-cooperative group (group_bit_ops): members i .. i+n-1 execute as ONE instruction, lane m doing member m.
+            // All operands must be resident when it starts; results may take the slots of operands that die here (the
+            // kernel reads every operand before any lane writes).
+            const uint32_t n = xp.group_len[i], last = (uint32_t)i + n - 1;
+            const bool lutg = ops[i].op == T_LUT;
+            std::vector<uint32_t> grs;
+            for (uint32_t m = 0; m < n; m++) {
+                const XOp &g = ops[i + m];
+                const uint32_t refs[3] = {g.a, lutg ? g.b : NO_REF, lutg ? g.c : NO_REF};
+                for (uint32_t r : refs)
+                    if (r != NO_REF) {
+                        if (r & CONST_FLAG) throw TraceError("group member takes a constant");
+                        grs.push_back(r);
+                    }
+            }
+            pinned.clear();
+            for (uint32_t r : grs)
+                if (val_slot[r] >= 0) pinned.push_back(slot_code(r));
+            for (uint32_t r : grs) {
+                if (val_slot[r] >= 0) continue;
+                if (val_home[r] == NO_REF) throw TraceError("slot allocator: value lost");
+                const int kd = kind_of(r);
+                uint32_t sl = alloc_slot(kd, (uint32_t)i, pinned);
+                out.ins.push_back(TapeIns{T_LD, 0, (uint16_t)(sl | (kd ? BSLOT_DST : 0)), 0, 0, val_home[r]});
+                out.stats.n_ld++;
+                out.stats.n_ld_bool += (uint64_t)kd;
+                val_slot[r] = (int32_t)sl;
+                slot_val[kd][sl] = (int32_t)r;
+                pinned.push_back(slot_code(r));
+            }
+            std::vector<uint32_t> recs(4 * (size_t)n, 0);
+            for (uint32_t m = 0; m < n; m++) {
+                const XOp &g = ops[i + m];
+                if (lutg) {
+                    const uint32_t s0 = slot_code(g.a) & 0xffffu, s1 = g.b != NO_REF ? slot_code(g.b) & 0xffffu : 0u,
+                                   s2 = g.c != NO_REF ? slot_code(g.c) & 0xffffu : 0u;
+                    recs[4 * m] = s0 | (s1 << 16);
+                    recs[4 * m + 1] = s2;
+                    recs[4 * m + 2] = g.aux & 0xffffu;
+                }
+            }
+            const uint32_t src_code = lutg ? 0u : slot_code(ops[i].a);
+            for (uint32_t r : grs)
+                if (val_slot[r] >= 0 && next_use(r, last) == 0xffffffffu) release_value(r);
+            still.clear();
+            for (uint32_t r : grs)
+                if (val_slot[r] >= 0) still.push_back(slot_code(r));
+            for (uint32_t m = 0; m < n; m++) {
+                const uint32_t v = (uint32_t)i + m;
+                if (!xp.isbool[v]) throw TraceError("group member is not typed 0/1");
+                const uint32_t d = alloc_slot(1, last, still);
+                val_slot[v] = (int32_t)d;
+                slot_val[1][d] = (int32_t)v;
+                still.push_back(d | BSLOT);
+                live_now++;
+                out.stats.max_live = std::max(out.stats.max_live, live_now);
+                uint32_t row = NO_ROW;
+                if (wire_head[v] != NO_REF) {
+                    row = out.wire_loc[wire_head[v]];
+                    val_home[v] = row;
+                    out.stats.n_st++;
+                }
+                if (lutg) recs[4 * m + 1] |= d << 16;
+                else recs[4 * m] = d;
+                recs[4 * m + 3] = row;
+            }
+            out.ins.push_back(TapeIns{(uint8_t)(lutg ? T_LUTG : T_IBITG), 0, 0, n, src_code, lutg ? 0u : ops[i].aux});
+            for (uint32_t m = 0; m < n; m++) {
+                TapeIns raw;
+                memcpy(&raw, &recs[4 * m], 16);
+                out.ins.push_back(raw);
+            }
+            if (lutg) out.stats.n_lut += n;
+            else out.stats.n_other += n;
+            out.stats.n_groups++;
+            for (uint32_t m = 0; m < n; m++) {
+                const uint32_t v = (uint32_t)i + m;
+                if (wire_head[v] != NO_REF)
+                    for (uint32_t w = wire_next[wire_head[v]]; w != NO_REF; w = wire_next[w]) {
+                        out.ins.push_back(TapeIns{T_ST, 0, 0, (uint32_t)val_slot[v] | BSLOT, 0, out.wire_loc[w]});
+                        out.stats.n_st++;
+                    }
+                if (next_use(v, last) == 0xffffffffu) release_value(v);
+            }
+            i = last;
+            continue;
+        }
         const XOp &o = ops[i];
         uint32_t pos = (uint32_t)i;
         operands(o, rs);
@@ -1024,7 +1218,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     if (out.stats.n_sel + out.stats.n_other > 2 * out.stats.n_mul) {
         for (size_t pc = 0; pc < out.ins.size(); pc++) {
             TapeIns &in = out.ins[pc];
-            if (in.op == T_DOT || in.op == T_ISUM) { pc += extra_records(in); continue; }
+            if (extra_records(in)) { pc += extra_records(in); continue; }
             if (in.op == T_MUL) in.flags |= F_TRIVIAL;
         }
     }
@@ -1034,7 +1228,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     else
         for (size_t pc = 0; pc < out.ins.size(); pc++) {
             TapeIns &in = out.ins[pc];
-            if (in.op == T_DOT || in.op == T_ISUM) { pc += extra_records(in); continue; }
+            if (extra_records(in)) { pc += extra_records(in); continue; }
             if (in.op == T_LD) in.a = NO_ROW;   // nothing to request: there is no ring
         }
     out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +

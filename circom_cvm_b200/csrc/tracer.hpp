@@ -49,6 +49,11 @@ enum TOp : uint8_t {
     T_IBIT,      // bit `aux` of the integer a (a value typed 0/1)
     T_IFAIL_NE,  // status if the integers a and b differ
     T_ISUM,      // addend + sum_j (bit_j << shift_j): a chain of T_ICADD with power-of-two constants (tape.hpp fuse_isums)
+    // warp-cooperative group instructions (tape.hpp group_bit_ops): up to 32 independent operations on values typed 0/1,
+    // one per LANE, each lane working on the packed word of the warp's 32 witnesses
+    T_LUTG,      // up to 32 T_LUT
+    T_IBITG,     // up to 32 consecutive bits of one integer (T_IBIT)
+    T_FILL,      // constant bit rows [c, c + b) = the word a (witness wires bound to the constants 0 / 1)
     T_COUNT
 };
 

@@ -8,7 +8,7 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM) = range(41)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL) = range(44)
 F_ADDEND = 32        # T_DOT: field b is an addend
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
@@ -116,6 +116,34 @@ def run_tape(tape, consts_mont, layout, inputs):
             pc += (a + 3) // 4
             assert acc < 1 << 62 and not dst & BSLOT_DST
             res = Int(acc)
+        elif op in (T_LUTG, T_IBITG):
+            # a members, one record each; every member reads its operands before any result is written
+            outs = []
+            src = get_int(b, 0) if op == T_IBITG else None
+            for m in range(a):
+                rec = [int(x) for x in words[pc + m]]
+                if op == T_LUTG:
+                    sl = [rec[0] & 0xFFFF, rec[0] >> 16, rec[1] & 0xFFFF]
+                    idx = 0
+                    for i in range((rec[2] >> 8) & 0xFF):
+                        v = bslots[sl[i]]
+                        assert v in (0, 1), "T_LUTG input is not a 0/1 value"
+                        idx |= v << i
+                    outs.append(((rec[2] >> idx) & 1, rec[1] >> 16, rec[3]))
+                else:
+                    outs.append(((src >> (c + m)) & 1, rec[0] & 0xFFFF, rec[3]))
+            for v, d, row in outs:
+                bslots[d] = v
+                if row != NO_ROW:
+                    assert row & ROW_BIT
+                    set_row(row, v)
+            pc += a
+            continue
+        elif op == T_FILL:
+            assert a in (0, 0xFFFFFFFF) and c & ROW_BIT
+            for k in range(b):
+                set_row(c + k, 1 if a else 0)
+            continue
         elif op == T_INPUT:
             res = inputs[a] % M.Q
         elif op == T_CADD:
