@@ -78,9 +78,9 @@ struct BoundDev {
     uint64_t layout_id = ~0ull;      // 0: the plain layout (row = wire)
     bool typed = false;
     uint32_t n_brows = 0;
-    uint64_t macs = 0, bit_adds = 0, n_int_constraints = 0, n_bterms = 0, n_fterms = 0;
-    DevBuf d_hdr, d_terms, d_bhdr, d_bterms;
-    void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); layout_id = ~0ull; }
+    uint64_t macs = 0, bit_adds = 0, n_int_constraints = 0, n_bterms = 0, n_fterms = 0, n_tcons = 0;
+    DevBuf d_hdr, d_terms, d_bhdr, d_bterms, d_tcons;
+    void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); d_tcons.release(); layout_id = ~0ull; }
 };
 
 struct cvmgpu_r1cs {
@@ -644,6 +644,23 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *out)
     info->bound_field_terms = r->typed.layout_id == ~0ull ? 0 : r->typed.n_fterms;
     info->bound_macs = r->typed.layout_id == ~0ull ? 0 : r->typed.macs;
     info->bound_bit_adds = r->typed.bit_adds;
+    info->bound_table_constraints = r->typed.n_tcons;
+    return fill_info(out, v);
+}
+
+extern "C" int cvmgpu_r1cs_bind_info(const cvmgpu_r1cs *r, const cvmgpu_program *p, cvmgpu_r1cs_info *out) {
+    if (!r || !p || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (r->file.n_wires != p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "r1cs and program disagree on the number of wires");
+    cvmgpu_r1cs_info v;
+    v.struct_size = sizeof(v);
+    if (int rc = cvmgpu_r1cs_info_get(r, &v)) return rc;
+    const r1cs::Bound b = r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow, p->tape.const_rows);
+    v.bound_int_constraints = b.n_int_constraints;
+    v.bound_bit_terms = b.bterms.size();
+    v.bound_field_terms = b.fterms.size();
+    v.bound_macs = b.macs;
+    v.bound_bit_adds = b.bit_adds;
+    v.bound_table_constraints = b.n_table_constraints;
     return fill_info(out, v);
 }
 
@@ -668,6 +685,9 @@ static int upload_bound(const r1cs::Bound &b, BoundDev &d) {
     if (!b.fterms.empty()) CUDA_TRY(cudaMemcpy(d.d_terms.p, b.fterms.data(), b.fterms.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d.d_bhdr.p, b.bhdr.data(), b.bhdr.size() * 4, cudaMemcpyHostToDevice));
     if (!b.bterms.empty()) CUDA_TRY(cudaMemcpy(d.d_bterms.p, b.bterms.data(), b.bterms.size() * 8, cudaMemcpyHostToDevice));
+    if (int rc = d.d_tcons.ensure(std::max<size_t>(32, b.tcons.size() * 4))) return rc;
+    if (!b.tcons.empty()) CUDA_TRY(cudaMemcpy(d.d_tcons.p, b.tcons.data(), b.tcons.size() * 4, cudaMemcpyHostToDevice));
+    d.n_tcons = b.n_table_constraints;
     d.macs = b.macs;
     d.bit_adds = b.bit_adds;
     d.n_int_constraints = b.n_int_constraints;
@@ -749,6 +769,24 @@ static int launch_check(cvmgpu_r1cs *r, const BoundDev &bd, const void *d_store,
         else kern::r1cs_kernel<4, false><<<grid, R1CS_NT, 0, s>>>(rp);
     }
     CUDA_TRY(cudaGetLastError());
+    if (bd.typed && bd.n_tcons) {
+        // the constraints that are boolean predicates of a few 0/1 wires: bitwise, 32 witnesses per lane
+        kern::R1csTableParams tp;
+        tp.tcons = (const uint4 *)bd.d_tcons.p;
+        tp.n_tcons = (uint32_t)bd.n_tcons;
+        const uint64_t tgx = (B + 127) / 128;
+        uint64_t tchunks = std::max<uint64_t>(1, (148ull * 16 + tgx - 1) / tgx);
+        uint32_t tper = (uint32_t)std::max<uint64_t>(32, ((bd.n_tcons + tchunks - 1) / tchunks + 31) / 32 * 32);
+        tchunks = std::min<uint64_t>(65535, (bd.n_tcons + tper - 1) / tper);
+        tper = (uint32_t)(((bd.n_tcons + tchunks - 1) / tchunks + 31) / 32 * 32);
+        tp.per_chunk = tper;
+        tp.bits = bits;
+        tp.n_brows = bd.n_brows;
+        tp.B = B;
+        tp.first_bad = (uint32_t *)d_first_bad;
+        kern::r1cs_table_kernel<<<dim3((unsigned)tgx, (unsigned)((bd.n_tcons + tper - 1) / tper)), 128, 0, s>>>(tp);
+        CUDA_TRY(cudaGetLastError());
+    }
     return CVMGPU_OK;
 }
 
@@ -776,9 +814,9 @@ extern "C" int cvmgpu_r1cs_check_store_dev(cvmgpu_r1cs *r, cvmgpu_program *p, co
     if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
     if (int rc = upload_r1cs(r)) return rc;
     if (r->typed.layout_id != p->layout_id) {
-        if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow), r->typed)) return rc;
+        if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow, p->tape.const_rows), r->typed)) return rc;
         r->typed.layout_id = p->layout_id;
-        r->typed.typed = r->typed.n_bterms != 0;   // no term on a bit row: the plain kernel runs on the field rows
+        r->typed.typed = r->typed.n_bterms != 0 || r->typed.n_tcons != 0;   // no term on a bit row: the plain kernel runs on the field rows
         r->typed.n_brows = p->tape.n_brows;
     }
     const uint32_t *bits = (const uint32_t *)((const char *)d_store + store_field_bytes(p, bstride));

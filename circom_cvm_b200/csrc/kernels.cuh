@@ -868,6 +868,7 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
             const uint4 bh = __ldg(p.bhdr + c);
             bA = bh.x & 0x3fffffffu; bB = bh.y; bC = bh.z; bN = bh.w;
             const uint32_t mode = bh.x >> 30;
+            if (mode == 3) continue;   // a boolean predicate of a few 0/1 wires: r1cs_table_kernel
             if (mode) {
                 // every term is a 0/1 wire with a small integer coefficient: |A*B - C| is far below q, so the constraint
                 // holds mod q iff it holds in the integers.  (No field-row terms: the operand stream is not touched.)
@@ -929,6 +930,63 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (active && bad != 0xffffffffu) atomicMin(p.first_bad + w, bad);
+}
+
+// Constraints over at most five distinct 0/1 wires (r1cs.hpp Bound::tcons): the constraint is a boolean predicate of
+// those wires, tabulated on the host.  A bit row holds the wire for 32 witnesses in one word, so ONE lane evaluates the
+// predicate for the warp's 32 witnesses with a multiplexer tree over the 32-entry table (63 bitwise instructions), and
+// the 32 lanes take 32 different constraints: ~2.5 instructions per constraint and 32 witnesses, against ~100 per
+// constraint and witness on the per-witness path.  Hash circuits are made of such gates (Sha256: 90 % of the constraints).
+// thread block = 4 warps = 4 groups of 32 witnesses; blockIdx.y = chunk of the table constraints.
+struct R1csTableParams {
+    const uint4 *tcons;          // 2 x uint4 per constraint: {row0..row3}, {row4, table, constraint index, 0}
+    uint32_t n_tcons, per_chunk;
+    const uint32_t *bits;
+    uint32_t n_brows;
+    uint64_t B;
+    uint32_t *first_bad;
+};
+__global__ void __launch_bounds__(128) r1cs_table_kernel(R1csTableParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t wg = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);   // group of 32 witnesses
+    const uint64_t w0 = wg * 32;
+    if (w0 >= p.B) return;
+    const uint32_t valid = (p.B - w0 >= 32) ? 0xffffffffu : ((1u << (uint32_t)(p.B - w0)) - 1u);
+    const uint32_t *brow = p.bits + wg * p.n_brows;
+    const uint32_t t0 = blockIdx.y * p.per_chunk, t1 = min(p.n_tcons, t0 + p.per_chunk);
+    for (uint32_t base = t0; base < t1; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t badw = 0, cidx = 0;
+        if (i < t1) {
+            const uint4 ra = __ldg(p.tcons + 2 * (uint64_t)i), rb = __ldg(p.tcons + 2 * (uint64_t)i + 1);
+            const uint32_t x0 = __ldg(brow + ra.x), x1 = __ldg(brow + ra.y), x2 = __ldg(brow + ra.z), x3 = __ldg(brow + ra.w),
+                           x4 = __ldg(brow + rb.x);
+            const int t = (int)rb.y;
+            cidx = rb.z;
+            // multiplexer tree: level 0 selects on x0 between table entries 2j and 2j+1 (as all-ones / all-zero masks)
+            uint32_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t m0 = (uint32_t)((t << (31 - 2 * j)) >> 31), m1 = (uint32_t)((t << (30 - 2 * j)) >> 31);
+                v[j] = (x0 & m1) | (~x0 & m0);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (x1 & v[2 * j + 1]) | (~x1 & v[2 * j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = (x2 & v[2 * j + 1]) | (~x2 & v[2 * j]);
+#pragma unroll
+            for (int j = 0; j < 2; j++) v[j] = (x3 & v[2 * j + 1]) | (~x3 & v[2 * j]);
+            const uint32_t sat = (x4 & v[1]) | (~x4 & v[0]);
+            badw = ~sat & valid;
+        }
+        if (__any_sync(0xffffffffu, badw != 0u)) {   // rare: some witness violates one of these 32 constraints
+            while (badw) {
+                const uint32_t j = __ffs(badw) - 1;
+                badw &= badw - 1;
+                atomicMin(p.first_bad + w0 + j, cidx);
+            }
+        }
+    }
 }
 
 // ---- device self-test of the field routines -----------------------------------------------------------

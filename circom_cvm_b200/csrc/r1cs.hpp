@@ -65,6 +65,12 @@ struct Bound {
     // below 2^31, the product in 64 bits)
     std::vector<uint32_t> bhdr;
     std::vector<Term> bterms;       // (bit row, coefficient index)
+    // mode 3: a constraint over at most TABLE_VARS distinct 0/1 wires IS a boolean predicate of them; its truth table is
+    // computed here and the kernel evaluates it bitwise for 32 witnesses at a time (r1cs_table_kernel): 8 words per
+    // constraint = {bit rows of the variables (unused: row of the constant 1), truth table, constraint index, 0}.
+    // Such constraints have no terms in either CSR.
+    std::vector<uint32_t> tcons;
+    uint64_t n_table_constraints = 0;
     uint64_t n_int_constraints = 0, n_field_constraints = 0;
     // 32x32->64 multiply-accumulates the check executes per witness on this layout (upper bound: products with a 0 / +-1
     // factor are skipped at run time), and its executed field additions of bit-row terms
@@ -72,11 +78,24 @@ struct Bound {
 };
 
 static const uint32_t LOC_BIT = 0x80000000u;   // tape::ROW_BIT
+static const int TABLE_VARS = 5;
 
 // wire_loc == nullptr: the plain layout (row = wire, no bit rows).  one_brow: the bit row that holds the constant 1 (wire 0
 // itself is a field row): terms on wire 0 use it in constraints evaluated in integers.
-inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0) {
+// const_rows[v] = {first, count}: bit rows of the wires bound to the constant v -- terms on them are folded (a wire that
+// is always 0 contributes nothing, a wire that is always 1 is the constant wire 0).
+inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0, const uint32_t (*const_rows)[2] = nullptr) {
     Bound b;
+    // wire -> 0 when it is bound to the constant 1, or 0xffffffff when bound to the constant 0 (the term vanishes)
+    auto fold = [&](uint32_t wire) -> uint32_t {
+        if (!wire_loc || !const_rows || wire == 0) return wire;
+        const uint32_t loc = wire_loc[wire];
+        if (!(loc & LOC_BIT)) return wire;
+        const uint32_t row = loc & ~LOC_BIT;
+        if (row >= const_rows[0][0] && row < const_rows[0][0] + const_rows[0][1]) return 0xffffffffu;
+        if (row >= const_rows[1][0] && row < const_rows[1][0] + const_rows[1][1]) return 0u;
+        return wire;
+    };
     const size_t n_lc = f.ptr.size() - 1;
     b.hdr.assign(4 * (n_lc + 1), 0);
     b.bhdr.assign(4 * ((size_t)f.n_constraints + 1), 0);
@@ -99,7 +118,8 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
             uint64_t sumabs = 0;
             for (uint32_t t = sb[src]; t < se[src] && intok; t++) {
                 const Term &tm = f.terms[t];
-                const uint32_t wire = tm.wire & 0x0fffffffu;
+                const uint32_t wire = fold(tm.wire & 0x0fffffffu);
+                if (wire == 0xffffffffu) continue;
                 if ((wire != 0 && !(loc_of(wire) & LOC_BIT)) || !f.cint_ok[tm.coef]) { intok = false; break; }
                 const int64_t v = f.cint[tm.coef];
                 sumabs += (uint64_t)(v < 0 ? -v : v);
@@ -107,7 +127,64 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
             }
             max_sumabs = std::max(max_sumabs, sumabs);
         }
-        const uint32_t mode = !intok ? 0u : (max_sumabs >> 31) ? 1u : 2u;
+        uint32_t mode = !intok ? 0u : (max_sumabs >> 31) ? 1u : 2u;
+        if (intok) {
+            // distinct variables (bit rows other than the constant 1)
+            uint32_t vars[TABLE_VARS];
+            int nv = 0;
+            bool fits = true;
+            for (int k = 0; k < 3 && fits; k++) {
+                const int src = (k == 1 && same_b) ? 0 : k;
+                for (uint32_t t = sb[src]; t < se[src] && fits; t++) {
+                    const uint32_t wire = fold(f.terms[t].wire & 0x0fffffffu);
+                    if (wire == 0 || wire == 0xffffffffu) continue;
+                    const uint32_t row = loc_of(wire) & ~LOC_BIT;
+                    bool seen = false;
+                    for (int q = 0; q < nv; q++) seen = seen || vars[q] == row;
+                    if (seen) continue;
+                    if (nv == TABLE_VARS) fits = false;
+                    else vars[nv++] = row;
+                }
+            }
+            if (fits && nv == 0) {
+                // no variable at all (an empty constraint, or constants only): decided here once and for all
+                __int128 lc[3] = {0, 0, 0};
+                for (int k = 0; k < 3; k++) {
+                    const int src = (k == 1 && same_b) ? 0 : k;
+                    for (uint32_t t = sb[src]; t < se[src]; t++)
+                        if (fold(f.terms[t].wire & 0x0fffffffu) == 0) lc[k] += f.cint[f.terms[t].coef];
+                }
+                if (lc[0] * lc[1] == lc[2]) mode = 3;   // always satisfied: nothing to evaluate
+                fits = false;
+            }
+            if (fits) {
+                uint32_t table = 0;
+                for (uint32_t asg = 0; asg < (1u << TABLE_VARS); asg++) {
+                    __int128 lc[3] = {0, 0, 0};
+                    for (int k = 0; k < 3; k++) {
+                        const int src = (k == 1 && same_b) ? 0 : k;
+                        for (uint32_t t = sb[src]; t < se[src]; t++) {
+                            const uint32_t wire = fold(f.terms[t].wire & 0x0fffffffu);
+                            if (wire == 0xffffffffu) continue;
+                            int64_t bit = 1;
+                            if (wire != 0) {
+                                const uint32_t row = loc_of(wire) & ~LOC_BIT;
+                                for (int q = 0; q < nv; q++)
+                                    if (vars[q] == row) bit = (asg >> q) & 1;
+                            }
+                            lc[k] += (__int128)f.cint[f.terms[t].coef] * bit;
+                        }
+                    }
+                    if (lc[0] * lc[1] == lc[2]) table |= 1u << asg;
+                }
+                for (int q = 0; q < TABLE_VARS; q++) b.tcons.push_back(q < nv ? vars[q] : one_brow);
+                b.tcons.push_back(table);
+                b.tcons.push_back(c);
+                b.tcons.push_back(0);
+                b.n_table_constraints++;
+                mode = 3;
+            }
+        }
         if (intok) b.n_int_constraints++; else b.n_field_constraints++;
         bool has[3] = {false, false, false};
         for (int k = 0; k < 3; k++) {
@@ -124,14 +201,17 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
                 has[1] = true;
                 continue;
             }
+            if (mode == 3) continue;   // evaluated from its truth table: no terms
             const int src = (k == 1 && same_b) ? 0 : k;
             const size_t js = 3 * (size_t)c + src;
             const uint32_t e0 = f.split[3 * js], e1 = f.split[3 * js + 1], e2 = f.split[3 * js + 2];
             uint32_t n[4] = {0, 0, 0, 0}, n_const = 0;
             for (uint32_t t = sb[src]; t < se[src]; t++) {
                 const Term &tm = f.terms[t];
-                uint32_t loc = loc_of(tm.wire & 0x0fffffffu);
-                if (intok && (tm.wire & 0x0fffffffu) == 0) loc = LOC_BIT | one_brow;
+                const uint32_t wire = fold(tm.wire & 0x0fffffffu);
+                if (wire == 0xffffffffu) continue;   // a wire that is always 0
+                uint32_t loc = loc_of(wire);
+                if (intok && wire == 0) loc = LOC_BIT | one_brow;
                 if (loc & LOC_BIT) {
                     b.bterms.push_back(Term{loc & ~LOC_BIT, tm.coef});
                     if (!intok) b.bit_adds++;

@@ -34,7 +34,7 @@ EXPORTS = [
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
-    "cvmgpu_r1cs_check_store_dev", "cvmgpu_witness_import_dev",
+    "cvmgpu_r1cs_check_store_dev", "cvmgpu_r1cs_bind_info", "cvmgpu_witness_import_dev",
     "cvmgpu_fr_host_op", "cvmgpu_fr_device_op", "cvmgpu_imad_peak", "cvmgpu_mul_peak", "cvmgpu_set_tape_mode",
 ]
 
@@ -67,7 +67,7 @@ class R1csInfo(ctypes.Structure):
                 ("n_coefs", c_uint32), ("nnz_small", c_uint64), ("macs", c_uint64), ("n_quadratic", c_uint64),
                 ("nnz_const", c_uint64), ("n_squares", c_uint64), ("bound_int_constraints", c_uint64),
                 ("bound_bit_terms", c_uint64), ("bound_field_terms", c_uint64), ("bound_macs", c_uint64),
-                ("bound_bit_adds", c_uint64)]
+                ("bound_bit_adds", c_uint64), ("bound_table_constraints", c_uint64)]
 
     def asdict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -95,6 +95,7 @@ def lib():
     L.cvmgpu_program_iconsts.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_witness_batch_select.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_export_range_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p]
+    L.cvmgpu_r1cs_bind_info.argtypes = [c_void_p, c_void_p, POINTER(R1csInfo)]
     L.cvmgpu_r1cs_check_store_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
     L.cvmgpu_release_buffers.argtypes = []
     L.cvmgpu_release_buffers.restype = None
@@ -321,6 +322,13 @@ class R1cs:
         info.struct_size = ctypes.sizeof(R1csInfo)
         _check(lib().cvmgpu_r1cs_info_get(self._h, byref(info)))
         self.info = info
+        return info
+
+    def bind_info(self, wc):
+        """how this constraint system maps onto WitnessCalculator wc's typed store (host only)"""
+        info = R1csInfo()
+        info.struct_size = ctypes.sizeof(R1csInfo)
+        _check(lib().cvmgpu_r1cs_bind_info(self._h, wc._h, byref(info)))
         return info
 
     def check(self, witnesses):

@@ -110,6 +110,7 @@ typedef struct {
     uint64_t bound_field_terms;     /* non-zeros on field rows (the operand stream) */
     uint64_t bound_macs;            /* multiply-accumulates per witness on that layout (upper bound: 0 / +-1 factors skip the product) */
     uint64_t bound_bit_adds;        /* field additions of bit-row terms outside integer constraints */
+    uint64_t bound_table_constraints; /* of bound_int_constraints: boolean predicates of <= 5 wires, evaluated bitwise for 32 witnesses at a time */
 } cvmgpu_r1cs_info;
 
 const char *cvmgpu_last_error(void);
@@ -182,6 +183,8 @@ int cvmgpu_wtns_write(const char *path, const uint8_t *witness, uint32_t n_wires
 int cvmgpu_r1cs_load(const char *r1cs_path, cvmgpu_r1cs **out);
 int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *info);
 void cvmgpu_r1cs_free(cvmgpu_r1cs *r);
+/* cvmgpu_r1cs_info_get with the bound_* counters computed for program p's value-store layout (host only, no GPU needed) */
+int cvmgpu_r1cs_bind_info(const cvmgpu_r1cs *r, const cvmgpu_program *p, cvmgpu_r1cs_info *info);
 /* HOST: witnesses B x n_wires x 32 B canonical; first_bad[b] = index of the first violated constraint or
  * 0xffffffff when witness b satisfies every constraint. */
 int cvmgpu_r1cs_check(cvmgpu_r1cs *r, const uint8_t *witnesses, uint64_t B, uint32_t *first_bad);
