@@ -8,9 +8,25 @@
 //   %%function line     compiler/src/circuit_design/function.rs:137-168
 //   instructions        `impl WriteCVM` in compiler/src/intermediate_representation/*_bucket.rs,
 //                       mnemonics cvm_code_generator.rs:26-283
-// Extension (not in the fork, which emits nothing for component creation:
-// create_component_bucket.rs:356-360):   ;;%%create_cmp <slot> $<header> <sig_off> <sig_jump> <cmp_off> <cmp_jump> <n>
+// Component creation: the fork emits nothing for it (create_component_bucket.rs:356-360).  Two sources are accepted:
+//   * the extension line  ;;%%create_cmp <slot> $<header> <sig_off> <sig_jump> <cmp_off> <cmp_jump> <n>
+//     (a comment to any other consumer; patches/create_component_bucket.rs.diff makes the emitter print it), or
+//   * the generated <circuit>.cpp of the same compile: recover_creates() reads the `<Sub>_create(...)` blocks that
+//     `impl WriteC for CreateCmpBucket` prints (create_component_bucket.rs:206-354) and places them at the top of the
+//     template's body (creation does not depend on signal values).
+//
+// Emitter defects that are honoured rather than rejected:
+//   * copy loops increment their address operands textually, so a literal address is assigned to
+//     (`i64.5 = i64.add i64.5 i64.1`, store_bucket.rs:1026-1028, call_bucket.rs:985-987): inside the loop that does this
+//     the token is a register initialised to its literal value at loop entry (fix_literal_registers);
+//   * a multi-element `return` passes the VALUE of the first element (return_bucket.rs:131 evaluates the load): the
+//     address of that load is used (link_returns);
+//   * array equality (compute_bucket.rs:538-586) compares the first elements and then increments those VALUES as if they
+//     were addresses, and leaves its result in a register nobody reads while the consumer reads one that is never
+//     written: the whole shape is recognised and replaced by OP_ARRAY_EQ, which computes what the C++ twin does
+//     (compute_bucket.rs:375-407: the conjunction of the element-wise Fr_eq) into the register the consumer reads.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -33,7 +49,8 @@ enum Op : uint16_t {
     OP_FF_LOAD, OP_FF_STORE, OP_GET_SIGNAL, OP_SET_SIGNAL, OP_GET_CMP_SIGNAL,
     OP_SET_CMP_INPUT, OP_SET_CMP_INPUT_CNT, OP_SET_CMP_INPUT_RUN, OP_SET_CMP_INPUT_CNT_CHECK,
     OP_LOOP, OP_IF, OP_ELSE, OP_END, OP_BREAK, OP_CONTINUE, OP_ERROR, OP_CALL, OP_RETURN, OP_CREATE_CMP,
-    OP_MAPPED_UNSUPPORTED
+    OP_MAPPED_UNSUPPORTED,
+    OP_ARRAY_EQ      // dst = AND_k (A[k] == B[k]); args = {addr A, cmp A, addr B, cmp B}; cc = {load op A, load op B, n}
 };
 
 enum OperandKind : uint8_t { K_REG, K_I64, K_FF, K_SPR, K_ARG_MEM, K_ARG_SIG, K_ARG_SUBSIG };
@@ -44,6 +61,9 @@ struct Operand {
     // call arguments of the form i64.memory(a,n) / signal(a,n) / subcmpsignal(c,a,n)
     uint8_t akind = K_I64, ckind = K_I64;
     int64_t aval = 0, cval = 0, n = 0;
+    // literal tokens (ids into Parser::lit_tokens) behind val / aval / cval: a literal that a copy loop assigns to
+    // becomes a register inside that loop
+    int32_t tok = -1, atok = -1, ctok = -1;
 };
 
 struct Ins {
@@ -57,6 +77,8 @@ struct Ins {
     // OP_CREATE_CMP payload
     int64_t cc[6] = {0, 0, 0, 0, 0, 0};  // slot, sig_off, sig_jump, cmp_off, cmp_jump, n
     bool scalar_return = false;
+    int32_t lit_dst = -1;         // the destination is a literal token (id): resolved by fix_literal_registers
+    bool ret_from_load = false;   // OP_RETURN of several elements whose operand is the VALUE loaded from args[2] (an address)
 };
 
 struct Code {
@@ -257,7 +279,21 @@ class Parser {
         return id;
     }
 
-    void simple_operand(const std::string &tok, uint8_t &kind, int64_t &val) {
+    std::vector<std::string> lit_tokens;
+    std::unordered_map<std::string, int> lit_index;
+    int lit_id(const std::string &tok) {
+        auto it = lit_index.find(tok);
+        if (it != lit_index.end()) return it->second;
+        lit_tokens.push_back(tok);
+        lit_index[tok] = (int)lit_tokens.size() - 1;
+        return (int)lit_tokens.size() - 1;
+    }
+    static bool is_literal_token(const std::string &tok) {
+        return (tok.rfind("i64.", 0) == 0 && is_int_token(tok.substr(4))) || (tok.rfind("ff.", 0) == 0 && is_int_token(tok.substr(3)));
+    }
+
+    void simple_operand(const std::string &tok, uint8_t &kind, int64_t &val, int32_t *tokid = nullptr) {
+        if (tokid && is_literal_token(tok)) *tokid = lit_id(tok);
         if (tok.rfind("i64.", 0) == 0 && is_int_token(tok.substr(4))) {
             kind = K_I64;
             val = atoll(tok.c_str() + 4);
@@ -297,18 +333,18 @@ class Parser {
                 o.kind = (f == 0) ? K_ARG_MEM : (f == 1 ? K_ARG_SIG : K_ARG_SUBSIG);
                 if (f == 2) {
                     if (parts.size() != 3) throw ParseError("bad call argument " + tok);
-                    simple_operand(parts[0], o.ckind, o.cval);
-                    simple_operand(parts[1], o.akind, o.aval);
+                    simple_operand(parts[0], o.ckind, o.cval, &o.ctok);
+                    simple_operand(parts[1], o.akind, o.aval, &o.atok);
                     o.n = atoll(parts[2].c_str());
                 } else {
                     if (parts.size() != 2) throw ParseError("bad call argument " + tok);
-                    simple_operand(parts[0], o.akind, o.aval);
+                    simple_operand(parts[0], o.akind, o.aval, &o.atok);
                     o.n = atoll(parts[1].c_str());
                 }
                 return o;
             }
         }
-        simple_operand(tok, o.kind, o.val);
+        simple_operand(tok, o.kind, o.val, &o.tok);
         return o;
     }
 
@@ -371,11 +407,8 @@ class Parser {
         in.line = lineno;
         if (t.size() >= 3 && t[1] == "=") {
             const std::string &d = t[0];
-            if (d.rfind("i64.", 0) == 0 || d.rfind("ff.", 0) == 0)
-                throw ParseError("line " + std::to_string(lineno) + ": assignment to the literal operand '" + d +
-                                 "' (reference emitter defect, store_bucket.rs:1026-1028); re-emit with "
-                                 "addresses held in registers");
-            in.dst = reg(d);
+            if (is_literal_token(d)) in.lit_dst = lit_id(d);   // emitter defect, store_bucket.rs:1026-1028: see fix_literal_registers
+            else in.dst = reg(d);
             if (t.size() == 3) {
                 in.op = OP_MOV;
                 in.args.push_back(operand(t[2]));
@@ -413,8 +446,278 @@ class Parser {
         auto it = prog.code_index.find(prog.start_name);
         if (it == prog.code_index.end()) throw ParseError("missing or unknown %%start");
         prog.start = it->second;
-        for (auto &c : prog.codes) link(c);
+        for (auto &c : prog.codes) {
+            cur = &c;
+            fix_array_eq(c);
+            fix_literal_registers(c);
+            link_returns(c);
+            link(c);
+        }
     }
+
+    // index of the innermost `loop` whose body holds instruction pc (-1: none), and of its `end`
+    static void loop_ranges(const Code &c, std::vector<int> &loop_of, std::vector<int> &end_of) {
+        loop_of.assign(c.ins.size(), -1);
+        end_of.assign(c.ins.size(), -1);
+        std::vector<std::pair<int, int>> st;   // (kind, start)
+        for (int pc = 0; pc < (int)c.ins.size(); pc++) {
+            int inner = -1;
+            for (int k = (int)st.size() - 1; k >= 0; k--)
+                if (st[k].first == 1) { inner = st[k].second; break; }
+            loop_of[pc] = inner;
+            const uint16_t op = c.ins[pc].op;
+            if (op == OP_IF) st.push_back({0, pc});
+            else if (op == OP_LOOP) st.push_back({1, pc});
+            else if (op == OP_END) {
+                if (st.empty()) throw ParseError("unbalanced end in " + c.header);
+                if (st.back().first == 1) end_of[st.back().second] = pc;
+                st.pop_back();
+            }
+        }
+    }
+
+    // `i64.5 = i64.add i64.5 i64.1` in a copy loop (store_bucket.rs:1016-1035, call_bucket.rs:975-994).  The loop's shape is
+    //     loop / if cnt / GET src_location / SET dest_location / cnt = i64.sub cnt i64.1 /
+    //     src_location = i64.add src_location i64.1 / dest_location = i64.add dest_location i64.1 / continue / end / break / end
+    //     [GET src_location / set_cmp_input_{run,cnt_check} c dest_location v]        <- the peeled last element
+    // and the two increments mean "the address operand of GET" and "the address operand of SET" -- by position, not by
+    // token (both may be the same literal, e.g. variable 0 copied to signal 0).  A literal address becomes a fresh register
+    // that is set to the literal right before `loop`, is used by GET / SET / the peeled pair, and nowhere else.
+    void fix_literal_registers(Code &c) {
+        bool any = false;
+        for (const Ins &in : c.ins) any = any || in.lit_dst >= 0;
+        if (!any) return;
+        auto get_addr_arg = [](uint16_t op) -> int {
+            return (op == OP_FF_LOAD || op == OP_GET_SIGNAL) ? 0 : op == OP_GET_CMP_SIGNAL ? 1 : -1;
+        };
+        auto set_addr_arg = [](uint16_t op) -> int {
+            if (op == OP_FF_STORE || op == OP_SET_SIGNAL) return 0;
+            if (op == OP_SET_CMP_INPUT || op == OP_SET_CMP_INPUT_CNT || op == OP_SET_CMP_INPUT_RUN || op == OP_SET_CMP_INPUT_CNT_CHECK) return 1;
+            return -1;
+        };
+        struct Init { int loop, reg, tok; };
+        std::vector<Init> inits;
+        std::vector<Ins> &I = c.ins;
+        for (int L = 0; L + 10 < (int)I.size(); L++) {
+            if (I[L].op != OP_LOOP || I[L + 1].op != OP_IF) continue;
+            const int ga = get_addr_arg(I[L + 2].op), sa = set_addr_arg(I[L + 3].op);
+            if (ga < 0 || sa < 0 || I[L + 4].op != OP_I64_SUB || I[L + 5].op != OP_I64_ADD || I[L + 6].op != OP_I64_ADD) continue;
+            if (I[L + 7].op != OP_CONTINUE || I[L + 8].op != OP_END || I[L + 9].op != OP_BREAK || I[L + 10].op != OP_END) continue;
+            const int end = L + 10;
+            const bool peeled = end + 2 < (int)I.size() && I[end + 1].op == I[L + 2].op &&
+                                (I[end + 2].op == OP_SET_CMP_INPUT_RUN || I[end + 2].op == OP_SET_CMP_INPUT_CNT_CHECK);
+            for (int k = 0; k < 2; k++) {
+                Ins &inc = I[L + 5 + k];
+                if (inc.lit_dst < 0) continue;
+                Ins &user = I[L + 2 + k];
+                const int ai = k ? sa : ga;
+                if ((int)user.args.size() <= ai || user.args[ai].tok != inc.lit_dst || inc.args.at(0).tok != inc.lit_dst)
+                    throw ParseError("line " + std::to_string(inc.line) + ": copy loop increments the literal '" + lit_tokens[inc.lit_dst] +
+                                     "' that is not the address of its " + (k ? "store" : "load"));
+                const int r = reg(lit_tokens[inc.lit_dst] + (k ? "@dst" : "@src") + std::to_string(inc.line));
+                auto to_reg = [&](Operand &o) { o.kind = K_REG; o.val = r; o.tok = -1; };
+                to_reg(user.args[ai]);
+                to_reg(inc.args[0]);
+                inc.dst = r;
+                if (peeled) {
+                    Ins &p = I[end + 1 + k];
+                    const int pi = k ? 1 : ga;
+                    if ((int)p.args.size() > pi && p.args[pi].tok == inc.lit_dst) to_reg(p.args[pi]);
+                }
+                inits.push_back({L, r, inc.lit_dst});
+                inc.lit_dst = -1;
+            }
+        }
+        for (const Ins &in : I)
+            if (in.lit_dst >= 0)
+                throw ParseError("line " + std::to_string(in.line) + ": assignment to the literal operand '" + lit_tokens[in.lit_dst] +
+                                 "' outside a loop of the copy-loop shape (store_bucket.rs:1016-1035)");
+        // initialisations, inserted from the back so that earlier loop indices stay valid
+        std::stable_sort(inits.begin(), inits.end(), [](const Init &x, const Init &y) { return x.loop > y.loop; });
+        for (const Init &p : inits) {
+            Ins mv;
+            mv.op = OP_MOV;
+            mv.dst = p.reg;
+            mv.line = I[p.loop].line;
+            Operand o;
+            uint8_t kind;
+            int64_t val;
+            simple_operand(lit_tokens[p.tok], kind, val);
+            o.kind = kind;
+            o.val = val;
+            mv.args.push_back(o);
+            I.insert(I.begin() + p.loop, mv);
+        }
+    }
+
+    // nearest instruction before pc that assigns register r (-1: none)
+    static int def_before(const Code &c, int pc, int r) {
+        for (int k = pc - 1; k >= 0; k--)
+            if (c.ins[k].dst == r) return k;
+        return -1;
+    }
+
+    // multi-element return whose operand is the loaded first element (return_bucket.rs:131): keep the load's address
+    static void link_returns(Code &c) {
+        for (int pc = 0; pc < (int)c.ins.size(); pc++) {
+            Ins &in = c.ins[pc];
+            if (in.op != OP_RETURN || in.scalar_return || in.args.empty() || in.args[0].kind != K_REG) continue;
+            const int d = def_before(c, pc, (int)in.args[0].val);
+            if (d >= 0 && c.ins[d].op == OP_FF_LOAD) {
+                in.ret_from_load = true;
+                in.args.resize(2);
+                in.args.push_back(c.ins[d].args.at(0));
+            }
+        }
+    }
+
+    // the emitter's array-equality shape (compute_bucket.rs:538-586) -> OP_ARRAY_EQ
+    void fix_array_eq(Code &c) {
+        auto is_reg = [](const Operand &o, int r) { return o.kind == K_REG && o.val == r; };
+        auto is_lit1 = [](const Operand &o) { return o.kind == K_I64 && o.val == 1; };
+        for (int i = 0; i + 12 < (int)c.ins.size(); i++) {
+            std::vector<Ins> &I = c.ins;
+            if (I[i].op != OP_MOV || I[i].args.size() != 1 || I[i].args[0].kind != K_I64) continue;
+            const int cnt = I[i].dst;
+            if (I[i + 1].op != OP_LOOP || I[i + 2].op != OP_IF || !is_reg(I[i + 2].args.at(0), cnt)) continue;
+            if (I[i + 3].op != OP_FF_EQ || I[i + 3].args.size() != 2 || I[i + 3].args[0].kind != K_REG || I[i + 3].args[1].kind != K_REG) continue;
+            const int ra = (int)I[i + 3].args[0].val, rb = (int)I[i + 3].args[1].val, r2 = I[i + 3].dst;
+            if (I[i + 4].op != OP_IF || !is_reg(I[i + 4].args.at(0), r2)) continue;
+            if (I[i + 5].op != OP_I64_SUB || I[i + 5].dst != cnt || !is_reg(I[i + 5].args.at(0), cnt) || !is_lit1(I[i + 5].args.at(1))) continue;
+            if (I[i + 6].op != OP_I64_ADD || I[i + 6].dst != ra || !is_reg(I[i + 6].args.at(0), ra) || !is_lit1(I[i + 6].args.at(1))) continue;
+            if (I[i + 7].op != OP_I64_ADD || I[i + 7].dst != rb || !is_reg(I[i + 7].args.at(0), rb) || !is_lit1(I[i + 7].args.at(1))) continue;
+            if (I[i + 8].op != OP_CONTINUE || I[i + 9].op != OP_END || I[i + 10].op != OP_END || I[i + 11].op != OP_BREAK || I[i + 12].op != OP_END) continue;
+            const int da = def_before(c, i, ra), db = def_before(c, i, rb);
+            auto is_load = [](uint16_t op) { return op == OP_FF_LOAD || op == OP_GET_SIGNAL || op == OP_GET_CMP_SIGNAL; };
+            if (da < 0 || db < 0 || !is_load(I[da].op) || !is_load(I[db].op))
+                throw ParseError("line " + std::to_string(I[i].line) + ": array-equality loop (compute_bucket.rs:538-586) whose operands are not loads");
+            // the consumer reads the register allocated two before the one the loop writes (fresh_var order: result, counter,
+            // inner result; cvm_elements/mod.rs:202-206)
+            std::string n2;
+            for (auto &kv : c.regmap)
+                if (kv.second == r2) n2 = kv.first;
+            if (n2.rfind("x_", 0) != 0 || !is_int_token(n2.substr(2)) || atoll(n2.c_str() + 2) < 2)
+                throw ParseError("line " + std::to_string(I[i].line) + ": array-equality loop with an unexpected result register " + n2);
+            Ins eq;
+            eq.op = OP_ARRAY_EQ;
+            eq.line = I[i].line;
+            eq.dst = reg("x_" + std::to_string(atoll(n2.c_str() + 2) - 2));
+            auto addr_of = [&](int d, Operand &addr, Operand &cmp) {
+                if (I[d].op == OP_GET_CMP_SIGNAL) { cmp = I[d].args.at(0); addr = I[d].args.at(1); }
+                else addr = I[d].args.at(0);
+            };
+            Operand aa, ca, ab, cb;
+            addr_of(da, aa, ca);
+            addr_of(db, ab, cb);
+            eq.args = {aa, ca, ab, cb};
+            eq.cc[0] = I[da].op;
+            eq.cc[1] = I[db].op;
+            eq.cc[2] = I[i].args[0].val;
+            I.erase(I.begin() + i, I.begin() + i + 13);
+            I.insert(I.begin() + i, eq);
+        }
+    }
+
+  public:
+    // Component creation recovered from the generated <circuit>.cpp (see the header comment).  Call after parse_text /
+    // before the program is used: it (re)links the units it touches.
+    void recover_creates(const std::string &cpp) {
+        size_t pos = 0;
+        Code *unit = nullptr;
+        std::vector<Ins> found;
+        auto flush = [&]() {
+            if (unit && !found.empty()) {
+                bool has = false;
+                for (const Ins &in : unit->ins) has = has || in.op == OP_CREATE_CMP;
+                if (!has) {
+                    unit->ins.insert(unit->ins.begin(), found.begin(), found.end());
+                    link(*unit);
+                }
+            }
+            found.clear();
+        };
+        auto num_after = [](const std::string &line, const std::string &key, int64_t &out) -> bool {
+            size_t p = line.find(key);
+            if (p == std::string::npos) return false;
+            out = atoll(line.c_str() + p + key.size());
+            return true;
+        };
+        int64_t multi_slot = -1, multi_cmp = 0, multi_sig = 0, multi_n = 0, sig_jump = 0, cmp_jump = 0;
+        std::string multi_sym;
+        bool in_multi = false;
+        while (pos < cpp.size()) {
+            size_t e = cpp.find('\n', pos);
+            if (e == std::string::npos) e = cpp.size();
+            std::string line = cpp.substr(pos, e - pos);
+            pos = e + 1;
+            size_t b = line.find_first_not_of(" \t\r");
+            if (b == std::string::npos) continue;
+            line = line.substr(b);
+            if (line.rfind("void ", 0) == 0) {
+                flush();
+                unit = nullptr;
+                in_multi = false;
+                size_t q = line.find("_run(uint ctx_index");
+                if (q != std::string::npos) {
+                    auto it = prog.code_index.find(line.substr(5, q - 5));
+                    if (it != prog.code_index.end() && !prog.codes[it->second].is_function) unit = &prog.codes[it->second];
+                }
+                continue;
+            }
+            if (!unit) continue;
+            int64_t v;
+            if (line.rfind("uint aux_create = ", 0) == 0) {
+                in_multi = true;
+                multi_slot = atoll(line.c_str() + 18);
+                multi_sym.clear();
+                sig_jump = cmp_jump = 0;
+                continue;
+            }
+            if (line.rfind("uint aux_positions", 0) == 0)
+                throw ParseError("component arrays with undefined positions are not supported by the .cpp recovery (" + unit->header + ")");
+            if (in_multi) {
+                if (line.rfind("int aux_cmp_num = ", 0) == 0) multi_cmp = atoll(line.c_str() + 18);
+                else if (num_after(line, "uint csoffset = mySignalStart+", v)) multi_sig = v;
+                else if (num_after(line, "for (uint i = 0; i < ", v)) multi_n = v;
+                else if (num_after(line, "csoffset += ", v)) sig_jump = v;
+                else if (num_after(line, "aux_cmp_num += ", v)) {
+                    cmp_jump = v;
+                    Ins in;
+                    in.op = OP_CREATE_CMP;
+                    in.cc[0] = multi_slot; in.cc[1] = multi_sig; in.cc[2] = sig_jump; in.cc[3] = multi_cmp; in.cc[4] = cmp_jump; in.cc[5] = multi_n;
+                    auto it = prog.code_index.find(multi_sym);
+                    if (it == prog.code_index.end()) throw ParseError("unknown template " + multi_sym + " in the generated C++");
+                    in.target = it->second;
+                    found.push_back(in);
+                    in_multi = false;
+                } else {
+                    size_t q = line.find("_create(csoffset,aux_cmp_num,");
+                    if (q != std::string::npos) multi_sym = line.substr(0, q);
+                }
+                continue;
+            }
+            size_t q = line.find("_create(mySignalStart+");
+            if (q != std::string::npos) {
+                // <Sym>_create(mySignalStart+<sig>,<cmp>+ctx_index+1,ctx,new_cmp_name,myId);  followed by mySubcomponents[<slot>] = ...
+                Ins in;
+                in.op = OP_CREATE_CMP;
+                in.cc[1] = atoll(line.c_str() + q + 22);
+                size_t comma = line.find(',', q);
+                in.cc[3] = comma == std::string::npos ? 0 : atoll(line.c_str() + comma + 1);
+                in.cc[5] = 1;
+                auto it = prog.code_index.find(line.substr(0, q));
+                if (it == prog.code_index.end()) throw ParseError("unknown template " + line.substr(0, q) + " in the generated C++");
+                in.target = it->second;
+                in.cc[0] = -1;
+                found.push_back(in);
+                continue;
+            }
+            if (!found.empty() && found.back().cc[0] == -1 && num_after(line, "mySubcomponents[", v)) found.back().cc[0] = v;
+        }
+        flush();
+    }
+
+  private:
 
     static void link(Code &c) {
         struct Fr_ { int kind, start, els; };

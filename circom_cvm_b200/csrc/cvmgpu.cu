@@ -214,6 +214,40 @@ extern "C" int cvmgpu_program_load(const char *cvm_path, uint32_t n_slots, cvmgp
     return build_program(parser, n_slots, out);
 }
 
+extern "C" int cvmgpu_program_load_with_cpp(const char *cvm_path, const char *cpp_path, uint32_t n_slots, cvmgpu_program **out) {
+    if (!cvm_path || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvm::Parser parser;
+    try {
+        parser.parse_file(cvm_path);
+        if (cpp_path) {
+            std::ifstream f(cpp_path);
+            if (!f) return fail(CVMGPU_ERR_IO, std::string("cannot open ") + cpp_path);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            parser.recover_creates(ss.str());
+        }
+    } catch (const cvm::ParseError &e) {
+        std::string m = e.what();
+        return fail(m.rfind("cannot open", 0) == 0 ? CVMGPU_ERR_IO : CVMGPU_ERR_PARSE, m);
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    return build_program(parser, n_slots, out);
+}
+
+extern "C" int cvmgpu_program_load_text2(const char *cvm_text, size_t len, const char *cpp_text, size_t cpp_len, uint32_t n_slots,
+                                         cvmgpu_program **out) {
+    if (!cvm_text || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvm::Parser parser;
+    try {
+        parser.parse_text(std::string(cvm_text, len));
+        if (cpp_text) parser.recover_creates(std::string(cpp_text, cpp_len));
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    return build_program(parser, n_slots, out);
+}
+
 extern "C" int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32_t n_slots, cvmgpu_program **out) {
     if (!cvm_text || !out) return fail(CVMGPU_ERR_ARG, "null argument");
     cvm::Parser parser;

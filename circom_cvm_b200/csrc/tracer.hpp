@@ -877,7 +877,8 @@ class Tracer {
                     if (in.scalar_return) {
                         set_lvar(*ret->frame, ret->addr, ref_av(field_ref(val(f, in.args.at(0)))));
                     } else {
-                        int64_t src = int_of(val(f, in.args.at(0)), "return address");
+                        // (the emitter passes the loaded first element; the parser kept that load's address: link_returns)
+                        int64_t src = int_of(val(f, in.args.at(in.ret_from_load ? 2 : 0)), "return address");
                         int64_t n = std::min(int_of(val(f, in.args.at(1)), "return size"), ret->size);
                         for (int64_t k = 0; k < n; k++) {
                             auto it = f.lvar.find(src + k);
@@ -895,6 +896,35 @@ class Tracer {
                         ret->returned = ret->returned == NO_REF ? p : emit(T_LOR, ret->returned, p);
                     }
                     pc = stop;
+                    break;
+                }
+                case OP_ARRAY_EQ: {
+                    // conjunction of the element-wise equalities (what the C++ twin computes, compute_bucket.rs:375-407)
+                    stats.ref_field_ops++;
+                    int64_t base[2];
+                    for (int k = 0; k < 2; k++) {
+                        const uint16_t lop = (uint16_t)in.cc[k];
+                        base[k] = int_of(val(f, in.args.at(2 * k)), "array address");
+                        if (lop == OP_GET_SIGNAL) base[k] += comps[(size_t)ci].start;
+                        else if (lop == OP_GET_CMP_SIGNAL) base[k] += sub_of(ci, val(f, in.args.at(2 * k + 1))).start;
+                    }
+                    uint32_t acc = NO_REF;
+                    for (int64_t j = 0; j < in.cc[2]; j++) {
+                        uint32_t v[2];
+                        for (int k = 0; k < 2; k++) {
+                            if ((uint16_t)in.cc[k] == OP_FF_LOAD) {
+                                auto it = f.lvar.find(base[k] + j);
+                                v[k] = it == f.lvar.end() ? (CONST_FLAG | c_zero) : field_ref(it->second);
+                            } else {
+                                if (base[k] + j < 0 || base[k] + j >= (int64_t)sig.size()) throw TraceError("signal index out of range");
+                                v[k] = field_ref(sig[(size_t)(base[k] + j)]);
+                            }
+                        }
+                        const uint32_t e = emit(T_EQ, v[0], v[1]);
+                        acc = acc == NO_REF ? e : emit(T_LAND, acc, e);
+                    }
+                    set_reg(f, in.dst, ref_av(acc == NO_REF ? (CONST_FLAG | c_one) : acc));
+                    pc++;
                     break;
                 }
                 case OP_MAPPED_UNSUPPORTED:

@@ -125,6 +125,13 @@ void cvmgpu_release_buffers(void);
 /* Parse + trace-compile a .cvm file.  n_slots = 0 picks the default.  Works without a GPU. */
 int cvmgpu_program_load(const char *cvm_path, uint32_t n_slots, cvmgpu_program **out);
 int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32_t n_slots, cvmgpu_program **out);
+/* The fork's --cvm emitter prints nothing for component creation (create_component_bucket.rs:356-360).  Either compile
+ * with patches/create_component_bucket.rs.diff (adds one `;;%%create_cmp` comment line per bucket), or pass the generated
+ * <circuit>.cpp of the same compile here: the `<Sub>_create(...)` blocks of its `_run` bodies
+ * (create_component_bucket.rs:206-354) supply the same information.  cpp_path / cpp_text may be NULL. */
+int cvmgpu_program_load_with_cpp(const char *cvm_path, const char *cpp_path, uint32_t n_slots, cvmgpu_program **out);
+int cvmgpu_program_load_text2(const char *cvm_text, size_t len, const char *cpp_text, size_t cpp_len, uint32_t n_slots,
+                              cvmgpu_program **out);
 int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info);
 void cvmgpu_program_free(cvmgpu_program *p);
 /* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table

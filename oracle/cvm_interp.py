@@ -128,10 +128,6 @@ class Program:
                 cur.local_memory = int(t[1])
                 continue
             if len(t) >= 3 and t[1] == "=":
-                if t[0].startswith("i64.") or t[0].startswith("ff."):
-                    # emitter defect: a literal used as a mutable register has no
-                    # consistent meaning; refuse instead of guessing.
-                    raise ValueError("assignment to literal operand %r" % t[0])
                 if len(t) == 3:
                     cur.ins.append(("mov", t[0], [t[2]]))
                 else:
@@ -139,7 +135,120 @@ class Program:
             else:
                 cur.ins.append((t[0], None, t[1:]))
         for c in self.codes.values():
+            self.fix_array_eq(c)
+            self.fix_literal_registers(c)
+            self.link_returns(c)
             self.link(c)
+
+    # ---- emitter defects that are honoured (same rules as csrc/cvm_parse.hpp, written independently)
+    @staticmethod
+    def _is_literal(tok):
+        return (tok.startswith("i64.") and tok[4:].lstrip("-").isdigit()) or (tok.startswith("ff.") and tok[3:].isdigit())
+
+    @staticmethod
+    def _loops(c):
+        """-> {loop pc: end pc}, and for every pc the innermost loop whose body holds it (or None)"""
+        ends, inner, stack = {}, [], []
+        for pc, (op, _d, _a) in enumerate(c.ins):
+            inner.append(next((s for k, s in reversed(stack) if k == "loop"), None))
+            if op in ("if", "loop"):
+                stack.append((op, pc))
+            elif op == "end":
+                k, s = stack.pop()
+                if k == "loop":
+                    ends[s] = pc
+        return ends, inner
+
+    def fix_literal_registers(self, c):
+        """copy loops increment their address operands textually (store_bucket.rs:1016-1035, call_bucket.rs:975-994):
+        `i64.5 = i64.add i64.5 i64.1`.  Shape:
+            loop / if cnt / GET src / SET dest / cnt = i64.sub cnt i64.1 / src = i64.add src i64.1 / dest = i64.add dest i64.1 /
+            continue / end / break / end  [ GET src / set_cmp_input_{run,cnt_check} c dest v ]   <- peeled last element
+        The first increment means GET's address, the second SET's address (by position: both may be the same literal).  A
+        literal address becomes a fresh register, set to the literal right before `loop` and used only by GET / SET / the
+        peeled pair."""
+        if not any(d is not None and self._is_literal(d) for (_o, d, _a) in c.ins):
+            return
+        GET = {"ff.load": 0, "get_signal": 0, "get_cmp_signal": 1}
+        SET = {"ff.store": 0, "set_signal": 0, "set_cmp_input": 1, "set_cmp_input_cnt": 1, "set_cmp_input_run": 1,
+               "set_cmp_input_cnt_check": 1}
+        I = c.ins
+        inits = []
+        for L in range(len(I) - 10):
+            if I[L][0] != "loop" or I[L + 1][0] != "if" or I[L + 2][0] not in GET or I[L + 3][0] not in SET:
+                continue
+            if [x[0] for x in I[L + 4:L + 11]] != ["i64.sub", "i64.add", "i64.add", "continue", "end", "break", "end"]:
+                continue
+            end = L + 10
+            peeled = (end + 2 < len(I) and I[end + 1][0] == I[L + 2][0]
+                      and I[end + 2][0] in ("set_cmp_input_run", "set_cmp_input_cnt_check"))
+            for k in range(2):
+                op, d, a = I[L + 5 + k]
+                if not self._is_literal(d):
+                    continue
+                uop, ud, ua = I[L + 2 + k]
+                ai = (SET if k else GET)[uop]
+                if ua[ai] != d or a[0] != d:
+                    raise ValueError("copy loop increments a literal that is not the address of its load/store")
+                name = "%s@%s%d" % (d, "dst" if k else "src", L)
+                ua = list(ua)
+                ua[ai] = name
+                I[L + 2 + k] = (uop, ud, ua)
+                I[L + 5 + k] = (op, name, [name] + list(a[1:]))
+                if peeled:
+                    pop, pd, pa = I[end + 1 + k]
+                    pi = 1 if k else GET[pop]
+                    if pa[pi] == d:
+                        pa = list(pa)
+                        pa[pi] = name
+                        I[end + 1 + k] = (pop, pd, pa)
+                inits.append((L, name, d))
+        for (_o, d, _a) in I:
+            if d is not None and self._is_literal(d):
+                raise ValueError("assignment to literal operand %r outside a loop of the copy-loop shape" % d)
+        for (L, name, lit) in sorted(inits, key=lambda x: -x[0]):
+            I.insert(L, ("mov", name, [lit]))
+
+    @staticmethod
+    def link_returns(c):
+        """a multi-element return passes the VALUE of the first element (return_bucket.rs:131): use that load's address"""
+        for pc, (op, d, a) in enumerate(c.ins):
+            if op != "return" or a[1] == "1":
+                continue
+            for k in range(pc - 1, -1, -1):
+                if c.ins[k][1] == a[0]:
+                    if c.ins[k][0] == "ff.load":
+                        c.ins[pc] = (op, d, [a[0], a[1], c.ins[k][2][0]])
+                    break
+
+    @staticmethod
+    def fix_array_eq(c):
+        """the emitter's array-equality shape (compute_bucket.rs:538-586) compares the first elements, increments those
+        values as addresses and leaves the result in a register nobody reads.  It is replaced by one `array_eq`
+        instruction that computes what the C++ twin does (compute_bucket.rs:375-407) into the register the consumer
+        reads (the one allocated two before the loop's own result register)."""
+        i = 0
+        while i + 12 < len(c.ins):
+            I = c.ins
+            ok = (I[i][0] == "mov" and I[i][2][0].startswith("i64.") and I[i + 1][0] == "loop" and I[i + 2][0] == "if"
+                  and I[i + 2][2][0] == I[i][1] and I[i + 3][0] == "ff.eq" and I[i + 4][0] == "if"
+                  and I[i + 4][2][0] == I[i + 3][1] and I[i + 5][0] == "i64.sub" and I[i + 5][1] == I[i][1]
+                  and I[i + 6][0] == "i64.add" and I[i + 6][1] == I[i + 3][2][0] and I[i + 6][2] == [I[i + 3][2][0], "i64.1"]
+                  and I[i + 7][0] == "i64.add" and I[i + 7][1] == I[i + 3][2][1] and I[i + 7][2] == [I[i + 3][2][1], "i64.1"]
+                  and [x[0] for x in I[i + 8:i + 13]] == ["continue", "end", "end", "break", "end"])
+            if not ok:
+                i += 1
+                continue
+            srcs = []
+            for r in I[i + 3][2]:
+                d = next((k for k in range(i - 1, -1, -1) if I[k][1] == r), None)
+                if d is None or I[d][0] not in ("ff.load", "get_signal", "get_cmp_signal"):
+                    raise ValueError("array-equality loop whose operands are not loads")
+                srcs.append((I[d][0], list(I[d][2])))
+            r2 = I[i + 3][1]
+            assert r2.startswith("x_"), r2
+            c.ins[i:i + 13] = [("array_eq", "x_%d" % (int(r2[2:]) - 2), [srcs[0], srcs[1], int(I[i][2][0][4:])])]
+            i += 1
 
     @staticmethod
     def link(c):
@@ -308,6 +417,21 @@ class Machine:
                 pc = match[code.loop_of[pc - 1]] + 1
             elif op == "error":
                 raise WitnessError(ST_ASSERT, "error %s in %s" % (a[0], code.header))
+            elif op == "array_eq":
+                (opa, aa), (opb, ab), n_elems = a
+                cnt["ops"] += 12
+                res = 1
+                for k in range(n_elems):
+                    v = []
+                    for (lop, la) in ((opa, aa), (opb, ab)):
+                        if lop == "ff.load":
+                            v.append(lvar.get(self.val(regs, la[0]) + k, 0))
+                        elif lop == "get_signal":
+                            v.append(sig[comp.start + self.val(regs, la[0]) + k])
+                        else:
+                            v.append(sig[comp.subs[self.val(regs, la[0])].start + self.val(regs, la[1]) + k])
+                    res &= int(v[0] == v[1])
+                regs[dst] = res
             elif op == "ff.call":
                 self.call(comp, regs, lvar, a)
             elif op == "return":
@@ -315,7 +439,7 @@ class Machine:
                 if a[1] == "1":
                     dlv[daddr] = self.val(regs, a[0]) % M.Q
                 else:
-                    src = self.val(regs, a[0])
+                    src = self.val(regs, a[2] if len(a) > 2 else a[0])      # (link_returns: the address behind a loaded value)
                     for k in range(min(self.val(regs, a[1]), dsize)):
                         dlv[daddr + k] = lvar.get(src + k, 0)
                 return
@@ -357,12 +481,66 @@ class Machine:
         self.exec(fn, comp, fregs, flv, dest=(lvar, daddr, dsize))
 
 
-def load(path_or_text):
+def recover_creates(prog, cpp_text):
+    """The fork's --cvm emitter prints nothing for component creation (create_component_bucket.rs:356-360); the generated
+    <circuit>.cpp of the same compile has it: the `<Sub>_create(...)` blocks that `impl WriteC for CreateCmpBucket` prints in
+    every `_run` body (create_component_bucket.rs:206-354).  They are placed at the top of the template (creation does not
+    depend on signal values)."""
+    unit, found, multi = None, [], None
+
+    def flush():
+        if unit is not None and found and not any(i[0] == "create_cmp" for i in unit.ins):
+            unit.ins[0:0] = found
+            unit.match, unit.loop_of = {}, {}
+            Program.link(unit)
+    for raw in cpp_text.split("\n"):
+        line = raw.strip()
+        if line.startswith("void "):
+            flush()
+            unit, found, multi = None, [], None
+            m = re.match(r"void (\w+)_run\(uint ctx_index", line)
+            if m and m.group(1) in prog.codes and not prog.codes[m.group(1)].is_function:
+                unit = prog.codes[m.group(1)]
+            continue
+        if unit is None:
+            continue
+        m = re.match(r"uint aux_create = (\d+);", line)
+        if m:
+            multi = {"slot": int(m.group(1))}
+            continue
+        if line.startswith("uint aux_positions"):
+            raise NotImplementedError("component arrays with undefined positions")
+        if multi is not None:
+            for key, pat in (("cmp", r"int aux_cmp_num = (\d+)\+ctx_index\+1;"), ("sig", r"uint csoffset = mySignalStart\+(\d+);"),
+                             ("n", r"for \(uint i = 0; i < (\d+); i\+\+\) \{"), ("sj", r"csoffset \+= (\d+) ;"),
+                             ("sym", r"(\w+)_create\(csoffset,aux_cmp_num,"), ("cj", r"aux_cmp_num \+= (\d+);")):
+                m = re.match(pat, line)
+                if m:
+                    multi[key] = m.group(1)
+            if "cj" in multi:
+                found.append(("create_cmp", None, [multi["slot"], multi["sym"], int(multi["sig"]), int(multi["sj"]), int(multi["cmp"]),
+                                                   int(multi["cj"]), int(multi["n"])]))
+                multi = None
+            continue
+        m = re.match(r"(\w+)_create\(mySignalStart\+(\d+),(\d+)\+ctx_index\+1,", line)
+        if m:
+            found.append(("create_cmp", None, [None, m.group(1), int(m.group(2)), 0, int(m.group(3)), 0, 1]))
+            continue
+        m = re.match(r"mySubcomponents\[(\d+)\] = ", line)
+        if m and found and found[-1][2][0] is None:
+            found[-1][2][0] = int(m.group(1))
+    flush()
+
+
+def load(path_or_text, cpp_text=None):
     text = path_or_text
     if "\n" not in path_or_text:
         with open(path_or_text) as f:
             text = f.read()
-    return Program(text)
+    prog = Program(text)
+    if cpp_text is not None:
+        recover_creates(prog, cpp_text)
+    return prog
 
 
 def compute_witness(prog, inputs):

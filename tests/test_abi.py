@@ -34,11 +34,13 @@ def test_load_errors_are_codes_not_aborts(cvmlib, tmp_path):
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_path=str(bad))
     assert e.value.code == -2
+    # a literal assigned to inside a copy loop is what the real emitter prints (store_bucket.rs:1026-1028) and loads
+    # (tests/test_faithful_cvm.py); outside any loop it has no meaning
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text="%%prime 21888242871839275222246405745257275088548364400416034343698204186575808495617\n"
                                      "%%signals 2\n%%start T_0\n%%witness 0 1\n%%template T_0 [ ] [ ff 0 ] [1] [0]\n"
                                      "i64.3 = i64.add i64.3 i64.1\n")
-    assert e.value.code == -2 and "literal" in str(e.value)
+    assert e.value.code == -2 and "outside a loop" in str(e.value)
     with pytest.raises(E.CvmGpuError) as e:
         E.R1cs(str(tmp_path / "missing.r1cs"))
     assert e.value.code == -1

@@ -47,6 +47,13 @@ def compile_circuit(main_fn, args=(), public=(), functions=(), name=None, o1=Tru
     return art
 
 
+def faithful_cvm(art):
+    """The same program printed exactly as the fork's --cvm emitters print it, defects included (emit_cvm.py): no component
+    creation, literal addresses assigned to, the defective array-equality and multi-element return shapes.  Loadable
+    together with the generated C++ (emit_cpp), which carries the component creation."""
+    return emit_cvm(art.compiled, faithful=True)
+
+
 def _indices(dims, flat):
     out = []
     for d in reversed(dims):

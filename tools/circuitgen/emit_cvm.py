@@ -1,7 +1,11 @@
 """Print the bucket IR as Circom-Virtual-Machine text, in the shapes of the reference's
 `impl WriteCVM` emitters (file:line cited per function).  Fixture tooling only.
 
-Two documented departures from what the fork's emitter prints today:
+Two modes.  faithful=True prints EXACTLY what the fork's emitters print, defects included: nothing for
+component creation, literal addresses assigned to in copy loops, the array-equality loop that increments values as
+addresses and returns a register nobody writes, the first element's value as the operand of a multi-element return.
+The product's parser (csrc/cvm_parse.hpp) and the oracle honour each of these; component creation then comes from the
+generated .cpp (cvmgpu_program_load_with_cpp).  The default mode keeps the departures the first round introduced:
   * CreateCmp emits nothing in the reference (create_component_bucket.rs:356-360), which makes
     a .cvm file non-executable on its own.  We emit one extension line per bucket,
         ;;%%create_cmp <slot> $<header> <sig_off> <sig_jump> <cmp_off> <cmp_jump> <n>
@@ -37,7 +41,8 @@ def declare_variable(dims):        # cvm_code_generator.rs:1770-1783
 
 
 class CvmEmitter:
-    def __init__(self, compiled):
+    def __init__(self, compiled, faithful=False):
+        self.faithful = faithful
         self.c = compiled
         self.var_no = 0
         self.out = []
@@ -112,6 +117,25 @@ class CvmEmitter:
         they were addresses, so its output cannot be executed.  We emit what the C++ twin computes
         (compute_bucket.rs:430-455: a loop of Fr_eq over both arrays): a counted loop over address
         registers that ANDs the per-element results, without the data-dependent early exit."""
+        if self.faithful:
+            # compute_bucket.rs:471-489, 538-586 verbatim: the operands are the LOADED first elements; `res` (returned) is
+            # allocated first and never written, the loop writes the third fresh variable
+            ins = [";; compute bucket"]
+            vres = []
+            for a in n.args:
+                i2, r = self.expr(a)
+                ins += i2
+                vres.append(r)
+            ins.append(";; OP(EQ)")
+            res = self.fresh()
+            counter = self.fresh()
+            res2 = self.fresh()
+            ins.append("%s = i64.%d" % (counter, size))
+            ins += ["loop", "if %s " % counter, "%s = ff.eq %s" % (res2, " ".join(vres)), "if %s " % res2,
+                    "%s = i64.sub %s i64.1" % (counter, counter), "%s = i64.add %s i64.1" % (vres[0], vres[0]),
+                    "%s = i64.add %s i64.1" % (vres[1], vres[1]), "continue", "end", "end", "break", "end",
+                    ";; end of compute bucket"]
+            return ins, res
         ins = [";; compute bucket"]
         locs = []
         for a in n.args:
@@ -181,19 +205,19 @@ class CvmEmitter:
         ins.append(";; end of store bucket")
         return ins
 
-    def _copy_loop(self, st, counter, n, get_src, src_value, sloc, vcmp, vloc):
+    def _copy_loop(self, st, counter, n, get_src, src_value, sloc, vcmp, vloc, call=False):
         """counter loop of single-element copies; the last element of a Last/Unknown sub-component
         input is peeled out so that only it can trigger the run (store_bucket.rs:944-1035)."""
         ins = []
         # The reference emitter increments its address operands textually, so a literal address
         # yields `i64.5 = i64.add i64.5 i64.1` (store_bucket.rs:1026-1028).  We materialise literal
         # addresses into fresh registers first, which is what that code means.
-        if not sloc.startswith("x_"):
+        if not self.faithful and not sloc.startswith("x_"):
             r = self.fresh()
             ins.append("%s = %s" % (r, sloc))
             get_src = get_src.replace(" " + sloc, " " + r) if get_src.endswith(" " + sloc) else get_src
             sloc = r
-        if not vloc.startswith("x_"):
+        if not self.faithful and not vloc.startswith("x_"):
             r = self.fresh()
             ins.append("%s = %s" % (r, vloc))
             vloc = r
@@ -212,7 +236,12 @@ class CvmEmitter:
             last_out = True
             set_dest = "set_cmp_input_cnt %s %s %s" % (vcmp, vloc, src_value)
             last_ins = [get_src, "set_cmp_input_cnt_check %s %s %s" % (vcmp, vloc, src_value)]
-        ins.append("%s = i64.%d" % (counter, n - 1 if last_out else n))
+        if call and self.faithful:       # call_bucket.rs:960-972: the full size, then one subtracted for a peeled last element
+            ins.append("%s = i64.%d" % (counter, n))
+            if last_out:
+                ins.append("%s = i64.sub %s i64.1" % (counter, counter))
+        else:
+            ins.append("%s = i64.%d" % (counter, n - 1 if last_out else n))
         ins += ["loop", "if %s " % counter, get_src, set_dest,
                 "%s = i64.sub %s i64.1" % (counter, counter),
                 "%s = i64.add %s i64.1" % (sloc, sloc),
@@ -249,7 +278,7 @@ class CvmEmitter:
         get_src = "%s = ff.load %s" % (src_value, call_dest)
         counter = self.fresh()
         # call_bucket.rs:960-990: counter = size, minus one when the last element is peeled
-        loop = self._copy_loop(d, counter, d.size, get_src, src_value, call_dest, vcmp, vloc)
+        loop = self._copy_loop(d, counter, d.size, get_src, src_value, call_dest, vcmp, vloc, call=True)
         ins += loop
         ins.append("// end call bucket")
         return ins
@@ -297,6 +326,8 @@ class CvmEmitter:
             cvar = self.fresh()
             ins += ["%s = ff.eqz %s" % (cvar, avar), "if %s" % cvar, "error 0", "end", ";; end of assert bucket"]
             return ins
+        if isinstance(n, CreateCmpB) and self.faithful:
+            return []                   # create_component_bucket.rs:356-360
         if isinstance(n, CreateCmpB):
             return [";;%%%%create_cmp %d $%s %d %d %d %d %d" % (
                 n.slot, n.symbol, n.signal_offset, n.signal_offset_jump, n.component_offset,
@@ -310,7 +341,10 @@ class CvmEmitter:
                 ins += i2
                 ins.append("return %s 1" % src)
             else:
-                i2, (_c, aloc) = self.location(n.value.atype, n.value.loc, n.value.cmp)
+                if self.faithful:       # return_bucket.rs:131: the value bucket is evaluated, i.e. the first element is loaded
+                    i2, aloc = self.expr(n.value)
+                else:
+                    i2, (_c, aloc) = self.location(n.value.atype, n.value.loc, n.value.cmp)
                 ins += i2
                 vcond, final = self.fresh(), self.fresh()
                 ins += ["%s = i64.le %d destination_size" % (vcond, n.size), "if %s" % vcond,
@@ -350,5 +384,5 @@ class CvmEmitter:
         return "\n".join(o) + "\n"
 
 
-def emit_cvm(compiled):
-    return CvmEmitter(compiled).emit()
+def emit_cvm(compiled, faithful=False):
+    return CvmEmitter(compiled, faithful).emit()
