@@ -76,6 +76,7 @@ struct Ins {
     int32_t m_else = -1, m_end = -1, m_loop = -1;
     // OP_CREATE_CMP payload
     int64_t cc[6] = {0, 0, 0, 0, 0, 0};  // slot, sig_off, sig_jump, cmp_off, cmp_jump, n
+    std::vector<int64_t> positions;   // OP_CREATE_CMP of an array with undefined positions: the defined ones (else empty)
     bool scalar_return = false;
     int32_t lit_dst = -1;         // the destination is a literal token (id): resolved by fix_literal_registers
     bool ret_from_load = false;   // OP_RETURN of several elements whose operand is the VALUE loaded from args[2] (an address)
@@ -357,6 +358,8 @@ class Parser {
         in.line = lineno;
         in.cc[0] = atoll(t[1].c_str());
         for (int k = 0; k < 5; k++) in.cc[1 + k] = atoll(t[3 + k].c_str());
+        for (size_t k = 8; k < t.size(); k++)
+            if (t[k] != "|") in.positions.push_back(atoll(t[k].c_str()));
         std::string name = t[2];
         if (!name.empty() && name[0] == '$') name = name.substr(1);
         fixups.push_back({{(int)(cur - &prog.codes[0]), (int)cur->ins.size()}, name});
@@ -644,6 +647,7 @@ class Parser {
         };
         int64_t multi_slot = -1, multi_cmp = 0, multi_sig = 0, multi_n = 0, sig_jump = 0, cmp_jump = 0;
         std::string multi_sym;
+        std::vector<int64_t> multi_positions;
         bool in_multi = false;
         while (pos < cpp.size()) {
             size_t e = cpp.find('\n', pos);
@@ -668,17 +672,27 @@ class Parser {
             int64_t v;
             if (line.rfind("uint aux_create = ", 0) == 0) {
                 in_multi = true;
+                multi_positions.clear();
                 multi_slot = atoll(line.c_str() + 18);
                 multi_sym.clear();
                 sig_jump = cmp_jump = 0;
                 continue;
             }
-            if (line.rfind("uint aux_positions", 0) == 0)
-                throw ParseError("component arrays with undefined positions are not supported by the .cpp recovery (" + unit->header + ")");
+            if (in_multi && line.rfind("uint aux_positions", 0) == 0) {
+                // uint aux_positions [N]= {a,b,c};   (create_component_bucket.rs:260)
+                multi_positions.clear();
+                size_t q = line.find('{');
+                while (q != std::string::npos && q + 1 < line.size() && line[q + 1] != '}') {
+                    multi_positions.push_back(atoll(line.c_str() + q + 1));
+                    q = line.find(',', q + 1);
+                }
+                continue;
+            }
             if (in_multi) {
                 if (line.rfind("int aux_cmp_num = ", 0) == 0) multi_cmp = atoll(line.c_str() + 18);
                 else if (num_after(line, "uint csoffset = mySignalStart+", v)) multi_sig = v;
                 else if (num_after(line, "for (uint i = 0; i < ", v)) multi_n = v;
+                else if (num_after(line, "for (uint i_aux = 0; i_aux < ", v)) multi_n = v;
                 else if (num_after(line, "csoffset += ", v)) sig_jump = v;
                 else if (num_after(line, "aux_cmp_num += ", v)) {
                     cmp_jump = v;
@@ -688,6 +702,7 @@ class Parser {
                     auto it = prog.code_index.find(multi_sym);
                     if (it == prog.code_index.end()) throw ParseError("unknown template " + multi_sym + " in the generated C++");
                     in.target = it->second;
+                    in.positions = multi_positions;
                     found.push_back(in);
                     in_multi = false;
                 } else {

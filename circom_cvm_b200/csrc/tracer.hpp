@@ -787,9 +787,12 @@ class Tracer {
                     if (!preds.empty()) throw TraceError("component created under a data-dependent condition");
                     // create_component_bucket.rs:206-354: slot k -> signalStart = mine + off + k*jump
                     const cvm::Code &tc = prog.codes[(size_t)in.target];
-                    for (int64_t k = 0; k < in.cc[5]; k++) {
+                    // an array with undefined positions creates only the defined ones; signal and component offsets advance
+                    // per CREATED component, the slot is the array position (create_component_bucket.rs:258-275, 339-349)
+                    const int64_t n_create = in.positions.empty() ? in.cc[5] : (int64_t)in.positions.size();
+                    for (int64_t k = 0; k < n_create; k++) {
                         int sidx = new_comp(in.target, comps[(size_t)ci].start + in.cc[1] + k * in.cc[2]);
-                        int64_t slot = in.cc[0] + k;
+                        int64_t slot = in.cc[0] + (in.positions.empty() ? k : in.positions[(size_t)k]);
                         if (slot < 0 || slot >= (int64_t)comps[(size_t)ci].subs.size())
                             throw TraceError("create_cmp slot out of range in " + code.header);
                         comps[(size_t)ci].subs[(size_t)slot] = sidx;

@@ -94,7 +94,8 @@ class Program:
                 continue
             if line.startswith(";;%%create_cmp"):
                 t = line.split()
-                cur.ins.append(("create_cmp", None, [int(t[1]), t[2].lstrip("$")] + [int(x) for x in t[3:8]]))
+                pos = [int(x) for x in t[9:]] if len(t) > 8 else None            # "| p0 p1 ...": arrays with undefined positions
+                cur.ins.append(("create_cmp", None, [int(t[1]), t[2].lstrip("$")] + [int(x) for x in t[3:8]] + [pos]))
                 continue
             if line.startswith(";;") or line.startswith("//"):
                 continue
@@ -394,11 +395,12 @@ class Machine:
                     if sub.counter == 0:
                         self.run(sub)
             elif op == "create_cmp":
-                slot, hdr, so, sj, _co, _cj, num = a
+                slot, hdr, so, sj, _co, _cj, num = a[:7]
+                positions = a[7] if len(a) > 7 and a[7] is not None else list(range(num))
                 tcode = self.p.codes[hdr]
-                for k in range(num):
+                for k, at in enumerate(positions):       # offsets advance per created component (create_component_bucket.rs:339-349)
                     sub = Component(tcode, comp.start + so + k * sj)
-                    comp.subs[slot + k] = sub
+                    comp.subs[slot + at] = sub
                     if tcode.n_inputs == 0:                    # template.rs:326-331
                         self.run(sub)
             elif op == "if":
@@ -508,18 +510,19 @@ def recover_creates(prog, cpp_text):
         if m:
             multi = {"slot": int(m.group(1))}
             continue
-        if line.startswith("uint aux_positions"):
-            raise NotImplementedError("component arrays with undefined positions")
+        if multi is not None and line.startswith("uint aux_positions"):
+            multi["pos"] = [int(x) for x in re.findall(r"\d+", line.split("{", 1)[1])]
+            continue
         if multi is not None:
             for key, pat in (("cmp", r"int aux_cmp_num = (\d+)\+ctx_index\+1;"), ("sig", r"uint csoffset = mySignalStart\+(\d+);"),
-                             ("n", r"for \(uint i = 0; i < (\d+); i\+\+\) \{"), ("sj", r"csoffset \+= (\d+) ;"),
+                             ("n", r"for \(uint i(?:_aux)? = 0; i(?:_aux)? < (\d+); i(?:_aux)?\+\+\) \{"), ("sj", r"csoffset \+= (\d+) ;"),
                              ("sym", r"(\w+)_create\(csoffset,aux_cmp_num,"), ("cj", r"aux_cmp_num \+= (\d+);")):
                 m = re.match(pat, line)
                 if m:
                     multi[key] = m.group(1)
             if "cj" in multi:
                 found.append(("create_cmp", None, [multi["slot"], multi["sym"], int(multi["sig"]), int(multi["sj"]), int(multi["cmp"]),
-                                                   int(multi["cj"]), int(multi["n"])]))
+                                                   int(multi["cj"]), int(multi["n"]), multi.get("pos")]))
                 multi = None
             continue
         m = re.match(r"(\w+)_create\(mySignalStart\+(\d+),(\d+)\+ctx_index\+1,", line)
