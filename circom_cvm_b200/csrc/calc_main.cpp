@@ -130,10 +130,26 @@ struct JParser {
 };
 
 // ---------------------------------------------------------------- numbers -> 32-byte little-endian
-// digits in `base` -> 256-bit LE; the device reduces mod q like Fr_str2element (bn128/fr.cpp:56-62)
-void parse_number(const std::string &digits, int base, const std::string &shown, uint8_t out[32]) {
-    uint32_t limb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (digits.empty()) throw Fail("Invalid number in JSON input: " + shown);
+// digits in `base` -> the value mod q as 32 bytes LE, like Fr_str2element (bn128/fr.cpp:56-62: mpz_set_str + mpz_fdiv_r):
+// any number of digits; `negative` (only JSON numbers can be: they go through a double, main.cpp:167-172) gives q - value
+void parse_number(const std::string &digits, int base, const std::string &shown, uint8_t out[32], bool negative = false) {
+    static const uint32_t Q[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    uint32_t limb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    (void)shown;
+    auto geq_q = [&]() {
+        if (limb[8]) return true;
+        for (int k = 7; k >= 0; k--)
+            if (limb[k] != Q[k]) return limb[k] > Q[k];
+        return true;
+    };
+    auto sub_q = [&]() {
+        uint64_t borrow = 0;
+        for (int k = 0; k < 9; k++) {
+            uint64_t d = (uint64_t)limb[k] - (k < 8 ? Q[k] : 0u) - borrow;
+            limb[k] = (uint32_t)d;
+            borrow = (d >> 32) & 1;
+        }
+    };
     for (char ch : digits) {
         int d;
         if (ch >= '0' && ch <= '9') d = ch - '0';
@@ -142,12 +158,24 @@ void parse_number(const std::string &digits, int base, const std::string &shown,
         else d = 99;
         if (d >= base) throw Fail("Invalid number in JSON input: " + shown);
         uint64_t carry = (uint64_t)d;
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 9; k++) {
             uint64_t t = (uint64_t)limb[k] * (uint64_t)base + carry;
             limb[k] = (uint32_t)t;
             carry = t >> 32;
         }
-        if (carry) throw Fail("number does not fit 256 bits: " + shown);
+        while (geq_q()) sub_q();     // value < q before the step, so < 16 q + 16 after it
+    }
+    if (negative) {
+        bool zero = true;
+        for (int k = 0; k < 8; k++) zero = zero && limb[k] == 0;
+        if (!zero) {
+            uint64_t borrow = 0;
+            for (int k = 0; k < 8; k++) {
+                uint64_t d = (uint64_t)Q[k] - limb[k] - borrow;
+                limb[k] = (uint32_t)d;
+                borrow = (d >> 32) & 1;
+            }
+        }
     }
     memcpy(out, limb, 32);
 }
@@ -166,8 +194,9 @@ void json_number(const JVal &v, uint8_t out[32]) {   // json2FrElements, main.cp
         char buf[400];
         snprintf(buf, sizeof buf, "%.0f", strtod(v.text.c_str(), nullptr));
         std::string t = buf;
-        if (!t.empty() && t[0] == '-') throw Fail("Invalid number in JSON input: " + t);
-        return parse_number(t, 10, t, out);
+        const bool neg = !t.empty() && t[0] == '-';
+        if (t.find_first_not_of("-0123456789") != std::string::npos) throw Fail("Invalid number in JSON input: " + t);   // inf / nan
+        return parse_number(neg ? t.substr(1) : t, 10, t, out, neg);
     }
     throw Fail("Invalid JSON type");
 }

@@ -10,6 +10,8 @@
 #include <cmath>
 #include <initializer_list>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <string>
 #include <vector>
@@ -68,9 +70,13 @@ struct cvmgpu_program {
     uint64_t n_signals = 0;
     uint32_t n_inputs = 0, n_outputs = 0;
     uint64_t layout_id = 0;          // identifies this program's value-store layout (r1cs bindings are cached against it)
-    // device copies (uploaded on first use on the current device)
-    int device = -1;
-    DevBuf d_tape, d_consts, d_wire_loc, d_iconsts;
+    // device copies of the tables, one set per device the program has run on (uploaded on first use there)
+    struct Dev {
+        DevBuf d_tape, d_consts, d_wire_loc, d_iconsts;
+        bool ready = false;
+    };
+    std::map<int, Dev> dev;
+    std::mutex mu;
 };
 
 // the CSR of an .r1cs bound to one value-store layout (r1cs.hpp bind), on the device
@@ -85,9 +91,22 @@ struct BoundDev {
 
 struct cvmgpu_r1cs {
     r1cs::File file;
-    int device = -1;
-    DevBuf d_coefs, d_cmag, d_cint, d_store, d_wtns, d_bad;
-    BoundDev plain, typed;           // typed: the binding to the last program layout used (re-bound when it changes)
+    // per device: the coefficient tables, the CSR bound to the plain layout and to the last program layout used there
+    // (re-bound when it changes), and the buffers of the host entry point
+    struct Dev {
+        DevBuf d_coefs, d_cmag, d_cint, d_store, d_wtns, d_bad;
+        BoundDev plain, typed;
+        bool ready = false;
+        void release() {
+            d_coefs.release(); d_cmag.release(); d_cint.release(); d_store.release(); d_wtns.release(); d_bad.release();
+            plain.release(); typed.release();
+            ready = false;
+        }
+    };
+    std::map<int, Dev> dev;
+    std::mutex mu;
+    // counters of the most recent typed binding (cvmgpu_r1cs_info_get)
+    uint64_t last_macs = 0, last_bit_adds = 0, last_int = 0, last_bterms = 0, last_fterms = 0, last_tcons = 0;
 };
 
 static uint64_t g_next_layout_id = 1;
@@ -348,16 +367,18 @@ extern "C" int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **
 }
 
 // device buffers belong to the device they were allocated on: release them there
-static void release_on(int device, std::initializer_list<DevBuf *> bufs) {
+template <class F>
+static void on_device(int device, F &&fn) {
     int cur = -1;
     bool sw = device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
-    for (DevBuf *b : bufs) b->release();
+    fn();
     if (sw) cudaSetDevice(cur);
 }
 
 extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
     if (!p) return;
-    release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc, &p->d_iconsts});
+    for (auto &kv : p->dev)
+        on_device(kv.first, [&] { kv.second.d_tape.release(); kv.second.d_consts.release(); kv.second.d_wire_loc.release(); kv.second.d_iconsts.release(); });
     release_pipe_buffers();
     delete p;
 }
@@ -371,30 +392,33 @@ static size_t tape_smem(const cvmgpu_program *p, uint32_t nt) {
     return tape_field_smem_per_witness(p) * nt + (((size_t)p->tape.n_bslots * (nt / 32) * 4 + 15) & ~(size_t)15);
 }
 
-static int upload_program(cvmgpu_program *p) {
+// the program's tables on the current device (uploaded on first use there)
+static int upload_program(cvmgpu_program *p, cvmgpu_program::Dev **out) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (p->device == dev && p->d_tape.p) return CVMGPU_OK;
-    if (p->device != dev) release_on(p->device, {&p->d_tape, &p->d_consts, &p->d_wire_loc, &p->d_iconsts});
+    std::lock_guard<std::mutex> lock(p->mu);
+    cvmgpu_program::Dev &d = p->dev[dev];
+    *out = &d;
+    if (d.ready) return CVMGPU_OK;
     size_t tb = (p->tape.ins.size() + TAPE_PAD) * sizeof(tape::TapeIns);
     size_t cb = std::max<size_t>(32, p->consts_mont.size() * sizeof(fr::Fr));
-    if (int rc = p->d_tape.ensure(tb)) return rc;
-    if (int rc = p->d_consts.ensure(cb)) return rc;
-    if (int rc = p->d_wire_loc.ensure(std::max<size_t>(4, p->tape.wire_loc.size() * 4))) return rc;
-    CUDA_TRY(cudaMemset(p->d_tape.p, 0, tb));   // the padding: T_NOP
+    if (int rc = d.d_tape.ensure(tb)) return rc;
+    if (int rc = d.d_consts.ensure(cb)) return rc;
+    if (int rc = d.d_wire_loc.ensure(std::max<size_t>(4, p->tape.wire_loc.size() * 4))) return rc;
+    CUDA_TRY(cudaMemset(d.d_tape.p, 0, tb));   // the padding: T_NOP
     if (!p->tape.ins.empty())
-        CUDA_TRY(cudaMemcpy(p->d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.d_tape.p, p->tape.ins.data(), p->tape.ins.size() * sizeof(tape::TapeIns), cudaMemcpyHostToDevice));
     if (!p->consts_mont.empty())
-        CUDA_TRY(cudaMemcpy(p->d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
-    if (int rc = p->d_iconsts.ensure(std::max<size_t>(8, p->tape.iconsts.size() * 8))) return rc;
+        CUDA_TRY(cudaMemcpy(d.d_consts.p, p->consts_mont.data(), p->consts_mont.size() * sizeof(fr::Fr), cudaMemcpyHostToDevice));
+    if (int rc = d.d_iconsts.ensure(std::max<size_t>(8, p->tape.iconsts.size() * 8))) return rc;
     if (!p->tape.iconsts.empty())
-        CUDA_TRY(cudaMemcpy(p->d_iconsts.p, p->tape.iconsts.data(), p->tape.iconsts.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.d_iconsts.p, p->tape.iconsts.data(), p->tape.iconsts.size() * 8, cudaMemcpyHostToDevice));
     if (!p->tape.wire_loc.empty())
-        CUDA_TRY(cudaMemcpy(p->d_wire_loc.p, p->tape.wire_loc.data(), p->tape.wire_loc.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.d_wire_loc.p, p->tape.wire_loc.data(), p->tape.wire_loc.size() * 4, cudaMemcpyHostToDevice));
     // the tables are read by kernels on non-blocking streams, which do not order themselves after the copies above
     // (pageable-memory copies may return once the data is staged)
     CUDA_TRY(cudaDeviceSynchronize());
-    p->device = dev;
+    d.ready = true;
     return CVMGPU_OK;
 }
 
@@ -432,17 +456,18 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     if (B == 0) return CVMGPU_OK;
     if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
     if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
-    if (int rc = upload_program(p)) return rc;
+    cvmgpu_program::Dev *pd = nullptr;
+    if (int rc = upload_program(p, &pd)) return rc;
     kern::TapeParams tp;
-    tp.tape = (const tape::TapeIns *)p->d_tape.p;
+    tp.tape = (const tape::TapeIns *)pd->d_tape.p;
     tp.n_ins = (uint32_t)p->tape.ins.size();
-    tp.consts = (const uint4 *)p->d_consts.p;
+    tp.consts = (const uint4 *)pd->d_consts.p;
     tp.store = (uint4 *)d_store;
     tp.bits = (uint32_t *)((char *)d_store + store_field_bytes(p, bstride));
     tp.bstride = bstride;
     tp.n_brows = p->tape.n_brows;
     tp.n_bslots = p->tape.n_bslots;
-    tp.iconsts = (const unsigned long long *)p->d_iconsts.p;
+    tp.iconsts = (const unsigned long long *)pd->d_iconsts.p;
     tp.inputs = (const uint4 *)d_inputs;
     tp.n_inputs = p->n_inputs;
     tp.status = (uint32_t *)d_status;
@@ -474,13 +499,13 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     return launch_tape<32, false>(tp, (unsigned)grid, smem, st);
 }
 
-static kern::StoreView store_view(const cvmgpu_program *p, const void *d_store, uint64_t bstride) {
+static kern::StoreView store_view(const cvmgpu_program *p, const cvmgpu_program::Dev *pd, const void *d_store, uint64_t bstride) {
     kern::StoreView sv;
     sv.store = (const uint4 *)d_store;
     sv.bits = (const uint32_t *)((const char *)d_store + store_field_bytes(p, bstride));
     sv.bstride = bstride;
     sv.n_brows = p->tape.n_brows;
-    sv.wire_loc = (const uint32_t *)p->d_wire_loc.p;
+    sv.wire_loc = (const uint32_t *)pd->d_wire_loc.p;
     return sv;
 }
 
@@ -489,9 +514,10 @@ extern "C" int cvmgpu_witness_export_range_dev(cvmgpu_program *p, const void *d_
     if (!p || !d_store || !d_out) return fail(CVMGPU_ERR_ARG, "null argument");
     if ((uint64_t)wire0 + n_sel > p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "wire range exceeds the witness");
     if (B == 0 || n_sel == 0) return CVMGPU_OK;
-    if (int rc = upload_program(p)) return rc;
+    cvmgpu_program::Dev *pd = nullptr;
+    if (int rc = upload_program(p, &pd)) return rc;
     dim3 grid((unsigned)((B + 31) / 32), (n_sel + 31) / 32);
-    kern::export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(store_view(p, d_store, bstride), B, wire0, n_sel, (uint4 *)d_out);
+    kern::export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(store_view(p, pd, d_store, bstride), B, wire0, n_sel, (uint4 *)d_out);
     CUDA_TRY(cudaGetLastError());
     return CVMGPU_OK;
 }
@@ -502,7 +528,7 @@ extern "C" int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store,
     return cvmgpu_witness_export_range_dev(p, d_store, B, bstride, 0, p->tape.n_wires, d_wtns, stream);
 }
 
-static int upload_r1cs(cvmgpu_r1cs *r);
+static int upload_r1cs(cvmgpu_r1cs *r, cvmgpu_r1cs::Dev **out);
 
 // largest chunk of witnesses whose buffers fit in the free device memory
 static uint64_t pick_chunk(uint64_t B, size_t bytes_per_witness) {
@@ -526,20 +552,21 @@ struct PipeBufs {
         stream = nullptr;
     }
 };
-// per host thread and device; released by cvmgpu_program_free / cvmgpu_release_buffers on the calling thread
+// one set per device, shared by the host threads (a call holds the device's lock while it uses the buffers); released by
+// cvmgpu_program_free / cvmgpu_release_buffers
 struct PipeSet {
     PipeBufs pipe[2];
-    int device = -1;
+    std::mutex mu;
 };
-static thread_local PipeSet g_pipe;
+static std::mutex g_pipes_mu;
+static std::map<int, PipeSet> g_pipes;
 
 static void release_pipe_buffers() {
-    if (g_pipe.device < 0) return;
-    int cur = -1;
-    bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != g_pipe.device && cudaSetDevice(g_pipe.device) == cudaSuccess;
-    for (auto &pb : g_pipe.pipe) pb.release();
-    if (sw) cudaSetDevice(cur);
-    g_pipe.device = -1;
+    std::lock_guard<std::mutex> lock(g_pipes_mu);
+    for (auto &kv : g_pipes) {
+        std::lock_guard<std::mutex> l2(kv.second.mu);
+        on_device(kv.first, [&] { for (auto &pb : kv.second.pipe) pb.release(); });
+    }
 }
 
 extern "C" void cvmgpu_release_buffers(void) { release_pipe_buffers(); }
@@ -555,9 +582,13 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
     if (wtns_out && (uint64_t)wire0 + n_sel > p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "wire range exceeds the witness");
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
     if (!wtns_out) n_sel = 0;
-    if (int rc = upload_program(p)) return rc;
-    if (r)
-        if (int rc = upload_r1cs(r)) return rc;
+    {
+        cvmgpu_program::Dev *pd = nullptr;
+        if (int rc = upload_program(p, &pd)) return rc;
+        cvmgpu_r1cs::Dev *rd = nullptr;
+        if (r)
+            if (int rc = upload_r1cs(r, &rd)) return rc;
+    }
     const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)n_sel * 32;
     size_t per_w = (cvmgpu_store_bytes(p, 1024) + 1023) / 1024 + in_row + out_row + 8;
     uint64_t fit = pick_chunk(B, 2 * per_w);
@@ -570,11 +601,13 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
     if (B <= chunk) chunk = B;
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (g_pipe.device != dev) {
-        release_pipe_buffers();
-        g_pipe.device = dev;
+    PipeSet *ps;
+    {
+        std::lock_guard<std::mutex> lock(g_pipes_mu);
+        ps = &g_pipes[dev];
     }
-    PipeBufs *pipe = g_pipe.pipe;
+    std::lock_guard<std::mutex> pipe_lock(ps->mu);
+    PipeBufs *pipe = ps->pipe;
     const int nbuf = (B > chunk) ? 2 : 1;
     const uint64_t cstride = (chunk + 31) / 32 * 32;
     for (int k = 0; k < nbuf; k++) {
@@ -614,6 +647,53 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
         if (e != cudaSuccess && rc == CVMGPU_OK) rc = fail(CVMGPU_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     }
     return rc;
+}
+
+// Single-process multi-device driver: witnesses are independent, so the batch is cut into one contiguous slice per device
+// of the mask and each slice runs cvmgpu_witness_batch_select on its device from its own host thread (own streams, own
+// pipeline buffers, the program / constraint tables replicated per device).  No inter-device traffic at all: the
+// per-witness flags land in the caller's arrays.
+extern "C" int cvmgpu_witness_batch_multi(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t device_mask,
+                                          uint32_t wire0, uint32_t n_sel, uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    const int n_dev = cvmgpu_device_count();
+    if (n_dev <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    std::vector<int> devs;
+    for (int d = 0; d < 32; d++)
+        if ((device_mask >> d) & 1u) {
+            if (d >= n_dev) return fail(CVMGPU_ERR_ARG, "device_mask names device " + std::to_string(d) + " but only " + std::to_string(n_dev) + " are visible");
+            devs.push_back(d);
+        }
+    if (devs.empty()) return fail(CVMGPU_ERR_ARG, "empty device_mask");
+    if (B == 0) return CVMGPU_OK;
+    if (!wtns_out) n_sel = 0;
+    const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)n_sel * 32;
+    const uint64_t per = (B + devs.size() - 1) / devs.size();
+    std::vector<int> rcs(devs.size(), CVMGPU_OK);
+    std::vector<std::string> errs(devs.size());
+    std::vector<std::thread> threads;
+    int caller_dev = 0;
+    cudaGetDevice(&caller_dev);
+    for (size_t k = 0; k < devs.size(); k++) {
+        const uint64_t b0 = std::min<uint64_t>(B, k * per), n = std::min<uint64_t>(per, B - b0);
+        if (n == 0) continue;
+        threads.emplace_back([&, k, b0, n] {
+            if (cudaSetDevice(devs[k]) != cudaSuccess) {
+                rcs[k] = CVMGPU_ERR_CUDA;
+                errs[k] = "cudaSetDevice(" + std::to_string(devs[k]) + ") failed";
+                return;
+            }
+            rcs[k] = cvmgpu_witness_batch_select(p, r, inputs ? inputs + b0 * in_row : nullptr, n, wire0, n_sel,
+                                                 wtns_out ? wtns_out + b0 * out_row : nullptr, status ? status + b0 : nullptr,
+                                                 first_bad ? first_bad + b0 : nullptr);
+            if (rcs[k] != CVMGPU_OK) errs[k] = "device " + std::to_string(devs[k]) + ": " + cvmgpu_last_error();
+        });
+    }
+    for (auto &t : threads) t.join();
+    cudaSetDevice(caller_dev);
+    for (size_t k = 0; k < devs.size(); k++)
+        if (rcs[k] != CVMGPU_OK) return fail(rcs[k], errs[k]);
+    return CVMGPU_OK;
 }
 
 extern "C" int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
@@ -681,12 +761,12 @@ extern "C" int cvmgpu_r1cs_info_get(const cvmgpu_r1cs *r, cvmgpu_r1cs_info *out)
     static_assert(r1cs::LOC_BIT == tape::ROW_BIT, "row type bit mismatch");
     info->n_coefs = (uint32_t)r->file.coefs.size();
     // the binding to the last program layout this handle checked (cvmgpu_r1cs_check_store_dev / witness_batch_checked)
-    info->bound_int_constraints = r->typed.n_int_constraints;
-    info->bound_bit_terms = r->typed.n_bterms;
-    info->bound_field_terms = r->typed.layout_id == ~0ull ? 0 : r->typed.n_fterms;
-    info->bound_macs = r->typed.layout_id == ~0ull ? 0 : r->typed.macs;
-    info->bound_bit_adds = r->typed.bit_adds;
-    info->bound_table_constraints = r->typed.n_tcons;
+    info->bound_int_constraints = r->last_int;
+    info->bound_bit_terms = r->last_bterms;
+    info->bound_field_terms = r->last_fterms;
+    info->bound_macs = r->last_macs;
+    info->bound_bit_adds = r->last_bit_adds;
+    info->bound_table_constraints = r->last_tcons;
     return fill_info(out, v);
 }
 
@@ -708,13 +788,7 @@ extern "C" int cvmgpu_r1cs_bind_info(const cvmgpu_r1cs *r, const cvmgpu_program 
 
 extern "C" void cvmgpu_r1cs_free(cvmgpu_r1cs *r) {
     if (!r) return;
-    int cur = -1;
-    bool sw = r->device >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != r->device && cudaSetDevice(r->device) == cudaSuccess;
-    r->d_coefs.release(); r->d_cmag.release(); r->d_cint.release();
-    r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
-    r->plain.release();
-    r->typed.release();
-    if (sw) cudaSetDevice(cur);
+    for (auto &kv : r->dev) on_device(kv.first, [&] { kv.second.release(); });
     delete r;
 }
 
@@ -739,37 +813,31 @@ static int upload_bound(const r1cs::Bound &b, BoundDev &d) {
     return CVMGPU_OK;
 }
 
-static int upload_r1cs(cvmgpu_r1cs *r) {
+// the coefficient tables on the current device (uploaded on first use there)
+static int upload_r1cs(cvmgpu_r1cs *r, cvmgpu_r1cs::Dev **out) {
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
-    if (r->device == dev && r->d_coefs.p) return CVMGPU_OK;
-    if (r->device != dev && r->device >= 0) {
-        int cur = dev;
-        if (cudaSetDevice(r->device) == cudaSuccess) {
-            r->d_coefs.release(); r->d_cmag.release(); r->d_cint.release();
-            r->d_store.release(); r->d_wtns.release(); r->d_bad.release();
-            r->plain.release();
-            r->typed.release();
-            cudaSetDevice(cur);
-        }
-    }
+    std::lock_guard<std::mutex> lock(r->mu);
+    cvmgpu_r1cs::Dev &d = r->dev[dev];
+    *out = &d;
+    if (d.ready) return CVMGPU_OK;
     const r1cs::File &f = r->file;
     std::vector<fr::Fr> cm;
     cm.reserve(f.coefs.size());
     for (const fr::Fr &c : f.coefs) cm.push_back(fr::to_mont(c));
-    if (int rc = r->d_coefs.ensure(cm.size() * 32)) return rc;
-    if (int rc = r->d_cmag.ensure(f.cmag.size() * 4)) return rc;
-    if (int rc = r->d_cint.ensure(f.cint.size() * 8)) return rc;
-    CUDA_TRY(cudaMemcpy(r->d_cmag.p, f.cmag.data(), f.cmag.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(r->d_cint.p, f.cint.data(), f.cint.size() * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(r->d_coefs.p, cm.data(), cm.size() * 32, cudaMemcpyHostToDevice));
+    if (int rc = d.d_coefs.ensure(cm.size() * 32)) return rc;
+    if (int rc = d.d_cmag.ensure(f.cmag.size() * 4)) return rc;
+    if (int rc = d.d_cint.ensure(f.cint.size() * 8)) return rc;
+    CUDA_TRY(cudaMemcpy(d.d_cmag.p, f.cmag.data(), f.cmag.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_cint.p, f.cint.data(), f.cint.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_coefs.p, cm.data(), cm.size() * 32, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaDeviceSynchronize());
-    r->device = dev;
+    d.ready = true;
     return CVMGPU_OK;
 }
 
 // bd: the CSR bound to the layout of d_store; bits / n_brows: its bit rows (nullptr / 0 for the plain layout)
-static int launch_check(cvmgpu_r1cs *r, const BoundDev &bd, const void *d_store, const uint32_t *bits, uint64_t B,
+static int launch_check(cvmgpu_r1cs *r, const cvmgpu_r1cs::Dev &rd, const BoundDev &bd, const void *d_store, const uint32_t *bits, uint64_t B,
                         uint64_t bstride, void *d_first_bad, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(d_first_bad, 0xff, B * 4, s));
     if (r->file.n_constraints == 0) return CVMGPU_OK;
@@ -786,8 +854,8 @@ static int launch_check(cvmgpu_r1cs *r, const BoundDev &bd, const void *d_store,
     kern::R1csParams rp;
     rp.hdr = (const uint4 *)bd.d_hdr.p;
     rp.terms = (const uint2 *)bd.d_terms.p;
-    rp.coefs = (const uint4 *)r->d_coefs.p;
-    rp.cmag = (const uint32_t *)r->d_cmag.p;
+    rp.coefs = (const uint4 *)rd.d_coefs.p;
+    rp.cmag = (const uint32_t *)rd.d_cmag.p;
     rp.n_cons = r->file.n_constraints;
     rp.cons_per_chunk = per;
     rp.store = (const uint4 *)d_store;
@@ -798,7 +866,7 @@ static int launch_check(cvmgpu_r1cs *r, const BoundDev &bd, const void *d_store,
     rp.n_brows = bd.n_brows;
     rp.bhdr = (const uint4 *)bd.d_bhdr.p;
     rp.bterms = (const uint2 *)bd.d_bterms.p;
-    rp.cint = (const long long *)r->d_cint.p;
+    rp.cint = (const long long *)rd.d_cint.p;
     dim3 grid((unsigned)gx, (unsigned)chunks);
     // resident CTAs per SM: 4 (128 registers) when the check is multiplier-bound (Poseidon: 28 % of the terms have
     // full-size coefficients, EdDSA 12 %), 5 (96 registers) when it is mostly +-1 / small coefficients and latency-bound
@@ -838,13 +906,17 @@ extern "C" int cvmgpu_r1cs_check_dev(cvmgpu_r1cs *r, const void *d_store, uint64
     if (B == 0) return CVMGPU_OK;
     if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
     if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
-    if (int rc = upload_r1cs(r)) return rc;
-    if (r->plain.layout_id != 0) {
-        if (int rc = upload_bound(r1cs::bind(r->file, nullptr), r->plain)) return rc;
-        r->plain.layout_id = 0;
-        r->plain.typed = false;
+    cvmgpu_r1cs::Dev *rd = nullptr;
+    if (int rc = upload_r1cs(r, &rd)) return rc;
+    {
+        std::lock_guard<std::mutex> lock(r->mu);
+        if (rd->plain.layout_id != 0) {
+            if (int rc = upload_bound(r1cs::bind(r->file, nullptr), rd->plain)) return rc;
+            rd->plain.layout_id = 0;
+            rd->plain.typed = false;
+        }
     }
-    return launch_check(r, r->plain, d_store, nullptr, B, bstride, d_first_bad, (cudaStream_t)stream);
+    return launch_check(r, *rd, rd->plain, d_store, nullptr, B, bstride, d_first_bad, (cudaStream_t)stream);
 }
 
 extern "C" int cvmgpu_r1cs_check_store_dev(cvmgpu_r1cs *r, cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride,
@@ -854,15 +926,21 @@ extern "C" int cvmgpu_r1cs_check_store_dev(cvmgpu_r1cs *r, cvmgpu_program *p, co
     if (B == 0) return CVMGPU_OK;
     if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
     if (bstride >> 27) return fail(CVMGPU_ERR_ARG, "bstride must be below 2^27 witnesses (32-bit row stride)");
-    if (int rc = upload_r1cs(r)) return rc;
-    if (r->typed.layout_id != p->layout_id) {
-        if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow, p->tape.const_rows), r->typed)) return rc;
-        r->typed.layout_id = p->layout_id;
-        r->typed.typed = r->typed.n_bterms != 0 || r->typed.n_tcons != 0;   // no term on a bit row: the plain kernel runs on the field rows
-        r->typed.n_brows = p->tape.n_brows;
+    cvmgpu_r1cs::Dev *rd = nullptr;
+    if (int rc = upload_r1cs(r, &rd)) return rc;
+    {
+        std::lock_guard<std::mutex> lock(r->mu);
+        if (rd->typed.layout_id != p->layout_id) {
+            if (int rc = upload_bound(r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow, p->tape.const_rows), rd->typed)) return rc;
+            rd->typed.layout_id = p->layout_id;
+            rd->typed.typed = rd->typed.n_bterms != 0 || rd->typed.n_tcons != 0;   // no term on a bit row: the plain kernel runs on the field rows
+            rd->typed.n_brows = p->tape.n_brows;
+            r->last_macs = rd->typed.macs; r->last_bit_adds = rd->typed.bit_adds; r->last_int = rd->typed.n_int_constraints;
+            r->last_bterms = rd->typed.n_bterms; r->last_fterms = rd->typed.n_fterms; r->last_tcons = rd->typed.n_tcons;
+        }
     }
     const uint32_t *bits = (const uint32_t *)((const char *)d_store + store_field_bytes(p, bstride));
-    return launch_check(r, r->typed, d_store, bits, B, bstride, d_first_bad, (cudaStream_t)stream);
+    return launch_check(r, *rd, rd->typed, d_store, bits, B, bstride, d_first_bad, (cudaStream_t)stream);
 }
 
 extern "C" int cvmgpu_witness_import_dev(uint32_t n_wires, const void *d_wtns, uint64_t B, uint64_t bstride, void *d_store,
@@ -879,20 +957,21 @@ extern "C" int cvmgpu_r1cs_check(cvmgpu_r1cs *r, const uint8_t *witnesses, uint6
     if (!r || !witnesses || !first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
     if (B == 0) return CVMGPU_OK;
-    if (int rc = upload_r1cs(r)) return rc;
+    cvmgpu_r1cs::Dev *rd = nullptr;
+    if (int rc = upload_r1cs(r, &rd)) return rc;
     const size_t row = (size_t)r->file.n_wires * 32;
     uint64_t chunk = std::min<uint64_t>(pick_chunk(B, 2 * row + 4), 1u << 22);
     if (chunk == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
-    if (int rc = r->d_store.ensure((size_t)r->file.n_wires * 32 * chunk)) return rc;
-    if (int rc = r->d_wtns.ensure(row * chunk)) return rc;
-    if (int rc = r->d_bad.ensure(4 * chunk)) return rc;
+    if (int rc = rd->d_store.ensure((size_t)r->file.n_wires * 32 * chunk)) return rc;
+    if (int rc = rd->d_wtns.ensure(row * chunk)) return rc;
+    if (int rc = rd->d_bad.ensure(4 * chunk)) return rc;
     cudaStream_t s = 0;
     for (uint64_t b0 = 0; b0 < B; b0 += chunk) {
         uint64_t n = std::min<uint64_t>(chunk, B - b0);
-        CUDA_TRY(cudaMemcpyAsync(r->d_wtns.p, witnesses + b0 * row, n * row, cudaMemcpyHostToDevice, s));
-        if (int rc = cvmgpu_witness_import_dev(r->file.n_wires, r->d_wtns.p, n, chunk, r->d_store.p, s)) return rc;
-        if (int rc = cvmgpu_r1cs_check_dev(r, r->d_store.p, n, chunk, r->d_bad.p, s)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(first_bad + b0, r->d_bad.p, n * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(rd->d_wtns.p, witnesses + b0 * row, n * row, cudaMemcpyHostToDevice, s));
+        if (int rc = cvmgpu_witness_import_dev(r->file.n_wires, rd->d_wtns.p, n, chunk, rd->d_store.p, s)) return rc;
+        if (int rc = cvmgpu_r1cs_check_dev(r, rd->d_store.p, n, chunk, rd->d_bad.p, s)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(first_bad + b0, rd->d_bad.p, n * 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
     }
     return CVMGPU_OK;

@@ -30,7 +30,7 @@ EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_info_get", "cvmgpu_program_free",
     "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
-    "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_dev",
+    "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_multi", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
     "cvmgpu_wtns_write",
     "cvmgpu_r1cs_load", "cvmgpu_r1cs_info_get", "cvmgpu_r1cs_free", "cvmgpu_r1cs_check", "cvmgpu_r1cs_check_dev",
@@ -96,6 +96,7 @@ def lib():
     L.cvmgpu_program_wire_rows.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_iconsts.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_witness_batch_select.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_witness_batch_multi.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_export_range_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p]
     L.cvmgpu_r1cs_bind_info.argtypes = [c_void_p, c_void_p, POINTER(R1csInfo)]
     L.cvmgpu_r1cs_check_store_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
@@ -254,6 +255,12 @@ class WitnessCalculator:
         B = status_out.shape[0]
         _check(lib().cvmgpu_witness_batch_select(self._h, r1cs._h if r1cs is not None else None, _ptr(inputs), B, wire0, n_sel,
                                                  _ptr(wtns_out), _ptr(status_out), _ptr(first_bad_out)))
+
+    def calculate_multi_into(self, inputs, device_mask, wire0, n_sel, wtns_out, status_out, r1cs=None, first_bad_out=None):
+        """the same over several devices of this process (bit d of device_mask = CUDA device d)"""
+        B = status_out.shape[0]
+        _check(lib().cvmgpu_witness_batch_multi(self._h, r1cs._h if r1cs is not None else None, _ptr(inputs), B, device_mask, wire0,
+                                                n_sel, _ptr(wtns_out), _ptr(status_out), _ptr(first_bad_out)))
 
     def wire_rows(self):
         """uint32 per witness wire: its row in the typed value store (ROW_BIT | bit row, or field row)"""

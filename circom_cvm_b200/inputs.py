@@ -92,7 +92,10 @@ class SymInputMap(InputMap):
         return self._pos[h]
 
 
-def _parse_number(val):             # json2FrElements, main.cpp:144-190 (value mod q is taken on the device)
+Q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def _parse_number(val):             # json2FrElements, main.cpp:144-190; -> the value mod q, as Fr_str2element (mpz_fdiv_r) leaves it
     if isinstance(val, bool):
         raise InputError("Invalid JSON type")
     if isinstance(val, str):
@@ -105,14 +108,18 @@ def _parse_number(val):             # json2FrElements, main.cpp:144-190 (value m
         elif p in ("0x", "0X"):
             s, base = val[2:], 16
         digits = "0123456789abcdef"[:base] if base == 16 else "0123456789"[:base]
-        body = s[1:] if s[:1] == "-" and base == 10 else s
-        if not body or any(ch not in digits + (digits.upper() if base == 16 else "") for ch in body):
+        # check_valid_number (main.cpp:126-142): digits of the base only -- a sign is not a digit, so "-5" is rejected
+        if any(ch not in digits + (digits.upper() if base == 16 else "") for ch in s):
             raise InputError("Invalid number in JSON input: %s" % val)
-        return int(s, base)
+        return int(s, base) % Q if s else 0
+    # JSON numbers go through a double printed with no decimals (main.cpp:167-172); the sign survives and Fr_str2element
+    # reduces with a floor modulus: -5 -> q - 5
     if isinstance(val, int):
-        return int(format(float(val), ".0f")) if abs(val) >= 1 << 53 else val      # the reference goes through a double
+        return (int(format(float(val), ".0f")) if abs(val) >= 1 << 53 else val) % Q
     if isinstance(val, float):
-        return int(format(val, ".0f"))
+        if val != val or val in (float("inf"), float("-inf")):
+            raise InputError("Invalid number in JSON input: %s" % val)
+        return int(format(val, ".0f")) % Q
     raise InputError("Invalid JSON type")
 
 

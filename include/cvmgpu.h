@@ -165,6 +165,13 @@ int cvmgpu_witness_batch_checked(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_
 int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t wire0,
                                 uint32_t n_sel, uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
 
+/* Single-process multi-device driver (SURVEY 8b `device_mask`): bit d of device_mask = use CUDA device d.  The batch is
+ * cut into one contiguous slice per device; each slice runs on its device from its own host thread with its own
+ * streams and buffers (program and constraint tables are replicated per device on first use).  Witnesses are
+ * independent: there is no inter-device traffic.  Arguments otherwise as cvmgpu_witness_batch_select. */
+int cvmgpu_witness_batch_multi(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t device_mask,
+                               uint32_t wire0, uint32_t n_sel, uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
+
 /* DEVICE buffers on the current device.
  *   d_inputs  B x n_inputs x 32 B, as above
  *   d_store   typed value store of cvmgpu_store_bytes(p, bstride) bytes, B <= bstride < 2^27:

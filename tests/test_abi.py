@@ -58,3 +58,36 @@ def test_no_cpu_fallback(cvmlib):
     assert e.value.code == -4
     with pytest.raises(E.CvmGpuError):
         E.fr_device_op("mul", [1], [2])
+
+
+def test_plain_c_caller(cvmlib, tmp_path):
+    """tests/abi_smoke.c: a C program built with gcc against include/cvmgpu.h and libcvmgpu.so -- struct sizes and offsets
+    equal the ctypes twins, the info structs honour struct_size (a smaller struct of an older header is not overrun, an
+    unset size is refused), and one batch runs (or fails with CVMGPU_ERR_CUDA where there is no GPU)."""
+    import ctypes
+    import os
+    import subprocess
+
+    from circom_cvm_b200 import engine as E
+    from conftest import ROOT, circuit
+    src = os.path.join(ROOT, "tests", "abi_smoke.c")
+    exe = str(tmp_path / "abi_smoke")
+    csrc = os.path.join(ROOT, "circom_cvm_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", csrc, "-lcvmgpu",
+                           "-Wl,-rpath," + csrc, "-o", exe])
+    cvm = tmp_path / "m2.cvm"
+    cvm.write_text(circuit("multiplier2").cvm)
+    out = subprocess.run([exe, str(cvm), "3", "11"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    kv = dict(l.split(" ", 1) for l in out.stdout.strip().split("\n"))
+    assert int(kv["sizeof_program_info"]) == ctypes.sizeof(E.ProgramInfo)
+    assert int(kv["sizeof_r1cs_info"]) == ctypes.sizeof(E.R1csInfo)
+    assert int(kv["offsetof_n_wires"]) == E.ProgramInfo.n_wires.offset
+    assert int(kv["offsetof_tape_len"]) == E.ProgramInfo.tape_len.offset
+    assert int(kv["offsetof_tape_int"]) == E.ProgramInfo.tape_int.offset
+    assert int(kv["offsetof_bound_table_constraints"]) == E.R1csInfo.bound_table_constraints.offset
+    assert kv["n_wires"].startswith("4 n_inputs 2")
+    if E.device_count() > 0:
+        assert kv["batch"] == "ok status 0 product 33" and kv["multi"] == "rc 0"
+    else:
+        assert kv["batch"].startswith("rc -4") and kv["multi"] == "rc -4"

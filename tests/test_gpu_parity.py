@@ -287,6 +287,35 @@ def test_output_selector_and_typed_check_agree(E, tmp_path):
         assert (out == wt[:, wire0:wire0 + n_sel]).all() and (st2 == st).all() and (bad2 == bad).all()
 
 
+def test_multi_device_driver(E, tmp_path):
+    """cvmgpu_witness_batch_multi (one host thread + streams per device of the mask): the same answers as the single-device
+    call, on every visible device."""
+    art = circuit("poseidon2")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    _write_r1cs(art, tmp_path / "p.r1cs")
+    r = E.R1cs(str(tmp_path / "p.r1cs"))
+    rng = random.Random(33)
+    rows = [[rng.randrange(M.Q) for _ in range(2)] for _ in range(1001)]
+    wt, st, bad = wc.calculate_checked(rows, r)
+    inp = E.ints_to_le(rows, 2)
+    n_dev = E.device_count()
+    for mask in sorted({1, (1 << n_dev) - 1}):
+        wt2 = np.zeros_like(wt)
+        st2 = np.full_like(st, 7)
+        bad2 = np.zeros_like(bad)
+        wc.calculate_multi_into(inp, mask, 0, wc.n_wires, wt2, st2, r, bad2)
+        assert (wt2 == wt).all() and (st2 == st).all() and (bad2 == bad).all(), mask
+    with pytest.raises(E.CvmGpuError):
+        wc.calculate_multi_into(inp, 1 << n_dev, 0, wc.n_wires, wt2, st2, r, bad2)    # a device that is not there
+
+
+def test_plain_c_caller_on_the_gpu(tmp_path):
+    from circom_cvm_b200 import build, engine
+    from test_abi import test_plain_c_caller
+    build.build()
+    test_plain_c_caller(engine.lib(), tmp_path)
+
+
 def test_eddsa_batch(E, tmp_path):
     """Config 4 shape: EdDSAPoseidonVerifier over signatures from the integer signer, 1 in 8 forged: per-witness
     flags, witness parity with the oracle, and the R1CS check."""

@@ -29,9 +29,15 @@ def test_scalar_and_array_inputs_in_any_key_order():
 def test_number_forms_follow_json2FrElements():
     m = imap_of(circuit("multiplier2"))
     q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
-    assert row_from_json(m, {"a": str(q + 5), "b": "0X1f"}) == [q + 5, 31]        # reduced mod q on the device
+    assert row_from_json(m, {"a": str(q + 5), "b": "0X1f"}) == [5, 31]            # Fr_str2element: mpz_fdiv_r by q
     assert row_from_json(m, {"a": 2 ** 60, "b": 1.0}) == [int(format(float(2 ** 60), ".0f")), 1]   # numbers pass through a double
-    for bad in ("12a", "0b102", "", "0x", "1e5"):
+    # a negative JSON number survives the double and is reduced with a floor modulus (bn128/fr.cpp:56-62): q - 5;
+    # values of any size are reduced, never refused
+    assert row_from_json(m, {"a": -5, "b": -2.0}) == [q - 5, q - 2]
+    assert row_from_json(m, {"a": str(2 ** 300 + 7), "b": 1e40}) == [(2 ** 300 + 7) % q, int(format(1e40, ".0f")) % q]
+    # an empty digit string passes check_valid_number (main.cpp:126-142) and mpz_init_set_str leaves 0
+    assert row_from_json(m, {"a": "", "b": "0x"}) == [0, 0]
+    for bad in ("12a", "0b102", "1e5", "-5", "+5", "0x-1"):           # a sign is not a digit of any base
         with pytest.raises(InputError, match="Invalid number"):
             row_from_json(m, {"a": bad, "b": "1"})
     with pytest.raises(InputError, match="Invalid JSON type"):
@@ -132,6 +138,7 @@ def test_native_calculator_input_errors_and_no_cpu_fallback(cvmlib, tmp_path):
                       ('{"p": ["1", "2"]}', "Not all inputs have been set"),
                       ('{"p": ["1", 2], "q": ["1", "2"]}', "Types are not the same"),
                       ('{"p": ["0x1g", "2"], "q": ["1", "2"]}', "Invalid number"),
+                      ('{"p": ["-1", "2"], "q": ["1", "2"]}', "Invalid number"),
                       ('{"p": ["1", "2"], "q": ["1", "2"]', "invalid JSON")):
         r = run(text)
         assert r.returncode == 1 and msg in r.stderr, (text, r.stderr)
