@@ -593,10 +593,11 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
     size_t per_w = (cvmgpu_store_bytes(p, 1024) + 1023) / 1024 + in_row + out_row + 8;
     uint64_t fit = pick_chunk(B, 2 * per_w);
     if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
-    // chunks keep the D2H of one chunk under the kernels of the next: about 1 GiB of exported rows per chunk; without a
-    // witness download there is nothing to overlap and larger launches fill the GPU better
-    uint64_t chunk = 262144;
-    if (out_row) chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(4096, ((1ull << 30) / out_row) / 1024 * 1024));
+    // chunks keep the D2H of one chunk under the kernels of the next: about 1 GiB of exported rows per chunk.  With little
+    // or nothing to download there is nothing to overlap, and one large launch fills the GPU best (and pays the host-side
+    // cost of a chunk once).
+    uint64_t chunk = 1u << 20;
+    if (out_row > 256) chunk = std::min<uint64_t>(262144, std::max<uint64_t>(4096, ((1ull << 30) / out_row) / 1024 * 1024));
     chunk = std::min<uint64_t>(fit, chunk);
     if (B <= chunk) chunk = B;
     int dev = -1;
