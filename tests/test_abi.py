@@ -91,3 +91,14 @@ def test_plain_c_caller(cvmlib, tmp_path):
         assert kv["batch"] == "ok status 0 product 33" and kv["multi"] == "rc 0"
     else:
         assert kv["batch"].startswith("rc -4") and kv["multi"] == "rc -4"
+
+
+def test_integration_md_holds_the_generated_rust_binding():
+    """INTEGRATION.md's `extern "C"` block is tools/gen_rust_ffi.py's output for the current header (round 1's hand-written
+    ProgramInfo was three fields short of the C struct)."""
+    import os
+    from conftest import ROOT
+    from tools.gen_rust_ffi import generate
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text.split("<!-- BEGIN GENERATED: tools/gen_rust_ffi.py -->\n```rust\n")[1].split("```\n<!-- END GENERATED -->")[0]
+    assert block == generate()
