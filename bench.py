@@ -405,9 +405,30 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         sec = float(te.item())
         ok = int((h_st != 0).sum()) == 0 and int((h_bad != -1).sum()) == 0
-        return {"value": world * Be / sec, "unit": UNIT, "h2d_bytes_per_step": Be * wc.n_inputs * 32,
-                "d2h_bytes_per_step": Be * (n_sel * 32 + 8), "batch_per_gpu": Be, "ms_per_step": 1000 * sec,
-                "all_witnesses_valid": bool(ok), "api": api}
+        out = {"value": world * Be / sec, "unit": UNIT, "h2d_bytes_per_step": Be * wc.n_inputs * 32,
+               "d2h_bytes_per_step": Be * (n_sel * 32 + 8), "batch_per_gpu": Be, "ms_per_step": 1000 * sec,
+               "all_witnesses_valid": bool(ok), "api": api}
+        if h_wt is not None and h_wt.numel() >= (64 << 20):
+            # what the host lets through: the same bytes copied device -> the same pinned buffer by plain cudaMemcpy, every
+            # rank at once.  The full-row call cannot beat this; with N processes on one host it is the shared PCIe / memory fabric.
+            d_wt = torch.empty(h_wt.shape, dtype=torch.uint8, device=dev)
+            h_wt.copy_(d_wt, non_blocking=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                h_wt.copy_(d_wt, non_blocking=True)
+            torch.cuda.synchronize()
+            tc = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            out["d2h_ceiling"] = {"gb_per_s_all_gpus": world * h_wt.numel() / float(tc.item()) / 1e9,
+                                  "witnesses_per_s": world * Be / float(tc.item()),
+                                  "what": "plain D2H cudaMemcpy of the same %d bytes per GPU into the same pinned buffers, all ranks "
+                                          "concurrently: the host-side ceiling of the full-row call" % h_wt.numel()}
+            del d_wt
+        return out
 
     e2e = e2e_public = e2e_flags = None
     if not args.skip_e2e:

@@ -182,8 +182,10 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
 // warp pack their bits into one word (__ballot_sync), every lane stores that same word to the warp's slot (so each lane
 // later reads its own store: no fence needed), and a bit row of the value store is that word per warp: 4 bytes where a
 // field row costs 1 KiB.
+// (programs without 0/1-typed values are bound by the multiplier pipe and want 20 resident warps per SM: 96 registers;
+// the bit-file instantiation is limited by its shared memory instead and keeps the registers it needs)
 template <int NT, bool BITS>
-__global__ void __launch_bounds__(NT) tape_kernel(TapeParams p) {
+__global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParams p) {
     extern __shared__ uint4 slots[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint64_t w = (uint64_t)blockIdx.x * NT + tid;
@@ -508,7 +510,10 @@ struct StoreView {
     const uint32_t *wire_loc;
 };
 __global__ void __launch_bounds__(256) export_kernel(StoreView sv, uint64_t B, uint32_t wire0, uint32_t n_sel, uint4 *out) {
-    __shared__ uint32_t tile[32][32][9];   // [wire][witness][limb], padded
+    // [wire][witness][limb]: 9 words per element and 33 elements per row make BOTH phases conflict-free -- the write phase
+    // strides lanes by 9 words, the read phase (lane = wire) by 33 * 9 = 297 = 9 mod 32, and 9 is coprime with the 32
+    // banks.  (With 32 elements per row the read stride was 288 = 0 mod 32: a 32-way bank conflict on every read.)
+    __shared__ uint32_t tile[32][33][9];
     const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const uint64_t w0 = (uint64_t)blockIdx.x * 32;
     const uint32_t r0 = blockIdx.y * 32;
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(256) export_kernel(StoreView sv, uint64_t B, u
 // canonical AoS -> Montgomery SoA (used by the stand-alone R1CS check on externally produced witnesses)
 __global__ void __launch_bounds__(256) import_kernel(const uint4 *in, uint64_t B, uint32_t n_wires, uint4 *store,
                                                      uint64_t bstride) {
-    __shared__ uint32_t tile[32][32][9];   // [witness][wire][limb]
+    __shared__ uint32_t tile[32][33][9];   // [witness][wire][limb]; the padding as in export_kernel
     const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const uint64_t w0 = (uint64_t)blockIdx.x * 32;
     const uint32_t r0 = blockIdx.y * 32;

@@ -21,7 +21,8 @@ wc.run_dev(inp, B, B, store, status, s)
 # corrupt a few witnesses
 view = store.view(torch.uint8)
 rows = wc.wire_rows()
-for b, wire in ((5, 3), (77777, 400), (B - 1, 636)):
+for b, wire in ((5, 3), (77777, 400), (B - 1, 600)):
+    assert not int(rows[wire]) & 0x80000000
     view[((int(rows[wire]) * 2) * B + b) * 16] ^= 1
 L = ctypes.CDLL(os.path.join(ROOT, "tools", "spec", "_libspec.so"))
 L.spec_check_launch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
