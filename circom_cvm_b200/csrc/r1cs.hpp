@@ -82,20 +82,12 @@ static const int TABLE_VARS = 5;
 
 // wire_loc == nullptr: the plain layout (row = wire, no bit rows).  one_brow: the bit row that holds the constant 1 (wire 0
 // itself is a field row): terms on wire 0 use it in constraints evaluated in integers.
-// const_rows[v] = {first, count}: bit rows of the wires bound to the constant v -- terms on them are folded (a wire that
-// is always 0 contributes nothing, a wire that is always 1 is the constant wire 0).
+// Every term is evaluated against the STORED row of its wire -- also for wires the program binds to constants: the check
+// is an independent evaluation of the .r1cs on the witness as stored, it does not trust the tape (const_rows is unused).
 inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0, const uint32_t (*const_rows)[2] = nullptr) {
     Bound b;
-    // wire -> 0 when it is bound to the constant 1, or 0xffffffff when bound to the constant 0 (the term vanishes)
-    auto fold = [&](uint32_t wire) -> uint32_t {
-        if (!wire_loc || !const_rows || wire == 0) return wire;
-        const uint32_t loc = wire_loc[wire];
-        if (!(loc & LOC_BIT)) return wire;
-        const uint32_t row = loc & ~LOC_BIT;
-        if (row >= const_rows[0][0] && row < const_rows[0][0] + const_rows[0][1]) return 0xffffffffu;
-        if (row >= const_rows[1][0] && row < const_rows[1][0] + const_rows[1][1]) return 0u;
-        return wire;
-    };
+    (void)const_rows;
+    auto fold = [&](uint32_t wire) -> uint32_t { return wire; };
     const size_t n_lc = f.ptr.size() - 1;
     b.hdr.assign(4 * (n_lc + 1), 0);
     b.bhdr.assign(4 * ((size_t)f.n_constraints + 1), 0);
