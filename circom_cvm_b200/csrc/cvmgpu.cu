@@ -85,8 +85,9 @@ struct BoundDev {
     bool typed = false;
     uint32_t n_brows = 0;
     uint64_t macs = 0, bit_adds = 0, n_int_constraints = 0, n_bterms = 0, n_fterms = 0, n_tcons = 0;
-    DevBuf d_hdr, d_terms, d_bhdr, d_bterms, d_tcons;
-    void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); d_tcons.release(); layout_id = ~0ull; }
+    uint64_t n_active = 0;
+    DevBuf d_hdr, d_terms, d_bhdr, d_bterms, d_tcons, d_active;
+    void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); d_tcons.release(); d_active.release(); layout_id = ~0ull; }
 };
 
 struct cvmgpu_r1cs {
@@ -805,6 +806,9 @@ static int upload_bound(const r1cs::Bound &b, BoundDev &d) {
     if (int rc = d.d_tcons.ensure(std::max<size_t>(32, b.tcons.size() * 4))) return rc;
     if (!b.tcons.empty()) CUDA_TRY(cudaMemcpy(d.d_tcons.p, b.tcons.data(), b.tcons.size() * 4, cudaMemcpyHostToDevice));
     d.n_tcons = b.n_table_constraints;
+    if (int rc = d.d_active.ensure(std::max<size_t>(16, b.active.size() * 4))) return rc;
+    if (!b.active.empty()) CUDA_TRY(cudaMemcpy(d.d_active.p, b.active.data(), b.active.size() * 4, cudaMemcpyHostToDevice));
+    d.n_active = b.active.size();
     d.macs = b.macs;
     d.bit_adds = b.bit_adds;
     d.n_int_constraints = b.n_int_constraints;
@@ -842,22 +846,27 @@ static int launch_check(cvmgpu_r1cs *r, const cvmgpu_r1cs::Dev &rd, const BoundD
                         uint64_t bstride, void *d_first_bad, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(d_first_bad, 0xff, B * 4, s));
     if (r->file.n_constraints == 0) return CVMGPU_OK;
+    const bool walk = !bd.typed || bd.n_active != 0;
     uint64_t gx = (B + R1CS_NT - 1) / R1CS_NT;
+    // the per-witness kernel walks every constraint (plain layout) or those the table kernel does not take (typed)
+    const uint64_t n_walk = bd.typed ? bd.n_active : r->file.n_constraints;
     // enough CTAs to fill 148 SMs several times over even for small batches (config 5: B = 1K, 1.5M constraints)
     uint64_t want = 148ull * 16;
     uint64_t chunks = std::max<uint64_t>(1, (want + gx - 1) / gx);
-    uint32_t per = (uint32_t)std::max<uint64_t>(32, (r->file.n_constraints + chunks - 1) / chunks);
-    chunks = (r->file.n_constraints + per - 1) / per;
+    uint32_t per = (uint32_t)std::max<uint64_t>(32, (n_walk + chunks - 1) / chunks);
+    chunks = (n_walk + per - 1) / per;
     if (chunks > 65535) {
-        per = (r->file.n_constraints + 65534) / 65535;
-        chunks = (r->file.n_constraints + per - 1) / per;
+        per = (uint32_t)((n_walk + 65534) / 65535);
+        chunks = (n_walk + per - 1) / per;
     }
     kern::R1csParams rp;
     rp.hdr = (const uint4 *)bd.d_hdr.p;
     rp.terms = (const uint2 *)bd.d_terms.p;
     rp.coefs = (const uint4 *)rd.d_coefs.p;
     rp.cmag = (const uint32_t *)rd.d_cmag.p;
-    rp.n_cons = r->file.n_constraints;
+    rp.n_cons = (uint32_t)n_walk;
+    rp.n_all = r->file.n_constraints;
+    rp.active = (const uint32_t *)bd.d_active.p;
     rp.cons_per_chunk = per;
     rp.store = (const uint4 *)d_store;
     rp.bstride = bstride;
@@ -872,7 +881,9 @@ static int launch_check(cvmgpu_r1cs *r, const cvmgpu_r1cs::Dev &rd, const BoundD
     // resident CTAs per SM: 4 (128 registers) when the check is multiplier-bound (Poseidon: 28 % of the terms have
     // full-size coefficients, EdDSA 12 %), 5 (96 registers) when it is mostly +-1 / small coefficients and latency-bound
     int minb = g_r1cs_minb ? g_r1cs_minb : (20 * r->file.nnz_general > r->file.nnz ? 4 : 5);
-    if (bd.typed) {
+    if (!walk) {
+        // every constraint is a truth-table constraint
+    } else if (bd.typed) {
         if (minb == 5) kern::r1cs_kernel<5, true><<<grid, R1CS_NT, 0, s>>>(rp);
         else kern::r1cs_kernel<4, true><<<grid, R1CS_NT, 0, s>>>(rp);
     } else {

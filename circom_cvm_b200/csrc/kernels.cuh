@@ -605,6 +605,9 @@ struct R1csParams {
     const uint4 *bhdr;
     const uint2 *bterms;
     const long long *cint;
+    // TYPED: the constraints this kernel walks (all but those r1cs_table_kernel takes), n_cons = their number
+    const uint32_t *active;
+    uint32_t n_all;
 };
 
 // One linear combination.  Its terms are ordered by coefficient class (r1cs.hpp):
@@ -628,15 +631,17 @@ struct TermStream {
     uint64_t bstride;
     uint4 *ring;            // [R1CS_STAGES][2][R1CS_NT]
     uint32_t t_end;
+    // this thread's column of the ring as a shared-space address, and the byte stride of a row (bstride < 2^27, so it fits
+    // 32 bits and a row address is ONE IMAD.WIDE.U32 instead of a 64-bit multiply)
+    __device__ __forceinline__ uint32_t column() const { return (uint32_t)__cvta_generic_to_shared(ring + threadIdx.x); }
     // the stream is position-determined: term t's value is requested R1CS_STAGES takes before it is consumed
     __device__ __forceinline__ void issue(uint32_t t) const {
         if (t < t_end) {
-            const uint2 term = __ldg(terms + t);
-            const uint4 *src = wbase + ((uint64_t)(term.x & 0x0fffffffu) * 2) * bstride;   // top bits: +-2^k meta (r1cs.hpp)
-            uint4 *dst = ring + (t % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
-            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+            const uint32_t row = __ldg(&terms[t].x) & 0x0fffffffu;   // top bits: +-2^k meta (r1cs.hpp)
+            const char *src = (const char *)wbase + (uint64_t)row * ((uint32_t)bstride * 32u);
+            const uint32_t d0 = column() + (t % R1CS_STAGES) * (2 * R1CS_NT * 16);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(src) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + R1CS_NT * 16), "l"(src + bstride) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + R1CS_NT * 16), "l"(src + bstride * 16) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -647,8 +652,11 @@ struct TermStream {
     // value of term t (terms are consumed strictly in order); refills the stage it frees
     __device__ __forceinline__ Fr take(uint32_t t) const {
         asm volatile("cp.async.wait_group %0;" ::"n"(R1CS_STAGES - 1) : "memory");
-        const uint4 *s = ring + (t % R1CS_STAGES) * 2 * R1CS_NT + threadIdx.x;
-        const Fr v = unpack(s[0], s[R1CS_NT]);
+        const uint32_t s0 = column() + (t % R1CS_STAGES) * (2 * R1CS_NT * 16);
+        uint4 lo, hi;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(s0));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(s0 + R1CS_NT * 16));
+        const Fr v = unpack(lo, hi);
         issue(t + R1CS_STAGES);
         return v;
     }
@@ -840,8 +848,13 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     // (a padding lane evaluates a copy of the last witness: its bit is the last witness's lane of that warp's word)
     const uint32_t lane = (uint32_t)(active ? w : p.B - 1) & 31u;
     if (!active) w = p.B - 1;
-    const uint32_t c0 = blockIdx.y * p.cons_per_chunk;
-    const uint32_t c1 = min(p.n_cons, c0 + p.cons_per_chunk);
+    // chunk of the walk: positions [i0, i1) of the active list (TYPED) or of the constraints themselves; its terms are the
+    // CSR range from the first constraint's begin to the begin of the first constraint after the chunk (skipped
+    // constraints have no terms)
+    const uint32_t i0 = blockIdx.y * p.cons_per_chunk;
+    const uint32_t i1 = min(p.n_cons, i0 + p.cons_per_chunk);
+    const uint32_t c0 = TYPED ? __ldg(p.active + i0) : i0;
+    const uint32_t c1 = TYPED ? (i1 < p.n_cons ? __ldg(p.active + i1) : p.n_all) : i1;
     const uint4 *wbase = p.store + w;
     const uint32_t *brow = TYPED ? p.bits + (w >> 5) * p.n_brows : nullptr;
     const uint32_t t_end = __ldg(&p.hdr[3 * c1].x);
@@ -867,7 +880,8 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
     }
     uint32_t bad = 0xffffffffu;
     uint4 hA = __ldg(p.hdr + 3 * c0);
-    for (uint32_t c = c0; c < c1; c++) {
+    for (uint32_t i = i0; i < i1; i++) {
+        const uint32_t c = TYPED ? __ldg(p.active + i) : i;
         uint32_t bA = 0, bB = 0, bC = 0, bN = 0;
         if (TYPED) {
             const uint4 bh = __ldg(p.bhdr + c);

@@ -71,6 +71,8 @@ struct Bound {
     // Such constraints have no terms in either CSR.
     std::vector<uint32_t> tcons;
     uint64_t n_table_constraints = 0;
+    // the constraints the per-witness kernel has to walk (every mode but 3), in order
+    std::vector<uint32_t> active;
     uint64_t n_int_constraints = 0, n_field_constraints = 0;
     // 32x32->64 multiply-accumulates the check executes per witness on this layout (upper bound: products with a 0 / +-1
     // factor are skipped at run time), and its executed field additions of bit-row terms
@@ -178,6 +180,7 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
             }
         }
         if (intok) b.n_int_constraints++; else b.n_field_constraints++;
+        if (mode != 3) b.active.push_back(c);
         bool has[3] = {false, false, false};
         for (int k = 0; k < 3; k++) {
             const size_t j = 3 * (size_t)c + k;
