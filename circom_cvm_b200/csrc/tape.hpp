@@ -780,6 +780,10 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
         }
         return xp.isbool[r] != 0;
     };
+    uint32_t ml[2];
+    max_live_by_kind(xp, ml);
+    out.stats.max_live_field = ml[0];
+    out.stats.max_live_bool = ml[1];
     // ---- witness wire -> typed row
     out.wire_loc.resize(out.n_wires);
     {
@@ -790,12 +794,15 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
         uint32_t nf = 0, nb = 0;
         auto const_bit = [&](uint32_t w) -> int {   // -1: not a constant 0/1 wire
             const uint32_t r = xp.witness_ref[w];
-            if (w == 0 || !(r & CONST_FLAG) || !is_bool_ref(r)) return -1;
+            // (a program without computed 0/1 values keeps its constant wires as field rows: its constraints then have no
+            // bit-row term at all and the check runs the plain kernel)
+            if (w == 0 || ml[1] == 0 || !(r & CONST_FLAG) || !is_bool_ref(r)) return -1;
             return (int)tr.consts[r & ~CONST_FLAG].v[0];
         };
         for (uint32_t w = 0; w < out.n_wires; w++) {
             if (const_bit(w) >= 0) continue;
-            out.wire_loc[w] = (w != 0 && is_bool_ref(xp.witness_ref[w])) ? (ROW_BIT | nb++) : nf++;
+            const bool as_bit = w != 0 && is_bool_ref(xp.witness_ref[w]) && (ml[1] != 0 || !(xp.witness_ref[w] & CONST_FLAG));
+            out.wire_loc[w] = as_bit ? (ROW_BIT | nb++) : nf++;
         }
         out.n_fwires = nf;
         for (int v = 0; v < 2; v++) {
@@ -807,10 +814,6 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
         }
         out.n_bwires = nb;
     }
-    uint32_t ml[2];
-    max_live_by_kind(xp, ml);
-    out.stats.max_live_field = ml[0];
-    out.stats.max_live_bool = ml[1];
     // the bit file: enough for every live 0/1 value when that fits (no bit spills at all), else the cap
     uint32_t n_bslots = ml[1] == 0 ? 0 : std::min<uint32_t>(max_bslots, ((ml[1] + 3 + 31) / 32) * 32);
     if (ml[1] && n_bslots < 64) n_bslots = 64;   // a T_ISUM pins up to ISUM_MAX bit slots at once
