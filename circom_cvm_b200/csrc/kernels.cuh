@@ -632,8 +632,8 @@ struct TermStream {
     uint4 *ring;            // [R1CS_STAGES][2][R1CS_NT]
     uint32_t t_end;
     // the stream is position-determined: term t's value is requested R1CS_STAGES takes before it is consumed
-    // (measured: hand-written shared-space addressing and a 32-bit row stride here made the Poseidon check SLOWER,
-    // 17.3 -> 19.4 ms -- the compiler's own schedule of this form is the better one)
+    // (measured: a 32-bit row stride / hand-written shared-space addressing here changes nothing -- Poseidon check
+    // 17.3 vs 17.6 ms)
     __device__ __forceinline__ void issue(uint32_t t) const {
         if (t < t_end) {
             const uint2 term = __ldg(terms + t);
