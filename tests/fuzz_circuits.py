@@ -13,7 +13,11 @@ BIN = ["add", "sub", "mul", "div", "idiv", "mod", "pow", "shl", "shr", "band", "
        "eq", "neq", "land", "lor"]
 
 
-def make_circuit(seed, n_stmts=40):
+def make_circuit(seed, n_stmts=40, bits=False):
+    """bits=True adds the shapes the typed paths of the tape compiler live on: sums of 0/1 values times powers of two that
+    are taken apart again bit by bit (circomlib BinSum / Num2Bits: small-integer typing, T_ISUM, T_IBITG), boolean
+    functions written as field polynomials (a + b - 2ab, Ch, Maj: T_LUT / T_LUTG), bit values feeding field arithmetic and
+    constraints over them (the check's integer and truth-table paths)."""
     rng = random.Random(seed)
 
     def tmpl(T):
@@ -57,8 +61,57 @@ def make_circuit(seed, n_stmts=40):
                 y = rng.choice([0, 1, 7, 31, 32, 33, 100, 253, 254, 300, P - 3])
             return x._b(op, y)
 
+        bools = []
+
+        def a_bool():
+            if bools and rng.random() < 0.7:
+                return rng.choice(bools)
+            x = rng.choice(vals)
+            r = rng.random()
+            if r < 0.4:
+                return (x >> rng.randrange(0, 40)) & 1
+            if r < 0.7:
+                return x < rng.choice(vals)
+            return x.eq(rng.choice([0, 1, 2]))
+
         for k in range(n_stmts):
             v = T.var("v%d" % k)
+            if bits and rng.random() < 0.45:
+                r = rng.random()
+                if r < 0.35:
+                    # lin = sum_j b_j * 2^(k_j) (several operands overlap, like BinSum), then its bits
+                    n_terms = rng.choice([2, 3, 8, 20, 33, 40])
+                    acc = None
+                    for j in range(n_terms):
+                        t = a_bool() * (1 << rng.choice([j % 34, j % 34, rng.randrange(0, 36), 61 if rng.random() < 0.03 else 0]))
+                        acc = t if acc is None else acc + t
+                    T.set(v, acc)
+                    vals.append(v)
+                    vars_.append(v)
+                    lo = rng.randrange(0, 8)
+                    for j in range(rng.choice([1, 3, 9, 36])):
+                        b = T.var("v%d_b%d" % (k, j))
+                        T.set(b, (v >> (lo + j)) & 1)
+                        bools.append(b)
+                        vars_.append(b)
+                    continue
+                x, y, z = a_bool(), a_bool(), a_bool()
+                if r < 0.55:
+                    T.set(v, x + y - 2 * x * y)                          # xor
+                elif r < 0.7:
+                    T.set(v, x * (y - z) + z)                            # Ch
+                elif r < 0.8:
+                    T.set(v, x * y + z * (x + y - 2 * x * y))            # Maj
+                elif r < 0.9:
+                    T.set(v, 1 - x)
+                else:
+                    T.set(v, x * rng.choice(vals) + y * 5)               # bits into field arithmetic
+                    vals.append(v)
+                    vars_.append(v)
+                    continue
+                bools.append(v)
+                vars_.append(v)
+                continue
             if rng.random() < 0.15 and len(vals) > 4:
                 cond = rng.choice(vals)
                 with T.if_(cond if rng.random() < 0.5 else cond.ne(rng.choice([0, 1]))):
@@ -81,6 +134,12 @@ def make_circuit(seed, n_stmts=40):
         T.constrain(out[0] * 1, out[0])
         if seed % 2 == 1:
             T.constrain(out[rng.randrange(12)] * out[rng.randrange(12)], out[rng.randrange(12)])
+        if bits:
+            # constraints over 0/1 outputs with small coefficients (truth-table / integer paths of the check), some of them
+            # false for some inputs
+            for _ in range(4):
+                a, b, c = (out[rng.randrange(12)] for _ in range(3))
+                T.constrain((a * rng.choice([1, 2, -1]) + rng.choice([0, 1])) * (b - rng.choice([0, 1])), c * rng.choice([0, 1, 3]))
     tmpl.__name__ = "Fuzz%d" % seed
     return tmpl
 
