@@ -173,6 +173,41 @@ __device__ __noinline__ uint32_t tape_slow_op(uint4 cur, uint4 *slots, const uin
     return status;
 }
 
+// ADD / SUB / MUL of the tape (shared by the dispatch fast path of field-only programs and the switch)
+template <int NT, bool BITS>
+__device__ __forceinline__ Fr tape_arith(uint32_t op, uint32_t flags, const uint4 &cur, const uint4 *slots, const uint32_t *bw,
+                                         const uint4 *consts, uint32_t tid) {
+    Fr r;
+    const Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
+    const Fr b = tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid);
+    if (op == tape::T_MUL) {
+        // bit-heavy programs (F_TRIVIAL, set by the tape builder): factors that are 0 or 1 at run time without
+        // being provably so (input bits of a hash) need no product; decided per warp to keep control flow uniform
+        bool cheap = false;
+        if (flags & tape::F_TRIVIAL) {
+            const Fr one = fr::one_mont();
+            const bool triv = fr::is_zero(a) || fr::is_zero(b) || fr::equal(a, one) || fr::equal(b, one);
+            cheap = __all_sync(0xffffffffu, triv);
+            if (cheap) {
+                const bool z = fr::is_zero(a) || fr::is_zero(b);
+                const bool a1 = fr::equal(a, one);
+#pragma unroll
+                for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : (a1 ? b.v[i] : a.v[i]);
+            }
+        }
+        if (!cheap) {
+            // same operand twice (x^2, x^4 of an S-box): the squaring needs 100 instead of 128 IMAD.WIDE
+            if (cur.y == cur.z && (flags & 3u) == 0) r = fr::mont_sqr(a);
+            else r = fr::mont_mul(a, b);
+        }
+    } else if (op == tape::T_ADD) {
+        r = fr::add(a, b);
+    } else {
+        r = fr::sub(a, b);
+    }
+    return r;
+}
+
 // One tape pass per witness.  Control flow is uniform (one instruction stream per circuit), so the branches on the
 // opcode never diverge.  Fast path, inlined once each: MUL / ADD / SUB, DOT, SEL, EQ / NEQ / EQZ, BITC, LUT, the failure
 // checks and the value-store moves; the result of a producing instruction can be written to its witness wire by
@@ -215,35 +250,14 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
         Fr r;
         uint32_t rb = 0;        // result of an instruction that produces a truth value
         bool is_rb = false;
+        // field-only programs (Poseidon: 240 products + 194 additions + 195 dot products in 1 025 instructions) test for
+        // their arithmetic first; everything else goes through the jump table
+        if (!BITS && op >= tape::T_ADD && op <= tape::T_MUL) {
+            r = tape_arith<NT, BITS>(op, flags, cur, slots, bw, consts, tid);
+        } else
         switch (op) {
         case tape::T_ADD: case tape::T_SUB: case tape::T_MUL: {
-            const Fr a = tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
-            const Fr b = tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid);
-            if (op == tape::T_MUL) {
-                // bit-heavy programs (F_TRIVIAL, set by the tape builder): factors that are 0 or 1 at run time without
-                // being provably so (input bits of a hash) need no product; decided per warp to keep control flow uniform
-                bool cheap = false;
-                if (flags & tape::F_TRIVIAL) {
-                    const Fr one = fr::one_mont();
-                    const bool triv = fr::is_zero(a) || fr::is_zero(b) || fr::equal(a, one) || fr::equal(b, one);
-                    cheap = __all_sync(0xffffffffu, triv);
-                    if (cheap) {
-                        const bool z = fr::is_zero(a) || fr::is_zero(b);
-                        const bool a1 = fr::equal(a, one);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : (a1 ? b.v[i] : a.v[i]);
-                    }
-                }
-                if (!cheap) {
-                    // same operand twice (x^2, x^4 of an S-box): the squaring needs 100 instead of 128 IMAD.WIDE
-                    if (cur.y == cur.z && (flags & 3u) == 0) r = fr::mont_sqr(a);
-                    else r = fr::mont_mul(a, b);
-                }
-            } else if (op == tape::T_ADD) {
-                r = fr::add(a, b);
-            } else {
-                r = fr::sub(a, b);
-            }
+            r = tape_arith<NT, BITS>(op, flags, cur, slots, bw, consts, tid);
             break;
         }
         case tape::T_DOT: {
@@ -659,8 +673,10 @@ struct TermStream {
     }
 };
 
-// out of line: called up to three times per constraint (A, B, C in CSR order); hdr = {begin, e0, e1, e2}
-__device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const uint32_t *cmag, const uint4 *wbase,
+// called up to three times per constraint (A, B, C in CSR order); hdr = {begin, e0, e1, e2}.  Inlined in the plain kernel
+// (Poseidon check 17.3 -> 16.5 ms: the calls were 13 % of its instructions), out of line in the typed one, whose register
+// budget is spent on the bit stream (EdDSA check 19.9 vs 20.3 ms inlined).
+__device__ __forceinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const uint32_t *cmag, const uint4 *wbase,
                                    uint64_t bstride, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
     TermStream ts;
     ts.terms = terms;
@@ -716,9 +732,21 @@ __device__ __noinline__ Fr lc_eval(const uint2 *terms, const uint4 *coefs, const
     return acc;
 }
 
+__device__ __noinline__ Fr lc_eval_call(const uint2 *terms, const uint4 *coefs, const uint32_t *cmag, const uint4 *wbase,
+                                        uint64_t bstride, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
+    return lc_eval(terms, coefs, cmag, wbase, bstride, ring, t_end, hdr, end);
+}
+template <bool INL>
+__device__ __forceinline__ Fr lc_eval_sel(const uint2 *terms, const uint4 *coefs, const uint32_t *cmag, const uint4 *wbase,
+                                          uint64_t bstride, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
+    if (INL) return lc_eval(terms, coefs, cmag, wbase, bstride, ring, t_end, hdr, end);
+    return lc_eval_call(terms, coefs, cmag, wbase, bstride, ring, t_end, hdr, end);
+}
+
 // linear combinations made of +-2^k (k <= 3) terms only stay inline
+template <bool INL>
 __device__ __forceinline__ Fr lc_any(const R1csParams &p, const uint4 *wbase, uint4 *ring, uint32_t t_end, uint4 hdr, uint32_t end) {
-    if (hdr.y != end) return lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hdr, end);
+    if (hdr.y != end) return lc_eval_sel<INL>(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hdr, end);
     TermStream ts;
     ts.terms = p.terms;
     ts.wbase = wbase;
@@ -908,7 +936,7 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
         Fr prod = fr::zero();
         if (hB.y == R1CS_SAME_AS_A) {        // B repeats A (r1cs.hpp): one evaluation, one squaring
             Fr sa = fr::zero();
-            if (hA.x != hB.x) sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            if (hA.x != hB.x) sa = lc_any<!TYPED>(p, wbase, ring, t_end, hA, hB.x);
             if (TYPED) sa = lc_bits(p, bs, bA, bB, sa);
             const Fr one = fr::one_mont();
             if (fr::is_zero(sa)) prod = fr::zero();
@@ -916,9 +944,9 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
             else prod = fr::mont_sqr(sa);
         } else if (hasA && hasB) {   // an empty A or B makes the product 0 (linear constraint, algebra.rs:1052-1054)
             Fr sa = fr::zero(), sb = fr::zero();
-            if (hA.x != hB.x) sa = lc_any(p, wbase, ring, t_end, hA, hB.x);
+            if (hA.x != hB.x) sa = lc_any<!TYPED>(p, wbase, ring, t_end, hA, hB.x);
             if (TYPED) sa = lc_bits(p, bs, bA, bB, sa);
-            if (hB.x != hC.x) sb = lc_any(p, wbase, ring, t_end, hB, hC.x);
+            if (hB.x != hC.x) sb = lc_any<!TYPED>(p, wbase, ring, t_end, hB, hC.x);
             if (TYPED) sb = lc_bits(p, bs, bB, bC, sb);
             // trivial factors need no product: 0, 1 and -1 (bit-valued wires and the +-1 combinations of them that
             // fill hash circuits).  The branch is per lane; a warp pays for the multiplication only if one of its
@@ -935,11 +963,11 @@ __global__ void __launch_bounds__(R1CS_NT, MINB) r1cs_kernel(R1csParams p) {
             else prod = fr::mont_mul(sa, sb);
         } else {
             // the field terms of a lone A or B still occupy the stream: consume them
-            if (hA.x != hB.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hA, hB.x);
-            if (hB.x != hC.x) (void)lc_eval(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hB, hC.x);
+            if (hA.x != hB.x) (void)lc_eval_call(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hA, hB.x);
+            if (hB.x != hC.x) (void)lc_eval_call(p.terms, p.coefs, p.cmag, wbase, p.bstride, ring, t_end, hB, hC.x);
         }
         Fr sc = fr::zero();
-        if (hC.x != hN.x) sc = lc_any(p, wbase, ring, t_end, hC, hN.x);
+        if (hC.x != hN.x) sc = lc_any<!TYPED>(p, wbase, ring, t_end, hC, hN.x);
         if (TYPED && hasC) sc = lc_bits(p, bs, bC, bN, sc);
         if (bad == 0xffffffffu && !fr::equal(prod, sc)) bad = c;
         hA = hN;
