@@ -1,6 +1,7 @@
 """Process-level drop-in for the reference's generated witness calculator (common/main.cpp:334-371):
 
     python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>] [--sym <circuit.sym>]
+                              [--cpp <circuit.cpp>]
 
 reads `<circuit>.dat` next to the program (as the reference reads `<argv0>.dat`) - or, with --sym or when there is no
 .dat, the `circom --sym` symbol file - to resolve the input names, takes the same input.json and
@@ -15,7 +16,7 @@ import sys
 def main(argv):
     args, opts, k = [], {}, 1
     while k < len(argv):
-        if argv[k] in ("--r1cs", "--sym") and k + 1 < len(argv):
+        if argv[k] in ("--r1cs", "--sym", "--cpp") and k + 1 < len(argv):
             opts[argv[k]] = argv[k + 1]
             k += 2
         elif argv[k].startswith("--"):
@@ -25,16 +26,20 @@ def main(argv):
             args.append(argv[k])
             k += 1
     if len(args) != 3:
-        print("Usage: python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <file>] [--sym <file>]",
+        print("Usage: python -m circom_cvm_b200 <circuit.cvm> <input.json> <output.wtns> [--r1cs <file>] [--sym <file>] [--cpp <file>]",
               file=sys.stderr)
         return 1
     from . import engine as E
     from .inputs import InputError, InputMap, SymInputMap, rows_from_json_text
     cvm, jin, wout = args
     r1cs_path = opts.get("--r1cs")
-    wc = E.WitnessCalculator(cvm_path=cvm)
+    # the generated C++ of the same compile (component creation for an unpatched emitter; section sizes of the .dat) and
+    # the .dat (io-map of mixed component arrays) are picked up next to the program when they are there
+    stem = os.path.splitext(cvm)[0]
+    cpp = opts.get("--cpp") or (stem + ".cpp" if os.path.exists(stem + ".cpp") else None)
+    dat = stem + ".dat" if cpp and os.path.exists(stem + ".dat") else None
+    wc = E.WitnessCalculator(cvm_path=cvm, cpp_path=cpp, dat_path=dat)
     try:
-        stem = os.path.splitext(cvm)[0]
         sym_path = opts.get("--sym") or (stem + ".sym" if not os.path.exists(stem + ".dat") and os.path.exists(stem + ".sym") else None)
         imap = SymInputMap.from_files(sym_path, wc) if sym_path else InputMap.from_files(stem + ".dat", wc)
         with open(jin) as f:

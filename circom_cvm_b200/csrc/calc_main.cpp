@@ -372,22 +372,32 @@ std::string strip_ext(const std::string &p) {
 
 int main(int argc, char *argv[]) {
     std::vector<std::string> pos;
-    std::string r1cs_path, sym_path;
+    std::string r1cs_path, sym_path, cpp_path;
     for (int k = 1; k < argc; k++) {
         std::string a = argv[k];
         if (a == "--r1cs" && k + 1 < argc) r1cs_path = argv[++k];
         else if (a == "--sym" && k + 1 < argc) sym_path = argv[++k];
+        else if (a == "--cpp" && k + 1 < argc) cpp_path = argv[++k];
         else pos.push_back(a);
     }
     if (pos.size() != 3) {
-        fprintf(stderr, "Usage: %s <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>] [--sym <circuit.sym>]\n", argv[0]);
+        fprintf(stderr, "Usage: %s <circuit.cvm> <input.json> <output.wtns> [--r1cs <circuit.r1cs>] [--sym <circuit.sym>] "
+                        "[--cpp <circuit.cpp>]\n", argv[0]);
         return 1;
     }
     cvmgpu_program *prog = nullptr;
     cvmgpu_r1cs *r1 = nullptr;
     int rc = 1;
     try {
-        if (cvmgpu_program_load(pos[0].c_str(), 0, &prog) != CVMGPU_OK) throw Fail(cvmgpu_last_error());
+        // the generated C++ of the same compile (component creation for an unpatched emitter; section sizes of the .dat)
+        // and the .dat (io-map of mixed component arrays) are picked up next to the program when they are there
+        const std::string stem = strip_ext(pos[0]);
+        if (cpp_path.empty() && std::ifstream(stem + ".cpp").good()) cpp_path = stem + ".cpp";
+        const std::string dat_path = stem + ".dat";
+        const bool have_dat = !cpp_path.empty() && std::ifstream(dat_path).good();
+        if (cvmgpu_program_load_files(pos[0].c_str(), cpp_path.empty() ? nullptr : cpp_path.c_str(),
+                                      have_dat ? dat_path.c_str() : nullptr, 0, &prog) != CVMGPU_OK)
+            throw Fail(cvmgpu_last_error());
         cvmgpu_program_info info;
         info.struct_size = sizeof(info);
         if (cvmgpu_program_info_get(prog, &info) != CVMGPU_OK) throw Fail(cvmgpu_last_error());

@@ -50,6 +50,11 @@ enum Op : uint16_t {
     OP_SET_CMP_INPUT, OP_SET_CMP_INPUT_CNT, OP_SET_CMP_INPUT_RUN, OP_SET_CMP_INPUT_CNT_CHECK,
     OP_LOOP, OP_IF, OP_ELSE, OP_END, OP_BREAK, OP_CONTINUE, OP_ERROR, OP_CALL, OP_RETURN, OP_CREATE_CMP,
     OP_MAPPED_UNSUPPORTED,
+    // "mapped" accesses (location_rule.rs:86-171): a signal of a component in a MIXED array is addressed through the io-map
+    OP_GET_TEMPLATE_ID,      // dst = template-instance id of sub-component args[0]
+    OP_GET_TMPL_SIG_POS,     // dst = io_map[args[0]].defs[args[1]].offset
+    OP_GET_TMPL_SIG_DIM,     // dst = io_map[args[0]].defs[args[1]].lengths[args[2]]   (args[2] >= 1)
+    OP_GET_TMPL_SIG_SIZE,    // dst = io_map[args[0]].defs[args[1]].size
     OP_ARRAY_EQ      // dst = AND_k (A[k] == B[k]); args = {addr A, cmp A, addr B, cmp B}; cc = {load op A, load op B, n}
 };
 
@@ -86,13 +91,24 @@ struct Code {
     std::string header;
     bool is_function = false;
     int64_t n_inputs = 0, n_outputs = 0, n_signals = 0, n_subcmps = 0, local_memory = 0;
+    int64_t template_id = -1;     // <name>_<id> (template headers: build.rs:50, executed_template.rs); what _create stores
     std::vector<Ins> ins;
     std::unordered_map<std::string, int> regmap;
     int nregs = 0;
     int reg_destination = -1, reg_destination_size = -1;
 };
 
+// one input/output signal of a template instance that sits in a mixed component array (IODef, build.rs:531-552; the
+// .dat record c_code_generator.rs:617-674 and its reader main.cpp:59-92 drop lengths[0], which no address needs)
+struct IoDef {
+    int64_t offset = 0;
+    std::vector<int64_t> lengths_tail;   // lengths[1..]
+    int64_t size = 1;
+    int64_t bus_id = 0;
+};
+
 struct Program {
+    std::unordered_map<int64_t, std::vector<IoDef>> io_map;   // template-instance id -> defs indexed by signal code
     std::vector<Code> codes;
     std::unordered_map<std::string, int> code_index;
     std::vector<fr::Fr> ffconst;                      // canonical values of ff.<n> literals
@@ -179,6 +195,10 @@ class Parser {
                 parse_create(line, lineno);
                 continue;
             }
+            if (line.rfind(";;%%io_map", 0) == 0) {
+                parse_io_map(line, lineno);
+                continue;
+            }
             if (line.rfind(";;", 0) == 0 || line.rfind("//", 0) == 0) continue;
             if (line.rfind("%%", 0) == 0) {
                 parse_directive(line, lineno);
@@ -254,6 +274,9 @@ class Parser {
             cur->n_outputs = dims_size(br[1]);
             cur->n_signals = atoll(br[2].c_str());
             cur->n_subcmps = atoll(br[3].c_str());
+            size_t us = cur->header.rfind('_');
+            if (us != std::string::npos && is_int_token(cur->header.substr(us + 1)) && cur->header[us + 1] != '-')
+                cur->template_id = atoll(cur->header.c_str() + us + 1);
         } else if (d == "%%function") {
             new_code(t.at(1), true);
         } else if (d == "%%components_heap" || d == "%%components" || d == "%%type") {
@@ -349,6 +372,29 @@ class Parser {
         return o;
     }
 
+    // ;;%%io_map <template id> <n defs> { <offset> <n> <n lengths (dimensions 1..)> <size> <bus id> }*
+    // -- the record of the .dat io-map (c_code_generator.rs:617-674) as text; a comment to any other consumer
+    void parse_io_map(const std::string &line, int lineno) {
+        auto t = split_ws(line);
+        if (t.size() < 3) throw ParseError("malformed io_map at line " + std::to_string(lineno));
+        const int64_t tid = atoll(t[1].c_str()), n = atoll(t[2].c_str());
+        std::vector<IoDef> defs;
+        size_t k = 3;
+        for (int64_t d = 0; d < n; d++) {
+            if (k + 2 > t.size()) throw ParseError("malformed io_map at line " + std::to_string(lineno));
+            IoDef def;
+            def.offset = atoll(t[k].c_str());
+            const int64_t len = atoll(t[k + 1].c_str());
+            k += 2;
+            if (len < 0 || k + (size_t)len + 2 > t.size()) throw ParseError("malformed io_map at line " + std::to_string(lineno));
+            for (int64_t i = 0; i < len; i++) def.lengths_tail.push_back(atoll(t[k++].c_str()));
+            def.size = atoll(t[k++].c_str());
+            def.bus_id = atoll(t[k++].c_str());
+            defs.push_back(def);
+        }
+        prog.io_map[tid] = std::move(defs);
+    }
+
     void parse_create(const std::string &line, int lineno) {
         if (!cur) throw ParseError("create_cmp outside a template");
         auto t = split_ws(line);
@@ -378,9 +424,9 @@ class Parser {
             {"i64.le", OP_I64_LE}, {"i64.gt", OP_I64_GT}, {"i64.ge", OP_I64_GE}, {"i64.eq", OP_I64_EQ},
             {"i64.neq", OP_I64_NEQ}, {"ff.load", OP_FF_LOAD}, {"get_signal", OP_GET_SIGNAL},
             {"get_cmp_signal", OP_GET_CMP_SIGNAL},
-            {"get_template_id", OP_MAPPED_UNSUPPORTED}, {"get_template_signal_position", OP_MAPPED_UNSUPPORTED},
-            {"get_template_signal_size", OP_MAPPED_UNSUPPORTED},
-            {"get_template_signal_dimension", OP_MAPPED_UNSUPPORTED},
+            {"get_template_id", OP_GET_TEMPLATE_ID}, {"get_template_signal_position", OP_GET_TMPL_SIG_POS},
+            {"get_template_signal_size", OP_GET_TMPL_SIG_SIZE},
+            {"get_template_signal_dimension", OP_GET_TMPL_SIG_DIM},
             {"get_template_signal_type", OP_MAPPED_UNSUPPORTED}, {"get_bus_signal_position", OP_MAPPED_UNSUPPORTED},
             {"get_bus_signal_size", OP_MAPPED_UNSUPPORTED}, {"get_bus_signal_dimension", OP_MAPPED_UNSUPPORTED},
             {"get_bus_signal_type", OP_MAPPED_UNSUPPORTED},
@@ -622,6 +668,51 @@ class Parser {
     }
 
   public:
+    // The io-map of a <circuit>.dat (only present when the circuit has mixed component arrays): the file carries no section
+    // sizes, the generated C++ does (`uint get_size_of_*() {return N;}`, circuit.rs:481-497), so both are needed.  Layout:
+    // hash map (24 B entries), witness list (u64), constants (40 B), then M template-instance ids (u32) and per id
+    // { u32 n ; n x { u32 offset, u32 len, len x u32 lengths[1..], u32 size, u32 busId } }   (c_code_generator.rs:617-674,
+    // reader main.cpp:59-92).  Returns the number of template instances read.
+    size_t read_dat_io_map(const std::string &cpp, const unsigned char *dat, size_t dat_len) {
+        auto getter = [&](const char *name, int64_t &out) -> bool {
+            std::string key = std::string("uint ") + name + "() {return ";
+            size_t p = cpp.find(key);
+            if (p == std::string::npos) return false;
+            out = atoll(cpp.c_str() + p + key.size());
+            return true;
+        };
+        int64_t n_hash = 0, n_wit = 0, n_const = 0, n_io = 0;
+        if (!getter("get_size_of_io_map", n_io) || n_io == 0) return 0;
+        if (!getter("get_size_of_input_hashmap", n_hash) || !getter("get_size_of_witness", n_wit) ||
+            !getter("get_size_of_constants", n_const))
+            throw ParseError("the generated C++ does not define the get_size_of_* functions the .dat layout depends on");
+        size_t pos = (size_t)n_hash * 24 + (size_t)n_wit * 8 + (size_t)n_const * 40;
+        auto u32_at = [&](size_t at) -> uint32_t {
+            if (at + 4 > dat_len) throw ParseError("the .dat file ends inside its io-map");
+            return (uint32_t)dat[at] | (uint32_t)dat[at + 1] << 8 | (uint32_t)dat[at + 2] << 16 | (uint32_t)dat[at + 3] << 24;
+        };
+        std::vector<uint32_t> ids;
+        for (int64_t i = 0; i < n_io; i++, pos += 4) ids.push_back(u32_at(pos));
+        for (uint32_t id : ids) {
+            const uint32_t n = u32_at(pos);
+            pos += 4;
+            std::vector<IoDef> defs;
+            for (uint32_t j = 0; j < n; j++) {
+                IoDef d;
+                d.offset = u32_at(pos);
+                const uint32_t len = u32_at(pos + 4);
+                pos += 8;
+                for (uint32_t k = 0; k < len; k++, pos += 4) d.lengths_tail.push_back(u32_at(pos));
+                d.size = u32_at(pos);
+                d.bus_id = u32_at(pos + 4);
+                pos += 8;
+                defs.push_back(std::move(d));
+            }
+            prog.io_map[id] = std::move(defs);
+        }
+        return ids.size();
+    }
+
     // Component creation recovered from the generated <circuit>.cpp (see the header comment).  Call after parse_text /
     // before the program is used: it (re)links the units it touches.
     void recover_creates(const std::string &cpp) {
@@ -646,6 +737,7 @@ class Parser {
             return true;
         };
         int64_t multi_slot = -1, multi_cmp = 0, multi_sig = 0, multi_n = 0, sig_jump = 0, cmp_jump = 0;
+        Code *create_unit = nullptr;
         std::string multi_sym;
         std::vector<int64_t> multi_positions;
         bool in_multi = false;
@@ -666,7 +758,17 @@ class Parser {
                     auto it = prog.code_index.find(line.substr(5, q - 5));
                     if (it != prog.code_index.end() && !prog.codes[it->second].is_function) unit = &prog.codes[it->second];
                 }
+                create_unit = nullptr;
+                q = line.find("_create(uint soffset");
+                if (q != std::string::npos) {
+                    auto it = prog.code_index.find(line.substr(5, q - 5));
+                    if (it != prog.code_index.end() && !prog.codes[it->second].is_function) create_unit = &prog.codes[it->second];
+                }
                 continue;
+            }
+            if (create_unit) {       // ctx->componentMemory[coffset].templateId = <id>;   (template.rs:243-249)
+                int64_t id;
+                if (num_after(line, "].templateId = ", id)) create_unit->template_id = id;
             }
             if (!unit) continue;
             int64_t v;

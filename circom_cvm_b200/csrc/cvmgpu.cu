@@ -268,6 +268,56 @@ extern "C" int cvmgpu_program_load_text2(const char *cvm_text, size_t len, const
     return build_program(parser, n_slots, out);
 }
 
+static bool slurp(const char *path, std::string &out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+extern "C" int cvmgpu_program_load_files(const char *cvm_path, const char *cpp_path, const char *dat_path, uint32_t n_slots,
+                                         cvmgpu_program **out) {
+    if (!cvm_path || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (dat_path && !cpp_path) return fail(CVMGPU_ERR_ARG, "the .dat io-map needs the section sizes of the generated C++ (cpp_path)");
+    cvm::Parser parser;
+    try {
+        parser.parse_file(cvm_path);
+        std::string cpp, dat;
+        if (cpp_path) {
+            if (!slurp(cpp_path, cpp)) return fail(CVMGPU_ERR_IO, std::string("cannot open ") + cpp_path);
+            parser.recover_creates(cpp);
+        }
+        if (dat_path) {
+            if (!slurp(dat_path, dat)) return fail(CVMGPU_ERR_IO, std::string("cannot open ") + dat_path);
+            parser.read_dat_io_map(cpp, (const unsigned char *)dat.data(), dat.size());
+        }
+    } catch (const cvm::ParseError &e) {
+        std::string m = e.what();
+        return fail(m.rfind("cannot open", 0) == 0 ? CVMGPU_ERR_IO : CVMGPU_ERR_PARSE, m);
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    return build_program(parser, n_slots, out);
+}
+
+extern "C" int cvmgpu_program_load_text3(const char *cvm_text, size_t len, const char *cpp_text, size_t cpp_len,
+                                         const void *dat, size_t dat_len, uint32_t n_slots, cvmgpu_program **out) {
+    if (!cvm_text || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (dat && !cpp_text) return fail(CVMGPU_ERR_ARG, "the .dat io-map needs the section sizes of the generated C++ (cpp_text)");
+    cvm::Parser parser;
+    try {
+        parser.parse_text(std::string(cvm_text, len));
+        std::string cpp = cpp_text ? std::string(cpp_text, cpp_len) : std::string();
+        if (cpp_text) parser.recover_creates(cpp);
+        if (dat) parser.read_dat_io_map(cpp, (const unsigned char *)dat, dat_len);
+    } catch (const std::exception &e) {
+        return fail(CVMGPU_ERR_PARSE, e.what());
+    }
+    return build_program(parser, n_slots, out);
+}
+
 extern "C" int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32_t n_slots, cvmgpu_program **out) {
     if (!cvm_text || !out) return fail(CVMGPU_ERR_ARG, "null argument");
     cvm::Parser parser;

@@ -930,9 +930,40 @@ class Tracer {
                     pc++;
                     break;
                 }
+                case OP_GET_TEMPLATE_ID: {
+                    // ctx->componentMemory[mySubcomponents[c]].templateId (load_bucket.rs:262-266)
+                    const int64_t id = prog.codes[(size_t)sub_of(ci, val(f, in.args.at(0))).code].template_id;
+                    if (id < 0) throw TraceError("template id of a sub-component is unknown (header without _<id> suffix)");
+                    set_reg(f, in.dst, i64_av(id));
+                    pc++;
+                    break;
+                }
+                case OP_GET_TMPL_SIG_POS: case OP_GET_TMPL_SIG_DIM: case OP_GET_TMPL_SIG_SIZE: {
+                    // templateInsId2IOSignalInfo[id].defs[code].{offset, lengths[i-1], size}: constants of the component tree
+                    const int64_t id = int_of(val(f, in.args.at(0)), "template id");
+                    const int64_t sc = int_of(val(f, in.args.at(1)), "signal code");
+                    auto it = prog.io_map.find(id);
+                    if (it == prog.io_map.end())
+                        throw TraceError("mapped access (mixed component array): no io-map entry for template instance " +
+                                         std::to_string(id) + " -- the .cvm file does not carry the io-map (circuit.rs:577-621); "
+                                         "load the program with its generated .cpp and .dat (cvmgpu_program_load_files)");
+                    if (sc < 0 || sc >= (int64_t)it->second.size()) throw TraceError("signal code outside the io-map entry");
+                    const cvm::IoDef &d = it->second[(size_t)sc];
+                    int64_t r;
+                    if (in.op == OP_GET_TMPL_SIG_POS) r = d.offset;
+                    else if (in.op == OP_GET_TMPL_SIG_SIZE) r = d.size;
+                    else {
+                        const int64_t i = int_of(val(f, in.args.at(2)), "dimension index");
+                        if (i < 1 || i > (int64_t)d.lengths_tail.size()) throw TraceError("dimension index outside the io-map entry");
+                        r = d.lengths_tail[(size_t)(i - 1)];
+                    }
+                    set_reg(f, in.dst, i64_av(r));
+                    pc++;
+                    break;
+                }
                 case OP_MAPPED_UNSUPPORTED:
-                    throw TraceError("mapped accesses (mixed component arrays / buses) need the io-map, which the "
-                                     ".cvm file does not carry (reference circuit.rs:577-621)");
+                    throw TraceError("bus accesses through the io-map (get_template_signal_type / get_bus_signal_*, "
+                                     "location_rule.rs:143-152) are not implemented");
                 default: throw TraceError("unhandled CVM instruction");
             }
         }

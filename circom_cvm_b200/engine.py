@@ -28,7 +28,7 @@ ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (cs
 
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
-    "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_info_get", "cvmgpu_program_free",
+    "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_load_files", "cvmgpu_program_load_text3", "cvmgpu_program_info_get", "cvmgpu_program_free",
     "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_multi", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
@@ -87,6 +87,8 @@ def lib():
     L.cvmgpu_program_load_text.argtypes = [c_char_p, c_size_t, c_uint32, POINTER(c_void_p)]
     L.cvmgpu_program_load_with_cpp.argtypes = [c_char_p, c_char_p, c_uint32, POINTER(c_void_p)]
     L.cvmgpu_program_load_text2.argtypes = [c_char_p, c_size_t, c_char_p, c_size_t, c_uint32, POINTER(c_void_p)]
+    L.cvmgpu_program_load_files.argtypes = [c_char_p, c_char_p, c_char_p, c_uint32, POINTER(c_void_p)]
+    L.cvmgpu_program_load_text3.argtypes = [c_char_p, c_size_t, c_char_p, c_size_t, c_char_p, c_size_t, c_uint32, POINTER(c_void_p)]
     L.cvmgpu_program_info_get.argtypes = [c_void_p, POINTER(ProgramInfo)]
     L.cvmgpu_program_free.argtypes = [c_void_p]
     L.cvmgpu_program_free.restype = None
@@ -173,17 +175,21 @@ def le_to_ints(arr):
 class WitnessCalculator:
     """Batched counterpart of the reference's generated witness calculator."""
 
-    def __init__(self, cvm_path=None, cvm_text=None, n_slots=0, cpp_path=None, cpp_text=None):
+    def __init__(self, cvm_path=None, cvm_text=None, n_slots=0, cpp_path=None, cpp_text=None, dat_path=None, dat_bytes=None):
         """cpp_path / cpp_text: the generated <circuit>.cpp of the same compile, from which component creation is
-        recovered when the .cvm file does not carry `;;%%create_cmp` lines (the unpatched emitter prints nothing)."""
+        recovered when the .cvm file does not carry `;;%%create_cmp` lines (the unpatched emitter prints nothing).
+        dat_path / dat_bytes: the <circuit>.dat of the same compile, whose io-map circuits with mixed component arrays
+        need (its section sizes are in the .cpp, so it is only read together with it)."""
         L = lib()
         h = c_void_p()
         if cvm_path is not None:
-            _check(L.cvmgpu_program_load_with_cpp(os.fsencode(cvm_path), os.fsencode(cpp_path) if cpp_path else None, n_slots, byref(h)))
+            _check(L.cvmgpu_program_load_files(os.fsencode(cvm_path), os.fsencode(cpp_path) if cpp_path else None,
+                                               os.fsencode(dat_path) if dat_path else None, n_slots, byref(h)))
         else:
             data = cvm_text.encode() if isinstance(cvm_text, str) else cvm_text
             cpp = cpp_text.encode() if isinstance(cpp_text, str) else cpp_text
-            _check(L.cvmgpu_program_load_text2(data, len(data), cpp, len(cpp) if cpp else 0, n_slots, byref(h)))
+            _check(L.cvmgpu_program_load_text3(data, len(data), cpp, len(cpp) if cpp else 0, dat_bytes,
+                                               len(dat_bytes) if dat_bytes else 0, n_slots, byref(h)))
         self._h = h
         info = ProgramInfo()
         info.struct_size = ctypes.sizeof(ProgramInfo)

@@ -138,9 +138,10 @@ def fnv1a(s):
     return h
 
 
-def dat_bytes(main_inputs, witness2signal, constants, prime=BN254_R):
+def dat_bytes(main_inputs, witness2signal, constants, prime=BN254_R, io_map=None):
     """main_inputs: list of (qualified name, first signal id, size).  constants: canonical ints.
-    No io-map / bus sections (only emitted for mixed component arrays / buses)."""
+    io_map: {template instance id: [(offset, dims, element size)] by signal code} (only circuits with mixed component
+    arrays have one, build.rs:520-552); no bus section."""
     n = len(main_inputs)
     size = 256
     while size < n:
@@ -163,6 +164,15 @@ def dat_bytes(main_inputs, witness2signal, constants, prime=BN254_R):
         else:
             short, typ = 0, 0xC0000000
         out.append(struct.pack("<iI", short, typ) + ((c * R) % prime).to_bytes(nbits // 8, "little"))
+    if io_map:                                 # c_code_generator.rs:617-674 (BTreeMap: ascending ids)
+        ids = sorted(io_map)
+        out += [struct.pack("<I", i) for i in ids]
+        for i in ids:
+            out.append(struct.pack("<I", len(io_map[i])))
+            for offset, dims, size in io_map[i]:
+                out.append(struct.pack("<II", offset, max(len(dims) - 1, 0)))
+                out += [struct.pack("<I", d) for d in dims[1:]]
+                out.append(struct.pack("<II", size, 0))
     return b"".join(out)
 
 

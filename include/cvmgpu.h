@@ -132,6 +132,16 @@ int cvmgpu_program_load_text(const char *cvm_text, size_t len, uint32_t n_slots,
 int cvmgpu_program_load_with_cpp(const char *cvm_path, const char *cpp_path, uint32_t n_slots, cvmgpu_program **out);
 int cvmgpu_program_load_text2(const char *cvm_text, size_t len, const char *cpp_text, size_t cpp_len, uint32_t n_slots,
                               cvmgpu_program **out);
+/* Circuits with MIXED component arrays (an array whose positions hold different template instances, e.g. circomlib's
+ * Poseidon) address the signals of those components through the io-map ("mapped" locations, location_rule.rs:86-171;
+ * C++ twin templateInsId2IOSignalInfo, load_bucket.rs:262-318).  The .cvm file does not carry it (circuit.rs:577-621).
+ * It is taken from the `;;%%io_map` comment lines of a patched emitter, or from the <circuit>.dat of the same compile
+ * (c_code_generator.rs:617-674; reader main.cpp:59-92) -- whose section sizes are only in the generated C++
+ * (`get_size_of_*`, circuit.rs:481-497), so dat requires cpp.  cpp / dat may be NULL. */
+int cvmgpu_program_load_files(const char *cvm_path, const char *cpp_path, const char *dat_path, uint32_t n_slots,
+                              cvmgpu_program **out);
+int cvmgpu_program_load_text3(const char *cvm_text, size_t len, const char *cpp_text, size_t cpp_len, const void *dat,
+                              size_t dat_len, uint32_t n_slots, cvmgpu_program **out);
 int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info);
 void cvmgpu_program_free(cvmgpu_program *p);
 /* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table

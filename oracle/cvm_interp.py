@@ -23,6 +23,7 @@ calcwit.cpp/main.cpp/fr.cpp must produce byte-identical .wtns).
 from __future__ import annotations
 
 import re
+import struct
 
 from . import fr_model as M
 
@@ -84,6 +85,7 @@ class Program:
         self.start = None
         self.witness = []
         self.codes = {}
+        self.io_map = {}              # template-instance id -> [(offset, lengths[1..], size, busId)] by signal code
         self.parse(text)
 
     def parse(self, text):
@@ -96,6 +98,11 @@ class Program:
                 t = line.split()
                 pos = [int(x) for x in t[9:]] if len(t) > 8 else None            # "| p0 p1 ...": arrays with undefined positions
                 cur.ins.append(("create_cmp", None, [int(t[1]), t[2].lstrip("$")] + [int(x) for x in t[3:8]] + [pos]))
+                continue
+            if line.startswith(";;%%io_map"):
+                # ;;%%io_map <template id> <n> { offset len <len lengths[1..]> size busId }*  (the .dat record as text)
+                t = [int(x) for x in line.split()[1:]]
+                self.io_map[t[0]] = _io_defs(t, 2, t[1])[0]
                 continue
             if line.startswith(";;") or line.startswith("//"):
                 continue
@@ -278,6 +285,41 @@ class Program:
         assert not stack, "unbalanced control flow in " + c.header
 
 
+def _io_defs(words, pos, n):
+    """n IODef records from a list of u32 (c_code_generator.rs:617-674; reader main.cpp:70-86) -> (defs, next position)"""
+    defs = []
+    for _ in range(n):
+        offset, ln = words[pos], words[pos + 1]
+        tail = list(words[pos + 2:pos + 2 + ln])
+        pos += 2 + ln
+        defs.append((offset, tail, words[pos], words[pos + 1]))
+        pos += 2
+    return defs, pos
+
+
+def read_dat_io_map(prog, cpp_text, dat):
+    """The io-map section of <circuit>.dat (present only with mixed component arrays).  The section sizes are not in the
+    file but in the generated C++ (`uint get_size_of_*() {return N;}`, circuit.rs:481-497; main.cpp:22-92 uses them)."""
+    def size_of(name):
+        m = re.search(r"uint get_size_of_%s\(\) \{return (\d+);\}" % name, cpp_text)
+        return int(m.group(1)) if m else 0
+    n_io = size_of("io_map")
+    if n_io == 0:
+        return
+    start = size_of("input_hashmap") * 24 + size_of("witness") * 8 + size_of("constants") * 40
+    words = struct.unpack("<%dI" % ((len(dat) - start) // 4), dat[start:start + (len(dat) - start) // 4 * 4])
+    ids = words[:n_io]
+    pos = n_io
+    for tid in ids:
+        n = words[pos]
+        prog.io_map[tid], pos = _io_defs(words, pos + 1, n)
+
+
+def _template_id(header):
+    """template headers are <name>_<instance id> (executed_template.rs; the id _create stores in componentMemory)"""
+    return int(header.rsplit("_", 1)[1])
+
+
 class Component:
     __slots__ = ("code", "start", "counter", "subs")
 
@@ -445,10 +487,24 @@ class Machine:
                     for k in range(min(self.val(regs, a[1]), dsize)):
                         dlv[daddr + k] = lvar.get(src + k, 0)
                 return
-            elif op in ("get_template_id", "get_template_signal_position", "get_template_signal_size",
-                        "get_template_signal_dimension", "get_template_signal_type"):
-                raise NotImplementedError("mapped (mixed component array) accesses need the io-map, which the "
-                                          "fork's .cvm does not carry (SURVEY.md F3)")
+            elif op == "get_template_id":                      # load_bucket.rs:262-266: componentMemory[sub].templateId
+                regs[dst] = _template_id(comp.subs[self.val(regs, a[0])].code.header)
+            elif op in ("get_template_signal_position", "get_template_signal_size", "get_template_signal_dimension"):
+                # location_rule.rs:99-146 / load_bucket.rs:262-318: templateInsId2IOSignalInfo[id].defs[code]
+                defs = self.p.io_map.get(self.val(regs, a[0]))
+                if defs is None:
+                    raise NotImplementedError("mapped (mixed component array) access without an io-map entry: the fork's "
+                                              ".cvm does not carry the io-map (SURVEY.md F3); load with the .cpp and .dat")
+                offset, tail, size, _bus = defs[self.val(regs, a[1])]
+                if op == "get_template_signal_position":
+                    regs[dst] = offset
+                elif op == "get_template_signal_size":
+                    regs[dst] = size
+                else:
+                    regs[dst] = tail[self.val(regs, a[2]) - 1]
+            elif op in ("get_template_signal_type", "get_bus_signal_position", "get_bus_signal_size",
+                        "get_bus_signal_dimension", "get_bus_signal_type"):
+                raise NotImplementedError("bus accesses through the io-map are not implemented")
             else:
                 raise ValueError("unknown CVM instruction %r" % op)
 
@@ -535,7 +591,7 @@ def recover_creates(prog, cpp_text):
     flush()
 
 
-def load(path_or_text, cpp_text=None):
+def load(path_or_text, cpp_text=None, dat=None):
     text = path_or_text
     if "\n" not in path_or_text:
         with open(path_or_text) as f:
@@ -543,6 +599,8 @@ def load(path_or_text, cpp_text=None):
     prog = Program(text)
     if cpp_text is not None:
         recover_creates(prog, cpp_text)
+        if dat is not None:
+            read_dat_io_map(prog, cpp_text, dat)
     return prog
 
 

@@ -53,8 +53,10 @@ def circuit(name):
         "isequal": (basic.IsEqual, ()),
         "lessthan8": (basic.LessThan, (8,)),
         "sum3cmp": (basic.Sum3Cmp, ()),
+        "mixedarr": (basic.MixedArr, ()),
         "opszoo": (basic.OpsZoo, ()),
         "poseidon2": (poseidon.Poseidon, (2,)),
+        "poseidon2m": (poseidon.PoseidonMixed, (2,)),     # circomlib 0.5.x shape: `ark` is a mixed component array
         "widesums": (basic.WideSums, ()),
     }
     if name == "eddsa":

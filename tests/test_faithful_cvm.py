@@ -27,14 +27,22 @@ def _texts(name):
     return art, faithful_cvm(art), emit_cpp(art)
 
 
+def _dat(art):
+    """<circuit>.dat of the same compile (tools/circuitgen/build.py write_artifact): carries the io-map of mixed arrays"""
+    from circom_cvm_b200 import formats
+    consts = sorted(art.compiled.constants, key=art.compiled.constants.get)
+    return formats.dat_bytes(art.main_inputs, art.witness, consts, io_map=art.compiled.io_map)
+
+
 @pytest.mark.parametrize("name", sorted(CASES) + ["eddsa"])
 def test_faithful_text_means_the_same(cvmlib, name):
     from circom_cvm_b200 import engine as E
     art, text, cpp = _texts(name)
-    assert ";;%%create_cmp" not in text
+    assert ";;%%create_cmp" not in text and ";;%%io_map" not in text
     ref = I.load(art.cvm)
-    prog = I.load(text, cpp_text=cpp)
-    wc = E.WitnessCalculator(cvm_text=text, cpp_text=cpp)
+    dat = _dat(art)
+    prog = I.load(text, cpp_text=cpp, dat=dat)
+    wc = E.WitnessCalculator(cvm_text=text, cpp_text=cpp, dat_bytes=dat)
     base = E.WitnessCalculator(cvm_text=art.cvm)
     assert wc.n_wires == art.n_wires and wc.n_inputs == art.n_inputs
     assert wc.info.tape_len == base.info.tape_len          # the same trace comes out of both dialects
@@ -76,6 +84,56 @@ def test_missing_component_creation_is_reported(cvmlib):
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text=text)
     assert e.value.code == -3 and "never created" in str(e.value)
+
+
+def test_mapped_accesses_need_the_io_map(cvmlib, tmp_path):
+    """A circuit with a mixed component array prints `get_template_id` / `get_template_signal_position` ... (location_rule.rs:
+    86-171).  As the fork prints it, the .cvm carries no io-map: it loads with the .cpp AND .dat of the same compile, from
+    memory or from files, and says what is missing otherwise."""
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.build import write_artifact
+    art, text, cpp = _texts("mixedarr")
+    assert "get_template_id" in text and "get_template_signal_dimension" in text and "get_template_signal_size" in text
+    with pytest.raises(E.CvmGpuError) as e:
+        E.WitnessCalculator(cvm_text=text, cpp_text=cpp)
+    assert "io-map" in str(e.value)
+    with pytest.raises(NotImplementedError):
+        I.compute_witness(I.load(text, cpp_text=cpp), CASES["mixedarr"][0])
+    with pytest.raises(E.CvmGpuError) as e:        # the .dat alone cannot be read: its section sizes are in the .cpp
+        E.WitnessCalculator(cvm_text=art.cvm, dat_bytes=_dat(art))
+    assert e.value.code == -5 and "section sizes" in str(e.value)          # CVMGPU_ERR_ARG
+    # from files, as a compile leaves them
+    paths = write_artifact(art, str(tmp_path), with_cpp=True)
+    with open(paths["cvm"], "w") as f:
+        f.write(text)
+    with open(paths["dat"], "rb") as f:
+        assert f.read() == _dat(art)
+    wc = E.WitnessCalculator(cvm_path=paths["cvm"], cpp_path=paths["cpp"], dat_path=paths["dat"])
+    base = E.WitnessCalculator(cvm_text=art.cvm)          # the default dialect carries ;;%%io_map lines
+    assert ";;%%io_map" in art.cvm
+    assert wc.info.tape_len == base.info.tape_len and wc.n_wires == art.n_wires
+    with pytest.raises(E.CvmGpuError):
+        E.WitnessCalculator(cvm_path=paths["cvm"], cpp_path=paths["cpp"])
+
+
+def test_dat_io_map_layout():
+    """The io-map section of the .dat as c_code_generator.rs:617-674 writes it (ids, then per id: n, n x {offset, len,
+    lengths[1..], size, busId}), read back by the oracle's reader with the sizes of the generated C++."""
+    import struct
+    art, _text, cpp = _texts("mixedarr")
+    dat = _dat(art)
+    io = art.compiled.io_map
+    assert sorted(io) == [0, 1, 2] and "uint get_size_of_io_map() {return 3;}" in cpp
+    n_words = 3 + sum(1 + sum(4 + max(len(d) - 1, 0) for _o, d, _s in defs) for defs in io.values())
+    words = struct.unpack("<%dI" % n_words, dat[-4 * n_words:])
+    assert words[:3] == (0, 1, 2) and words[3] == 4                       # partial, total, m, w
+    assert words[4:8] == (0, 0, 1, 0)                                     # partial[2]: offset 0, no further dimension
+    assert words[12:17] == (3, 1, 2, 1, 0)                                # m[2][2]: offset 3, lengths[1] = 2
+    prog = I.Program(art.cvm.replace(";;%%io_map", ";;-"))
+    assert prog.io_map == {}
+    I.read_dat_io_map(prog, cpp, dat)
+    assert prog.io_map == I.load(art.cvm).io_map
+    assert prog.io_map[2][2] == (5, [4], 1, 0)
 
 
 def test_literal_register_scope(cvmlib):

@@ -77,8 +77,10 @@ CASES = {
     "isequal": [[5, 5], [5, 6]],
     "lessthan8": [[3, 200], [200, 3], [7, 7]],
     "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
+    "mixedarr": [list(range(1, 10)) + list(range(11, 20)) + [3, 5, 7], [M.Q - 1] * 21, [0] * 21],   # mapped accesses (io-map)
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
     "poseidon2": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],
+    "poseidon2m": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],    # circomlib's shape: mapped accesses to ark[i]
     "widesums": [[M.Q - 1] * 40, [(1 << 253) - 1] * 40, list(range(40)),
                  [(M.Q - 1 - i) if i % 2 else ((1 << 224) - 1 + i) for i in range(40)]],
 }

@@ -50,8 +50,10 @@ CASES = {
     "iszero": [[0], [7]],
     "lessthan8": [[3, 200], [200, 3]],
     "sum3cmp": [[1, 0, 1, 1]],
+    "mixedarr": [list(range(1, 10)) + list(range(11, 20)) + [3, 5, 7], [M.Q - 1] * 21],
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [1 << 200, (1 << 253) + 5, 254]],
     "poseidon2": [[1, 2], [M.Q - 1, 12345678901234567890]],
+    "poseidon2m": [[1, 2], [M.Q - 1, 12345678901234567890]],
 }
 
 
@@ -62,7 +64,7 @@ def test_oracle_matches_reference_runtime_byte_for_byte(name, tmp_path):
     prog = I.load(art.cvm)
     rng = random.Random(21)
     cases = list(CASES[name])
-    if name in ("multiplier2", "opszoo", "poseidon2", "multiplier4", "babyadd4", "earlyret"):
+    if name in ("multiplier2", "opszoo", "poseidon2", "multiplier4", "babyadd4", "earlyret", "mixedarr", "poseidon2m"):
         cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
     for k, values in enumerate(cases):
         jin, wout = tmp_path / ("in%d.json" % k), tmp_path / ("out%d.wtns" % k)

@@ -96,6 +96,6 @@ def write_artifact(art, outdir, with_cpp=False):
             f.write(emit_cpp(art))
         consts = sorted(art.compiled.constants, key=art.compiled.constants.get)
         with open(base + ".dat", "wb") as f:
-            f.write(formats.dat_bytes(art.main_inputs, art.witness, consts))
+            f.write(formats.dat_bytes(art.main_inputs, art.witness, consts, io_map=art.compiled.io_map))
         paths.update(cpp=base + ".cpp", dat=base + ".dat")
     return paths

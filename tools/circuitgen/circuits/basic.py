@@ -254,3 +254,46 @@ def WideSums(T):
             e = term if e is None else e + term
         T.bind(out[k], e)
     T.bind(sq, out[3] * out[5])
+
+
+def WeightedRows(T, n, k):
+    """Sub-component of MixedArr.  `partial` comes first and has n elements, so the offsets of every later signal - and
+    the second dimension of `m` - depend on n: instances with different n have different io-map entries."""
+    n_ = T.param("n", n)
+    k_ = T.param("k", k)
+    partial = T.output("partial", (n,))
+    total = T.output("total")
+    m = T.input("m", (2, n))
+    w = T.input("w")
+    acc = T.var("acc", init=0)
+    j = T.var("j")
+    with T.for_(j, 0, j < n_):
+        T.set(acc, acc + m[0][j] * (k_ + j) + m[1][j])
+        T.bind(partial[j], acc)
+    T.bind(total, acc * w)
+
+
+def MixedArr(T):
+    """A MIXED component array (its positions hold different template instances: n = 2, 3, 4), wired through loop
+    variables: every access to c[i].<signal> is a "mapped" location (location_rule.rs:86-171) that goes through the
+    io-map - scalar and 1-D outputs, a 2-D input (get_template_signal_dimension), an input behind the arrays."""
+    a = T.input("a", (9,))
+    b = T.input("b", (9,))
+    w = T.input("w", (3,))
+    out = T.output("out", (3,))
+    last = T.output("last", (3,))
+    c = T.component("c", (3,))
+    i = T.var("i")
+    j = T.var("j")
+    pos = T.var("pos", init=0)
+    with T.for_(i, 0, i < 3):
+        T.new(c[i], WeightedRows, i + 2, 7)
+    with T.for_(i, 0, i < 3):
+        with T.for_(j, 0, j < i + 2):
+            T.bind(c[i].pin("m")[0][j], a[pos])
+            T.bind(c[i].pin("m")[1][j], b[pos] + 1)
+            T.set(pos, pos + 1)
+        T.bind(c[i].pin("w"), w[i])
+    with T.for_(i, 0, i < 3):
+        T.bind(out[i], c[i].pin("total"))
+        T.bind(last[i], c[i].pin("partial")[i + 1] + c[2].pin("partial")[0])

@@ -182,3 +182,63 @@ def Poseidon(T, n_inputs):
             with T.for_(k, 1, k < t):
                 T.bind(mix[r].pin("in")[k], ark.pin("out")[k])
     T.bind(out, mix[rf + rp - 1].pin("out")[0])
+
+
+def ArkAt(T, t, C, r):
+    """circomlib 0.5.x `template Ark(t, C, r)`: the WHOLE constant table and an offset are the arguments, so every round is
+    a different template instance."""
+    t_ = T.param("t", t)
+    C_ = T.param("C", list(C))
+    r_ = T.param("r", r)
+    inp = T.input("in", (t,))
+    out = T.output("out", (t,))
+    i = T.var("i")
+    with T.for_(i, 0, i < t_):
+        T.bind(out[i], inp[i] + C_[i + r_])
+
+
+def PoseidonMixed(T, n_inputs):
+    """The same permutation written the way circomlib 0.5.x's poseidon.circom writes it: ONE loop over the rounds,
+    `ark[i] = Ark(t, C, t*i)` inside it.  `ark` is therefore a MIXED component array (each position a different template
+    instance) and every `ark[i].in[j]` / `ark[i].out[j]` is a "mapped" access through the io-map (location_rule.rs:86-171),
+    with a component index and a signal index that are loop variables."""
+    t = n_inputs + 1
+    C, M = constants(t)
+    rf, rp = N_ROUNDS_F, N_ROUNDS_P[t - 2]
+    inputs = T.input("inputs", (n_inputs,))
+    out = T.output("out")
+    ark = T.component("ark", (rf + rp,))
+    sigma_f = T.component("sigmaF", (rf, t))
+    sigma_p = T.component("sigmaP", (rp,))
+    mix = T.component("mix", (rf + rp,))
+    i = T.var("i")
+    j = T.var("j")
+    k = T.var("k")
+    with T.for_(i, 0, i < rf + rp):
+        T.new(ark[i], ArkAt, t, C, t * i)
+        with T.for_(j, 0, j < t):
+            with T.if_(i.eq(0)):
+                with T.if_(j > 0):
+                    T.bind(ark[i].pin("in")[j], inputs[j - 1])
+                with T.else_():
+                    T.bind(ark[i].pin("in")[j], 0)
+            with T.else_():
+                T.bind(ark[i].pin("in")[j], mix[i - 1].pin("out")[j])
+        T.new(mix[i], Mix, t, M)
+        with T.if_((i < rf // 2).lor(i >= rp + rf // 2)):
+            with T.if_(i < rf // 2):
+                T.set(k, i)
+            with T.else_():
+                T.set(k, i - rp)
+            with T.for_(j, 0, j < t):
+                T.new(sigma_f[k][j], Sigma)
+                T.bind(sigma_f[k][j].pin("in"), ark[i].pin("out")[j])
+                T.bind(mix[i].pin("in")[j], sigma_f[k][j].pin("out"))
+        with T.else_():
+            T.set(k, i - rf // 2)
+            T.new(sigma_p[k], Sigma)
+            T.bind(sigma_p[k].pin("in"), ark[i].pin("out")[0])
+            T.bind(mix[i].pin("in")[0], sigma_p[k].pin("out"))
+            with T.for_(j, 1, j < t):
+                T.bind(mix[i].pin("in")[j], ark[i].pin("out")[j])
+    T.bind(out, mix[rf + rp - 1].pin("out")[0])

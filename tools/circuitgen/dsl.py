@@ -252,7 +252,9 @@ class Body:
         return _Block(self, st.then)
 
     def else_(self):
-        return _Block(self, self._last_if.other)
+        st = self._stack[-1][-1]        # the `if` that was just closed in THIS block (not a nested one)
+        assert isinstance(st, If), "else_ must directly follow an if_ block"
+        return _Block(self, st.other)
 
     def assert_(self, e):
         self._emit(Assert(wrap(e)))

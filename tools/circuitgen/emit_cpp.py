@@ -12,7 +12,7 @@ Shapes followed (compiler/src/...):
 """
 from __future__ import annotations
 
-from .translate import (AssertB, BranchB, CallB, Compute, CreateCmpB, Load, LoopB, ReturnB, Store, Value)
+from .translate import (AssertB, BranchB, CallB, Compute, CreateCmpB, Load, LoopB, Mapped, ReturnB, Store, Value)
 
 FR_OP = {"add": "Fr_add", "div": "Fr_div", "mul": "Fr_mul", "sub": "Fr_sub", "pow": "Fr_pow", "idiv": "Fr_idiv",
          "mod": "Fr_mod", "shl": "Fr_shl", "shr": "Fr_shr", "leq": "Fr_leq", "geq": "Fr_geq", "lt": "Fr_lt",
@@ -39,6 +39,10 @@ class CppEmitter:
         raise TypeError(n)
 
     def location(self, atype, loc, cmp, depth):           # load_bucket.rs:249-457
+        if isinstance(loc, Mapped):
+            p2, c = self.expr(cmp, depth)
+            pro, idx = self.mapped_load(loc, c, depth)
+            return p2 + pro, "&ctx->signalValues[ctx->componentMemory[mySubcomponents[%s]].signalStart + %s]" % (c, idx)
         pro, idx = self.expr(loc, depth)
         if atype == "var":
             return pro, "&lvar[%s]" % idx
@@ -46,6 +50,60 @@ class CppEmitter:
             return pro, "&signalValues[mySignalStart + %s]" % idx
         p2, c = self.expr(cmp, depth)
         return pro + p2, "&ctx->signalValues[ctx->componentMemory[mySubcomponents[%s]].signalStart + %s]" % (c, idx)
+
+    def mapped_load(self, loc, cmp_expr, depth):           # load_bucket.rs:262-318 (no bus accesses)
+        cur_def = "ctx->templateInsId2IOSignalInfo[ctx->componentMemory[mySubcomponents[%s]].templateId].defs[%d]" % (cmp_expr, loc.code)
+        access = cur_def + ".offset"
+        pro = []
+        if loc.indexes:
+            p0, map_index = self.expr(loc.indexes[0], depth)
+            pro += p0
+            for i in range(1, len(loc.indexes)):
+                pi, e = self.expr(loc.indexes[i], depth)
+                pro += pi
+                map_index = "(%s)*(%s.lengths[%d])+%s" % (map_index, cur_def, i - 1, e)
+            if loc.ndims - len(loc.indexes) > 0:
+                pro.append("//There is a difference %d;" % (loc.ndims - len(loc.indexes)))
+                for i in range(len(loc.indexes), loc.ndims):
+                    map_index = "%s*%s.lengths[%d]" % (map_index, cur_def, i - 1)
+            access = "%s+(%s)*%s.size" % (access, map_index, cur_def)
+        return pro, access
+
+    def mapped_store(self, loc, cmp_expr):                  # store_bucket.rs:500-566 (no bus accesses)
+        tid = "ctx->componentMemory[mySubcomponents[%s]].templateId" % cmp_expr
+        access = "ctx->templateInsId2IOSignalInfo[%s].defs[%d].offset" % (tid, loc.code)
+        pro = []
+        if loc.indexes:
+            pro += ["{", "uint map_accesses_aux[1];", "{",
+                    "IOFieldDef *cur_def = &(ctx->templateInsId2IOSignalInfo[%s].defs[%d]);" % (tid, loc.code),
+                    "{", "uint map_index_aux[%d];" % len(loc.indexes)]
+            p0, e0 = self.expr(loc.indexes[0], 0)
+            pro += p0
+            pro.append("map_index_aux[0]=%s;" % e0)
+            map_index = "map_index_aux[0]"
+            for i in range(1, len(loc.indexes)):
+                pi, e = self.expr(loc.indexes[i], 0)
+                pro += pi
+                pro.append("map_index_aux[%d]=%s;" % (i, e))
+                map_index = "(%s)*cur_def->lengths[%d]+map_index_aux[%d]" % (map_index, i - 1, i)
+            if loc.ndims - len(loc.indexes) > 0:
+                pro.append("//There is a difference %d;" % (loc.ndims - len(loc.indexes)))
+                for i in range(len(loc.indexes), loc.ndims):
+                    map_index = "%s*cur_def->lengths[%d]" % (map_index, i - 1)
+            pro.append("map_accesses_aux[0] = %s*cur_def->size;" % map_index)
+            pro += ["}", "}"]
+            access += "+map_accesses_aux[0]"
+        return pro, access, bool(loc.indexes)
+
+    def sub_dest(self, d, out):
+        """destination inside a sub-component (cmp_index_ref already declared) -> (C expression, close the extra block?)"""
+        if isinstance(d.loc, Mapped):
+            pro, idx, opened = self.mapped_store(d.loc, "cmp_index_ref")
+        else:
+            pro, idx = self.expr(d.loc, 0)
+            opened = False
+        out += pro
+        return "&ctx->signalValues[ctx->componentMemory[mySubcomponents[cmp_index_ref]].signalStart + %s]" % idx, opened
 
     def compute(self, n, depth):                          # compute_bucket.rs:314-469
         op = n.op
@@ -88,7 +146,10 @@ class CppEmitter:
                 out.append("%s -= %d;" % (counter, size))
                 out.append("assert(%s > 0);" % counter)
             return out
-        call = "%s_run(mySubcomponents[%s],ctx);" % (st.sub_header, cmp_expr)
+        if st.sub_header is None:        # mapped destination: through the table of run functions (store_bucket.rs:706-710)
+            call = "(*_functionTable[ctx->componentMemory[mySubcomponents[%s]].templateId])(mySubcomponents[%s],ctx);" % (cmp_expr, cmp_expr)
+        else:
+            call = "%s_run(mySubcomponents[%s],ctx);" % (st.sub_header, cmp_expr)
         if st.status == "unknown":
             out.append("if(!(%s -= %d)){" % (counter, size))
             out.append(call)
@@ -108,10 +169,9 @@ class CppEmitter:
             out += p
             out.append("uint cmp_index_ref = %s;" % c)
             cmp_expr = "cmp_index_ref"
-            pro, idx = self.expr(st.loc, 0)
-            out += pro
-            dest = "&ctx->signalValues[ctx->componentMemory[mySubcomponents[cmp_index_ref]].signalStart + %s]" % idx
+            dest, opened = self.sub_dest(st, out)
         else:
+            opened = False
             pro, dest = self.location(st.atype, st.loc, None, 0)
             out += pro
         out.append("PFrElement aux_dest = %s;" % dest)
@@ -125,6 +185,8 @@ class CppEmitter:
             out.append("Fr_copy(aux_dest,%s);" % src)
         if st.atype == "sub":
             out += self.trigger(st, cmp_expr, st.size)
+        if opened:
+            out.append("}")             # the map_accesses_aux block (store_bucket.rs:510,565 + :809)
         out.append("}")
         return out
 
@@ -146,15 +208,16 @@ class CppEmitter:
             out += p
             out.append("uint cmp_index_ref = %s;" % c)
             cmp_expr = "cmp_index_ref"
-            pro, idx = self.expr(d.loc, 0)
-            out += pro
-            dest = "&ctx->signalValues[ctx->componentMemory[mySubcomponents[cmp_index_ref]].signalStart + %s]" % idx
+            dest, opened = self.sub_dest(d, out)
         else:
+            opened = False
             pro, dest = self.location(d.atype, d.loc, None, 0)
             out += pro
         out.append("%s(ctx,lvarcall,myId,%s,%d);" % (n.symbol, dest, d.size))
         if d.atype == "sub":
             out += self.trigger(d, cmp_expr, d.size)
+        if opened:
+            out.append("}")
         out.append("}")
         return out
 
@@ -303,7 +366,7 @@ class CppEmitter:
               "uint get_size_of_input_hashmap() {return %d;}\n" % n_in_map,
               "uint get_size_of_witness() {return %d;}\n" % len(art.witness),
               "uint get_size_of_constants() {return %d;}\n" % len(c.constants),
-              "uint get_size_of_io_map() {return 0;}\n",
+              "uint get_size_of_io_map() {return %d;}\n" % len(c.io_map),
               "uint get_size_of_bus_field_map() {return 0;}\n"]
         o += ["void release_memory_component(Circom_CalcWit* ctx, uint pos) {", "if (pos != 0){",
               "if(ctx->componentMemory[pos].subcomponents)", "delete []ctx->componentMemory[pos].subcomponents;",

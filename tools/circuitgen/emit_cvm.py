@@ -14,6 +14,8 @@ generated .cpp (cvmgpu_program_load_with_cpp).  The default mode keeps the depar
     addresses would be assigned to (`i64.5 = i64.add i64.5 i64.1`, store_bucket.rs:1026-1028);
     we first move literal addresses into fresh registers.
   * array equality (`===` on arrays) is emitted as a counted loop over address registers, see array_eq().
+  * the io-map that "mapped" accesses (mixed component arrays) read is not in the fork's .cvm at all (circuit.rs:577-621);
+    we emit one `;;%%io_map <template id> <n> {offset len lengths[1..] size busId}*` line per template instance.
   * multi-element `return` passes the *address* register as documented in
     mkdocs/docs/circom-language/formats/circom-virtual-machine.md:201-203 (the emitter at
     return_bucket.rs:131 loads the first element instead, which cannot work).
@@ -21,7 +23,7 @@ generated .cpp (cvmgpu_program_load_with_cpp).  The default mode keeps the depar
 from __future__ import annotations
 
 from .dsl import P
-from .translate import (AssertB, BranchB, CallB, Compute, CreateCmpB, Load, LoopB, ReturnB, Store, Value)
+from .translate import (AssertB, BranchB, CallB, Compute, CreateCmpB, Load, LoopB, Mapped, ReturnB, Store, Value)
 
 OPNAME = {
     "mul": ("ff.mul", "MUL"), "div": ("ff.div", "DIV"), "add": ("ff.add", "ADD"), "sub": ("ff.sub", "SUB"),
@@ -66,11 +68,53 @@ class CvmEmitter:
         raise TypeError(n)
 
     def location(self, atype, loc, cmp):        # location_rule.rs:66-85 (Indexed)
+        if isinstance(loc, Mapped):
+            return self.mapped(loc, cmp)
         ins, vloc = self.expr(loc)
         if atype == "sub":
             ins2, vcmp = self.expr(cmp)
             return ins + ins2, (vcmp, vloc)
         return ins, (None, vloc)
+
+    def mapped(self, loc, cmp):                 # location_rule.rs:86-171 (Mapped; no bus accesses)
+        ins = [";; is subcomponent mapped"]
+        i2, vcmp = self.expr(cmp)
+        ins += i2
+        tid = self.fresh()
+        ins.append("%s = get_template_id %s" % (tid, vcmp))
+        sp = self.fresh()
+        ins.append("%s = get_template_signal_position %s %d" % (sp, tid, loc.code))
+        if not loc.indexes:
+            return ins, (vcmp, sp)
+        i3, prev = self.expr(loc.indexes[0])
+        ins += i3
+        for i in range(1, len(loc.indexes)):
+            dimi = self.fresh()
+            ins.append("%s =  get_template_signal_dimension %s %d %d" % (dimi, tid, loc.code, i))
+            i4, vidx = self.expr(loc.indexes[i])
+            ins += i4
+            curmul = self.fresh()
+            ins.append("%s = i64.mul %s %s" % (curmul, prev, dimi))
+            cursize = self.fresh()
+            ins.append("%s = i64.add %s %s" % (cursize, curmul, vidx))
+            prev = cursize
+        diff = loc.ndims - len(loc.indexes)
+        if diff > 0:
+            # as printed: diff-1 factors starting at dimension <number of accesses> (= 1 without buses), :135-140
+            for i in range(diff - 1):
+                dimi = self.fresh()
+                ins.append("%s =  get_template_signal_dimension %s %d %d" % (dimi, tid, loc.code, 1 + i))
+                cursize = self.fresh()
+                ins.append("%s = i64.mul %s %s" % (cursize, prev, dimi))
+                prev = cursize
+        vsize = self.fresh()
+        ins.append("%s =  get_template_signal_size %s %d" % (vsize, tid, loc.code))
+        finalsize = self.fresh()
+        ins.append("%s = i64.mul %s %s" % (finalsize, prev, vsize))
+        access = self.fresh()
+        ins.append("%s = i64.add %s %s" % (access, sp, prev))
+        ins.append(";; end of load bucket")
+        return ins, (vcmp, access)
 
     def load(self, n):              # load_bucket.rs:459-485
         ins = [";; load bucket"]
@@ -367,6 +411,11 @@ class CvmEmitter:
         o += [";; Main template", "%%%%start %s" % main.header, "\n"]
         o += [";; Component creation mode (implicit/explicit)", "%%components explicit", "\n"]
         o += [";; Witness (signal list)", "%%witness" + "".join(" %d" % s for s in c.witness), "\n"]
+        if not self.faithful:       # extension (a comment to other consumers): the .dat io-map records as text
+            for tid, defs in sorted(getattr(c, "io_map", {}).items()):
+                rec = "".join(" %d %d%s %d 0" % (off, max(len(dims) - 1, 0), "".join(" %d" % d for d in dims[1:]), size)
+                              for off, dims, size in defs)
+                o.append(";;%%%%io_map %d %d%s" % (tid, len(defs), rec))
         for f in c.functions:      # function.rs:137-168
             ins = "".join(" " + declare_variable(p.dims) for p in f.params)
             o.append("%%%%function %s [%s] [%s]" % (f.header, declare_variable(f.returns), ins))

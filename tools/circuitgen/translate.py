@@ -29,6 +29,12 @@ class Compute:
     def __init__(self, op, args): self.op, self.args = op, args
 
 
+class Mapped:
+    """LocationRule::Mapped (location_rule.rs:41-45): a signal of a component of a MIXED array (its instances are not
+    all the same template instance), addressed through the io-map at run time: signal code + one index list."""
+    def __init__(self, code, indexes, ndims): self.code, self.indexes, self.ndims = code, indexes, ndims
+
+
 class Store:
     def __init__(self, atype, loc, cmp, src, size, line, cmp_name=None):
         self.atype, self.loc, self.cmp, self.src, self.size, self.line = atype, loc, cmp, src, size, line
@@ -94,6 +100,19 @@ def fold_addr(terms):
     return acc
 
 
+def io_signals(inst):
+    """outputs then inputs in declaration order = the order of TemplateInstance::wires, whose positions are the signal
+    codes (translate.rs:77-86; build.rs:531-552 keeps the non-intermediate ones)."""
+    return [s for xt in ("out", "in") for s in inst.tmpl.signals if s.xtype == xt]
+
+
+def signal_code(inst, name):
+    for k, s in enumerate(io_signals(inst)):
+        if s.name == name:
+            return k
+    raise CircuitError("%s is not an input/output of %s" % (name, inst.name))
+
+
 class _Translator:
     def __init__(self, prog, body_owner, inst=None):
         self.prog, self.owner, self.inst = prog, body_owner, inst
@@ -133,11 +152,28 @@ class _Translator:
         assert cn == 1
         subs = {id(s): s for s in sym.instances.values()}
         if len(subs) != 1:
-            raise CircuitError("mixed component arrays (%s) are not supported by the generator yet" % sym.name)
+            return self.mapped_location(ref, cmp_loc, list(subs.values()))
         sub = next(iter(subs.values()))
         ss = sub.sigsym[ref.sig]
         loc, n = self.address(ss.offset, ss.dims, ref.sigidx)
         return "sub", loc, cmp_loc, n, sym, (sub, ss)
+
+    def mapped_location(self, ref, cmp_loc, subs):
+        """translate.rs:1009-1041 (ClusterType::Mixed): the offset, the dimensions and the size of the signal come from
+        the io-map entry of whichever template instance sits in the slot (build.rs:520-552)."""
+        sym = ref.sym
+        infos = [(signal_code(s, ref.sig), s.sigsym[ref.sig]) for s in subs]
+        code, first = infos[0]
+        if any(c != code or len(ss.dims) != len(first.dims) or ss.xtype != first.xtype for c, ss in infos):
+            raise CircuitError("instances of the mixed array %s disagree on signal %s" % (sym.name, ref.sig))
+        sizes = {prod(ss.dims[len(ref.sigidx):]) for _c, ss in infos}
+        if len(sizes) != 1:
+            raise CircuitError("copy of %s.%s whose length differs between instances (SizeOption::Multiple) is not "
+                               "supported by the generator" % (sym.name, ref.sig))
+        idx = []
+        for i in ref.sigidx:
+            idx.append(u32(i.v) if isinstance(i, Num) else Compute("to_addr", [self.expr(i)]))
+        return "sub", Mapped(code, idx, len(first.dims)), cmp_loc, sizes.pop(), sym, (None, first)
 
     # ---- expressions
     def expr(self, e):
@@ -165,7 +201,7 @@ class _Translator:
             sub, ss = subinfo
             if ss.xtype != "in":
                 raise CircuitError("assignment to a non-input signal of a sub-component")
-            st.sub_header = sub.header
+            st.sub_header = sub.header if sub is not None else None      # None: through _functionTable[templateId]
         return st
 
     def call(self, dst, e, line):
@@ -184,7 +220,7 @@ class _Translator:
         atype, loc, cmp, n, csym, subinfo = self.location(dst)
         dest = Store(atype, loc, cmp, None, n, line, cmp_name=csym.name if csym else None)
         if atype == "sub":
-            dest.sub_header = subinfo[0].header
+            dest.sub_header = subinfo[0].header if subinfo[0] is not None else None
         self.max_arena = max(self.max_arena, fcode.arena)
         return CallB(fcode.header, args, dest, line, fcode.arena)
 
@@ -232,6 +268,8 @@ def _collect_values(node, acc):
     if isinstance(node, Value):
         if node.kind == "ff":
             acc.setdefault(node.value, len(acc))
+    elif isinstance(node, Mapped):
+        for a in node.indexes: _collect_values(a, acc)
     elif isinstance(node, Load):
         _collect_values(node.loc, acc)
         if node.cmp is not None: _collect_values(node.cmp, acc)
@@ -313,6 +351,14 @@ def build_inputs_info(code):
 
 
 # ------------------------------------------------------------------ drivers
+def _position(dims, flat):
+    out = []
+    for d in reversed(dims):
+        out.append(flat % d)
+        flat //= d
+    return "".join("[%d]" % i for i in reversed(out))
+
+
 def translate_template(prog, inst):
     t = inst.tmpl
     tr = _Translator(prog, t, inst)
@@ -328,8 +374,15 @@ def translate_template(prog, inst):
         subs = [s for s in inst.subs if s[0] is c]
         first = subs[0]
         kinds = {id(s[2]) for s in subs}
-        if len(kinds) != 1:
-            raise CircuitError("mixed component arrays (%s) are not supported by the generator yet" % c.name)
+        if len(kinds) != 1:             # mixed cluster: one bucket per position (translate.rs:444-507)
+            for (_c, flat, sub, sig_off, cmp_off) in subs:
+                prog.templates_in_mixed.add(sub.id)
+                code.append(CreateCmpB(
+                    line=0, symbol=sub.header, template_id=sub.id, name=c.name + _position(c.dims, flat),
+                    slot=c.offset + flat, signal_offset=sig_off, signal_offset_jump=0,
+                    component_offset=cmp_off, component_offset_jump=0,
+                    number_of_cmp=1, dimensions=list(c.dims), has_inputs=sub.n_in > 0))
+            continue
         sub = first[2]
         code.append(CreateCmpB(
             line=0, symbol=sub.header, template_id=sub.id, name=c.name, slot=c.offset,
@@ -374,6 +427,7 @@ class Compiled:
 def compile_program(prog, constraint_assert_disabled=False):
     prog.constraint_assert_disabled = constraint_assert_disabled
     prog._fcodes = {}
+    prog.templates_in_mixed = set()
 
     def function_code(fn):
         if fn.name not in prog._fcodes:
@@ -394,4 +448,7 @@ def compile_program(prog, constraint_assert_disabled=False):
         for n in f.code: _collect_values(n, consts)
     out.constants = consts          # value -> index in the constant table
     out.main = prog.main
+    # io-map (build.rs:520-552): template instance id -> [(offset, dims, element size)] indexed by signal code
+    out.io_map = {i: [(sg.offset, tuple(sg.dims), 1) for sg in io_signals(prog.order[i])]
+                  for i in sorted(prog.templates_in_mixed)}
     return out
