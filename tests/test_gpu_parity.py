@@ -393,6 +393,54 @@ def test_process_abi_drop_in(E, name, doc, tmp_path):
         assert out.read_bytes() == formats.wtns_bytes(I.compute_witness(I.load(art.cvm), row))
 
 
+@pytest.mark.parametrize("name,doc", [
+    ("poseidon2m", {"inputs": ["1", "2"]}),
+    ("mixedarr", {"a": [str(v) for v in range(1, 10)], "b": [str(v) for v in range(11, 20)], "w": ["3", "5", "7"]}),
+])
+def test_process_drop_in_on_unpatched_compiler_outputs(E, name, doc, tmp_path):
+    """The three files an UNPATCHED compile leaves (--cvm text as the fork prints it: no component creation, no io-map;
+    the generated .cpp; the .dat) for circuits with a mixed component array: both entry-point programs pick the .cpp and
+    .dat up next to the .cvm and write the bytes the reference's own binary writes."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from tools.circuitgen.build import faithful_cvm, write_artifact
+    art = circuit(name)
+    paths = write_artifact(art, str(tmp_path), with_cpp=True)
+    text = faithful_cvm(art)
+    assert ";;%%" not in text and "get_template_id" in text
+    with open(paths["cvm"], "w") as f:
+        f.write(text)
+    jin = tmp_path / "input.json"
+    jin.write_text(json.dumps(doc))
+    out = tmp_path / "ours.wtns"
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, "-m", "circom_cvm_b200", paths["cvm"], str(jin), str(out), "--r1cs", paths["r1cs"]],
+                   check=True, env=env, cwd=ROOT, timeout=300)
+    from circom_cvm_b200 import build as cbuild
+    cbuild.build()
+    nout = tmp_path / "native.wtns"
+    subprocess.run([cbuild.CALC, paths["cvm"], str(jin), str(nout), "--r1cs", paths["r1cs"]], check=True, timeout=300)
+    assert nout.read_bytes() == out.read_bytes()
+    ref = os.path.join(ROOT, "oracle", "_ref", name)
+    if os.path.exists(ref):
+        rout = tmp_path / "ref.wtns"
+        subprocess.run([ref, str(jin), str(rout)], check=True, timeout=60)
+        assert out.read_bytes() == rout.read_bytes()
+    if name == "poseidon2m":
+        from circom_cvm_b200 import formats
+        from tools.circuitgen.circuits import poseidon
+        assert formats.read_wtns(out.read_bytes())["values"][1] == poseidon.poseidon_hash([1, 2])
+    # without the .cpp/.dat next to it the same text cannot run, and says why
+    lone = tmp_path / "lone"
+    lone.mkdir()
+    (lone / "c.cvm").write_text(text)
+    r = subprocess.run([cbuild.CALC, str(lone / "c.cvm"), str(jin), str(lone / "o.wtns")], capture_output=True, timeout=300)
+    assert r.returncode != 0 and b"never created" in r.stderr
+
+
 def test_sha256_batch(E, tmp_path):
     """Config 3 shape (bit-decomposition heavy): Sha256 over 64-bit messages, checked against hashlib for every
     witness, against the CVM oracle for one, and through the R1CS check."""
