@@ -291,7 +291,13 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
     else:
         inputs = torch.randint(0, 256, (B, wc.n_inputs, 32), dtype=torch.uint8, device=dev, generator=g)
         inputs[:, :, 31] &= 0x1F          # < 2^253 < q: canonical field elements
-    store_bytes = wc.store_bytes(CH)
+    # field programs run ONE kernel: the tape with the R1CS check scheduled into it (csrc/fused.hpp); bit-heavy ones run the
+    # tape and then the check kernels.  Either way this is what cvmgpu_witness_batch_checked_dev launches.
+    finfo = wc.fused_info(r1)
+    fused = finfo is not None
+    if fused:
+        finfo = finfo.asdict()
+    store_bytes = wc.store_bytes_checked(r1, CH)
     store = torch.empty(store_bytes, dtype=torch.uint8, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     bad = torch.empty(B, dtype=torch.int32, device=dev)
@@ -307,10 +313,17 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         n = min(CH, B - k * CH)
         r1.check_store_dev(wc, store, n, CH, bad[k * CH:], stream)
 
+    def gen_checked(k):
+        n = min(CH, B - k * CH)
+        wc.run_checked_dev(r1, inputs[k * CH:], n, CH, store, status[k * CH:], bad[k * CH:], stream)
+
     for _ in range(args.warmup):
         for k in range(n_chunks):
-            gen(k)
-            check(k)
+            if fused:
+                gen_checked(k)
+            else:
+                gen(k)
+                check(k)
     torch.cuda.synchronize()
     rinfo = r1.refresh_info().asdict()
     if world > 1:
@@ -327,9 +340,13 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         if flush is not None:
             flush.zero_()
         ev[3 * k].record()
-        gen(k % n_chunks)
-        ev[3 * k + 1].record()
-        check(k % n_chunks)
+        if fused:
+            gen_checked(k % n_chunks)
+            ev[3 * k + 1].record()
+        else:
+            gen(k % n_chunks)
+            ev[3 * k + 1].record()
+            check(k % n_chunks)
         ev[3 * k + 2].record()
     t_end.record()
     torch.cuda.synchronize()
@@ -343,6 +360,22 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
     # the L2 flush (when there is one) sits between the iterations, outside the step
     ms_total = (ms_tape + ms_check) * args.steps if flush is not None else t_start.elapsed_time(t_end)
     n_fail = int((status != 0).sum()) + int((bad != -1).sum())
+    sep_tape = sep_check = None
+    if fused:
+        # the two stand-alone kernels on the same data, outside the step (what CVMGPU_FUSED=0 would run): reported next to it
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        gen(0)
+        check(0)
+        e[0].record()
+        for _ in range(3):
+            gen(0)
+        e[1].record()
+        for _ in range(3):
+            check(0)
+        e[2].record()
+        torch.cuda.synchronize()
+        sep_tape, sep_check = e[0].elapsed_time(e[1]) / 3 * n_chunks, e[1].elapsed_time(e[2]) / 3 * n_chunks
+        n_fail += int((bad[:min(CH, B)] != -1).sum())
     # the path's only exchange (north_star): the final gather of the per-witness flags to rank 0, outside the timed region
     gather_ms = 0.0
     if world > 1:
@@ -458,6 +491,9 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         t = traffic.get(kernel)
         return None if t is None else t["dram_bytes_per_witness"] * CH      # per launch, like `achieved`
 
+    ms_fused = ms_tape if fused else None
+    if fused:           # the stand-alone kernels were timed outside the step (rank 0's numbers)
+        ms_tape, ms_check = sep_tape, sep_check
     t_tape, t_check = ms_tape * 1e-3, ms_check * 1e-3
     tape_stored = B * ((info["tape_st"] - info["tape_spill_st_bool"]) * 32 + (info["tape_ld"] - info["tape_ld_bool"]) * 32
                        + info["n_inputs"] * 32)
@@ -507,10 +543,35 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
                     "achieved": export_bytes / (ms_export * 1e-3) / 1e9, "frac": export_bytes / (ms_export * 1e-3) / 1e9 / hbm_peak,
                     "bytes": "B * (stored wires read + nWires * 32 canonical AoS written); timed alone, outside `value`"}},
     }
-    dom = "tape_kernel" if ms_tape >= ms_check else "r1cs_kernel"
+    if fused:
+        # ONE kernel does both: integer-multiply bound.  Algorithmic work = the reference program's multiplications plus the
+        # multiply-accumulates of the constraint system as the stand-alone check counts them; executed = the fused tape's
+        # own count.  Bytes = what it has to write (the value store) + inputs: it reads no wire back.
+        t_f = ms_fused * 1e-3
+        alg_macs = info["ref_mul"] * MACS_PER_MUL + rinfo["macs"]
+        fused_bytes = B * ((finfo["tape_st"] - finfo["tape_spill_st_bool"]) * 32 + (finfo["tape_ld"] - finfo["tape_ld_bool"]) * 32
+                           + info["n_inputs"] * 32 + 8)
+        for kk in ("tape_kernel", "r1cs_kernel"):
+            kernels[kk]["note"] = "stand-alone kernel timed outside the step, for comparison (the step runs tape_check_kernel)"
+        kernels["tape_check_kernel"] = {
+            "ms": ms_fused, "launches_per_step": n_chunks, "what": "tape_kernel running the tape with the R1CS check scheduled into it "
+            "(csrc/fused.hpp): %d instructions (tape alone: %d), %d slots" % (finfo["tape_len"], info["tape_len"], finfo["n_slots"]),
+            "imad": {"bound": "imad", "unit": "Tmac/s", "peak": peak_macs / 1e12,
+                     "achieved": B * alg_macs / t_f / 1e12, "frac": B * alg_macs / t_f / peak_macs,
+                     "achieved_executed": B * finfo["tape_macs"] / t_f / 1e12, "frac_executed": B * finfo["tape_macs"] / t_f / peak_macs,
+                     "algorithmic_unit": "%d macs per field multiplication x N_mul=%d (reference program) + %d macs of the constraint "
+                                         "system (64 per general-coefficient term, 72 per reduction, 136 per product) per witness; "
+                                         "executed: %d macs per witness" % (MACS_PER_MUL, info["ref_mul"], rinfo["macs"], finfo["tape_macs"])},
+            "hbm": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "peak_kind": peak_kind,
+                    "achieved": fused_bytes / t_f / 1e9, "frac": fused_bytes / t_f / 1e9 / hbm_peak,
+                    "bytes": "B*(field-row stores + reloads)*32 + inputs + flags: no wire is read back for the check",
+                    "traffic": dram("tape_check_kernel")},
+            "constraints_per_s": world * B * rinfo["n_constraints"] / t_f,
+        }
+    dom = "tape_check_kernel" if fused else ("tape_kernel" if ms_tape >= ms_check else "r1cs_kernel")
     kd = kernels[dom]
     # the view SURVEY 8d prescribes for the dominant kernel: witness generation = IMAD, check = HBM
-    view, other = ("imad", "hbm") if dom == "tape_kernel" else ("hbm", "imad")
+    view, other = ("hbm", "imad") if dom == "r1cs_kernel" else ("imad", "hbm")
     roofline = dict(kd[view])
     roofline.update({"kernel": dom, "ms": kd["ms"],
                      "peak_source": peak_src if view == "imad" else "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_kind,
@@ -532,16 +593,20 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
                          else ("value store %.0f MB: a 256 MB buffer is rewritten between timed iterations (L2 flush, outside "
                                "the per-kernel events that make up the step)" % (store_bytes / 1e6)),
                    "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
-                   "n_slots": info["n_slots"], "n_bit_slots": info["n_bslots"], "tape_len": info["tape_len"],
+                   "n_slots": (finfo if fused else info)["n_slots"], "n_bit_slots": (finfo if fused else info)["n_bslots"],
+                   "tape_len": (finfo if fused else info)["tape_len"],
+                   "check": ("scheduled into the tape: one kernel per launch (csrc/fused.hpp)" if fused
+                             else "separate kernels on the value store (r1cs_kernel + r1cs_table_kernel)"),
                    "stored_bytes_per_witness": stored_per_witness, "failures": n_fail, "flags_gather_ms": gather_ms},
-        "kernels_ms": {"tape_kernel": ms_tape, "r1cs_kernel": ms_check},
+        "kernels_ms": {"tape_check_kernel": ms_fused} if fused else {"tape_kernel": ms_tape, "r1cs_kernel": ms_check},
+        "separate_kernels_ms": {"tape_kernel": ms_tape, "r1cs_kernel": ms_check, "note": "timed outside the step"} if fused else None,
         "witnesses_per_s_gen_only": world * B / (ms_tape * 1e-3),
         "constraints_per_s_check_only": world * B * rinfo["n_constraints"] / (ms_check * 1e-3),
         "roofline": roofline, "kernels": kernels,
         "cpu_baseline": cpu, "e2e": e2e, "e2e_public_outputs": e2e_public, "e2e_flags_only": e2e_flags,
-        "gpu_launches": 2 * n_launch,
+        "gpu_launches": n_launch if fused else 2 * n_launch,
         "clocks": sampler.summary(),
-        "program": info, "r1cs": rinfo,
+        "program": info, "fused_program": finfo if fused else None, "r1cs": rinfo,
     }
     wc.close()
     r1.close()
@@ -594,7 +659,7 @@ def main():
         # BASELINE.json's metric names two circuits: the second one (config 3) rides in the same line under `secondary`
         sec = bench_workload(args, sec_name, dist_ctx, peak_ctx)
         if rank == 0:
-            keep = ("metric", "value", "unit", "ms_per_step", "config", "kernels_ms", "witnesses_per_s_gen_only",
+            keep = ("metric", "value", "unit", "ms_per_step", "config", "kernels_ms", "separate_kernels_ms", "witnesses_per_s_gen_only",
                     "constraints_per_s_check_only", "roofline", "kernels", "cpu_baseline", "e2e", "e2e_public_outputs",
                     "e2e_flags_only", "gpu_launches", "program", "r1cs")
             line["secondary"] = {k: sec[k] for k in keep}

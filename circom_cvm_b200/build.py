@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libcvmgpu.so")
 CALC = os.path.join(CSRC, "cvmgpu_calc")        # native host program with the reference calculator's process interface
 SOURCES = ["cvmgpu.cu"]
-HEADERS = ["fr.cuh", "kernels.cuh", "cvm_parse.hpp", "tracer.hpp", "tape.hpp", "r1cs.hpp", "host_fr.hpp",
+HEADERS = ["fr.cuh", "kernels.cuh", "cvm_parse.hpp", "tracer.hpp", "tape.hpp", "fused.hpp", "r1cs.hpp", "host_fr.hpp",
            os.path.join("..", "..", "include", "cvmgpu.h")]
 
 

@@ -16,7 +16,10 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+
 #include "cvm_parse.hpp"
+#include "fused.hpp"
 #include "host_fr.hpp"
 #include "kernels.cuh"
 #include "r1cs.hpp"
@@ -77,6 +80,16 @@ struct cvmgpu_program {
     };
     std::map<int, Dev> dev;
     std::mutex mu;
+    // what the fused R1CS check (fused.hpp) is built from: the prepared program, its constants (canonical), and the tapes
+    // already built for the constraint systems this program has been run with (by cvmgpu_r1cs::uid)
+    tape::XProg xp;
+    std::vector<fr::Fr> consts;
+    size_t n_ssa = 0;
+    uint32_t max_terms = 0;
+    uint32_t explicit_slots = 0;     // the caller's slot count (0: chosen by the cost model), also used for fused tapes
+    bool fusable = false;
+    std::map<uint64_t, std::unique_ptr<cvmgpu_program>> fused;
+    std::map<uint64_t, bool> fuse_worth;
 };
 
 // the CSR of an .r1cs bound to one value-store layout (r1cs.hpp bind), on the device
@@ -90,8 +103,11 @@ struct BoundDev {
     void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); d_tcons.release(); d_active.release(); layout_id = ~0ull; }
 };
 
+static std::atomic<uint64_t> g_next_r1cs_uid{1};
+
 struct cvmgpu_r1cs {
     r1cs::File file;
+    const uint64_t uid = g_next_r1cs_uid++;
     // per device: the coefficient tables, the CSR bound to the plain layout and to the last program layout used there
     // (re-bound when it changes), and the buffers of the host entry point
     struct Dev {
@@ -133,6 +149,23 @@ extern "C" int cvmgpu_set_device(int device) {
 }
 
 // ------------------------------------------------------------------------------------------ program
+// launch-cost estimate of a tape (slot-file search of build_program and of fused_for)
+static double tape_cost(const tape::Tape &t) {
+    // resident warps per SM at one warp per CTA (what small batches launch): 1 KiB of the SM's 228 KiB is reserved
+    // per CTA.  A 64 K batch -- 2 048 warps over 148 SMs, BASELINE configs 3 and 4 -- must fit in ONE wave: at 13
+    // resident warps per SM it takes two (measured: Sha256(512) 115 ms against 64 ms), hence the quantisation term.
+    const size_t per_warp = (size_t)(t.n_slots + (t.use_ring ? tape::LD_RING : 0)) * 1024u + (size_t)t.n_bslots * 4u + 1024u;
+    const double resident = std::min<double>(std::floor(228.0 * 1024.0 / (double)per_warp), 64.0);
+    const double waves = 2048.0 / (148.0 * std::max(1.0, resident));
+    const double quant = std::ceil(waves) / std::max(waves, 1.0);
+    // value-store traffic: field rows move 1 KiB per warp; a bit-row reload is one word, but it is a dependent
+    // global load on the tape's critical path (measured on Sha256(512): 256 bit slots with 11 K such reloads
+    // 22.6 ms, 512 with 1.7 K 20.1 ms)
+    const double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st - t.stats.n_ld_bool - t.stats.n_spill_st_bool) +
+                        2.0 * (double)t.stats.n_ld_bool;
+    return work * quant / std::max(4.0, std::min(resident, 24.0));
+}
+
 static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program **out) {
     std::unique_ptr<cvmgpu_program> p(new cvmgpu_program());
     if (n_slots > 55) n_slots = 55;   // 55 * 4 KiB = 220 KiB of the 227 KiB a CTA may use
@@ -154,22 +187,8 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
                 if (it == prepared.end()) it = prepared.emplace(mt, tape::prepare_program(tr, mt)).first;
                 return tape::allocate_tape(tr, it->second, c, max_bslots);
             };
-            auto cost_of = [&](const tape::Tape &t) {
-                // resident warps per SM at one warp per CTA (what small batches launch): 1 KiB of the SM's 228 KiB is reserved
-                // per CTA.  A 64 K batch -- 2 048 warps over 148 SMs, BASELINE configs 3 and 4 -- must fit in ONE wave: at 13
-                // resident warps per SM it takes two (measured: Sha256(512) 115 ms against 64 ms), hence the quantisation term.
-                const size_t per_warp = (size_t)(t.n_slots + (t.use_ring ? tape::LD_RING : 0)) * 1024u + (size_t)t.n_bslots * 4u + 1024u;
-                const double resident = std::min<double>(std::floor(228.0 * 1024.0 / (double)per_warp), 64.0);
-                const double waves = 2048.0 / (148.0 * std::max(1.0, resident));
-                const double quant = std::ceil(waves) / std::max(waves, 1.0);
-                // value-store traffic: field rows move 1 KiB per warp; a bit-row reload is one word, but it is a dependent
-                // global load on the tape's critical path (measured on Sha256(512): 256 bit slots with 11 K such reloads
-                // 22.6 ms, 512 with 1.7 K 20.1 ms)
-                const double work = (double)t.ins.size() + 2.0 * (double)(t.stats.n_ld + t.stats.n_st - t.stats.n_ld_bool - t.stats.n_spill_st_bool) +
-                                    2.0 * (double)t.stats.n_ld_bool;
-                return work * quant / std::max(4.0, std::min(resident, 24.0));
-            };
             double best = 0, prev_best_c = 0;
+            uint32_t best_mt = 0;
             for (uint32_t c : cand) {
                 uint32_t live_field = 0, full_bslots = 0;
                 double best_c = 0;
@@ -177,22 +196,39 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
                     if (nb != 2048u && nb >= full_bslots) continue;   // the file already holds every live 0/1 value
                     tape::Tape t = build(c, nb);
                     if (nb == 2048u) { full_bslots = t.n_bslots; live_field = t.stats.max_live_field; }
-                    const double cost = cost_of(t);
+                    const double cost = tape_cost(t);
                     if (best_c == 0 || cost < best_c) best_c = cost;
                     if (best == 0 || cost < best) {
                         best = cost;
                         p->tape = std::move(t);
+                        best_mt = std::min<uint32_t>(16, c - 2);
                     }
                 }
                 if (c >= live_field + 2) break;   // every field value already has a slot
                 if (prev_best_c != 0 && best_c > prev_best_c) break;   // past the optimum: larger files only cost occupancy
                 prev_best_c = best_c;
             }
+            // field-only programs keep what a fused R1CS check is built from (fused.hpp)
+            auto it = prepared.find(best_mt);
+            if (it != prepared.end() && tape::check_fusable(it->second)) {
+                p->xp = std::move(it->second);
+                p->max_terms = best_mt;
+                p->fusable = true;
+            }
         } else {
             // explicit slot count (experiments): CVMGPU_BSLOTS caps the bit file
             const uint32_t nb = getenv("CVMGPU_BSLOTS") ? (uint32_t)atoi(getenv("CVMGPU_BSLOTS")) : 2048u;
-            p->tape = tape::build_tape(tr, n_slots, true, std::max<uint32_t>(8, nb));
+            p->max_terms = std::min<uint32_t>(16, n_slots - 2);
+            p->explicit_slots = n_slots;
+            tape::XProg xp = tape::prepare_program(tr, p->max_terms);
+            p->tape = tape::allocate_tape(tr, xp, n_slots, std::max<uint32_t>(8, nb));
+            if (tape::check_fusable(xp)) {
+                p->xp = std::move(xp);
+                p->fusable = true;
+            }
         }
+        p->consts = tr.consts;
+        p->n_ssa = tr.ops.size();
         p->layout_id = g_next_layout_id++;
         p->tstats = tr.stats;
         p->wire_bool.reserve(tr.witness_ref.size());
@@ -426,12 +462,88 @@ static void on_device(int device, F &&fn) {
     if (sw) cudaSetDevice(cur);
 }
 
-extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
-    if (!p) return;
+static void release_program_tables(cvmgpu_program *p) {
     for (auto &kv : p->dev)
         on_device(kv.first, [&] { kv.second.d_tape.release(); kv.second.d_consts.release(); kv.second.d_wire_loc.release(); kv.second.d_iconsts.release(); });
+    for (auto &kv : p->fused) release_program_tables(kv.second.get());
+}
+
+extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
+    if (!p) return;
+    release_program_tables(p);
     release_pipe_buffers();
     delete p;
+}
+
+// The tape of `p` with the check of `r` scheduled into it (fused.hpp), built on first use and kept per constraint
+// system; nullptr when the program is not field-only (its check keeps the separate kernels), when the two do not belong
+// together, or with CVMGPU_FUSED=0 in the environment (measurements of the separate kernels).
+// 0: never, 1: when it pays (field programs whose constraints are all evaluated in the field), 2: whenever it is possible
+static std::atomic<int> g_fused_mode{getenv("CVMGPU_FUSED") ? atoi(getenv("CVMGPU_FUSED")) : 1};
+
+extern "C" int cvmgpu_set_fused_mode(int mode) {
+    if (mode < 0 || mode > 2) return fail(CVMGPU_ERR_ARG, "fused mode must be 0, 1 or 2");
+    g_fused_mode = mode;
+    return CVMGPU_OK;
+}
+
+static cvmgpu_program *fused_for(cvmgpu_program *p, cvmgpu_r1cs *r) {
+    const int mode = g_fused_mode;
+    if (mode == 0 || !p || !r || !p->fusable || r->file.n_wires != p->tape.n_wires) return nullptr;
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (mode == 1) {
+        // Constraints over 0/1 wires are evaluated 32 witnesses at a time by the table / integer kernels (r1cs.hpp bind):
+        // a program that has them (EdDSAPoseidonVerifier: measured 62.2 ms fused against 38.8 + 19.8 ms) keeps those kernels
+        auto w = p->fuse_worth.find(r->uid);
+        if (w == p->fuse_worth.end()) {
+            const r1cs::Bound b = r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow, p->tape.const_rows);
+            w = p->fuse_worth.emplace(r->uid, b.n_table_constraints == 0 && b.n_int_constraints == 0).first;
+        }
+        if (!w->second) return nullptr;
+    }
+    auto it = p->fused.find(r->uid);
+    if (it != p->fused.end()) return it->second.get();
+    std::unique_ptr<cvmgpu_program> q(new cvmgpu_program());
+    try {
+        std::vector<fr::Fr> consts = p->consts;
+        tape::XProg xp = tape::fuse_check(p->xp, consts, r->file, p->max_terms);
+        // the slot file is chosen again: the check's operands stay live a little longer
+        double best = 0;
+        for (uint32_t c : {8u, 12u, 16u, 24u, 32u}) {
+            if (c < p->max_terms + 2 || p->explicit_slots) continue;
+            tape::Tape t = tape::allocate_tape(consts, p->n_ssa, xp, c, 2048);
+            const double cost = tape_cost(t);
+            const bool all_resident = c >= t.stats.max_live_field + 2;
+            if (best == 0 || cost < best) {
+                best = cost;
+                q->tape = std::move(t);
+            }
+            if (all_resident) break;
+        }
+        if (best == 0) q->tape = tape::allocate_tape(consts, p->n_ssa, xp, p->tape.n_slots, 2048);   // (explicit slot count)
+        q->consts_mont.reserve(consts.size());
+        for (const fr::Fr &c : consts) q->consts_mont.push_back(fr::to_mont(c));
+    } catch (const std::exception &e) {
+        fail(CVMGPU_ERR_UNSUPPORTED, e.what());
+        p->fused.emplace(r->uid, nullptr);   // do not try again
+        return nullptr;
+    }
+    // the value store keeps the program's wire rows (wire_loc depends on the wires only); spill rows may differ
+    if (q->tape.wire_loc != p->tape.wire_loc) {
+        p->fused.emplace(r->uid, nullptr);
+        return nullptr;
+    }
+    q->tstats = p->tstats;
+    q->binv = p->binv;
+    q->witness = p->witness;
+    q->wire_bool = p->wire_bool;
+    q->n_signals = p->n_signals;
+    q->n_inputs = p->n_inputs;
+    q->n_outputs = p->n_outputs;
+    q->layout_id = g_next_layout_id++;
+    cvmgpu_program *out = q.get();
+    p->fused.emplace(r->uid, std::move(q));
+    return out;
 }
 
 // dynamic shared memory of a tape CTA of nt witnesses: the field slots, the reload ring when the tape reloads
@@ -501,8 +613,16 @@ static int launch_tape(const kern::TapeParams &tp, unsigned grid, size_t smem, c
     return CVMGPU_OK;
 }
 
+static int run_tape(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store, void *d_status,
+                    void *d_first_bad, void *stream);
+
 extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride,
                                         void *d_store, void *d_status, void *stream) {
+    return run_tape(p, d_inputs, B, bstride, d_store, d_status, nullptr, stream);
+}
+
+static int run_tape(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store, void *d_status,
+                    void *d_first_bad, void *stream) {
     if (!p || !d_store || (!d_inputs && p->n_inputs)) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
     if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
@@ -522,6 +642,7 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     tp.inputs = (const uint4 *)d_inputs;
     tp.n_inputs = p->n_inputs;
     tp.status = (uint32_t *)d_status;
+    tp.first_bad = (uint32_t *)d_first_bad;
     tp.B = B;
     // CTA size: 128 witnesses for large batches; smaller CTAs when the batch would leave SMs with an uneven number of
     // CTAs (a 64 K batch is 512 CTAs of 128 for 148 SMs: 3.46 per SM)
@@ -548,6 +669,42 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
     if (nt == 128) return launch_tape<128, false>(tp, (unsigned)grid, smem, st);
     if (nt == 64) return launch_tape<64, false>(tp, (unsigned)grid, smem, st);
     return launch_tape<32, false>(tp, (unsigned)grid, smem, st);
+}
+
+// Witness generation + R1CS check on device buffers.  Field-only programs run one kernel (the check is part of the tape,
+// fused.hpp); the others run the tape and then the check kernels on the store.  The store must hold
+// cvmgpu_store_bytes_checked(p, r, bstride) bytes.
+extern "C" int cvmgpu_witness_batch_checked_dev(cvmgpu_program *p, cvmgpu_r1cs *r, const void *d_inputs, uint64_t B, uint64_t bstride,
+                                                void *d_store, void *d_status, void *d_first_bad, void *stream) {
+    if (!p || !r || !d_first_bad) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (r->file.n_wires != p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "r1cs and program disagree on the number of wires");
+    if (cvmgpu_program *q = fused_for(p, r)) return run_tape(q, d_inputs, B, bstride, d_store, d_status, d_first_bad, stream);
+    if (int rc = run_tape(p, d_inputs, B, bstride, d_store, d_status, nullptr, stream)) return rc;
+    if (B == 0) return CVMGPU_OK;
+    return cvmgpu_r1cs_check_store_dev(r, p, d_store, B, bstride, d_first_bad, stream);
+}
+
+extern "C" size_t cvmgpu_store_bytes_checked(cvmgpu_program *p, cvmgpu_r1cs *r, uint64_t bstride) {
+    if (!p) return 0;
+    size_t n = cvmgpu_store_bytes(p, bstride);
+    if (cvmgpu_program *q = fused_for(p, r)) n = std::max(n, cvmgpu_store_bytes(q, bstride));
+    return n;
+}
+
+// the tape that cvmgpu_witness_batch_checked[_dev] runs for this pair when it is a fused one (CVMGPU_ERR_UNSUPPORTED if not)
+extern "C" int cvmgpu_program_fused_info_get(cvmgpu_program *p, cvmgpu_r1cs *r, cvmgpu_program_info *out) {
+    if (!p || !r || !out) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvmgpu_program *q = fused_for(p, r);
+    if (!q) return fail(CVMGPU_ERR_UNSUPPORTED, "no fused tape for this program / constraint system (not field-only, or disabled)");
+    return cvmgpu_program_info_get(q, out);
+}
+
+extern "C" int cvmgpu_program_fused_tape(cvmgpu_program *p, cvmgpu_r1cs *r, const void **ins, uint64_t *n_ins, const void **consts,
+                                         uint32_t *n_consts) {
+    if (!p || !r) return fail(CVMGPU_ERR_ARG, "null argument");
+    cvmgpu_program *q = fused_for(p, r);
+    if (!q) return fail(CVMGPU_ERR_UNSUPPORTED, "no fused tape for this program / constraint system (not field-only, or disabled)");
+    return cvmgpu_program_tape(q, ins, n_ins, consts, n_consts);
 }
 
 static kern::StoreView store_view(const cvmgpu_program *p, const cvmgpu_program::Dev *pd, const void *d_store, uint64_t bstride) {
@@ -633,11 +790,14 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
     if (wtns_out && (uint64_t)wire0 + n_sel > p->tape.n_wires) return fail(CVMGPU_ERR_ARG, "wire range exceeds the witness");
     if (cvmgpu_device_count() <= 0) return fail(CVMGPU_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
     if (!wtns_out) n_sel = 0;
+    // field-only programs run ONE kernel: the tape with the check of `r` scheduled into it
+    const bool fused = r && fused_for(p, r) != nullptr;
+    if (fused) p = fused_for(p, r);
     {
         cvmgpu_program::Dev *pd = nullptr;
         if (int rc = upload_program(p, &pd)) return rc;
         cvmgpu_r1cs::Dev *rd = nullptr;
-        if (r)
+        if (r && !fused)
             if (int rc = upload_r1cs(r, &rd)) return rc;
     }
     const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)n_sel * 32;
@@ -681,9 +841,9 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
         cudaError_t e = cudaSuccess;
         // the stream's previous chunk must have left its buffers (stream order guarantees it)
         if (in_row) e = cudaMemcpyAsync(pb.inputs.p, inputs + b0 * in_row, n * in_row, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) rc = cvmgpu_witness_batch_dev(p, pb.inputs.p, n, cstride, pb.store.p, pb.status.p, s);
+        if (e == cudaSuccess) rc = run_tape(p, pb.inputs.p, n, cstride, pb.store.p, pb.status.p, fused ? pb.bad.p : nullptr, s);
         if (e == cudaSuccess && rc == CVMGPU_OK && r) {
-            rc = cvmgpu_r1cs_check_store_dev(r, p, pb.store.p, n, cstride, pb.bad.p, s);
+            if (!fused) rc = cvmgpu_r1cs_check_store_dev(r, p, pb.store.p, n, cstride, pb.bad.p, s);
             if (rc == CVMGPU_OK) e = cudaMemcpyAsync(first_bad + b0, pb.bad.p, n * 4, cudaMemcpyDeviceToHost, s);
         }
         if (e == cudaSuccess && rc == CVMGPU_OK && out_row) {

@@ -57,6 +57,7 @@ struct TapeParams {
     const unsigned long long *iconsts;   // constants of the integer operations
     uint32_t ring_off;       // uint4 offset of the reload ring inside the dynamic shared memory (after the field slots)
     uint32_t bslot_off;      // uint4 offset of the bit-slot file (after the ring)
+    uint32_t *first_bad;     // tapes with a fused R1CS check (T_RNE): first violated constraint per witness, else nullptr
 };
 
 __device__ __forceinline__ Fr mont_bool(bool b) { return b ? fr::one_mont() : fr::zero(); }
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
     const bool warp_active = (w - lane) < p.B;
     if (!active) w = p.B - 1;   // keep the warp converged; results of padding lanes are discarded
     uint32_t status = 0;
+    uint32_t first_bad = 0xffffffffu;
     uint4 *const wbase = p.store + w;
     const uint64_t bstride = p.bstride;
     const uint4 *const consts = p.consts;
@@ -415,13 +417,17 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
             is_rb = true;
             break;
         }
-        case tape::T_EQ: case tape::T_NEQ: case tape::T_EQZ: case tape::T_FAIL_IF: case tape::T_FAIL_NE: {
+        case tape::T_EQ: case tape::T_NEQ: case tape::T_EQZ: case tape::T_FAIL_IF: case tape::T_FAIL_NE: case tape::T_RNE: {
             bool e;
             if (op == tape::T_EQZ || op == tape::T_FAIL_IF) e = !tape_truth<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid);
             else e = fr::equal(tape_operand<NT, BITS>(slots, bw, consts, cur.y, flags & 1u, tid),
                                tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid));
             if (op == tape::T_FAIL_IF || op == tape::T_FAIL_NE) {
                 if (!e && status == 0) status = cur.w;
+                continue;
+            }
+            if (op == tape::T_RNE) {   // constraint cur.w of the fused R1CS check (fused.hpp)
+                if (!e) first_bad = min(first_bad, cur.w);
                 continue;
             }
             rb = (op == tape::T_NEQ) ? !e : e;
@@ -495,6 +501,12 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
             if ((flags & tape::F_STORE) && warp_active) brow[cur.w & ~tape::ROW_BIT] = word;
         } else {
             if (is_rb) r = mont_bool(rb);
+            if (flags & tape::F_CHECK) {
+                // last instruction of a constraint of the fused R1CS check (fused.hpp): dst names the slot that holds the other
+                // side of the comparison, cur.w the constraint; nothing is written
+                if (!fr::equal(r, tape_operand<NT, BITS>(slots, bw, consts, dst, false, tid))) first_bad = min(first_bad, cur.w);
+                continue;
+            }
             uint4 lo, hi;
             pack(r, lo, hi);
             slots[(dst * 2) * NT + tid] = lo;
@@ -508,6 +520,7 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (active && p.status) p.status[w] = status;
+    if (active && p.first_bad) p.first_bad[w] = first_bad;
 }
 
 // ---- typed value store -> .wtns rows (canonical AoS: B x n_sel x 32 B) ----------------------------------

@@ -32,6 +32,7 @@ static const uint8_t F_STORE = 8;
 static const uint8_t F_CZERO = 16;
 static const uint8_t F_TRIVIAL = 16;  // T_MUL: check at run time whether the factors are 0 / 1 (bit-heavy programs)
 static const uint8_t F_ADDEND = 32;
+static const uint8_t F_CHECK = 128;  // T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: dst = slot to compare the result with, c = constraint
 static const uint8_t F_RING = 64;    // T_LD: the value was requested LD_RING reloads ago and sits in ring entry b
 static const uint32_t LD_RING = 4;   // reloads in flight per witness (32 B of shared memory each)
 static const uint32_t BSLOT = 0x40000000u;     // operand field: the value lives in the bit-slot file (one word per warp; bit = lane)
@@ -43,7 +44,7 @@ static_assert(sizeof(TapeIns) == 16, "tape instruction must be 16 bytes");
 struct TapeStats {
     uint64_t n_ssa = 0, n_live = 0, n_tape = 0;
     uint64_t n_mul = 0, n_div = 0, n_addsub = 0, n_other = 0, n_inv = 0, n_sel = 0;   // executed per witness
-    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
+    uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_rne = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
     uint64_t n_groups = 0;         // warp-cooperative group instructions (T_LUTG / T_IBITG)
     uint64_t n_isum_terms = 0;     // conditional adds of bits fused into T_ISUM instructions
     uint64_t n_int = 0;            // small-integer operations (type_ints): sums of 0/1 values kept as raw 64-bit integers
@@ -172,6 +173,9 @@ struct XOp {
     uint8_t op;
     uint32_t a, b, c, aux;
     uint32_t t0 = 0, tn = 0;   // T_DOT: terms [t0, t0+tn) of XProg::terms; c = addend ref or NO_REF
+    // fused R1CS check (fused.hpp): the result is compared with a value instead of kept -- T_ADD / T_SUB / T_MUL: with c,
+    // T_DOT: with a -- and constraint `aux` is recorded in first_bad when they differ
+    uint8_t chk = 0;
 };
 struct XProg {
     std::vector<XOp> ops;
@@ -714,7 +718,10 @@ inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
         use(o.b);
         use(o.c);
     }
-    auto produces = [&](size_t i) { return xp.ops[i].op != T_FAIL_IF && xp.ops[i].op != T_FAIL_NE && xp.ops[i].op != T_IFAIL_NE; };
+    auto produces = [&](size_t i) {
+        const uint8_t op = xp.ops[i].op;
+        return op != T_FAIL_IF && op != T_FAIL_NE && op != T_IFAIL_NE && op != T_RNE && !xp.ops[i].chk;
+    };
     std::vector<uint32_t> deaths[2];
     deaths[0].assign(N, 0);
     deaths[1].assign(N, 0);
@@ -760,20 +767,20 @@ inline XProg prepare_program(const Tracer &tr, uint32_t max_terms, bool fuse = t
     return xp;
 }
 
-inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, uint32_t max_bslots = 2048) {
+inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const XProg &xp, uint32_t n_slots, uint32_t max_bslots = 2048) {
     if (n_slots < 4) throw TraceError("need at least 4 slots");
     const std::vector<XOp> &ops = xp.ops;
     const size_t N = ops.size();
     Tape out;
     out.n_slots = n_slots;
     out.n_wires = (uint32_t)xp.witness_ref.size();
-    out.stats.n_ssa = tr.ops.size();
+    out.stats.n_ssa = n_ssa;
     out.stats.n_live = N;
 
     auto is_bool_ref = [&](uint32_t r) -> bool {
         if (r == NO_REF) return false;
         if (r & CONST_FLAG) {
-            const fr::Fr &c = tr.consts[r & ~CONST_FLAG];
+            const fr::Fr &c = consts[r & ~CONST_FLAG];
             for (int i = 1; i < 8; i++)
                 if (c.v[i]) return false;
             return c.v[0] <= 1;
@@ -797,7 +804,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
             // (a program without computed 0/1 values keeps its constant wires as field rows: its constraints then have no
             // bit-row term at all and the check runs the plain kernel)
             if (w == 0 || ml[1] == 0 || !(r & CONST_FLAG) || !is_bool_ref(r)) return -1;
-            return (int)tr.consts[r & ~CONST_FLAG].v[0];
+            return (int)consts[r & ~CONST_FLAG].v[0];
         };
         for (uint32_t w = 0; w < out.n_wires; w++) {
             if (const_bit(w) >= 0) continue;
@@ -825,6 +832,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
         if (o.op == T_DOT || o.op == T_ISUM) {
             for (uint32_t k = 0; k < o.tn; k++) rs.push_back(xp.terms[o.t0 + k].second);
             rs.push_back(o.c);
+            if (o.chk) rs.push_back(o.a);   // a checked T_DOT: the value its result is compared with
         } else {
             rs.push_back(o.a);
             rs.push_back(o.b);
@@ -1079,7 +1087,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
             // integer operations take their constants from the table of raw 64-bit integers
             for (size_t k = (o.op == T_ISEL ? 1 : 0); k < 3; k++) {
                 if (!isc[k]) continue;
-                const fr::Fr &cv = tr.consts[enc[k]];
+                const fr::Fr &cv = consts[enc[k]];
                 const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
                 auto it = iconst_index.find(v);
                 if (it == iconst_index.end()) {
@@ -1090,9 +1098,36 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
             }
             if (o.op != T_IFAIL_NE) out.stats.n_int++;
         }
-        if (o.op == T_FAIL_IF || o.op == T_FAIL_NE || o.op == T_IFAIL_NE) {
+        if (o.op == T_FAIL_IF || o.op == T_FAIL_NE || o.op == T_IFAIL_NE || o.op == T_RNE) {
             out.ins.push_back(TapeIns{o.op, flags, 0, enc[0], enc[1], o.aux});
-            out.stats.n_fail++;
+            if (o.op == T_RNE) out.stats.n_rne++;
+            else out.stats.n_fail++;
+            continue;
+        }
+        if (o.chk) {
+            // checked instruction of a fused R1CS check: the comparison's other side is an operand like the others (resident
+            // now); nothing is written
+            if (o.op == T_DOT) {
+                const bool has_add = o.c != NO_REF;
+                if (has_add) flags |= F_ADDEND;
+                if (has_add && isc[o.tn]) flags |= 2;
+                out.ins.push_back(TapeIns{T_DOT, (uint8_t)(flags | F_CHECK), (uint16_t)enc[o.tn + 1], o.tn, has_add ? enc[o.tn] : 0u, o.aux});
+                for (uint32_t k = 0; k < o.tn; k += 2) {
+                    uint32_t rec[4] = {xp.terms[o.t0 + k].first & ~CONST_FLAG, enc[k], 0, 0};
+                    if (k + 1 < o.tn) { rec[2] = xp.terms[o.t0 + k + 1].first & ~CONST_FLAG; rec[3] = enc[k + 1]; }
+                    TapeIns raw;
+                    memcpy(&raw, rec, sizeof(rec));
+                    out.ins.push_back(raw);
+                }
+                out.stats.n_dot++;
+                out.stats.n_dot_terms += o.tn;
+            } else {
+                if (isc[2]) throw TraceError("checked instruction compares with a constant");
+                out.ins.push_back(TapeIns{o.op, (uint8_t)((flags & 3u) | F_CHECK), (uint16_t)enc[2], enc[0], enc[1], o.aux});
+                if (o.op == T_MUL) out.stats.n_mul++;
+                else out.stats.n_addsub++;
+            }
+            out.stats.n_rne++;
             continue;
         }
         // destination (may reuse the slot of an operand that died; ops read all operands before writing)
@@ -1119,7 +1154,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
                 addend = enc[o.tn];
                 if (isc[o.tn]) {
                     flags |= 2;
-                    const fr::Fr &cv = tr.consts[enc[o.tn]];
+                    const fr::Fr &cv = consts[enc[o.tn]];
                     const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
                     auto it = iconst_index.find(v);
                     if (it == iconst_index.end()) {
@@ -1133,7 +1168,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
             for (uint32_t k = 0; k < o.tn; k += 4) {
                 uint32_t rec[4] = {0, 0, 0, 0};
                 for (uint32_t j = 0; j < 4 && k + j < o.tn; j++) {
-                    const fr::Fr &cv = tr.consts[xp.terms[o.t0 + k + j].first & ~CONST_FLAG];
+                    const fr::Fr &cv = consts[xp.terms[o.t0 + k + j].first & ~CONST_FLAG];
                     const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
                     uint32_t sh = 0;
                     while (!((v >> sh) & 1)) sh++;
@@ -1180,7 +1215,7 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
                 e2 = 0;
                 out.stats.n_lut++;
             }
-            if (o.op == T_SEL && (o.c != NO_REF) && (o.c & CONST_FLAG) && fr::is_zero(tr.consts[o.c & ~CONST_FLAG])) {
+            if (o.op == T_SEL && (o.c != NO_REF) && (o.c & CONST_FLAG) && fr::is_zero(consts[o.c & ~CONST_FLAG])) {
                 flags = (uint8_t)((flags & ~4u) | F_CZERO);
                 e2 = 0;
             }
@@ -1237,6 +1272,10 @@ inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, u
     out.stats.macs = 136 * (out.stats.n_mul + out.stats.n_input + out.stats.n_inv + 2 * out.stats.n_div) + 64 * out.stats.n_dot_terms +
                      72 * out.stats.n_dot + 1800 * (out.stats.n_inv + out.stats.n_div);
     return out;
+}
+
+inline Tape allocate_tape(const Tracer &tr, const XProg &xp, uint32_t n_slots, uint32_t max_bslots = 2048) {
+    return allocate_tape(tr.consts, tr.ops.size(), xp, n_slots, max_bslots);
 }
 
 inline Tape build_tape(const Tracer &tr, uint32_t n_slots, bool fuse = true, uint32_t max_bslots = 2048) {

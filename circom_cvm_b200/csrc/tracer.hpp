@@ -54,6 +54,8 @@ enum TOp : uint8_t {
     T_LUTG,      // up to 32 T_LUT
     T_IBITG,     // up to 32 consecutive bits of one integer (T_IBIT)
     T_FILL,      // constant bit rows [c, c + b) = the word a (witness wires bound to the constants 0 / 1)
+    // R1CS check scheduled into the tape (fused.hpp)
+    T_RNE,       // first_bad = min(first_bad, c) if a != b   (a = A.w * B.w, b = C.w of constraint c)
     T_COUNT
 };
 

@@ -28,7 +28,8 @@ ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (cs
 
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
-    "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_load_files", "cvmgpu_program_load_text3", "cvmgpu_program_info_get", "cvmgpu_program_free",
+    "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_load_files", "cvmgpu_program_load_text3", "cvmgpu_witness_batch_checked_dev", "cvmgpu_store_bytes_checked",
+    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_info_get", "cvmgpu_program_free",
     "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_multi", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
@@ -110,6 +111,11 @@ def lib():
     L.cvmgpu_witness_export_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
     L.cvmgpu_store_bytes.argtypes = [c_void_p, c_uint64]
     L.cvmgpu_store_bytes.restype = c_size_t
+    L.cvmgpu_store_bytes_checked.argtypes = [c_void_p, c_void_p, c_uint64]
+    L.cvmgpu_store_bytes_checked.restype = c_size_t
+    L.cvmgpu_witness_batch_checked_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_program_fused_info_get.argtypes = [c_void_p, c_void_p, POINTER(ProgramInfo)]
+    L.cvmgpu_program_fused_tape.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_wtns_write.argtypes = [c_char_p, c_void_p, c_uint32]
     L.cvmgpu_r1cs_load.argtypes = [c_char_p, POINTER(c_void_p)]
     L.cvmgpu_r1cs_info_get.argtypes = [c_void_p, POINTER(R1csInfo)]
@@ -250,6 +256,35 @@ class WitnessCalculator:
     def run_dev(self, d_inputs, B, bstride, d_store, d_status, stream=0):
         _check(lib().cvmgpu_witness_batch_dev(self._h, _ptr(d_inputs), B, bstride, _ptr(d_store), _ptr(d_status), stream))
 
+    def run_checked_dev(self, r1cs, d_inputs, B, bstride, d_store, d_status, d_first_bad, stream=0):
+        """witness generation + R1CS check on device buffers: one kernel for field-only programs (the check is scheduled into
+        the tape), tape + check kernels otherwise.  d_store: store_bytes_checked(r1cs, bstride) bytes."""
+        _check(lib().cvmgpu_witness_batch_checked_dev(self._h, r1cs._h, _ptr(d_inputs), B, bstride, _ptr(d_store), _ptr(d_status),
+                                                      _ptr(d_first_bad), stream))
+
+    def store_bytes_checked(self, r1cs, bstride):
+        return int(lib().cvmgpu_store_bytes_checked(self._h, r1cs._h, bstride))
+
+    def fused_info(self, r1cs):
+        """ProgramInfo of the tape with r1cs's check scheduled into it, or None when the pair runs separate kernels"""
+        info = ProgramInfo()
+        info.struct_size = ctypes.sizeof(ProgramInfo)
+        if lib().cvmgpu_program_fused_info_get(self._h, r1cs._h, byref(info)) != 0:
+            return None
+        return info
+
+    def fused_tape(self, r1cs):
+        """-> (tape instructions, constants, layout) of the fused tape, for tests/tape_emulator.py; None if there is none"""
+        info = self.fused_info(r1cs)
+        if info is None:
+            return None
+        ins, n, cs, nc = c_void_p(), c_uint64(), c_void_p(), c_uint32()
+        _check(lib().cvmgpu_program_fused_tape(self._h, r1cs._h, byref(ins), byref(n), byref(cs), byref(nc)))
+        tape, consts = self._tape_arrays(ins, n, cs, nc)
+        layout = dict(self.layout(), n_slots=int(info.n_slots), n_bslots=int(info.n_bslots), n_frows=int(info.n_frows),
+                      n_brows=int(info.n_brows), iconsts=[])
+        return tape, consts, layout
+
     def export_dev(self, d_store, B, bstride, d_wtns, stream=0):
         _check(lib().cvmgpu_witness_export_dev(self._h, _ptr(d_store), B, bstride, _ptr(d_wtns), stream))
 
@@ -307,6 +342,10 @@ class WitnessCalculator:
         """-> (numpy structured array of tape instructions, constants as python ints in Montgomery form)"""
         ins, n, cs, nc = c_void_p(), c_uint64(), c_void_p(), c_uint32()
         _check(lib().cvmgpu_program_tape(self._h, byref(ins), byref(n), byref(cs), byref(nc)))
+        return self._tape_arrays(ins, n, cs, nc)
+
+    @staticmethod
+    def _tape_arrays(ins, n, cs, nc):
         dt = np.dtype([("op", "u1"), ("flags", "u1"), ("dst", "<u2"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
         tape = np.frombuffer((ctypes.c_char * (n.value * 16)).from_address(ins.value), dtype=dt).copy() if n.value else np.zeros(0, dt)
         raw = bytes((ctypes.c_char * (nc.value * 32)).from_address(cs.value)) if nc.value else b""
@@ -365,6 +404,12 @@ class R1cs:
     def check_store_dev(self, wc, d_store, B, bstride, d_first_bad, stream=0):
         """typed store written by wc.run_dev (WitnessCalculator wc)"""
         _check(lib().cvmgpu_r1cs_check_store_dev(self._h, wc._h, _ptr(d_store), B, bstride, _ptr(d_first_bad), stream))
+
+
+def set_fused_mode(mode):
+    """0: tape and R1CS check always as separate kernels; 1 (default): the check is scheduled into the tape of field programs
+    whose constraints are all evaluated in the field; 2: whenever the program allows it"""
+    _check(lib().cvmgpu_set_fused_mode(int(mode)))
 
 
 def set_tape_mode(mode):

@@ -192,6 +192,23 @@ int cvmgpu_witness_batch_multi(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t 
  * stream: a cudaStream_t (0 = default stream). */
 int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store,
                              void *d_status, void *stream);
+/* Witness generation AND R1CS check on device buffers (what cvmgpu_witness_batch_checked runs per chunk).  For programs
+ * whose values are all field elements (no 0/1-typed values: Poseidon-like arithmetic circuits) the constraints are
+ * scheduled into the tape -- each one is evaluated right after the last wire it mentions is produced, operands still
+ * on chip -- and ONE kernel writes the store, the status and first_bad; other programs run the tape and then the check
+ * kernels.  Same results either way (A.w * B.w = C.w on the stored values, first violated constraint or CVMGPU_NO_BAD).
+ * d_store: cvmgpu_store_bytes_checked(p, r, bstride) bytes. */
+int cvmgpu_witness_batch_checked_dev(cvmgpu_program *p, cvmgpu_r1cs *r, const void *d_inputs, uint64_t B, uint64_t bstride,
+                                     void *d_store, void *d_status, void *d_first_bad, void *stream);
+size_t cvmgpu_store_bytes_checked(cvmgpu_program *p, cvmgpu_r1cs *r, uint64_t bstride);
+/* 0: never fuse; 1 (default): fuse field programs whose constraints are all evaluated in the field (constraints over 0/1
+ * wires are cheaper in the table / integer check kernels); 2: fuse whenever the program allows it (tests, measurements).
+ * Initial value: CVMGPU_FUSED in the environment. */
+int cvmgpu_set_fused_mode(int mode);
+/* counters / instructions of the fused tape of (p, r); CVMGPU_ERR_UNSUPPORTED when the pair runs separate kernels */
+int cvmgpu_program_fused_info_get(cvmgpu_program *p, cvmgpu_r1cs *r, cvmgpu_program_info *info);
+int cvmgpu_program_fused_tape(cvmgpu_program *p, cvmgpu_r1cs *r, const void **ins, uint64_t *n_ins, const void **consts,
+                              uint32_t *n_consts);
 /* value store -> .wtns row layout: d_wtns = B x n_wires x 32 B canonical LE */
 int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_wtns,
                               void *stream);

@@ -8,8 +8,9 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL) = range(44)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE) = range(45)
 F_ADDEND = 32        # T_DOT: field b is an addend
+F_CHECK = 128        # T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: compare the result with slot dst, c = constraint
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
 F_CZERO = 16         # T_SEL: third operand is the constant 0
@@ -26,9 +27,11 @@ BSLOT_DST = 0x8000      # dst field: idem
 ROW_BIT = 0x80000000    # row field: a bit row
 
 
-def run_tape(tape, consts_mont, layout, inputs):
+def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
     """layout: WitnessCalculator.layout() (slot files, typed rows, wire -> row map)
-    -> (witness: canonical value of every wire (None = its row was never written), status)"""
+    -> (witness: canonical value of every wire (None = its row was never written), status)
+    want_first_bad: also the first violated constraint of a tape with a fused R1CS check (T_RNE), 0xffffffff if none"""
+    first_bad = 0xFFFFFFFF
     consts = [M.from_mont(c) for c in consts_mont]
     slots = [None] * layout["n_slots"]
     bslots = [None] * layout["n_bslots"]
@@ -168,6 +171,10 @@ def run_tape(tape, consts_mont, layout, inputs):
             if status == 0 and operand(a, 1) != operand(b, 2):
                 status = c
             continue
+        elif op == T_RNE:
+            if operand(a, 1) != operand(b, 2):
+                first_bad = min(first_bad, c)
+            continue
         elif op == T_IFAIL_NE:
             if status == 0 and get_int(a, flags & 1) != get_int(b, flags & 2):
                 status = c
@@ -235,10 +242,16 @@ def run_tape(tape, consts_mont, layout, inputs):
             res = BIN[op](operand(a, 1), operand(b, 2))
         else:
             raise ValueError("bad tape op %d" % op)
+        if flags & F_CHECK:
+            # last instruction of a constraint of the fused R1CS check: compare with slot dst, constraint c; nothing is written
+            assert op in (T_ADD, T_SUB, T_MUL, T_DOT) and not flags & F_STORE
+            if res != get_slot(dst):
+                first_bad = min(first_bad, c)
+            continue
         set_slot(dst, res)
         if flags & F_STORE:
             assert op not in (T_CADD,) and (op != T_SEL or flags & F_CZERO)
             assert bool(dst & BSLOT_DST) == bool(c & ROW_BIT), "fused store between a slot and a row of different types"
             set_row(c, res)
     witness = [(brows[loc & ~ROW_BIT] if loc & ROW_BIT else frows[loc]) for loc in layout["wire_loc"]]
-    return witness, status
+    return (witness, status, first_bad) if want_first_bad else (witness, status)

@@ -31,3 +31,11 @@ for sub in (1 << 18, 1 << 17):
 
 h_wt = torch.empty((1 << 17, wc.n_wires, 32), dtype=torch.uint8).pin_memory()
 print("full rows B=131072: %.1f ms" % t(lambda: wc.calculate_select_into(h_in[:1 << 17], 0, wc.n_wires, h_wt, h_st[:1 << 17], r, h_bad[:1 << 17]), 6))
+
+for mode in (0, 1, 0, 1):
+    E.set_fused_mode(mode)
+    print("fused mode %d: full rows B=131072: %.1f ms | flags-only 1M: %.1f ms" % (
+        mode, t(lambda: wc.calculate_select_into(h_in[:1 << 17], 0, wc.n_wires, h_wt, h_st[:1 << 17], r, h_bad[:1 << 17]), 6),
+        t(lambda: wc.calculate_select_into(h_in, 0, 0, None, h_st, r, h_bad))))
+d_wt = torch.empty(h_wt.shape, dtype=torch.uint8, device="cuda")
+print("plain D2H of the same bytes: %.1f ms" % t(lambda: h_wt.copy_(d_wt, non_blocking=True), 6))
