@@ -243,6 +243,8 @@ def parse_args():
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--tape-mode", type=int, default=0, help="reserved")
+    ap.add_argument("--no-speculation", action="store_true",
+                    help="device-resident legs run the general tape even when the program has a speculative (bit-input) one")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: leave the host-buffer leg out")
     return ap.parse_args()
@@ -276,8 +278,14 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
     tmpdir = tempfile.mkdtemp(prefix="cvmbench_")
     art, cvm_path, r1cs_path = build_workload(tmpdir)
 
-    wc = E.WitnessCalculator(cvm_path=cvm_path, n_slots=args.slots)
+    wc_host = E.WitnessCalculator(cvm_path=cvm_path, n_slots=args.slots)
     r1 = E.R1cs(r1cs_path)
+    # Bit-heavy programs come with a second tape traced under "every main input is 0 or 1" that checks the assumption per
+    # witness (speculative typing, cvmgpu_program_speculative).  The host-buffer API (the e2e legs) uses it on its own and
+    # recomputes flagged witnesses with the general tape; the device-resident legs opt in here -- the synthetic messages are
+    # bits, `speculation_fallbacks` counts the witnesses that would have to be redone (0).
+    wc_spec = None if args.no_speculation else wc_host.speculative()
+    wc = wc_spec or wc_host
     info = wc.info.asdict()
     n_chunks = (B + CH - 1) // CH
     g = torch.Generator(device=dev)
@@ -360,6 +368,7 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
     # the L2 flush (when there is one) sits between the iterations, outside the step
     ms_total = (ms_tape + ms_check) * args.steps if flush is not None else t_start.elapsed_time(t_end)
     n_fail = int((status != 0).sum()) + int((bad != -1).sum())
+    n_spec_fail = int((status == E.ST_SPECULATION).sum())
     sep_tape = sep_check = None
     if fused:
         # the two stand-alone kernels on the same data, outside the step (what CVMGPU_FUSED=0 would run): reported next to it
@@ -425,13 +434,13 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         h_st = torch.empty(Be, dtype=torch.int32).pin_memory()
         h_bad = torch.empty(Be, dtype=torch.int32).pin_memory()
         for _ in range(2):
-            wc.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)
+            wc_host.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)
         if world > 1:
             dist.barrier()
         steps = max(2, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(steps):
-            wc.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)
+            wc_host.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)
         torch.cuda.synchronize()
         te = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
         if world > 1:
@@ -476,7 +485,7 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
     E.lib().cvmgpu_release_buffers()
 
     if rank != 0:
-        wc.close()
+        wc_host.close()
         r1.close()
         return None
 
@@ -595,6 +604,7 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
                    "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                    "n_slots": (finfo if fused else info)["n_slots"], "n_bit_slots": (finfo if fused else info)["n_bslots"],
                    "tape_len": (finfo if fused else info)["tape_len"],
+                   "speculative_bit_inputs": wc_spec is not None, "speculation_fallbacks": n_spec_fail,
                    "check": ("scheduled into the tape: one kernel per launch (csrc/fused.hpp)" if fused
                              else "separate kernels on the value store (r1cs_kernel + r1cs_table_kernel)"),
                    "stored_bytes_per_witness": stored_per_witness, "failures": n_fail, "flags_gather_ms": gather_ms},
@@ -608,7 +618,7 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         "clocks": sampler.summary(),
         "program": info, "fused_program": finfo if fused else None, "r1cs": rinfo,
     }
-    wc.close()
+    wc_host.close()
     r1.close()
     return line
 

@@ -90,6 +90,9 @@ struct cvmgpu_program {
     bool fusable = false;
     std::map<uint64_t, std::unique_ptr<cvmgpu_program>> fused;
     std::map<uint64_t, bool> fuse_worth;
+    // the same circuit traced under the assumption that every main input is 0 or 1 (see build_program), or null
+    std::unique_ptr<cvmgpu_program> spec;
+    std::atomic<bool> spec_off{false};   // set when a batch showed that the inputs are mostly not bits
 };
 
 // the CSR of an .r1cs bound to one value-store layout (r1cs.hpp bind), on the device
@@ -166,11 +169,12 @@ static double tape_cost(const tape::Tape &t) {
     return work * quant / std::max(4.0, std::min(resident, 24.0));
 }
 
-static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program **out) {
+static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume_bit_inputs, cvmgpu_program **out) {
     std::unique_ptr<cvmgpu_program> p(new cvmgpu_program());
     if (n_slots > 55) n_slots = 55;   // 55 * 4 KiB = 220 KiB of the 227 KiB a CTA may use
     try {
         tape::Tracer tr(parser.prog);
+        tr.assume_bit_inputs = assume_bit_inputs;
         tr.trace();
         p->binv = tape::batch_inversions(tr);
         if (n_slots == 0) {
@@ -246,6 +250,38 @@ static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program *
         return fail(CVMGPU_ERR_PARSE, e.what());
     }
     *out = p.release();
+    return CVMGPU_OK;
+}
+
+// Speculative typing.  Hash circuits take their message as unconstrained signals (nothing in Sha256(n) proves in[k] a bit),
+// so everything derived from the message before the first bit decomposition is field arithmetic on values that ARE 0 / 1
+// in every sensible input: for Sha256(512) 2 400 of the 2 401 field rows, 11 K of the 97 K tape instructions and all the
+// Montgomery products.  A bit-heavy program is therefore traced a second time under the assumption that every main input
+// is 0 or 1; that tape checks the assumption per witness (T_INPUT_BIT) and raises CVMGPU_ST_SPECULATION where it does not
+// hold.  The host-buffer entry points run the speculative tape and recompute the witnesses that raised the flag with the
+// general one, so results never depend on the assumption; device-API callers opt in (cvmgpu_program_speculative).
+// CVMGPU_SPECULATE=0 in the environment disables it.
+static int build_program(cvm::Parser &parser, uint32_t n_slots, cvmgpu_program **out) {
+    cvmgpu_program *p = nullptr;
+    if (int rc = build_program_impl(parser, n_slots, false, &p)) return rc;
+    static const bool enabled = !(getenv("CVMGPU_SPECULATE") && atoi(getenv("CVMGPU_SPECULATE")) == 0);
+    const tape::Tape &t = p->tape;
+    // (a handful of inputs that feed bit decompositions -- Num2Bits, comparators -- are numbers, not bits)
+    if (enabled && p->n_inputs >= 8 && t.n_fwires > 1 && t.n_bwires > 4 * (uint64_t)t.n_fwires) {
+        cvmgpu_program *q = nullptr;
+        if (build_program_impl(parser, n_slots, true, &q) == CVMGPU_OK) {
+            // worth it when it removes at least half of the field rows
+            if (q->tape.n_wires == t.n_wires && 2 * (uint64_t)q->tape.n_frows <= t.n_frows) p->spec.reset(q);
+            else delete q;
+        }
+    }
+    *out = p;
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_speculative(cvmgpu_program *p, cvmgpu_program **spec) {
+    if (!p || !spec) return fail(CVMGPU_ERR_ARG, "null argument");
+    *spec = p->spec.get();
     return CVMGPU_OK;
 }
 
@@ -465,7 +501,9 @@ static void on_device(int device, F &&fn) {
 static void release_program_tables(cvmgpu_program *p) {
     for (auto &kv : p->dev)
         on_device(kv.first, [&] { kv.second.d_tape.release(); kv.second.d_consts.release(); kv.second.d_wire_loc.release(); kv.second.d_iconsts.release(); });
-    for (auto &kv : p->fused) release_program_tables(kv.second.get());
+    for (auto &kv : p->fused)
+        if (kv.second) release_program_tables(kv.second.get());
+    if (p->spec) release_program_tables(p->spec.get());
 }
 
 extern "C" void cvmgpu_program_free(cvmgpu_program *p) {
@@ -779,9 +817,47 @@ static void release_pipe_buffers() {
 
 extern "C" void cvmgpu_release_buffers(void) { release_pipe_buffers(); }
 
+static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t wire0, uint32_t n_sel,
+                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
+
 extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
                                            uint32_t wire0, uint32_t n_sel, uint8_t *wtns_out, uint32_t *status,
                                            uint32_t *first_bad) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (!p->spec || p->spec_off || B == 0) return batch_select_impl(p, r, inputs, B, wire0, n_sel, wtns_out, status, first_bad);
+    // Speculative typing (build_program): the tape traced under "every main input is 0 or 1" runs the batch; the witnesses
+    // whose inputs are not (CVMGPU_ST_SPECULATION) are recomputed with the general tape and put in their places.
+    std::vector<uint32_t> st_local;
+    uint32_t *st = status;
+    if (!st) {
+        st_local.resize(B);
+        st = st_local.data();
+    }
+    if (int rc = batch_select_impl(p->spec.get(), r, inputs, B, wire0, n_sel, wtns_out, st, first_bad)) return rc;
+    std::vector<uint64_t> redo;
+    for (uint64_t b = 0; b < B; b++)
+        if (st[b] == tape::ST_SPECULATION) redo.push_back(b);
+    if (redo.empty()) return CVMGPU_OK;
+    // inputs that are mostly not bits: this circuit's inputs are numbers after all -- stop speculating on it
+    if (redo.size() * 2 > B && B >= 16) p->spec_off = true;
+    if (!wtns_out) n_sel = 0;
+    const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)n_sel * 32, n = redo.size();
+    std::vector<uint8_t> t_in(n * in_row), t_wt(n * out_row);
+    std::vector<uint32_t> t_st(n), t_bad(n);
+    for (size_t k = 0; k < n; k++) memcpy(t_in.data() + k * in_row, inputs + redo[k] * in_row, in_row);
+    if (int rc = batch_select_impl(p, r, t_in.data(), n, wire0, n_sel, out_row ? t_wt.data() : nullptr, t_st.data(),
+                                   r ? t_bad.data() : nullptr))
+        return rc;
+    for (size_t k = 0; k < n; k++) {
+        if (out_row) memcpy(wtns_out + redo[k] * out_row, t_wt.data() + k * out_row, out_row);
+        st[redo[k]] = t_st[k];
+        if (r && first_bad) first_bad[redo[k]] = t_bad[k];
+    }
+    return CVMGPU_OK;
+}
+
+static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t wire0, uint32_t n_sel,
+                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
     if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
     if (!inputs && p->n_inputs) return fail(CVMGPU_ERR_ARG, "null argument");

@@ -408,6 +408,16 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
             is_rb = true;
             break;
         }
+        case tape::T_INPUT_BIT: {
+            // speculative typing: main input cur.y taken as a bit.  Anything but a literal 0 / 1 marks the witness for the
+            // program traced without the assumption (the caller recomputes it there); sticky, nothing else overwrites it.
+            const uint4 *src = p.inputs + (w * p.n_inputs + cur.y) * 2;
+            const uint4 lo = src[0], hi = src[1];
+            if (lo.x > 1u || (lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) != 0u) status = tape::ST_SPECULATION;
+            rb = lo.x & 1u;
+            is_rb = true;
+            break;
+        }
         case tape::T_BITC: {
             // bit cur.z of the raw limbs of slot a: one 32-bit shared-memory read
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(slots);

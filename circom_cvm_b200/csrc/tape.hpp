@@ -1207,7 +1207,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
             out.stats.n_dot_terms += o.tn;
         } else {
             uint32_t e0 = enc[0], e1 = enc[1], e2 = enc[2];
-            if (o.op == T_INPUT) e0 = o.aux;
+            if (o.op == T_INPUT || o.op == T_INPUT_BIT) e0 = o.aux;
             if (o.op == T_BITC || o.op == T_IBIT) e1 = o.aux;
             if (o.op == T_LUT) {   // a = bit slots 0 and 1 (16 bits each); b = table | k << 8 | bit slot 2 << 16; c is free for the fused store
                 e0 = (enc[0] & 0xffffu) | ((enc[1] & 0xffffu) << 16);

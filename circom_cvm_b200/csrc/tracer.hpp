@@ -56,13 +56,16 @@ enum TOp : uint8_t {
     T_FILL,      // constant bit rows [c, c + b) = the word a (witness wires bound to the constants 0 / 1)
     // R1CS check scheduled into the tape (fused.hpp)
     T_RNE,       // first_bad = min(first_bad, c) if a != b   (a = A.w * B.w, b = C.w of constraint c)
+    // speculative typing (Tracer::assume_bit_inputs): main input `a`, which must be literally 0 or 1 -- typed 0/1; any
+    // other value raises ST_SPECULATION and the witness is recomputed by the program traced without the assumption
+    T_INPUT_BIT,
     T_COUNT
 };
 
 static const uint32_t CONST_FLAG = 0x80000000u;
 static const uint32_t NO_REF = 0xffffffffu;
 
-enum Status : uint32_t { ST_OK = 0, ST_ASSERT = 1, ST_TOINT = 2, ST_DIVZERO = 3, ST_INPUT = 4, ST_LOOP = 5 };
+enum Status : uint32_t { ST_OK = 0, ST_ASSERT = 1, ST_TOINT = 2, ST_DIVZERO = 3, ST_INPUT = 4, ST_LOOP = 5, ST_SPECULATION = 6 };
 
 struct SOp {
     uint8_t op;
@@ -106,6 +109,10 @@ class Tracer {
         uint32_t ref = 0;   // AV_FF: const index ; AV_DYN: value id
     };
 
+    // Trace under the assumption that every main input is 0 or 1 (hash circuits take their message as unconstrained
+    // signals: nothing in Sha256(n) proves in[k] a bit, so everything derived from the message before the first bit
+    // decomposition is field arithmetic).  The assumption is CHECKED per witness at run time (T_INPUT_BIT).
+    bool assume_bit_inputs = false;
     std::vector<SOp> ops;
     std::vector<uint8_t> isbool;  // per op: the value is provably 0 or 1 (comparison results, extracted bits, ANDs of those)
     // Boolean-cone collapsing.  For every value that is an arithmetic function of at most three provably-0/1 values, the
@@ -145,7 +152,7 @@ class Tracer {
         n_outputs = mainc.n_outputs;
         int main_idx = new_comp(prog.start, 1);              // circuit.rs:539: main at signal 1
         for (int64_t k = 0; k < n_inputs; k++) {             // main inputs follow main outputs (App. A.5)
-            SOp o{T_INPUT, NO_REF, NO_REF, NO_REF, (uint32_t)k};
+            SOp o{(uint8_t)(assume_bit_inputs ? T_INPUT_BIT : T_INPUT), NO_REF, NO_REF, NO_REF, (uint32_t)k};
             push_op(o);
             AV v;
             v.kind = AV_DYN;
@@ -283,7 +290,7 @@ class Tracer {
         bool bl = false;
         switch (o.op) {
             case T_LT: case T_LE: case T_GT: case T_GE: case T_EQ: case T_NEQ: case T_LAND: case T_LOR: case T_EQZ:
-            case T_BITC: case T_LUT: bl = true; break;
+            case T_BITC: case T_LUT: case T_INPUT_BIT: bl = true; break;
             case T_SEL: bl = is_bool(o.b) && is_bool(o.c); break;
             default: break;
         }

@@ -22,14 +22,14 @@ import numpy as np
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libcvmgpu.so")
 
-ST_OK, ST_ASSERT, ST_TOINT, ST_DIVZERO, ST_INPUT, ST_LOOP = 0, 1, 2, 3, 4, 5   # include/cvmgpu.h CVMGPU_ST_*
+ST_OK, ST_ASSERT, ST_TOINT, ST_DIVZERO, ST_INPUT, ST_LOOP, ST_SPECULATION = 0, 1, 2, 3, 4, 5, 6   # include/cvmgpu.h CVMGPU_ST_*
 NO_BAD = 0xFFFFFFFF
 ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (csrc/tape.hpp ROW_BIT)
 
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_load_files", "cvmgpu_program_load_text3", "cvmgpu_witness_batch_checked_dev", "cvmgpu_store_bytes_checked",
-    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_info_get", "cvmgpu_program_free",
+    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_speculative", "cvmgpu_program_info_get", "cvmgpu_program_free",
     "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_multi", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
@@ -114,6 +114,7 @@ def lib():
     L.cvmgpu_store_bytes_checked.argtypes = [c_void_p, c_void_p, c_uint64]
     L.cvmgpu_store_bytes_checked.restype = c_size_t
     L.cvmgpu_witness_batch_checked_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_program_speculative.argtypes = [c_void_p, POINTER(c_void_p)]
     L.cvmgpu_program_fused_info_get.argtypes = [c_void_p, c_void_p, POINTER(ProgramInfo)]
     L.cvmgpu_program_fused_tape.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_wtns_write.argtypes = [c_char_p, c_void_p, c_uint32]
@@ -197,6 +198,11 @@ class WitnessCalculator:
             _check(L.cvmgpu_program_load_text3(data, len(data), cpp, len(cpp) if cpp else 0, dat_bytes,
                                                len(dat_bytes) if dat_bytes else 0, n_slots, byref(h)))
         self._h = h
+        self._owner = None
+        self._finish_init()
+
+    def _finish_init(self):
+        L = lib()
         info = ProgramInfo()
         info.struct_size = ctypes.sizeof(ProgramInfo)
         _check(L.cvmgpu_program_info_get(self._h, byref(info)))
@@ -205,10 +211,24 @@ class WitnessCalculator:
         self.n_wires = int(info.n_wires)
         self.n_rows = int(info.n_rows)
 
+    def speculative(self):
+        """The same circuit traced under "every main input is 0 or 1" (bit-heavy programs only; None otherwise): a
+        WitnessCalculator for the DEVICE API with its own value-store layout.  Witnesses it flags ST_SPECULATION must be
+        recomputed with this calculator; the host-buffer calls (calculate*, calculate_checked ...) do all of that themselves.
+        The handle belongs to this object."""
+        h = c_void_p()
+        _check(lib().cvmgpu_program_speculative(self._h, byref(h)))
+        if not h.value:
+            return None
+        child = WitnessCalculator.__new__(WitnessCalculator)
+        child._h, child._owner = h, self
+        child._finish_init()
+        return child
+
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self, "_owner", None) is None:
             lib().cvmgpu_program_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:

@@ -48,6 +48,8 @@ extern "C" {
 #define CVMGPU_ST_ASSERT 1   /* failed assert / `===`   (assert_bucket.rs:71-86) */
 #define CVMGPU_ST_TOINT 2    /* Fr_toInt overflow        (bn128/fr.cpp:165-167) */
 #define CVMGPU_ST_DIVZERO 3  /* `\` or `%` by zero       (GMP division by zero in the reference) */
+#define CVMGPU_ST_SPECULATION 6 /* only from a speculative program (cvmgpu_program_speculative): a main input is not 0 / 1 --
+                                   recompute this witness with the program itself.  The host-buffer calls do that. */
 #define CVMGPU_ST_LOOP 5     /* a data-dependent while loop needed more iterations than were traced (260) */
 
 typedef struct cvmgpu_program cvmgpu_program;
@@ -142,6 +144,16 @@ int cvmgpu_program_load_files(const char *cvm_path, const char *cpp_path, const 
                               cvmgpu_program **out);
 int cvmgpu_program_load_text3(const char *cvm_text, size_t len, const char *cpp_text, size_t cpp_len, const void *dat,
                               size_t dat_len, uint32_t n_slots, cvmgpu_program **out);
+/* Speculative typing.  Hash circuits take their message as unconstrained signals (nothing in Sha256(n) proves in[k] a
+ * bit), so what is derived from the message before the first bit decomposition is field arithmetic on values that are
+ * 0 / 1 in every sensible input.  Bit-heavy programs are traced a second time under the assumption that EVERY main input
+ * is literally 0 or 1; that tape checks the assumption per witness and sets CVMGPU_ST_SPECULATION where it fails.  The
+ * host-buffer entry points (cvmgpu_witness_batch*, _select, _multi) run it and recompute the flagged witnesses with the
+ * general tape: results are identical for every input.  Device-API callers opt in: *spec (owned by p; NULL when p has
+ * none) is a program handle with its own value-store layout for cvmgpu_witness_batch_dev / _export_dev /
+ * cvmgpu_r1cs_check_store_dev / cvmgpu_store_bytes / cvmgpu_program_info_get; witnesses it flags must be redone with p.
+ * CVMGPU_SPECULATE=0 in the environment: never build one. */
+int cvmgpu_program_speculative(cvmgpu_program *p, cvmgpu_program **spec);
 int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info);
 void cvmgpu_program_free(cvmgpu_program *p);
 /* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table

@@ -8,8 +8,9 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE) = range(45)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE, T_INPUT_BIT) = range(46)
 F_ADDEND = 32        # T_DOT: field b is an addend
+ST_SPECULATION = 6
 F_CHECK = 128        # T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: compare the result with slot dst, c = constraint
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
 NO_ROW = 0xFFFFFFFF
@@ -171,6 +172,12 @@ def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
             if status == 0 and operand(a, 1) != operand(b, 2):
                 status = c
             continue
+        elif op == T_INPUT_BIT:
+            # speculative typing: the input must be literally 0 or 1, else the witness is marked for the generic program
+            v = int(inputs[a])
+            if v > 1:
+                status = ST_SPECULATION
+            res = v & 1
         elif op == T_RNE:
             if operand(a, 1) != operand(b, 2):
                 first_bad = min(first_bad, c)

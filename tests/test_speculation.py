@@ -1,0 +1,126 @@
+"""Speculative typing of main inputs (csrc/cvmgpu.cu build_program, tracer.hpp assume_bit_inputs).
+
+Sha256(n) takes its message as unconstrained signals, so nothing proves in[k] a bit and what is derived from the message
+before the first bit decomposition is field arithmetic.  Bit-heavy programs are traced a second time under "every main
+input is 0 or 1"; that tape checks the assumption per witness (ST_SPECULATION) and the host-buffer API recomputes flagged
+witnesses with the general tape -- so the results must be the oracle's for EVERY input, bits or not."""
+import random
+
+import pytest
+
+from conftest import circuit
+from oracle import cvm_interp as I
+from oracle import fr_model as M
+from tape_emulator import ST_SPECULATION, run_tape
+
+
+def test_speculative_tape_of_sha256(cvmlib):
+    from circom_cvm_b200 import engine as E
+    art = circuit("sha256_64")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    sp = wc.speculative()
+    assert sp is not None
+    assert sp.n_wires == wc.n_wires and sp.n_inputs == wc.n_inputs
+    # the field rows are gone (wire 0 keeps one), and so are the Montgomery products
+    assert wc.info.n_frows > 100 and sp.info.n_frows == 1
+    assert wc.info.tape_mul > 0 and sp.info.tape_mul == 0
+    assert sp.info.tape_len < wc.info.tape_len
+    tape, consts = sp.tape()
+    prog = I.load(art.cvm)
+    rng = random.Random(3)
+    for _ in range(3):
+        inp = [rng.randrange(2) for _ in range(art.n_inputs)]
+        rows, st = run_tape(tape, consts, sp.layout(), inp)
+        assert st == 0 and rows == I.compute_witness(prog, inp)
+    for bad in (2, 7, M.Q - 1, 1 << 200):
+        inp = [rng.randrange(2) for _ in range(art.n_inputs)]
+        inp[rng.randrange(art.n_inputs)] = bad
+        _rows, st = run_tape(tape, consts, sp.layout(), inp)
+        assert st == ST_SPECULATION
+    sp.close()
+    assert wc.speculative() is not None          # the handle belongs to the program, closing the view does not free it
+
+
+@pytest.mark.parametrize("name", ["poseidon2", "eddsa", "num2bits8", "lessthan8", "opszoo", "multiplier2", "babyadd4"])
+def test_programs_that_do_not_speculate(cvmlib, name):
+    """field programs have nothing to gain; a handful of inputs feeding bit decompositions are numbers, not bits"""
+    from circom_cvm_b200 import engine as E
+    assert E.WitnessCalculator(cvm_text=circuit(name).cvm).speculative() is None
+
+
+@pytest.mark.gpu
+def test_host_api_is_exact_for_bits_and_for_anything_else(cvmlib, tmp_path):
+    """Sha256(64): messages of bits, and rows where some `bit` is 2, q-1, a random field element.  The host-buffer call runs the
+    speculative tape and redoes the flagged rows with the general one: every row equals the oracle's witness, the R1CS verdict
+    is that of the stand-alone check on the returned rows, and the speculative program alone flags exactly the non-bit rows."""
+    import numpy as np
+    import torch
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.build import write_artifact
+    art = circuit("sha256_64")
+    paths = write_artifact(art, str(tmp_path))
+    wc, r = E.WitnessCalculator(cvm_text=art.cvm), E.R1cs(paths["r1cs"])
+    rng = random.Random(17)
+    rows = [[rng.randrange(2) for _ in range(art.n_inputs)] for _ in range(97)]
+    odd = {5: 2, 31: M.Q - 1, 32: rng.randrange(M.Q), 96: 1 << 64}
+    for b, v in odd.items():
+        rows[b][rng.randrange(art.n_inputs)] = v
+    wt, st, bad = wc.calculate_checked(rows, r)
+    assert not st.any()
+    assert (r.check(wt) == bad).all()
+    assert (bad[[b for b in range(97) if b not in odd]] == E.NO_BAD).all()
+    got = E.le_to_ints(wt)
+    prog = I.load(art.cvm)
+    for b in list(odd) + [0, 1, 50]:
+        assert got[b] == I.compute_witness(prog, rows[b]), b
+    # the same batch without the check, and through the output selector
+    wt2, st2 = wc.calculate(rows)
+    assert np.array_equal(wt2, wt) and not st2.any()
+    # device API, opted in: the speculative program flags exactly the rows that are not bits
+    sp = wc.speculative()
+    B = len(rows)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(E.ints_to_le(rows, art.n_inputs)).to(dev)
+    store = torch.zeros(sp.store_bytes(B), dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(B, dtype=torch.int32, device=dev)
+    sp.run_dev(d_in, B, B, store, d_st, torch.cuda.current_stream().cuda_stream)
+    d_wt = torch.empty((B, sp.n_wires, 32), dtype=torch.uint8, device=dev)
+    sp.export_dev(store, B, B, d_wt, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    flagged = set(int(b) for b in torch.nonzero(d_st == E.ST_SPECULATION).flatten().cpu())
+    assert flagged == set(odd) and int((d_st != 0).sum()) == len(odd)
+    keep = [b for b in range(B) if b not in odd]
+    assert np.array_equal(d_wt.cpu().numpy()[keep], wt[keep])
+
+
+@pytest.mark.gpu
+def test_speculation_switches_itself_off_when_inputs_are_numbers(cvmlib, tmp_path):
+    """A bit-heavy circuit whose many inputs are NUMBERS (each one range-checked by a Num2Bits): the first batch shows it, the
+    program stops speculating, results are exact throughout."""
+    import numpy as np
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.build import compile_circuit
+    from tools.circuitgen.circuits import basic
+
+    def RangeChecks(T):
+        x = T.input("x", (12,))
+        out = T.output("out", (12,))
+        n2b = T.component("n2b", (12,))
+        i = T.var("i")
+        with T.for_(i, 0, i < 12):
+            T.new(n2b[i], basic.Num2Bits, 16)
+        with T.for_(i, 0, i < 12):
+            T.bind(n2b[i].pin("in"), x[i])
+            T.bind(out[i], n2b[i].pin("out")[3])
+    art = compile_circuit(RangeChecks, (), name="rangechecks")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    assert wc.speculative() is not None
+    rng = random.Random(4)
+    rows = [[rng.randrange(1 << 16) for _ in range(12)] for _ in range(64)]
+    prog = I.load(art.cvm)
+    for _round in range(2):
+        wt, st = wc.calculate(rows)
+        assert not st.any()
+        got = E.le_to_ints(wt)
+        for b in (0, 7, 63):
+            assert got[b] == I.compute_witness(prog, rows[b])
