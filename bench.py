@@ -433,14 +433,17 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         h_wt = torch.empty((Be, n_sel, 32), dtype=torch.uint8).pin_memory() if n_sel else None
         h_st = torch.empty(Be, dtype=torch.int32).pin_memory()
         h_bad = torch.empty(Be, dtype=torch.int32).pin_memory()
-        for _ in range(2):
+        for _ in range(3):
             wc_host.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)
         if world > 1:
             dist.barrier()
-        steps = max(2, min(args.steps, 5))
+        steps = max(3, min(args.steps, 8))
+        per_step = []
         t0 = time.perf_counter()
         for _ in range(steps):
-            wc_host.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)
+            t1 = time.perf_counter()
+            wc_host.calculate_select_into(h_in, wire0, n_sel, h_wt, h_st, r1, h_bad)     # synchronous: returns with the results
+            per_step.append(time.perf_counter() - t1)
         torch.cuda.synchronize()
         te = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
         if world > 1:
@@ -449,6 +452,7 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         ok = int((h_st != 0).sum()) == 0 and int((h_bad != -1).sum()) == 0
         out = {"value": world * Be / sec, "unit": UNIT, "h2d_bytes_per_step": Be * wc.n_inputs * 32,
                "d2h_bytes_per_step": Be * (n_sel * 32 + 8), "batch_per_gpu": Be, "ms_per_step": 1000 * sec,
+               "steps": steps, "ms_per_step_median": 1000 * sorted(per_step)[len(per_step) // 2], "ms_per_step_max": 1000 * max(per_step),
                "all_witnesses_valid": bool(ok), "api": api}
         if h_wt is not None and h_wt.numel() >= (64 << 20):
             # what the host lets through: the same bytes copied device -> the same pinned buffer by plain cudaMemcpy, every
