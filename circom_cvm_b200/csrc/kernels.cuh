@@ -27,7 +27,7 @@ __device__ __forceinline__ uint4 *row_ptr(const uint4 *wbase, uint32_t row, uint
 
 using fr::Fr;
 
-#define TAPE_PAD 48   // no-op instructions after the last one on the device copy of a tape (fetch / prefetch without bound checks)
+#define TAPE_PAD 96   // no-op instructions after the last one on the device copy of a tape (fetch / prefetch without bound checks)
 #define CVM_NT 128   // threads (= witnesses) per CTA of the tape kernel for large batches (64 / 32 for small ones)
 
 __device__ __forceinline__ Fr unpack(const uint4 &lo, const uint4 &hi) {
@@ -242,10 +242,18 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
     const uint4 *tp = reinterpret_cast<const uint4 *>(p.tape);
     const uint32_t n_ins = p.n_ins;
     uint4 raw = __ldg(tp);
+    uint32_t pf = 0;   // first tape word (8 per 128-byte line) not yet prefetched into L1
     for (uint32_t pc = 0; pc < n_ins; pc++) {
         const uint4 cur = raw;
         raw = __ldg(tp + pc + 1);   // the next instruction (re-done after the records of a DOT / ISUM)
-        if ((pc & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + pc + 32));   // tape lines ahead
+        // tape lines ahead.  With group instructions pc jumps over up to 33 words at a time: the window follows pc.
+        if (BITS) {
+#pragma unroll 1
+            while (pf < pc + 64u) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + pf));
+                pf += 8u;
+            }
+        } else if ((pc & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + pc + 32));
         const uint32_t op = cur.x & 0xffu;
         const uint32_t flags = (cur.x >> 8) & 0xffu;
         const uint32_t dst = cur.x >> 16;
@@ -304,16 +312,20 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
             const uint32_t n = cur.y;
             unsigned long long v = 0;
             if (flags & tape::F_ADDEND) v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            // record 0 is what the loop fetched as "the next instruction"; each iteration fetches the record after the one it
+            // works on, and the last one thereby fetches the instruction that follows the records
+            uint4 rec = raw;
             for (uint32_t j = 0; j < n; j += 4) {
-                const uint4 rec = __ldg(tp + pc + 1 + (j >> 2));
+                const uint4 nxt = __ldg(tp + pc + 2 + (j >> 2));
                 v += (unsigned long long)((bw[rec.x & 0xffffu] >> lane) & 1u) << (rec.x >> 16);
                 if (j + 1 < n) v += (unsigned long long)((bw[rec.y & 0xffffu] >> lane) & 1u) << (rec.y >> 16);
                 if (j + 2 < n) v += (unsigned long long)((bw[rec.z & 0xffffu] >> lane) & 1u) << (rec.z >> 16);
                 if (j + 3 < n) v += (unsigned long long)((bw[rec.w & 0xffffu] >> lane) & 1u) << (rec.w >> 16);
+                rec = nxt;
             }
             slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
             pc += (n + 3) >> 2;
-            raw = __ldg(tp + pc + 1);
+            raw = rec;
             continue;
         }
         case tape::T_LUTG: case tape::T_IBITG: {
