@@ -84,6 +84,7 @@ struct TraceStats {
     uint64_t ref_field_ops = 0;      // all ff.* executions of the reference program
     uint64_t folded = 0, cse_hits = 0;
     uint64_t dyn_branches = 0;
+    uint64_t dyn_addresses = 0;     // ff.wrap_i64 of a witness value (data-dependent array index)
     uint64_t luts = 0;                  // boolean cones emitted as one T_LUT
     uint64_t unrolled_iterations = 0;   // iterations of data-dependent while loops traced under predicates
     uint64_t unset_signal_reads = 0;
@@ -102,11 +103,15 @@ struct FrEq {
 
 class Tracer {
   public:
-    enum { AV_UNDEF = 0, AV_I64, AV_FF, AV_DYN };
+    // AV_DADDR: an address that depends on a witness value: i + scale * toInt(value `ref`) (ff.wrap_i64 of a dynamic value,
+    // then i64.add / i64.mul with constants).  Loads and variable stores through it are traced as selections over the
+    // addresses it can name (mux_candidates); everything else that needs a static integer rejects it.
+    enum { AV_UNDEF = 0, AV_I64, AV_FF, AV_DYN, AV_DADDR };
     struct AV {
         uint8_t kind = AV_UNDEF;
         int64_t i = 0;
-        uint32_t ref = 0;   // AV_FF: const index ; AV_DYN: value id
+        uint32_t ref = 0;   // AV_FF: const index ; AV_DYN, AV_DADDR: value id
+        int64_t scale = 0;  // AV_DADDR
     };
 
     // Trace under the assumption that every main input is 0 or 1 (hash circuits take their message as unconstrained
@@ -261,10 +266,64 @@ class Tracer {
                 throw TraceError(std::string("field constant does not fit an address (") + what + ")");
             return out;
         }
-        if (v.kind == AV_DYN)
+        if (v.kind == AV_DYN || v.kind == AV_DADDR)
             throw TraceError(std::string("data-dependent ") + what + " is not supported by the trace compiler");
         return 0;
     }
+    // ---- data-dependent addresses
+    static const size_t MAX_MUX = 4096;
+    // Upper bound of a value as a non-negative integer when the shape of its computation gives one (masks, remainders,
+    // shifts, sums and products of such, truth values), else -1.  Bounds the locations an index can name: without one a
+    // variable store through a data-dependent index has to treat every variable of the frame as a possible target.
+    std::vector<int64_t> ub_memo;
+    int64_t ubound(uint32_t r, int depth = 0) {
+        static const int64_t LIM = (int64_t)1 << 40;
+        if (r == NO_REF) return -1;
+        if (r & CONST_FLAG) {
+            const int64_t c = small_const(r);
+            return c;
+        }
+        if (isbool[r]) return 1;
+        if (depth > 64) return -1;
+        if (ub_memo.size() < ops.size()) ub_memo.resize(ops.size(), -2);
+        if (ub_memo[r] != -2) return ub_memo[r];
+        const SOp &o = ops[r];
+        int64_t res = -1;
+        const int64_t a = (o.a != NO_REF) ? ubound(o.a, depth + 1) : -1, b = (o.b != NO_REF) ? ubound(o.b, depth + 1) : -1;
+        switch (o.op) {
+            case T_BAND: res = a < 0 ? b : b < 0 ? a : std::min(a, b); break;
+            case T_MOD: if (b > 0) res = a >= 0 ? std::min(a, b - 1) : b - 1; break;
+            case T_IDIV: if (a >= 0 && is_const(o.b) && b > 0) res = a / b; break;
+            case T_SHR: if (a >= 0 && is_const(o.b) && b >= 0 && b < 63) res = a >> b; else if (a >= 0) res = a; break;
+            case T_ADD: if (a >= 0 && b >= 0 && a + b < LIM) res = a + b; break;
+            case T_MUL: if (a >= 0 && b >= 0 && (a == 0 || b < LIM / std::max<int64_t>(a, 1))) res = a * b; break;
+            case T_SEL: {
+                const int64_t c = (o.c != NO_REF) ? ubound(o.c, depth + 1) : -1;
+                if (b >= 0 && c >= 0) res = std::max(b, c);
+                break;
+            }
+            default: break;
+        }
+        if (res >= LIM) res = -1;
+        ub_memo[r] = res;
+        return res;
+    }
+    // the (index k, address) pairs an AV_DADDR can name inside [0, limit), smallest address first
+    std::vector<std::pair<int64_t, int64_t>> mux_candidates(const AV &a, int64_t limit, const char *what) {
+        std::vector<std::pair<int64_t, int64_t>> out;
+        if (a.scale == 0) throw TraceError("degenerate data-dependent address");
+        const int64_t kmax = ubound(a.ref);
+        for (int64_t k = 0;; k++) {
+            const int64_t addr = a.i + a.scale * k;
+            if (kmax >= 0 && k > kmax) break;
+            if (a.scale > 0 ? addr >= limit : addr < 0) break;
+            if (addr >= 0 && addr < limit) out.emplace_back(k, addr);
+            if (out.size() > MAX_MUX) throw TraceError(std::string("data-dependent ") + what + " ranges over more than 4096 locations");
+            if (k > (int64_t)1 << 31) break;
+        }
+        return out;
+    }
+    uint32_t index_is(const AV &a, int64_t k) { return emit(T_EQ, a.ref, CONST_FLAG | intern(hostfr::from_i64(k))); }
 
     // ---------------------------------------------------------------- SSA emission
     static bool commutative(uint8_t op) {
@@ -720,12 +779,49 @@ class Tracer {
                 }
                 case OP_FF_WRAP_I64: {
                     AV v = val(f, in.args.at(0));
+                    if (v.kind == AV_DYN) {
+                        // Fr_toInt of a witness value (generic/fr.cpp:1102-1170): defined for -2^31 <= x < 2^31 (around 0 mod q),
+                        // the reference asserts otherwise -> ST_TOINT.  The result is only usable as (part of) an address.
+                        const uint32_t lo = emit(T_GE, v.ref, CONST_FLAG | intern(hostfr::from_i64(-((int64_t)1 << 31))));
+                        const uint32_t hi = emit(T_LT, v.ref, CONST_FLAG | intern(hostfr::from_i64((int64_t)1 << 31)));
+                        uint32_t bad = emit(T_EQZ, emit(T_LAND, lo, hi));
+                        if (!preds.empty()) bad = emit(T_LAND, pred_conj(), bad);
+                        emit(T_FAIL_IF, bad, NO_REF, NO_REF, ST_TOINT);
+                        stats.dyn_addresses++;
+                        AV a;
+                        a.kind = AV_DADDR;
+                        a.ref = v.ref;
+                        a.i = 0;
+                        a.scale = 1;
+                        set_reg(f, in.dst, a);
+                        pc++;
+                        break;
+                    }
                     set_reg(f, in.dst, i64_av(int_of(v, "array index (ff.wrap_i64)")));
                     pc++;
                     break;
                 }
                 case OP_I64_ADD: case OP_I64_SUB: case OP_I64_MUL: case OP_I64_LT: case OP_I64_LE: case OP_I64_GT:
                 case OP_I64_GE: case OP_I64_EQ: case OP_I64_NEQ: {
+                    {
+                        // address arithmetic on a data-dependent index: affine in it (AddAddress / MulAddress with constants)
+                        const AV x = val(f, in.args.at(0)), y = val(f, in.args.at(1));
+                        if (x.kind == AV_DADDR || y.kind == AV_DADDR) {
+                            AV r = x.kind == AV_DADDR ? x : y;
+                            const AV &o = x.kind == AV_DADDR ? y : x;
+                            if (o.kind == AV_DADDR) throw TraceError("arithmetic on two data-dependent addresses is not supported");
+                            const int64_t c = int_of(o, "i64 operand");
+                            if (in.op == OP_I64_ADD) r.i += c;
+                            else if (in.op == OP_I64_SUB && x.kind == AV_DADDR) r.i -= c;
+                            else if (in.op == OP_I64_SUB) { r.i = c - r.i; r.scale = -r.scale; }
+                            else if (in.op == OP_I64_MUL) { r.i *= c; r.scale *= c; }
+                            else throw TraceError("comparison of a data-dependent address is not supported");
+                            if (r.scale == 0) r = i64_av(r.i);
+                            set_reg(f, in.dst, r);
+                            pc++;
+                            break;
+                        }
+                    }
                     int64_t a = int_of(val(f, in.args.at(0)), "i64 operand"), b = int_of(val(f, in.args.at(1)), "i64 operand");
                     int64_t r = 0;
                     switch (in.op) {
@@ -740,6 +836,21 @@ class Tracer {
                     break;
                 }
                 case OP_FF_LOAD: {
+                    if (val(f, in.args.at(0)).kind == AV_DADDR) {
+                        // var[index]: the value of whichever written variable the index names (an unwritten one reads 0)
+                        const AV a = val(f, in.args.at(0));
+                        int64_t limit = code.is_function ? code.local_memory : 0;
+                        for (const auto &kv : f.lvar) limit = std::max(limit, kv.first + 1);
+                        uint32_t r = CONST_FLAG | c_zero;
+                        for (const auto &ka : mux_candidates(a, limit, "variable address")) {
+                            auto it = f.lvar.find(ka.second);
+                            if (it == f.lvar.end()) continue;
+                            r = emit(T_SEL, index_is(a, ka.first), field_ref(it->second), r);
+                        }
+                        set_reg(f, in.dst, ref_av(r));
+                        pc++;
+                        break;
+                    }
                     int64_t addr = int_of(val(f, in.args.at(0)), "variable address");
                     auto it = f.lvar.find(addr);
                     set_reg(f, in.dst, it == f.lvar.end() ? ff_av(c_zero) : it->second);
@@ -747,12 +858,36 @@ class Tracer {
                     break;
                 }
                 case OP_FF_STORE: {
+                    if (val(f, in.args.at(0)).kind == AV_DADDR) {
+                        // var[index] = v: every variable the index can name keeps its value unless it is the one
+                        const AV a = val(f, in.args.at(0));
+                        int64_t limit = code.is_function ? code.local_memory : 0;
+                        for (const auto &kv : f.lvar) limit = std::max(limit, kv.first + 1);
+                        const uint32_t v = field_ref(val(f, in.args.at(1)));
+                        for (const auto &ka : mux_candidates(a, limit, "variable address")) {
+                            auto it = f.lvar.find(ka.second);
+                            const uint32_t old = it == f.lvar.end() ? (CONST_FLAG | c_zero) : field_ref(it->second);
+                            set_lvar(f, ka.second, ref_av(emit(T_SEL, index_is(a, ka.first), v, old)));
+                        }
+                        pc++;
+                        break;
+                    }
                     int64_t addr = int_of(val(f, in.args.at(0)), "variable address");
                     set_lvar(f, addr, ref_av(field_ref(val(f, in.args.at(1)))));
                     pc++;
                     break;
                 }
                 case OP_GET_SIGNAL: {
+                    if (val(f, in.args.at(0)).kind == AV_DADDR) {
+                        const AV a = val(f, in.args.at(0));
+                        const int64_t start = comps[(size_t)ci].start, limit = prog.codes[(size_t)comps[(size_t)ci].code].n_signals;
+                        uint32_t r = CONST_FLAG | c_zero;
+                        for (const auto &ka : mux_candidates(a, limit, "signal index"))
+                            r = emit(T_SEL, index_is(a, ka.first), field_ref(sig[(size_t)(start + ka.second)]), r);
+                        set_reg(f, in.dst, ref_av(r));
+                        pc++;
+                        break;
+                    }
                     int64_t idx = comps[(size_t)ci].start + int_of(val(f, in.args.at(0)), "signal index");
                     if (idx < 0 || idx >= (int64_t)sig.size()) throw TraceError("signal index out of range");
                     set_reg(f, in.dst, ref_av(field_ref(sig[(size_t)idx])));
@@ -766,6 +901,17 @@ class Tracer {
                     break;
                 }
                 case OP_GET_CMP_SIGNAL: {
+                    if (val(f, in.args.at(1)).kind == AV_DADDR) {
+                        Comp &sc = sub_of(ci, val(f, in.args.at(0)));
+                        const AV a = val(f, in.args.at(1));
+                        const int64_t limit = prog.codes[(size_t)sc.code].n_signals;
+                        uint32_t r = CONST_FLAG | c_zero;
+                        for (const auto &ka : mux_candidates(a, limit, "signal index"))
+                            r = emit(T_SEL, index_is(a, ka.first), field_ref(sig[(size_t)(sc.start + ka.second)]), r);
+                        set_reg(f, in.dst, ref_av(r));
+                        pc++;
+                        break;
+                    }
                     Comp &s = sub_of(ci, val(f, in.args.at(0)));
                     int64_t idx = s.start + int_of(val(f, in.args.at(1)), "signal index");
                     if (idx < 0 || idx >= (int64_t)sig.size()) throw TraceError("signal index out of range");

@@ -46,7 +46,7 @@ extern "C" {
 /* per-witness status words (the reference aborts the process in these cases) */
 #define CVMGPU_ST_OK 0
 #define CVMGPU_ST_ASSERT 1   /* failed assert / `===`   (assert_bucket.rs:71-86) */
-#define CVMGPU_ST_TOINT 2    /* Fr_toInt overflow        (bn128/fr.cpp:165-167) */
+#define CVMGPU_ST_TOINT 2    /* Fr_toInt of a value outside [-2^31, 2^31): a data-dependent array index (generic/fr.cpp:1102-1170) */
 #define CVMGPU_ST_DIVZERO 3  /* `\` or `%` by zero       (GMP division by zero in the reference) */
 #define CVMGPU_ST_SPECULATION 6 /* only from a speculative program (cvmgpu_program_speculative): a main input is not 0 / 1 --
                                    recompute this witness with the program itself.  The host-buffer calls do that. */

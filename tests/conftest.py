@@ -54,6 +54,7 @@ def circuit(name):
         "lessthan8": (basic.LessThan, (8,)),
         "sum3cmp": (basic.Sum3Cmp, ()),
         "mixedarr": (basic.MixedArr, ()),
+        "dynindex": (basic.DynIndex, ()),
         "opszoo": (basic.OpsZoo, ()),
         "poseidon2": (poseidon.Poseidon, (2,)),
         "poseidon2m": (poseidon.PoseidonMixed, (2,)),     # circomlib 0.5.x shape: `ark` is a mixed component array

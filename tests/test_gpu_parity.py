@@ -77,6 +77,8 @@ CASES = {
     "isequal": [[5, 5], [5, 6]],
     "lessthan8": [[3, 200], [200, 3], [7, 7]],
     "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
+    "dynindex": [[5, 10, 21, 32, 43, 54, 65, 76, 87], [0] + [0] * 8, [7] + [3] * 8, [9, 1, 2, 3, 4, 5, 6, 7, 8],
+                 [1 << 40] + [1] * 8, [M.Q - 1] + [1] * 8, [3] + [M.Q - 1] * 8],          # data-dependent array indices, ST_TOINT
     "mixedarr": [list(range(1, 10)) + list(range(11, 20)) + [3, 5, 7], [M.Q - 1] * 21, [0] * 21],   # mapped accesses (io-map)
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
     "poseidon2": [[1, 2], [0, 0], [M.Q - 1, 12345678901234567890]],

@@ -50,6 +50,7 @@ CASES = {
     "iszero": [[0], [7]],
     "lessthan8": [[3, 200], [200, 3]],
     "sum3cmp": [[1, 0, 1, 1]],
+    "dynindex": [[5, 10, 21, 32, 43, 54, 65, 76, 87], [0] + [0] * 8, [7] + [3] * 8, [2, 1, 2, 3, 4, 5, 6, 7, 8]],
     "mixedarr": [list(range(1, 10)) + list(range(11, 20)) + [3, 5, 7], [M.Q - 1] * 21],
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [1 << 200, (1 << 253) + 5, 254]],
     "poseidon2": [[1, 2], [M.Q - 1, 12345678901234567890]],

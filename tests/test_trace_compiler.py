@@ -21,6 +21,10 @@ CASES = {
     "isequal": [[5, 5], [5, 6]],
     "lessthan8": [[3, 200], [200, 3], [7, 7]],
     "sum3cmp": [[1, 0, 1, 1], [0, 0, 0, 0]],
+    # data-dependent array indices (Fr_toInt of a witness value): in range, out of range (reads / writes nothing that exists),
+    # and values that do not fit an int (the reference asserts: ST_TOINT)
+    "dynindex": [[5, 10, 21, 32, 43, 54, 65, 76, 87], [0] + [0] * 8, [7] + [3] * 8, [9, 1, 2, 3, 4, 5, 6, 7, 8],
+                 [1 << 40] + [1] * 8, [M.Q - 1] + [1] * 8, [3] + [M.Q - 1] * 8],
     # a MIXED component array: every access to its components is a "mapped" location through the io-map
     "mixedarr": [list(range(1, 10)) + list(range(11, 20)) + [3, 5, 7], [M.Q - 1] * 21, [0] * 21],
     "opszoo": [[12345, 678, 3], [M.Q - 5, 17, 250], [0, 0, 0], [1 << 200, (1 << 253) + 5, 254]],
@@ -51,6 +55,8 @@ def test_tape_matches_oracle(cvmlib, name, slots):
     cases = list(CASES[name])
     if name not in ("num2bits8", "sum3cmp", "lessthan8", "countdown"):
         cases += [[rng.randrange(M.Q) for _ in range(art.n_inputs)] for _ in range(3)]
+    if name == "dynindex":
+        cases += [[rng.randrange(8)] + [rng.randrange(M.Q) for _ in range(8)] for _ in range(6)]
     for inp in cases:
         w, st = oracle(prog, inp)
         rows, status = run_tape(tape, consts, wc.layout(), inp)
@@ -102,11 +108,22 @@ def test_unsupported_programs_are_rejected_with_a_reason(cvmlib):
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text=text)
     assert e.value.code == -3 and "data-dependent" in str(e.value)
-    # data-dependent address
-    text = head + "x_0 = get_signal i64.1\nx_1 = ff.wrap_i64 x_0\nx_2 = get_signal x_1\nset_signal i64.0 x_2\n"
+    # a signal STORE through a data-dependent address (loads and variable stores are traced: fixture `dynindex`)
+    head1 = "%%prime " + q + "\n%%signals 4\n%%start T_0\n%%witness 0 1 2 3\n%%template T_0 [ ff 1 2 ] [ ff 0 ] [3] [0]\n"
+    text = head1 + "x_0 = get_signal i64.1\nx_1 = ff.wrap_i64 x_0\nset_signal x_1 x_0\n"
     with pytest.raises(E.CvmGpuError) as e:
         E.WitnessCalculator(cvm_text=text)
-    assert e.value.code == -3
+    assert e.value.code == -3 and "data-dependent" in str(e.value)
+    # the load form of the same program is accepted: out = in[in[0]] read through a computed index
+    text = head1 + "x_0 = get_signal i64.1\nx_1 = ff.wrap_i64 x_0\nx_2 = get_signal x_1\nset_signal i64.0 x_2\n"
+    wc = E.WitnessCalculator(cvm_text=text)
+    tape, consts = wc.tape()
+    for inp, out in (([1, 77], 1), ([2, 77], 77), ([0, 5], 0), ([3, 5], 0)):
+        rows, status = run_tape(tape, consts, wc.layout(), inp)
+        # (index 0 names the output itself, still unset: 0; index 3 is outside the component: nothing)
+        assert status == 0 and rows[1] == out, (inp, rows)
+    rows, status = run_tape(tape, consts, wc.layout(), [1 << 35, 1])
+    assert status == 2          # CVMGPU_ST_TOINT: the reference's Fr_toInt asserts
 
 
 def test_data_dependent_while_is_unrolled_under_predicates(cvmlib):

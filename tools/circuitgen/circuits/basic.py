@@ -297,3 +297,23 @@ def MixedArr(T):
     with T.for_(i, 0, i < 3):
         T.bind(out[i], c[i].pin("total"))
         T.bind(last[i], c[i].pin("partial")[i + 1] + c[2].pin("partial")[0])
+
+
+def DynIndex(T):
+    """Data-dependent array indices in `<--` code (Fr_toInt of a signal-dependent value as an address): a table lookup in a
+    var array, a histogram (var[index] += ...), a signal array read at a computed index.  `sel` values outside 0..7 read /
+    write nothing that exists; values that do not fit an int make the reference abort (ST_TOINT)."""
+    sel = T.input("sel")
+    x = T.input("x", (8,))
+    out = T.output("out")
+    picked = T.output("picked")
+    hist_out = T.output("hist", (4,))
+    table = T.var("table", (8,), init=[3, 1, 4, 1, 5, 9, 2, 6])
+    hist = T.var("h", (4,), init=[0, 0, 0, 0])
+    i = T.var("i")
+    T.assign(out, table[sel] * 10 + table[(sel + 1) & 7])
+    T.assign(picked, x[sel & 7] + x[(sel * 3 + 1) & 7])
+    with T.for_(i, 0, i < 8):
+        T.set(hist[x[i] & 3], hist[x[i] & 3] + 1)
+    with T.for_(i, 0, i < 4):
+        T.assign(hist_out[i], hist[i])

@@ -243,7 +243,9 @@ class _Executor:
         inst.n_slots = slot
 
     # ---- expressions
-    def index(self, dims, idx):
+    def index(self, dims, idx, dynamic_ok=False):
+        """-> (flat offset, element count); with dynamic_ok an index that depends on signals gives (None, count): legal in
+        `<--` code and in var computations, whose values the constraint system does not see"""
         assert len(idx) <= len(dims)
         flat = 0
         for k, d in enumerate(dims):
@@ -251,6 +253,8 @@ class _Executor:
             if k < len(idx):
                 i = self.ev(idx[k])
                 if not isinstance(i, int):
+                    if dynamic_ok:
+                        return None, prod(dims[len(idx):])
                     raise CircuitError("array index is not a compile-time constant")
                 if i >= d:
                     raise CircuitError("index %d out of range %d" % (i, d))
@@ -277,9 +281,11 @@ class _Executor:
             return e.v
         if isinstance(e, Ref):
             if e.sym.kind == "var":
-                flat, n = self.index(e.sym.dims, e.idx)
+                flat, n = self.index(e.sym.dims, e.idx, dynamic_ok=True)
                 assert n == 1, "array-valued var used as a scalar"
-                return self.env[e.sym][flat]
+                return UNK if flat is None else self.env[e.sym][flat]
+            if e.sym.kind == "sig" and self.index(e.sym.dims, e.idx, dynamic_ok=True)[0] is None:
+                return UNK          # signal array read at a data-dependent index (only meaningful on the right of `<--`)
             keys = self.sigkey(e)
             assert len(keys) == 1, "array-valued signal used as a scalar"
             return Lin({keys[0]: 1}, 0)
@@ -325,8 +331,11 @@ class _Executor:
 
     def stmt(self, st):
         if isinstance(st, Set):
-            flat, n = self.index(st.dst.sym.dims, st.dst.idx)
-            if n == 1:
+            flat, n = self.index(st.dst.sym.dims, st.dst.idx, dynamic_ok=True)
+            if flat is None:            # var[data-dependent index] = ...: any element may have changed
+                self.ev(st.src)
+                self.env[st.dst.sym] = [UNK] * len(self.env[st.dst.sym])
+            elif n == 1:
                 val = self.ev(st.src)
                 self.env[st.dst.sym][flat] = UNK if self.shadow else val
             else:   # array-valued assignment (function result or array copy): contents unknown to constraints
