@@ -4,7 +4,7 @@
                               [--cpp <circuit.cpp>]
 
 reads `<circuit>.dat` next to the program (as the reference reads `<argv0>.dat`) - or, with --sym or when there is no
-.dat, the `circom --sym` symbol file - to resolve the input names, takes the same input.json and
+.dat, the `circom --sym` symbol file, or the program's own `;;%%main_input` lines - to resolve the input names, takes the same input.json and
 writes the same bytes to output.wtns -- computed on the GPU.  input.json may also be an array of input objects:
 the batch goes through one kernel launch and `<output>` gets one file per witness (`out.wtns`, `out.1.wtns`, ...).
 Exit code 1 with the reference's message on a failing assert (the reference aborts).
@@ -30,7 +30,7 @@ def main(argv):
               file=sys.stderr)
         return 1
     from . import engine as E
-    from .inputs import InputError, InputMap, SymInputMap, rows_from_json_text
+    from .inputs import InputError, InputMap, NamedInputMap, SymInputMap, rows_from_json_text
     cvm, jin, wout = args
     r1cs_path = opts.get("--r1cs")
     # the generated C++ of the same compile (component creation for an unpatched emitter; section sizes of the .dat) and
@@ -41,7 +41,12 @@ def main(argv):
     wc = E.WitnessCalculator(cvm_path=cvm, cpp_path=cpp, dat_path=dat)
     try:
         sym_path = opts.get("--sym") or (stem + ".sym" if not os.path.exists(stem + ".dat") and os.path.exists(stem + ".sym") else None)
-        imap = SymInputMap.from_files(sym_path, wc) if sym_path else InputMap.from_files(stem + ".dat", wc)
+        if sym_path:
+            imap = SymInputMap.from_files(sym_path, wc)
+        elif os.path.exists(stem + ".dat"):
+            imap = InputMap.from_files(stem + ".dat", wc)
+        else:                               # the program text itself (;;%%main_input lines)
+            imap = NamedInputMap.from_program(wc)
         with open(jin) as f:
             rows = rows_from_json_text(imap, f.read())
     except InputError as e:

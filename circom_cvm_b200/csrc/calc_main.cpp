@@ -284,6 +284,22 @@ InputMap load_map(const std::string &dat_path, const uint64_t *witness, uint32_t
 // The same table built from a `circom --sym` file (one "#s,#w,#c,name" line per signal,
 // constraint_writers/src/sym_writer.rs:4-14): the main component's input signals grouped by name without their trailing
 // indices ("main.in[3]" -> key "in", as loadJson addresses them), first signal and element count per key.
+InputMap map_from_groups(const std::map<std::string, std::pair<uint64_t, uint64_t>> &groups, uint64_t input_start, uint64_t n_inputs) {
+    InputMap m;
+    m.input_start = input_start;
+    m.n_inputs = n_inputs;
+    size_t size = 256;
+    while (size < 2 * groups.size()) size *= 2;
+    m.table.assign(size, HashEntry{0, 0, 0});
+    for (const auto &kv : groups) {
+        const uint64_t h = fnv1a(kv.first);
+        size_t pos = (size_t)(h % size);
+        while (m.table[pos].signalid != 0) pos = (pos + 1) % size;
+        m.table[pos] = HashEntry{h, kv.second.first, kv.second.second};
+    }
+    return m;
+}
+
 InputMap load_sym_map(const std::string &sym_path, uint64_t input_start, uint64_t n_inputs) {
     std::ifstream f(sym_path);
     if (!f) throw Fail("cannot open " + sym_path);
@@ -309,19 +325,25 @@ InputMap load_sym_map(const std::string &sym_path, uint64_t input_start, uint64_
         total++;
     }
     if (total != n_inputs) throw Fail("the .sym file does not belong to this program (main inputs not found)");
-    InputMap m;
-    m.input_start = input_start;
-    m.n_inputs = n_inputs;
-    size_t size = 256;
-    while (size < 2 * groups.size()) size *= 2;
-    m.table.assign(size, HashEntry{0, 0, 0});
-    for (const auto &kv : groups) {
-        const uint64_t h = fnv1a(kv.first);
-        size_t pos = (size_t)(h % size);
-        while (m.table[pos].signalid != 0) pos = (pos + 1) % size;
-        m.table[pos] = HashEntry{h, kv.second.first, kv.second.second};
+    return map_from_groups(groups, input_start, n_inputs);
+}
+
+// the program's own `;;%%main_input <name> <first signal> <size>` lines (cvmgpu_program_main_inputs)
+InputMap load_named_map(const cvmgpu_program *prog, uint64_t input_start, uint64_t n_inputs) {
+    const char *text = nullptr;
+    size_t len = 0;
+    cvmgpu_program_main_inputs(prog, &text, &len);
+    std::map<std::string, std::pair<uint64_t, uint64_t>> groups;
+    std::istringstream ss(std::string(text ? text : "", len));
+    std::string name;
+    uint64_t start, size, total = 0;
+    while (ss >> name >> start >> size) {
+        groups[name] = std::make_pair(start, size);
+        total += size;
     }
-    return m;
+    if (groups.empty() || total != n_inputs)
+        throw Fail("no <circuit>.dat next to the program, no --sym file, and the program text does not name its main inputs");
+    return map_from_groups(groups, input_start, n_inputs);
 }
 
 void row_from_json(const InputMap &m, const JVal &doc, uint8_t *row) {   // loadJson + setInputSignal
@@ -404,8 +426,9 @@ int main(int argc, char *argv[]) {
         const uint64_t *witness = nullptr;
         uint32_t n_wit = 0;
         cvmgpu_program_witness(prog, &witness, &n_wit);
-        InputMap m = sym_path.empty() ? load_map(strip_ext(pos[0]) + ".dat", witness, n_wit, 1 + info.n_outputs, info.n_inputs)
-                                      : load_sym_map(sym_path, 1 + info.n_outputs, info.n_inputs);
+        InputMap m = !sym_path.empty()                  ? load_sym_map(sym_path, 1 + info.n_outputs, info.n_inputs)
+                     : std::ifstream(dat_path).good() ? load_map(dat_path, witness, n_wit, 1 + info.n_outputs, info.n_inputs)
+                                                      : load_named_map(prog, 1 + info.n_outputs, info.n_inputs);
         std::string text = slurp(pos[1]);
         JParser jp(text);
         JVal doc = jp.value();

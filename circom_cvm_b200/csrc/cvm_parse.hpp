@@ -107,7 +107,13 @@ struct IoDef {
     int64_t bus_id = 0;
 };
 
+struct MainInput {
+    std::string name;        // as loadJson addresses it (qualified for buses), without indices
+    int64_t start = 0, size = 0;   // first signal, number of elements
+};
+
 struct Program {
+    std::vector<MainInput> main_inputs;   // ;;%%main_input lines (the name table the .dat carries, c_code_generator.rs:511-539)
     std::unordered_map<int64_t, std::vector<IoDef>> io_map;   // template-instance id -> defs indexed by signal code
     std::vector<Code> codes;
     std::unordered_map<std::string, int> code_index;
@@ -197,6 +203,16 @@ class Parser {
             }
             if (line.rfind(";;%%io_map", 0) == 0) {
                 parse_io_map(line, lineno);
+                continue;
+            }
+            if (line.rfind(";;%%main_input", 0) == 0) {   // ;;%%main_input <name> <first signal> <size>
+                auto t = split_ws(line);
+                if (t.size() != 4) throw ParseError("malformed main_input at line " + std::to_string(lineno));
+                MainInput mi;
+                mi.name = t[1];
+                mi.start = atoll(t[2].c_str());
+                mi.size = atoll(t[3].c_str());
+                prog.main_inputs.push_back(mi);
                 continue;
             }
             if (line.rfind(";;", 0) == 0 || line.rfind("//", 0) == 0) continue;

@@ -69,6 +69,7 @@ struct cvmgpu_program {
     tape::BatchInvStats binv;
     std::vector<fr::Fr> consts_mont;
     std::vector<uint64_t> witness;   // %%witness: signal index of every witness wire
+    std::string main_inputs;         // ;;%%main_input lines of the program: "name first_signal size\n" each
     std::vector<uint8_t> wire_bool;  // per witness wire: the value is proven 0/1 by the trace compiler's typing
     uint64_t n_signals = 0;
     uint32_t n_inputs = 0, n_outputs = 0;
@@ -240,6 +241,8 @@ static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume
         if (!p->wire_bool.empty()) p->wire_bool[0] = 1;   // the constant 1 (kept as a field row, plus a bit row of ones)
         p->n_signals = (uint64_t)parser.prog.n_signals;
         p->witness.assign(parser.prog.witness.begin(), parser.prog.witness.end());
+        for (const cvm::MainInput &mi : parser.prog.main_inputs)
+            p->main_inputs += mi.name + " " + std::to_string(mi.start) + " " + std::to_string(mi.size) + "\n";
         p->n_inputs = (uint32_t)tr.n_inputs;
         p->n_outputs = (uint32_t)tr.n_outputs;
         p->consts_mont.reserve(tr.consts.size());
@@ -479,6 +482,13 @@ extern "C" int cvmgpu_program_wire_rows(const cvmgpu_program *p, const uint32_t 
     if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
     if (wire_loc) *wire_loc = p->tape.wire_loc.data();
     if (n) *n = (uint32_t)p->tape.wire_loc.size();
+    return CVMGPU_OK;
+}
+
+extern "C" int cvmgpu_program_main_inputs(const cvmgpu_program *p, const char **text, size_t *len) {
+    if (!p || !text) return fail(CVMGPU_ERR_ARG, "null argument");
+    *text = p->main_inputs.c_str();
+    if (len) *len = p->main_inputs.size();
     return CVMGPU_OK;
 }
 

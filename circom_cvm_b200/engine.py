@@ -29,7 +29,7 @@ ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (cs
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_load_files", "cvmgpu_program_load_text3", "cvmgpu_witness_batch_checked_dev", "cvmgpu_store_bytes_checked",
-    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_speculative", "cvmgpu_program_info_get", "cvmgpu_program_free",
+    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_speculative", "cvmgpu_program_main_inputs", "cvmgpu_program_info_get", "cvmgpu_program_free",
     "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_multi", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
@@ -114,6 +114,7 @@ def lib():
     L.cvmgpu_store_bytes_checked.argtypes = [c_void_p, c_void_p, c_uint64]
     L.cvmgpu_store_bytes_checked.restype = c_size_t
     L.cvmgpu_witness_batch_checked_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_program_main_inputs.argtypes = [c_void_p, POINTER(c_char_p), POINTER(c_size_t)]
     L.cvmgpu_program_speculative.argtypes = [c_void_p, POINTER(c_void_p)]
     L.cvmgpu_program_fused_info_get.argtypes = [c_void_p, c_void_p, POINTER(ProgramInfo)]
     L.cvmgpu_program_fused_tape.argtypes = [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint32)]
@@ -341,6 +342,16 @@ class WitnessCalculator:
     def write_wtns(self, path, witness_row):
         row = np.ascontiguousarray(witness_row, dtype=np.uint8)
         _check(lib().cvmgpu_wtns_write(os.fsencode(path), _ptr(row), self.n_wires))
+
+    def main_inputs(self):
+        """[(name, first signal, size)] from the program's `;;%%main_input` lines ([] when it has none)"""
+        text, n = c_char_p(), c_size_t()
+        _check(lib().cvmgpu_program_main_inputs(self._h, byref(text), byref(n)))
+        out = []
+        for line in (text.value or b"").decode().splitlines():
+            name, start, size = line.rsplit(" ", 2)
+            out.append((name, int(start), int(size)))
+        return out
 
     def witness_signals(self):
         """the %%witness list: signal index of every witness wire"""

@@ -92,6 +92,22 @@ class SymInputMap(InputMap):
         return self._pos[h]
 
 
+class NamedInputMap(SymInputMap):
+    """The same lookup from the program's own `;;%%main_input <name> <first signal> <size>` lines (a compiler that carries
+    patches/main_input_directive.rs.diff): neither the .dat nor the .sym is needed."""
+
+    def __init__(self, main_inputs, input_start: int, n_inputs: int):
+        self.input_start, self.n_inputs = input_start, n_inputs
+        if not main_inputs or sum(sz for _n, _s, sz in main_inputs) != n_inputs:
+            raise InputError("the program text does not name its main inputs")
+        self.table = [(fnv1a(name), start, size) for name, start, size in main_inputs]
+        self._pos = {h: i for i, (h, _f, _c) in enumerate(self.table)}
+
+    @classmethod
+    def from_program(cls, wc):
+        return cls(wc.main_inputs(), 1 + wc.n_outputs, wc.n_inputs)
+
+
 Q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 
 

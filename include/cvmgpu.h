@@ -164,6 +164,10 @@ int cvmgpu_program_iconsts(const cvmgpu_program *p, const uint64_t **iconsts, ui
 /* The program's %%witness list: signal index of every witness wire (= the witness2SignalList of the .dat,
  * c_code_generator.rs:541-550; used to locate the input hash map of a .dat, circom_cvm_b200/inputs.py). */
 int cvmgpu_program_witness(const cvmgpu_program *p, const uint64_t **signals, uint32_t *n);
+/* The main component's input names, when the program text carries them: `;;%%main_input <name> <first signal> <size>` comment
+ * lines (patches/main_input_directive.rs.diff; the fork's .cvm has no name table, the .dat hash map and the .sym file do).
+ * text: one "name first_signal size" line per input, empty when there are none. */
+int cvmgpu_program_main_inputs(const cvmgpu_program *p, const char **text, size_t *len);
 /* Per witness wire: 1 when the trace compiler's value-range typing proves the wire 0/1 for every input (comparison
  * results, extracted bits, boolean combinations of those, constants 0 and 1).  Such wires are stored as bit rows. */
 int cvmgpu_program_wire_types(const cvmgpu_program *p, const uint8_t **is_bool, uint32_t *n);

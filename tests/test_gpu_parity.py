@@ -382,6 +382,15 @@ def test_process_abi_drop_in(E, name, doc, tmp_path):
     nout = tmp_path / "native.wtns"
     subprocess.run([cbuild.CALC, paths["cvm"], str(jin), str(nout)], check=True, timeout=300)
     assert nout.read_bytes() == out.read_bytes()
+    # the program text alone (its ;;%%create_cmp / ;;%%main_input lines): no .dat, no .cpp, no .sym next to it
+    lone = tmp_path / "lone"
+    lone.mkdir()
+    with open(paths["cvm"]) as fsrc:
+        (lone / "c.cvm").write_text(fsrc.read())
+    subprocess.run([sys.executable, "-m", "circom_cvm_b200", str(lone / "c.cvm"), str(jin), str(lone / "py.wtns")], check=True,
+                   env=env, cwd=ROOT, timeout=300)
+    subprocess.run([cbuild.CALC, str(lone / "c.cvm"), str(jin), str(lone / "native.wtns")], check=True, timeout=300)
+    assert (lone / "py.wtns").read_bytes() == out.read_bytes() == (lone / "native.wtns").read_bytes()
     ref = os.path.join(ROOT, "oracle", "_ref", name)
     if os.path.exists(ref):
         rout = tmp_path / "ref.wtns"

@@ -179,3 +179,28 @@ def test_native_calculator_reads_sym(cvmlib, tmp_path):
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
     else:
         assert r.returncode == 0, r.stderr
+
+
+def test_input_names_from_the_program_text(cvmlib):
+    """`;;%%main_input <name> <first signal> <size>` lines (patches/main_input_directive.rs.diff): the same rows as the .dat
+    hash map gives, with neither the .dat nor the .sym; a program without them says so."""
+    from circom_cvm_b200 import engine as E
+    from circom_cvm_b200 import formats
+    from circom_cvm_b200.inputs import InputError, InputMap, NamedInputMap, row_from_json
+    from conftest import circuit
+    from tools.circuitgen.build import faithful_cvm
+    from tools.circuitgen.emit_cpp import emit_cpp
+    art = circuit("mixedarr")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    assert wc.main_inputs() == art.main_inputs
+    doc = {"a": [str(v) for v in range(1, 10)], "b": list(range(11, 20)), "w": ["0x3", "5", "7"]}
+    consts = sorted(art.compiled.constants, key=art.compiled.constants.get)
+    dat = formats.dat_bytes(art.main_inputs, art.witness, consts, io_map=art.compiled.io_map)
+    want = row_from_json(InputMap(dat, art.witness, art.input_start, art.n_inputs), doc)
+    assert row_from_json(NamedInputMap.from_program(wc), doc) == want == list(range(1, 10)) + list(range(11, 20)) + [3, 5, 7]
+    with pytest.raises(InputError):
+        row_from_json(NamedInputMap.from_program(wc), {"a": [1] * 9, "b": [1] * 9})
+    bare = E.WitnessCalculator(cvm_text=faithful_cvm(art), cpp_text=emit_cpp(art), dat_bytes=dat)
+    assert bare.main_inputs() == []
+    with pytest.raises(InputError):
+        NamedInputMap.from_program(bare)

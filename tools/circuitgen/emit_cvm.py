@@ -16,6 +16,7 @@ generated .cpp (cvmgpu_program_load_with_cpp).  The default mode keeps the depar
   * array equality (`===` on arrays) is emitted as a counted loop over address registers, see array_eq().
   * the io-map that "mapped" accesses (mixed component arrays) read is not in the fork's .cvm at all (circuit.rs:577-621);
     we emit one `;;%%io_map <template id> <n> {offset len lengths[1..] size busId}*` line per template instance.
+  * the main component's input names are only in the .dat / .sym; we emit `;;%%main_input <name> <first signal> <size>`.
   * multi-element `return` passes the *address* register as documented in
     mkdocs/docs/circom-language/formats/circom-virtual-machine.md:201-203 (the emitter at
     return_bucket.rs:131 loads the first element instead, which cannot work).
@@ -411,6 +412,10 @@ class CvmEmitter:
         o += [";; Main template", "%%%%start %s" % main.header, "\n"]
         o += [";; Component creation mode (implicit/explicit)", "%%components explicit", "\n"]
         o += [";; Witness (signal list)", "%%witness" + "".join(" %d" % s for s in c.witness), "\n"]
+        if not self.faithful:       # extension (a comment to other consumers): the main-input name table of the .dat
+            for sg in main.tmpl.signals:
+                if sg.xtype == "in":
+                    o.append(";;%%%%main_input %s %d %d" % (sg.name, 1 + sg.offset, sg.size))
         if not self.faithful:       # extension (a comment to other consumers): the .dat io-map records as text
             for tid, defs in sorted(getattr(c, "io_map", {}).items()):
                 rec = "".join(" %d %d%s %d 0" % (off, max(len(dims) - 1, 0), "".join(" %d" % d for d in dims[1:]), size)
