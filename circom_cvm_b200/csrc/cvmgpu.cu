@@ -76,7 +76,7 @@ struct cvmgpu_program {
     uint64_t layout_id = 0;          // identifies this program's value-store layout (r1cs bindings are cached against it)
     // device copies of the tables, one set per device the program has run on (uploaded on first use there)
     struct Dev {
-        DevBuf d_tape, d_consts, d_wire_loc, d_iconsts;
+        DevBuf d_tape, d_consts, d_wire_loc, d_iconsts, d_flist, d_blist;
         bool ready = false;
     };
     std::map<int, Dev> dev;
@@ -510,7 +510,10 @@ static void on_device(int device, F &&fn) {
 
 static void release_program_tables(cvmgpu_program *p) {
     for (auto &kv : p->dev)
-        on_device(kv.first, [&] { kv.second.d_tape.release(); kv.second.d_consts.release(); kv.second.d_wire_loc.release(); kv.second.d_iconsts.release(); });
+        on_device(kv.first, [&] {
+            kv.second.d_tape.release(); kv.second.d_consts.release(); kv.second.d_wire_loc.release(); kv.second.d_iconsts.release();
+            kv.second.d_flist.release(); kv.second.d_blist.release();
+        });
     for (auto &kv : p->fused)
         if (kv.second) release_program_tables(kv.second.get());
     if (p->spec) release_program_tables(p->spec.get());
@@ -662,7 +665,7 @@ static int launch_tape(const kern::TapeParams &tp, unsigned grid, size_t smem, c
 }
 
 static int run_tape(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store, void *d_status,
-                    void *d_first_bad, void *stream);
+                    void *d_first_bad, void *stream, uint32_t in_row_bytes = 0);
 
 extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride,
                                         void *d_store, void *d_status, void *stream) {
@@ -670,7 +673,7 @@ extern "C" int cvmgpu_witness_batch_dev(cvmgpu_program *p, const void *d_inputs,
 }
 
 static int run_tape(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_t bstride, void *d_store, void *d_status,
-                    void *d_first_bad, void *stream) {
+                    void *d_first_bad, void *stream, uint32_t in_row_bytes) {
     if (!p || !d_store || (!d_inputs && p->n_inputs)) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
     if (bstride < B) return fail(CVMGPU_ERR_ARG, "bstride < B");
@@ -691,6 +694,7 @@ static int run_tape(cvmgpu_program *p, const void *d_inputs, uint64_t B, uint64_
     tp.n_inputs = p->n_inputs;
     tp.status = (uint32_t *)d_status;
     tp.first_bad = (uint32_t *)d_first_bad;
+    tp.in_row_bytes = in_row_bytes;
     tp.B = B;
     // CTA size: 128 witnesses for large batches; smaller CTAs when the batch would leave SMs with an uneven number of
     // CTAs (a 64 K batch is 512 CTAs of 128 for 148 SMs: 3.46 per SM)
@@ -784,6 +788,70 @@ extern "C" int cvmgpu_witness_export_dev(cvmgpu_program *p, const void *d_store,
     return cvmgpu_witness_export_range_dev(p, d_store, B, bstride, 0, p->tape.n_wires, d_wtns, stream);
 }
 
+// ---- packed rows: [field wires x 32 B][0/1 wires as bits], the witness in the types the program proved
+static void packed_lists(const cvmgpu_program *p, std::vector<uint32_t> &fl, std::vector<uint32_t> &bl) {
+    for (uint32_t loc : p->tape.wire_loc) {
+        if (loc & tape::ROW_BIT) bl.push_back(loc & ~tape::ROW_BIT);
+        else fl.push_back(loc);
+    }
+}
+static size_t packed_row_bytes(const cvmgpu_program *p) {
+    size_t nf = 0, nb = 0;
+    for (uint32_t loc : p->tape.wire_loc) ((loc & tape::ROW_BIT) ? nb : nf)++;
+    return nf * 32 + ((nb + 127) / 128) * 16;   // rows stay 16-byte aligned
+}
+
+extern "C" int cvmgpu_witness_export_packed_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_out,
+                                                void *stream) {
+    if (!p || !d_store || !d_out) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (B == 0) return CVMGPU_OK;
+    cvmgpu_program::Dev *pd = nullptr;
+    if (int rc = upload_program(p, &pd)) return rc;
+    std::vector<uint32_t> fl, bl;
+    packed_lists(p, fl, bl);
+    {
+        std::lock_guard<std::mutex> lock(p->mu);
+        if (!pd->d_flist.p) {
+            if (int rc = pd->d_flist.ensure(std::max<size_t>(4, fl.size() * 4))) return rc;
+            if (int rc = pd->d_blist.ensure(std::max<size_t>(4, bl.size() * 4))) return rc;
+            if (!fl.empty()) CUDA_TRY(cudaMemcpy(pd->d_flist.p, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice));
+            if (!bl.empty()) CUDA_TRY(cudaMemcpy(pd->d_blist.p, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaDeviceSynchronize());
+        }
+    }
+    kern::PackedView pv;
+    pv.sv = store_view(p, pd, d_store, bstride);
+    pv.flist = (const uint32_t *)pd->d_flist.p;
+    pv.blist = (const uint32_t *)pd->d_blist.p;
+    pv.n_f = (uint32_t)fl.size();
+    pv.n_b = (uint32_t)bl.size();
+    pv.n_ftiles = (pv.n_f + 7) / 8;
+    pv.row_bytes = packed_row_bytes(p);
+    const uint32_t n_btiles = (pv.n_b + 31) / 32;
+    if (pv.n_ftiles + n_btiles == 0) return CVMGPU_OK;
+    if (pv.n_ftiles + n_btiles > 65535) return fail(CVMGPU_ERR_UNSUPPORTED, "witness too wide for the packed export");
+    dim3 grid((unsigned)((B + 255) / 256), pv.n_ftiles + n_btiles);
+    kern::export_packed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pv, B, (unsigned char *)d_out);
+    CUDA_TRY(cudaGetLastError());
+    return CVMGPU_OK;
+}
+
+// row layout of the packed export of `p` (or of its bit-input tape): n_field wires x 32 bytes, then n_bits wires as bits;
+// cvmgpu_program_wire_rows of the same handle says which wire is which (ROW_BIT = a 0/1 wire), both in wire order
+extern "C" int cvmgpu_packed_layout(cvmgpu_program *p, int bit_input_tape, uint64_t *row_bytes, uint32_t *n_field, uint32_t *n_bits,
+                                    const uint32_t **wire_rows) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (bit_input_tape && !p->spec) return fail(CVMGPU_ERR_UNSUPPORTED, "this program has no bit-input tape (its inputs are field elements)");
+    cvmgpu_program *q = bit_input_tape ? p->spec.get() : p;
+    uint32_t nf = 0, nb = 0;
+    for (uint32_t loc : q->tape.wire_loc) ((loc & tape::ROW_BIT) ? nb : nf)++;
+    if (row_bytes) *row_bytes = packed_row_bytes(q);
+    if (n_field) *n_field = nf;
+    if (n_bits) *n_bits = nb;
+    if (wire_rows) *wire_rows = q->tape.wire_loc.data();
+    return CVMGPU_OK;
+}
+
 static int upload_r1cs(cvmgpu_r1cs *r, cvmgpu_r1cs::Dev **out);
 
 // largest chunk of witnesses whose buffers fit in the free device memory
@@ -828,7 +896,31 @@ static void release_pipe_buffers() {
 extern "C" void cvmgpu_release_buffers(void) { release_pipe_buffers(); }
 
 static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t wire0, uint32_t n_sel,
-                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
+                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad, uint32_t in_row_bytes = 0, bool packed = false);
+
+// The whole witness in the types the program proved (cvmgpu_packed_layout): field wires as 32-byte values, 0/1 wires as
+// bits.  For a hash circuit that is what there is to say about a witness -- Sha256(512): 8.6 KB instead of 2.2 MB -- and
+// what a device-to-host link can carry at the rate the kernels produce it.  inputs_are_bits: the inputs are packed bits
+// (cvmgpu_witness_batch_bits) and the row layout is that of the bit-input tape; else 32-byte field elements and the
+// layout of the program itself (computed by the general tape: a fixed layout cannot depend on what the inputs turn out to be).
+extern "C" int cvmgpu_witness_batch_packed(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, int inputs_are_bits, uint64_t B,
+                                           uint8_t *packed_out, uint32_t *status, uint32_t *first_bad) {
+    if (!p || !packed_out) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (inputs_are_bits && !p->spec) return fail(CVMGPU_ERR_UNSUPPORTED, "this program has no bit-input tape (its inputs are field elements)");
+    cvmgpu_program *q = inputs_are_bits ? p->spec.get() : p;
+    return batch_select_impl(q, r, inputs, B, 0, q->tape.n_wires, packed_out, status, first_bad,
+                             inputs_are_bits ? (p->n_inputs + 7) / 8 : 0, true);
+}
+
+// Inputs as PACKED BITS (row = ceil(n_inputs / 8) bytes per witness, input k = bit k & 7 of byte k >> 3): for programs whose
+// inputs are bits -- those that have a bit-input tape (cvmgpu_program_speculative) -- 256 times less to upload than one
+// 32-byte field element per bit, and nothing to speculate about.  Same outputs as cvmgpu_witness_batch_select.
+extern "C" int cvmgpu_witness_batch_bits(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *input_bits, uint64_t B, uint32_t wire0,
+                                         uint32_t n_sel, uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
+    if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
+    if (!p->spec) return fail(CVMGPU_ERR_UNSUPPORTED, "this program has no bit-input tape (its inputs are field elements)");
+    return batch_select_impl(p->spec.get(), r, input_bits, B, wire0, n_sel, wtns_out, status, first_bad, (p->n_inputs + 7) / 8);
+}
 
 extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B,
                                            uint32_t wire0, uint32_t n_sel, uint8_t *wtns_out, uint32_t *status,
@@ -867,7 +959,7 @@ extern "C" int cvmgpu_witness_batch_select(cvmgpu_program *p, cvmgpu_r1cs *r, co
 }
 
 static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, uint64_t B, uint32_t wire0, uint32_t n_sel,
-                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad) {
+                             uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad, uint32_t in_row_bytes, bool packed) {
     if (!p) return fail(CVMGPU_ERR_ARG, "null argument");
     if (B == 0) return CVMGPU_OK;
     if (!inputs && p->n_inputs) return fail(CVMGPU_ERR_ARG, "null argument");
@@ -886,7 +978,8 @@ static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *i
         if (r && !fused)
             if (int rc = upload_r1cs(r, &rd)) return rc;
     }
-    const size_t in_row = (size_t)p->n_inputs * 32, out_row = (size_t)n_sel * 32;
+    const size_t in_row = in_row_bytes ? (size_t)in_row_bytes : (size_t)p->n_inputs * 32;
+    const size_t out_row = packed ? packed_row_bytes(p) : (size_t)n_sel * 32;
     size_t per_w = (cvmgpu_store_bytes(p, 1024) + 1023) / 1024 + in_row + out_row + 8;
     uint64_t fit = pick_chunk(B, 2 * per_w);
     if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
@@ -927,13 +1020,14 @@ static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *i
         cudaError_t e = cudaSuccess;
         // the stream's previous chunk must have left its buffers (stream order guarantees it)
         if (in_row) e = cudaMemcpyAsync(pb.inputs.p, inputs + b0 * in_row, n * in_row, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) rc = run_tape(p, pb.inputs.p, n, cstride, pb.store.p, pb.status.p, fused ? pb.bad.p : nullptr, s);
+        if (e == cudaSuccess) rc = run_tape(p, pb.inputs.p, n, cstride, pb.store.p, pb.status.p, fused ? pb.bad.p : nullptr, s, in_row_bytes);
         if (e == cudaSuccess && rc == CVMGPU_OK && r) {
             if (!fused) rc = cvmgpu_r1cs_check_store_dev(r, p, pb.store.p, n, cstride, pb.bad.p, s);
             if (rc == CVMGPU_OK) e = cudaMemcpyAsync(first_bad + b0, pb.bad.p, n * 4, cudaMemcpyDeviceToHost, s);
         }
         if (e == cudaSuccess && rc == CVMGPU_OK && out_row) {
-            rc = cvmgpu_witness_export_range_dev(p, pb.store.p, n, cstride, wire0, n_sel, pb.wtns.p, s);
+            rc = packed ? cvmgpu_witness_export_packed_dev(p, pb.store.p, n, cstride, pb.wtns.p, s)
+                        : cvmgpu_witness_export_range_dev(p, pb.store.p, n, cstride, wire0, n_sel, pb.wtns.p, s);
             if (rc == CVMGPU_OK) e = cudaMemcpyAsync(wtns_out + b0 * out_row, pb.wtns.p, n * out_row, cudaMemcpyDeviceToHost, s);
         }
         if (e == cudaSuccess && rc == CVMGPU_OK && status) e = cudaMemcpyAsync(status + b0, pb.status.p, n * 4, cudaMemcpyDeviceToHost, s);

@@ -58,6 +58,8 @@ struct TapeParams {
     uint32_t ring_off;       // uint4 offset of the reload ring inside the dynamic shared memory (after the field slots)
     uint32_t bslot_off;      // uint4 offset of the bit-slot file (after the ring)
     uint32_t *first_bad;     // tapes with a fused R1CS check (T_RNE): first violated constraint per witness, else nullptr
+    uint32_t in_row_bytes;   // != 0: the inputs are PACKED BITS, in_row_bytes per witness, input k = bit k & 7 of byte k >> 3
+                             // (only tapes that read their inputs with T_INPUT_BIT)
 };
 
 __device__ __forceinline__ Fr mont_bool(bool b) { return b ? fr::one_mont() : fr::zero(); }
@@ -423,6 +425,12 @@ __global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParam
         case tape::T_INPUT_BIT: {
             // speculative typing: main input cur.y taken as a bit.  Anything but a literal 0 / 1 marks the witness for the
             // program traced without the assumption (the caller recomputes it there); sticky, nothing else overwrites it.
+            if (p.in_row_bytes) {   // packed-bit inputs: nothing to check
+                const unsigned char *row = reinterpret_cast<const unsigned char *>(p.inputs) + w * p.in_row_bytes;
+                rb = ((uint32_t)row[cur.y >> 3] >> (cur.y & 7u)) & 1u;
+                is_rb = true;
+                break;
+            }
             const uint4 *src = p.inputs + (w * p.n_inputs + cur.y) * 2;
             const uint4 lo = src[0], hi = src[1];
             if (lo.x > 1u || (lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) != 0u) status = tape::ST_SPECULATION;
@@ -592,6 +600,50 @@ __global__ void __launch_bounds__(256) export_kernel(StoreView sv, uint64_t B, u
             d[1] = make_uint4(tile[lane][k][4], tile[lane][k][5], tile[lane][k][6], tile[lane][k][7]);
         }
     }
+}
+
+// ---- typed value store -> PACKED rows: per witness [field wires x 32 B canonical, in wire order][0/1 wires, in wire order,
+// packed LSB-first into 32-bit words].  flist / blist: the field rows / bit rows of those wires in that order.
+// blockIdx.y < n_ftiles: field wires (thread = witness: coalesced reads of the row, one 32-byte segment written per witness);
+// the other blocks: one warp per 32 witnesses x 32 bit wires -- lane l fetches the word of bit row blist[t * 32 + l] (bit i =
+// witness i), 32 ballots transpose the 32 x 32 bit matrix, lane i ends up with the word of witness i.
+struct PackedView {
+    StoreView sv;
+    const uint32_t *flist, *blist;
+    uint32_t n_f, n_b, n_ftiles;
+    uint64_t row_bytes;
+};
+__global__ void __launch_bounds__(256) export_packed_kernel(PackedView pv, uint64_t B, unsigned char *out) {
+    const uint32_t lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (blockIdx.y < pv.n_ftiles) {
+        const uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+        if (w >= B) return;
+        for (uint32_t j = blockIdx.y * 8; j < pv.n_f && j < blockIdx.y * 8 + 8; j++) {
+            const uint32_t loc = __ldg(pv.flist + j);
+            const uint4 *src = pv.sv.store + ((uint64_t)loc * 2) * pv.sv.bstride + w;
+            const Fr v = fr::from_mont(unpack(src[0], src[pv.sv.bstride]));
+            uint4 lo, hi;
+            pack(v, lo, hi);
+            uint4 *d = reinterpret_cast<uint4 *>(out + w * pv.row_bytes + (uint64_t)j * 32);
+            d[0] = lo;
+            d[1] = hi;
+        }
+        return;
+    }
+    const uint64_t wg = (uint64_t)blockIdx.x * 8 + wrp;          // group of 32 witnesses
+    const uint32_t t = blockIdx.y - pv.n_ftiles;                 // tile of 32 bit wires
+    if (wg * 32 >= B) return;
+    const uint32_t e = t * 32 + lane;
+    uint32_t word = 0;
+    if (e < pv.n_b) word = __ldg(pv.sv.bits + wg * pv.sv.n_brows + __ldg(pv.blist + e));
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const uint32_t col = __ballot_sync(0xffffffffu, (word >> i) & 1u);   // bit l = wire e(l) of witness i
+        if (lane == (uint32_t)i) mine = col;
+    }
+    const uint64_t w = wg * 32 + lane;
+    if (w < B) *reinterpret_cast<uint32_t *>(out + w * pv.row_bytes + (uint64_t)pv.n_f * 32 + (uint64_t)t * 4) = mine;
 }
 
 // canonical AoS -> Montgomery SoA (used by the stand-alone R1CS check on externally produced witnesses)

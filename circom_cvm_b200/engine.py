@@ -29,7 +29,8 @@ ROW_BIT = 0x80000000       # cvmgpu_program_wire_rows: the wire is a bit row (cs
 EXPORTS = [
     "cvmgpu_last_error", "cvmgpu_device_count", "cvmgpu_set_device",
     "cvmgpu_program_load", "cvmgpu_program_load_text", "cvmgpu_program_load_with_cpp", "cvmgpu_program_load_text2", "cvmgpu_program_load_files", "cvmgpu_program_load_text3", "cvmgpu_witness_batch_checked_dev", "cvmgpu_store_bytes_checked",
-    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_speculative", "cvmgpu_program_main_inputs", "cvmgpu_program_info_get", "cvmgpu_program_free",
+    "cvmgpu_program_fused_info_get", "cvmgpu_program_fused_tape", "cvmgpu_set_fused_mode", "cvmgpu_program_speculative", "cvmgpu_program_main_inputs", "cvmgpu_witness_batch_bits", "cvmgpu_packed_layout", "cvmgpu_witness_batch_packed",
+    "cvmgpu_witness_export_packed_dev", "cvmgpu_program_info_get", "cvmgpu_program_free",
     "cvmgpu_program_tape", "cvmgpu_program_witness", "cvmgpu_program_wire_types", "cvmgpu_program_wire_rows", "cvmgpu_program_iconsts",
     "cvmgpu_witness_batch", "cvmgpu_witness_batch_checked", "cvmgpu_witness_batch_select", "cvmgpu_witness_batch_multi", "cvmgpu_witness_batch_dev",
     "cvmgpu_witness_export_dev", "cvmgpu_witness_export_range_dev", "cvmgpu_store_bytes", "cvmgpu_release_buffers",
@@ -99,6 +100,10 @@ def lib():
     L.cvmgpu_program_wire_rows.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_program_iconsts.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]
     L.cvmgpu_witness_batch_select.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_packed_layout.argtypes = [c_void_p, c_int, POINTER(c_uint64), POINTER(c_uint32), POINTER(c_uint32), POINTER(c_void_p)]
+    L.cvmgpu_witness_batch_packed.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_void_p, c_void_p]
+    L.cvmgpu_witness_export_packed_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]
+    L.cvmgpu_witness_batch_bits.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_batch_multi.argtypes = [c_void_p, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]
     L.cvmgpu_witness_export_range_dev.argtypes = [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p]
     L.cvmgpu_r1cs_bind_info.argtypes = [c_void_p, c_void_p, POINTER(R1csInfo)]
@@ -317,6 +322,46 @@ class WitnessCalculator:
         B = status_out.shape[0]
         _check(lib().cvmgpu_witness_batch_select(self._h, r1cs._h if r1cs is not None else None, _ptr(inputs), B, wire0, n_sel,
                                                  _ptr(wtns_out), _ptr(status_out), _ptr(first_bad_out)))
+
+    def calculate_bits_into(self, input_bits, wire0, n_sel, wtns_out, status_out, r1cs=None, first_bad_out=None):
+        """calculate_select_into with the inputs as packed bits: uint8 [B, ceil(n_inputs / 8)], input k = bit k & 7 of byte
+        k >> 3 (np.packbits(..., bitorder="little")).  Only programs that have a bit-input tape (speculative())."""
+        B = status_out.shape[0]
+        _check(lib().cvmgpu_witness_batch_bits(self._h, r1cs._h if r1cs is not None else None, _ptr(input_bits), B, wire0, n_sel,
+                                               _ptr(wtns_out), _ptr(status_out), _ptr(first_bad_out)))
+
+    def packed_layout(self, bit_input_tape=False):
+        """-> (row bytes, number of field wires, number of 0/1 wires, wire -> typed row map) of the packed witness rows"""
+        rb, nf, nb, ptr = c_uint64(), c_uint32(), c_uint32(), c_void_p()
+        _check(lib().cvmgpu_packed_layout(self._h, int(bit_input_tape), byref(rb), byref(nf), byref(nb), byref(ptr)))
+        rows = np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(c_uint32)), shape=(self.n_wires,)).copy()
+        return int(rb.value), int(nf.value), int(nb.value), rows
+
+    def calculate_packed_into(self, inputs, inputs_are_bits, packed_out, status_out, r1cs=None, first_bad_out=None):
+        """the whole witness as packed rows (packed_layout(inputs_are_bits)): field wires 32 bytes each, 0/1 wires one bit each"""
+        B = status_out.shape[0]
+        _check(lib().cvmgpu_witness_batch_packed(self._h, r1cs._h if r1cs is not None else None, _ptr(inputs), int(inputs_are_bits), B,
+                                                 _ptr(packed_out), _ptr(status_out), _ptr(first_bad_out)))
+
+    @staticmethod
+    def unpack_rows(packed, layout):
+        """packed rows [B, row_bytes] + packed_layout() -> canonical ints per witness (test / inspection helper)"""
+        row_bytes, n_f, n_b, rows = layout
+        out = []
+        for r in packed:
+            raw = bytes(r)
+            fvals = [int.from_bytes(raw[32 * j:32 * j + 32], "little") for j in range(n_f)]
+            bits = np.unpackbits(np.frombuffer(raw[32 * n_f:], dtype=np.uint8), bitorder="little")
+            w, fi, bi = [], 0, 0
+            for loc in rows:
+                if loc & ROW_BIT:
+                    w.append(int(bits[bi]))
+                    bi += 1
+                else:
+                    w.append(fvals[fi])
+                    fi += 1
+            out.append(w)
+        return out
 
     def calculate_multi_into(self, inputs, device_mask, wire0, n_sel, wtns_out, status_out, r1cs=None, first_bad_out=None):
         """the same over several devices of this process (bit d of device_mask = CUDA device d)"""

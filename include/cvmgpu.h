@@ -154,6 +154,25 @@ int cvmgpu_program_load_text3(const char *cvm_text, size_t len, const char *cpp_
  * cvmgpu_r1cs_check_store_dev / cvmgpu_store_bytes / cvmgpu_program_info_get; witnesses it flags must be redone with p.
  * CVMGPU_SPECULATE=0 in the environment: never build one. */
 int cvmgpu_program_speculative(cvmgpu_program *p, cvmgpu_program **spec);
+/* The same programs take their inputs as PACKED BITS: row = ceil(n_inputs / 8) bytes per witness, input k = bit (k & 7) of
+ * byte (k >> 3).  One 32-byte field element per message bit is what the reference's input.json amounts to; for a batch
+ * it is 256 times the bytes (Sha256(512) x 65 536: 1 GiB against 4 MiB, 19 ms of PCIe per call).  Outputs as
+ * cvmgpu_witness_batch_select.  CVMGPU_ERR_UNSUPPORTED for programs without a bit-input tape. */
+int cvmgpu_witness_batch_bits(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *input_bits, uint64_t B, uint32_t wire0,
+                              uint32_t n_sel, uint8_t *wtns_out, uint32_t *status, uint32_t *first_bad);
+/* PACKED witness rows: the whole witness in the types the trace compiler proved -- per witness the field wires as 32-byte
+ * canonical values in wire order, then the 0/1 wires as bits in wire order (bit j & 31 of 32-bit word j >> 5, the words
+ * following the field part, padded to a multiple of 16 bytes).  cvmgpu_packed_layout gives the row size, the two counts and
+ * the wire -> typed-row map of the
+ * same handle (entry & 0x80000000: a 0/1 wire).  Sha256(512): 8.6 KB per witness instead of 2.2 MB of 32-byte values.
+ * bit_input_tape / inputs_are_bits != 0: the layout of the bit-input tape, inputs as packed bits (cvmgpu_witness_batch_bits);
+ * 0: the layout of the program itself, inputs as 32-byte field elements. */
+int cvmgpu_packed_layout(cvmgpu_program *p, int bit_input_tape, uint64_t *row_bytes, uint32_t *n_field, uint32_t *n_bits,
+                         const uint32_t **wire_rows);
+int cvmgpu_witness_batch_packed(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *inputs, int inputs_are_bits, uint64_t B,
+                                uint8_t *packed_out, uint32_t *status, uint32_t *first_bad);
+/* DEVICE: the packed rows of a value store written by program p (the handle whose layout applies) */
+int cvmgpu_witness_export_packed_dev(cvmgpu_program *p, const void *d_store, uint64_t B, uint64_t bstride, void *d_out, void *stream);
 int cvmgpu_program_info_get(const cvmgpu_program *p, cvmgpu_program_info *info);
 void cvmgpu_program_free(cvmgpu_program *p);
 /* Read-only view of the compiled tape (16-byte instructions, layout in csrc/tape.hpp) and of its constant table

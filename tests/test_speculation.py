@@ -139,3 +139,66 @@ def test_speculation_switches_itself_off_when_inputs_are_numbers(cvmlib, tmp_pat
         got = E.le_to_ints(wt)
         for b in (0, 7, 63):
             assert got[b] == I.compute_witness(prog, rows[b])
+
+
+def test_packed_layout(cvmlib):
+    """row layout of the packed witness: field wires x 32 B, then one bit per 0/1 wire (32-bit words)"""
+    from circom_cvm_b200 import engine as E
+    art = circuit("sha256_64")
+    wc = E.WitnessCalculator(cvm_text=art.cvm)
+    rb, nf, nb, rows = wc.packed_layout(bit_input_tape=True)
+    assert nf == 1 and nf + nb == wc.n_wires and rb == 32 + 16 * ((nb + 127) // 128)
+    assert not rows[0] & E.ROW_BIT and all(r & E.ROW_BIT for r in rows[1:])
+    rb0, nf0, nb0, _rows0 = wc.packed_layout()
+    assert nf0 > nf and nf0 + nb0 == wc.n_wires and rb0 == 32 * nf0 + 16 * ((nb0 + 127) // 128)
+    pos = E.WitnessCalculator(cvm_text=circuit("poseidon2").cvm)
+    assert pos.packed_layout()[:3] == (32 * pos.n_wires, pos.n_wires, 0)
+    with pytest.raises(E.CvmGpuError) as e:
+        pos.packed_layout(bit_input_tape=True)
+    assert e.value.code == -3
+
+
+@pytest.mark.gpu
+def test_packed_bit_inputs_and_packed_witness_rows(cvmlib, tmp_path):
+    """Sha256(64): messages as packed bits in (8 bytes per witness instead of 2 KB), the whole witness as packed rows out
+    (field wires 32 B, 0/1 wires one bit): the same witnesses, flags and R1CS verdicts as the 32-byte interfaces."""
+    import numpy as np
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.build import write_artifact
+    art = circuit("sha256_64")
+    paths = write_artifact(art, str(tmp_path))
+    wc, r = E.WitnessCalculator(cvm_text=art.cvm), E.R1cs(paths["r1cs"])
+    rng = random.Random(23)
+    B = 133
+    rows = [[rng.randrange(2) for _ in range(art.n_inputs)] for _ in range(B)]
+    wt, st, bad = wc.calculate_checked(rows, r)
+    assert not st.any() and (bad == E.NO_BAD).all()
+    bits = np.packbits(np.array(rows, dtype=np.uint8), axis=1, bitorder="little")
+    assert bits.shape == (B, (art.n_inputs + 7) // 8)
+    # packed bits in, a wire range out
+    n_pub = 1 + art.n_pub_out
+    wt_b = np.zeros((B, n_pub, 32), dtype=np.uint8)
+    st_b, bad_b = np.full(B, 9, dtype=np.uint32), np.zeros(B, dtype=np.uint32)
+    wc.calculate_bits_into(bits, 0, n_pub, wt_b, st_b, r, bad_b)
+    assert not st_b.any() and (bad_b == E.NO_BAD).all() and np.array_equal(wt_b, wt[:, :n_pub])
+    # packed bits in, packed rows out
+    for as_bits in (True, False):
+        layout = wc.packed_layout(bit_input_tape=as_bits)
+        out = np.zeros((B, layout[0]), dtype=np.uint8)
+        st_p, bad_p = np.full(B, 9, dtype=np.uint32), np.zeros(B, dtype=np.uint32)
+        wc.calculate_packed_into(bits if as_bits else E.ints_to_le(rows, art.n_inputs), as_bits, out, st_p, r, bad_p)
+        assert not st_p.any() and (bad_p == E.NO_BAD).all()
+        got = E.WitnessCalculator.unpack_rows(out[[0, 1, 64, B - 1]], layout)
+        want = E.le_to_ints(wt[[0, 1, 64, B - 1]])
+        assert got == want, as_bits
+    # a field program: its packed rows are its .wtns rows
+    pos_art = circuit("poseidon2")
+    pos = E.WitnessCalculator(cvm_text=pos_art.cvm)
+    prow = [[rng.randrange(M.Q), rng.randrange(M.Q)] for _ in range(40)]
+    pw, pst = pos.calculate(prow)
+    pout = np.zeros((40, pos.packed_layout()[0]), dtype=np.uint8)
+    pst2 = np.zeros(40, dtype=np.uint32)
+    pos.calculate_packed_into(E.ints_to_le(prow, 2), False, pout, pst2)
+    assert np.array_equal(pout.reshape(40, pos.n_wires, 32), pw) and not pst2.any()
+    with pytest.raises(E.CvmGpuError):
+        pos.calculate_bits_into(np.zeros((4, 1), dtype=np.uint8), 0, 1, np.zeros((4, 1, 32), dtype=np.uint8), np.zeros(4, dtype=np.uint32))
