@@ -476,7 +476,40 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
             del d_wt
         return out
 
-    e2e = e2e_public = e2e_flags = None
+    def compact_leg(Be):
+        """The compact wire formats of a program whose inputs are bits: the messages go up as packed bits (n_inputs / 8 bytes per
+        witness) and the WHOLE witness comes back as packed rows (field wires 32 B, 0/1 wires one bit each)."""
+        import numpy as np
+        layout = wc_host.packed_layout(bit_input_tape=True)
+        h_bits = torch.from_numpy(np.packbits(inputs[:Be, :, 0].cpu().numpy(), axis=1, bitorder="little")).pin_memory()
+        h_out = torch.empty((Be, layout[0]), dtype=torch.uint8).pin_memory()
+        h_st = torch.empty(Be, dtype=torch.int32).pin_memory()
+        h_bad = torch.empty(Be, dtype=torch.int32).pin_memory()
+        for _ in range(3):
+            wc_host.calculate_packed_into(h_bits, True, h_out, h_st, r1, h_bad)
+        if world > 1:
+            dist.barrier()
+        steps = max(3, min(args.steps, 8))
+        per_step = []
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            t1 = time.perf_counter()
+            wc_host.calculate_packed_into(h_bits, True, h_out, h_st, r1, h_bad)
+            per_step.append(time.perf_counter() - t1)
+        torch.cuda.synchronize()
+        te = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        sec = float(te.item())
+        ok = int((h_st != 0).sum()) == 0 and int((h_bad != -1).sum()) == 0
+        return {"value": world * Be / sec, "unit": UNIT, "h2d_bytes_per_step": int(h_bits.numel()), "d2h_bytes_per_step": int(h_out.numel()) + 8 * Be,
+                "batch_per_gpu": Be, "ms_per_step": 1000 * sec, "steps": steps,
+                "ms_per_step_median": 1000 * sorted(per_step)[len(per_step) // 2], "ms_per_step_max": 1000 * max(per_step),
+                "all_witnesses_valid": bool(ok), "packed_row_bytes": layout[0], "field_wires": layout[1], "bit_wires": layout[2],
+                "api": "cvmgpu_witness_batch_packed(inputs_are_bits = 1): packed message bits in, witness generation + R1CS check, the WHOLE "
+                       "witness back as packed rows (every wire, in the type the program proved: 32 bytes or 1 bit)"}
+
+    e2e = e2e_public = e2e_flags = e2e_compact = None
     if not args.skip_e2e:
         Be = min(e2e_b, B)
         e2e = e2e_leg(Be, 0, wc.n_wires, "WitnessCalculator.calculate_into -> cvmgpu_witness_batch_checked "
@@ -486,6 +519,8 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
                                           "of every witness (constant 1, %d outputs, %d public inputs) comes back"
                              % (art.n_pub_out, art.n_pub_in))
         e2e_flags = e2e_leg(B, 0, 0, "same call with wtns_out = NULL: witness generation + R1CS check, flags only")
+        if wc_spec is not None and WL["bits"]:
+            e2e_compact = compact_leg(B)
     E.lib().cvmgpu_release_buffers()
 
     if rank != 0:
@@ -617,7 +652,7 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
         "witnesses_per_s_gen_only": world * B / (ms_tape * 1e-3),
         "constraints_per_s_check_only": world * B * rinfo["n_constraints"] / (ms_check * 1e-3),
         "roofline": roofline, "kernels": kernels,
-        "cpu_baseline": cpu, "e2e": e2e, "e2e_public_outputs": e2e_public, "e2e_flags_only": e2e_flags,
+        "cpu_baseline": cpu, "e2e": e2e, "e2e_public_outputs": e2e_public, "e2e_flags_only": e2e_flags, "e2e_compact": e2e_compact,
         "gpu_launches": n_launch if fused else 2 * n_launch,
         "clocks": sampler.summary(),
         "program": info, "fused_program": finfo if fused else None, "r1cs": rinfo,
@@ -675,7 +710,7 @@ def main():
         if rank == 0:
             keep = ("metric", "value", "unit", "ms_per_step", "config", "kernels_ms", "separate_kernels_ms", "witnesses_per_s_gen_only",
                     "constraints_per_s_check_only", "roofline", "kernels", "cpu_baseline", "e2e", "e2e_public_outputs",
-                    "e2e_flags_only", "gpu_launches", "program", "r1cs")
+                    "e2e_flags_only", "e2e_compact", "gpu_launches", "program", "r1cs")
             line["secondary"] = {k: sec[k] for k in keep}
             line["gpu_launches"] += sec["gpu_launches"]
     if rank == 0:

@@ -159,7 +159,9 @@ static double tape_cost(const tape::Tape &t) {
     // per CTA.  A 64 K batch -- 2 048 warps over 148 SMs, BASELINE configs 3 and 4 -- must fit in ONE wave: at 13
     // resident warps per SM it takes two (measured: Sha256(512) 115 ms against 64 ms), hence the quantisation term.
     const size_t per_warp = (size_t)(t.n_slots + (t.use_ring ? tape::LD_RING : 0)) * 1024u + (size_t)t.n_bslots * 4u + 1024u;
-    const double resident = std::min<double>(std::floor(228.0 * 1024.0 / (double)per_warp), 64.0);
+    // (the bit-file instantiation is bounded at 128 registers: 4 warps per scheduler, 16 per SM -- at 136 it was 3 and 12,
+    // and a 64 K batch took two waves: 17.5 ms instead of 9.5)
+    const double resident = std::min<double>(std::floor(228.0 * 1024.0 / (double)per_warp), t.n_bslots ? 16.0 : 64.0);
     const double waves = 2048.0 / (148.0 * std::max(1.0, resident));
     const double quant = std::ceil(waves) / std::max(waves, 1.0);
     // value-store traffic: field rows move 1 KiB per warp; a bit-row reload is one word, but it is a dependent

@@ -221,9 +221,10 @@ __device__ __forceinline__ Fr tape_arith(uint32_t op, uint32_t flags, const uint
 // later reads its own store: no fence needed), and a bit row of the value store is that word per warp: 4 bytes where a
 // field row costs 1 KiB.
 // (programs without 0/1-typed values are bound by the multiplier pipe and want 20 resident warps per SM: 96 registers;
-// the bit-file instantiation is limited by its shared memory instead and keeps the registers it needs)
+// the bit-file instantiation gets 128: the register file is split between the four schedulers, so 129..168 registers mean 3
+// warps per scheduler = 12 per SM, and a 64 K batch -- 13.8 one-warp CTAs per SM -- no longer fits one wave)
 template <int NT, bool BITS>
-__global__ void __launch_bounds__(NT, BITS ? 1 : 640 / NT) tape_kernel(TapeParams p) {
+__global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(TapeParams p) {
     extern __shared__ uint4 slots[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint64_t w = (uint64_t)blockIdx.x * NT + tid;
