@@ -70,7 +70,10 @@ def build_workload(tmpdir):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md): NVML polled every 10 ms from this process
+    (a timed region of ~125 ms is over before an `nvidia-smi -lms` child has printed its first line); `nvidia-smi` as fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,12 +82,44 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.stop_flag = False
         self.proc = None
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def run(self):
+        try:
+            nv, h = self._nvml_handle()
+            sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.source = "nvml"
+            while not self.stop_flag:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.samples.append((sm, sm_max, pw))
+                mask = int(get_reasons(h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.01)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -109,14 +144,16 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
+        self.join(timeout=1.0)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
         sm = sorted(s[0] for s in self.samples)
         hi = [s for s in sm if s >= 0.5 * max(sm)] or sm
         return {"sm_mhz": hi[len(hi) // 2], "sm_max_mhz": max(s[1] for s in self.samples),
-                "power_w_max": max(s[2] for s in self.samples), "reasons": sorted(self.reasons)}
+                "power_w_max": max(s[2] for s in self.samples), "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "source": self.source}
 
 
 def measured_peaks():
@@ -625,6 +662,11 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
                      "peak_source": peak_src if view == "imad" else "MEASURED_PEAKS.json hbm_gbs (%s)" % peak_kind,
                      "traffic": kd["hbm"]["traffic"], "traffic_source": traffic_src,
                      "other_view": {k: kd[other][k] for k in ("bound", "achieved", "peak", "unit", "frac")}})
+    if roofline.get("frac", 0) > 1.0:
+        roofline["note"] = ("frac > 1 is the algorithmic count SURVEY 8(d) prescribes (the reference program's field multiplications x 136) "
+                            "over the multiplier peak: the trace compiler removed that arithmetic (fused dot products; for 0/1-typed values "
+                            "the reference multiplies field elements to AND two bits, the typed tape does not multiply there).  "
+                            "frac_executed is what the kernel issues.")
     if args.skip_cpu:
         cpu = None
     else:
