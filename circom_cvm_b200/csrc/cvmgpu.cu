@@ -89,6 +89,7 @@ struct cvmgpu_program {
     uint32_t max_terms = 0;
     uint32_t explicit_slots = 0;     // the caller's slot count (0: chosen by the cost model), also used for fused tapes
     bool fusable = false;
+    bool typed = true;               // false: compiled untyped (a field program with a sprinkling of 0/1 values)
     std::map<uint64_t, std::unique_ptr<cvmgpu_program>> fused;
     std::map<uint64_t, bool> fuse_worth;
     // the same circuit traced under the assumption that every main input is 0 or 1 (see build_program), or null
@@ -176,9 +177,26 @@ static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume
     std::unique_ptr<cvmgpu_program> p(new cvmgpu_program());
     if (n_slots > 55) n_slots = 55;   // 55 * 4 KiB = 220 KiB of the 227 KiB a CTA may use
     try {
-        tape::Tracer tr(parser.prog);
-        tr.assume_bit_inputs = assume_bit_inputs;
-        tr.trace();
+        std::unique_ptr<tape::Tracer> trp(new tape::Tracer(parser.prog));
+        trp->assume_bit_inputs = assume_bit_inputs;
+        trp->trace();
+        // A field program with a sprinkling of 0/1 values (comparison results, the bits of a few scalars: the EdDSA verifier
+        // has 3 %) is traced again without boolean-function instructions and compiled untyped: the bit-slot file would cost
+        // it the field-only kernel (96 registers, 20 warps per SM) and the fused R1CS check for nothing.
+        bool typed = true;
+        {
+            size_t n_bool = 0;
+            for (uint8_t b : trp->isbool) n_bool += b;
+            static const bool allow = !(getenv("CVMGPU_UNTYPED") && atoi(getenv("CVMGPU_UNTYPED")) == 0);
+            if (allow && !assume_bit_inputs && n_bool > 0 && n_bool * 10 < trp->ops.size()) {
+                typed = false;
+                trp.reset(new tape::Tracer(parser.prog));
+                trp->use_luts = false;
+                trp->trace();
+            }
+        }
+        tape::Tracer &tr = *trp;
+        p->typed = typed;
         p->binv = tape::batch_inversions(tr);
         if (n_slots == 0) {
             // Fewer slots per witness = more resident warps per SM (1 KiB of shared memory per field slot and warp, 4 B per
@@ -191,7 +209,7 @@ static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume
             auto build = [&](uint32_t c, uint32_t max_bslots) {
                 const uint32_t mt = std::min<uint32_t>(16, c - 2);
                 auto it = prepared.find(mt);
-                if (it == prepared.end()) it = prepared.emplace(mt, tape::prepare_program(tr, mt)).first;
+                if (it == prepared.end()) it = prepared.emplace(mt, tape::prepare_program(tr, mt, true, typed)).first;
                 return tape::allocate_tape(tr, it->second, c, max_bslots);
             };
             double best = 0, prev_best_c = 0;
@@ -227,7 +245,7 @@ static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume
             const uint32_t nb = getenv("CVMGPU_BSLOTS") ? (uint32_t)atoi(getenv("CVMGPU_BSLOTS")) : 2048u;
             p->max_terms = std::min<uint32_t>(16, n_slots - 2);
             p->explicit_slots = n_slots;
-            tape::XProg xp = tape::prepare_program(tr, p->max_terms);
+            tape::XProg xp = tape::prepare_program(tr, p->max_terms, true, typed);
             p->tape = tape::allocate_tape(tr, xp, n_slots, std::max<uint32_t>(8, nb));
             if (tape::check_fusable(xp)) {
                 p->xp = std::move(xp);
@@ -545,8 +563,11 @@ static cvmgpu_program *fused_for(cvmgpu_program *p, cvmgpu_r1cs *r) {
     if (mode == 0 || !p || !r || !p->fusable || r->file.n_wires != p->tape.n_wires) return nullptr;
     std::lock_guard<std::mutex> lock(p->mu);
     if (mode == 1) {
+        // A program compiled untyped has 0/1 values the stand-alone check exploits at run time (it skips products with a 0 / 1
+        // factor): EdDSAPoseidonVerifier untyped, measured 58.3 ms fused against 36.6 + 17.9 ms.
+        if (!p->typed) return nullptr;
         // Constraints over 0/1 wires are evaluated 32 witnesses at a time by the table / integer kernels (r1cs.hpp bind):
-        // a program that has them (EdDSAPoseidonVerifier: measured 62.2 ms fused against 38.8 + 19.8 ms) keeps those kernels
+        // a program that has them (EdDSAPoseidonVerifier typed: measured 62.2 ms fused against 38.8 + 19.8 ms) keeps those kernels
         auto w = p->fuse_worth.find(r->uid);
         if (w == p->fuse_worth.end()) {
             const r1cs::Bound b = r1cs::bind(r->file, p->tape.wire_loc.data(), p->tape.one_brow, p->tape.const_rows);

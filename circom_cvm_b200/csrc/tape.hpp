@@ -756,9 +756,14 @@ inline void max_live_by_kind(const XProg &xp, uint32_t out[2]) {
 // FIELD file (32-byte slots per witness) and in field rows.  A witness wire is a bit row or a field row according to
 // the type of the value bound to it (Tape::wire_loc); consumers of a 0/1 value in field arithmetic convert on fetch.
 // fusions and typing that do not depend on the slot files (max_terms: longest fused dot product)
-inline XProg prepare_program(const Tracer &tr, uint32_t max_terms, bool fuse = true) {
+// typed = false: every value a field element (no bit-slot file, no integer typing, no groups): programs with only a
+// sprinkling of 0/1 values run the field-only kernel instantiation, which has the registers for 20 warps per SM
+inline XProg prepare_program(const Tracer &tr, uint32_t max_terms, bool fuse = true, bool typed = true) {
     XProg xp = fuse_dots(tr, max_terms, fuse);
-    if (fuse) {
+    if (!typed) {
+        xp.isbool.assign(xp.ops.size(), 0);
+        xp.isint.assign(xp.ops.size(), 0);
+    } else if (fuse) {
         type_ints(xp, tr);
         fuse_isums(xp, tr);
         group_bit_ops(xp);

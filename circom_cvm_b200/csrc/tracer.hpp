@@ -118,6 +118,9 @@ class Tracer {
     // signals: nothing in Sha256(n) proves in[k] a bit, so everything derived from the message before the first bit
     // decomposition is field arithmetic).  The assumption is CHECKED per witness at run time (T_INPUT_BIT).
     bool assume_bit_inputs = false;
+    // Emit boolean cones as T_LUT (operands and result in the bit-slot file).  Off for programs that are traced for the
+    // untyped tape (a field program with a sprinkling of 0/1 values: everything stays a field element).
+    bool use_luts = true;
     std::vector<SOp> ops;
     std::vector<uint8_t> isbool;  // per op: the value is provably 0 or 1 (comparison results, extracted bits, ANDs of those)
     // Boolean-cone collapsing.  For every value that is an arithmetic function of at most three provably-0/1 values, the
@@ -484,6 +487,7 @@ class Tracer {
         else if (isbool[id] && (o.op == T_EQ || o.op == T_NEQ || o.op == T_EQZ || o.op == T_LAND || o.op == T_LOR) && c.k >= 2 &&
                  !(o.a & CONST_FLAG) && (o.b == NO_REF || !(o.b & CONST_FLAG)) && isbool[o.a] && (o.b == NO_REF || isbool[o.b]))
             return id;   // already one cheap instruction on 0/1 operands
+        else if (!use_luts) return id;
         else {
             uint32_t table = 0;
             for (int r = 0; r < (1 << c.k); r++) table |= (uint32_t)c.tt[r] << r;
