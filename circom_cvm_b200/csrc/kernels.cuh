@@ -331,6 +331,32 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             raw = rec;
             continue;
         }
+        case tape::T_ISUMT: {
+            // T_ISUM in transposed form (tape.hpp): cur.y layers; in a layer lane l fetches the packed word of the term whose shift
+            // is base + l (bit w = witness w, 0 if none) and the transpose of that 32 x 32 bit matrix hands every lane the
+            // integer sum_l bit_l << l of its own witness.
+            const uint32_t nl = cur.y;
+            unsigned long long v = 0;
+            if (flags & tape::F_ADDEND) v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            const uint32_t *words = reinterpret_cast<const uint32_t *>(tp + pc + 1);
+            uint32_t e = __ldg(words + lane);
+            for (uint32_t L = 0; L < nl; L++) {
+                const uint32_t nxt = __ldg(words + (L + 1) * 32 + lane);   // next layer (after the last: the following instructions)
+                uint32_t x = (e & 0xffffu) == 0xffffu ? 0u : bw[e & 0xffffu];
+                // 32 x 32 bit-matrix transpose across the warp: five exchange steps
+#pragma unroll
+                for (uint32_t k = 16, m = 0x0000ffffu; k >= 1; k >>= 1, m ^= m << k) {
+                    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+                    x = (lane & k) ? ((y >> k) & m) | (x & ~m) : (x & m) | ((y & m) << k);
+                }
+                v += (unsigned long long)x << (e >> 16);
+                e = nxt;
+            }
+            slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
+            pc += nl * 8;
+            raw = __ldg(tp + pc + 1);
+            continue;
+        }
         case tape::T_LUTG: case tape::T_IBITG: {
             // Warp-cooperative groups (tape.hpp group_bit_ops): cur.y independent operations on values typed 0/1, lane m doing
             // member m for all 32 witnesses of the warp at once on their packed words.  Record m = (operand slots, result

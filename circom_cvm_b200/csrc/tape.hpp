@@ -47,6 +47,7 @@ struct TapeStats {
     uint64_t n_ld = 0, n_st = 0, n_spill_st = 0, n_stc = 0, n_input = 0, n_fail = 0, n_rne = 0, n_dot = 0, n_dot_terms = 0, n_ld_streamed = 0, n_lut = 0;
     uint64_t n_groups = 0;         // warp-cooperative group instructions (T_LUTG / T_IBITG)
     uint64_t n_isum_terms = 0;     // conditional adds of bits fused into T_ISUM instructions
+    uint64_t n_isum_layers = 0;    // 32 x 32 bit-matrix transposes of the T_ISUMT form
     uint64_t n_int = 0;            // small-integer operations (type_ints): sums of 0/1 values kept as raw 64-bit integers
     uint64_t n_ld_bool = 0, n_spill_st_bool = 0;   // of n_ld / n_spill_st: the value is typed 0/1 (what compact bit rows would shrink)
     uint32_t n_spill_rows = 0;
@@ -659,6 +660,7 @@ inline void group_bit_ops(XProg &xp) {
 inline uint32_t extra_records(const TapeIns &in) {
     if (in.op == T_DOT) return (in.a + 1) / 2;
     if (in.op == T_ISUM) return (in.a + 3) / 4;
+    if (in.op == T_ISUMT) return in.a * 8;
     if (in.op == T_LUTG || in.op == T_IBITG) return in.a;
     return 0;
 }
@@ -1169,6 +1171,57 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
                     addend = it->second;
                 }
             }
+            // Transposed form (T_ISUMT).  The terms are (bit slot, shift) pairs and the sum does not care about their order: they
+            // are dealt into LAYERS in which every shift occurs at most once and all shifts lie within a 32-wide window.  A
+            // layer is a 32 x 32 bit matrix -- lane l holds the word of the term whose shift is base + l (bit w = witness w) --
+            // whose transpose gives every lane the integer  sum_j bit_j << (shift_j - base)  of ITS witness in five shuffle
+            // steps, instead of one shared-memory read, mask, shift and 64-bit add per term and lane.
+            {
+                struct Term { uint32_t sh, slot; };
+                std::vector<Term> terms;
+                for (uint32_t k = 0; k < o.tn; k++) {
+                    const fr::Fr &cv = consts[xp.terms[o.t0 + k].first & ~CONST_FLAG];
+                    const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
+                    uint32_t sh = 0;
+                    while (!((v >> sh) & 1)) sh++;
+                    terms.push_back(Term{sh, enc[k] & 0xffffu});
+                }
+                std::stable_sort(terms.begin(), terms.end(), [](const Term &x, const Term &y) { return x.sh < y.sh; });
+                struct Layer { uint32_t base; uint32_t slot[32]; };
+                std::vector<Layer> layers;
+                for (const Term &t : terms) {
+                    bool placed = false;
+                    for (Layer &L : layers)
+                        if (t.sh >= L.base && t.sh - L.base < 32 && L.slot[t.sh - L.base] == 0xffffu) {
+                            L.slot[t.sh - L.base] = t.slot;
+                            placed = true;
+                            break;
+                        }
+                    if (!placed) {
+                        Layer L;
+                        L.base = t.sh;
+                        for (uint32_t &x : L.slot) x = 0xffffu;
+                        L.slot[0] = t.slot;
+                        layers.push_back(L);
+                    }
+                }
+                // a layer costs about as much as five terms of the serial form
+                if (layers.size() * 5 < o.tn && layers.size() < 256) {
+                    out.ins.push_back(TapeIns{T_ISUMT, flags, dcode, (uint32_t)layers.size(), addend, 0});
+                    for (const Layer &L : layers)
+                        for (uint32_t k = 0; k < 32; k += 4) {
+                            uint32_t rec[4];
+                            for (uint32_t j = 0; j < 4; j++) rec[j] = L.slot[k + j] | (L.base << 16);
+                            TapeIns raw;
+                            memcpy(&raw, rec, sizeof(rec));
+                            out.ins.push_back(raw);
+                        }
+                    out.stats.n_int++;
+                    out.stats.n_isum_terms += o.tn;
+                    out.stats.n_isum_layers += layers.size();
+                    goto isum_done;
+                }
+            }
             out.ins.push_back(TapeIns{T_ISUM, flags, dcode, o.tn, addend, 0});
             for (uint32_t k = 0; k < o.tn; k += 4) {
                 uint32_t rec[4] = {0, 0, 0, 0};
@@ -1185,6 +1238,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
             }
             out.stats.n_int++;
             out.stats.n_isum_terms += o.tn;
+        isum_done:;
         } else if (o.op == T_DOT) {
             // header: a = number of terms, b = addend (slot or constant index), c = wire row with F_STORE;
             // then ceil(n/2) records of (constant index, slot) x 2

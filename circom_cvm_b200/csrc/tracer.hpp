@@ -59,6 +59,10 @@ enum TOp : uint8_t {
     // speculative typing (Tracer::assume_bit_inputs): main input `a`, which must be literally 0 or 1 -- typed 0/1; any
     // other value raises ST_SPECULATION and the witness is recomputed by the program traced without the assumption
     T_INPUT_BIT,
+    // T_ISUM with its terms dealt into layers of distinct shifts: a = number of layers, b = addend; per layer 8 records =
+    // 32 words, word l = bit slot | base << 16 of the term whose shift is base + l (slot 0xffff: none).  Produced by the
+    // allocator only (tape.hpp), never an SSA operation.
+    T_ISUMT,
     T_COUNT
 };
 

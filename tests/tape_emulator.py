@@ -8,7 +8,7 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE, T_INPUT_BIT) = range(46)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE, T_INPUT_BIT, T_ISUMT) = range(47)
 F_ADDEND = 32        # T_DOT: field b is an addend
 ST_SPECULATION = 6
 F_CHECK = 128        # T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: compare the result with slot dst, c = constraint
@@ -118,6 +118,21 @@ def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
                 assert v in (0, 1), "T_ISUM term is not a 0/1 value"
                 acc += v << (t >> 16)
             pc += (a + 3) // 4
+            assert acc < 1 << 62 and not dst & BSLOT_DST
+            res = Int(acc)
+        elif op == T_ISUMT:
+            # T_ISUM with its terms dealt into layers of distinct shifts: a layers of 32 words, word l = bit slot | base << 16 of
+            # the term whose shift is base + l (slot 0xffff: none)
+            acc = get_int(b, flags & 2) if flags & F_ADDEND else 0
+            for layer in range(a):
+                for l in range(32):
+                    t = int(words[pc + layer * 8 + l // 4][l % 4])
+                    if t & 0xFFFF == 0xFFFF:
+                        continue
+                    v = bslots[t & 0xFFFF]
+                    assert v in (0, 1), "T_ISUMT term is not a 0/1 value"
+                    acc += v << ((t >> 16) + l)
+            pc += a * 8
             assert acc < 1 << 62 and not dst & BSLOT_DST
             res = Int(acc)
         elif op in (T_LUTG, T_IBITG):
