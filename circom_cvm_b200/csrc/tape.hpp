@@ -497,7 +497,7 @@ inline void type_ints(XProg &xp, const Tracer &tr) {
 // up to ISUM_MAX links: the accumulator stays in a register instead of going through its slot once per bit, and the
 // instruction fetch / dispatch of the interpreter is paid once.  Links whose constant is not a power of two, or whose
 // condition is not a value typed 0/1, stay T_ICADD.
-static const uint32_t ISUM_MAX = 32;
+static const uint32_t ISUM_MAX = 128;
 
 inline void fuse_isums(XProg &xp, const Tracer &tr) {
     std::vector<XOp> &ops = xp.ops;
@@ -830,7 +830,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
     }
     // the bit file: enough for every live 0/1 value when that fits (no bit spills at all), else the cap
     uint32_t n_bslots = ml[1] == 0 ? 0 : std::min<uint32_t>(max_bslots, ((ml[1] + 3 + 31) / 32) * 32);
-    if (ml[1] && n_bslots < 64) n_bslots = 64;   // a T_ISUM pins up to ISUM_MAX bit slots at once
+    if (ml[1] && n_bslots < ISUM_MAX + 64) n_bslots = ISUM_MAX + 64;   // a T_ISUM pins up to ISUM_MAX bit slots at once
     out.n_bslots = n_bslots;
     const uint32_t file_slots[2] = {n_slots, n_bslots};
 
