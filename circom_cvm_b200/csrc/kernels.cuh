@@ -245,10 +245,26 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
     const uint4 *tp = reinterpret_cast<const uint4 *>(p.tape);
     const uint32_t n_ins = p.n_ins;
     uint4 raw = __ldg(tp);
+    uint4 lrec = BITS ? __ldg(tp + 1 + lane) : make_uint4(0u, 0u, 0u, 0u);
     uint32_t pf = 0;   // first tape word (8 per 128-byte line) not yet prefetched into L1
     for (uint32_t pc = 0; pc < n_ins; pc++) {
         const uint4 cur = raw;
-        raw = __ldg(tp + pc + 1);   // the next instruction (re-done after the records of a DOT / ISUM)
+        // Bit-file programs are bound by latency, and most of what they run are group instructions whose lane m works on
+        // record m: as soon as an instruction is known, the NEXT one (which follows this one's records) and the 32 words
+        // after it -- one per lane: its records, if it is a group -- are requested, so that they arrive while this one
+        // executes.  myrec = the word after this instruction that belongs to this lane.
+        const uint4 myrec = lrec;
+        if (BITS) {
+            const uint32_t o = cur.x & 0xffu;
+            const uint32_t ext = (o == tape::T_LUTG || o == tape::T_IBITG) ? cur.y
+                                 : o == tape::T_ISUMT                     ? cur.y * 8u
+                                 : o == tape::T_ISUM                      ? (cur.y + 3u) >> 2
+                                 : o == tape::T_DOT                       ? (cur.y + 1u) >> 1
+                                                                          : 0u;
+            raw = __ldg(tp + pc + 1 + ext);
+            lrec = __ldg(tp + pc + 2 + ext + lane);
+        } else
+            raw = __ldg(tp + pc + 1);   // the next instruction (re-done after the records of a DOT)
         // tape lines ahead.  With group instructions pc jumps over up to 33 words at a time: the window follows pc.
         if (BITS) {
 #pragma unroll 1
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             r = fr::wide_reduce(T, n);
             if (flags & tape::F_ADDEND) r = fr::add(r, tape_operand<NT, BITS>(slots, bw, consts, cur.z, flags & 2u, tid));
             pc += (n + 1) >> 1;
-            raw = __ldg(tp + pc + 1);
+            if (!BITS) raw = __ldg(tp + pc + 1);
             break;
         }
         case tape::T_SEL: {
@@ -317,7 +333,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             if (flags & tape::F_ADDEND) v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
             // record 0 is what the loop fetched as "the next instruction"; each iteration fetches the record after the one it
             // works on, and the last one thereby fetches the instruction that follows the records
-            uint4 rec = raw;
+            uint4 rec = BITS ? __ldg(tp + pc + 1) : raw;
             for (uint32_t j = 0; j < n; j += 4) {
                 const uint4 nxt = __ldg(tp + pc + 2 + (j >> 2));
                 v += (unsigned long long)((bw[rec.x & 0xffffu] >> lane) & 1u) << (rec.x >> 16);
@@ -328,7 +344,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             }
             slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
             pc += (n + 3) >> 2;
-            raw = rec;
+            if (!BITS) raw = rec;
             continue;
         }
         case tape::T_ISUMT: {
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             }
             slots[(dst * 2) * NT + tid] = make_uint4((uint32_t)v, (uint32_t)(v >> 32), 0u, 0u);
             pc += nl * 8;
-            raw = __ldg(tp + pc + 1);
+            if (!BITS) raw = __ldg(tp + pc + 1);
             continue;
         }
         case tape::T_LUTG: case tape::T_IBITG: {
@@ -365,7 +381,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             uint32_t word = 0, dslot = 0, row = tape::NO_ROW;
             if (op == tape::T_LUTG) {
                 if (lane < n) {
-                    const uint4 rec = __ldg(tp + pc + 1 + lane);
+                    const uint4 rec = BITS ? myrec : __ldg(tp + pc + 1 + lane);
                     const uint32_t nin = (rec.z >> 8) & 0xffu;
                     const uint32_t x0 = bw[rec.x & 0xffffu];
                     const uint32_t x1 = nin > 1 ? bw[rec.x >> 16] : 0u;
@@ -382,15 +398,18 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
                     row = rec.w;
                 }
             } else {
-                // bits cur.w .. cur.w + n - 1 of the integer in slot cur.z: one vote per bit, lane m keeps word m
+                // bits cur.w .. cur.w + n - 1 of the integer in slot cur.z: the 32 x 32 bit matrix (lane = witness, bit = position)
+                // transposed across the warp -- lane m ends up with the word of bit cur.w + m
                 const unsigned long long a = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, false, tid);
-                for (uint32_t j = 0; j < n; j++) {
-                    const uint32_t k = cur.w + j;
-                    const uint32_t b = __ballot_sync(0xffffffffu, k < 64u ? (uint32_t)(a >> k) & 1u : 0u);
-                    if (lane == j) word = b;
+                uint32_t x = cur.w < 64u ? (uint32_t)(a >> cur.w) : 0u;
+#pragma unroll
+                for (uint32_t k = 16, m = 0x0000ffffu; k >= 1; k >>= 1, m ^= m << k) {
+                    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+                    x = (lane & k) ? ((y >> k) & m) | (x & ~m) : (x & m) | ((y & m) << k);
                 }
+                word = x;
                 if (lane < n) {
-                    const uint4 rec = __ldg(tp + pc + 1 + lane);
+                    const uint4 rec = BITS ? myrec : __ldg(tp + pc + 1 + lane);
                     dslot = rec.x & 0xffffu;
                     row = rec.w;
                 }
@@ -402,7 +421,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             }
             __syncwarp();
             pc += n;
-            raw = __ldg(tp + pc + 1);
+            if (!BITS) raw = __ldg(tp + pc + 1);
             continue;
         }
         case tape::T_FILL: {
