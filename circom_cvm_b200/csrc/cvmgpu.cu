@@ -819,8 +819,7 @@ static void packed_lists(const cvmgpu_program *p, std::vector<uint32_t> &fl, std
     }
 }
 static size_t packed_row_bytes(const cvmgpu_program *p) {
-    size_t nf = 0, nb = 0;
-    for (uint32_t loc : p->tape.wire_loc) ((loc & tape::ROW_BIT) ? nb : nf)++;
+    const size_t nf = p->tape.n_fwires, nb = p->tape.n_wires - p->tape.n_fwires;
     return nf * 32 + ((nb + 127) / 128) * 16;   // rows stay 16-byte aligned
 }
 
@@ -830,11 +829,11 @@ extern "C" int cvmgpu_witness_export_packed_dev(cvmgpu_program *p, const void *d
     if (B == 0) return CVMGPU_OK;
     cvmgpu_program::Dev *pd = nullptr;
     if (int rc = upload_program(p, &pd)) return rc;
-    std::vector<uint32_t> fl, bl;
-    packed_lists(p, fl, bl);
     {
         std::lock_guard<std::mutex> lock(p->mu);
-        if (!pd->d_flist.p) {
+        if (!pd->d_flist.p) {   // the row lists of this device, built once
+            std::vector<uint32_t> fl, bl;
+            packed_lists(p, fl, bl);
             if (int rc = pd->d_flist.ensure(std::max<size_t>(4, fl.size() * 4))) return rc;
             if (int rc = pd->d_blist.ensure(std::max<size_t>(4, bl.size() * 4))) return rc;
             if (!fl.empty()) CUDA_TRY(cudaMemcpy(pd->d_flist.p, fl.data(), fl.size() * 4, cudaMemcpyHostToDevice));
@@ -846,8 +845,8 @@ extern "C" int cvmgpu_witness_export_packed_dev(cvmgpu_program *p, const void *d
     pv.sv = store_view(p, pd, d_store, bstride);
     pv.flist = (const uint32_t *)pd->d_flist.p;
     pv.blist = (const uint32_t *)pd->d_blist.p;
-    pv.n_f = (uint32_t)fl.size();
-    pv.n_b = (uint32_t)bl.size();
+    pv.n_f = p->tape.n_fwires;
+    pv.n_b = p->tape.n_wires - p->tape.n_fwires;
     pv.n_ftiles = (pv.n_f + 7) / 8;
     pv.row_bytes = packed_row_bytes(p);
     const uint32_t n_btiles = (pv.n_b + 31) / 32;

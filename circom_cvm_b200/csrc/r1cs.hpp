@@ -71,6 +71,7 @@ struct Bound {
     // Such constraints have no terms in either CSR.
     std::vector<uint32_t> tcons;
     uint64_t n_table_constraints = 0;
+    uint64_t n_tautologies = 0;      // constraints over 0/1 wires that hold for every assignment (not evaluated)
     // the constraints the per-witness kernel has to walk (every mode but 3), in order
     std::vector<uint32_t> active;
     uint64_t n_int_constraints = 0, n_field_constraints = 0;
@@ -171,11 +172,17 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
                     }
                     if (lc[0] * lc[1] == lc[2]) table |= 1u << asg;
                 }
-                for (int q = 0; q < TABLE_VARS; q++) b.tcons.push_back(q < nv ? vars[q] : one_brow);
-                b.tcons.push_back(table);
-                b.tcons.push_back(c);
-                b.tcons.push_back(0);
-                b.n_table_constraints++;
+                if (table == 0xffffffffu) {
+                    // true for EVERY assignment of its 0/1 wires (x * (x - 1) = 0 on a wire stored as a bit): a bit row cannot
+                    // hold anything that violates it -- nothing to evaluate
+                    b.n_tautologies++;
+                } else {
+                    for (int q = 0; q < TABLE_VARS; q++) b.tcons.push_back(q < nv ? vars[q] : one_brow);
+                    b.tcons.push_back(table);
+                    b.tcons.push_back(c);
+                    b.tcons.push_back(0);
+                    b.n_table_constraints++;
+                }
                 mode = 3;
             }
         }
