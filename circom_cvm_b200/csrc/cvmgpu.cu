@@ -1265,6 +1265,19 @@ static int launch_check(cvmgpu_r1cs *r, const cvmgpu_r1cs::Dev &rd, const BoundD
     // enough CTAs to fill 148 SMs several times over even for small batches (config 5: B = 1K, 1.5M constraints)
     uint64_t want = 148ull * 16;
     uint64_t chunks = std::max<uint64_t>(1, (want + gx - 1) / gx);
+    {
+        // ... in a whole number of waves: 512 x 5 CTAs at 5 resident per SM are 3.46 waves, i.e. four rounds of which the last
+        // is half empty; 512 x 13 are 8.99
+        const uint64_t slots = 148ull * 5;
+        double best_eff = 0;
+        uint64_t best_c = chunks;
+        for (uint64_t c = chunks; c <= 4 * chunks && c * 32 <= std::max<uint64_t>(n_walk, 32); c++) {
+            const double waves = (double)(gx * c) / (double)slots;
+            const double eff = waves / std::ceil(waves);
+            if (eff > best_eff + 0.02) { best_eff = eff; best_c = c; }
+        }
+        chunks = best_c;
+    }
     uint32_t per = (uint32_t)std::max<uint64_t>(32, (n_walk + chunks - 1) / chunks);
     chunks = (n_walk + per - 1) / per;
     if (chunks > 65535) {
