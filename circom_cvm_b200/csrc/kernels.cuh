@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
         const uint4 myrec = lrec;
         if (BITS) {
             const uint32_t o = cur.x & 0xffu;
-            const uint32_t ext = (o == tape::T_LUTG || o == tape::T_IBITG) ? cur.y
+            const uint32_t ext = (o == tape::T_LUTG || o == tape::T_IBITG || o == tape::T_INBITG) ? cur.y
                                  : o == tape::T_ISUMT                     ? cur.y * 8u
                                  : o == tape::T_ISUM                      ? (cur.y + 3u) >> 2
                                  : o == tape::T_DOT                       ? (cur.y + 1u) >> 1
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             if (!BITS) raw = __ldg(tp + pc + 1);
             continue;
         }
-        case tape::T_LUTG: case tape::T_IBITG: {
+        case tape::T_LUTG: case tape::T_IBITG: case tape::T_INBITG: {
             // Warp-cooperative groups (tape.hpp group_bit_ops): cur.y independent operations on values typed 0/1, lane m doing
             // member m for all 32 witnesses of the warp at once on their packed words.  Record m = (operand slots, result
             // slot, truth table, bit row or NO_ROW).  Every lane reads its operands before any lane writes a result.
@@ -397,6 +397,38 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
                     dslot = rec.y >> 16;
                     row = rec.w;
                 }
+            } else if (op == tape::T_INBITG) {
+                // main inputs cur.w .. cur.w + n - 1 taken as bits (speculative typing): lane m reads input cur.w + m of each of the
+                // warp's 32 witnesses -- for a fixed witness the 32 lanes read 1 KB in a row, and the 32 loads of a lane are
+                // independent (one T_INPUT_BIT per input waited for a DRAM access each).  Bit i of lane m's word = witness i.
+                const uint64_t w_first = (uint64_t)blockIdx.x * NT + (tid & ~31u);
+                uint32_t badw = 0;
+                if (lane < n) {
+                    const uint32_t k = cur.w + lane;
+                    if (p.in_row_bytes) {
+                        const unsigned char *base = reinterpret_cast<const unsigned char *>(p.inputs);
+#pragma unroll 8
+                        for (uint32_t i = 0; i < 32; i++) {
+                            const uint64_t wi = min(w_first + i, p.B - 1);
+                            word |= (((uint32_t)base[wi * p.in_row_bytes + (k >> 3)] >> (k & 7u)) & 1u) << i;
+                        }
+                    } else {
+#pragma unroll 8
+                        for (uint32_t i = 0; i < 32; i++) {
+                            const uint64_t wi = min(w_first + i, p.B - 1);
+                            const uint4 *src = p.inputs + (wi * p.n_inputs + k) * 2;
+                            const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+                            const bool bad = lo.x > 1u || (lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) != 0u;
+                            word |= (lo.x & 1u) << i;
+                            badw |= (bad ? 1u : 0u) << i;
+                        }
+                    }
+                    const uint4 rec = BITS ? myrec : __ldg(tp + pc + 1 + lane);
+                    dslot = rec.x & 0xffffu;
+                    row = rec.w;
+                }
+                // witness i is flagged when any of the n inputs read for it is not a bit
+                if ((__reduce_or_sync(0xffffffffu, badw) >> lane) & 1u) status = tape::ST_SPECULATION;
             } else {
                 // bits cur.w .. cur.w + n - 1 of the integer in slot cur.z: the 32 x 32 bit matrix (lane = witness, bit = position)
                 // transposed across the warp -- lane m ends up with the word of bit cur.w + m

@@ -588,8 +588,8 @@ inline void group_bit_ops(XProg &xp) {
     std::vector<uint8_t> glen;
     order.reserve(N);
     glen.reserve(N);
-    std::vector<uint32_t> open_lut, open_bit;
-    std::vector<uint8_t> deferred(N, 0);   // 1: in open_lut, 2: in open_bit
+    std::vector<uint32_t> open_lut, open_bit, open_in;
+    std::vector<uint8_t> deferred(N, 0);   // 1: in open_lut, 2: in open_bit, 3: in open_in
     auto flush = [&](std::vector<uint32_t> &open) {
         if (open.empty()) return;
         const size_t at = order.size();
@@ -603,18 +603,25 @@ inline void group_bit_ops(XProg &xp) {
     };
     for (size_t i = 0; i < N; i++) {
         const XOp &o = ops[i];
-        bool use_lut = false, use_bit = false;
+        bool use_lut = false, use_bit = false, use_in = false;
         auto chk = [&](uint32_t r) {
             if (r == NO_REF || (r & CONST_FLAG)) return;
             if (deferred[r] == 1) use_lut = true;
             if (deferred[r] == 2) use_bit = true;
+            if (deferred[r] == 3) use_in = true;
         };
         if (o.op == T_DOT || o.op == T_ISUM)
             for (uint32_t k = 0; k < o.tn; k++) chk(xp.terms[o.t0 + k].second);
         chk(o.a); chk(o.b); chk(o.c);
         if (use_lut) flush(open_lut);
         if (use_bit) flush(open_bit);
-        if (o.op == T_LUT) {
+        if (use_in) flush(open_in);
+        if (o.op == T_INPUT_BIT) {   // runs of consecutive main inputs taken as bits (speculative typing): one coalesced group load
+            if (!open_in.empty() && ops[open_in.back()].aux + 1 != o.aux) flush(open_in);
+            open_in.push_back((uint32_t)i);
+            deferred[i] = 3;
+            if (open_in.size() == 32) flush(open_in);
+        } else if (o.op == T_LUT) {
             open_lut.push_back((uint32_t)i);
             deferred[i] = 1;
             if (open_lut.size() == 32) flush(open_lut);
@@ -633,6 +640,7 @@ inline void group_bit_ops(XProg &xp) {
     }
     flush(open_lut);
     flush(open_bit);
+    flush(open_in);
     std::vector<uint32_t> remap(N, NO_REF);
     for (size_t k = 0; k < N; k++) remap[order[k]] = (uint32_t)k;
     auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
@@ -661,7 +669,7 @@ inline uint32_t extra_records(const TapeIns &in) {
     if (in.op == T_DOT) return (in.a + 1) / 2;
     if (in.op == T_ISUM) return (in.a + 3) / 4;
     if (in.op == T_ISUMT) return in.a * 8;
-    if (in.op == T_LUTG || in.op == T_IBITG) return in.a;
+    if (in.op == T_LUTG || in.op == T_IBITG || in.op == T_INBITG) return in.a;
     return 0;
 }
 
@@ -966,7 +974,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
             // All operands must be resident when it starts; results may take the slots of operands that die here (the
             // kernel reads every operand before any lane writes).
             const uint32_t n = xp.group_len[i], last = (uint32_t)i + n - 1;
-            const bool lutg = ops[i].op == T_LUT;
+            const bool lutg = ops[i].op == T_LUT, ing = ops[i].op == T_INPUT_BIT;
             std::vector<uint32_t> grs;
             for (uint32_t m = 0; m < n; m++) {
                 const XOp &g = ops[i + m];
@@ -1003,7 +1011,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
                     recs[4 * m + 2] = g.aux & 0xffffu;
                 }
             }
-            const uint32_t src_code = lutg ? 0u : slot_code(ops[i].a);
+            const uint32_t src_code = (lutg || ing) ? 0u : slot_code(ops[i].a);
             for (uint32_t r : grs)
                 if (val_slot[r] >= 0 && next_use(r, last) == 0xffffffffu) release_value(r);
             still.clear();
@@ -1028,7 +1036,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
                 else recs[4 * m] = d;
                 recs[4 * m + 3] = row;
             }
-            out.ins.push_back(TapeIns{(uint8_t)(lutg ? T_LUTG : T_IBITG), 0, 0, n, src_code, lutg ? 0u : ops[i].aux});
+            out.ins.push_back(TapeIns{(uint8_t)(lutg ? T_LUTG : ing ? T_INBITG : T_IBITG), 0, 0, n, src_code, lutg ? 0u : ops[i].aux});
             for (uint32_t m = 0; m < n; m++) {
                 TapeIns raw;
                 memcpy(&raw, &recs[4 * m], 16);

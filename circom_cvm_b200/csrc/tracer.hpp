@@ -63,6 +63,7 @@ enum TOp : uint8_t {
     // 32 words, word l = bit slot | base << 16 of the term whose shift is base + l (slot 0xffff: none).  Produced by the
     // allocator only (tape.hpp), never an SSA operation.
     T_ISUMT,
+    T_INBITG,    // up to 32 consecutive T_INPUT_BIT (first input index in c): record m = (bit slot, -, -, bit row or NO_ROW)
     T_COUNT
 };
 

@@ -8,7 +8,7 @@ from oracle import fr_model as M
 
 (T_NOP, T_INPUT, T_ADD, T_SUB, T_MUL, T_DIV, T_IDIV, T_MOD, T_POW, T_SHL, T_SHR, T_BAND, T_BOR, T_BXOR, T_BNOT,
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
- T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE, T_INPUT_BIT, T_ISUMT) = range(47)
+ T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE, T_INPUT_BIT, T_ISUMT, T_INBITG) = range(48)
 F_ADDEND = 32        # T_DOT: field b is an addend
 ST_SPECULATION = 6
 F_CHECK = 128        # T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: compare the result with slot dst, c = constraint
@@ -135,7 +135,7 @@ def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
             pc += a * 8
             assert acc < 1 << 62 and not dst & BSLOT_DST
             res = Int(acc)
-        elif op in (T_LUTG, T_IBITG):
+        elif op in (T_LUTG, T_IBITG, T_INBITG):
             # a members, one record each; every member reads its operands before any result is written
             outs = []
             src = get_int(b, 0) if op == T_IBITG else None
@@ -149,6 +149,11 @@ def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
                         assert v in (0, 1), "T_LUTG input is not a 0/1 value"
                         idx |= v << i
                     outs.append(((rec[2] >> idx) & 1, rec[1] >> 16, rec[3]))
+                elif op == T_INBITG:
+                    v = int(inputs[c + m])          # main input c + m taken as a bit (speculative typing)
+                    if v > 1:
+                        status = ST_SPECULATION
+                    outs.append((v & 1, rec[0] & 0xFFFF, rec[3]))
                 else:
                     outs.append(((src >> (c + m)) & 1, rec[0] & 0xFFFF, rec[3]))
             for v, d, row in outs:
