@@ -17,6 +17,7 @@
 #include <vector>
 
 #include <atomic>
+#include <chrono>
 
 #include "cvm_parse.hpp"
 #include "fused.hpp"
@@ -877,10 +878,10 @@ extern "C" int cvmgpu_packed_layout(cvmgpu_program *p, int bit_input_tape, uint6
 static int upload_r1cs(cvmgpu_r1cs *r, cvmgpu_r1cs::Dev **out);
 
 // largest chunk of witnesses whose buffers fit in the free device memory
-static uint64_t pick_chunk(uint64_t B, size_t bytes_per_witness) {
+static uint64_t pick_chunk(uint64_t B, size_t bytes_per_witness, size_t already_held = 0) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
-    uint64_t cap = (uint64_t)((double)free_b * 0.85 / (double)std::max<size_t>(1, bytes_per_witness));
+    uint64_t cap = (uint64_t)((double)(free_b + already_held) * 0.85 / (double)std::max<size_t>(1, bytes_per_witness));
     cap = cap / 1024 * 1024;
     if (cap < 128) cap = 128;
     return std::min<uint64_t>(B, cap);
@@ -1002,15 +1003,12 @@ static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *i
     }
     const size_t in_row = in_row_bytes ? (size_t)in_row_bytes : (size_t)p->n_inputs * 32;
     const size_t out_row = packed ? packed_row_bytes(p) : (size_t)n_sel * 32;
-    size_t per_w = (cvmgpu_store_bytes(p, 1024) + 1023) / 1024 + in_row + out_row + 8;
-    uint64_t fit = pick_chunk(B, 2 * per_w);
-    if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
     // chunks keep the D2H of one chunk under the kernels of the next: about 1 GiB of exported rows per chunk.  With little
     // or nothing to download there is nothing to overlap, and one large launch fills the GPU best (and pays the host-side
     // cost of a chunk once).
     uint64_t chunk = 1u << 20;
     if (out_row > 256) chunk = std::min<uint64_t>(262144, std::max<uint64_t>(4096, ((1ull << 30) / out_row) / 1024 * 1024));
-    chunk = std::min<uint64_t>(fit, chunk);
+    if (const char *e = getenv("CVMGPU_CHUNK")) chunk = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));   // experiments
     if (B <= chunk) chunk = B;
     int dev = -1;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -1021,7 +1019,31 @@ static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *i
     }
     std::lock_guard<std::mutex> pipe_lock(ps->mu);
     PipeBufs *pipe = ps->pipe;
-    const int nbuf = (B > chunk) ? 2 : 1;
+    int nbuf = (B > chunk) ? 2 : 1;
+    if (const char *e = getenv("CVMGPU_NBUF")) nbuf = std::max(1, std::min(2, atoi(e)));   // experiments
+    {
+        // The free-memory query (cudaMemGetInfo) takes driver-wide locks: on a host whose other GPUs are busy allocating it was
+        // seen to block for 50-90 ms (traced: the whole of the "slow" calls of the full-row leg, none of it in the pipeline).
+        // It is only needed when the buffers have to grow.
+        const uint64_t cs = (chunk + 31) / 32 * 32;
+        bool have = true;
+        for (int k = 0; k < nbuf; k++) {
+            const PipeBufs &pb = pipe[k];
+            have = have && pb.stream && pb.store.n >= cvmgpu_store_bytes(p, cs) && pb.inputs.n >= std::max<size_t>(32, in_row * chunk) &&
+                   pb.status.n >= 4 * chunk && pb.bad.n >= 4 * chunk && (!out_row || pb.wtns.n >= out_row * chunk);
+        }
+        if (!have) {
+            const size_t per_w = (cvmgpu_store_bytes(p, 1024) + 1023) / 1024 + in_row + out_row + 8;
+            size_t held = 0;   // what these buffers already hold counts as available
+            for (int k = 0; k < 2; k++) held += pipe[k].store.n + pipe[k].inputs.n + pipe[k].wtns.n;
+            uint64_t fit = pick_chunk(B, 2 * per_w, held);
+            if (fit == 0) return fail(CVMGPU_ERR_CUDA, "cudaMemGetInfo failed");
+            if (fit < chunk) {
+                chunk = fit;
+                nbuf = (B > chunk) ? 2 : 1;
+            }
+        }
+    }
     const uint64_t cstride = (chunk + 31) / 32 * 32;
     for (int k = 0; k < nbuf; k++) {
         PipeBufs &pb = pipe[k];
@@ -1035,14 +1057,28 @@ static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *i
     }
     int rc = CVMGPU_OK;
     uint64_t idx = 0;
+    // CVMGPU_TRACE=1: per-chunk device timestamps (events) of a call, printed when it took more than 1.5 x its best so far
+    static const bool trace = getenv("CVMGPU_TRACE") && atoi(getenv("CVMGPU_TRACE"));
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tev.push_back(ev);
+    };
+    const auto host_t0 = std::chrono::steady_clock::now();
     for (uint64_t b0 = 0; b0 < B && rc == CVMGPU_OK; b0 += chunk, idx++) {
         PipeBufs &pb = pipe[idx % nbuf];
         cudaStream_t s = pb.stream;
         uint64_t n = std::min<uint64_t>(chunk, B - b0);
         cudaError_t e = cudaSuccess;
+        mark(s);
         // the stream's previous chunk must have left its buffers (stream order guarantees it)
         if (in_row) e = cudaMemcpyAsync(pb.inputs.p, inputs + b0 * in_row, n * in_row, cudaMemcpyHostToDevice, s);
+        mark(s);
         if (e == cudaSuccess) rc = run_tape(p, pb.inputs.p, n, cstride, pb.store.p, pb.status.p, fused ? pb.bad.p : nullptr, s, in_row_bytes);
+        mark(s);
         if (e == cudaSuccess && rc == CVMGPU_OK && r) {
             if (!fused) rc = cvmgpu_r1cs_check_store_dev(r, p, pb.store.p, n, cstride, pb.bad.p, s);
             if (rc == CVMGPU_OK) e = cudaMemcpyAsync(first_bad + b0, pb.bad.p, n * 4, cudaMemcpyDeviceToHost, s);
@@ -1050,15 +1086,34 @@ static int batch_select_impl(cvmgpu_program *p, cvmgpu_r1cs *r, const uint8_t *i
         if (e == cudaSuccess && rc == CVMGPU_OK && out_row) {
             rc = packed ? cvmgpu_witness_export_packed_dev(p, pb.store.p, n, cstride, pb.wtns.p, s)
                         : cvmgpu_witness_export_range_dev(p, pb.store.p, n, cstride, wire0, n_sel, pb.wtns.p, s);
+            mark(s);
             if (rc == CVMGPU_OK) e = cudaMemcpyAsync(wtns_out + b0 * out_row, pb.wtns.p, n * out_row, cudaMemcpyDeviceToHost, s);
+            mark(s);
         }
         if (e == cudaSuccess && rc == CVMGPU_OK && status) e = cudaMemcpyAsync(status + b0, pb.status.p, n * 4, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) rc = fail(CVMGPU_ERR_CUDA, std::string("host-buffer pipeline: ") + cudaGetErrorString(e));
     }
+    const auto host_t1 = std::chrono::steady_clock::now();
     // also on the error path: copies into the caller's buffers must not be in flight when this returns
     for (int k = 0; k < nbuf; k++) {
         cudaError_t e = cudaStreamSynchronize(pipe[k].stream);
         if (e != cudaSuccess && rc == CVMGPU_OK) rc = fail(CVMGPU_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    }
+    if (trace && !tev.empty()) {
+        static double best = 1e30;
+        const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        best = std::min(best, total);
+        if (total > 1.5 * best) {
+            fprintf(stderr, "[cvmgpu trace] call %.1f ms (best %.1f), enqueue %.1f ms; per chunk [start, h2d, tape, export, d2h] ms since the first event:",
+                    total, best, std::chrono::duration<double, std::milli>(host_t1 - host_t0).count());
+            for (size_t k = 0; k < tev.size(); k++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, tev[0], tev[k]);
+                fprintf(stderr, "%s%.1f", k % 5 == 0 ? " |" : " ", ms);
+            }
+            fprintf(stderr, "\n");
+        }
+        for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
     }
     return rc;
 }
