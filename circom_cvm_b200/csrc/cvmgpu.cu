@@ -653,6 +653,11 @@ static int upload_program(cvmgpu_program *p, cvmgpu_program::Dev **out) {
         CUDA_TRY(cudaMemcpy(d.d_iconsts.p, p->tape.iconsts.data(), p->tape.iconsts.size() * 8, cudaMemcpyHostToDevice));
     if (!p->tape.wire_loc.empty())
         CUDA_TRY(cudaMemcpy(d.d_wire_loc.p, p->tape.wire_loc.data(), p->tape.wire_loc.size() * 4, cudaMemcpyHostToDevice));
+    {
+        uint32_t ext[256];
+        kern::fill_ext_table(ext);
+        CUDA_TRY(cudaMemcpyToSymbol(kern::c_ext_table, ext, sizeof(ext)));
+    }
     // the tables are read by kernels on non-blocking streams, which do not order themselves after the copies above
     // (pageable-memory copies may return once the data is staged)
     CUDA_TRY(cudaDeviceSynchronize());

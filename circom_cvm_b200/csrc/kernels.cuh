@@ -223,6 +223,16 @@ __device__ __forceinline__ Fr tape_arith(uint32_t op, uint32_t flags, const uint
 // (programs without 0/1-typed values are bound by the multiplier pipe and want 20 resident warps per SM: 96 registers;
 // the bit-file instantiation gets 128: the register file is split between the four schedulers, so 129..168 registers mean 3
 // warps per scheduler = 12 per SM, and a 64 K batch -- 13.8 one-warp CTAs per SM -- no longer fits one wave)
+// records that follow an instruction (tape.hpp extra_records) as (a * M + A) >> S; entry = M | A << 8 | S << 16
+__constant__ uint32_t c_ext_table[256];
+inline void fill_ext_table(uint32_t *t) {
+    for (int i = 0; i < 256; i++) t[i] = 0;
+    t[tape::T_DOT] = 1u | (1u << 8) | (1u << 16);
+    t[tape::T_ISUM] = 1u | (3u << 8) | (2u << 16);
+    t[tape::T_ISUMT] = 8u;
+    t[tape::T_LUTG] = t[tape::T_IBITG] = t[tape::T_INBITG] = 1u;
+}
+
 template <int NT, bool BITS>
 __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(TapeParams p) {
     extern __shared__ uint4 slots[];
@@ -255,12 +265,9 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
         // executes.  myrec = the word after this instruction that belongs to this lane.
         const uint4 myrec = lrec;
         if (BITS) {
-            const uint32_t o = cur.x & 0xffu;
-            const uint32_t ext = (o == tape::T_LUTG || o == tape::T_IBITG || o == tape::T_INBITG) ? cur.y
-                                 : o == tape::T_ISUMT                     ? cur.y * 8u
-                                 : o == tape::T_ISUM                      ? (cur.y + 3u) >> 2
-                                 : o == tape::T_DOT                       ? (cur.y + 1u) >> 1
-                                                                          : 0u;
+            // records behind this instruction: (a * M + A) >> S with per-opcode constants (one packed word from constant memory)
+            const uint32_t ek = c_ext_table[cur.x & 0xffu];
+            const uint32_t ext = (cur.y * (ek & 0xffu) + ((ek >> 8) & 0xffu)) >> (ek >> 16);
             raw = __ldg(tp + pc + 1 + ext);
             lrec = __ldg(tp + pc + 2 + ext + lane);
         } else
