@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             const uint32_t n = cur.y;
             unsigned long long v = 0;
             if (flags & tape::F_ADDEND) v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            if (flags & tape::F_ADDEND2) v += tape_int<NT, BITS>(slots, bw, p.iconsts, cur.w, flags & 4u, tid);
             // record 0 is what the loop fetched as "the next instruction"; each iteration fetches the record after the one it
             // works on, and the last one thereby fetches the instruction that follows the records
             uint4 rec = BITS ? __ldg(tp + pc + 1) : raw;
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(NT, BITS ? 512 / NT : 640 / NT) tape_kernel(Ta
             const uint32_t nl = cur.y;
             unsigned long long v = 0;
             if (flags & tape::F_ADDEND) v = tape_int<NT, BITS>(slots, bw, p.iconsts, cur.z, flags & 2u, tid);
+            if (flags & tape::F_ADDEND2) v += tape_int<NT, BITS>(slots, bw, p.iconsts, cur.w, flags & 4u, tid);
             const uint32_t *words = reinterpret_cast<const uint32_t *>(tp + pc + 1);
             uint32_t e = __ldg(words + lane);
             for (uint32_t L = 0; L < nl; L++) {

@@ -32,6 +32,7 @@ static const uint8_t F_STORE = 8;
 static const uint8_t F_CZERO = 16;
 static const uint8_t F_TRIVIAL = 16;  // T_MUL: check at run time whether the factors are 0 / 1 (bit-heavy programs)
 static const uint8_t F_ADDEND = 32;
+static const uint8_t F_ADDEND2 = 16;  // T_ISUM / T_ISUMT: a second addend in field c (constant: flag bit 2)
 static const uint8_t F_CHECK = 128;  // T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: dst = slot to compare the result with, c = constraint
 static const uint8_t F_RING = 64;    // T_LD: the value was requested LD_RING reloads ago and sits in ring entry b
 static const uint32_t LD_RING = 4;   // reloads in flight per witness (32 B of shared memory each)
@@ -549,6 +550,42 @@ inline void fuse_isums(XProg &xp, const Tracer &tr) {
         }
         ops[i] = x;
     }
+    // Sums of sums: a + b of the 32-bit words of a hash round arrives as T_IADD of two such sums (or of a sum and another
+    // integer).  The terms do not care which instruction adds them: a single-use T_ISUM operand is merged into the addition,
+    // which becomes one T_ISUM over all the terms (the other operand, if it is not a sum, is its addend).  Cascades: the merged
+    // sum is itself a single-use T_ISUM for the next addition of the chain.
+    for (size_t i = 0; i < N; i++) {
+        if (absorbed[i] || ops[i].op != T_IADD) continue;
+        const XOp o = ops[i];
+        auto is_sum = [&](uint32_t r) {
+            return r != NO_REF && !(r & CONST_FLAG) && !absorbed[r] && ops[r].op == T_ISUM && uses[r] == 1;
+        };
+        const bool sa = is_sum(o.a), sb = is_sum(o.b) && o.b != o.a;
+        if (!sa && !sb) continue;
+        uint32_t addend = NO_REF, addend2 = NO_REF;   // a T_ISUM carries up to two (c and a)
+        std::vector<std::pair<uint32_t, uint32_t>> terms;
+        bool ok = true;
+        auto other = [&](uint32_t r) {
+            if (addend == NO_REF) addend = r;
+            else if (addend2 == NO_REF) addend2 = r;
+            else ok = false;
+        };
+        auto take = [&](uint32_t r) {
+            for (uint32_t k = 0; k < ops[r].tn; k++) terms.push_back(xp.terms[ops[r].t0 + k]);
+            for (uint32_t c : {ops[r].c, ops[r].a})
+                if (c != NO_REF && !((c & CONST_FLAG) && fr::is_zero(tr.consts[c & ~CONST_FLAG]))) other(c);   // (a chain usually starts from 0)
+        };
+        if (sa) take(o.a); else other(o.a);
+        if (sb) take(o.b); else other(o.b);
+        if (!ok || terms.size() > ISUM_MAX || terms.size() < 2) continue;
+        XOp x{T_ISUM, addend2, NO_REF, addend, 0};
+        x.t0 = (uint32_t)xp.terms.size();
+        x.tn = (uint32_t)terms.size();
+        for (const auto &t : terms) xp.terms.push_back(t);
+        if (sa) absorbed[o.a] = 1;
+        if (sb) absorbed[o.b] = 1;
+        ops[i] = x;
+    }
     // compact
     std::vector<uint32_t> remap(N, NO_REF);
     auto mapref = [&](uint32_t r) -> uint32_t { return (r == NO_REF || (r & CONST_FLAG)) ? r : remap[r]; };
@@ -847,7 +884,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
         if (o.op == T_DOT || o.op == T_ISUM) {
             for (uint32_t k = 0; k < o.tn; k++) rs.push_back(xp.terms[o.t0 + k].second);
             rs.push_back(o.c);
-            if (o.chk) rs.push_back(o.a);   // a checked T_DOT: the value its result is compared with
+            if (o.chk || o.op == T_ISUM) rs.push_back(o.a);   // a checked T_DOT: the value its result is compared with; T_ISUM: a second addend
         } else {
             rs.push_back(o.a);
             rs.push_back(o.b);
@@ -1179,6 +1216,23 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
                     addend = it->second;
                 }
             }
+            // a second addend (sums of sums merged by fuse_isums): field c, flag F_ADDEND2, constant flag bit 2
+            uint32_t addend2 = 0;
+            if (o.a != NO_REF) {
+                flags |= F_ADDEND2;
+                addend2 = enc[o.tn + 1];
+                if (isc[o.tn + 1]) {
+                    flags |= 4;
+                    const fr::Fr &cv = consts[enc[o.tn + 1]];
+                    const uint64_t v = ((uint64_t)cv.v[1] << 32) | cv.v[0];
+                    auto it = iconst_index.find(v);
+                    if (it == iconst_index.end()) {
+                        it = iconst_index.emplace(v, (uint32_t)out.iconsts.size()).first;
+                        out.iconsts.push_back(v);
+                    }
+                    addend2 = it->second;
+                }
+            }
             // Transposed form (T_ISUMT).  The terms are (bit slot, shift) pairs and the sum does not care about their order: they
             // are dealt into LAYERS in which every shift occurs at most once and all shifts lie within a 32-wide window.  A
             // layer is a 32 x 32 bit matrix -- lane l holds the word of the term whose shift is base + l (bit w = witness w) --
@@ -1215,7 +1269,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
                 }
                 // a layer costs about as much as five terms of the serial form
                 if (layers.size() * 5 < o.tn && layers.size() < 256) {
-                    out.ins.push_back(TapeIns{T_ISUMT, flags, dcode, (uint32_t)layers.size(), addend, 0});
+                    out.ins.push_back(TapeIns{T_ISUMT, flags, dcode, (uint32_t)layers.size(), addend, addend2});
                     for (const Layer &L : layers)
                         for (uint32_t k = 0; k < 32; k += 4) {
                             uint32_t rec[4];
@@ -1230,7 +1284,7 @@ inline Tape allocate_tape(const std::vector<fr::Fr> &consts, size_t n_ssa, const
                     goto isum_done;
                 }
             }
-            out.ins.push_back(TapeIns{T_ISUM, flags, dcode, o.tn, addend, 0});
+            out.ins.push_back(TapeIns{T_ISUM, flags, dcode, o.tn, addend, addend2});
             for (uint32_t k = 0; k < o.tn; k += 4) {
                 uint32_t rec[4] = {0, 0, 0, 0};
                 for (uint32_t j = 0; j < 4 && k + j < o.tn; j++) {

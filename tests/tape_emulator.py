@@ -10,6 +10,7 @@ from oracle import fr_model as M
  T_LT, T_LE, T_GT, T_GE, T_EQ, T_NEQ, T_LAND, T_LOR, T_EQZ, T_SEL, T_FAIL_IF, T_FAIL_NE, T_BITC, T_LUT, T_INV,
  T_CADD, T_DOT, T_LD, T_ST, T_STC, T_ICADD, T_IADD, T_ISEL, T_IBIT, T_IFAIL_NE, T_ISUM, T_LUTG, T_IBITG, T_FILL, T_RNE, T_INPUT_BIT, T_ISUMT, T_INBITG) = range(48)
 F_ADDEND = 32        # T_DOT: field b is an addend
+F_ADDEND2 = 16       # T_ISUM / T_ISUMT: a second addend in field c
 ST_SPECULATION = 6
 F_CHECK = 128        # T_ADD / T_SUB / T_MUL / T_DOT of a fused R1CS check: compare the result with slot dst, c = constraint
 F_RING = 64          # T_LD: value comes from ring entry b (requested LD_RING reloads earlier)
@@ -112,6 +113,8 @@ def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
         elif op == T_ISUM:
             # addend + sum_j (bit_j << shift_j): a terms follow, four (bit slot | shift << 16) per 16-byte record
             acc = get_int(b, flags & 2) if flags & F_ADDEND else 0
+            if flags & F_ADDEND2:
+                acc += get_int(c, flags & 4)
             for j in range(a):
                 t = int(words[pc + j // 4][j % 4])
                 v = bslots[t & 0xFFFF]
@@ -124,6 +127,8 @@ def run_tape(tape, consts_mont, layout, inputs, want_first_bad=False):
             # T_ISUM with its terms dealt into layers of distinct shifts: a layers of 32 words, word l = bit slot | base << 16 of
             # the term whose shift is base + l (slot 0xffff: none)
             acc = get_int(b, flags & 2) if flags & F_ADDEND else 0
+            if flags & F_ADDEND2:
+                acc += get_int(c, flags & 4)
             for layer in range(a):
                 for l in range(32):
                     t = int(words[pc + layer * 8 + l // 4][l % 4])
