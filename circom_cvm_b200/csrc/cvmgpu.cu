@@ -205,7 +205,7 @@ static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume
             // (work / resident warps) estimate; the kernel stops gaining from occupancy at about 24 warps per SM.
             // Field-slot candidates beyond what the program keeps live at once cannot differ (max_live_field), and the
             // bit file is first sized to hold every live 0/1 value, then tried smaller for the chosen field file.
-            static const uint32_t cand[] = {8, 12, 16, 24, 32};
+            static const uint32_t cand[] = {4, 8, 12, 16, 24, 32};   // (4: programs that are all bits keep the shared memory for the bit file)
             std::map<uint32_t, tape::XProg> prepared;   // by longest dot product: fusion and typing run once each
             auto build = [&](uint32_t c, uint32_t max_bslots) {
                 const uint32_t mt = std::min<uint32_t>(16, c - 2);
@@ -215,7 +215,11 @@ static int build_program_impl(cvm::Parser &parser, uint32_t n_slots, bool assume
             };
             double best = 0, prev_best_c = 0;
             uint32_t best_mt = 0;
+            size_t n_bool_ops = 0;
+            for (uint8_t b : tr.isbool) n_bool_ops += b;
+            const bool bit_heavy = typed && (2 * n_bool_ops > tr.ops.size() || assume_bit_inputs);
             for (uint32_t c : cand) {
+                if (c == 4 && !bit_heavy) continue;   // field programs: measured from 8 up (EdDSA verifier: 8 is best)
                 uint32_t live_field = 0, full_bslots = 0;
                 double best_c = 0;
                 for (uint32_t nb : {2048u, 1024u, 512u, 256u}) {
