@@ -105,8 +105,13 @@ struct BoundDev {
     uint32_t n_brows = 0;
     uint64_t macs = 0, bit_adds = 0, n_int_constraints = 0, n_bterms = 0, n_fterms = 0, n_tcons = 0;
     uint64_t n_active = 0;
-    DevBuf d_hdr, d_terms, d_bhdr, d_bterms, d_tcons, d_active;
-    void release() { d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); d_tcons.release(); d_active.release(); layout_id = ~0ull; }
+    DevBuf d_hdr, d_terms, d_bhdr, d_bterms, d_tcons, d_active, d_shh, d_shl, d_shm;
+    uint64_t n_shift = 0;
+    void release() {
+        d_hdr.release(); d_terms.release(); d_bhdr.release(); d_bterms.release(); d_tcons.release(); d_active.release();
+        d_shh.release(); d_shl.release(); d_shm.release();
+        layout_id = ~0ull;
+    }
 };
 
 static std::atomic<uint64_t> g_next_r1cs_uid{1};
@@ -1285,6 +1290,16 @@ static int upload_bound(const r1cs::Bound &b, BoundDev &d) {
     if (int rc = d.d_active.ensure(std::max<size_t>(16, b.active.size() * 4))) return rc;
     if (!b.active.empty()) CUDA_TRY(cudaMemcpy(d.d_active.p, b.active.data(), b.active.size() * 4, cudaMemcpyHostToDevice));
     d.n_active = b.active.size();
+    d.n_shift = b.n_shift_constraints;
+    if (b.n_shift_constraints) {
+        if (int rc = d.d_shh.ensure(b.shh.size() * 4)) return rc;
+        if (int rc = d.d_shl.ensure((b.shl.size() + 32) * 4)) return rc;   // + one layer: the kernel fetches one ahead
+        if (int rc = d.d_shm.ensure(b.shm.size() * 4)) return rc;
+        CUDA_TRY(cudaMemcpy(d.d_shh.p, b.shh.data(), b.shh.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset((char *)d.d_shl.p + b.shl.size() * 4, 0xff, 32 * 4));
+        CUDA_TRY(cudaMemcpy(d.d_shl.p, b.shl.data(), b.shl.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.d_shm.p, b.shm.data(), b.shm.size() * 4, cudaMemcpyHostToDevice));
+    }
     d.macs = b.macs;
     d.bit_adds = b.bit_adds;
     d.n_int_constraints = b.n_int_constraints;
@@ -1396,6 +1411,24 @@ static int launch_check(cvmgpu_r1cs *r, const cvmgpu_r1cs::Dev &rd, const BoundD
         tp.B = B;
         tp.first_bad = (uint32_t *)d_first_bad;
         kern::r1cs_table_kernel<<<dim3((unsigned)tgx, (unsigned)((bd.n_tcons + tper - 1) / tper)), 128, 0, s>>>(tp);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (bd.typed && bd.n_shift) {
+        // the linear constraints over 0/1 wires with +-2^k coefficients: bit-matrix transposes, 32 witnesses per warp
+        kern::R1csShiftParams sp;
+        sp.shh = (const uint4 *)bd.d_shh.p;
+        sp.shl = (const uint32_t *)bd.d_shl.p;
+        sp.shm = (const uint32_t *)bd.d_shm.p;
+        sp.n_cons = (uint32_t)bd.n_shift;
+        const uint64_t sgx = (B + 127) / 128;
+        uint64_t schunks = std::max<uint64_t>(1, std::min<uint64_t>(bd.n_shift, (148ull * 16 + sgx - 1) / sgx));
+        sp.per_chunk = (uint32_t)((bd.n_shift + schunks - 1) / schunks);
+        schunks = (bd.n_shift + sp.per_chunk - 1) / sp.per_chunk;
+        sp.bits = bits;
+        sp.n_brows = bd.n_brows;
+        sp.B = B;
+        sp.first_bad = (uint32_t *)d_first_bad;
+        kern::r1cs_shift_kernel<<<dim3((unsigned)sgx, (unsigned)std::min<uint64_t>(65535, schunks)), 128, 0, s>>>(sp);
         CUDA_TRY(cudaGetLastError());
     }
     return CVMGPU_OK;

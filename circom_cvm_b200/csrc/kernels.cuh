@@ -733,6 +733,49 @@ __global__ void __launch_bounds__(256) export_packed_kernel(PackedView pv, uint6
     if (w < B) *reinterpret_cast<uint32_t *>(out + w * pv.row_bytes + (uint64_t)pv.n_f * 32 + (uint64_t)t * 4) = mine;
 }
 
+// ---- R1CS: linear constraints over 0/1 wires with coefficients +-2^k (r1cs.hpp Bound::shl).  Warp = 32 witnesses; per layer
+// lane l fetches the packed word of the wire whose shift is base + l, the 32 x 32 bit-matrix transpose (five shuffle steps)
+// hands every lane the partial sum of its own witness; the constraint holds iff the signed total is 0 (|total| < 2^62).
+struct R1csShiftParams {
+    const uint4 *shh;        // per constraint: first layer, number of layers, constraint index, 0
+    const uint32_t *shl;     // 32 words per layer: bit row or 0xffffffff
+    const uint32_t *shm;     // per layer: base | negative << 8
+    uint32_t n_cons, per_chunk;
+    const uint32_t *bits;
+    uint32_t n_brows;
+    uint64_t B;
+    uint32_t *first_bad;
+};
+__global__ void __launch_bounds__(128) r1cs_shift_kernel(R1csShiftParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t wg = (uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wg * 32 >= p.B) return;
+    const uint32_t *brow = p.bits + wg * p.n_brows;
+    const uint32_t c0 = blockIdx.y * p.per_chunk, c1 = min(p.n_cons, c0 + p.per_chunk);
+    uint32_t bad = 0xffffffffu;
+    for (uint32_t c = c0; c < c1; c++) {
+        const uint4 h = __ldg(p.shh + c);
+        long long acc = 0;
+        uint32_t row = __ldg(p.shl + (uint64_t)h.x * 32 + lane);
+        for (uint32_t L = 0; L < h.y; L++) {
+            const uint32_t meta = __ldg(p.shm + h.x + L);
+            const uint32_t nxt = __ldg(p.shl + (uint64_t)(h.x + L + 1) * 32 + lane);   // (the array is padded by one layer)
+            uint32_t x = row == 0xffffffffu ? 0u : __ldg(brow + row);
+#pragma unroll
+            for (uint32_t k = 16, m = 0x0000ffffu; k >= 1; k >>= 1, m ^= m << k) {
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+                x = (lane & k) ? ((y >> k) & m) | (x & ~m) : (x & m) | ((y & m) << k);
+            }
+            const long long term = (long long)((unsigned long long)x << (meta & 0xffu));
+            acc += (meta >> 8) & 1u ? -term : term;
+            row = nxt;
+        }
+        if (acc != 0) bad = min(bad, h.z);
+    }
+    const uint64_t w = wg * 32 + lane;
+    if (bad != 0xffffffffu && w < p.B) atomicMin(p.first_bad + w, bad);
+}
+
 // canonical AoS -> Montgomery SoA (used by the stand-alone R1CS check on externally produced witnesses)
 __global__ void __launch_bounds__(256) import_kernel(const uint4 *in, uint64_t B, uint32_t n_wires, uint4 *store,
                                                      uint64_t bstride) {

@@ -72,6 +72,13 @@ struct Bound {
     std::vector<uint32_t> tcons;
     uint64_t n_table_constraints = 0;
     uint64_t n_tautologies = 0;      // constraints over 0/1 wires that hold for every assignment (not evaluated)
+    // mode 3 as well: LINEAR constraints over 0/1 wires whose coefficients are +-2^k (the sums of a hash round: sum_k 2^k
+    // (a_k + b_k ...) = sum_k 2^k out_k).  Their terms are dealt into layers of distinct shifts within a 32-wide window; a
+    // layer is a 32 x 32 bit matrix (lane = shift, bit = witness) whose transpose gives every lane the partial sum of its
+    // own witness (r1cs_shift_kernel).  shl: 32 words per layer (bit row, 0xffffffff = none); shm: per layer base | negative
+    // << 8; shh: per constraint {first layer, number of layers, constraint index, 0}.
+    std::vector<uint32_t> shl, shm, shh;
+    uint64_t n_shift_constraints = 0;
     // the constraints the per-witness kernel has to walk (every mode but 3), in order
     std::vector<uint32_t> active;
     uint64_t n_int_constraints = 0, n_field_constraints = 0;
@@ -184,6 +191,58 @@ inline Bound bind(const File &f, const uint32_t *wire_loc, uint32_t one_brow = 0
                     b.n_table_constraints++;
                 }
                 mode = 3;
+            }
+        }
+        if (intok && mode != 3 && wire_loc != nullptr) {
+            // linear, every coefficient +-2^k: a shift-sum constraint
+            const bool a_none = sb[0] == se[0], b_none = !same_b && sb[1] == se[1];
+            bool ok = a_none || b_none;
+            struct T { uint32_t sh, row; bool neg; };
+            std::vector<T> ts;
+            for (uint32_t t = sb[2]; t < se[2] && ok; t++) {
+                const Term &tm = f.terms[t];
+                const uint32_t wire = fold(tm.wire & 0x0fffffffu);
+                if (wire == 0xffffffffu) continue;
+                const int64_t v = f.cint[tm.coef];
+                const uint64_t m = (uint64_t)(v < 0 ? -v : v);
+                if (m == 0 || (m & (m - 1))) { ok = false; break; }
+                uint32_t sh = 0;
+                while (!((m >> sh) & 1)) sh++;
+                ts.push_back(T{sh, wire == 0 ? one_brow : (loc_of(wire) & ~LOC_BIT), v < 0});
+            }
+            if (ok && !ts.empty()) {
+                std::stable_sort(ts.begin(), ts.end(), [](const T &x, const T &y) { return x.neg != y.neg ? x.neg < y.neg : x.sh < y.sh; });
+                struct L { uint32_t base; bool neg; uint32_t row[32]; };
+                std::vector<L> layers;
+                for (const T &t : ts) {
+                    bool placed = false;
+                    for (L &l : layers)
+                        if (l.neg == t.neg && t.sh >= l.base && t.sh - l.base < 32 && l.row[t.sh - l.base] == 0xffffffffu) {
+                            l.row[t.sh - l.base] = t.row;
+                            placed = true;
+                            break;
+                        }
+                    if (!placed) {
+                        L l;
+                        l.base = t.sh;
+                        l.neg = t.neg;
+                        for (uint32_t &x : l.row) x = 0xffffffffu;
+                        l.row[0] = t.row;
+                        layers.push_back(l);
+                    }
+                }
+                if (layers.size() * 6 < ts.size() && layers.size() < 65536) {   // a layer costs about as much as six terms
+                    b.shh.push_back((uint32_t)b.shm.size());
+                    b.shh.push_back((uint32_t)layers.size());
+                    b.shh.push_back(c);
+                    b.shh.push_back(0);
+                    for (const L &l : layers) {
+                        b.shm.push_back(l.base | (l.neg ? 1u << 8 : 0u));
+                        for (uint32_t x : l.row) b.shl.push_back(x);
+                    }
+                    b.n_shift_constraints++;
+                    mode = 3;
+                }
             }
         }
         if (intok) b.n_int_constraints++; else b.n_field_constraints++;
