@@ -202,3 +202,46 @@ def test_packed_bit_inputs_and_packed_witness_rows(cvmlib, tmp_path):
     assert np.array_equal(pout.reshape(40, pos.n_wires, 32), pw) and not pst2.any()
     with pytest.raises(E.CvmGpuError):
         pos.calculate_bits_into(np.zeros((4, 1), dtype=np.uint8), 0, 1, np.zeros((4, 1, 32), dtype=np.uint8), np.zeros(4, dtype=np.uint32))
+
+
+@pytest.mark.gpu
+def test_typed_check_on_corrupted_bit_rows_agrees_with_the_plain_check(cvmlib, tmp_path):
+    """The three check kernels of a bit-heavy layout (truth tables, shift-sums as bit-matrix transposes, per-witness integers)
+    against the plain check of the exported rows, on a store whose bit rows were corrupted at random: the first violated
+    constraint of every witness must be the same."""
+    import numpy as np
+    import torch
+    from circom_cvm_b200 import engine as E
+    from tools.circuitgen.build import write_artifact
+    art = circuit("sha256_64")
+    paths = write_artifact(art, str(tmp_path))
+    wc, r = E.WitnessCalculator(cvm_text=art.cvm), E.R1cs(paths["r1cs"])
+    rng = random.Random(29)
+    B = 320
+    rows = [[rng.randrange(2) for _ in range(art.n_inputs)] for _ in range(B)]
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_in = torch.from_numpy(E.ints_to_le(rows, art.n_inputs)).to(dev)
+    for prog in (wc.speculative(), wc):
+        info = prog.info
+        store = torch.zeros(prog.store_bytes(B), dtype=torch.uint8, device=dev)
+        st = torch.zeros(B, dtype=torch.int32, device=dev)
+        prog.run_dev(d_in, B, B, store, st, stream)
+        torch.cuda.synchronize()
+        assert not st.any()
+        # the bit region follows the field rows: n_brows words per group of 32 witnesses
+        field_bytes = int(info.n_frows) * 32 * B
+        n_words = (B // 32) * int(info.n_brows)
+        words = store[field_bytes:field_bytes + 4 * n_words].view(torch.int32)
+        assert words.numel() == n_words
+        idx = torch.tensor([rng.randrange(n_words) for _ in range(400)], device=dev)
+        words[idx] ^= torch.tensor([1 << rng.randrange(31) for _ in range(400)], dtype=torch.int32, device=dev)
+        bad = torch.empty(B, dtype=torch.int32, device=dev)
+        r.check_store_dev(prog, store, B, B, bad, stream)
+        wt = torch.empty((B, prog.n_wires, 32), dtype=torch.uint8, device=dev)
+        prog.export_dev(store, B, B, wt, stream)
+        torch.cuda.synchronize()
+        plain = r.check(wt.cpu().numpy())
+        got = bad.cpu().numpy().astype(np.uint32)
+        assert np.array_equal(got, plain)
+        assert (got != E.NO_BAD).sum() > 50
