@@ -263,7 +263,7 @@ def run_reference_arm(args, art):
                                         "has no R1CS checker (SURVEY F4)"},
             "cpu_baseline": res,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def parse_args():
@@ -709,8 +709,29 @@ def bench_workload(args, name, dist_ctx, peak_ctx, batch=0, chunk=0, e2e_batch=0
     return line
 
 
+_RESULT_FD = None
+
+
+def protect_stdout():
+    """stdout carries exactly one JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr, so banners that
+    libraries print from C (NCCL's version line under torchrun) cannot land in front of the result."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    fd = 1 if _RESULT_FD is None else _RESULT_FD
+    while data:
+        data = data[os.write(fd, data):]
+
+
 def main():
     args = parse_args()
+    protect_stdout()
     select_workload(args.workload)
     if args.impl == "reference":
         tmpdir = tempfile.mkdtemp(prefix="cvmbench_")
@@ -761,7 +782,7 @@ def main():
             line["secondary"] = {k: sec[k] for k in keep}
             line["gpu_launches"] += sec["gpu_launches"]
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
